@@ -243,18 +243,29 @@ __device__ __forceinline__ float gelu_erf_exact(float x) {
 }
 // Cheap erf for the bf16 epilogue (Abramowitz-Stegun 7.1.26, |err| <= 1.5e-7 — far below bf16
 // resolution): ~14 issue slots instead of erff's branchy ~30.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
   p *= t;
-  const float e = exp2f(-z * z * 1.4426950408889634f);
+  const float e = ex2_approx(-z * z * 1.4426950408889634f);
   const float erf_abs = fmaf(-p, e, 1.0f);
   const float erf_v = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_v);
+  const float hx = 0.5f * x;
+  return fmaf(hx, erf_v, hx);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

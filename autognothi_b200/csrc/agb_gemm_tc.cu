@@ -153,73 +153,97 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ------------------------------ epilogue ------------------------------
+    // Two phases per 32-column chunk so that every global access is coalesced:
+    //  (1) thread = TMEM lane = output row: tcgen05.ld 32 fp32 columns, park them in a per-warp
+    //      4 KB staging tile (16-byte pieces XOR-swizzled by row -> conflict-free both ways);
+    //  (2) 8 lanes per row x 4 rows per pass: read 4 columns back, apply alpha/bias/GELU/residual
+    //      and store 128 B (fp32) or 64 B (bf16) contiguous per row.
     const int q = warp & 3;                 // TMEM lane quarter this warp may touch
     const int h = (warp - 2) >> 2;          // column half
     constexpr int COLS_PER_WARP = BN / 2;
+    uint8_t* stage_tile = smem + STAGES * STAGE_BYTES + 256 + (warp - 2) * 4096;
+    const uint32_t stage_u32 = smem_u32(stage_tile);
+    const int piece = lane & 7, rsub = lane >> 3;
     uint32_t acc = 0, acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m0 = (t / tiles_n) * GEMM_BM;
       const int n0 = (t % tiles_n) * BN;
       mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      long long res_row = row;
-      if (p.res_group > 0) res_row = (long long)(row / p.res_group) * p.res_rows + (row % p.res_rows);
 #pragma unroll 1
       for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
         const int col0 = h * COLS_PER_WARP + c * 32;
         uint32_t r[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col0, r);
+        const int n = n0 + col0 + piece * 4;
+        const bool n_ok = n < p.N;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr && n_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
         tmem_wait_ld();
-        const int n = n0 + col0;
-        if (row_ok && n < p.N) {
-          float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t addr = stage_u32 + lane * 128 + ((j ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[4 * j]),
+                       "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                       : "memory");
+        }
+        __syncwarp();
+        if (n_ok) {
+          // residual prefetch for the 8 passes (coalesced, issued back to back)
+          uint2 rb[8];
+          float4 rf[8];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int ng = n + g * 8;
-            if (ng >= p.N) break;
-            float* vg = v + g * 8;
-            if (p.bias != nullptr) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ng));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ng + 4));
-              vg[0] += b0.x; vg[1] += b0.y; vg[2] += b0.z; vg[3] += b0.w;
-              vg[4] += b1.x; vg[5] += b1.y; vg[6] += b1.z; vg[7] += b1.w;
+          for (int ps = 0; ps < 8; ++ps) {
+            const int row = m0 + q * 32 + ps * 4 + rsub;
+            rb[ps] = make_uint2(0u, 0u);
+            rf[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < p.M && (p.res_bf16 != nullptr || p.res_f32 != nullptr)) {
+              long long res_row = row;
+              if (p.res_group > 0)
+                res_row = (long long)(row / p.res_group) * p.res_rows + (row % p.res_rows);
+              if (p.res_bf16 != nullptr)
+                rb[ps] = __ldg(reinterpret_cast<const uint2*>(p.res_bf16 + res_row * p.ldr + n));
+              else
+                rf[ps] = __ldg(reinterpret_cast<const float4*>(p.res_f32 + res_row * p.ldr + n));
             }
-            if (p.act == 1) {
+          }
 #pragma unroll
-              for (int j = 0; j < 8; ++j) vg[j] = gelu_erf_fast(vg[j]);
+          for (int ps = 0; ps < 8; ++ps) {
+            const int row_l = ps * 4 + rsub;
+            const int row = m0 + q * 32 + row_l;
+            float4 v;
+            const uint32_t addr = stage_u32 + row_l * 128 + ((piece ^ (row_l & 7)) << 4);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                         : "r"(addr)
+                         : "memory");
+            v.x = fmaf(v.x, p.alpha, bias4.x);
+            v.y = fmaf(v.y, p.alpha, bias4.y);
+            v.z = fmaf(v.z, p.alpha, bias4.z);
+            v.w = fmaf(v.w, p.alpha, bias4.w);
+            if (p.act == 1) {
+              v.x = gelu_erf_fast(v.x); v.y = gelu_erf_fast(v.y);
+              v.z = gelu_erf_fast(v.z); v.w = gelu_erf_fast(v.w);
             }
             if (p.res_bf16 != nullptr) {
-              const uint4 rr = __ldg(reinterpret_cast<const uint4*>(p.res_bf16 + res_row * p.ldr + ng));
-              vg[0] += bf16_lo(rr.x); vg[1] += bf16_hi(rr.x);
-              vg[2] += bf16_lo(rr.y); vg[3] += bf16_hi(rr.y);
-              vg[4] += bf16_lo(rr.z); vg[5] += bf16_hi(rr.z);
-              vg[6] += bf16_lo(rr.w); vg[7] += bf16_hi(rr.w);
+              v.x += bf16_lo(rb[ps].x); v.y += bf16_hi(rb[ps].x);
+              v.z += bf16_lo(rb[ps].y); v.w += bf16_hi(rb[ps].y);
+            } else if (p.res_f32 != nullptr) {
+              v.x += rf[ps].x; v.y += rf[ps].y; v.z += rf[ps].z; v.w += rf[ps].w;
             }
-            if (p.res_f32 != nullptr) {
-              const float4 r0 = __ldg(reinterpret_cast<const float4*>(p.res_f32 + res_row * p.ldr + ng));
-              const float4 r1 = __ldg(reinterpret_cast<const float4*>(p.res_f32 + res_row * p.ldr + ng + 4));
-              vg[0] += r0.x; vg[1] += r0.y; vg[2] += r0.z; vg[3] += r0.w;
-              vg[4] += r1.x; vg[5] += r1.y; vg[6] += r1.z; vg[7] += r1.w;
-            }
-            if (p.out_f32) {
-              float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + ng;
-              *reinterpret_cast<float4*>(o) = make_float4(vg[0], vg[1], vg[2], vg[3]);
-              *reinterpret_cast<float4*>(o + 4) = make_float4(vg[4], vg[5], vg[6], vg[7]);
-            } else {
-              bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + ng;
-              uint4 pk;
-              pk.x = pack_bf16x2(vg[0], vg[1]);
-              pk.y = pack_bf16x2(vg[2], vg[3]);
-              pk.z = pack_bf16x2(vg[4], vg[5]);
-              pk.w = pack_bf16x2(vg[6], vg[7]);
-              *reinterpret_cast<uint4*>(o) = pk;
+            if (row < p.M) {
+              if (p.out_f32) {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + n) = v;
+              } else {
+                uint2 pk;
+                pk.x = pack_bf16x2(v.x, v.y);
+                pk.y = pack_bf16x2(v.z, v.w);
+                *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + n) = pk;
+              }
             }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -237,7 +261,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int BN, int STAGES>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
                        cudaStream_t stream) {
-  constexpr int SMEM = STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024 + 256;
+  constexpr int SMEM = STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024 + 256 + GEMM_EPI_WARPS * 4096;
   static bool configured = false;
   if (!configured) {
     AGB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>,
@@ -259,7 +283,7 @@ int gemm_bf16_tc(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b
                  int out_f32, cudaStream_t stream) {
   AGB_REQUIRE(M > 0 && N > 0 && K > 0, "empty GEMM");
   AGB_REQUIRE(A && B && out, "null operand");
-  AGB_REQUIRE((N % 8) == 0, "N must be a multiple of 8");
+  AGB_REQUIRE((N % 4) == 0, "N must be a multiple of 4");
   AGB_REQUIRE((lda % 8) == 0 && (ldb % 8) == 0, "operand pitch must be a multiple of 8 elements");
   AGB_REQUIRE((ldo % (out_f32 ? 4 : 8)) == 0, "output pitch alignment");
   AGB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&

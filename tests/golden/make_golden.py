@@ -1,0 +1,167 @@
+"""Generate the golden fixtures in tests/golden/ by running the UNMODIFIED reference.
+
+Run in the development container only (needs /root/reference):
+    python tests/golden/make_golden.py
+The reference is imported as a package from its parent directory (as reference main.py:7-9 does).
+Weights and inputs are oracle.synth tensors (a pure function of names/seeds, so nothing large is
+stored); outputs of the reference's own recipes/*.py and models/shapley.py are saved as small .npz
+files.  Each fixture records the seeds needed to rebuild its inputs.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF_PARENT = os.environ.get("AGB_REFERENCE_PARENT", "/root")
+REF_NAME = os.environ.get("AGB_REFERENCE_NAME", "reference")
+sys.path.insert(0, REF_PARENT)
+
+from oracle import configs as ocfg  # noqa: E402
+from oracle import synth  # noqa: E402
+
+ref_shapley = __import__(f"{REF_NAME}.models.shapley", fromlist=["x"])
+ref_vit = __import__(f"{REF_NAME}.models.vanilla_vit", fromlist=["x"])
+ref_bert = __import__(f"{REF_NAME}.models.vanilla_bert", fromlist=["x"])
+ref_rvit = __import__(f"{REF_NAME}.recipes.vanilla_vit", fromlist=["x"])
+ref_rbert = __import__(f"{REF_NAME}.recipes.vanilla_bert", fromlist=["x"])
+
+torch.set_grad_enabled(False)
+
+
+def to_torch_state(sd):
+    return {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}
+
+
+def sample_masks_with_uniforms(seed: int, n_rows: int, n_players: int):
+    """Run the reference sampler under `seed` and replay the same generator to capture the uniforms
+    it consumed (reference models/shapley.py:69 draws (P,n) first, then l.133 draws (P,1))."""
+    torch.manual_seed(seed)
+    masks = ref_shapley.mask_shapley_new(n_rows, n_players)
+    torch.manual_seed(seed)
+    u_players = torch.rand(n_rows // 2, n_players)
+    u_size = torch.rand((n_rows // 2, 1)).reshape(-1)
+    # prefix table exactly as the reference builds it (l.65-67, 132)
+    probs = torch.arange(1, n_players) * (n_players - torch.arange(1, n_players))
+    probs = 1 / probs
+    probs = probs / probs.sum()
+    prefix = torch.cumsum(probs, dim=0) - probs
+    return masks.numpy(), u_players.numpy(), u_size.numpy(), prefix.numpy()
+
+
+def gen_sampler():
+    out = {}
+    for n_players, rows, seed in [(196, 64, 3407), (127, 32, 11), (511, 16, 5), (16, 64, 7), (2, 8, 1)]:
+        masks, u_p, u_s, prefix = sample_masks_with_uniforms(seed, rows, n_players)
+        key = f"n{n_players}"
+        out[key + "_masks"] = masks.astype(np.int8)
+        out[key + "_u_players"] = u_p
+        out[key + "_u_size"] = u_s
+        out[key + "_prefix"] = prefix
+        out[key + "_seed"] = np.array([seed, rows], dtype=np.int64)
+    # mask_purely_uniform (reference models/shapley.py:109-115)
+    torch.manual_seed(99)
+    pu = ref_shapley.mask_purely_uniform(16, 196)
+    torch.manual_seed(99)
+    a = torch.rand((16, 196))
+    b = torch.rand((16, 1))
+    out["pu_masks"] = pu.numpy().astype(np.int8)
+    out["pu_u_players"] = a.numpy()
+    out["pu_u_row"] = b.numpy().reshape(-1)
+    np.savez_compressed(os.path.join(HERE, "sampler.npz"), **out)
+    print("sampler.npz", {k: v.shape for k, v in out.items() if k.endswith("_masks")})
+
+
+def gen_shapley_math():
+    """normalize_shapley_explanation + loss_shapley_new (+ autograd dphi) on random tensors."""
+    out = {}
+    g = torch.Generator().manual_seed(1234)
+    for tag, (B, S, n, C) in {"vit": (3, 8, 196, 10), "bert": (2, 4, 127, 2), "tiny": (1, 2, 5, 3)}.items():
+        T = n + 1
+        pred = torch.randn(B, T, C, generator=g)
+        grand = torch.rand(B, C, generator=g)
+        null = torch.rand(1, C, generator=g)
+        norm = ref_shapley.normalize_shapley_explanation(pred, grand, null)
+        phi = norm[:, 1:, :].permute(0, 2, 1).contiguous()
+        torch.manual_seed(77)
+        mask = ref_shapley.mask_shapley_new(B * S, n).reshape(B, S, n)
+        v_s = torch.rand(B * S, C, generator=g)
+        with torch.enable_grad():
+            phi_g = phi.clone().requires_grad_(True)
+            loss = ref_shapley.loss_shapley_new(B, S, n, mask, null, v_s, grand, phi_g)
+            loss.backward()
+        out.update({
+            f"{tag}_pred": pred.numpy(), f"{tag}_grand": grand.numpy(), f"{tag}_null": null.numpy(),
+            f"{tag}_norm": norm.numpy(), f"{tag}_phi": phi.numpy(), f"{tag}_mask": mask.numpy().astype(np.int8),
+            f"{tag}_v_s": v_s.numpy(), f"{tag}_loss": loss.detach().numpy(), f"{tag}_dphi": phi_g.grad.numpy(),
+        })
+    np.savez_compressed(os.path.join(HERE, "shapley_math.npz"), **out)
+    print("shapley_math.npz ok")
+
+
+MODEL_CASES = [
+    # name, rows B (inputs), coalitions per input S, seeds
+    ("vit_mini", 2, 4),
+    ("vit_mini_px64", 3, 4),
+    ("vit_tiny", 2, 4),
+    ("vit_base", 1, 2),
+    ("bert_mini", 3, 4),
+    ("bert_base_128", 1, 2),
+]
+
+
+def gen_models():
+    keys = {}
+    for name, B, S in MODEL_CASES:
+        cfg = ocfg.get_config(name)
+        vit = ocfg.is_vit(cfg)
+        n = ocfg.n_players(cfg)
+        if vit:
+            rcfg = ref_vit.VanillaViTConfig(**cfg)
+            srg, exp, rec = ref_vit.VanillaViTSurrogate(rcfg), ref_vit.VanillaViTExplainer(rcfg), ref_rvit
+        else:
+            rcfg = ref_bert.VanillaBertConfig(**cfg)
+            srg, exp, rec = ref_bert.VanillaBertSurrogate(rcfg), ref_bert.VanillaBertExplainer(rcfg), ref_rbert
+        keys[name] = {
+            "surrogate": {k: list(v.shape) for k, v in srg.state_dict().items()},
+            "explainer": {k: list(v.shape) for k, v in exp.state_dict().items()},
+        }
+        srg.load_state_dict(to_torch_state(synth.surrogate_state(cfg, seed=0)), strict=True)
+        exp.load_state_dict(to_torch_state(synth.explainer_state(cfg, seed=1)), strict=True)
+        srg.eval()
+        exp.eval()
+        xs = torch.from_numpy(synth.inputs(cfg, B, seed=0))
+        torch.manual_seed(3407)
+        masks = ref_shapley.mask_shapley_new(B * S, n)                      # (B*S, n) int64
+        xs_ext = xs.repeat_interleave(S, dim=0)                              # row b*S+s (train_explainer.py:159-163)
+        ones = torch.ones((B, n), dtype=torch.long)
+        null_x = rec._gen_null(cfg["img_px_size"], cfg["img_patch_size"], torch.device("cpu")) if vit else \
+            torch.from_numpy(__import__("oracle.transformer", fromlist=["x"]).null_input(cfg))
+        v_s, _ = rec._fw_surrogate(srg, xs_ext, masks)
+        grand, _ = rec._fw_surrogate(srg, xs, ones)
+        null, _ = rec._fw_surrogate(srg, null_x, torch.ones((1, n), dtype=torch.long))
+        phi, _ = rec._fw_explainer(exp, xs, ones, grand, null)
+        # a coalition-masked explainer call too (exercises the mask inside the explainer layers)
+        phi_masked, _ = rec._fw_explainer(exp, xs, masks.reshape(B, S, n)[:, 0, :], grand, null)
+        loss = ref_shapley.loss_shapley_new(B, S, n, masks.reshape(B, S, n), null, v_s, grand, phi)
+        np.savez_compressed(
+            os.path.join(HERE, f"model_{name}.npz"),
+            masks=masks.numpy().astype(np.int8), v_s=v_s.numpy(), grand=grand.numpy(), null=null.numpy(),
+            phi=phi.numpy(), phi_masked=phi_masked.numpy(), loss=loss.numpy(),
+            meta=np.array([B, S, n], dtype=np.int64),
+        )
+        print(f"model_{name}.npz  v_s{tuple(v_s.shape)} phi{tuple(phi.shape)} loss={float(loss):.6f}")
+    with open(os.path.join(HERE, "state_dict_keys.json"), "w") as f:
+        json.dump(keys, f, indent=0, sort_keys=True)
+
+
+if __name__ == "__main__":
+    gen_sampler()
+    gen_shapley_math()
+    gen_models()

@@ -18,8 +18,8 @@ run 300   264  136   0 0 1 1 1 1
 run 256   256  128   1 0 0 0 0 1
 run 256   256  128   0 1 0 0 0 1
 run 256   256  128   1 1 0 0 0 1
-run 333   320  200   1 1 0 1 0 1
-run 333   128  200   1 1 0 1 0 0
+run 336   320  200   1 1 0 1 0 1
+run 336   128  200   1 1 0 1 0 0
 run 25216  768  768  0 0 0 1 1 0 20
 run 25216 2304  768  0 0 0 1 0 0 20
 run 25216 3072  768  0 0 1 1 0 0 20
