@@ -10,9 +10,50 @@ int gemm_bf16_tc(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b
                  int K, float alpha, const float* bias, int act, const bf16* res_bf16,
                  const float* res_f32, int ldr, int res_group, int res_rows, void* out, int ldo,
                  int out_f32, cudaStream_t stream);
+int gemm_f32(const float* A, int lda, const float* B, int ldb, int M, int N, int K, float alpha,
+             const float* bias, int act, const float* res, int ldr, float* C, int ldc, cudaStream_t st);
+int pack_masks_i64(const int64_t* mask, int rows, int n, int prepend_cls, uint32_t* packed, int words,
+                   cudaStream_t st);
+int unpack_masks_i64(const uint32_t* packed, int rows, int n, int skip, int words, int64_t* out,
+                     cudaStream_t st);
+int shapley_masks(const float* u_players, const float* u_size, const float* prefix, int use_philox,
+                  uint64_t seed, uint64_t offset, int pairs, int n, uint32_t* packed, int words,
+                  int64_t* dense, cudaStream_t st);
+int uniform_masks(const float* u_players, const float* u_row, int use_philox, uint64_t seed,
+                  uint64_t offset, int rows, int n, uint32_t* packed, int words, int64_t* dense,
+                  cudaStream_t st);
+int layernorm(const void* x, int in_bf16, long long in_stride, int rows, int H, const float* gamma,
+              const float* beta, float eps, bf16* out_bf16, float* out_f32, long long out_stride,
+              cudaStream_t st);
+int cast_f32_to_bf16(const float* in, bf16* out, long long n, cudaStream_t st);
+int vit_im2col(const float* img, int B, int C, int px, int P, void* out, int out_bf16, cudaStream_t st);
+int vit_assemble(const float* patch_emb, const float* cls, const float* pos, int B, int S, int T, int H,
+                 float* x, cudaStream_t st);
+int bert_embed(const int64_t* ids, const float* word, const float* pos, const float* type0,
+               const float* gamma, const float* beta, float eps, int B, int S, int T, int H, int vocab,
+               float* x, cudaStream_t st);
+int cls_head(const float* x, long long row_stride, int rows, int H, int C, int mode, const float* ln_g,
+             const float* ln_b, float eps, const float* wp, const float* bp, const float* wc,
+             const float* bc, float* probs, float* logits_out, cudaStream_t st);
+int attention_simt(const void* qkv, int io_bf16, const uint32_t* mask, int words, int rows, int T, int H,
+                   int heads, int mode, void* ctx, cudaStream_t st);
+int attention_tc(const bf16* qkv, const uint32_t* mask, int words, int rows, int T, int H, int heads,
+                 int mode, bf16* ctx, cudaStream_t st);
+int explainer_head_fwd(const void* h, int h_bf16, int B, int T, int E, int C, const float* W,
+                       const float* bias, const float* grand, const float* null_v, int normalize,
+                       float* phi, float* pred_out, cudaStream_t st);
+int explainer_head_bwd(const float* dphi, const void* h, int h_bf16, int B, int T, int E, int C,
+                       const float* W, int normalize, void* dh, float* dW, float* db, cudaStream_t st);
+int normalize_shapley(const float* pred, const float* grand, const float* null_v, int B, int T, int C,
+                      float* out, cudaStream_t st);
+int shapley_loss_fwd(const uint32_t* packed, int words, const float* v0, const float* v_s, const float* phi,
+                     int B, int S, int n, int C, float* resid, float* partial, float* loss, cudaStream_t st);
+int shapley_loss_bwd(const uint32_t* packed, int words, const float* resid, const float* gout, int B, int S,
+                     int n, int C, float* dphi, cudaStream_t st);
 }  // namespace agb
 
 using agb::bf16;
+#define ST(s) static_cast<cudaStream_t>(s)
 
 extern "C" {
 
@@ -27,6 +68,97 @@ int agb_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb
                            ldb, b_mn_major, M, N, K, alpha, bias, act,
                            static_cast<const bf16*>(residual_bf16), residual_f32, ldr, res_group,
                            res_rows, out, ldo, out_is_f32, static_cast<cudaStream_t>(stream));
+}
+
+
+int agb_gemm_f32(const float* A, int lda, const float* B, int ldb, int M, int N, int K, float alpha,
+                 const float* bias, int act, const float* residual, int ldr, float* C, int ldc,
+                 void* stream) {
+  return agb::gemm_f32(A, lda, B, ldb, M, N, K, alpha, bias, act, residual, ldr, C, ldc, ST(stream));
+}
+int agb_pack_masks_i64(const int64_t* mask, int rows, int n_players, int prepend_cls,
+                       uint32_t* packed, int words, void* stream) {
+  return agb::pack_masks_i64(mask, rows, n_players, prepend_cls, packed, words, ST(stream));
+}
+int agb_unpack_masks_i64(const uint32_t* packed, int rows, int n, int skip, int words, int64_t* out,
+                         void* stream) {
+  return agb::unpack_masks_i64(packed, rows, n, skip, words, out, ST(stream));
+}
+int agb_shapley_masks(const float* u_players, const float* u_size, const float* prefix,
+                      int use_philox, uint64_t seed, uint64_t offset, int pairs, int n_players,
+                      uint32_t* packed, int words, int64_t* dense, void* stream) {
+  return agb::shapley_masks(u_players, u_size, prefix, use_philox, seed, offset, pairs, n_players, packed,
+                            words, dense, ST(stream));
+}
+int agb_uniform_masks(const float* u_players, const float* u_row, int use_philox, uint64_t seed,
+                      uint64_t offset, int rows, int n_players, uint32_t* packed, int words,
+                      int64_t* dense, void* stream) {
+  return agb::uniform_masks(u_players, u_row, use_philox, seed, offset, rows, n_players, packed, words,
+                            dense, ST(stream));
+}
+int agb_layernorm(const void* x, int x_is_bf16, long long in_stride, int rows, int H,
+                  const float* gamma, const float* beta, float eps, void* out_bf16, float* out_f32,
+                  long long out_stride, void* stream) {
+  return agb::layernorm(x, x_is_bf16, in_stride, rows, H, gamma, beta, eps, static_cast<bf16*>(out_bf16),
+                        out_f32, out_stride, ST(stream));
+}
+int agb_cast_f32_to_bf16(const float* in, void* out_bf16, long long n, void* stream) {
+  return agb::cast_f32_to_bf16(in, static_cast<bf16*>(out_bf16), n, ST(stream));
+}
+int agb_vit_im2col(const float* images, int B, int C, int px, int P, void* out, int out_is_bf16,
+                   void* stream) {
+  return agb::vit_im2col(images, B, C, px, P, out, out_is_bf16, ST(stream));
+}
+int agb_vit_assemble(const float* patch_emb, const float* cls_token, const float* pos_emb, int B,
+                     int S, int T, int H, float* x, void* stream) {
+  return agb::vit_assemble(patch_emb, cls_token, pos_emb, B, S, T, H, x, ST(stream));
+}
+int agb_bert_embed(const int64_t* ids, const float* word, const float* pos, const float* type0,
+                   const float* gamma, const float* beta, float eps, int B, int S, int T, int H,
+                   int vocab, float* x, void* stream) {
+  return agb::bert_embed(ids, word, pos, type0, gamma, beta, eps, B, S, T, H, vocab, x, ST(stream));
+}
+int agb_cls_head(const float* x, long long row_stride, int rows, int H, int C, int mode,
+                 const float* ln_gamma, const float* ln_beta, float eps, const float* w_pool,
+                 const float* b_pool, const float* w_cls, const float* b_cls, float* probs,
+                 float* logits_or_null, void* stream) {
+  return agb::cls_head(x, row_stride, rows, H, C, mode, ln_gamma, ln_beta, eps, w_pool, b_pool, w_cls,
+                       b_cls, probs, logits_or_null, ST(stream));
+}
+int agb_masked_attention_simt(const void* qkv, int io_is_bf16, const uint32_t* mask, int words,
+                              int rows, int T, int H, int heads, int mode, void* ctx, void* stream) {
+  return agb::attention_simt(qkv, io_is_bf16, mask, words, rows, T, H, heads, mode, ctx, ST(stream));
+}
+int agb_masked_attention_bf16(const void* qkv, const uint32_t* mask, int words, int rows, int T,
+                              int H, int heads, int mode, void* ctx, void* stream) {
+  return agb::attention_tc(static_cast<const bf16*>(qkv), mask, words, rows, T, H, heads, mode,
+                           static_cast<bf16*>(ctx), ST(stream));
+}
+int agb_explainer_head_fwd(const void* h, int h_is_bf16, int B, int T, int E, int C, const float* W,
+                           const float* bias, const float* grand, const float* null_v,
+                           int normalize, float* phi, float* pred_or_null, void* stream) {
+  return agb::explainer_head_fwd(h, h_is_bf16, B, T, E, C, W, bias, grand, null_v, normalize, phi,
+                                 pred_or_null, ST(stream));
+}
+int agb_explainer_head_bwd(const float* dphi, const void* h, int h_is_bf16, int B, int T, int E,
+                           int C, const float* W, int normalize, void* dh, float* dW, float* db,
+                           void* stream) {
+  return agb::explainer_head_bwd(dphi, h, h_is_bf16, B, T, E, C, W, normalize, dh, dW, db, ST(stream));
+}
+int agb_normalize_shapley(const float* pred, const float* grand, const float* null_v, int B, int T,
+                          int C, float* out, void* stream) {
+  return agb::normalize_shapley(pred, grand, null_v, B, T, C, out, ST(stream));
+}
+int agb_shapley_loss_fwd(const uint32_t* packed, int words, const float* v0, const float* v_s,
+                         const float* phi, int B, int S, int n_players, int C, float* resid,
+                         float* partial, float* loss, void* stream) {
+  return agb::shapley_loss_fwd(packed, words, v0, v_s, phi, B, S, n_players, C, resid, partial, loss,
+                               ST(stream));
+}
+int agb_shapley_loss_bwd(const uint32_t* packed, int words, const float* resid,
+                         const float* grad_out, int B, int S, int n_players, int C, float* dphi,
+                         void* stream) {
+  return agb::shapley_loss_bwd(packed, words, resid, grad_out, B, S, n_players, C, dphi, ST(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,340 @@
+// HBM-bound glue kernels of the surrogate / explainer forward: LayerNorm, ViT patchify + embedding
+// assembly, BERT embeddings, CLS classification heads.  All are vectorised row kernels (one warp per
+// token row, 16-byte lane accesses) — no data reuse, so no shared-memory tiling; the aim is one
+// read and one write of each activation at full HBM sector efficiency.
+#include "agb_common.cuh"
+
+namespace agb {
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the hidden dimension (reference nn.LayerNorm at models/vanilla_vit.py:213,369,373,
+// 94; models/vanilla_bert.py:318,548,596).  Two-pass mean/variance in fp32 (matches torch's
+// numerics to ~1 ulp), input fp32 or bf16, outputs bf16 and/or fp32.
+// ------------------------------------------------------------------------------------------------
+template <typename TIn>
+__device__ __forceinline__ float4 load4(const TIn* p);
+template <>
+__device__ __forceinline__ float4 load4<float>(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+template <>
+__device__ __forceinline__ float4 load4<bf16>(const bf16* p) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  return make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));
+}
+
+template <typename TIn>
+__global__ void layernorm_kernel(const TIn* __restrict__ x, long long in_stride, int rows, int H,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 float eps, bf16* __restrict__ out_bf16, float* __restrict__ out_f32,
+                                 long long out_stride) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const TIn* xr = x + (long long)row * in_stride;
+  float s = 0.f;
+  for (int i = lane * 4; i < H; i += 128) {
+    const float4 v = load4<TIn>(xr + i);
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mean = warp_sum(s) / (float)H;
+  float ss = 0.f;
+  for (int i = lane * 4; i < H; i += 128) {
+    const float4 v = load4<TIn>(xr + i);
+    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+    ss += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / (float)H + eps);
+  for (int i = lane * 4; i < H; i += 128) {
+    const float4 v = load4<TIn>(xr + i);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + i));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + i));
+    float4 o;
+    o.x = (v.x - mean) * rstd * g.x + b.x;
+    o.y = (v.y - mean) * rstd * g.y + b.y;
+    o.z = (v.z - mean) * rstd * g.z + b.z;
+    o.w = (v.w - mean) * rstd * g.w + b.w;
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + (long long)row * out_stride + i) = o;
+    if (out_bf16) {
+      uint2 pk;
+      pk.x = pack_bf16x2(o.x, o.y);
+      pk.y = pack_bf16x2(o.z, o.w);
+      *reinterpret_cast<uint2*>(out_bf16 + (long long)row * out_stride + i) = pk;
+    }
+  }
+}
+
+int layernorm(const void* x, int in_bf16, long long in_stride, int rows, int H, const float* gamma,
+              const float* beta, float eps, bf16* out_bf16, float* out_f32, long long out_stride,
+              cudaStream_t st) {
+  AGB_REQUIRE(rows >= 0 && H > 0 && (H % 4) == 0, "LayerNorm width must be a multiple of 4");
+  AGB_REQUIRE((in_stride % 4) == 0 && (out_stride % 4) == 0, "row strides must be multiples of 4");
+  if (rows == 0) return AGB_OK;
+  AGB_REQUIRE(x && gamma && beta && (out_bf16 || out_f32), "null pointer");
+  const int warps = 8;
+  const int blocks = (rows + warps - 1) / warps;
+  if (in_bf16)
+    layernorm_kernel<bf16><<<blocks, warps * 32, 0, st>>>(static_cast<const bf16*>(x), in_stride, rows, H, gamma,
+                                                          beta, eps, out_bf16, out_f32, out_stride);
+  else
+    layernorm_kernel<float><<<blocks, warps * 32, 0, st>>>(static_cast<const float*>(x), in_stride, rows, H,
+                                                           gamma, beta, eps, out_bf16, out_f32, out_stride);
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 -> bf16 cast (weights, once per load) and bf16 -> fp32
+// ------------------------------------------------------------------------------------------------
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(in + i);
+    uint2 pk;
+    pk.x = pack_bf16x2(v.x, v.y);
+    pk.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + i) = pk;
+  } else {
+    for (long long j = i; j < n; ++j) out[j] = __float2bfloat16(in[j]);
+  }
+}
+int cast_f32_to_bf16(const float* in, bf16* out, long long n, cudaStream_t st) {
+  if (n <= 0) return AGB_OK;
+  AGB_REQUIRE(in && out, "null pointer");
+  AGB_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0, "alignment");
+  const long long threads = (n + 3) / 4;
+  cast_f32_bf16_kernel<<<(int)((threads + 255) / 256), 256, 0, st>>>(in, out, n);
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ViT patchify (im2col of the stride-16 conv, reference models/vanilla_vit.py:279-284):
+// images (B,C,px,px) fp32 NCHW -> patches (B*gh*gw, C*P*P) in Conv2d weight order (c, py, px).
+// One thread moves 4 consecutive pixels of one patch row (16 B read, 8/16 B write).
+// ------------------------------------------------------------------------------------------------
+template <typename TOut>
+__global__ void vit_im2col_kernel(const float* __restrict__ img, int B, int C, int px, int P,
+                                  TOut* __restrict__ out) {
+  const int g = px / P;
+  const int K = C * P * P;
+  const long long total4 = (long long)B * g * g * K / 4;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total4) return;
+  const long long e = gid * 4;
+  const int k = (int)(e % K);
+  const long long prow = e / K;
+  const int b = (int)(prow / (g * g));
+  const int pidx = (int)(prow % (g * g));
+  const int gy = pidx / g, gx = pidx % g;
+  const int c = k / (P * P), py = (k / P) % P, pxx = k % P;
+  const float4 v = *reinterpret_cast<const float4*>(
+      img + (((long long)b * C + c) * px + (gy * P + py)) * px + gx * P + pxx);
+  if (sizeof(TOut) == 4) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + e) = v;
+  } else {
+    uint2 pk;
+    pk.x = pack_bf16x2(v.x, v.y);
+    pk.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(out) + e) = pk;
+  }
+}
+
+int vit_im2col(const float* img, int B, int C, int px, int P, void* out, int out_bf16, cudaStream_t st) {
+  AGB_REQUIRE(B >= 0 && C > 0 && P > 0 && px % P == 0 && P % 4 == 0, "patchify shape");
+  if (B == 0) return AGB_OK;
+  AGB_REQUIRE(img && out, "null pointer");
+  const long long total4 = (long long)B * px * px * C / 4;
+  const int blocks = (int)((total4 + 255) / 256);
+  if (out_bf16) vit_im2col_kernel<bf16><<<blocks, 256, 0, st>>>(img, B, C, px, P, static_cast<bf16*>(out));
+  else vit_im2col_kernel<float><<<blocks, 256, 0, st>>>(img, B, C, px, P, static_cast<float*>(out));
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ViT embedding assembly (reference models/vanilla_vit.py:242-253): x[b*S+s, 0] = cls + pos[0],
+// x[b*S+s, 1+p] = patch_emb[b, p] + pos[1+p]; each image is broadcast to its S coalition rows here
+// (this replaces the reference's Xs_EXT pixel replication, scripts/train_explainer.py:159-163).
+// ------------------------------------------------------------------------------------------------
+__global__ void vit_assemble_kernel(const float* __restrict__ patch_emb, const float* __restrict__ cls,
+                                    const float* __restrict__ pos, int B, int S, int T, int H,
+                                    float* __restrict__ x) {
+  const long long total4 = (long long)B * T * H / 4;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total4) return;
+  const long long e = gid * 4;
+  const int hcol = (int)(e % H);
+  const int t = (int)((e / H) % T);
+  const int b = (int)(e / ((long long)H * T));
+  float4 v = (t == 0) ? __ldg(reinterpret_cast<const float4*>(cls + hcol))
+                      : *reinterpret_cast<const float4*>(patch_emb + ((long long)b * (T - 1) + (t - 1)) * H + hcol);
+  const float4 pe = __ldg(reinterpret_cast<const float4*>(pos + (long long)t * H + hcol));
+  v.x += pe.x; v.y += pe.y; v.z += pe.z; v.w += pe.w;
+  for (int s = 0; s < S; ++s)
+    *reinterpret_cast<float4*>(x + (((long long)b * S + s) * T + t) * H + hcol) = v;
+}
+
+int vit_assemble(const float* patch_emb, const float* cls, const float* pos, int B, int S, int T, int H,
+                 float* x, cudaStream_t st) {
+  AGB_REQUIRE(B >= 0 && S > 0 && T > 1 && H % 4 == 0, "embedding shape");
+  if (B == 0) return AGB_OK;
+  AGB_REQUIRE(patch_emb && cls && pos && x, "null pointer");
+  const long long total4 = (long long)B * T * H / 4;
+  vit_assemble_kernel<<<(int)((total4 + 255) / 256), 256, 0, st>>>(patch_emb, cls, pos, B, S, T, H, x);
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BERT embeddings (reference models/vanilla_bert.py:307-325): LN(word[id] + type[tt] + pos[t]),
+// token_type_ids are all zero on this path (reference recipes/vanilla_bert.py:289).  One warp per
+// token; the normalised row is broadcast to the S coalition rows of its input.
+// ------------------------------------------------------------------------------------------------
+__global__ void bert_embed_kernel(const int64_t* __restrict__ ids, const float* __restrict__ word,
+                                  const float* __restrict__ pos, const float* __restrict__ type0,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                  int B, int S, int T, int H, int vocab, float* __restrict__ x) {
+  const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tok >= B * T) return;
+  const int lane = threadIdx.x & 31;
+  const int b = tok / T, t = tok % T;
+  long long id = ids[tok];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const float* w = word + id * H;
+  const float* pp = pos + (long long)t * H;
+  float s = 0.f;
+  for (int i = lane * 4; i < H; i += 128) {
+    const float4 a = *reinterpret_cast<const float4*>(w + i);
+    const float4 c = __ldg(reinterpret_cast<const float4*>(type0 + i));
+    const float4 d = __ldg(reinterpret_cast<const float4*>(pp + i));
+    s += ((a.x + c.x) + d.x) + ((a.y + c.y) + d.y) + ((a.z + c.z) + d.z) + ((a.w + c.w) + d.w);
+  }
+  const float mean = warp_sum(s) / (float)H;
+  float ss = 0.f;
+  for (int i = lane * 4; i < H; i += 128) {
+    const float4 a = *reinterpret_cast<const float4*>(w + i);
+    const float4 c = __ldg(reinterpret_cast<const float4*>(type0 + i));
+    const float4 d = __ldg(reinterpret_cast<const float4*>(pp + i));
+    const float e0 = ((a.x + c.x) + d.x) - mean, e1 = ((a.y + c.y) + d.y) - mean;
+    const float e2 = ((a.z + c.z) + d.z) - mean, e3 = ((a.w + c.w) + d.w) - mean;
+    ss += (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / (float)H + eps);
+  for (int i = lane * 4; i < H; i += 128) {
+    const float4 a = *reinterpret_cast<const float4*>(w + i);
+    const float4 c = __ldg(reinterpret_cast<const float4*>(type0 + i));
+    const float4 d = __ldg(reinterpret_cast<const float4*>(pp + i));
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + i));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + i));
+    float4 o;
+    o.x = (((a.x + c.x) + d.x) - mean) * rstd * g.x + bb.x;
+    o.y = (((a.y + c.y) + d.y) - mean) * rstd * g.y + bb.y;
+    o.z = (((a.z + c.z) + d.z) - mean) * rstd * g.z + bb.z;
+    o.w = (((a.w + c.w) + d.w) - mean) * rstd * g.w + bb.w;
+    for (int sidx = 0; sidx < S; ++sidx)
+      *reinterpret_cast<float4*>(x + (((long long)b * S + sidx) * T + t) * H + i) = o;
+  }
+}
+
+int bert_embed(const int64_t* ids, const float* word, const float* pos, const float* type0,
+               const float* gamma, const float* beta, float eps, int B, int S, int T, int H, int vocab,
+               float* x, cudaStream_t st) {
+  AGB_REQUIRE(B >= 0 && S > 0 && T > 0 && H % 4 == 0 && vocab > 0, "embedding shape");
+  if (B == 0) return AGB_OK;
+  AGB_REQUIRE(ids && word && pos && type0 && gamma && beta && x, "null pointer");
+  const int warps = 8;
+  bert_embed_kernel<<<(B * T + warps - 1) / warps, warps * 32, 0, st>>>(ids, word, pos, type0, gamma, beta, eps, B,
+                                                                        S, T, H, vocab, x);
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CLS heads -> class PROBABILITIES (fp32 end to end: these are the Shapley value function v(S)).
+//   ViT  (reference models/vanilla_vit.py:213, 52-56): softmax(W * LN_final(x[row, 0]) + b)
+//   BERT (reference models/vanilla_bert.py:73-77, 615-619): softmax(W * tanh(Wp * x[row, 0] + bp) + b)
+// One CTA per row; H <= 4096, C <= 64.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+
+__global__ void cls_head_kernel(const float* __restrict__ x, long long row_stride, int H, int C, int mode,
+                                const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps,
+                                const float* __restrict__ wp, const float* __restrict__ bp,
+                                const float* __restrict__ wc, const float* __restrict__ bc,
+                                float* __restrict__ probs, float* __restrict__ logits_out) {
+  extern __shared__ float sm[];
+  float* h = sm;            // H
+  float* h2 = sm + H;       // H (BERT pooled)
+  float* lg = sm + 2 * H;   // C
+  float* red = sm + 2 * H + 64;
+  const float* xr = x + (long long)blockIdx.x * row_stride;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  const float* feat = h;
+  if (mode == 0) {
+    float s = 0.f;
+    for (int i = tid; i < H; i += nt) { h[i] = xr[i]; s += xr[i]; }
+    const float mean = block_sum(s, red) / (float)H;
+    float ss = 0.f;
+    for (int i = tid; i < H; i += nt) { const float d = h[i] - mean; ss += d * d; }
+    const float rstd = rsqrtf(block_sum(ss, red) / (float)H + eps);
+    for (int i = tid; i < H; i += nt) h[i] = (h[i] - mean) * rstd * ln_g[i] + ln_b[i];
+    __syncthreads();
+  } else {
+    for (int i = tid; i < H; i += nt) h[i] = xr[i];
+    __syncthreads();
+    for (int j = warp; j < H; j += nw) {
+      const float* wrow = wp + (long long)j * H;
+      float a = 0.f;
+      for (int i = lane; i < H; i += 32) a = fmaf(h[i], wrow[i], a);
+      a = warp_sum(a);
+      if (lane == 0) h2[j] = tanhf(a + bp[j]);
+    }
+    __syncthreads();
+    feat = h2;
+  }
+  for (int c = warp; c < C; c += nw) {
+    const float* wrow = wc + (long long)c * H;
+    float a = 0.f;
+    for (int i = lane; i < H; i += 32) a = fmaf(feat[i], wrow[i], a);
+    a = warp_sum(a);
+    if (lane == 0) lg[c] = a + bc[c];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float m = -INFINITY;
+    for (int c = 0; c < C; ++c) m = fmaxf(m, lg[c]);
+    float z = 0.f;
+    for (int c = 0; c < C; ++c) z += expf(lg[c] - m);
+    for (int c = 0; c < C; ++c) {
+      probs[(long long)blockIdx.x * C + c] = expf(lg[c] - m) / z;
+      if (logits_out) logits_out[(long long)blockIdx.x * C + c] = lg[c];
+    }
+  }
+}
+
+int cls_head(const float* x, long long row_stride, int rows, int H, int C, int mode, const float* ln_g,
+             const float* ln_b, float eps, const float* wp, const float* bp, const float* wc,
+             const float* bc, float* probs, float* logits_out, cudaStream_t st) {
+  AGB_REQUIRE(rows >= 0 && H > 0 && H <= 4096 && C > 0 && C <= 64, "head shape");
+  if (rows == 0) return AGB_OK;
+  AGB_REQUIRE(x && wc && bc && probs, "null pointer");
+  AGB_REQUIRE(mode == 0 ? (ln_g && ln_b) : (wp && bp), "head parameters");
+  const size_t smem = (2 * H + 64 + 32) * sizeof(float);
+  cls_head_kernel<<<rows, 256, smem, st>>>(x, row_stride, H, C, mode, ln_g, ln_b, eps, wp, bp, wc, bc, probs,
+                                           logits_out);
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+}  // namespace agb

@@ -1,0 +1,215 @@
+// Coalition-mask kernels: bit packing (a2), the paired Shapley-kernel sampler (a1) and the uniform
+// sampler (a15).  Integer/byte work, HBM-bound; one thread produces one packed 32-bit word so every
+// store is a coalesced 4-byte lane write and the int64 {0,1} tensors of the reference are only
+// touched when a caller asks for them.
+//
+// Layout contract (include/autognothi_b200.h): bit 0 of word 0 = CLS (always 1, reference
+// recipes/vanilla_vit.py:219-224), bit j+1 = player j.
+#include "agb_common.cuh"
+
+namespace agb {
+
+// ------------------------------------------------------------------------------------------------
+// pack: (rows, n) int64 {0,1}  ->  (rows, words) uint32
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_masks_kernel(const int64_t* __restrict__ mask, int rows, int n, int prepend_cls,
+                                  uint32_t* __restrict__ packed, int words) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)rows * words) return;
+  const int row = (int)(gid / words), w = (int)(gid % words);
+  const int64_t* src = mask + (long long)row * n;
+  uint32_t bits = 0;
+#pragma unroll 4
+  for (int b = 0; b < 32; ++b) {
+    const int tok = w * 32 + b;          // token index (CLS = 0 when prepend_cls)
+    const int j = tok - prepend_cls;     // player index
+    uint32_t v = 0;
+    if (prepend_cls && tok == 0) v = 1u;
+    else if (j >= 0 && j < n) v = (src[j] != 0) ? 1u : 0u;
+    bits |= v << b;
+  }
+  packed[gid] = bits;
+}
+
+// unpack: packed -> (rows, n) int64; `skip` leading tokens dropped (1 removes the CLS bit)
+__global__ void unpack_masks_kernel(const uint32_t* __restrict__ packed, int rows, int n, int skip,
+                                    int words, int64_t* __restrict__ out) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)rows * n) return;
+  const int row = (int)(gid / n), j = (int)(gid % n);
+  const int tok = j + skip;
+  out[gid] = (packed[(long long)row * words + (tok >> 5)] >> (tok & 31)) & 1u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Shapley-kernel sampler (reference models/shapley.py:56-79, 131-135)
+// ------------------------------------------------------------------------------------------------
+// inverse-CDF subset-size draw: position = max(count(u >= prefix[k]) - 1, 0); threshold =
+// float32(1/n) * float32(position)   (python-float scalar times int64 tensor -> float32 product)
+__device__ __forceinline__ float shapley_threshold(float u_size, const float* __restrict__ prefix,
+                                                   int n, float inv_n) {
+  int count = 0;
+  for (int k = 0; k < n - 1; ++k) count += (u_size >= prefix[k]) ? 1 : 0;
+  const int position = count > 0 ? count - 1 : 0;
+  return __fmul_rn(inv_n, (float)position);
+}
+
+// Philox4x32-10 (counter-based; Salmon et al. 2011) — the on-device uniform source.
+struct Philox {
+  uint32_t k0, k1;
+  __device__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+  __device__ uint4 operator()(uint64_t ctr_lo, uint64_t ctr_hi) const {
+    uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = (uint32_t)ctr_hi,
+             c3 = (uint32_t)(ctr_hi >> 32);
+    uint32_t a = k0, b = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      const uint32_t n0 = hi1 ^ c1 ^ a, n1 = lo1, n2 = hi0 ^ c3 ^ b, n3 = lo0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      a += 0x9E3779B9u; b += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+__device__ __forceinline__ float u24(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+// One thread = one packed word of one PAIR; writes the word for row 2i and its complement for row
+// 2i+1 (complement restricted to real player bits; CLS bit stays 1 in both).
+// MODE 0: uniforms given (bit-exact mirror of the reference given the same draws)
+// MODE 1: uniforms drawn on device from Philox(seed, offset)
+template <int MODE>
+__global__ void shapley_masks_kernel(const float* __restrict__ u_players, const float* __restrict__ u_size,
+                                     const float* __restrict__ prefix, uint64_t seed, uint64_t offset,
+                                     int pairs, int n, float inv_n, uint32_t* __restrict__ packed,
+                                     int words, int64_t* __restrict__ dense) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)pairs * words) return;
+  const int pair = (int)(gid / words), w = (int)(gid % words);
+  Philox rng(seed);
+  float us;
+  if (MODE == 0) us = u_size[pair];
+  else us = u24(rng(offset + (uint64_t)pair, 0xFFFFFFFFull).x);
+  const float thresh = shapley_threshold(us, prefix, n, inv_n);
+  uint32_t bits = 0, valid = 0;
+  for (int b4 = 0; b4 < 32; b4 += 4) {
+    uint4 rnd4 = make_uint4(0, 0, 0, 0);
+    if (MODE == 1) rnd4 = rng(offset + (uint64_t)pair, (uint64_t)(w * 8 + (b4 >> 2)));
+    const uint32_t rr[4] = {rnd4.x, rnd4.y, rnd4.z, rnd4.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int b = b4 + i;
+      const int tok = w * 32 + b;
+      const int j = tok - 1;
+      if (tok == 0) { bits |= 1u; continue; }
+      if (j < n) {
+        const float u = (MODE == 0) ? u_players[(long long)pair * n + j] : u24(rr[i]);
+        const uint32_t keep = (u > thresh) ? 1u : 0u;
+        bits |= keep << b;
+        valid |= 1u << b;
+        if (dense != nullptr) {
+          dense[((long long)2 * pair) * n + j] = keep;
+          dense[((long long)2 * pair + 1) * n + j] = 1 - (int64_t)keep;
+        }
+      }
+    }
+  }
+  const uint32_t cls = (w == 0) ? 1u : 0u;
+  packed[((long long)2 * pair) * words + w] = bits;
+  packed[((long long)2 * pair + 1) * words + w] = ((~bits) & valid) | cls;
+}
+
+// mask_purely_uniform (reference models/shapley.py:109-115): keep player j iff u[j] > u_row
+template <int MODE>
+__global__ void uniform_masks_kernel(const float* __restrict__ u_players, const float* __restrict__ u_row,
+                                     uint64_t seed, uint64_t offset, int rows, int n,
+                                     uint32_t* __restrict__ packed, int words, int64_t* __restrict__ dense) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)rows * words) return;
+  const int row = (int)(gid / words), w = (int)(gid % words);
+  Philox rng(seed);
+  const float thresh = (MODE == 0) ? u_row[row] : u24(rng(offset + (uint64_t)row, 0xFFFFFFFFull).x);
+  uint32_t bits = 0;
+  for (int b4 = 0; b4 < 32; b4 += 4) {
+    uint4 rnd4 = make_uint4(0, 0, 0, 0);
+    if (MODE == 1) rnd4 = rng(offset + (uint64_t)row, (uint64_t)(w * 8 + (b4 >> 2)));
+    const uint32_t rr[4] = {rnd4.x, rnd4.y, rnd4.z, rnd4.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int b = b4 + i;
+      const int tok = w * 32 + b;
+      const int j = tok - 1;
+      if (tok == 0) { bits |= 1u; continue; }
+      if (j < n) {
+        const float u = (MODE == 0) ? u_players[(long long)row * n + j] : u24(rr[i]);
+        const uint32_t keep = (u > thresh) ? 1u : 0u;
+        bits |= keep << b;
+        if (dense != nullptr) dense[(long long)row * n + j] = keep;
+      }
+    }
+  }
+  packed[gid] = bits;
+}
+
+static inline int blocks_for(long long n, int threads) { return (int)((n + threads - 1) / threads); }
+
+int pack_masks_i64(const int64_t* mask, int rows, int n, int prepend_cls, uint32_t* packed, int words,
+                   cudaStream_t st) {
+  AGB_REQUIRE(rows >= 0 && n > 0 && words * 32 >= n + (prepend_cls ? 1 : 0), "mask shape");
+  if (rows == 0) return AGB_OK;
+  AGB_REQUIRE(mask && packed, "null pointer");
+  pack_masks_kernel<<<blocks_for((long long)rows * words, 256), 256, 0, st>>>(mask, rows, n, prepend_cls ? 1 : 0,
+                                                                              packed, words);
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+int unpack_masks_i64(const uint32_t* packed, int rows, int n, int skip, int words, int64_t* out,
+                     cudaStream_t st) {
+  AGB_REQUIRE(rows >= 0 && n > 0 && words * 32 >= n + skip && skip >= 0, "mask shape");
+  if (rows == 0) return AGB_OK;
+  AGB_REQUIRE(packed && out, "null pointer");
+  unpack_masks_kernel<<<blocks_for((long long)rows * n, 256), 256, 0, st>>>(packed, rows, n, skip, words, out);
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+int shapley_masks(const float* u_players, const float* u_size, const float* prefix, int use_philox,
+                  uint64_t seed, uint64_t offset, int pairs, int n, uint32_t* packed, int words,
+                  int64_t* dense, cudaStream_t st) {
+  AGB_REQUIRE(pairs >= 0 && n >= 2 && words * 32 >= n + 1, "sampler shape (n_players >= 2)");
+  if (pairs == 0) return AGB_OK;
+  AGB_REQUIRE(prefix && packed, "null pointer");
+  const float inv_n = (float)(1.0 / (double)n);
+  const int blocks = blocks_for((long long)pairs * words, 128);
+  if (use_philox) {
+    shapley_masks_kernel<1><<<blocks, 128, 0, st>>>(nullptr, nullptr, prefix, seed, offset, pairs, n, inv_n,
+                                                    packed, words, dense);
+  } else {
+    AGB_REQUIRE(u_players && u_size, "uniforms required");
+    shapley_masks_kernel<0><<<blocks, 128, 0, st>>>(u_players, u_size, prefix, 0, 0, pairs, n, inv_n, packed,
+                                                    words, dense);
+  }
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+int uniform_masks(const float* u_players, const float* u_row, int use_philox, uint64_t seed,
+                  uint64_t offset, int rows, int n, uint32_t* packed, int words, int64_t* dense,
+                  cudaStream_t st) {
+  AGB_REQUIRE(rows >= 0 && n >= 1 && words * 32 >= n + 1, "sampler shape");
+  if (rows == 0) return AGB_OK;
+  AGB_REQUIRE(packed, "null pointer");
+  const int blocks = blocks_for((long long)rows * words, 128);
+  if (use_philox) {
+    uniform_masks_kernel<1><<<blocks, 128, 0, st>>>(nullptr, nullptr, seed, offset, rows, n, packed, words, dense);
+  } else {
+    AGB_REQUIRE(u_players && u_row, "uniforms required");
+    uniform_masks_kernel<0><<<blocks, 128, 0, st>>>(u_players, u_row, 0, 0, rows, n, packed, words, dense);
+  }
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+}  // namespace agb

@@ -1,0 +1,181 @@
+// fp32 CUDA-core kernels: the "exact" precision mode used to verify the path against the reference
+// at fp32 rtol 1e-4 (BASELINE.json north_star, SURVEY.md §7 "fp32 rtol 1e-4 gate"): a register-tiled
+// fp32 GEMM with the same fused epilogues as the tensor-core kernel, and a key-masked attention that
+// never materialises the (N,h,T,T) score tensor.  These are correctness instruments, not the
+// throughput path — the bf16 tcgen05 kernels are — but they run on the GPU with no library calls.
+#include "agb_common.cuh"
+
+namespace agb {
+
+// ------------------------------------------------------------------------------------------------
+// C[M,N] = act(alpha * A[M,K] * B[N,K]^T + bias) + residual      (all fp32, row-major)
+// 64x64 tile, 16x16 threads, 4x4 outputs per thread, K tiles of 16 staged in shared memory.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gemm_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int M, int N,
+                int K, float alpha, const float* __restrict__ bias, int act,
+                const float* __restrict__ res, int ldr, float* __restrict__ C, int ldc) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    // 64 rows x 16 k per operand = 1024 elements, 4 per thread
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = threadIdx.x + i * 256;
+      const int r = e >> 4, kk = e & 15;
+      const int gm = m0 + r, gn = n0 + r, gk = k0 + kk;
+      As[kk][r] = (gm < M && gk < K) ? A[(long long)gm * lda + gk] : 0.f;
+      Bs[kk][r] = (gn < N && gk < K) ? B[(long long)gn * ldb + gk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j] * alpha;
+      if (bias) v += bias[gn];
+      if (act == 1) v = gelu_erf_exact(v);
+      if (res) v += res[(long long)gm * ldr + gn];
+      C[(long long)gm * ldc + gn] = v;
+    }
+  }
+}
+
+int gemm_f32(const float* A, int lda, const float* B, int ldb, int M, int N, int K, float alpha,
+             const float* bias, int act, const float* res, int ldr, float* C, int ldc, cudaStream_t st) {
+  AGB_REQUIRE(M >= 0 && N > 0 && K > 0, "GEMM shape");
+  if (M == 0) return AGB_OK;
+  AGB_REQUIRE(A && B && C, "null pointer");
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  AGB_REQUIRE(grid.y <= 65535, "M too large for the fp32 verification GEMM (chunk the rows)");
+  gemm_f32_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, M, N, K, alpha, bias, act, res, ldr, C, ldc);
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Key-masked attention, CUDA-core version (fp32 math; fp32 or bf16 I/O).
+//   qkv : (N, T, 3H) fused projections, q | k | v along the last axis
+//   mask: packed key bitmask (N, words); bit t = token t kept
+//   mode AGB_MASK_MUL0   : s = m_j ? q.k/sqrt(d) : 0          (reference models/vanilla_vit.py:444-454)
+//   mode AGB_MASK_NEGINF : s = q.k/sqrt(d) + (1-m_j)*FLT_MIN  (reference models/vanilla_bert.py:520-523)
+// One warp per (row, head, query).  Scores live in a per-warp shared-memory strip of T floats.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float ldf(const T* p);
+template <>
+__device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ldf<bf16>(const bf16* p) { return __bfloat162float(*p); }
+template <typename T>
+__device__ __forceinline__ void stf(T* p, float v);
+template <>
+__device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void stf<bf16>(bf16* p, float v) { *p = __float2bfloat16(v); }
+
+template <typename TIO, int MAXD32>
+__global__ void attention_simt_kernel(const TIO* __restrict__ qkv, const uint32_t* __restrict__ mask,
+                                      int words, int T, int H, int heads, int mode, TIO* __restrict__ ctx) {
+  extern __shared__ float sc_all[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int d = H / heads;
+  const int row = blockIdx.z, head = blockIdx.y;
+  const int qi = blockIdx.x * nw + warp;
+  if (qi >= T) return;
+  float* sc = sc_all + warp * T;
+  const long long base = (long long)row * T * 3 * H;
+  const TIO* qp = qkv + base + (long long)qi * 3 * H + head * d;
+  const uint32_t* mrow = mask + (long long)row * words;
+  const float scale = 1.0f / sqrtf((float)d);
+  float qreg[MAXD32];
+#pragma unroll
+  for (int i = 0; i < MAXD32; ++i) qreg[i] = (lane + 32 * i < d) ? ldf<TIO>(qp + lane + 32 * i) : 0.f;
+  float mx = -INFINITY;
+  for (int j = 0; j < T; ++j) {
+    const TIO* kp = qkv + base + (long long)j * 3 * H + H + head * d;
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXD32; ++i)
+      if (lane + 32 * i < d) a = fmaf(qreg[i], ldf<TIO>(kp + lane + 32 * i), a);
+    a = warp_sum(a);
+    float s = a / sqrtf((float)d);
+    (void)scale;
+    const uint32_t keep = (mrow[j >> 5] >> (j & 31)) & 1u;
+    if (mode == AGB_MASK_MUL0) s = keep ? s : 0.f;
+    else s = keep ? s : s + (-3.402823466e+38f);
+    if (lane == 0) sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  __syncwarp();
+  float z = 0.f;
+  for (int j = lane; j < T; j += 32) {
+    const float e = expf(sc[j] - mx);
+    sc[j] = e;
+    z += e;
+  }
+  z = warp_sum(z);
+  __syncwarp();
+  float o[MAXD32];
+#pragma unroll
+  for (int i = 0; i < MAXD32; ++i) o[i] = 0.f;
+  for (int j = 0; j < T; ++j) {
+    const float pj = sc[j] / z;
+    const TIO* vp = qkv + base + (long long)j * 3 * H + 2 * H + head * d;
+#pragma unroll
+    for (int i = 0; i < MAXD32; ++i)
+      if (lane + 32 * i < d) o[i] = fmaf(pj, ldf<TIO>(vp + lane + 32 * i), o[i]);
+  }
+  TIO* op = ctx + ((long long)row * T + qi) * H + head * d;
+#pragma unroll
+  for (int i = 0; i < MAXD32; ++i)
+    if (lane + 32 * i < d) stf<TIO>(op + lane + 32 * i, o[i]);
+}
+
+int attention_simt(const void* qkv, int io_bf16, const uint32_t* mask, int words, int rows, int T, int H,
+                   int heads, int mode, void* ctx, cudaStream_t st) {
+  AGB_REQUIRE(rows >= 0 && T > 0 && heads > 0 && H % heads == 0, "attention shape");
+  AGB_REQUIRE(words * 32 >= T, "mask words");
+  AGB_REQUIRE(mode == AGB_MASK_MUL0 || mode == AGB_MASK_NEGINF, "mask mode");
+  const int d = H / heads;
+  AGB_REQUIRE(d <= 128, "head dim <= 128");
+  if (rows == 0) return AGB_OK;
+  AGB_REQUIRE(qkv && mask && ctx, "null pointer");
+  AGB_REQUIRE(rows <= 65535 && heads <= 65535, "grid limits (chunk the rows)");
+  const int nw = 4;
+  dim3 grid((T + nw - 1) / nw, heads, rows);
+  const size_t smem = (size_t)nw * T * sizeof(float);
+  if (io_bf16)
+    attention_simt_kernel<bf16, 4><<<grid, nw * 32, smem, st>>>(static_cast<const bf16*>(qkv), mask, words, T, H,
+                                                                heads, mode, static_cast<bf16*>(ctx));
+  else
+    attention_simt_kernel<float, 4><<<grid, nw * 32, smem, st>>>(static_cast<const float*>(qkv), mask, words, T, H,
+                                                                 heads, mode, static_cast<float*>(ctx));
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+}  // namespace agb

@@ -1,0 +1,244 @@
+"""Forward engine: strings the CUDA kernels into the masked surrogate / explainer passes.
+
+Two precision policies share one code path:
+  * "bf16"  — the throughput path: bf16 operands on tcgen05 tensor cores, fp32 accumulation, an fp32
+              residual stream, fp32 LayerNorm statistics, fp32 heads / normalisation / loss;
+  * "fp32"  — the exact path (CUDA-core fp32 GEMM + attention) used to verify against the reference
+              at rtol 1e-4 (BASELINE.json north_star).
+Inputs are (B, ...) tensors plus packed coalition masks of shape (B*S, words): each input is embedded
+ONCE and broadcast to its S coalition rows inside the embedding kernel, so the reference's Xs_EXT
+replication (scripts/train_explainer.py:159-163) never exists.  S = 1 gives the reference-shaped call.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import ops
+
+State = Dict[str, Tensor]
+
+
+def _is_vit(cfg) -> bool:
+    return hasattr(cfg, "img_px_size")
+
+
+def n_players_of(cfg) -> int:
+    if _is_vit(cfg):
+        return (cfg.img_px_size // cfg.img_patch_size) ** 2
+    return cfg.max_position_embeddings - 1
+
+
+class _Policy:
+    def __init__(self, precision: str):
+        assert precision in ("bf16", "fp32"), precision
+        self.precision = precision
+        self.bf16 = precision == "bf16"
+        self.act_dtype = torch.bfloat16 if self.bf16 else torch.float32
+
+    def weight(self, w: Tensor) -> Tensor:
+        w = w.detach().reshape(w.shape[0], -1).contiguous().float()
+        return ops.to_bf16(w) if self.bf16 else w
+
+    def linear(self, a: Tensor, w: Tensor, b: Optional[Tensor], *, act: int = 0, residual: Optional[Tensor] = None,
+               out_f32: bool = False, out: Optional[Tensor] = None, res_group: int = 0, res_rows: int = 0) -> Tensor:
+        if self.bf16:
+            return ops.gemm_bf16(a, w, b, act=act, residual=residual, out=out,
+                                 out_dtype=torch.float32 if out_f32 else torch.bfloat16,
+                                 res_group=res_group, res_rows=res_rows)
+        assert res_group == 0
+        return ops.gemm_f32(a, w, b, act=act, residual=residual, out=out)
+
+    def ln(self, x: Tensor, g: Tensor, b: Tensor, eps: float, *, want_f32: bool = False) -> Tuple[Tensor, Optional[Tensor]]:
+        """-> (activation-dtype copy, fp32 copy | None)"""
+        if self.bf16:
+            ob, of = ops.layernorm(x, g, b, eps, want_bf16=True, want_f32=want_f32)
+            return ob, of
+        _, of = ops.layernorm(x, g, b, eps, want_bf16=False, want_f32=True)
+        return of, of
+
+    def act(self, x_f32: Tensor) -> Tensor:
+        return ops.to_bf16(x_f32) if self.bf16 else x_f32
+
+
+def _f32(t: Tensor) -> Tensor:
+    return t.detach().float().contiguous()
+
+
+class LayerWeights:
+    """One transformer block in kernel-ready form (fused QKV, operand dtype per policy)."""
+
+    def __init__(self, sd: State, prefix: str, pol: _Policy, vit: bool):
+        sa = prefix + ".attention.self."
+        self.wqkv = pol.weight(torch.cat([sd[sa + "query.weight"], sd[sa + "key.weight"], sd[sa + "value.weight"]], 0))
+        self.bqkv = _f32(torch.cat([sd[sa + "query.bias"], sd[sa + "key.bias"], sd[sa + "value.bias"]], 0))
+        self.wo = pol.weight(sd[prefix + ".attention.output.dense.weight"])
+        self.bo = _f32(sd[prefix + ".attention.output.dense.bias"])
+        self.w1 = pol.weight(sd[prefix + ".intermediate.dense.weight"])
+        self.b1 = _f32(sd[prefix + ".intermediate.dense.bias"])
+        self.w2 = pol.weight(sd[prefix + ".output.dense.weight"])
+        self.b2 = _f32(sd[prefix + ".output.dense.bias"])
+        n1 = prefix + (".layernorm_before" if vit else ".attention.output.LayerNorm")
+        n2 = prefix + (".layernorm_after" if vit else ".output.LayerNorm")
+        self.ln1 = (_f32(sd[n1 + ".weight"]), _f32(sd[n1 + ".bias"])) if (n1 + ".weight") in sd else None
+        self.ln2 = (_f32(sd[n2 + ".weight"]), _f32(sd[n2 + ".bias"])) if (n2 + ".weight") in sd else None
+
+
+class BackboneWeights:
+    def __init__(self, sd: State, cfg, pol: _Policy):
+        self.vit = _is_vit(cfg)
+        root = "vit" if self.vit else "bert"
+        self.layers = [LayerWeights(sd, f"{root}.encoder.layers.{i}", pol, self.vit) for i in range(cfg.num_hidden_layers)]
+        if self.vit:
+            e = "vit.embeddings."
+            self.cls_token = _f32(sd[e + "cls_token"]).reshape(-1)
+            self.pos_emb = _f32(sd[e + "position_embeddings"]).reshape(-1, cfg.hidden_size)
+            self.w_patch = pol.weight(sd[e + "patch_embeddings.projection.weight"])
+            self.b_patch = _f32(sd[e + "patch_embeddings.projection.bias"])
+            self.final_ln = (_f32(sd["vit.layernorm.weight"]), _f32(sd["vit.layernorm.bias"]))
+        else:
+            e = "bert.embeddings."
+            self.word = _f32(sd[e + "word_embeddings.weight"])
+            self.pos = _f32(sd[e + "position_embeddings.weight"])
+            self.type0 = _f32(sd[e + "token_type_embeddings.weight"])[0].contiguous()
+            self.emb_ln = (_f32(sd[e + "LayerNorm.weight"]), _f32(sd[e + "LayerNorm.bias"]))
+
+
+def embed(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, S: int) -> Tensor:
+    """-> x (B*S, T, H) fp32 (reference models/vanilla_vit.py:242-253, models/vanilla_bert.py:307-325)"""
+    H = cfg.hidden_size
+    if bw.vit:
+        assert xs.dim() == 4 and xs.shape[1] == cfg.img_channels and xs.shape[2] == cfg.img_px_size == xs.shape[3], \
+            "pixel_values must be (B, img_channels, img_px_size, img_px_size)"
+        B = xs.shape[0]
+        T = n_players_of(cfg) + 1
+        patches = ops.vit_im2col(xs.float(), cfg.img_patch_size, pol.act_dtype)
+        pe = pol.linear(patches, bw.w_patch, bw.b_patch, out_f32=True)
+        return ops.vit_assemble(pe, bw.cls_token, bw.pos_emb, B, S, T, H)
+    assert xs.dim() == 2 and xs.dtype == torch.int64, "input_ids must be (B, T) int64"
+    assert xs.shape[1] <= cfg.max_position_embeddings
+    return ops.bert_embed(xs, bw.word, bw.pos, bw.type0, bw.emb_ln[0], bw.emb_ln[1], cfg.layer_norm_eps, S)
+
+
+def vit_layer(pol: _Policy, lw: LayerWeights, x: Tensor, masks: Tensor, T: int, heads: int, eps: float) -> Tensor:
+    """pre-LN block on the fp32 residual stream x (rows*T, H); updates x in place.
+    reference models/vanilla_vit.py:364-377"""
+    h = pol.ln(x, lw.ln1[0], lw.ln1[1], eps)[0] if lw.ln1 is not None else pol.act(x)
+    qkv = pol.linear(h, lw.wqkv, lw.bqkv)
+    ctx = ops.masked_attention(qkv, masks, T, heads, ops.MASK_MUL0)
+    pol.linear(ctx, lw.wo, lw.bo, residual=x, out_f32=True, out=x)
+    h = pol.ln(x, lw.ln2[0], lw.ln2[1], eps)[0]
+    f = pol.linear(h, lw.w1, lw.b1, act=ops.ACT_GELU)
+    pol.linear(f, lw.w2, lw.b2, residual=x, out_f32=True, out=x)
+    return x
+
+
+def bert_layer(pol: _Policy, lw: LayerWeights, x: Tensor, xa: Tensor, masks: Tensor, T: int, heads: int, eps: float
+               ) -> Tuple[Tensor, Tensor]:
+    """post-LN block; x fp32 residual stream, xa its activation-dtype copy.
+    reference models/vanilla_bert.py:396-427, 556-560, 600-604"""
+    qkv = pol.linear(xa, lw.wqkv, lw.bqkv)
+    ctx = ops.masked_attention(qkv, masks, T, heads, ops.MASK_NEGINF)
+    a = pol.linear(ctx, lw.wo, lw.bo, residual=x, out_f32=True)
+    if lw.ln1 is not None:
+        aa, a = pol.ln(a, lw.ln1[0], lw.ln1[1], eps, want_f32=True)
+    else:
+        aa = pol.act(a)
+    f = pol.linear(aa, lw.w1, lw.b1, act=ops.ACT_GELU)
+    y = pol.linear(f, lw.w2, lw.b2, residual=a, out_f32=True)
+    ya, y = pol.ln(y, lw.ln2[0], lw.ln2[1], eps, want_f32=True)
+    return y, ya
+
+
+def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tensor, S: int) -> Tuple[Tensor, Optional[Tensor]]:
+    """-> (x (rows*T, H) fp32 after the encoder stack [ViT: BEFORE the final LayerNorm], activation copy | None)"""
+    T = n_players_of(cfg) + 1
+    H, heads, eps = cfg.hidden_size, cfg.num_attention_heads, cfg.layer_norm_eps
+    x3 = embed(bw, cfg, pol, xs, S)
+    assert x3.shape[1] == T, f"sequence length {x3.shape[1]} != n_players + 1 = {T}"
+    rows = x3.shape[0]
+    assert masks.shape[0] == rows, f"need one packed mask row per (input, coalition): {masks.shape[0]} vs {rows}"
+    x = x3.reshape(rows * T, H)
+    if bw.vit:
+        for lw in bw.layers:
+            x = vit_layer(pol, lw, x, masks, T, heads, eps)
+        return x, None
+    xa = pol.act(x)
+    for lw in bw.layers:
+        x, xa = bert_layer(pol, lw, x, xa, masks, T, heads, eps)
+    return x, xa
+
+
+class SurrogateEngine:
+    """Masked value function v(S): class probabilities for (input, coalition) rows.
+    reference models/vanilla_vit.py:51-56, models/vanilla_bert.py:61-77"""
+
+    def __init__(self, sd: State, cfg, precision: str):
+        self.cfg = cfg
+        self.pol = _Policy(precision)
+        self.bw = BackboneWeights(sd, cfg, self.pol)
+        self.w_cls, self.b_cls = _f32(sd["classifier.weight"]), _f32(sd["classifier.bias"])
+        if not self.bw.vit:
+            self.w_pool, self.b_pool = _f32(sd["bert_pooler.dense.weight"]), _f32(sd["bert_pooler.dense.bias"])
+
+    @torch.no_grad()
+    def probs(self, xs: Tensor, masks: Tensor, S: int, max_rows: int = 1024) -> Tensor:
+        """xs (B, ...), masks packed (B*S, words) -> (B*S, C) fp32 probabilities, row order b*S+s."""
+        cfg, T = self.cfg, n_players_of(self.cfg) + 1
+        B = xs.shape[0]
+        assert masks.shape[0] == B * S
+        per = max(1, max_rows // S)
+        outs: List[Tensor] = []
+        for b0 in range(0, B, per):
+            b1 = min(B, b0 + per)
+            x, _ = run_backbone(self.bw, cfg, self.pol, xs[b0:b1], masks[b0 * S:b1 * S], S)
+            x3 = x.reshape((b1 - b0) * S, T, cfg.hidden_size)
+            if self.bw.vit:
+                outs.append(ops.cls_head(x3, 0, self.w_cls, self.b_cls, ln=(self.bw.final_ln[0], self.bw.final_ln[1], cfg.layer_norm_eps)))
+            else:
+                outs.append(ops.cls_head(x3, 1, self.w_cls, self.b_cls, pool=(self.w_pool, self.b_pool)))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+
+
+class ExplainerEngine:
+    """Inference-time explainer: backbone -> explainer_attn -> explainer_mlp -> fused head/normalise.
+    reference models/vanilla_vit.py:102-130, models/vanilla_bert.py:123-162"""
+
+    def __init__(self, sd: State, cfg, precision: str):
+        self.cfg = cfg
+        self.pol = pol = _Policy(precision)
+        self.bw = BackboneWeights(sd, cfg, pol)
+        vit = self.bw.vit
+        self.attn = [LayerWeights(sd, f"explainer_attn.{i}", pol, vit) for i in range(cfg.explainer_attn_num_layers)]
+        if vit:
+            self.mlp_ln = (_f32(sd["explainer_mlp.0.weight"]), _f32(sd["explainer_mlp.0.bias"]))
+            names = ("explainer_mlp.1", "explainer_mlp.3", "explainer_mlp.5")
+        else:
+            self.mlp_ln = None
+            names = ("explainer_mlp.0", "explainer_mlp.2", "explainer_mlp.4")
+        self.w_a, self.b_a = pol.weight(sd[names[0] + ".weight"]), _f32(sd[names[0] + ".bias"])
+        self.w_b, self.b_b = pol.weight(sd[names[1] + ".weight"]), _f32(sd[names[1] + ".bias"])
+        self.w_c, self.b_c = _f32(sd[names[2] + ".weight"]), _f32(sd[names[2] + ".bias"])  # fp32 head
+
+    @torch.no_grad()
+    def phi(self, xs: Tensor, masks: Tensor, grand: Optional[Tensor], null: Optional[Tensor], want_pred: bool = False):
+        """xs (B,...), masks packed (B, words) -> phi (B, C, n) fp32 [, pred (B,T,C)]"""
+        cfg, pol = self.cfg, self.pol
+        T = n_players_of(cfg) + 1
+        H, heads, eps = cfg.hidden_size, cfg.num_attention_heads, cfg.layer_norm_eps
+        B = xs.shape[0]
+        x, xa = run_backbone(self.bw, cfg, pol, xs, masks, 1)
+        if self.bw.vit:
+            _, x = ops.layernorm(x, self.bw.final_ln[0], self.bw.final_ln[1], eps, want_bf16=False, want_f32=True)
+            for lw in self.attn:
+                x = vit_layer(pol, lw, x, masks, T, heads, eps)
+            h = pol.ln(x, self.mlp_ln[0], self.mlp_ln[1], 1e-5)[0]  # nn.LayerNorm default eps (reference l.94)
+        else:
+            for lw in self.attn:
+                x, xa = bert_layer(pol, lw, x, xa, masks, T, heads, eps)
+            h = xa
+        h = pol.linear(h, self.w_a, self.b_a, act=ops.ACT_GELU)
+        h = pol.linear(h, self.w_b, self.b_b, act=ops.ACT_GELU)
+        return ops.explainer_head_fwd(h, B, T, self.w_c, self.b_c, grand, null, bool(cfg.explainer_normalize), want_pred)

@@ -1,0 +1,273 @@
+"""Tensor-level wrappers over the C-ABI (device memory and streams come from PyTorch; the arithmetic
+is ours).  Every function launches on torch's current CUDA stream and checks shapes/dtypes before
+handing raw pointers across the boundary."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _native as nat
+
+MASK_MUL0 = 0
+MASK_NEGINF = 1
+ACT_NONE = 0
+ACT_GELU = 1
+
+
+def _c(t: Tensor) -> Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def mask_words(n_tokens: int) -> int:
+    return (n_tokens + 31) // 32
+
+
+# ------------------------------------------------------------------------------------------------
+# masks
+# ------------------------------------------------------------------------------------------------
+def pack_masks(mask: Tensor, prepend_cls: bool = True) -> Tensor:
+    """(rows, n) int64 {0,1} player masks -> (rows, words) packed int32 (bit 0 = CLS)."""
+    assert mask.dim() == 2 and mask.dtype == torch.int64, "mask must be (rows, n_players) int64"
+    mask = _c(mask)
+    rows, n = mask.shape
+    words = mask_words(n + (1 if prepend_cls else 0))
+    out = torch.empty((rows, words), dtype=torch.int32, device=mask.device)
+    nat.call("agb_pack_masks_i64", nat.ptr(mask), rows, n, 1 if prepend_cls else 0, nat.ptr(out), words, nat.stream())
+    return out
+
+
+def unpack_masks(packed: Tensor, n: int, skip: int = 1) -> Tensor:
+    packed = _c(packed)
+    rows, words = packed.shape
+    out = torch.empty((rows, n), dtype=torch.int64, device=packed.device)
+    nat.call("agb_unpack_masks_i64", nat.ptr(packed), rows, n, skip, words, nat.ptr(out), nat.stream())
+    return out
+
+
+def shapley_masks(prefix: Tensor, pairs: int, n_players: int, *, u_players: Optional[Tensor] = None,
+                  u_size: Optional[Tensor] = None, seed: int = 0, offset: int = 0,
+                  want_dense: bool = False) -> Tuple[Tensor, Optional[Tensor]]:
+    """Paired Shapley-kernel sampler -> (packed (2*pairs, words), dense (2*pairs, n) int64 | None)."""
+    dev = prefix.device
+    words = mask_words(n_players + 1)
+    packed = torch.empty((2 * pairs, words), dtype=torch.int32, device=dev)
+    dense = torch.empty((2 * pairs, n_players), dtype=torch.int64, device=dev) if want_dense else None
+    use_philox = u_players is None
+    if not use_philox:
+        assert u_players.shape == (pairs, n_players) and u_size.numel() == pairs
+        u_players, u_size = _c(u_players.float()), _c(u_size.float().reshape(-1))
+    nat.call("agb_shapley_masks", nat.ptr(u_players), nat.ptr(u_size), nat.ptr(_c(prefix)), 1 if use_philox else 0,
+             seed, offset, pairs, n_players, nat.ptr(packed), words, nat.ptr(dense), nat.stream())
+    return packed, dense
+
+
+def uniform_masks(rows: int, n_players: int, device, *, u_players: Optional[Tensor] = None,
+                  u_row: Optional[Tensor] = None, seed: int = 0, offset: int = 0,
+                  want_dense: bool = False) -> Tuple[Tensor, Optional[Tensor]]:
+    words = mask_words(n_players + 1)
+    packed = torch.empty((rows, words), dtype=torch.int32, device=device)
+    dense = torch.empty((rows, n_players), dtype=torch.int64, device=device) if want_dense else None
+    use_philox = u_players is None
+    if not use_philox:
+        u_players, u_row = _c(u_players.float()), _c(u_row.float().reshape(-1))
+    nat.call("agb_uniform_masks", nat.ptr(u_players), nat.ptr(u_row), 1 if use_philox else 0, seed, offset, rows,
+             n_players, nat.ptr(packed), words, nat.ptr(dense), nat.stream())
+    return packed, dense
+
+
+# ------------------------------------------------------------------------------------------------
+# dense
+# ------------------------------------------------------------------------------------------------
+def gemm_bf16(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, act: int = ACT_NONE,
+              residual: Optional[Tensor] = None, out_dtype=torch.bfloat16, out: Optional[Tensor] = None,
+              a_mn: bool = False, w_mn: bool = False, alpha: float = 1.0,
+              res_group: int = 0, res_rows: int = 0) -> Tensor:
+    """out[M,N] = act(alpha * A @ W^T + bias) + residual.   K-major: a [M,K], w [N,K] (nn.Linear layout).
+    MN-major (a_mn / w_mn): the operand is stored transposed, a [K,M] / w [K,N]."""
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
+    assert a.stride(1) == 1 and w.stride(1) == 1
+    M, K = (a.shape[1], a.shape[0]) if a_mn else a.shape
+    N, Kw = (w.shape[1], w.shape[0]) if w_mn else w.shape
+    assert K == Kw, f"inner dims differ: {K} vs {Kw}"
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    res_bf16 = residual if (residual is not None and residual.dtype == torch.bfloat16) else None
+    res_f32 = residual if (residual is not None and residual.dtype == torch.float32) else None
+    if residual is not None:
+        assert residual.stride(-1) == 1 and (res_bf16 is not None or res_f32 is not None)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N
+    ldr = residual.stride(0) if residual is not None else 0
+    nat.call("agb_gemm_bf16", nat.ptr(a), a.stride(0), 1 if a_mn else 0, nat.ptr(w), w.stride(0), 1 if w_mn else 0,
+             M, N, K, float(alpha), nat.ptr(bias), act, nat.ptr(res_bf16), nat.ptr(res_f32), ldr, res_group, res_rows,
+             nat.ptr(out), out.stride(0), 1 if out.dtype == torch.float32 else 0, nat.stream())
+    return out
+
+
+def gemm_f32(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, act: int = ACT_NONE,
+             residual: Optional[Tensor] = None, out: Optional[Tensor] = None, alpha: float = 1.0) -> Tensor:
+    assert a.dtype == torch.float32 and w.dtype == torch.float32 and a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    step = 65535 * 64
+    for m0 in range(0, M, step):
+        m1 = min(M, m0 + step)
+        r = residual[m0:m1] if residual is not None else None
+        nat.call("agb_gemm_f32", nat.ptr(a[m0:m1]), a.stride(0), nat.ptr(w), w.stride(0), m1 - m0, N, K, float(alpha),
+                 nat.ptr(bias), act, nat.ptr(r), r.stride(0) if r is not None else 0, nat.ptr(out[m0:m1]),
+                 out.stride(0), nat.stream())
+    return out
+
+
+def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, *, want_bf16: bool, want_f32: bool
+              ) -> Tuple[Optional[Tensor], Optional[Tensor]]:
+    """LayerNorm over the last dim of a 2-D tensor; returns (bf16 copy | None, fp32 copy | None)."""
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype in (torch.float32, torch.bfloat16)
+    rows, H = x.shape
+    ob = torch.empty((rows, H), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    of = torch.empty((rows, H), dtype=torch.float32, device=x.device) if want_f32 else None
+    nat.call("agb_layernorm", nat.ptr(x), 1 if x.dtype == torch.bfloat16 else 0, x.stride(0), rows, H, nat.ptr(gamma),
+             nat.ptr(beta), float(eps), nat.ptr(ob), nat.ptr(of), H, nat.stream())
+    return ob, of
+
+
+def to_bf16(x: Tensor) -> Tensor:
+    x = _c(x)
+    assert x.dtype == torch.float32
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    nat.call("agb_cast_f32_to_bf16", nat.ptr(x), nat.ptr(out), x.numel(), nat.stream())
+    return out
+
+
+def vit_im2col(images: Tensor, patch: int, out_dtype) -> Tensor:
+    images = _c(images)
+    assert images.dtype == torch.float32 and images.dim() == 4
+    B, C, px, px2 = images.shape
+    assert px == px2
+    g = px // patch
+    out = torch.empty((B * g * g, C * patch * patch), dtype=out_dtype, device=images.device)
+    nat.call("agb_vit_im2col", nat.ptr(images), B, C, px, patch, nat.ptr(out), 1 if out_dtype == torch.bfloat16 else 0,
+             nat.stream())
+    return out
+
+
+def vit_assemble(patch_emb: Tensor, cls_token: Tensor, pos_emb: Tensor, B: int, S: int, T: int, H: int) -> Tensor:
+    x = torch.empty((B * S, T, H), dtype=torch.float32, device=patch_emb.device)
+    nat.call("agb_vit_assemble", nat.ptr(_c(patch_emb)), nat.ptr(_c(cls_token)), nat.ptr(_c(pos_emb)), B, S, T, H,
+             nat.ptr(x), nat.stream())
+    return x
+
+
+def bert_embed(ids: Tensor, word: Tensor, pos: Tensor, type_emb: Tensor, gamma: Tensor, beta: Tensor, eps: float,
+               S: int) -> Tensor:
+    ids = _c(ids)
+    assert ids.dtype == torch.int64 and ids.dim() == 2
+    B, T = ids.shape
+    H = word.shape[1]
+    x = torch.empty((B * S, T, H), dtype=torch.float32, device=ids.device)
+    nat.call("agb_bert_embed", nat.ptr(ids), nat.ptr(word), nat.ptr(pos), nat.ptr(type_emb), nat.ptr(gamma),
+             nat.ptr(beta), float(eps), B, S, T, H, word.shape[0], nat.ptr(x), nat.stream())
+    return x
+
+
+def cls_head(x: Tensor, mode: int, w_cls: Tensor, b_cls: Tensor, *, ln: Optional[Tuple[Tensor, Tensor, float]] = None,
+             pool: Optional[Tuple[Tensor, Tensor]] = None, want_logits: bool = False):
+    """x (rows, T, H) fp32 -> probabilities (rows, C) [, logits]."""
+    assert x.dtype == torch.float32 and x.dim() == 3 and x.is_contiguous()
+    rows, T, H = x.shape
+    C = w_cls.shape[0]
+    probs = torch.empty((rows, C), dtype=torch.float32, device=x.device)
+    logits = torch.empty((rows, C), dtype=torch.float32, device=x.device) if want_logits else None
+    g, b, eps = ln if ln is not None else (None, None, 0.0)
+    wp, bp = pool if pool is not None else (None, None)
+    nat.call("agb_cls_head", nat.ptr(x), T * H, rows, H, C, mode, nat.ptr(g), nat.ptr(b), float(eps), nat.ptr(wp),
+             nat.ptr(bp), nat.ptr(w_cls), nat.ptr(b_cls), nat.ptr(probs), nat.ptr(logits), nat.stream())
+    return (probs, logits) if want_logits else probs
+
+
+def masked_attention(qkv: Tensor, packed_mask: Tensor, T: int, heads: int, mode: int, *, force_simt: bool = False) -> Tensor:
+    """qkv (rows*T, 3H) fused projections -> ctx (rows*T, H), same dtype.  bf16 + head dim 64 + T <= 256 runs
+    the tcgen05 kernel; fp32 (the exact mode) and the remaining shapes run the CUDA-core kernel."""
+    assert qkv.is_contiguous() and packed_mask.is_contiguous() and packed_mask.dtype == torch.int32
+    rows = qkv.shape[0] // T
+    H = qkv.shape[1] // 3
+    words = packed_mask.shape[1]
+    assert packed_mask.shape[0] == rows, "one mask row per input row"
+    ctx = torch.empty((rows * T, H), dtype=qkv.dtype, device=qkv.device)
+    tc_ok = qkv.dtype == torch.bfloat16 and H == heads * 64 and T <= 256 and not force_simt
+    if tc_ok:
+        nat.call("agb_masked_attention_bf16", nat.ptr(qkv), nat.ptr(packed_mask), words, rows, T, H, heads, mode,
+                 nat.ptr(ctx), nat.stream())
+    else:
+        step = 65535
+        for r0 in range(0, rows, step):
+            r1 = min(rows, r0 + step)
+            nat.call("agb_masked_attention_simt", nat.ptr(qkv[r0 * T:r1 * T]), 1 if qkv.dtype == torch.bfloat16 else 0,
+                     nat.ptr(packed_mask[r0:r1]), words, r1 - r0, T, H, heads, mode, nat.ptr(ctx[r0 * T:r1 * T]),
+                     nat.stream())
+    return ctx
+
+
+# ------------------------------------------------------------------------------------------------
+# explainer head / loss
+# ------------------------------------------------------------------------------------------------
+def explainer_head_fwd(h: Tensor, B: int, T: int, W: Tensor, bias: Tensor, grand: Optional[Tensor],
+                       null: Optional[Tensor], normalize: bool, want_pred: bool = False):
+    assert h.dim() == 2 and h.is_contiguous() and h.shape[0] == B * T
+    E, C = h.shape[1], W.shape[0]
+    phi = torch.empty((B, C, T - 1), dtype=torch.float32, device=h.device)
+    pred = torch.empty((B, T, C), dtype=torch.float32, device=h.device) if want_pred else None
+    if normalize:
+        grand = _c(grand.float())
+        null = _c(null.float().reshape(-1))
+        assert grand.shape == (B, C) and null.numel() == C
+    nat.call("agb_explainer_head_fwd", nat.ptr(h), 1 if h.dtype == torch.bfloat16 else 0, B, T, E, C, nat.ptr(_c(W)),
+             nat.ptr(_c(bias)), nat.ptr(grand) if normalize else None, nat.ptr(null) if normalize else None,
+             1 if normalize else 0, nat.ptr(phi), nat.ptr(pred), nat.stream())
+    return (phi, pred) if want_pred else phi
+
+
+def explainer_head_bwd(dphi: Tensor, h: Tensor, B: int, T: int, W: Tensor, normalize: bool,
+                       dW: Optional[Tensor], db: Optional[Tensor], want_dh: bool = True) -> Optional[Tensor]:
+    E, C = h.shape[1], W.shape[0]
+    dphi = _c(dphi.float())
+    dh = torch.empty_like(h) if want_dh else None
+    nat.call("agb_explainer_head_bwd", nat.ptr(dphi), nat.ptr(h), 1 if h.dtype == torch.bfloat16 else 0, B, T, E, C,
+             nat.ptr(_c(W)), 1 if normalize else 0, nat.ptr(dh), nat.ptr(dW), nat.ptr(db), nat.stream())
+    return dh
+
+
+def normalize_shapley(pred: Tensor, grand: Tensor, null: Tensor) -> Tensor:
+    pred = _c(pred.float())
+    B, T, C = pred.shape
+    out = torch.empty_like(pred)
+    nat.call("agb_normalize_shapley", nat.ptr(pred), nat.ptr(_c(grand.float())), nat.ptr(_c(null.float().reshape(-1))),
+             B, T, C, nat.ptr(out), nat.stream())
+    return out
+
+
+def shapley_loss_fwd(packed: Tensor, v0: Tensor, v_s: Tensor, phi: Tensor, B: int, S: int, n: int):
+    C = phi.shape[1]
+    packed, v_s, phi = _c(packed), _c(v_s.float()), _c(phi.float())
+    v0 = _c(v0.float().reshape(-1))
+    assert packed.shape[0] == B * S and v_s.shape == (B * S, C) and phi.shape == (B, C, n)
+    resid = torch.empty((B * S, C), dtype=torch.float32, device=phi.device)
+    partial = torch.empty((B,), dtype=torch.float32, device=phi.device)
+    loss = torch.empty((1,), dtype=torch.float32, device=phi.device)
+    nat.call("agb_shapley_loss_fwd", nat.ptr(packed), packed.shape[1], nat.ptr(v0), nat.ptr(v_s), nat.ptr(phi), B, S, n,
+             C, nat.ptr(resid), nat.ptr(partial), nat.ptr(loss), nat.stream())
+    return loss.reshape(()), resid
+
+
+def shapley_loss_bwd(packed: Tensor, resid: Tensor, grad_out: Optional[Tensor], B: int, S: int, n: int, C: int) -> Tensor:
+    dphi = torch.empty((B, C, n), dtype=torch.float32, device=resid.device)
+    g = _c(grad_out.float().reshape(1)) if grad_out is not None else None
+    nat.call("agb_shapley_loss_bwd", nat.ptr(_c(packed)), packed.shape[1], nat.ptr(resid), nat.ptr(g), B, S, n, C,
+             nat.ptr(dphi), nat.stream())
+    return dphi

@@ -49,6 +49,98 @@ int agb_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb
                   const void* residual_bf16, const float* residual_f32, int ldr, int res_group,
                   int res_rows, void* out, int ldo, int out_is_f32, void* stream);
 
+
+/* fp32 CUDA-core GEMM with the same epilogue — the "exact" verification mode (fp32 rtol 1e-4 gate
+ * of BASELINE.json).  A [M,K], B [N,K], C [M,N] row-major fp32. */
+int agb_gemm_f32(const float* A, int lda, const float* B, int ldb, int M, int N, int K, float alpha,
+                 const float* bias, int act, const float* residual, int ldr, float* C, int ldc,
+                 void* stream);
+
+/* ---- coalition masks (reference models/shapley.py:56-79,109-115,131-135; recipes/vanilla_vit.py:
+ *      219-224) ------------------------------------------------------------------------------- */
+/* (rows, n_players) int64 {0,1} -> packed words; prepend_cls=1 adds the always-on CLS bit 0. */
+int agb_pack_masks_i64(const int64_t* mask, int rows, int n_players, int prepend_cls,
+                       uint32_t* packed, int words, void* stream);
+/* packed -> (rows, n) int64; `skip` leading tokens are dropped (1 removes the CLS bit). */
+int agb_unpack_masks_i64(const uint32_t* packed, int rows, int n, int skip, int words, int64_t* out,
+                         void* stream);
+/* Paired Shapley-kernel sampler, `pairs` = n_mask_samples / 2 (reference models/shapley.py:56-79).
+ * use_philox=0: u_players (pairs, n) and u_size (pairs) are the torch.rand draws of l.69 and l.133
+ * — output is then bit-identical to mask_shapley_new under the same generator state.
+ * use_philox=1: uniforms come from Philox4x32-10(seed, offset) on the device.
+ * prefix = cumsum(p) - p (n-1 floats, l.132).  Row 2i+1 is the complement of row 2i (l.75-78).
+ * dense (2*pairs, n) int64 is optional (the reference's return layout). */
+int agb_shapley_masks(const float* u_players, const float* u_size, const float* prefix,
+                      int use_philox, uint64_t seed, uint64_t offset, int pairs, int n_players,
+                      uint32_t* packed, int words, int64_t* dense, void* stream);
+/* mask_purely_uniform (reference models/shapley.py:109-115). */
+int agb_uniform_masks(const float* u_players, const float* u_row, int use_philox, uint64_t seed,
+                      uint64_t offset, int rows, int n_players, uint32_t* packed, int words,
+                      int64_t* dense, void* stream);
+
+/* ---- row kernels ---------------------------------------------------------------------------- */
+/* nn.LayerNorm over the last dim (reference models/vanilla_vit.py:94,213,369,373; vanilla_bert.py:
+ * 318,548,596).  x fp32 or bf16 [rows, in_stride]; writes bf16 and/or fp32 [rows, out_stride]. */
+int agb_layernorm(const void* x, int x_is_bf16, long long in_stride, int rows, int H,
+                  const float* gamma, const float* beta, float eps, void* out_bf16, float* out_f32,
+                  long long out_stride, void* stream);
+int agb_cast_f32_to_bf16(const float* in, void* out_bf16, long long n, void* stream);
+/* stride-P patchify of NCHW fp32 images into Conv2d-weight order (reference models/vanilla_vit.py:
+ * 279-284): (B,C,px,px) -> (B*(px/P)^2, C*P*P) fp32 or bf16. */
+int agb_vit_im2col(const float* images, int B, int C, int px, int P, void* out, int out_is_bf16,
+                   void* stream);
+/* cat(cls, patches) + position embeddings, broadcast to S coalition rows per image (reference
+ * models/vanilla_vit.py:242-253; replaces Xs_EXT of scripts/train_explainer.py:159-163). */
+int agb_vit_assemble(const float* patch_emb, const float* cls_token, const float* pos_emb, int B,
+                     int S, int T, int H, float* x, void* stream);
+/* word + token_type(0) + position embeddings -> LayerNorm, broadcast to S rows per input
+ * (reference models/vanilla_bert.py:307-325). ids (B,T) int64. */
+int agb_bert_embed(const int64_t* ids, const float* word, const float* pos, const float* type0,
+                   const float* gamma, const float* beta, float eps, int B, int S, int T, int H,
+                   int vocab, float* x, void* stream);
+/* CLS head -> class probabilities.  mode 0 (ViT): softmax(Wc LN(x[row,0]) + bc) (reference
+ * models/vanilla_vit.py:213,52-56); mode 1 (BERT): softmax(Wc tanh(Wp x[row,0] + bp) + bc)
+ * (reference models/vanilla_bert.py:73-77,615-619).  x fp32, row_stride = T*H. */
+int agb_cls_head(const float* x, long long row_stride, int rows, int H, int C, int mode,
+                 const float* ln_gamma, const float* ln_beta, float eps, const float* w_pool,
+                 const float* b_pool, const float* w_cls, const float* b_cls, float* probs,
+                 float* logits_or_null, void* stream);
+
+/* ---- key-masked attention ------------------------------------------------------------------- */
+/* qkv (rows, T, 3H) fused q|k|v; packed key mask (rows, words); ctx (rows, T, H).
+ * mode AGB_MASK_MUL0 / AGB_MASK_NEGINF.  Scores are never written to HBM. */
+int agb_masked_attention_simt(const void* qkv, int io_is_bf16, const uint32_t* mask, int words,
+                              int rows, int T, int H, int heads, int mode, void* ctx, void* stream);
+/* tcgen05/TMA version: bf16 in/out, head dim 64, T <= 512. */
+int agb_masked_attention_bf16(const void* qkv, const uint32_t* mask, int words, int rows, int T,
+                              int H, int heads, int mode, void* ctx, void* stream);
+
+/* ---- explainer head + efficiency normalisation (reference models/vanilla_vit.py:123-129,
+ *      models/shapley.py:82-93) --------------------------------------------------------------- */
+/* h (B*T, E) fp32|bf16, W (C,E), bias (C), grand (B,C), null (C) -> phi (B,C,T-1); pred (B,T,C)
+ * optional.  The divisor is T (CLS included), CLS row dropped afterwards. */
+int agb_explainer_head_fwd(const void* h, int h_is_bf16, int B, int T, int E, int C, const float* W,
+                           const float* bias, const float* grand, const float* null_v,
+                           int normalize, float* phi, float* pred_or_null, void* stream);
+/* adjoint: dh (B*T,E) same dtype as h (nullable), dW (C,E) and db (C) ACCUMULATED (nullable). */
+int agb_explainer_head_bwd(const float* dphi, const void* h, int h_is_bf16, int B, int T, int E,
+                           int C, const float* W, int normalize, void* dh, float* dW, float* db,
+                           void* stream);
+/* normalize_shapley_explanation on a materialised pred (B,T,C) (reference models/shapley.py:82-93) */
+int agb_normalize_shapley(const float* pred, const float* grand, const float* null_v, int B, int T,
+                          int C, float* out, void* stream);
+
+/* ---- Shapley loss (reference models/shapley.py:9-53) ---------------------------------------- */
+/* packed (B*S, words), v0 (C), v_s (B*S,C), phi (B,C,n) -> resid (B*S,C), partial (B) scratch,
+ * loss (1) = n * mean((v0 + mask.phi - v_s)^2); deterministic reduction order. */
+int agb_shapley_loss_fwd(const uint32_t* packed, int words, const float* v0, const float* v_s,
+                         const float* phi, int B, int S, int n_players, int C, float* resid,
+                         float* partial, float* loss, void* stream);
+/* dphi (B,C,n) = grad_out * dloss/dphi; grad_out (1) device scalar or NULL for 1. */
+int agb_shapley_loss_bwd(const uint32_t* packed, int words, const float* resid,
+                         const float* grad_out, int B, int S, int n_players, int C, float* dphi,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

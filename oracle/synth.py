@@ -29,8 +29,8 @@ def _splitmix64(x: np.ndarray) -> np.ndarray:
 def uniform(name: str, shape: Tuple[int, ...], seed: int = 0) -> np.ndarray:
     """float32 uniforms in [-1, 1), a pure function of (name, seed, flat index)."""
     n = int(np.prod(shape)) if len(shape) else 1
-    key = _U64(zlib.crc32(name.encode("utf-8"))) * _U64(0x100000001B3) + _U64(seed) * _U64(0x9E3779B1)
     with np.errstate(over="ignore"):
+        key = _U64(zlib.crc32(name.encode("utf-8"))) * _U64(0x100000001B3) + _U64(seed) * _U64(0x9E3779B1)
         idx = np.arange(n, dtype=np.uint64) * _U64(0xD1342543DE82EF95) + key
         h = _splitmix64(idx)
     u = (h >> _U64(40)).astype(np.float64) / float(1 << 24)  # [0, 1)

@@ -1,0 +1,358 @@
+"""GPU parity tests proper: every kernel and the full masked surrogate / explainer path, called through
+the C-ABI (ctypes), against the CPU oracle and the golden fixtures minted from the reference.
+
+Tolerances (BASELINE.json north_star): integer / bit work is bit-exact; fp32 mode rtol 1e-4; bf16 mode
+attributions Pearson r >= 0.999 and relative L2 <= 1e-2.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import configs as ocfg
+from oracle import shapley as osh
+from oracle import synth
+from oracle import transformer as otr
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _np(t):
+    return t.detach().float().cpu().numpy()
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def pearson(a, b):
+    a, b = a.reshape(-1).astype(np.float64), b.reshape(-1).astype(np.float64)
+    return float(np.corrcoef(a, b)[0, 1])
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b.astype(np.float64)))
+
+
+@pytest.fixture(scope="module")
+def agb():
+    import autognothi_b200  # noqa: F401  (raises if the CUDA library is missing)
+    from autognothi_b200 import ops
+    return ops
+
+
+# ------------------------------------------------------------------------------------------------
+# masks: bit-exact
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 30, 31, 32, 63, 127, 196, 511])
+def test_pack_unpack_bit_exact(agb, n):
+    rng = np.random.default_rng(n)
+    m = (rng.random((37, n)) > 0.5).astype(np.int64)
+    packed = agb.pack_masks(torch.from_numpy(m).to(DEV))
+    np.testing.assert_array_equal(packed.cpu().numpy().view(np.uint32), osh.pack_player_mask(m))
+    back = agb.unpack_masks(packed, n, skip=1)
+    np.testing.assert_array_equal(back.cpu().numpy(), m)
+
+
+def test_pack_empty(agb):
+    packed = agb.pack_masks(torch.zeros((0, 196), dtype=torch.int64, device=DEV))
+    assert packed.shape == (0, 7)
+
+
+@pytest.mark.parametrize("n", [196, 127, 511, 16, 2])
+def test_sampler_bit_exact_with_reference_uniforms(agb, golden_dir, n):
+    g = _load(golden_dir, "sampler.npz")
+    u_p = torch.from_numpy(g[f"n{n}_u_players"]).to(DEV)
+    u_s = torch.from_numpy(g[f"n{n}_u_size"]).to(DEV)
+    prefix = torch.from_numpy(g[f"n{n}_prefix"]).to(DEV)
+    pairs = u_p.shape[0]
+    packed, dense = agb.shapley_masks(prefix, pairs, n, u_players=u_p, u_size=u_s, want_dense=True)
+    ref = g[f"n{n}_masks"].astype(np.int64)
+    np.testing.assert_array_equal(dense.cpu().numpy(), ref)
+    np.testing.assert_array_equal(packed.cpu().numpy().view(np.uint32), osh.pack_player_mask(ref))
+
+
+def test_sampler_matches_reference_under_torch_seed(agb, golden_dir):
+    """mask_shapley_new with rng='torch' consumes the CPU generator like the reference does."""
+    from autognothi_b200.models import shapley as ash
+    g = _load(golden_dir, "sampler.npz")
+    for n in (196, 127):
+        seed, rows = (int(v) for v in g[f"n{n}_seed"])
+        torch.manual_seed(seed)
+        m = ash.mask_shapley_new(rows, n)
+        assert m.dtype == torch.int64 and m.shape == (rows, n) and m.is_cuda
+        np.testing.assert_array_equal(m.cpu().numpy(), g[f"n{n}_masks"].astype(np.int64))
+    torch.manual_seed(99)
+    pu = ash.mask_purely_uniform(16, 196)
+    np.testing.assert_array_equal(pu.cpu().numpy(), g["pu_masks"].astype(np.int64))
+
+
+def test_sampler_philox_properties(agb):
+    from autognothi_b200.models import shapley as ash
+    n, rows = 196, 8192
+    pm = ash.mask_shapley_new(rows, n, rng="philox", seed=123, packed=True)
+    m = pm.dense().cpu().numpy()
+    assert m.shape == (rows, n) and set(np.unique(m)) <= {0, 1}
+    np.testing.assert_array_equal(m[0::2] + m[1::2], 1)            # paired complements
+    assert np.all(pm.words.cpu().numpy().view(np.uint32)[:, 0] & 1 == 1)  # CLS bit always on
+    sizes = m[0::2].sum(axis=1)
+    # reference sampler statistics: mean size ~99.4, P(all-ones row) ~0.108
+    assert 92 < sizes.mean() < 107
+    assert 0.07 < (sizes == n).mean() < 0.15
+    pm2 = ash.mask_shapley_new(rows, n, rng="philox", seed=123, packed=True)
+    assert torch.equal(pm.words, pm2.words)                         # deterministic in (seed, offset)
+    pm3 = ash.mask_shapley_new(rows, n, rng="philox", seed=124, packed=True)
+    assert not torch.equal(pm.words, pm3.words)
+
+
+# ------------------------------------------------------------------------------------------------
+# dense kernels
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(197, 192, 192), (394, 768, 768), (1000, 2304, 768), (130, 128, 64), (64, 3072, 768)])
+@pytest.mark.parametrize("variant", ["plain", "bias_gelu", "bias_res_f32"])
+def test_gemm_bf16(agb, M, N, K, variant):
+    torch.manual_seed(0)
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    w = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device=DEV) * 0.1
+    res = torch.randn(M, N, device=DEV)
+    ref = a.float() @ w.float().t()
+    if variant == "plain":
+        out = agb.gemm_bf16(a, w, out_dtype=torch.float32)
+    elif variant == "bias_gelu":
+        out = agb.gemm_bf16(a, w, bias, act=agb.ACT_GELU)
+        ref = torch.nn.functional.gelu(ref + bias)
+    else:
+        out = agb.gemm_bf16(a, w, bias, residual=res, out_dtype=torch.float32)
+        ref = ref + bias + res
+    tol = 2e-2 if out.dtype == torch.bfloat16 else 2e-3
+    torch.testing.assert_close(out.float(), ref, rtol=tol, atol=tol)
+
+
+def test_gemm_bf16_mn_major_operands(agb):
+    """dgrad / wgrad operand layouts: dX = dY @ W (W MN-major), dW = dY^T @ X (both MN-major)."""
+    torch.manual_seed(1)
+    M, N, K = 520, 256, 384
+    dy = torch.randn(M, N, device=DEV).bfloat16()
+    w = torch.randn(N, K, device=DEV).bfloat16()
+    x = torch.randn(M, K, device=DEV).bfloat16()
+    dx = agb.gemm_bf16(dy, w, w_mn=True, out_dtype=torch.float32)          # [M,N] x [N,K]
+    torch.testing.assert_close(dx, dy.float() @ w.float(), rtol=2e-3, atol=2e-2)
+    dw = agb.gemm_bf16(dy, x, a_mn=True, w_mn=True, out_dtype=torch.float32)  # [N,M] x [M,K]
+    torch.testing.assert_close(dw, dy.float().t() @ x.float(), rtol=2e-3, atol=5e-2)
+
+
+def test_gemm_f32_exact_mode(agb):
+    torch.manual_seed(2)
+    a, w = torch.randn(197, 130, device=DEV), torch.randn(75, 130, device=DEV)
+    b, r = torch.randn(75, device=DEV), torch.randn(197, 75, device=DEV)
+    out = agb.gemm_f32(a, w, b, act=agb.ACT_GELU, residual=r)
+    ref = torch.nn.functional.gelu(a.double() @ w.double().t() + b.double()) + r.double()
+    torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("H", [128, 192, 768, 1024])
+def test_layernorm(agb, H):
+    torch.manual_seed(3)
+    x = torch.randn(333, H, device=DEV) * 3 + 1
+    g, b = torch.randn(H, device=DEV), torch.randn(H, device=DEV)
+    ob, of = agb.layernorm(x, g, b, 1e-12, want_bf16=True, want_f32=True)
+    ref = torch.nn.functional.layer_norm(x.double(), (H,), g.double(), b.double(), 1e-12)
+    torch.testing.assert_close(of.double(), ref, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(ob.double(), ref, rtol=1e-2, atol=1e-2)
+
+
+def _attention_case(T, heads, rows, seed):
+    rng = np.random.default_rng(seed)
+    H = heads * 64
+    qkv = rng.standard_normal((rows, T, 3 * H)).astype(np.float32)
+    mask = (rng.random((rows, T)) > 0.5).astype(np.int64)
+    mask[:, 0] = 1
+    if rows > 1:
+        mask[1, 1:] = 0   # empty coalition
+    if rows > 2:
+        mask[2, :] = 1    # grand coalition
+    return qkv, mask, H
+
+
+@pytest.mark.parametrize("mode", ["mul0", "neginf"])
+@pytest.mark.parametrize("T,heads", [(197, 3), (128, 2), (17, 2), (256, 1), (33, 1)])
+def test_attention_exact_fp32(agb, mode, T, heads):
+    qkv, mask, H = _attention_case(T, heads, 3, T)
+    q, k, v = qkv[..., :H], qkv[..., H:2 * H], qkv[..., 2 * H:]
+    ref = otr.masked_attention(q.astype(np.float64), k.astype(np.float64), v.astype(np.float64), mask, heads, mode)
+    packed = torch.from_numpy(osh.pack_token_mask(mask).view(np.int32)).to(DEV)
+    t = torch.from_numpy(qkv).to(DEV).reshape(-1, 3 * H)
+    ctx = agb.masked_attention(t, packed, T, heads, agb.MASK_MUL0 if mode == "mul0" else agb.MASK_NEGINF)
+    np.testing.assert_allclose(_np(ctx).reshape(ref.shape), ref, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("mode", ["mul0", "neginf"])
+@pytest.mark.parametrize("T,heads,rows", [(197, 3, 3), (128, 12, 2), (17, 2, 3), (256, 1, 2), (197, 12, 5), (130, 2, 1)])
+def test_attention_tcgen05_bf16(agb, mode, T, heads, rows):
+    qkv, mask, H = _attention_case(T, heads, rows, 7 * T + heads)
+    t = torch.from_numpy(qkv).to(DEV).bfloat16().reshape(-1, 3 * H)
+    qr = _np(t).reshape(rows, T, 3 * H).astype(np.float64)  # bf16-rounded inputs for the yardstick
+    ref = otr.masked_attention(qr[..., :H], qr[..., H:2 * H], qr[..., 2 * H:], mask, heads, mode)
+    packed = torch.from_numpy(osh.pack_token_mask(mask).view(np.int32)).to(DEV)
+    m = agb.MASK_MUL0 if mode == "mul0" else agb.MASK_NEGINF
+    ctx = agb.masked_attention(t, packed, T, heads, m)
+    got = _np(ctx).reshape(ref.shape)
+    assert np.isfinite(got).all()
+    np.testing.assert_allclose(got, ref, rtol=3e-2, atol=3e-2)
+    assert rel_l2(got, ref) < 1e-2
+    # and it agrees with the CUDA-core kernel on the same bf16 inputs
+    ctx2 = agb.masked_attention(t, packed, T, heads, m, force_simt=True)
+    assert rel_l2(_np(ctx), _np(ctx2).astype(np.float64)) < 1e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# explainer head / normalisation / loss
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["vit", "bert", "tiny"])
+def test_normalize_and_loss_vs_reference_golden(agb, golden_dir, tag):
+    from autognothi_b200.models import shapley as ash
+    g = _load(golden_dir, "shapley_math.npz")
+    pred, grand, null = (torch.from_numpy(g[f"{tag}_{k}"]).to(DEV) for k in ("pred", "grand", "null"))
+    out = ash.normalize_shapley_explanation(pred, grand, null)
+    np.testing.assert_allclose(_np(out), g[f"{tag}_norm"], rtol=1e-5, atol=1e-6)
+    mask = torch.from_numpy(g[f"{tag}_mask"].astype(np.int64)).to(DEV)
+    B, S, n = mask.shape
+    phi = torch.from_numpy(g[f"{tag}_phi"]).to(DEV).requires_grad_(True)
+    v_s = torch.from_numpy(g[f"{tag}_v_s"]).to(DEV)
+    loss = ash.loss_shapley_new(B, S, n, mask, null, v_s, grand, phi)
+    np.testing.assert_allclose(_np(loss), g[f"{tag}_loss"], rtol=1e-5)
+    loss.backward()
+    np.testing.assert_allclose(_np(phi.grad), g[f"{tag}_dphi"], rtol=1e-4, atol=1e-6)
+    # packed masks give the same numbers
+    phi2 = phi.detach().clone().requires_grad_(True)
+    loss2 = ash.loss_shapley_new(B, S, n, ash.PackedMasks.from_dense(mask), null, v_s, grand, phi2)
+    assert float(loss2) == float(loss)
+
+
+def test_explainer_head_fused_normalise(agb):
+    rng = np.random.default_rng(5)
+    B, T, E, C = 3, 197, 256, 10
+    h = rng.standard_normal((B * T, E)).astype(np.float32)
+    W = (rng.standard_normal((C, E)) / 16).astype(np.float32)
+    b = rng.standard_normal(C).astype(np.float32)
+    grand, null = rng.random((B, C)).astype(np.float32), rng.random((1, C)).astype(np.float32)
+    pred_ref = (h.astype(np.float64) @ W.T.astype(np.float64) + b).reshape(B, T, C)
+    phi_ref = osh.explainer_output(pred_ref, grand.astype(np.float64), null.astype(np.float64))
+    th, tW, tb = (torch.from_numpy(x).to(DEV) for x in (h, W, b))
+    phi, pred = agb.explainer_head_fwd(th, B, T, tW, tb, torch.from_numpy(grand).to(DEV), torch.from_numpy(null).to(DEV), True, True)
+    np.testing.assert_allclose(_np(pred), pred_ref, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(_np(phi), phi_ref, rtol=1e-4, atol=1e-5)
+    # adjoint
+    dphi = rng.standard_normal((B, C, T - 1)).astype(np.float32)
+    dpred = osh.explainer_output_grad(dphi.astype(np.float64), T)
+    dW = torch.zeros(C, E, device=DEV)
+    db = torch.zeros(C, device=DEV)
+    dh = agb.explainer_head_bwd(torch.from_numpy(dphi).to(DEV), th, B, T, tW, True, dW, db)
+    np.testing.assert_allclose(_np(dh), dpred.reshape(B * T, C) @ W.astype(np.float64), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(_np(dW), dpred.reshape(B * T, C).T @ h.astype(np.float64), rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(_np(db), dpred.sum(axis=(0, 1)), rtol=1e-3, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------
+# full path: masked surrogate + explainer through the recipe boundary
+# ------------------------------------------------------------------------------------------------
+def _build(name, precision):
+    from autognothi_b200.recipes.vanilla_bert import vanilla_bert_recipe
+    from autognothi_b200.recipes.vanilla_vit import vanilla_vit_recipe
+    cfgd = ocfg.get_config(name)
+    rec = vanilla_vit_recipe() if ocfg.is_vit(cfgd) else vanilla_bert_recipe()
+    cfg = rec.t_config(**cfgd)
+    srg, exp = rec.t_surrogate(cfg), rec.t_explainer(cfg)
+    srg.load_state_dict({k: torch.from_numpy(v) for k, v in synth.surrogate_state(cfgd, seed=0).items()}, strict=True)
+    exp.load_state_dict({k: torch.from_numpy(v) for k, v in synth.explainer_state(cfgd, seed=1).items()}, strict=True)
+    srg, exp = srg.to(DEV).eval(), exp.to(DEV).eval()
+    srg.agb_precision = exp.agb_precision = precision
+    return rec, cfgd, srg, exp
+
+
+FP32_CASES = ["vit_mini", "vit_mini_px64", "bert_mini", "vit_tiny"]
+
+
+@pytest.mark.parametrize("name", FP32_CASES + ["vit_base", "bert_base_128"])
+def test_full_path_fp32_vs_reference_golden(agb, golden_dir, name):
+    g = _load(golden_dir, f"model_{name}.npz")
+    B, S, n = (int(v) for v in g["meta"])
+    rec, cfgd, srg, exp = _build(name, "fp32")
+    xs = torch.from_numpy(synth.inputs(cfgd, B, seed=0)).to(DEV)
+    masks = torch.from_numpy(g["masks"].astype(np.int64)).to(DEV)
+    with torch.no_grad():
+        # reference-shaped call: caller replicates the inputs, one mask row per input row
+        v_s, _ = rec.fw_surrogate(srg, xs.repeat_interleave(S, dim=0), masks)
+        # additive fast path: (B, S, n) masks, no replication — must give identical numbers
+        v_s2, _ = rec.fw_surrogate(srg, xs, masks.reshape(B, S, n))
+        ones = torch.ones((B, n), dtype=torch.int64, device=DEV)
+        grand, _ = rec.fw_surrogate(srg, xs, ones)
+        null_x = torch.from_numpy(otr.null_input(cfgd)).to(DEV)
+        null, _ = rec.fw_surrogate(srg, null_x, torch.ones((1, n), dtype=torch.int64, device=DEV))
+        gg, gn = torch.from_numpy(g["grand"]).to(DEV), torch.from_numpy(g["null"]).to(DEV)
+        phi, _ = rec.fw_explainer(exp, xs, ones, gg, gn)
+        phi_m, _ = rec.fw_explainer(exp, xs, masks.reshape(B, S, n)[:, 0, :].contiguous(), gg, gn)
+    assert torch.equal(v_s, v_s2)
+    np.testing.assert_allclose(_np(v_s), g["v_s"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(_np(grand), g["grand"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(_np(null), g["null"], rtol=1e-4, atol=2e-6)
+    scale = np.abs(g["phi"]).max()
+    np.testing.assert_allclose(_np(phi), g["phi"], rtol=1e-4, atol=1e-4 * scale)
+    np.testing.assert_allclose(_np(phi_m), g["phi_masked"], rtol=1e-4, atol=1e-4 * scale)
+
+
+@pytest.mark.parametrize("name", ["vit_mini", "bert_mini", "vit_tiny", "vit_base", "bert_base_128"])
+def test_full_path_bf16_tensor_cores_vs_reference_golden(agb, golden_dir, name):
+    g = _load(golden_dir, f"model_{name}.npz")
+    B, S, n = (int(v) for v in g["meta"])
+    rec, cfgd, srg, exp = _build(name, "bf16")
+    xs = torch.from_numpy(synth.inputs(cfgd, B, seed=0)).to(DEV)
+    masks = torch.from_numpy(g["masks"].astype(np.int64)).to(DEV)
+    with torch.no_grad():
+        v_s, _ = rec.fw_surrogate(srg, xs, masks.reshape(B, S, n))
+        ones = torch.ones((B, n), dtype=torch.int64, device=DEV)
+        gg, gn = torch.from_numpy(g["grand"]).to(DEV), torch.from_numpy(g["null"]).to(DEV)
+        phi, _ = rec.fw_explainer(exp, xs, ones, gg, gn)
+    assert np.isfinite(_np(v_s)).all() and np.isfinite(_np(phi)).all()
+    np.testing.assert_allclose(_np(v_s), g["v_s"], atol=2e-2)          # probabilities
+    np.testing.assert_allclose(_np(v_s).sum(axis=1), 1.0, atol=1e-5)
+    r, l2 = pearson(_np(phi), g["phi"]), rel_l2(_np(phi), g["phi"])
+    assert r >= 0.999, f"Pearson {r}"
+    assert l2 <= 1e-2, f"relative L2 {l2}"
+
+
+def test_final_coherency(agb):
+    """The reference's only numerical self-check (scripts/train_all.py:166-218): the bundled Final model
+    agrees with the separate classifier / surrogate / explainer on the same input."""
+    rec, cfgd, srg, exp = _build("vit_mini", "fp32")
+    cfg = srg.config
+    cls = rec.conv_pretrained_classifier(cfg, srg).to(DEV).eval()
+    cls.agb_precision = "fp32"
+    final = rec.conv_explainer_final(cfg, rec.load_misc(None, cfg), cls, srg, exp).eval()
+    for m in (final.classifier, final.surrogate, final.explainer):
+        m.agb_precision = "fp32"
+    xs = torch.from_numpy(synth.inputs(cfgd, 2, seed=3)).to(DEV)
+    n = rec.n_players(cfg)
+    ones = torch.ones((2, n), dtype=torch.int64, device=DEV)
+    with torch.no_grad():
+        logits, phi = rec.fw_final(final, xs)
+        l2, _ = rec.fw_classifier(cls, xs, ones)
+        grand, _ = rec.fw_surrogate(srg, xs, ones)
+        phi2, _ = rec.fw_explainer(exp, xs, ones, grand, final.surrogate_null)
+    assert float((logits - l2).abs().max()) <= 1e-5
+    assert float((phi - phi2).abs().max()) <= 1e-5
+
+
+def test_reference_checkpoint_roundtrip(agb, golden_dir):
+    """state-dict ABI: keys and shapes equal the reference's (dumped into state_dict_keys.json)."""
+    import json
+    with open(os.path.join(golden_dir, "state_dict_keys.json")) as f:
+        ref = json.load(f)
+    for name in ("vit_mini", "bert_mini"):
+        _, _, srg, exp = _build(name, "fp32")
+        assert {k: list(v.shape) for k, v in srg.state_dict().items()} == ref[name]["surrogate"]
+        assert {k: list(v.shape) for k, v in exp.state_dict().items()} == ref[name]["explainer"]
