@@ -90,10 +90,21 @@ def stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-LAUNCHES = 0  # number of kernel-launching C-ABI calls made through `call` (bench.py's gpu_launches)
+LAUNCHES = 0       # number of kernel-launching C-ABI calls made through `call` (bench.py's gpu_launches)
+PROFILE = None     # when a list: every call appends (name, meta, start_event, end_event) — bench.py's roofline leg
+NEXT_META = None   # set by ops wrappers right before `call` (e.g. algorithmic FLOPs of a GEMM)
 
 
 def call(name: str, *args) -> None:
-    global LAUNCHES
+    global LAUNCHES, NEXT_META
     LAUNCHES += 1
+    if PROFILE is None:
+        check(getattr(lib, name)(*args), name)
+        return
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(getattr(lib, name)(*args), name)
+    e1.record()
+    PROFILE.append((name, NEXT_META, e0, e1))
+    NEXT_META = None

@@ -143,8 +143,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
   } else {
     // ------------------------------ softmax + epilogue (128 threads) ------------------------------
-    const int r = threadIdx.x - 64;                 // query row within the tile = TMEM lane
-    const int q = warp & 3;                         // TMEM lane quarter of this warp
+    const int q = warp & 3;                         // TMEM lane quarter this warp may touch
+    const int r = q * 32 + lane;                    // query row within the tile = TMEM lane
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const float scale_log2 = 0.125f * 1.4426950408889634f;
     int it = 0, un = 0;

@@ -101,6 +101,7 @@ def gemm_bf16(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, act: int =
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N
     ldr = residual.stride(0) if residual is not None else 0
+    nat.NEXT_META = 2.0 * M * N * K
     nat.call("agb_gemm_bf16", nat.ptr(a), a.stride(0), 1 if a_mn else 0, nat.ptr(w), w.stride(0), 1 if w_mn else 0,
              M, N, K, float(alpha), nat.ptr(bias), act, nat.ptr(res_bf16), nat.ptr(res_f32), ldr, res_group, res_rows,
              nat.ptr(out), out.stride(0), 1 if out.dtype == torch.float32 else 0, nat.stream())
@@ -202,6 +203,7 @@ def masked_attention(qkv: Tensor, packed_mask: Tensor, T: int, heads: int, mode:
     ctx = torch.empty((rows * T, H), dtype=qkv.dtype, device=qkv.device)
     tc_ok = qkv.dtype == torch.bfloat16 and H == heads * 64 and T <= 256 and not force_simt
     if tc_ok:
+        nat.NEXT_META = 4.0 * rows * T * T * H
         nat.call("agb_masked_attention_bf16", nat.ptr(qkv), nat.ptr(packed_mask), words, rows, T, H, heads, mode,
                  nat.ptr(ctx), nat.stream())
     else:

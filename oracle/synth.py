@@ -138,9 +138,11 @@ def _init_one(name: str, shape: Tuple[int, ...], seed: int) -> np.ndarray:
     if leaf == "bias":
         return (0.1 * u).astype(np.float32)
     if "embeddings" in name and len(shape) in (2, 3) and "projection" not in name:
-        return (0.5 * u).astype(np.float32)  # cls/pos/word/type tables
+        # cls/pos/word/type tables: unit variance like the reference's randn / nn.Embedding initialisers
+        return (np.float32(np.sqrt(3.0)) * u).astype(np.float32)
+    # nn.Linear / nn.Conv2d default initialiser of the reference's constructors: U(-1/sqrt(fan_in), 1/sqrt(fan_in))
     fan_in = int(np.prod(shape[1:]))
-    return (u * (1.7 / np.sqrt(fan_in))).astype(np.float32)
+    return (u * (1.0 / np.sqrt(fan_in))).astype(np.float32)
 
 
 def make_state_dict(shapes: List[Tuple[str, Tuple[int, ...]]], seed: int = 0) -> Dict[str, np.ndarray]:
