@@ -1,0 +1,518 @@
+// Backward-pass kernels of explainer training (reference scripts/train_explainer.py:182-198 runs
+// autograd over models/vanilla_vit.py:102-130 / models/vanilla_bert.py:123-162; here the adjoints are
+// written out): GELU forward/backward, LayerNorm backward, bias (column-sum) gradients, masked-attention
+// backward and the embedding adjoints.  The four GEMMs per Linear (dgrad + wgrad) reuse the tcgen05
+// kernel through its MN-major operand modes, so these are the HBM-bound remainder plus the attention
+// adjoint (CUDA-core v1: no score matrix in HBM, no atomics, deterministic).
+#include "agb_common.cuh"
+
+namespace agb {
+
+// ------------------------------------------------------------------------------------------------
+// element access helpers (fp32 or bf16 storage, fp32 math)
+// ------------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float ld1(const T* p);
+template <> __device__ __forceinline__ float ld1<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ld1<bf16>(const bf16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void st1(T* p, float v);
+template <> __device__ __forceinline__ void st1<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void st1<bf16>(bf16* p, float v) { *p = __float2bfloat16(v); }
+
+template <typename T> __device__ __forceinline__ float4 ldv4(const T* p);
+template <> __device__ __forceinline__ float4 ldv4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float4 ldv4<bf16>(const bf16* p) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  return make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));
+}
+template <typename T> __device__ __forceinline__ void stv4(T* p, float4 v);
+template <> __device__ __forceinline__ void stv4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+template <> __device__ __forceinline__ void stv4<bf16>(bf16* p, float4 v) {
+  uint2 pk;
+  pk.x = pack_bf16x2(v.x, v.y);
+  pk.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = pk;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GELU (exact erf form) forward / backward, vectorised
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.3989422804014327f * expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+template <typename T>
+__global__ void gelu_fwd_kernel(const T* __restrict__ z, T* __restrict__ out, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = ldv4<T>(z + i * 4);
+  v.x = gelu_erf_exact(v.x); v.y = gelu_erf_exact(v.y); v.z = gelu_erf_exact(v.z); v.w = gelu_erf_exact(v.w);
+  stv4<T>(out + i * 4, v);
+}
+template <typename T>
+__global__ void gelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ z, T* __restrict__ dz, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 g = ldv4<T>(dy + i * 4);
+  const float4 v = ldv4<T>(z + i * 4);
+  stv4<T>(dz + i * 4, make_float4(g.x * gelu_grad(v.x), g.y * gelu_grad(v.y), g.z * gelu_grad(v.z), g.w * gelu_grad(v.w)));
+}
+
+int gelu_fwd(const void* z, void* out, long long n, int is_bf16, cudaStream_t st) {
+  AGB_REQUIRE(n >= 0 && (n % 4) == 0, "element count must be a multiple of 4");
+  if (n == 0) return AGB_OK;
+  AGB_REQUIRE(z && out, "null pointer");
+  const long long n4 = n / 4;
+  const int blocks = (int)((n4 + 255) / 256);
+  if (is_bf16) gelu_fwd_kernel<bf16><<<blocks, 256, 0, st>>>(static_cast<const bf16*>(z), static_cast<bf16*>(out), n4);
+  else gelu_fwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(z), static_cast<float*>(out), n4);
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+int gelu_bwd(const void* dy, const void* z, void* dz, long long n, int is_bf16, cudaStream_t st) {
+  AGB_REQUIRE(n >= 0 && (n % 4) == 0, "element count must be a multiple of 4");
+  if (n == 0) return AGB_OK;
+  AGB_REQUIRE(dy && z && dz, "null pointer");
+  const long long n4 = n / 4;
+  const int blocks = (int)((n4 + 255) / 256);
+  if (is_bf16) gelu_bwd_kernel<bf16><<<blocks, 256, 0, st>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(z), static_cast<bf16*>(dz), n4);
+  else gelu_bwd_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(dy), static_cast<const float*>(z), static_cast<float*>(dz), n4);
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums (bias gradients): out[n] (+)= sum_m Y[m, n].  Grid-stride over row slabs, fp32 atomics
+// per slab (a few hundred adds per column in total).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ y, long long ld, int M, int N, float* __restrict__ out) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= N) return;
+  const int rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int m0 = blockIdx.y * rows_per;
+  const int m1 = min(M, m0 + rows_per);
+  float s = 0.f;
+  for (int m = m0; m < m1; ++m) s += ld1<T>(y + (long long)m * ld + col);
+  if (m1 > m0) atomicAdd(out + col, s);
+}
+int colsum(const void* y, int is_bf16, long long ld, int M, int N, float* out, cudaStream_t st) {
+  AGB_REQUIRE(M >= 0 && N > 0, "shape");
+  if (M == 0) return AGB_OK;
+  AGB_REQUIRE(y && out, "null pointer");
+  dim3 grid((N + 127) / 128, M >= 4096 ? 64 : (M >= 256 ? 16 : 1));
+  if (is_bf16) colsum_kernel<bf16><<<grid, 128, 0, st>>>(static_cast<const bf16*>(y), ld, M, N, out);
+  else colsum_kernel<float><<<grid, 128, 0, st>>>(static_cast<const float*>(y), ld, M, N, out);
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward.  y = (x - mean) * rstd * gamma + beta
+//   dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma     (+ dres when given)
+//   dgamma += sum_rows dy * xhat,  dbeta += sum_rows dy
+// One warp per row for dx; per-CTA partial dgamma/dbeta in shared memory, then one atomic per column.
+// ------------------------------------------------------------------------------------------------
+template <typename TX, typename TDY>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const TX* __restrict__ x, const TDY* __restrict__ dy, const float* __restrict__ gamma,
+                     const float* __restrict__ dres, int rows, int H, float eps, float* __restrict__ dx,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ float sm[];
+  float* sg = sm;       // H
+  float* sb = sm + H;   // H
+  for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int row = blockIdx.x * nw + warp; row < rows; row += gridDim.x * nw) {
+    const TX* xr = x + (long long)row * H;
+    const TDY* gr = dy + (long long)row * H;
+    float s = 0.f;
+    for (int i = lane; i < H; i += 32) s += ld1<TX>(xr + i);
+    const float mean = warp_sum(s) / (float)H;
+    float ss = 0.f;
+    for (int i = lane; i < H; i += 32) { const float d = ld1<TX>(xr + i) - mean; ss += d * d; }
+    const float rstd = rsqrtf(warp_sum(ss) / (float)H + eps);
+    float a = 0.f, b = 0.f;
+    for (int i = lane; i < H; i += 32) {
+      const float xh = (ld1<TX>(xr + i) - mean) * rstd;
+      const float g = ld1<TDY>(gr + i) * gamma[i];
+      a += g;
+      b += g * xh;
+    }
+    a = warp_sum(a) / (float)H;
+    b = warp_sum(b) / (float)H;
+    for (int i = lane; i < H; i += 32) {
+      const float xh = (ld1<TX>(xr + i) - mean) * rstd;
+      const float d = ld1<TDY>(gr + i);
+      const float g = d * gamma[i];
+      float v = rstd * (g - a - xh * b);
+      if (dres) v += dres[(long long)row * H + i];
+      dx[(long long)row * H + i] = v;
+      atomicAdd(sg + i, d * xh);
+      atomicAdd(sb + i, d);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    if (dgamma) atomicAdd(dgamma + i, sg[i]);
+    if (dbeta) atomicAdd(dbeta + i, sb[i]);
+  }
+}
+
+int layernorm_bwd(const void* x, int x_bf16, const void* dy, int dy_bf16, const float* gamma, const float* dres,
+                  int rows, int H, float eps, float* dx, float* dgamma, float* dbeta, cudaStream_t st) {
+  AGB_REQUIRE(rows >= 0 && H > 0 && H <= 8192, "LayerNorm shape");
+  if (rows == 0) return AGB_OK;
+  AGB_REQUIRE(x && dy && gamma && dx, "null pointer");
+  const int blocks = min((rows + 7) / 8, 4 * sm_count());
+  const size_t smem = 2 * (size_t)H * sizeof(float);
+#define LNB(TX, TDY)                                                                                   \
+  layernorm_bwd_kernel<TX, TDY><<<blocks, 256, smem, st>>>(static_cast<const TX*>(x), static_cast<const TDY*>(dy), \
+                                                           gamma, dres, rows, H, eps, dx, dgamma, dbeta)
+  if (x_bf16 && dy_bf16) LNB(bf16, bf16);
+  else if (x_bf16) LNB(bf16, float);
+  else if (dy_bf16) LNB(float, bf16);
+  else LNB(float, float);
+#undef LNB
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Masked attention backward (CUDA cores, fp32 math, fp32|bf16 I/O), one CTA per (row, head), T <= 256.
+//   P = softmax(X), X_ij = m_j ? s_ij/sqrt(d) : 0 (mul0) | -inf (neginf);  O = P V
+//   dV_j = sum_i P_ij dO_i;  dP_ij = dO_i . V_j;  D_i = sum_j P_ij dP_ij
+//   dS_ij = m_j * P_ij (dP_ij - D_i) / sqrt(d);  dQ_i = sum_j dS_ij K_j;  dK_j = sum_i dS_ij Q_i
+// (a masked key's logit is the constant 0 in mul0 mode, so it passes no gradient to Q/K but its V row
+// still receives P_ij dO_i).  Pass A is query-owned (row statistics, dQ), pass B is key-owned (dK, dV)
+// and recomputes the scores — nothing T x T is stored and no atomics are needed.
+// ------------------------------------------------------------------------------------------------
+constexpr int AB_D = 64;
+constexpr int AB_LD = AB_D + 2;   // padded row pitch (bf16 elements) -> conflict-free row-per-lane reads
+
+template <typename TIO>
+__global__ void __launch_bounds__(256)
+attention_bwd_kernel(const TIO* __restrict__ qkv, const TIO* __restrict__ dctx, const uint32_t* __restrict__ mask,
+                     int words, int T, int H, int heads, int mode, TIO* __restrict__ dqkv) {
+  extern __shared__ uint8_t smraw[];
+  bf16* sQ = reinterpret_cast<bf16*>(smraw);
+  bf16* sK = sQ + T * AB_LD;
+  bf16* sV = sK + T * AB_LD;
+  bf16* sdO = sV + T * AB_LD;
+  float* lse = reinterpret_cast<float*>(sdO + T * AB_LD);  // T   (max + log-sum)
+  float* Dv = lse + T;                                      // T
+  float* strips = Dv + T;                                   // nw * 2 * T
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int row = blockIdx.x / heads, head = blockIdx.x % heads;
+  const long long base = (long long)row * T * 3 * H;
+  const uint32_t* mrow = mask + (long long)row * words;
+  const float scale = 0.125f;  // 1/sqrt(64)
+  // stage Q, K, V, dO (bf16 in smem; fp32 inputs are rounded here only for the staging of the bf16 path —
+  // the fp32 instantiation keeps a float copy instead, see sF below)
+  for (int e = threadIdx.x; e < T * AB_D; e += blockDim.x) {
+    const int t = e / AB_D, c = e % AB_D;
+    const TIO* p = qkv + base + (long long)t * 3 * H + head * AB_D + c;
+    sQ[t * AB_LD + c] = __float2bfloat16(ld1<TIO>(p));
+    sK[t * AB_LD + c] = __float2bfloat16(ld1<TIO>(p + H));
+    sV[t * AB_LD + c] = __float2bfloat16(ld1<TIO>(p + 2 * H));
+    sdO[t * AB_LD + c] = __float2bfloat16(ld1<TIO>(dctx + ((long long)row * T + t) * H + head * AB_D + c));
+  }
+  __syncthreads();
+  float* s0 = strips + warp * 2 * T;
+  float* s1 = s0 + T;
+  // ---------------- pass A: query-owned ----------------
+  for (int i = warp; i < T; i += nw) {
+    float mx = -INFINITY;
+    for (int j = lane; j < T; j += 32) {
+      float a = 0.f, b = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < AB_D; ++c) {
+        a = fmaf(__bfloat162float(sQ[i * AB_LD + c]), __bfloat162float(sK[j * AB_LD + c]), a);
+        b = fmaf(__bfloat162float(sdO[i * AB_LD + c]), __bfloat162float(sV[j * AB_LD + c]), b);
+      }
+      const uint32_t keep = (mrow[j >> 5] >> (j & 31)) & 1u;
+      float x = a * scale;
+      if (!keep) x = (mode == AGB_MASK_MUL0) ? 0.f : -INFINITY;
+      s0[j] = x;
+      s1[j] = b;
+      mx = fmaxf(mx, x);
+    }
+    mx = warp_max(mx);
+    float z = 0.f;
+    for (int j = lane; j < T; j += 32) z += expf(s0[j] - mx);
+    z = warp_sum(z);
+    const float l = mx + logf(z);
+    float dsum = 0.f;
+    for (int j = lane; j < T; j += 32) {
+      const float pj = expf(s0[j] - l);
+      dsum += pj * s1[j];
+      s0[j] = pj;
+    }
+    dsum = warp_sum(dsum);
+    if (lane == 0) { lse[i] = l; Dv[i] = dsum; }
+    __syncwarp();
+    // dS strip, then dQ_i[c] = sum_j dS_ij K_j[c]  (lanes over the head dim)
+    for (int j = lane; j < T; j += 32) {
+      const uint32_t keep = (mrow[j >> 5] >> (j & 31)) & 1u;
+      s0[j] = keep ? s0[j] * (s1[j] - dsum) * scale : 0.f;
+    }
+    __syncwarp();
+    float q0 = 0.f, q1 = 0.f;
+    for (int j = 0; j < T; ++j) {
+      const float ds = s0[j];
+      q0 = fmaf(ds, __bfloat162float(sK[j * AB_LD + lane]), q0);
+      q1 = fmaf(ds, __bfloat162float(sK[j * AB_LD + lane + 32]), q1);
+    }
+    TIO* dq = dqkv + base + (long long)i * 3 * H + head * AB_D;
+    st1<TIO>(dq + lane, q0);
+    st1<TIO>(dq + lane + 32, q1);
+    __syncwarp();
+  }
+  __syncthreads();
+  // ---------------- pass B: key-owned ----------------
+  for (int j = warp; j < T; j += nw) {
+    const uint32_t keep = (mrow[j >> 5] >> (j & 31)) & 1u;
+    for (int i = lane; i < T; i += 32) {
+      float a = 0.f, b = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < AB_D; ++c) {
+        a = fmaf(__bfloat162float(sQ[i * AB_LD + c]), __bfloat162float(sK[j * AB_LD + c]), a);
+        b = fmaf(__bfloat162float(sdO[i * AB_LD + c]), __bfloat162float(sV[j * AB_LD + c]), b);
+      }
+      float x = a * scale;
+      if (!keep) x = (mode == AGB_MASK_MUL0) ? 0.f : -INFINITY;
+      const float pij = expf(x - lse[i]);
+      s0[i] = pij;                                               // for dV
+      s1[i] = keep ? pij * (b - Dv[i]) * scale : 0.f;            // dS for dK
+    }
+    __syncwarp();
+    float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
+    for (int i = 0; i < T; ++i) {
+      const float pij = s0[i], ds = s1[i];
+      k0 = fmaf(ds, __bfloat162float(sQ[i * AB_LD + lane]), k0);
+      k1 = fmaf(ds, __bfloat162float(sQ[i * AB_LD + lane + 32]), k1);
+      v0 = fmaf(pij, __bfloat162float(sdO[i * AB_LD + lane]), v0);
+      v1 = fmaf(pij, __bfloat162float(sdO[i * AB_LD + lane + 32]), v1);
+    }
+    TIO* dk = dqkv + base + (long long)j * 3 * H + H + head * AB_D;
+    TIO* dv = dqkv + base + (long long)j * 3 * H + 2 * H + head * AB_D;
+    st1<TIO>(dk + lane, k0); st1<TIO>(dk + lane + 32, k1);
+    st1<TIO>(dv + lane, v0); st1<TIO>(dv + lane + 32, v1);
+    __syncwarp();
+  }
+}
+
+// fp32-exact variant: same algorithm with float staging (used by the fp32 verification mode).
+__global__ void __launch_bounds__(256)
+attention_bwd_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ dctx,
+                         const uint32_t* __restrict__ mask, int words, int T, int H, int heads, int mode,
+                         float* __restrict__ dqkv) {
+  extern __shared__ uint8_t smraw[];
+  constexpr int LD = AB_D + 1;
+  float* sQ = reinterpret_cast<float*>(smraw);
+  float* sK = sQ + T * LD;
+  float* sV = sK + T * LD;
+  float* sdO = sV + T * LD;
+  float* lse = sdO + T * LD;
+  float* Dv = lse + T;
+  float* strips = Dv + T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int row = blockIdx.x / heads, head = blockIdx.x % heads;
+  const long long base = (long long)row * T * 3 * H;
+  const uint32_t* mrow = mask + (long long)row * words;
+  const float scale = 0.125f;
+  for (int e = threadIdx.x; e < T * AB_D; e += blockDim.x) {
+    const int t = e / AB_D, c = e % AB_D;
+    const float* p = qkv + base + (long long)t * 3 * H + head * AB_D + c;
+    sQ[t * LD + c] = p[0];
+    sK[t * LD + c] = p[H];
+    sV[t * LD + c] = p[2 * H];
+    sdO[t * LD + c] = dctx[((long long)row * T + t) * H + head * AB_D + c];
+  }
+  __syncthreads();
+  float* s0 = strips + warp * 2 * T;
+  float* s1 = s0 + T;
+  for (int i = warp; i < T; i += nw) {
+    float mx = -INFINITY;
+    for (int j = lane; j < T; j += 32) {
+      float a = 0.f, b = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < AB_D; ++c) {
+        a = fmaf(sQ[i * LD + c], sK[j * LD + c], a);
+        b = fmaf(sdO[i * LD + c], sV[j * LD + c], b);
+      }
+      const uint32_t keep = (mrow[j >> 5] >> (j & 31)) & 1u;
+      float x = a * scale;
+      if (!keep) x = (mode == AGB_MASK_MUL0) ? 0.f : -INFINITY;
+      s0[j] = x; s1[j] = b;
+      mx = fmaxf(mx, x);
+    }
+    mx = warp_max(mx);
+    float z = 0.f;
+    for (int j = lane; j < T; j += 32) z += expf(s0[j] - mx);
+    z = warp_sum(z);
+    const float l = mx + logf(z);
+    float dsum = 0.f;
+    for (int j = lane; j < T; j += 32) {
+      const float pj = expf(s0[j] - l);
+      dsum += pj * s1[j];
+      s0[j] = pj;
+    }
+    dsum = warp_sum(dsum);
+    if (lane == 0) { lse[i] = l; Dv[i] = dsum; }
+    __syncwarp();
+    for (int j = lane; j < T; j += 32) {
+      const uint32_t keep = (mrow[j >> 5] >> (j & 31)) & 1u;
+      s0[j] = keep ? s0[j] * (s1[j] - dsum) * scale : 0.f;
+    }
+    __syncwarp();
+    float q0 = 0.f, q1 = 0.f;
+    for (int j = 0; j < T; ++j) {
+      const float ds = s0[j];
+      q0 = fmaf(ds, sK[j * LD + lane], q0);
+      q1 = fmaf(ds, sK[j * LD + lane + 32], q1);
+    }
+    float* dq = dqkv + base + (long long)i * 3 * H + head * AB_D;
+    dq[lane] = q0; dq[lane + 32] = q1;
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int j = warp; j < T; j += nw) {
+    const uint32_t keep = (mrow[j >> 5] >> (j & 31)) & 1u;
+    for (int i = lane; i < T; i += 32) {
+      float a = 0.f, b = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < AB_D; ++c) {
+        a = fmaf(sQ[i * LD + c], sK[j * LD + c], a);
+        b = fmaf(sdO[i * LD + c], sV[j * LD + c], b);
+      }
+      float x = a * scale;
+      if (!keep) x = (mode == AGB_MASK_MUL0) ? 0.f : -INFINITY;
+      const float pij = expf(x - lse[i]);
+      s0[i] = pij;
+      s1[i] = keep ? pij * (b - Dv[i]) * scale : 0.f;
+    }
+    __syncwarp();
+    float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
+    for (int i = 0; i < T; ++i) {
+      const float pij = s0[i], ds = s1[i];
+      k0 = fmaf(ds, sQ[i * LD + lane], k0);
+      k1 = fmaf(ds, sQ[i * LD + lane + 32], k1);
+      v0 = fmaf(pij, sdO[i * LD + lane], v0);
+      v1 = fmaf(pij, sdO[i * LD + lane + 32], v1);
+    }
+    float* dk = dqkv + base + (long long)j * 3 * H + H + head * AB_D;
+    float* dv = dqkv + base + (long long)j * 3 * H + 2 * H + head * AB_D;
+    dk[lane] = k0; dk[lane + 32] = k1;
+    dv[lane] = v0; dv[lane + 32] = v1;
+    __syncwarp();
+  }
+}
+
+int attention_bwd(const void* qkv, const void* dctx, int io_bf16, const uint32_t* mask, int words, int rows, int T,
+                  int H, int heads, int mode, void* dqkv, cudaStream_t st) {
+  AGB_REQUIRE(rows >= 0 && T > 0 && heads > 0 && H == heads * AB_D, "attention backward needs head dim 64");
+  AGB_REQUIRE(words * 32 >= T, "mask words");
+  AGB_REQUIRE(mode == AGB_MASK_MUL0 || mode == AGB_MASK_NEGINF, "mask mode");
+  if (T > 256) {
+    set_last_error("agb_masked_attention_bwd supports T <= 256 (got %d)", T);
+    return AGB_ERR_UNSUPPORTED;
+  }
+  if (rows == 0) return AGB_OK;
+  AGB_REQUIRE(qkv && dctx && mask && dqkv, "null pointer");
+  const int nw = 8;
+  if (io_bf16) {
+    const size_t smem = (size_t)4 * T * AB_LD * 2 + (size_t)2 * T * 4 + (size_t)nw * 2 * T * 4;
+    AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attention_bwd_kernel<bf16><<<rows * heads, nw * 32, smem, st>>>(static_cast<const bf16*>(qkv), static_cast<const bf16*>(dctx),
+                                                                    mask, words, T, H, heads, mode, static_cast<bf16*>(dqkv));
+  } else {
+    const size_t smem = (size_t)4 * T * (AB_D + 1) * 4 + (size_t)2 * T * 4 + (size_t)nw * 2 * T * 4;
+    AGB_REQUIRE(smem <= 227 * 1024, "T too large for the fp32 attention backward (<= 200)");
+    AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attention_bwd_f32_kernel<<<rows * heads, nw * 32, smem, st>>>(static_cast<const float*>(qkv), static_cast<const float*>(dctx),
+                                                                  mask, words, T, H, heads, mode, static_cast<float*>(dqkv));
+  }
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// embedding adjoints
+// ------------------------------------------------------------------------------------------------
+// ViT (reference models/vanilla_vit.py:242-253): dpos[t] += sum_b dx[b,t]; dcls += sum_b dx[b,0];
+// dpatch[b,p] = dx[b,1+p] (fp32 or bf16, feeds the patch-projection wgrad GEMM).
+template <typename TOut>
+__global__ void vit_embed_bwd_kernel(const float* __restrict__ dx, int B, int T, int H, float* __restrict__ dpos,
+                                     float* __restrict__ dcls, TOut* __restrict__ dpatch) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)T * H) return;
+  const int t = (int)(gid / H), c = (int)(gid % H);
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float v = dx[((long long)b * T + t) * H + c];
+    s += v;
+    if (t > 0) st1<TOut>(dpatch + ((long long)b * (T - 1) + (t - 1)) * H + c, v);
+  }
+  dpos[gid] += s;
+  if (t == 0) dcls[c] += s;
+}
+int vit_embed_bwd(const float* dx, int B, int T, int H, float* dpos, float* dcls, void* dpatch, int dpatch_bf16,
+                  cudaStream_t st) {
+  AGB_REQUIRE(B > 0 && T > 1 && H > 0, "shape");
+  AGB_REQUIRE(dx && dpos && dcls && dpatch, "null pointer");
+  const long long n = (long long)T * H;
+  const int blocks = (int)((n + 255) / 256);
+  if (dpatch_bf16) vit_embed_bwd_kernel<bf16><<<blocks, 256, 0, st>>>(dx, B, T, H, dpos, dcls, static_cast<bf16*>(dpatch));
+  else vit_embed_bwd_kernel<float><<<blocks, 256, 0, st>>>(dx, B, T, H, dpos, dcls, static_cast<float*>(dpatch));
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+// BERT (reference models/vanilla_bert.py:307-325): the embedding LayerNorm adjoint is layernorm_bwd on the
+// recomputed pre-norm sum; this kernel rebuilds that sum (fwd) and scatters its gradient (bwd).
+__global__ void bert_embed_sum_kernel(const int64_t* __restrict__ ids, const float* __restrict__ word,
+                                      const float* __restrict__ pos, const float* __restrict__ type0, int BT, int T,
+                                      int H, int vocab, float* __restrict__ out) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)BT * H) return;
+  const int tok = (int)(gid / H), c = (int)(gid % H);
+  long long id = ids[tok];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  out[gid] = (word[id * H + c] + type0[c]) + pos[(long long)(tok % T) * H + c];
+}
+__global__ void bert_embed_scatter_kernel(const int64_t* __restrict__ ids, const float* __restrict__ dsum, int BT,
+                                          int T, int H, int vocab, int pad_id, float* __restrict__ dword,
+                                          float* __restrict__ dpos, float* __restrict__ dtype0) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)BT * H) return;
+  const int tok = (int)(gid / H), c = (int)(gid % H);
+  long long id = ids[tok];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const float g = dsum[gid];
+  if (id != pad_id) atomicAdd(dword + id * H + c, g);   // nn.Embedding(padding_idx): no gradient for [PAD]
+  atomicAdd(dpos + (long long)(tok % T) * H + c, g);
+  atomicAdd(dtype0 + c, g);
+}
+int bert_embed_sum(const int64_t* ids, const float* word, const float* pos, const float* type0, int BT, int T, int H,
+                   int vocab, float* out, cudaStream_t st) {
+  AGB_REQUIRE(BT > 0 && T > 0 && H > 0, "shape");
+  AGB_REQUIRE(ids && word && pos && type0 && out, "null pointer");
+  const long long n = (long long)BT * H;
+  bert_embed_sum_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(ids, word, pos, type0, BT, T, H, vocab, out);
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+int bert_embed_scatter(const int64_t* ids, const float* dsum, int BT, int T, int H, int vocab, int pad_id,
+                       float* dword, float* dpos, float* dtype0, cudaStream_t st) {
+  AGB_REQUIRE(BT > 0 && T > 0 && H > 0, "shape");
+  AGB_REQUIRE(ids && dsum && dword && dpos && dtype0, "null pointer");
+  const long long n = (long long)BT * H;
+  bert_embed_scatter_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(ids, dsum, BT, T, H, vocab, pad_id, dword, dpos, dtype0);
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+}  // namespace agb
