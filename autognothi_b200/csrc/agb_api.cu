@@ -10,8 +10,21 @@ int gemm_bf16_tc(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b
                  int K, float alpha, const float* bias, int act, const bf16* res_bf16,
                  const float* res_f32, int ldr, int res_group, int res_rows, void* out, int ldo,
                  int out_f32, cudaStream_t stream);
-int gemm_f32(const float* A, int lda, const float* B, int ldb, int M, int N, int K, float alpha,
+int gemm_f32(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, int M, int N, int K, float alpha,
              const float* bias, int act, const float* res, int ldr, float* C, int ldc, cudaStream_t st);
+int gelu_fwd(const void* z, void* out, long long n, int is_bf16, cudaStream_t st);
+int gelu_bwd(const void* dy, const void* z, void* dz, long long n, int is_bf16, cudaStream_t st);
+int colsum(const void* y, int is_bf16, long long ld, int M, int N, float* out, cudaStream_t st);
+int layernorm_bwd(const void* x, int x_bf16, const void* dy, int dy_bf16, const float* gamma, const float* dres,
+                  int rows, int H, float eps, float* dx, float* dgamma, float* dbeta, cudaStream_t st);
+int attention_bwd(const void* qkv, const void* dctx, int io_bf16, const uint32_t* mask, int words, int rows, int T,
+                  int H, int heads, int mode, void* dqkv, cudaStream_t st);
+int vit_embed_bwd(const float* dx, int B, int T, int H, float* dpos, float* dcls, void* dpatch, int dpatch_bf16,
+                  cudaStream_t st);
+int bert_embed_sum(const int64_t* ids, const float* word, const float* pos, const float* type0, int BT, int T, int H,
+                   int vocab, float* out, cudaStream_t st);
+int bert_embed_scatter(const int64_t* ids, const float* dsum, int BT, int T, int H, int vocab, int pad_id,
+                       float* dword, float* dpos, float* dtype0, cudaStream_t st);
 int pack_masks_i64(const int64_t* mask, int rows, int n, int prepend_cls, uint32_t* packed, int words,
                    cudaStream_t st);
 int unpack_masks_i64(const uint32_t* packed, int rows, int n, int skip, int words, int64_t* out,
@@ -71,10 +84,41 @@ int agb_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb
 }
 
 
-int agb_gemm_f32(const float* A, int lda, const float* B, int ldb, int M, int N, int K, float alpha,
-                 const float* bias, int act, const float* residual, int ldr, float* C, int ldc,
-                 void* stream) {
-  return agb::gemm_f32(A, lda, B, ldb, M, N, K, alpha, bias, act, residual, ldr, C, ldc, ST(stream));
+int agb_gemm_f32(const float* A, int lda, int a_mn_major, const float* B, int ldb, int b_mn_major, int M, int N,
+                 int K, float alpha, const float* bias, int act, const float* residual, int ldr, float* C,
+                 int ldc, void* stream) {
+  return agb::gemm_f32(A, lda, a_mn_major, B, ldb, b_mn_major, M, N, K, alpha, bias, act, residual, ldr, C, ldc,
+                       ST(stream));
+}
+int agb_gelu_fwd(const void* z, void* out, long long n, int is_bf16, void* stream) {
+  return agb::gelu_fwd(z, out, n, is_bf16, ST(stream));
+}
+int agb_gelu_bwd(const void* dy, const void* z, void* dz, long long n, int is_bf16, void* stream) {
+  return agb::gelu_bwd(dy, z, dz, n, is_bf16, ST(stream));
+}
+int agb_colsum(const void* y, int is_bf16, long long ld, int M, int N, float* out, void* stream) {
+  return agb::colsum(y, is_bf16, ld, M, N, out, ST(stream));
+}
+int agb_layernorm_bwd(const void* x, int x_is_bf16, const void* dy, int dy_is_bf16, const float* gamma,
+                      const float* dres, int rows, int H, float eps, float* dx, float* dgamma, float* dbeta,
+                      void* stream) {
+  return agb::layernorm_bwd(x, x_is_bf16, dy, dy_is_bf16, gamma, dres, rows, H, eps, dx, dgamma, dbeta, ST(stream));
+}
+int agb_masked_attention_bwd(const void* qkv, const void* dctx, int io_is_bf16, const uint32_t* mask, int words,
+                             int rows, int T, int H, int heads, int mode, void* dqkv, void* stream) {
+  return agb::attention_bwd(qkv, dctx, io_is_bf16, mask, words, rows, T, H, heads, mode, dqkv, ST(stream));
+}
+int agb_vit_embed_bwd(const float* dx, int B, int T, int H, float* dpos, float* dcls, void* dpatch,
+                      int dpatch_is_bf16, void* stream) {
+  return agb::vit_embed_bwd(dx, B, T, H, dpos, dcls, dpatch, dpatch_is_bf16, ST(stream));
+}
+int agb_bert_embed_sum(const int64_t* ids, const float* word, const float* pos, const float* type0, int BT, int T,
+                       int H, int vocab, float* out, void* stream) {
+  return agb::bert_embed_sum(ids, word, pos, type0, BT, T, H, vocab, out, ST(stream));
+}
+int agb_bert_embed_scatter(const int64_t* ids, const float* dsum, int BT, int T, int H, int vocab, int pad_id,
+                           float* dword, float* dpos, float* dtype0, void* stream) {
+  return agb::bert_embed_scatter(ids, dsum, BT, T, H, vocab, pad_id, dword, dpos, dtype0, ST(stream));
 }
 int agb_pack_masks_i64(const int64_t* mask, int rows, int n_players, int prepend_cls,
                        uint32_t* packed, int words, void* stream) {

@@ -12,8 +12,8 @@ namespace agb {
 // 64x64 tile, 16x16 threads, 4x4 outputs per thread, K tiles of 16 staged in shared memory.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-gemm_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int M, int N,
-                int K, float alpha, const float* __restrict__ bias, int act,
+gemm_f32_kernel(const float* __restrict__ A, int lda, int a_mn, const float* __restrict__ B, int ldb, int b_mn,
+                int M, int N, int K, float alpha, const float* __restrict__ bias, int act,
                 const float* __restrict__ res, int ldr, float* __restrict__ C, int ldc) {
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
@@ -31,8 +31,8 @@ gemm_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
       const int e = threadIdx.x + i * 256;
       const int r = e >> 4, kk = e & 15;
       const int gm = m0 + r, gn = n0 + r, gk = k0 + kk;
-      As[kk][r] = (gm < M && gk < K) ? A[(long long)gm * lda + gk] : 0.f;
-      Bs[kk][r] = (gn < N && gk < K) ? B[(long long)gn * ldb + gk] : 0.f;
+      As[kk][r] = (gm < M && gk < K) ? (a_mn ? A[(long long)gk * lda + gm] : A[(long long)gm * lda + gk]) : 0.f;
+      Bs[kk][r] = (gn < N && gk < K) ? (b_mn ? B[(long long)gk * ldb + gn] : B[(long long)gn * ldb + gk]) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -64,14 +64,14 @@ gemm_f32_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
   }
 }
 
-int gemm_f32(const float* A, int lda, const float* B, int ldb, int M, int N, int K, float alpha,
+int gemm_f32(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, int M, int N, int K, float alpha,
              const float* bias, int act, const float* res, int ldr, float* C, int ldc, cudaStream_t st) {
   AGB_REQUIRE(M >= 0 && N > 0 && K > 0, "GEMM shape");
   if (M == 0) return AGB_OK;
   AGB_REQUIRE(A && B && C, "null pointer");
   dim3 grid((N + 63) / 64, (M + 63) / 64);
   AGB_REQUIRE(grid.y <= 65535, "M too large for the fp32 verification GEMM (chunk the rows)");
-  gemm_f32_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, M, N, K, alpha, bias, act, res, ldr, C, ldc);
+  gemm_f32_kernel<<<grid, 256, 0, st>>>(A, lda, a_mn, B, ldb, b_mn, M, N, K, alpha, bias, act, res, ldr, C, ldc);
   AGB_CHECK_CUDA(cudaGetLastError());
   return AGB_OK;
 }

@@ -109,20 +109,22 @@ def gemm_bf16(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, act: int =
 
 
 def gemm_f32(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, act: int = ACT_NONE,
-             residual: Optional[Tensor] = None, out: Optional[Tensor] = None, alpha: float = 1.0) -> Tensor:
+             residual: Optional[Tensor] = None, out: Optional[Tensor] = None, alpha: float = 1.0,
+             a_mn: bool = False, w_mn: bool = False) -> Tensor:
     assert a.dtype == torch.float32 and w.dtype == torch.float32 and a.stride(1) == 1 and w.stride(1) == 1
-    M, K = a.shape
-    N = w.shape[0]
-    assert w.shape[1] == K
+    M, K = (a.shape[1], a.shape[0]) if a_mn else a.shape
+    N, Kw = (w.shape[1], w.shape[0]) if w_mn else w.shape
+    assert K == Kw
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=a.device)
     step = 65535 * 64
     for m0 in range(0, M, step):
         m1 = min(M, m0 + step)
         r = residual[m0:m1] if residual is not None else None
-        nat.call("agb_gemm_f32", nat.ptr(a[m0:m1]), a.stride(0), nat.ptr(w), w.stride(0), m1 - m0, N, K, float(alpha),
-                 nat.ptr(bias), act, nat.ptr(r), r.stride(0) if r is not None else 0, nat.ptr(out[m0:m1]),
-                 out.stride(0), nat.stream())
+        a_sub = a[:, m0:m1] if a_mn else a[m0:m1]
+        nat.call("agb_gemm_f32", nat.ptr(a_sub), a.stride(0), 1 if a_mn else 0, nat.ptr(w), w.stride(0),
+                 1 if w_mn else 0, m1 - m0, N, K, float(alpha), nat.ptr(bias), act, nat.ptr(r),
+                 r.stride(0) if r is not None else 0, nat.ptr(out[m0:m1]), out.stride(0), nat.stream())
     return out
 
 
@@ -273,3 +275,80 @@ def shapley_loss_bwd(packed: Tensor, resid: Tensor, grad_out: Optional[Tensor], 
     nat.call("agb_shapley_loss_bwd", nat.ptr(_c(packed)), packed.shape[1], nat.ptr(resid), nat.ptr(g), B, S, n, C,
              nat.ptr(dphi), nat.stream())
     return dphi
+
+
+# ------------------------------------------------------------------------------------------------
+# training adjoints
+# ------------------------------------------------------------------------------------------------
+def _is_bf16(t: Tensor) -> int:
+    assert t.dtype in (torch.float32, torch.bfloat16)
+    return 1 if t.dtype == torch.bfloat16 else 0
+
+
+def gelu_fwd(z: Tensor) -> Tensor:
+    z = _c(z)
+    out = torch.empty_like(z)
+    nat.call("agb_gelu_fwd", nat.ptr(z), nat.ptr(out), z.numel(), _is_bf16(z), nat.stream())
+    return out
+
+
+def gelu_bwd(dy: Tensor, z: Tensor) -> Tensor:
+    dy, z = _c(dy), _c(z)
+    assert dy.dtype == z.dtype and dy.shape == z.shape
+    dz = torch.empty_like(z)
+    nat.call("agb_gelu_bwd", nat.ptr(dy), nat.ptr(z), nat.ptr(dz), z.numel(), _is_bf16(z), nat.stream())
+    return dz
+
+
+def colsum_into(y: Tensor, out: Tensor) -> None:
+    """out[n] += sum_m y[m, n]   (bias gradients)"""
+    assert y.dim() == 2 and y.stride(1) == 1 and out.dtype == torch.float32 and out.numel() == y.shape[1]
+    nat.call("agb_colsum", nat.ptr(y), _is_bf16(y), y.stride(0), y.shape[0], y.shape[1], nat.ptr(out), nat.stream())
+
+
+def layernorm_bwd(x: Tensor, dy: Tensor, gamma: Tensor, eps: float, dres: Optional[Tensor], dgamma: Optional[Tensor],
+                  dbeta: Optional[Tensor]) -> Tensor:
+    x, dy = _c(x), _c(dy)
+    rows, H = x.shape
+    dx = torch.empty((rows, H), dtype=torch.float32, device=x.device)
+    if dres is not None:
+        assert dres.dtype == torch.float32 and dres.is_contiguous()
+    nat.call("agb_layernorm_bwd", nat.ptr(x), _is_bf16(x), nat.ptr(dy), _is_bf16(dy), nat.ptr(gamma), nat.ptr(dres), rows, H,
+             float(eps), nat.ptr(dx), nat.ptr(dgamma), nat.ptr(dbeta), nat.stream())
+    return dx
+
+
+def masked_attention_bwd(qkv: Tensor, dctx: Tensor, packed_mask: Tensor, T: int, heads: int, mode: int) -> Tensor:
+    qkv, dctx = _c(qkv), _c(dctx)
+    assert qkv.dtype == dctx.dtype
+    rows = qkv.shape[0] // T
+    H = qkv.shape[1] // 3
+    dqkv = torch.empty_like(qkv)
+    nat.call("agb_masked_attention_bwd", nat.ptr(qkv), nat.ptr(dctx), _is_bf16(qkv), nat.ptr(packed_mask),
+             packed_mask.shape[1], rows, T, H, heads, mode, nat.ptr(dqkv), nat.stream())
+    return dqkv
+
+
+def vit_embed_bwd(dx: Tensor, B: int, T: int, H: int, dpos: Tensor, dcls: Tensor, patch_dtype) -> Tensor:
+    dpatch = torch.empty((B * (T - 1), H), dtype=patch_dtype, device=dx.device)
+    nat.call("agb_vit_embed_bwd", nat.ptr(_c(dx)), B, T, H, nat.ptr(dpos), nat.ptr(dcls), nat.ptr(dpatch),
+             1 if patch_dtype == torch.bfloat16 else 0, nat.stream())
+    return dpatch
+
+
+def bert_embed_sum(ids: Tensor, word: Tensor, pos: Tensor, type0: Tensor) -> Tensor:
+    ids = _c(ids)
+    B, T = ids.shape
+    H = word.shape[1]
+    out = torch.empty((B * T, H), dtype=torch.float32, device=ids.device)
+    nat.call("agb_bert_embed_sum", nat.ptr(ids), nat.ptr(word), nat.ptr(pos), nat.ptr(type0), B * T, T, H, word.shape[0],
+             nat.ptr(out), nat.stream())
+    return out
+
+
+def bert_embed_scatter(ids: Tensor, dsum: Tensor, pad_id: int, dword: Tensor, dpos: Tensor, dtype0: Tensor) -> None:
+    ids = _c(ids)
+    B, T = ids.shape
+    H = dword.shape[1]
+    nat.call("agb_bert_embed_scatter", nat.ptr(ids), nat.ptr(_c(dsum)), B * T, T, H, dword.shape[0], pad_id, nat.ptr(dword),
+             nat.ptr(dpos), nat.ptr(dtype0), nat.stream())

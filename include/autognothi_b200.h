@@ -52,9 +52,9 @@ int agb_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb
 
 /* fp32 CUDA-core GEMM with the same epilogue — the "exact" verification mode (fp32 rtol 1e-4 gate
  * of BASELINE.json).  A [M,K], B [N,K], C [M,N] row-major fp32. */
-int agb_gemm_f32(const float* A, int lda, const float* B, int ldb, int M, int N, int K, float alpha,
-                 const float* bias, int act, const float* residual, int ldr, float* C, int ldc,
-                 void* stream);
+int agb_gemm_f32(const float* A, int lda, int a_mn_major, const float* B, int ldb, int b_mn_major, int M, int N,
+                 int K, float alpha, const float* bias, int act, const float* residual, int ldr, float* C,
+                 int ldc, void* stream);
 
 /* ---- coalition masks (reference models/shapley.py:56-79,109-115,131-135; recipes/vanilla_vit.py:
  *      219-224) ------------------------------------------------------------------------------- */
@@ -140,6 +140,32 @@ int agb_shapley_loss_fwd(const uint32_t* packed, int words, const float* v0, con
 int agb_shapley_loss_bwd(const uint32_t* packed, int words, const float* resid,
                          const float* grad_out, int B, int S, int n_players, int C, float* dphi,
                          void* stream);
+
+/* ---- explainer training: adjoints (the reference relies on torch autograd over models/vanilla_vit.py:
+ *      102-130 / models/vanilla_bert.py:123-162 inside scripts/train_explainer.py:182-198) ------------- */
+/* exact-erf GELU (nn.GELU(), reference models/vanilla_vit.py:488) forward and backward, fp32 or bf16 */
+int agb_gelu_fwd(const void* z, void* out, long long n, int is_bf16, void* stream);
+int agb_gelu_bwd(const void* dy, const void* z, void* dz, long long n, int is_bf16, void* stream);
+/* bias gradient of an nn.Linear: out[n] += sum_m Y[m,n] */
+int agb_colsum(const void* y, int is_bf16, long long ld, int M, int N, float* out, void* stream);
+/* nn.LayerNorm adjoint: dx = dres + dLN(dy); dgamma/dbeta ACCUMULATED (nullable) */
+int agb_layernorm_bwd(const void* x, int x_is_bf16, const void* dy, int dy_is_bf16, const float* gamma,
+                      const float* dres, int rows, int H, float eps, float* dx, float* dgamma, float* dbeta,
+                      void* stream);
+/* adjoint of the key-masked attention (reference models/vanilla_vit.py:436-465, vanilla_bert.py:503-537):
+ * qkv (rows,T,3H), dctx (rows,T,H) -> dqkv (rows,T,3H); head dim 64, T <= 256; a ViT-masked key passes no
+ * gradient to Q/K (its logit is the constant 0) but its V row still receives P^T dO. */
+int agb_masked_attention_bwd(const void* qkv, const void* dctx, int io_is_bf16, const uint32_t* mask, int words,
+                             int rows, int T, int H, int heads, int mode, void* dqkv, void* stream);
+/* ViT embedding adjoint (reference models/vanilla_vit.py:242-253): dpos/dcls ACCUMULATED, dpatch (B*(T-1),H) */
+int agb_vit_embed_bwd(const float* dx, int B, int T, int H, float* dpos, float* dcls, void* dpatch,
+                      int dpatch_is_bf16, void* stream);
+/* BERT embedding pre-LayerNorm sum and its scatter adjoint (reference models/vanilla_bert.py:307-325;
+ * the padding_idx row of word_embeddings receives no gradient) */
+int agb_bert_embed_sum(const int64_t* ids, const float* word, const float* pos, const float* type0, int BT, int T,
+                       int H, int vocab, float* out, void* stream);
+int agb_bert_embed_scatter(const int64_t* ids, const float* dsum, int BT, int T, int H, int vocab, int pad_id,
+                           float* dword, float* dpos, float* dtype0, void* stream);
 
 #ifdef __cplusplus
 }

@@ -161,7 +161,52 @@ def gen_models():
         json.dump(keys, f, indent=0, sort_keys=True)
 
 
+def gen_train_grads():
+    """One explainer training step's loss and parameter gradients from the reference's autograd
+    (scripts/train_explainer.py:182-197 semantics), in eval() mode so that dropout is the identity."""
+    for name, B, S in [("vit_mini", 2, 4), ("vit_mini_px64", 3, 4), ("bert_mini", 3, 4)]:
+        cfg = ocfg.get_config(name)
+        vit = ocfg.is_vit(cfg)
+        n = ocfg.n_players(cfg)
+        if vit:
+            rcfg = ref_vit.VanillaViTConfig(**cfg)
+            srg, exp, rec = ref_vit.VanillaViTSurrogate(rcfg), ref_vit.VanillaViTExplainer(rcfg), ref_rvit
+        else:
+            rcfg = ref_bert.VanillaBertConfig(**cfg)
+            srg, exp, rec = ref_bert.VanillaBertSurrogate(rcfg), ref_bert.VanillaBertExplainer(rcfg), ref_rbert
+        srg.load_state_dict(to_torch_state(synth.surrogate_state(cfg, seed=0)), strict=True)
+        exp.load_state_dict(to_torch_state(synth.explainer_state(cfg, seed=1)), strict=True)
+        srg.eval(); exp.eval()
+        g = np.load(os.path.join(HERE, f"model_{name}.npz"))
+        masks = torch.from_numpy(g["masks"].astype(np.int64))
+        xs = torch.from_numpy(synth.inputs(cfg, B, seed=0))
+        v_s, grand, null = (torch.from_numpy(g[k]) for k in ("v_s", "grand", "null"))
+        ones = torch.ones((B, n), dtype=torch.long)
+        with torch.enable_grad():
+            for p_ in exp.parameters():
+                p_.requires_grad_(True)
+            phi, _ = rec._fw_explainer(exp, xs, ones, grand, null)
+            loss = ref_shapley.loss_shapley_new(B, S, n, masks.reshape(B, S, n), null, v_s, grand, phi)
+            loss.backward()
+        out = {"loss": loss.detach().numpy()}
+        norms = {}
+        for k, p_ in exp.named_parameters():
+            gr = p_.grad
+            norms[k] = float(gr.norm()) if gr is not None else 0.0
+            if gr is not None and (gr.numel() <= 1024 or "layers.0.attention.self.query.weight" in k
+                                   or "explainer_attn.0.output.dense.weight" in k):
+                out["grad::" + k] = gr.numpy()
+        out["norm_names"] = np.array(list(norms.keys()))
+        out["norm_values"] = np.array(list(norms.values()), dtype=np.float64)
+        np.savez_compressed(os.path.join(HERE, f"train_{name}.npz"), **out)
+        print(f"train_{name}.npz loss={float(loss):.6f} params={len(norms)} stored={len(out) - 3}")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "train":
+        gen_train_grads()
+        sys.exit(0)
     gen_sampler()
     gen_shapley_math()
     gen_models()
+    gen_train_grads()

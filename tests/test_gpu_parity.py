@@ -356,3 +356,82 @@ def test_reference_checkpoint_roundtrip(agb, golden_dir):
         _, _, srg, exp = _build(name, "fp32")
         assert {k: list(v.shape) for k, v in srg.state_dict().items()} == ref[name]["surrogate"]
         assert {k: list(v.shape) for k, v in exp.state_dict().items()} == ref[name]["explainer"]
+
+
+# ------------------------------------------------------------------------------------------------
+# explainer training: loss.backward() through the hand-written adjoints vs the reference's autograd
+# ------------------------------------------------------------------------------------------------
+def _train_step_grads(golden_dir, name, precision):
+    from autognothi_b200.models import shapley as ash
+    g = _load(golden_dir, f"model_{name}.npz")
+    B, S, n = (int(v) for v in g["meta"])
+    rec, cfgd, srg, exp = _build(name, precision)
+    exp.train()   # dropout is not applied on this path (p = 0); the golden ran the reference in eval()
+    xs = torch.from_numpy(synth.inputs(cfgd, B, seed=0)).to(DEV)
+    masks = torch.from_numpy(g["masks"].astype(np.int64)).to(DEV).reshape(B, S, n)
+    v_s, grand, null = (torch.from_numpy(g[k]).to(DEV) for k in ("v_s", "grand", "null"))
+    ones = torch.ones((B, n), dtype=torch.int64, device=DEV)
+    phi, _ = rec.fw_explainer(exp, xs, ones, grand, null)
+    assert phi.requires_grad
+    loss = ash.loss_shapley_new(B, S, n, masks, null, v_s, grand, phi)
+    loss.backward()
+    return exp, float(loss.detach())
+
+
+@pytest.mark.parametrize("name", ["vit_mini", "vit_mini_px64", "bert_mini"])
+def test_training_gradients_fp32_vs_reference_autograd(agb, golden_dir, name):
+    t = _load(golden_dir, f"train_{name}.npz")
+    exp, loss = _train_step_grads(golden_dir, name, "fp32")
+    np.testing.assert_allclose(loss, float(t["loss"]), rtol=1e-4)
+    ref_norms = dict(zip([str(s) for s in t["norm_names"]], t["norm_values"]))
+    params = dict(exp.named_parameters())
+    assert set(params) == set(ref_norms)
+    for k, p in params.items():
+        assert p.grad is not None, f"no gradient for {k}"
+        got = float(p.grad.norm())
+        assert abs(got - ref_norms[k]) <= 2e-3 * ref_norms[k] + 1e-6, f"{k}: |grad| {got} vs {ref_norms[k]}"
+    for key in t.files:
+        if key.startswith("grad::"):
+            k = key[len("grad::"):]
+            ref = t[key]
+            np.testing.assert_allclose(_np(params[k].grad), ref, rtol=2e-3, atol=2e-3 * np.abs(ref).max() + 1e-7, err_msg=k)
+
+
+@pytest.mark.parametrize("name", ["vit_mini", "bert_mini"])
+def test_training_gradients_bf16_tensor_cores(agb, golden_dir, name):
+    t = _load(golden_dir, f"train_{name}.npz")
+    exp, loss = _train_step_grads(golden_dir, name, "bf16")
+    assert abs(loss - float(t["loss"])) <= 2e-2 * abs(float(t["loss"]))
+    params = dict(exp.named_parameters())
+    for key in t.files:
+        if key.startswith("grad::"):
+            k = key[len("grad::"):]
+            ref, got = t[key].reshape(-1).astype(np.float64), _np(params[k].grad).reshape(-1).astype(np.float64)
+            if np.linalg.norm(ref) < 1e-8:
+                continue
+            cos = float(ref @ got / (np.linalg.norm(ref) * np.linalg.norm(got) + 1e-30))
+            assert cos > 0.99, f"{k}: cosine {cos}"
+
+
+def test_training_loop_reduces_loss(agb, golden_dir):
+    """The reference's loop body (scripts/train_explainer.py:182-198) runs unchanged and learns."""
+    from autognothi_b200.models import shapley as ash
+    name = "vit_mini"
+    g = _load(golden_dir, f"model_{name}.npz")
+    B, S, n = (int(v) for v in g["meta"])
+    rec, cfgd, srg, exp = _build(name, "bf16")
+    exp.train()
+    opt = torch.optim.AdamW(exp.parameters(), lr=1e-4)
+    xs = torch.from_numpy(synth.inputs(cfgd, B, seed=0)).to(DEV)
+    masks = torch.from_numpy(g["masks"].astype(np.int64)).to(DEV).reshape(B, S, n)
+    v_s, grand, null = (torch.from_numpy(g[k]).to(DEV) for k in ("v_s", "grand", "null"))
+    ones = torch.ones((B, n), dtype=torch.int64, device=DEV)
+    losses = []
+    for _ in range(8):
+        opt.zero_grad()
+        phi, _ = rec.fw_explainer(exp, xs, ones, grand, null)
+        loss = ash.loss_shapley_new(B, S, n, masks, null, v_s, grand, phi)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert losses[-1] < 0.7 * losses[0], losses
