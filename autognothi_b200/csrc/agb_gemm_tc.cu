@@ -38,7 +38,7 @@ struct GemmParams {
   float alpha;              // scale applied to the accumulator before bias
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int ACT, int RES, int OUT_F32>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmParams p) {
@@ -158,88 +158,93 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     //      4 KB staging tile (16-byte pieces XOR-swizzled by row -> conflict-free both ways);
     //  (2) 8 lanes per row x 4 rows per pass: read 4 columns back, apply alpha/bias/GELU/residual
     //      and store 128 B (fp32) or 64 B (bf16) contiguous per row.
+    // ACT / RES / OUT_F32 are compile-time so the inner passes carry no branches or pointer tests.
     const int q = warp & 3;                 // TMEM lane quarter this warp may touch
     const int h = (warp - 2) >> 2;          // column half
     constexpr int COLS_PER_WARP = BN / 2;
-    uint8_t* stage_tile = smem + STAGES * STAGE_BYTES + 256 + (warp - 2) * 4096;
-    const uint32_t stage_u32 = smem_u32(stage_tile);
+    constexpr int OUT_ES = OUT_F32 ? 4 : 2;                 // output element size
+    constexpr int RES_ES = (RES == 2) ? 4 : 2;              // residual element size
+    const uint32_t stage_u32 = smem_u32(smem + STAGES * STAGE_BYTES + 256 + (warp - 2) * 4096);
     const int piece = lane & 7, rsub = lane >> 3;
+    const uint32_t st_base = stage_u32 + lane * 128;
+    const uint32_t st_xor = static_cast<uint32_t>(lane & 7);
+    // read-back address of pass ps: row_l = 4*ps + rsub, (row_l & 7) = rsub + 4*(ps & 1)
+    const uint32_t ld_even = stage_u32 + rsub * 128 + ((piece ^ rsub) << 4);
+    const uint32_t ld_odd = stage_u32 + (rsub + 4) * 128 + ((piece ^ (rsub + 4)) << 4);
+    const long long out_pitch4 = 4ll * p.ldo * OUT_ES;      // bytes between passes
+    const long long res_pitch4 = 4ll * p.ldr * RES_ES;
     uint32_t acc = 0, acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m0 = (t / tiles_n) * GEMM_BM;
       const int n0 = (t % tiles_n) * BN;
       mbar_wait(smem_u32(&bar_tfull[acc]), acc_phase);
       tc_fence_after();
+      const int row0 = m0 + q * 32 + rsub;                  // row of pass 0 for this lane
+      const int rows_left = p.M - row0;                     // pass ps valid iff 4*ps < rows_left
+      const int ncol0 = n0 + h * COLS_PER_WARP + piece * 4;
+      uint8_t* out_row = reinterpret_cast<uint8_t*>(p.out) + ((long long)row0 * p.ldo + ncol0) * OUT_ES;
+      const uint8_t* res_row = nullptr;
+      if (RES == 1) res_row = reinterpret_cast<const uint8_t*>(p.res_bf16) + ((long long)row0 * p.ldr + ncol0) * 2;
+      if (RES == 2) res_row = reinterpret_cast<const uint8_t*>(p.res_f32) + ((long long)row0 * p.ldr + ncol0) * 4;
+      const uint32_t tm_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + h * COLS_PER_WARP;
 #pragma unroll 1
       for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
-        const int col0 = h * COLS_PER_WARP + c * 32;
         uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + col0, r);
-        const int n = n0 + col0 + piece * 4;
+        tmem_ld32(tm_addr + c * 32, r);
+        const int n = ncol0 + c * 32;
         const bool n_ok = n < p.N;
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias != nullptr && n_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        // residual prefetch for the 8 passes (coalesced, issued before the TMEM wait)
+        uint2 rb[8];
+        float4 rf[8];
+        if (RES != 0) {
+#pragma unroll
+          for (int ps = 0; ps < 8; ++ps) {
+            const bool ok = n_ok && (4 * ps < rows_left);
+            const uint8_t* rp = res_row + ps * res_pitch4 + (long long)c * 32 * RES_ES;
+            if (RES == 1) rb[ps] = ok ? __ldg(reinterpret_cast<const uint2*>(rp)) : make_uint2(0u, 0u);
+            if (RES == 2) rf[ps] = ok ? __ldg(reinterpret_cast<const float4*>(rp)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const uint32_t addr = stage_u32 + lane * 128 + ((j ^ (lane & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[4 * j]),
-                       "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_base + ((j ^ st_xor) << 4)),
+                       "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
                        : "memory");
         }
         __syncwarp();
-        if (n_ok) {
-          // residual prefetch for the 8 passes (coalesced, issued back to back)
-          uint2 rb[8];
-          float4 rf[8];
 #pragma unroll
-          for (int ps = 0; ps < 8; ++ps) {
-            const int row = m0 + q * 32 + ps * 4 + rsub;
-            rb[ps] = make_uint2(0u, 0u);
-            rf[ps] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < p.M && (p.res_bf16 != nullptr || p.res_f32 != nullptr)) {
-              long long res_row = row;
-              if (p.res_group > 0)
-                res_row = (long long)(row / p.res_group) * p.res_rows + (row % p.res_rows);
-              if (p.res_bf16 != nullptr)
-                rb[ps] = __ldg(reinterpret_cast<const uint2*>(p.res_bf16 + res_row * p.ldr + n));
-              else
-                rf[ps] = __ldg(reinterpret_cast<const float4*>(p.res_f32 + res_row * p.ldr + n));
-            }
+        for (int ps = 0; ps < 8; ++ps) {
+          float4 v;
+          const uint32_t addr = ((ps & 1) ? ld_odd : ld_even) + (ps >> 1) * 1024;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                       : "r"(addr)
+                       : "memory");
+          v.x = fmaf(v.x, p.alpha, bias4.x);
+          v.y = fmaf(v.y, p.alpha, bias4.y);
+          v.z = fmaf(v.z, p.alpha, bias4.z);
+          v.w = fmaf(v.w, p.alpha, bias4.w);
+          if (ACT == 1) {
+            v.x = gelu_erf_fast(v.x); v.y = gelu_erf_fast(v.y);
+            v.z = gelu_erf_fast(v.z); v.w = gelu_erf_fast(v.w);
           }
-#pragma unroll
-          for (int ps = 0; ps < 8; ++ps) {
-            const int row_l = ps * 4 + rsub;
-            const int row = m0 + q * 32 + row_l;
-            float4 v;
-            const uint32_t addr = stage_u32 + row_l * 128 + ((piece ^ (row_l & 7)) << 4);
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                         : "r"(addr)
-                         : "memory");
-            v.x = fmaf(v.x, p.alpha, bias4.x);
-            v.y = fmaf(v.y, p.alpha, bias4.y);
-            v.z = fmaf(v.z, p.alpha, bias4.z);
-            v.w = fmaf(v.w, p.alpha, bias4.w);
-            if (p.act == 1) {
-              v.x = gelu_erf_fast(v.x); v.y = gelu_erf_fast(v.y);
-              v.z = gelu_erf_fast(v.z); v.w = gelu_erf_fast(v.w);
-            }
-            if (p.res_bf16 != nullptr) {
-              v.x += bf16_lo(rb[ps].x); v.y += bf16_hi(rb[ps].x);
-              v.z += bf16_lo(rb[ps].y); v.w += bf16_hi(rb[ps].y);
-            } else if (p.res_f32 != nullptr) {
-              v.x += rf[ps].x; v.y += rf[ps].y; v.z += rf[ps].z; v.w += rf[ps].w;
-            }
-            if (row < p.M) {
-              if (p.out_f32) {
-                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + n) = v;
-              } else {
-                uint2 pk;
-                pk.x = pack_bf16x2(v.x, v.y);
-                pk.y = pack_bf16x2(v.z, v.w);
-                *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + n) = pk;
-              }
+          if (RES == 1) {
+            v.x += bf16_lo(rb[ps].x); v.y += bf16_hi(rb[ps].x);
+            v.z += bf16_lo(rb[ps].y); v.w += bf16_hi(rb[ps].y);
+          }
+          if (RES == 2) { v.x += rf[ps].x; v.y += rf[ps].y; v.z += rf[ps].z; v.w += rf[ps].w; }
+          if (n_ok && 4 * ps < rows_left) {
+            uint8_t* op = out_row + ps * out_pitch4 + (long long)c * 32 * OUT_ES;
+            if (OUT_F32) {
+              *reinterpret_cast<float4*>(op) = v;
+            } else {
+              uint2 pk;
+              pk.x = pack_bf16x2(v.x, v.y);
+              pk.y = pack_bf16x2(v.z, v.w);
+              *reinterpret_cast<uint2*>(op) = pk;
             }
           }
         }
@@ -258,21 +263,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int ACT, int RES, int OUT_F32>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
                        cudaStream_t stream) {
   constexpr int SMEM = STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 1024 + 256 + GEMM_EPI_WARPS * 4096;
   static bool configured = false;
   if (!configured) {
-    AGB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>,
+    AGB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, ACT, RES, OUT_F32>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
   const int tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<BN, STAGES><<<grid, GEMM_THREADS, SMEM, stream>>>(tmA, tmB, p);
+  gemm_tc_kernel<BN, STAGES, ACT, RES, OUT_F32><<<grid, GEMM_THREADS, SMEM, stream>>>(tmA, tmB, p);
   AGB_CHECK_CUDA(cudaGetLastError());
   return AGB_OK;
+}
+
+template <int BN, int STAGES>
+static int dispatch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+  const int res = p.res_bf16 ? 1 : (p.res_f32 ? 2 : 0);
+#define AGB_CASE(A, R, O) \
+  if (p.act == A && res == R && p.out_f32 == O) return launch_gemm<BN, STAGES, A, R, O>(tmA, tmB, p, st);
+  AGB_CASE(0, 0, 0) AGB_CASE(0, 0, 1) AGB_CASE(0, 1, 0) AGB_CASE(0, 1, 1) AGB_CASE(0, 2, 0) AGB_CASE(0, 2, 1)
+  AGB_CASE(1, 0, 0) AGB_CASE(1, 0, 1) AGB_CASE(1, 1, 0) AGB_CASE(1, 1, 1) AGB_CASE(1, 2, 0) AGB_CASE(1, 2, 1)
+#undef AGB_CASE
+  set_last_error("unsupported GEMM epilogue (act=%d)", p.act);
+  return AGB_ERR_INVALID;
 }
 
 // Host entry used by the C-ABI (agb_api.cu).  lda/ldb are row pitches in elements of the stored
@@ -291,6 +308,9 @@ int gemm_bf16_tc(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b
               "operands must be 16-byte aligned");
   AGB_REQUIRE(!(res_bf16 || res_f32) || (ldr % 8) == 0, "residual pitch alignment");
   AGB_REQUIRE(!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "bias alignment");
+  AGB_REQUIRE(res_group == 0 && res_rows == 0, "residual row remap is reserved (pass 0, 0)");
+  AGB_REQUIRE(act == 0 || act == 1, "activation");
+  AGB_REQUIRE(!(res_bf16 && res_f32), "one residual at most");
 
   const bool wide = N >= 192;
   const int BN = wide ? 256 : 128;
@@ -309,8 +329,8 @@ int gemm_bf16_tc(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b
   p.res_group = res_group; p.res_rows = res_rows;
   p.out = out; p.ldo = ldo; p.out_f32 = out_f32; p.act = act;
   p.a_mn = a_mn; p.b_mn = b_mn; p.alpha = alpha;
-  if (wide) return launch_gemm<256, 4>(tmA, tmB, p, stream);
-  return launch_gemm<128, 6>(tmA, tmB, p, stream);
+  if (wide) return dispatch_gemm<256, 4>(tmA, tmB, p, stream);
+  return dispatch_gemm<128, 6>(tmA, tmB, p, stream);
 }
 
 }  // namespace agb

@@ -386,15 +386,19 @@ def test_training_gradients_fp32_vs_reference_autograd(agb, golden_dir, name):
     ref_norms = dict(zip([str(s) for s in t["norm_names"]], t["norm_values"]))
     params = dict(exp.named_parameters())
     assert set(params) == set(ref_norms)
+    # some gradients are identically zero in exact arithmetic (key biases: softmax shift invariance; the last
+    # head bias under the efficiency normalisation) — both sides then hold rounding noise, so the absolute
+    # floor is tied to the overall gradient scale
+    floor = 1e-5 * max(ref_norms.values())
     for k, p in params.items():
         assert p.grad is not None, f"no gradient for {k}"
         got = float(p.grad.norm())
-        assert abs(got - ref_norms[k]) <= 2e-3 * ref_norms[k] + 1e-6, f"{k}: |grad| {got} vs {ref_norms[k]}"
+        assert abs(got - ref_norms[k]) <= 2e-3 * ref_norms[k] + floor, f"{k}: |grad| {got} vs {ref_norms[k]}"
     for key in t.files:
         if key.startswith("grad::"):
             k = key[len("grad::"):]
             ref = t[key]
-            np.testing.assert_allclose(_np(params[k].grad), ref, rtol=2e-3, atol=2e-3 * np.abs(ref).max() + 1e-7, err_msg=k)
+            np.testing.assert_allclose(_np(params[k].grad), ref, rtol=2e-3, atol=2e-3 * np.abs(ref).max() + floor, err_msg=k)
 
 
 @pytest.mark.parametrize("name", ["vit_mini", "bert_mini"])
@@ -403,11 +407,13 @@ def test_training_gradients_bf16_tensor_cores(agb, golden_dir, name):
     exp, loss = _train_step_grads(golden_dir, name, "bf16")
     assert abs(loss - float(t["loss"])) <= 2e-2 * abs(float(t["loss"]))
     params = dict(exp.named_parameters())
+    floor = 1e-4 * float(np.max(t["norm_values"]))
     for key in t.files:
         if key.startswith("grad::"):
             k = key[len("grad::"):]
             ref, got = t[key].reshape(-1).astype(np.float64), _np(params[k].grad).reshape(-1).astype(np.float64)
-            if np.linalg.norm(ref) < 1e-8:
+            if np.linalg.norm(ref) < floor:      # identically-zero gradients (see the fp32 test): noise only
+                assert np.linalg.norm(got) < 50 * floor, k
                 continue
             cos = float(ref @ got / (np.linalg.norm(ref) * np.linalg.norm(got) + 1e-30))
             assert cos > 0.99, f"{k}: cosine {cos}"
