@@ -23,6 +23,7 @@ _CTYPES = {
     "float": ctypes.c_float,
     "long long": ctypes.c_longlong,
     "uint64_t": ctypes.c_uint64,
+    "double": ctypes.c_double,
 }
 
 

@@ -63,6 +63,9 @@ int shapley_loss_fwd(const uint32_t* packed, int words, const float* v0, const f
                      int B, int S, int n, int C, float* resid, float* partial, float* loss, cudaStream_t st);
 int shapley_loss_bwd(const uint32_t* packed, int words, const float* resid, const float* gout, int B, int S,
                      int n, int C, float* dphi, cudaStream_t st);
+int kernelshap_solve(const uint32_t* Z, int words, const double* w, const double* probs, const double* fx,
+                     const double* f0, int B, int S, int d, int C, int link, double* A, double* R, double* phi,
+                     int* info, cudaStream_t st);
 }  // namespace agb
 
 using agb::bf16;
@@ -203,6 +206,13 @@ int agb_shapley_loss_bwd(const uint32_t* packed, int words, const float* resid,
                          const float* grad_out, int B, int S, int n_players, int C, float* dphi,
                          void* stream) {
   return agb::shapley_loss_bwd(packed, words, resid, grad_out, B, S, n_players, C, dphi, ST(stream));
+}
+
+int agb_kernelshap_solve(const uint32_t* Z, int words, const double* weights, const double* probs,
+                         const double* f_x, const double* f_null, int B, int S, int d, int C, int link_logit,
+                         double* gram_ws, double* rhs_ws, double* phi, int* info, void* stream) {
+  return agb::kernelshap_solve(Z, words, weights, probs, f_x, f_null, B, S, d, C, link_logit, gram_ws, rhs_ws, phi,
+                               info, ST(stream));
 }
 
 }  // extern "C"

@@ -352,3 +352,29 @@ def bert_embed_scatter(ids: Tensor, dsum: Tensor, pad_id: int, dword: Tensor, dp
     H = dword.shape[1]
     nat.call("agb_bert_embed_scatter", nat.ptr(ids), nat.ptr(_c(dsum)), B * T, T, H, dword.shape[0], pad_id, nat.ptr(dword),
              nat.ptr(dpos), nat.ptr(dtype0), nat.stream())
+
+
+# ------------------------------------------------------------------------------------------------
+# KernelSHAP
+# ------------------------------------------------------------------------------------------------
+def pack_feature_masks(Z: Tensor) -> Tensor:
+    """(rows, d) {0,1} -> packed (rows, ceil(d/32)) int32 with bit j = feature j (no CLS offset)."""
+    return pack_masks(Z.to(torch.int64), prepend_cls=False)
+
+
+def kernelshap_solve(Zp: Tensor, weights: Tensor, probs: Tensor, f_x: Tensor, f_null: Tensor, d: int,
+                     link_logit: bool = True):
+    """Zp (B,S,words) packed, weights (B,S), probs (B,S,C), f_x (B,C), f_null (C) -> (phi (B,C,d) float64, info (B))"""
+    B, S, words = Zp.shape
+    C = probs.shape[2]
+    dev = Zp.device
+    f64 = lambda t: _c(t.to(torch.float64))  # noqa: E731
+    weights, probs, f_x, f_null = f64(weights), f64(probs), f64(f_x), f64(f_null.reshape(-1))
+    n = d - 1
+    A = torch.empty((B, n * n), dtype=torch.float64, device=dev)
+    R = torch.empty((B, n, C), dtype=torch.float64, device=dev)
+    phi = torch.empty((B, C, d), dtype=torch.float64, device=dev)
+    info = torch.empty((B,), dtype=torch.int32, device=dev)
+    nat.call("agb_kernelshap_solve", nat.ptr(_c(Zp)), words, nat.ptr(weights), nat.ptr(probs), nat.ptr(f_x), nat.ptr(f_null),
+             B, S, d, C, 1 if link_logit else 0, nat.ptr(A), nat.ptr(R), nat.ptr(phi), nat.ptr(info), nat.stream())
+    return phi, info

@@ -167,6 +167,19 @@ int agb_bert_embed_sum(const int64_t* ids, const float* word, const float* pos, 
 int agb_bert_embed_scatter(const int64_t* ids, const float* dsum, int BT, int T, int H, int vocab, int pad_id,
                            float* dword, float* dpos, float* dtype0, void* stream);
 
+/* ---- KernelSHAP weighted least squares (reference models/kernel_shap_bert.py:170-185 hands this to the
+ *      third-party shap.KernelExplainer; requirements.txt:10 pins shap~=0.44.1) ------------------------- */
+/* Batched over B explained samples, float64 throughout.  Z (B,S,words) packed coalitions over the d = T token
+ * features (bit j = feature j, no CLS offset); weights (B,S) kernel weights; probs (B,S,C) background-averaged
+ * model outputs; f_x (B,C) outputs on the unperturbed rows; f_null (C) background expectation; link_logit = 1
+ * applies shap's link="logit".  gram_ws (B,(d-1)^2) and rhs_ws (B,(d-1),C) are caller-provided scratch.
+ * phi (B,C,d) satisfies sum_j phi = link(f_x) - link(f_null) exactly (efficiency constraint).
+ * info[b] = 0, or k+1 if the Gram matrix lost positive definiteness at column k (LAPACK potrf convention).
+ * shap's optional l1_reg feature pre-selection is not applied. */
+int agb_kernelshap_solve(const uint32_t* Z, int words, const double* weights, const double* probs,
+                         const double* f_x, const double* f_null, int B, int S, int d, int C, int link_logit,
+                         double* gram_ws, double* rhs_ws, double* phi, int* info, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

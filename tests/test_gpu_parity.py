@@ -441,3 +441,62 @@ def test_training_loop_reduces_loss(agb, golden_dir):
         opt.step()
         losses.append(float(loss.detach()))
     assert losses[-1] < 0.7 * losses[0], losses
+
+
+# ------------------------------------------------------------------------------------------------
+# KernelSHAP: batched Gram + Cholesky solve vs the float64 oracle (oracle parity itself is UNPINNED: shap absent)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,S,C,B", [(128, 2048, 2, 3), (33, 400, 2, 2), (197, 1024, 10, 1), (8, 64, 3, 4)])
+def test_kernelshap_solve_vs_oracle(agb, d, S, C, B):
+    from oracle import kernelshap as oks
+    rng = np.random.default_rng(d)
+    Zs, Ws, Ps, refs = [], [], [], []
+    f_x = rng.uniform(0.05, 0.95, (B, C))
+    f0 = rng.uniform(0.05, 0.95, C)
+    for b in range(B):
+        Z, w = oks.sample_coalitions(d, S, seed=b)
+        p = rng.uniform(0.05, 0.95, (Z.shape[0], C))
+        Zs.append(oks.pack_features(Z).view(np.int32)); Ws.append(w); Ps.append(p)
+        refs.append(oks.explain(p, f_x[b], f0, Z, w))
+    phi, info = agb.kernelshap_solve(torch.from_numpy(np.stack(Zs)).to(DEV), torch.from_numpy(np.stack(Ws)).to(DEV),
+                                     torch.from_numpy(np.stack(Ps)).to(DEV), torch.from_numpy(f_x).to(DEV),
+                                     torch.from_numpy(f0).to(DEV), d, link_logit=True)
+    assert int(info.abs().max()) == 0
+    got = phi.cpu().numpy()
+    ref = np.stack(refs)
+    np.testing.assert_allclose(got, ref, rtol=1e-7, atol=1e-9 * np.abs(ref).max() + 1e-10)
+    # efficiency: attributions sum to link(f(x)) - link(f_null) exactly
+    np.testing.assert_allclose(got.sum(axis=2), oks.logit(f_x) - oks.logit(f0)[None, :], rtol=1e-9, atol=1e-10)
+
+
+def test_kernelshap_flags_a_singular_system(agb):
+    d, S, C = 16, 4, 2   # far fewer coalitions than features
+    Z = torch.zeros((1, S, 1), dtype=torch.int32, device=DEV)
+    w = torch.full((1, S), 0.25, dtype=torch.float64, device=DEV)
+    p = torch.full((1, S, C), 0.5, dtype=torch.float64, device=DEV)
+    _, info = agb.kernelshap_solve(Z, w, p, torch.full((1, C), 0.6, device=DEV), torch.full((C,), 0.4, device=DEV), d)
+    assert int(info[0]) != 0
+
+
+def test_kernel_shap_recipe_end_to_end(agb):
+    """fw_final of the KernelSHAP recipe: classifier forwards on the GPU + device solve; additive toy check."""
+    from autognothi_b200.recipes.kernel_shap_bert import kernel_shap_bert_recipe
+    rec = kernel_shap_bert_recipe()
+    cfgd = ocfg.get_config("bert_mini")
+    cfgd.update(kernel_shap_n_samples=256, kernel_shap_data_size=4)
+    cfg = rec.t_config(**cfgd)
+    cls = rec.t_classifier(cfg)
+    cls.load_state_dict({k: torch.from_numpy(v) for k, v in synth.surrogate_state(ocfg.get_config("bert_mini"), 0).items()})
+    cls = cls.to(DEV).eval()
+    cls.agb_precision = "fp32"
+    exp = rec.t_explainer(cfg).to(DEV)
+    with torch.no_grad():
+        exp.Xs_train.copy_(torch.from_numpy(synth.inputs(ocfg.get_config("bert_mini"), 4, seed=9)).to(DEV))
+    final = rec.conv_explainer_final(cfg, None, cls, None, exp).eval()
+    final.classifier.agb_precision = "fp32"
+    xs = torch.from_numpy(synth.inputs(ocfg.get_config("bert_mini"), 2, seed=0)).to(DEV)
+    logits, attr = rec.fw_final(final, xs)
+    n = rec.n_players(cfg)
+    assert logits.shape == (2, 2) and attr.shape == (2, 2, n) and torch.isfinite(attr).all()
+    with pytest.raises(NotImplementedError):
+        rec.fw_explainer(exp, xs, None, None, None)
