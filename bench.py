@@ -31,6 +31,21 @@ METRIC = "masked_coalition_evals_per_sec"
 UNIT = "evals/s"
 
 
+# reference experiments/vit_base_imagenette_vanilla/.hparams.json:20-35 (net.params)
+VIT_BASE = dict(attention_probs_dropout_prob=0.1, explainer_attn_num_layers=1, explainer_head_hidden_size=3072,
+                explainer_normalize=True, hidden_dropout_prob=0.1, hidden_size=768, intermediate_size=3072,
+                layer_norm_eps=1e-12, num_attention_heads=12, num_hidden_layers=12, num_labels=10, img_channels=3,
+                img_px_size=224, img_patch_size=16)
+
+
+def flops_per_eval(c):
+    """Dense forward FLOPs of one masked ViT surrogate evaluation (SURVEY.md §8d / BASELINE.md §4: 35.13 GFLOP for ViT-B)."""
+    H, I, L, C = c["hidden_size"], c["intermediate_size"], c["num_hidden_layers"], c["num_labels"]
+    T = (c["img_px_size"] // c["img_patch_size"]) ** 2 + 1
+    layer = 2 * T * H * 3 * H + 2 * T * H * H + 4 * T * H * I + 4 * T * T * H
+    return float(L * layer + 2 * H * C + 2 * (T - 1) * H * c["img_channels"] * c["img_patch_size"] ** 2)
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -153,8 +168,6 @@ def run_ours(args):
     from autognothi_b200 import _native as nat
     from autognothi_b200.models import shapley as ash
     from autognothi_b200.recipes.vanilla_vit import vanilla_vit_recipe
-    from oracle import configs as ocfg
-    from oracle import transformer as otr
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -170,7 +183,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     rec = vanilla_vit_recipe()
-    cfgd = ocfg.get_config("vit_base")
+    cfgd = dict(VIT_BASE)
     cfg = rec.t_config(**cfgd)
     n = rec.n_players(cfg)
     torch.manual_seed(3407)                       # the reference's checked-in seed (.hparams.json:3)
@@ -223,6 +236,50 @@ def run_ours(args):
         clocks = sampler.stop() if rank == 0 else None
         ms_e2e, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
 
+    # ---- explainer training step (reference scripts/train_explainer.py:148-198): sample coalitions, S masked
+    # surrogate evals + 1 grand eval per image, explainer fwd/bwd, gradient all-reduce, AdamW ----
+    train = None
+    if not args.no_train:
+        from autognothi_b200.dist import GradAllReducer
+        Bt = args.train_images
+        explainer = rec.conv_surrogate_explainer(cfg, None, surrogate).train()
+        explainer.agb_precision = "bf16"
+        opt = torch.optim.AdamW(explainer.parameters(), lr=5e-5, fused=True)   # lr: .hparams.json train_explainer.lr
+        reducer = GradAllReducer(explainer.parameters(), bucket_mb=64.0)
+        ones = ash.PackedMasks.ones(Bt, n, dev)
+        with torch.no_grad():
+            null, _ = rec.fw_surrogate(surrogate, rec.gen_null(cfg, None, dev), ash.PackedMasks.ones(1, n, dev))
+        xs_t = images_dev[:Bt]
+
+        def step_train(i):
+            pm = ash.mask_shapley_new(Bt * S, n, device=dev, rng="philox", seed=99 + rank, offset=i * Bt * S, packed=True)
+            with torch.no_grad():
+                v_s, _ = rec.fw_surrogate(surrogate, xs_t, pm)
+                grand, _ = rec.fw_surrogate(surrogate, xs_t, ones)
+            phi, _ = rec.fw_explainer(explainer, xs_t, ones, grand, null)
+            loss = ash.loss_shapley_new(Bt, S, n, pm, null, v_s, grand, phi)
+            loss.backward()
+            reducer.allreduce()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            return loss
+
+        t_steps = max(2, min(args.steps, 5))
+        ms_t, launches_t, _ = timed(step_train, t_steps, 2)
+        sps = world * Bt * t_steps / (ms_t * 1e-3)
+        fl_eval = flops_per_eval(cfgd)
+        H, I, E, T = cfg.hidden_size, cfg.intermediate_size, cfg.explainer_head_hidden_size, n + 1
+        layer = 2 * T * H * 3 * H + 2 * T * H * H + 4 * T * H * I + 4 * T * T * H
+        fl_exp = fl_eval + layer + 2 * T * H * E + 2 * T * E * E + 2 * T * E * cfg.num_labels
+        fl_sample = (S + 1) * fl_eval + 3 * fl_exp
+        train = {"metric": "explainer_train_samples_per_sec", "value": sps, "unit": "samples/s", "ms_per_step": ms_t / t_steps,
+                 "steps": t_steps, "images_per_gpu_per_step": Bt, "coalitions_per_image": S, "flops_per_sample": fl_sample,
+                 "tflops_per_gpu": sps / world * fl_sample * 1e-12, "gpu_launches": launches_t,
+                 "dropout": "p=0 (identity); the reference trains with p=0.1", "optimizer": "torch.optim.AdamW(fused=True), fp32 master weights",
+                 "grad_allreduce": f"NCCL, 64 MB flat buckets, world={world}"}
+        peaks_t = load_peaks()
+        train["frac_of_sustained_peak"] = train["tflops_per_gpu"] / peaks_t["bf16_tflops_sustained"]
+
     value = world * rows * args.steps / (ms * 1e-3)
     e2e_value = world * rows * args.steps / (ms_e2e * 1e-3)
 
@@ -244,7 +301,7 @@ def run_ours(args):
         "avg_launch_us": gemm[0] / gemm[2] * 1e3, "launches": gemm[2], "share_of_step": gemm[0] / total_t,
         "step_shares": {k: round(v[0] / total_t, 4) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1][0])},
     }
-    flops_eval = otr.flops_per_eval(cfgd)
+    flops_eval = flops_per_eval(cfgd)
     whole = {"tflops_per_gpu": value / world * flops_eval * 1e-12,
              "frac_of_sustained_peak": value / world * flops_eval * 1e-12 / peaks["bf16_tflops_sustained"],
              "frac_of_burst_peak": value / world * flops_eval * 1e-12 / peaks["bf16_tflops"],
@@ -270,6 +327,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": rows * C * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "whole_path": whole,
         }
+        if train is not None:
+            line["train"] = train
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -285,6 +344,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=32, help="images per GPU per step (x32 coalitions each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the explainer-training leg")
+    ap.add_argument("--train-images", type=int, default=32, help="images per GPU per training step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
