@@ -204,6 +204,155 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// TMA stores (smem -> global, bulk async-group completion) and the CTA-pair (cta_group::2) forms
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most N of this thread's most recent bulk groups may still be READING their smem source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// full completion (global writes performed)
+template <int N>
+__device__ __forceinline__ void bulk_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+// address of the same smem offset in CTA `rank` of this cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// The pair's TMA loads land in the issuing CTA's smem but complete on the LEADER's mbarrier: clearing
+// the peer bit of a shared::cta address names the same offset in the even CTA of the pair.
+constexpr uint32_t PAIR_LEADER_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar,
+                                                 int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & PAIR_LEADER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_result_addr, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result_addr),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem, 128 rows per CTA] * B[smem, N/2 rows per CTA]; leader CTA issues.
+__device__ __forceinline__ void umma_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once) on the barrier at this smem offset in BOTH CTAs of the pair when the MMAs retire
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}\n"
+      :
+      : "r"(bar)
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// "Elected" forms for the single-thread roles.  The whole warp executes these convergently with
+// warp-uniform operands and only the instruction itself is predicated on the elected lane (e != 0 in
+// exactly one lane, from elect_one()).  Keeping the address / descriptor arithmetic outside a
+// divergent `if (lane == 0)` lets ptxas hold it in uniform registers instead of emitting an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY loop around every TMA and MMA instruction (round-1 finding:
+// the producer and MMA-issue loops cost ~750 cycles per 512-cycle k-block).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_idx_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
+__device__ __forceinline__ void mbar_arrive_expect_tx_e(uint32_t e, uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+               "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}\n" ::"r"(bar), "r"(bytes), "r"(e)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_e(uint32_t e, uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar,
+                                              int c0, int c1) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+               "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+               " [%0], [%1, {%3, %4}], [%2];\n\t}\n"
+               :
+               : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(e)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_e(uint32_t e, uint32_t smem_dst, const CUtensorMap* tmap,
+                                                   uint32_t bar, int c0, int c1) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+               "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+               " [%0], [%1, {%3, %4}], [%2];\n\t}\n"
+               :
+               : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & PAIR_LEADER_MASK), "r"(c0),
+                 "r"(c1), "r"(e)
+               : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void umma_ss_e(uint32_t e, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+  if (CG == 2) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 :
+                 : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(e)
+                 : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 :
+                 : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(e)
+                 : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void umma_commit_e(uint32_t e, uint32_t bar) {
+  if (CG == 2) {
+    asm volatile("{\n\t.reg .pred q;\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}\n"
+                 :
+                 : "r"(bar), "r"(e)
+                 : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
+                 :
+                 : "r"(bar), "r"(e)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // descriptors
 // ---------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_128B canonical layouts (Blackwell "version 1" format):
@@ -268,6 +417,39 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaf(hx, erf_v, hx);
 }
 
+// erf-GELU for the tensor-core epilogues with ONE MUFU op:  gelu(x) = max(x,0) - |x| * Phi(-|x|)  and
+//   Phi(-t) ~= 0.5 / (1 + t(c1 + t(c2 + t(c3 + t(c4 + t c5)))))^16      (fitted on t in [0,8], A&S 7.1.28 form)
+// max |gelu error| 1.8e-6, max |Phi error| 1e-5 — far below bf16 resolution; for t > 8 the power
+// overflows to +inf and the reciprocal is exactly 0, so gelu(x) = max(x,0).  13 issue slots.
+__device__ __forceinline__ float gelu_erf_rational(float x) {
+  const float t = fabsf(x);
+  float p = fmaf(9.285284751883197e-05f, t, -9.362633048630915e-05f);
+  p = fmaf(p, t, 0.003455584071090405f);
+  p = fmaf(p, t, 0.02103458463851493f);
+  p = fmaf(p, t, 0.04988919561503405f);
+  p = fmaf(p, t, 1.0f);
+  p *= p; p *= p; p *= p; p *= p;
+  const float r = rcp_approx(p);
+  return fmaf(-0.5f * t, r, fmaxf(x, 0.f));
+}
+
+// erf-GELU with ONE MUFU and 8 issue slots:  gelu(x) = 0.5 x (1 + tanh(x (a + b x^2 + c x^4))), the tanh-form
+// REFITTED to the erf definition (not the classic 0.044715 "tanh GELU"): max |error| 2.5e-5 in exact
+// arithmetic, + tanh.approx (2^-11 relative).  x^2 is clamped at 49 (the quartic turns over at |x| ~ 11).
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_erf_tanhform(float x) {
+  const float x2 = fminf(x * x, 49.0f);
+  float q = fmaf(-0.00035151717489776405f, x2, 0.0370056485719943f);
+  q = fmaf(q, x2, 0.797507881265216f);
+  const float th = tanh_approx(x * q);
+  const float hx = 0.5f * x;
+  return fmaf(hx, th, hx);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -289,6 +471,8 @@ __device__ __forceinline__ float warp_max(float v) {
 // host side: cuTensorMapEncodeTiled resolved through the runtime (no link-time libcuda dependency)
 int encode_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t inner, uint64_t outer,
                         uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+int encode_tmap_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t inner, uint64_t outer,
+                   uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer);
 int encode_tmap_3d_bf16(CUtensorMap* out, const void* gptr, uint64_t d0, uint64_t d1, uint64_t d2,
                         uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0,
                         uint32_t box1, uint32_t box2);

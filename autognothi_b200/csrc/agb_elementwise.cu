@@ -64,6 +64,74 @@ __global__ void layernorm_kernel(const TIn* __restrict__ x, long long in_stride,
   }
 }
 
+// Register-resident variant for the common widths (H = 128*NV4 floats per warp pass, H <= 1024): the row is
+// read from HBM exactly once (NV4 independent 16-byte loads per lane, all issued before the first use), the
+// two-pass mean / variance runs on registers, and the normalised row is written once.
+template <typename TIn, int NV4>
+__global__ void __launch_bounds__(256)
+layernorm_reg_kernel(const TIn* __restrict__ x, long long in_stride, int rows, int H,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                     bf16* __restrict__ out_bf16, float* __restrict__ out_f32, long long out_stride) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const TIn* xr = x + (long long)row * in_stride;
+  float4 v[NV4];
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) v[i] = load4<TIn>(xr + lane * 4 + i * 128);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) / (float)H;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    ss += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / (float)H + eps);
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const int col = lane * 4 + i * 128;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + col));
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * g.x + b.x;
+    o.y = (v[i].y - mean) * rstd * g.y + b.y;
+    o.z = (v[i].z - mean) * rstd * g.z + b.z;
+    o.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + (long long)row * out_stride + col) = o;
+    if (out_bf16) {
+      uint2 pk;
+      pk.x = pack_bf16x2(o.x, o.y);
+      pk.y = pack_bf16x2(o.z, o.w);
+      *reinterpret_cast<uint2*>(out_bf16 + (long long)row * out_stride + col) = pk;
+    }
+  }
+}
+
+template <typename TIn>
+static void launch_layernorm(const TIn* x, long long in_stride, int rows, int H, const float* gamma, const float* beta,
+                             float eps, bf16* out_bf16, float* out_f32, long long out_stride, cudaStream_t st) {
+  const int warps = 8;
+  const int blocks = (rows + warps - 1) / warps;
+#define AGB_LN(NV4)                                                                                                  \
+  layernorm_reg_kernel<TIn, NV4><<<blocks, warps * 32, 0, st>>>(x, in_stride, rows, H, gamma, beta, eps, out_bf16, \
+                                                                out_f32, out_stride)
+  switch ((H % 128 == 0 && H <= 1024) ? H / 128 : 0) {
+    case 1: AGB_LN(1); break;
+    case 2: AGB_LN(2); break;
+    case 3: AGB_LN(3); break;
+    case 4: AGB_LN(4); break;
+    case 6: AGB_LN(6); break;
+    case 8: AGB_LN(8); break;
+    default:
+      layernorm_kernel<TIn><<<blocks, warps * 32, 0, st>>>(x, in_stride, rows, H, gamma, beta, eps, out_bf16, out_f32,
+                                                           out_stride);
+  }
+#undef AGB_LN
+}
+
 int layernorm(const void* x, int in_bf16, long long in_stride, int rows, int H, const float* gamma,
               const float* beta, float eps, bf16* out_bf16, float* out_f32, long long out_stride,
               cudaStream_t st) {
@@ -71,14 +139,10 @@ int layernorm(const void* x, int in_bf16, long long in_stride, int rows, int H, 
   AGB_REQUIRE((in_stride % 4) == 0 && (out_stride % 4) == 0, "row strides must be multiples of 4");
   if (rows == 0) return AGB_OK;
   AGB_REQUIRE(x && gamma && beta && (out_bf16 || out_f32), "null pointer");
-  const int warps = 8;
-  const int blocks = (rows + warps - 1) / warps;
   if (in_bf16)
-    layernorm_kernel<bf16><<<blocks, warps * 32, 0, st>>>(static_cast<const bf16*>(x), in_stride, rows, H, gamma,
-                                                          beta, eps, out_bf16, out_f32, out_stride);
+    launch_layernorm<bf16>(static_cast<const bf16*>(x), in_stride, rows, H, gamma, beta, eps, out_bf16, out_f32, out_stride, st);
   else
-    layernorm_kernel<float><<<blocks, warps * 32, 0, st>>>(static_cast<const float*>(x), in_stride, rows, H,
-                                                           gamma, beta, eps, out_bf16, out_f32, out_stride);
+    launch_layernorm<float>(static_cast<const float*>(x), in_stride, rows, H, gamma, beta, eps, out_bf16, out_f32, out_stride, st);
   AGB_CHECK_CUDA(cudaGetLastError());
   return AGB_OK;
 }

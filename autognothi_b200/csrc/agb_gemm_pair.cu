@@ -1,0 +1,444 @@
+// Dense bf16 GEMM, second generation:  C[M,N] = act(alpha * A[M,K] * B[N,K]^T + bias) (+ residual)
+//
+// Same contract as agb_gemm_tc.cu (the nn.Linear replacement; reference models/vanilla_vit.py:437-441,
+// 473-479, 487-493, 506-513 and models/vanilla_bert.py:503-537, 556-604) but built around the two
+// findings of the round-1 ncu captures (profiles/r01_gemm_ncu.txt): the K=768 shapes were paced by the
+// epilogue (tensor pipe 30-45 % active) and the 1-CTA 128x256 tile pays full B-operand smem traffic.
+//   * CG = 2: a CTA pair (cluster of 2, same TPC) computes one 256x256 tile with
+//     tcgen05.mma.cta_group::2 — each CTA stages its own 128 A rows and HALF of the B tile, the
+//     leader's single thread issues M=256 UMMAs that read both halves, and each CTA keeps its
+//     128x256 fp32 accumulator in its own TMEM (double-buffered, 512 columns).
+//     CG = 1 keeps one CTA per 128x256 tile (small problems, odd tile counts).
+//   * TMA epilogue: thread = accumulator row; tcgen05.ld 32 columns -> alpha/bias/GELU in registers ->
+//     st.shared into a SWIZZLE_128B staging box (conflict-free) -> ONE cp.async.bulk.tensor store per
+//     32x128-byte box.  The fp32 residual is TMA-LOADED into the same box ahead of time
+//     (NBUF-deep per-warp ring, prefetched across tile boundaries), so the epilogue issues ~3
+//     instructions per output element instead of ~14 and touches global memory only through TMA.
+//   * GELU costs one MUFU and 8 issue slots (gelu_erf_tanhform) instead of two MUFU and ~16.
+//   * producer and MMA warps run convergently with elected-lane predication (uniform-register operands).
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (leader CTA only) + TMEM owner, 2..9 = epilogue.
+#include "agb_common.cuh"
+
+namespace agb {
+
+constexpr int PG_BM = 128;   // accumulator rows per CTA (= TMEM lanes)
+constexpr int PG_BN = 256;   // tile columns
+constexpr int PG_BK = 64;    // K per pipeline stage (one 128-byte swizzle atom of bf16)
+constexpr int PG_EPI_WARPS = 8;
+constexpr int PG_THREADS = 64 + 32 * PG_EPI_WARPS;
+constexpr int PG_BOX_BYTES = 4096;  // 32 rows x 128 bytes
+
+struct PairGemmParams {
+  int M, N, K;
+  const float* bias;  // [N] fp32 or nullptr
+  float alpha;
+  int a_mn, b_mn;     // operand majorness (0 = K-major, 1 = MN-major)
+};
+
+template <int CG, int STAGES, int NBUF, int ACT, int RES, int OUT_F32>
+__global__ void __launch_bounds__(PG_THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
+                 const PairGemmParams p) {
+  static_assert(RES == 0 || OUT_F32 == 1, "fp32 residual pairs with fp32 output");
+  constexpr int B_ROWS = PG_BN / CG;                 // B rows staged by this CTA
+  constexpr int A_BYTES = PG_BM * PG_BK * 2;
+  constexpr int B_BYTES = B_ROWS * PG_BK * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int ATOM_BYTES = PG_BK * 128;            // one MN-major atom: 64 k-rows x 128 B
+  constexpr int TMEM_COLS = 2 * PG_BN;
+  constexpr int CHUNK_COLS = OUT_F32 ? 32 : 64;      // output columns per 128-byte staging row
+  constexpr int NCHUNK = (PG_BN / 2) / CHUNK_COLS;   // chunks per warp per tile (warp owns 128 columns)
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* stg_base = smem + STAGES * STAGE_BYTES;                            // [EPI_WARPS][NBUF][4096]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + PG_EPI_WARPS * NBUF * PG_BOX_BYTES);
+  uint64_t* bar_full = bars;
+  uint64_t* bar_empty = bars + STAGES;
+  uint64_t* bar_tfull = bars + 2 * STAGES;
+  uint64_t* bar_tempty = bars + 2 * STAGES + 2;
+  uint64_t* bar_res = bars + 2 * STAGES + 4;                                  // [EPI_WARPS][NBUF]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_res + PG_EPI_WARPS * NBUF);
+
+  const int warp = warp_idx_uniform();
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+
+  const int pair = blockIdx.x / CG;
+  const int num_pairs = gridDim.x / CG;
+  const int tiles_m = (p.M + PG_BM * CG - 1) / (PG_BM * CG);
+  const int tiles_n = (p.N + PG_BN - 1) / PG_BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (p.K + PG_BK - 1) / PG_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
+    if (RES) tma_prefetch_desc(&tmRes);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_tfull[s]), 1);
+      mbar_init(smem_u32(&bar_tempty[s]), PG_EPI_WARPS * CG);
+    }
+    for (int s = 0; s < PG_EPI_WARPS * NBUF; ++s) mbar_init(smem_u32(&bar_res[s]), 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    if (CG == 2) { tmem_alloc_pair(smem_u32(tmem_slot), TMEM_COLS); tmem_relinquish_pair(); }
+    else         { tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);      tmem_relinquish(); }
+  }
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs of a pair) ------------------------------
+    // Whole warp runs the loop convergently; only the elected lane's instructions take effect.
+    const uint32_t e = elect_one();
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]);
+    uint32_t stage = 0, phase = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      const int m0 = (t / tiles_n) * (PG_BM * CG) + (int)cta_rank * PG_BM;
+      const int n0 = (t % tiles_n) * PG_BN + (int)cta_rank * B_ROWS;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty0 + stage * 8, phase ^ 1);
+        const uint32_t full = full0 + stage * 8;
+        if (leader) mbar_arrive_expect_tx_e(e, full, STAGE_BYTES * CG);   // both CTAs' bytes land on the leader
+        const uint32_t sa = smem_base + stage * STAGE_BYTES;
+        const uint32_t sb = sa + A_BYTES;
+        const int k0 = kb * PG_BK;
+        if (CG == 2) {
+          if (!p.a_mn) {
+            tma_load_2d_pair_e(e, sa, &tmA, full, k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < PG_BM / 64; ++j) tma_load_2d_pair_e(e, sa + j * ATOM_BYTES, &tmA, full, m0 + 64 * j, k0);
+          }
+          if (!p.b_mn) {
+            tma_load_2d_pair_e(e, sb, &tmB, full, k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < B_ROWS / 64; ++j) tma_load_2d_pair_e(e, sb + j * ATOM_BYTES, &tmB, full, n0 + 64 * j, k0);
+          }
+        } else {
+          if (!p.a_mn) {
+            tma_load_2d_e(e, sa, &tmA, full, k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < PG_BM / 64; ++j) tma_load_2d_e(e, sa + j * ATOM_BYTES, &tmA, full, m0 + 64 * j, k0);
+          }
+          if (!p.b_mn) {
+            tma_load_2d_e(e, sb, &tmB, full, k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < B_ROWS / 64; ++j) tma_load_2d_e(e, sb + j * ATOM_BYTES, &tmB, full, n0 + 64 * j, k0);
+          }
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (leader CTA) ------------------------------
+    if (leader) {
+      const uint32_t e = elect_one();
+      const uint32_t idesc = make_idesc_bf16(PG_BM * CG, PG_BN, p.a_mn, p.b_mn);
+      const uint32_t a_lbo = p.a_mn ? ATOM_BYTES : 16, a_kstep = (p.a_mn ? 2048 : 32) >> 4;
+      const uint32_t b_lbo = p.b_mn ? ATOM_BYTES : 16, b_kstep = (p.b_mn ? 2048 : 32) >> 4;
+      // descriptor = constant fields + (smem address >> 4); addresses stay below 2^18 so the add never carries
+      const uint64_t da0 = make_smem_desc_sw128(0, a_lbo, 1024), db0 = make_smem_desc_sw128(0, b_lbo, 1024);
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]);
+      const uint32_t tfull0 = smem_u32(&bar_tfull[0]), tempty0 = smem_u32(&bar_tempty[0]);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        mbar_wait(tempty0 + acc * 8, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * PG_BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full0 + stage * 8, phase);
+          tc_fence_after();
+          const uint32_t sa = (smem_base + stage * STAGE_BYTES) >> 4;
+          const uint32_t sb = sa + (A_BYTES >> 4);
+#pragma unroll
+          for (int k = 0; k < PG_BK / 16; ++k) {
+            umma_ss_e<CG>(e, d_tmem, da0 + (sa + k * a_kstep), db0 + (sb + k * b_kstep), idesc,
+                          (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_e<CG>(e, empty0 + stage * 8);
+          if (kb == num_kb - 1) umma_commit_e<CG>(e, tfull0 + acc * 8);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (both CTAs) ------------------------------
+    const int e = warp - 2;
+    const int q = warp & 3;                 // TMEM lane quarter this warp may touch (rows q*32 .. +31)
+    const int h = e >> 2;                   // column half (128 columns)
+    const uint32_t stg_u32 = smem_u32(stg_base + e * NBUF * PG_BOX_BYTES);
+    const uint32_t row_off = lane * 128;
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);
+    uint64_t* my_res = bar_res + e * NBUF;
+    const uint32_t tempty_remote0 = (CG == 2) ? mapa_rank(smem_u32(&bar_tempty[0]), 0) : smem_u32(&bar_tempty[0]);
+
+    // coordinates of this warp's running chunk g (tile sequence is static): returns false if the box is
+    // entirely outside the output (M / N tails, the idle half of a pair on the last M tile)
+    auto chunk_coords = [&](int g, int& row0, int& col0) -> bool {
+      const int t = pair + (g / NCHUNK) * num_pairs;
+      if (t >= num_tiles) return false;
+      row0 = (t / tiles_n) * (PG_BM * CG) + (int)cta_rank * PG_BM + q * 32;
+      col0 = (t % tiles_n) * PG_BN + h * (PG_BN / 2) + (g % NCHUNK) * CHUNK_COLS;
+      return row0 < p.M && col0 < p.N;
+    };
+    auto issue_res = [&](int g) {  // lane 0 only
+      int row0, col0;
+      if (!chunk_coords(g, row0, col0)) return;
+      const int b = g % NBUF;
+      const uint32_t bar = smem_u32(&my_res[b]);
+      mbar_arrive_expect_tx(bar, PG_BOX_BYTES);
+      tma_load_2d(stg_u32 + b * PG_BOX_BYTES, &tmRes, bar, col0, row0);
+    };
+
+    if (RES && lane == 0) {
+#pragma unroll
+      for (int g = 0; g < NBUF; ++g) issue_res(g);
+    }
+    uint32_t res_phase = 0;  // bit b = parity of the next wait on my_res[b]
+    uint32_t acc = 0, acc_phase = 0;
+    const uint32_t tfull0 = smem_u32(&bar_tfull[0]);
+    int g = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      const int row0 = (t / tiles_n) * (PG_BM * CG) + (int)cta_rank * PG_BM + q * 32;
+      const int tcol0 = (t % tiles_n) * PG_BN + h * (PG_BN / 2);
+      const bool row_ok = row0 < p.M;
+      mbar_wait(tfull0 + acc * 8, acc_phase);
+      tc_fence_after();
+      const uint32_t tm_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * PG_BN + h * (PG_BN / 2);
+#pragma unroll 1
+      for (int c = 0; c < NCHUNK; ++c, ++g) {
+        const int col0 = tcol0 + c * CHUNK_COLS;
+        const bool active = row_ok && col0 < p.N;
+        const int b = g % NBUF;
+        const uint32_t buf = stg_u32 + b * PG_BOX_BYTES;
+        uint32_t r[CHUNK_COLS];
+        if (active) {
+          tmem_ld32(tm_addr + c * CHUNK_COLS, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+          if (!OUT_F32)
+            tmem_ld32(tm_addr + c * CHUNK_COLS + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[CHUNK_COLS - 32]));
+          if (RES) {
+            mbar_wait(smem_u32(&my_res[b]), (res_phase >> b) & 1u);
+            res_phase ^= 1u << b;
+          } else {
+            if (lane == 0) bulk_wait_read<NBUF - 1>();   // the store that last used this box has read it
+            __syncwarp();
+          }
+          tmem_wait_ld();
+        }
+        if (c == NCHUNK - 1) {
+          // every TMEM read of this accumulator stage has landed in registers: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_cluster(tempty_remote0 + acc * 8);
+            else         mbar_arrive(tempty_remote0 + acc * 8);
+          }
+        }
+        if (active) {
+          // bias columns past N are clamped to a valid address: those outputs are clipped by the TMA store
+          const float* bias_c = p.bias + col0;
+          const int n_last = p.N - 4 - col0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t addr = buf + row_off + ((static_cast<uint32_t>(j) ^ sw) << 4);
+            if (OUT_F32) {
+              const float4 bias4 = __ldg(reinterpret_cast<const float4*>(bias_c + min(4 * j, n_last)));
+              float4 v;
+              v.x = fmaf(__uint_as_float(r[4 * j + 0]), p.alpha, bias4.x);
+              v.y = fmaf(__uint_as_float(r[4 * j + 1]), p.alpha, bias4.y);
+              v.z = fmaf(__uint_as_float(r[4 * j + 2]), p.alpha, bias4.z);
+              v.w = fmaf(__uint_as_float(r[4 * j + 3]), p.alpha, bias4.w);
+              if (ACT == 1) {
+                v.x = gelu_erf_tanhform(v.x); v.y = gelu_erf_tanhform(v.y);
+                v.z = gelu_erf_tanhform(v.z); v.w = gelu_erf_tanhform(v.w);
+              }
+              if (RES) {
+                float4 rr;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(rr.x), "=f"(rr.y), "=f"(rr.z), "=f"(rr.w)
+                             : "r"(addr)
+                             : "memory");
+                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+              }
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
+                           "f"(v.w)
+                           : "memory");
+            } else {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias_c + min(8 * j, n_last)));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias_c + min(8 * j + 4, n_last)));
+              float v[8];
+              v[0] = fmaf(__uint_as_float(r[8 * j + 0]), p.alpha, b0.x);
+              v[1] = fmaf(__uint_as_float(r[8 * j + 1]), p.alpha, b0.y);
+              v[2] = fmaf(__uint_as_float(r[8 * j + 2]), p.alpha, b0.z);
+              v[3] = fmaf(__uint_as_float(r[8 * j + 3]), p.alpha, b0.w);
+              v[4] = fmaf(__uint_as_float(r[8 * j + 4]), p.alpha, b1.x);
+              v[5] = fmaf(__uint_as_float(r[8 * j + 5]), p.alpha, b1.y);
+              v[6] = fmaf(__uint_as_float(r[8 * j + 6]), p.alpha, b1.z);
+              v[7] = fmaf(__uint_as_float(r[8 * j + 7]), p.alpha, b1.w);
+              if (ACT == 1) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = gelu_erf_tanhform(v[i]);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(v[0], v[1])),
+                           "r"(pack_bf16x2(v[2], v[3])), "r"(pack_bf16x2(v[4], v[5])), "r"(pack_bf16x2(v[6], v[7]))
+                           : "memory");
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmOut, buf, col0, row0);
+            bulk_commit();
+            if (RES) bulk_wait_read<0>();   // box handed to the store engine: free for the next residual
+          }
+        }
+        if (RES && lane == 0) issue_res(g + NBUF);   // residual NBUF chunks ahead (crosses tile boundaries)
+        __syncwarp();
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) bulk_wait<0>();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    if (CG == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else         tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int CG, int STAGES, int NBUF>
+constexpr int pair_smem_bytes() {
+  return STAGES * (PG_BM * PG_BK * 2 + (PG_BN / CG) * PG_BK * 2) + PG_EPI_WARPS * NBUF * PG_BOX_BYTES +
+         (2 * STAGES + 4 + PG_EPI_WARPS * NBUF) * 8 + 16 + 1024;
+}
+
+template <int CG, int STAGES, int NBUF, int ACT, int RES, int OUT_F32>
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                       const CUtensorMap& tmRes, const PairGemmParams& p, cudaStream_t stream) {
+  constexpr int SMEM = pair_smem_bytes<CG, STAGES, NBUF>();
+  static_assert(SMEM <= 232448, "shared memory budget");
+  auto kern = gemm_pair_kernel<CG, STAGES, NBUF, ACT, RES, OUT_F32>;
+  static int max_pairs = 0;   // co-resident CTAs (CG = 1) or clusters (CG = 2)
+  if (max_pairs == 0) {
+    AGB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    if (CG == 2) {
+      cudaLaunchConfig_t qc = {};
+      qc.gridDim = dim3(sm_count(), 1, 1);
+      qc.blockDim = dim3(PG_THREADS, 1, 1);
+      qc.dynamicSmemBytes = SMEM;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      qc.attrs = at; qc.numAttrs = 1;
+      int n = 0;
+      AGB_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &qc));
+      AGB_REQUIRE(n > 0, "no co-resident CTA pair fits");
+      max_pairs = n < sm_count() / 2 ? n : sm_count() / 2;
+    } else {
+      max_pairs = sm_count();
+    }
+  }
+  const int tiles = ((p.M + PG_BM * CG - 1) / (PG_BM * CG)) * ((p.N + PG_BN - 1) / PG_BN);
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(pairs * CG, 1, 1);
+  cfg.blockDim = dim3(PG_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  AGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmRes, p));
+  return AGB_OK;
+}
+
+static int g_gemm_variant = 0;  // 0 auto, 1 legacy kernel only, 2 force CG=1, 3 force CG=2
+void set_gemm_variant(int v) { g_gemm_variant = v; }
+int get_gemm_variant() { return g_gemm_variant; }
+
+// Returns AGB_ERR_UNSUPPORTED when this kernel does not cover the request (the caller then uses the
+// first-generation kernel): narrow N, bf16 residual, fp32 residual with bf16 output, GELU + residual.
+int gemm_bf16_pair(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, int M, int N, int K,
+                   float alpha, const float* bias, int act, const bf16* res_bf16, const float* res_f32, int ldr,
+                   void* out, int ldo, int out_f32, cudaStream_t stream) {
+  if (g_gemm_variant == 1) return AGB_ERR_UNSUPPORTED;
+  if (N < 192 || res_bf16 != nullptr) return AGB_ERR_UNSUPPORTED;
+  if (res_f32 != nullptr && (!out_f32 || act != 0)) return AGB_ERR_UNSUPPORTED;
+  const int oes = out_f32 ? 4 : 2;
+  if (((long long)ldo * oes) % 16 != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0) return AGB_ERR_UNSUPPORTED;
+  if (res_f32 && ((((long long)ldr * 4) % 16) != 0 || (reinterpret_cast<uintptr_t>(res_f32) & 15) != 0))
+    return AGB_ERR_UNSUPPORTED;
+
+  // CTA pairs pay off once there is at least ~one full wave of 256-row tiles; small problems keep CG = 1
+  const long long tiles_pair = (long long)((M + 255) / 256) * ((N + PG_BN - 1) / PG_BN);
+  int cg = tiles_pair >= 2 * (sm_count() / 2) ? 2 : 1;
+  if (g_gemm_variant == 2) cg = 1;
+  if (g_gemm_variant == 3) cg = 2;
+
+  CUtensorMap tmA, tmB, tmOut, tmRes;
+  int rc;
+  if (!a_mn) rc = encode_tmap_2d_bf16(&tmA, A, K, M, (uint64_t)lda * 2, PG_BK, PG_BM);
+  else       rc = encode_tmap_2d_bf16(&tmA, A, M, K, (uint64_t)lda * 2, 64, PG_BK);
+  if (rc != AGB_OK) return rc;
+  if (!b_mn) rc = encode_tmap_2d_bf16(&tmB, B, K, N, (uint64_t)ldb * 2, PG_BK, PG_BN / cg);
+  else       rc = encode_tmap_2d_bf16(&tmB, B, N, K, (uint64_t)ldb * 2, 64, PG_BK);
+  if (rc != AGB_OK) return rc;
+  rc = encode_tmap_2d(&tmOut, out, oes, N, M, (uint64_t)ldo * oes, out_f32 ? 32 : 64, 32);
+  if (rc != AGB_OK) return rc;
+  if (res_f32) rc = encode_tmap_2d(&tmRes, res_f32, 4, N, M, (uint64_t)ldr * 4, 32, 32);
+  else         tmRes = tmOut;
+  if (rc != AGB_OK) return rc;
+
+  if (bias == nullptr) {   // the epilogue reads bias unconditionally: substitute zeros
+    static float* zero_bias = nullptr;
+    constexpr int ZB = 16384;
+    if (N > ZB) return AGB_ERR_UNSUPPORTED;
+    if (zero_bias == nullptr) {
+      AGB_CHECK_CUDA(cudaMalloc(&zero_bias, ZB * sizeof(float)));
+      AGB_CHECK_CUDA(cudaMemset(zero_bias, 0, ZB * sizeof(float)));
+    }
+    bias = zero_bias;
+  }
+  PairGemmParams p;
+  p.M = M; p.N = N; p.K = K; p.bias = bias; p.alpha = alpha; p.a_mn = a_mn; p.b_mn = b_mn;
+  const int res = res_f32 ? 2 : 0;
+#define AGB_PAIR_CASE(A_, R_, O_)                                                                        \
+  if (act == A_ && res == R_ && out_f32 == O_) {                                                         \
+    if (cg == 2) return launch_pair<2, (R_ ? 4 : 5), (R_ ? 3 : 2), A_, R_, O_>(tmA, tmB, tmOut, tmRes, p, stream); \
+    return launch_pair<1, 3, 2, A_, R_, O_>(tmA, tmB, tmOut, tmRes, p, stream);                         \
+  }
+  AGB_PAIR_CASE(0, 0, 0)
+  AGB_PAIR_CASE(0, 0, 1)
+  AGB_PAIR_CASE(0, 2, 1)
+  AGB_PAIR_CASE(1, 0, 0)
+  AGB_PAIR_CASE(1, 0, 1)
+#undef AGB_PAIR_CASE
+  return AGB_ERR_UNSUPPORTED;
+}
+
+}  // namespace agb

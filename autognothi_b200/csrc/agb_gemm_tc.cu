@@ -292,6 +292,10 @@ static int dispatch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
   return AGB_ERR_INVALID;
 }
 
+int gemm_bf16_pair(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, int M, int N, int K,
+                   float alpha, const float* bias, int act, const bf16* res_bf16, const float* res_f32, int ldr,
+                   void* out, int ldo, int out_f32, cudaStream_t stream);
+
 // Host entry used by the C-ABI (agb_api.cu).  lda/ldb are row pitches in elements of the stored
 // matrices: K-major operand = [rows, K] (pitch >= K); MN-major operand = [K, rows] (pitch >= rows).
 int gemm_bf16_tc(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, int M, int N,
@@ -312,6 +316,12 @@ int gemm_bf16_tc(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b
   AGB_REQUIRE(act == 0 || act == 1, "activation");
   AGB_REQUIRE(!(res_bf16 && res_f32), "one residual at most");
 
+  // second-generation kernel (CTA pairs + TMA epilogue) covers the hot shapes; this file keeps the rest
+  {
+    const int rc2 = gemm_bf16_pair(A, lda, a_mn, B, ldb, b_mn, M, N, K, alpha, bias, act, res_bf16, res_f32, ldr,
+                                   out, ldo, out_f32, stream);
+    if (rc2 != AGB_ERR_UNSUPPORTED) return rc2;
+  }
   const bool wide = N >= 192;
   const int BN = wide ? 256 : 128;
   CUtensorMap tmA, tmB;

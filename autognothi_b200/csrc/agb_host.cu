@@ -37,8 +37,9 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int encode_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t inner, uint64_t outer,
-                        uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+// elem_bytes: 2 = bf16, 4 = fp32.  SWIZZLE_128B boxes (inner box extent must be <= 128 bytes).
+int encode_tmap_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t inner, uint64_t outer,
+                   uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_last_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -48,16 +49,21 @@ int encode_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t inner, uint
   cuuint64_t strides[1] = {outer_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = fn(out, dt, 2, const_cast<void*>(gptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_last_error("cuTensorMapEncodeTiled(2d) failed: CUresult %d (inner=%llu outer=%llu stride=%llu box=%ux%u)",
-                   (int)r, (unsigned long long)inner, (unsigned long long)outer,
+    set_last_error("cuTensorMapEncodeTiled(2d) failed: CUresult %d (es=%d inner=%llu outer=%llu stride=%llu box=%ux%u)",
+                   (int)r, elem_bytes, (unsigned long long)inner, (unsigned long long)outer,
                    (unsigned long long)outer_stride_bytes, box_inner, box_outer);
     return AGB_ERR_CUDA;
   }
   return AGB_OK;
+}
+
+int encode_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t inner, uint64_t outer,
+                        uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+  return encode_tmap_2d(out, gptr, 2, inner, outer, outer_stride_bytes, box_inner, box_outer);
 }
 
 int encode_tmap_3d_bf16(CUtensorMap* out, const void* gptr, uint64_t d0, uint64_t d1, uint64_t d2,

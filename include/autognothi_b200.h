@@ -49,6 +49,11 @@ int agb_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb
                   const void* residual_bf16, const float* residual_f32, int ldr, int res_group,
                   int res_rows, void* out, int ldo, int out_is_f32, void* stream);
 
+/* Kernel selection for agb_gemm_bf16 (diagnostics / benchmarking): 0 = automatic, 1 = first-generation
+ * 1-CTA kernel only, 2 = TMA-epilogue kernel with one CTA per tile, 3 = TMA-epilogue kernel on CTA pairs
+ * (tcgen05 cta_group::2).  Returns the previous setting. */
+int agb_gemm_set_variant(int variant);
+
 
 /* fp32 CUDA-core GEMM with the same epilogue — the "exact" verification mode (fp32 rtol 1e-4 gate
  * of BASELINE.json).  A [M,K], B [N,K], C [M,N] row-major fp32. */

@@ -1,5 +1,6 @@
 // Native (no Python) check of the tcgen05 GEMM through the C-ABI.  Test infrastructure only.
-//   gemm_check M N K a_mn b_mn act bias res out_f32 [iters]
+//   gemm_check M N K a_mn b_mn act bias res out_f32 [iters] [variant]
+//   res: 0 none, 1 bf16, 2 fp32, 3 fp32 in place (out aliases the residual); variant: agb_gemm_set_variant
 // Verifies sampled (or all) output entries against a double-precision host dot product of the
 // bf16-rounded inputs and, when iters > 0, times the kernel with CUDA events.
 #include <cuda_bf16.h>
@@ -35,41 +36,54 @@ static double gelu_ref(double x) { return 0.5 * x * (1.0 + erf(x / sqrt(2.0))); 
 
 int main(int argc, char** argv) {
   if (argc < 10) {
-    printf("usage: gemm_check M N K a_mn b_mn act bias res out_f32 [iters]\n");
+    printf("usage: gemm_check M N K a_mn b_mn act bias res out_f32 [iters] [variant]\n");
     return 1;
   }
   const int M = atoi(argv[1]), N = atoi(argv[2]), K = atoi(argv[3]);
   const int a_mn = atoi(argv[4]), b_mn = atoi(argv[5]), act = atoi(argv[6]);
   const int use_bias = atoi(argv[7]), use_res = atoi(argv[8]), out_f32 = atoi(argv[9]);
   const int iters = argc > 10 ? atoi(argv[10]) : 0;
+  const int variant = argc > 11 ? atoi(argv[11]) : 0;
+  agb_gemm_set_variant(variant);
+  if (use_res >= 2 && !out_f32) { printf("fp32 residual needs out_f32\n"); return 1; }
 
   // stored shapes: K-major [rows, K]; MN-major [K, rows]
   const size_t a_elems = (size_t)M * K, b_elems = (size_t)N * K;
-  std::vector<__nv_bfloat16> hA(a_elems), hB(b_elems), hR((size_t)M * N);
-  std::vector<float> fA(a_elems), fB(b_elems), fR((size_t)M * N), hBias(N);
+  const size_t r_elems = use_res ? (size_t)M * N : 1;
+  std::vector<__nv_bfloat16> hA(a_elems), hB(b_elems), hR(r_elems);
+  std::vector<float> fA(a_elems), fB(b_elems), fR(r_elems), hBias(N);
   for (size_t i = 0; i < a_elems; ++i) { hA[i] = __float2bfloat16(urand()); fA[i] = __bfloat162float(hA[i]); }
   for (size_t i = 0; i < b_elems; ++i) { hB[i] = __float2bfloat16(urand()); fB[i] = __bfloat162float(hB[i]); }
-  for (size_t i = 0; i < (size_t)M * N; ++i) { hR[i] = __float2bfloat16(urand()); fR[i] = __bfloat162float(hR[i]); }
+  for (size_t i = 0; i < r_elems; ++i) {
+    const float v = urand();
+    hR[i] = __float2bfloat16(v);
+    fR[i] = use_res >= 2 ? v : __bfloat162float(hR[i]);
+  }
   for (int i = 0; i < N; ++i) hBias[i] = urand();
 
   __nv_bfloat16 *dA, *dB, *dR;
-  float* dBias;
+  float *dBias, *dRf;
   void* dC;
   CK(cudaMalloc(&dA, a_elems * 2));
   CK(cudaMalloc(&dB, b_elems * 2));
-  CK(cudaMalloc(&dR, (size_t)M * N * 2));
+  CK(cudaMalloc(&dR, r_elems * 2));
   CK(cudaMalloc(&dBias, N * 4));
+  CK(cudaMalloc(&dRf, r_elems * 4));
+  CK(cudaMemcpy(dRf, fR.data(), r_elems * 4, cudaMemcpyHostToDevice));
   CK(cudaMalloc(&dC, (size_t)M * N * (out_f32 ? 4 : 2)));
   CK(cudaMemcpy(dA, hA.data(), a_elems * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dB, hB.data(), b_elems * 2, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(dR, hR.data(), (size_t)M * N * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dR, hR.data(), r_elems * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dBias, hBias.data(), N * 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(dC, 0xff, (size_t)M * N * (out_f32 ? 4 : 2)));
+  if (use_res == 3) CK(cudaMemcpy(dC, fR.data(), (size_t)M * N * 4, cudaMemcpyHostToDevice));
 
   const int lda = a_mn ? M : K, ldb = b_mn ? N : K;
   auto run = [&]() {
     return agb_gemm_bf16(dA, lda, a_mn, dB, ldb, b_mn, M, N, K, 1.0f, use_bias ? dBias : nullptr, act,
-                         use_res ? dR : nullptr, nullptr, N, 0, 0, dC, N, out_f32, nullptr);
+                         use_res == 1 ? dR : nullptr,
+                         use_res == 2 ? dRf : (use_res == 3 ? static_cast<const float*>(dC) : nullptr), N, 0, 0, dC, N,
+                         out_f32, nullptr);
   };
   int rc = run();
   if (rc != 0) { printf("agb_gemm_bf16 rc=%d: %s\n", rc, agb_last_error()); return 3; }
@@ -112,8 +126,8 @@ int main(int argc, char** argv) {
     if (err > max_err) max_err = err;
     if (fabs(acc) > max_ref) max_ref = fabs(acc);
   }
-  printf("gemm M=%d N=%d K=%d a_mn=%d b_mn=%d act=%d bias=%d res=%d f32=%d: checked=%zu bad=%zu max_err=%.3e max_ref=%.3e %s\n",
-         M, N, K, a_mn, b_mn, act, use_bias, use_res, out_f32, nsamples, bad, max_err, max_ref,
+  printf("gemm v%d M=%d N=%d K=%d a_mn=%d b_mn=%d act=%d bias=%d res=%d f32=%d: checked=%zu bad=%zu max_err=%.3e max_ref=%.3e %s\n",
+         variant, M, N, K, a_mn, b_mn, act, use_bias, use_res, out_f32, nsamples, bad, max_err, max_ref,
          bad ? "FAIL" : "PASS");
 
   if (iters > 0 && !bad) {
