@@ -10,6 +10,11 @@ int gemm_bf16_tc(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b
                  int K, float alpha, const float* bias, int act, const bf16* res_bf16,
                  const float* res_f32, int ldr, int res_group, int res_rows, void* out, int ldo,
                  int out_f32, cudaStream_t stream);
+void set_attention_variant(int v);
+void set_attention_bwd_variant(int v);
+int get_attention_bwd_variant();
+void set_attention_trace(long long* t);
+int get_attention_variant();
 void set_gemm_variant(int v);
 int get_gemm_variant();
 int gemm_f32(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, int M, int N, int K, float alpha,
@@ -88,6 +93,23 @@ int agb_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb
                            res_rows, out, ldo, out_is_f32, static_cast<cudaStream_t>(stream));
 }
 
+
+int agb_attention_set_variant(int variant) {
+  const int prev = agb::get_attention_variant();
+  agb::set_attention_variant(variant);
+  return prev;
+}
+
+int agb_attention_set_trace(void* trace) {
+  agb::set_attention_trace(static_cast<long long*>(trace));
+  return AGB_OK;
+}
+
+int agb_attention_bwd_set_variant(int variant) {
+  const int prev = agb::get_attention_bwd_variant();
+  agb::set_attention_bwd_variant(variant);
+  return prev;
+}
 
 int agb_gemm_set_variant(int variant) {
   const int prev = agb::get_gemm_variant();

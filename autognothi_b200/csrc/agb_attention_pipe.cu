@@ -1,0 +1,401 @@
+// Fused key-masked attention, second generation: a warp-specialised software pipeline per SM.
+//
+// Same contract as agb_attention_tc.cu (reference models/vanilla_vit.py:444-463, models/vanilla_bert.py:
+// 517-537; bf16 in/out, head dim 64, T <= 256) — the (N,h,T,T) score tensor never leaves the SM and
+// masked copies of the input are never built.  Round-1 measurement: the first-generation kernel ran one
+// (row, head, m-tile) at a time per CTA and spent 18 % of the step on 4 % of the FLOPs, ~3x off its MUFU
+// bound, because load -> mask -> QK^T -> softmax -> PV -> store were serialised and only overlapped
+// through 2 CTAs/SM.  Here ONE persistent CTA per SM pipelines "items" (unit = (row, head), m-tile):
+//   warp 0      TMA producer: K/V of a unit into a 3-deep ring, Q tiles into a 2-deep ring
+//   warp 1      tcgen05 issuer for S_k = Q_k K^T (into TMEM region k&1)
+//   warp 2      tcgen05 issuer for O_k = P_k V, the moment P_k arrives (independent of warp 1: no head-of-line wait)
+//   warp 3      mask prep (ViT): zero the K rows of masked keys in smem => logit exactly 0 ("scores * mask")
+//   warps 4-11  two softmax groups of 4 warps (thread = query row = TMEM lane); group k&1 owns item k,
+//               so the MUFU-bound exp of one item overlaps the MMAs / epilogue / loads of its neighbours.
+// Softmax: pass 1 row max, pass 2 P = exp2((s - max) * scale*log2e) -> bf16 pairs written back into TMEM over
+// the consumed S columns and used as the A operand FROM TENSOR MEMORY of the second MMA; the row sum is
+// accumulated in fp32 registers (key padding and, for BERT, masked keys are forced to P = 0 = "finfo.min
+// additive mask", so neither numerator nor denominator sees them).
+#include "agb_common.cuh"
+
+namespace agb {
+
+constexpr int AP_D = 64;
+constexpr int AP_THREADS = 384;
+constexpr int AP_TMEM_COLS = 512;
+constexpr int AP_O_COL = 128;      // O accumulator at columns [128, 192) of the group's 256-column region
+constexpr int AP_KV_RING = 3;
+constexpr int AP_PREP_THREADS = 32;
+
+struct AttPipeParams {
+  const uint32_t* mask;
+  int words;
+  int rows, T, H, heads, mode;
+  int NK;            // keys padded to a multiple of 16
+  int units;         // rows * heads
+  int mtiles;        // ceil(T / 128)
+  bf16* ctx;
+  long long* trace;  // optional [items][8] clock64 timestamps of CTA 0 (diagnostics), or nullptr
+};
+
+#define AP_TRACE(k, slot)                                                             \
+  do {                                                                                \
+    if (p.trace != nullptr && blockIdx.x == 0 && (k) < 64 && lane == 0) p.trace[(k) * 8 + (slot)] = clock64(); \
+  } while (0)
+
+// ---- softmax helpers (thread = one query row) ---------------------------------------------------------
+template <int W>
+__device__ __forceinline__ void ap_load(uint32_t addr, uint32_t (&s)[W]) {
+  if (W == 64) {
+    tmem_ld32(addr, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+    tmem_ld32(addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+  } else {
+    tmem_ld16(addr, *reinterpret_cast<uint32_t(*)[16]>(&s[0]));
+  }
+  tmem_wait_ld();
+}
+
+template <int W, bool MASKED>
+__device__ __forceinline__ float ap_max_chunk(uint32_t addr, float m, uint32_t live_lo, uint32_t live_hi) {
+  uint32_t s[W];
+  ap_load<W>(addr, s);
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    float v = __uint_as_float(s[j]);
+    if (MASKED && !(((j < 32 ? live_lo : live_hi) >> (j & 31)) & 1u)) v = -INFINITY;
+    m = fmaxf(m, v);
+  }
+  return m;
+}
+
+template <int W, bool MASKED>
+__device__ __forceinline__ float ap_exp_chunk(uint32_t s_addr, uint32_t p_addr, float scale_log2, float m_scaled,
+                                              uint32_t live_lo, uint32_t live_hi) {
+  uint32_t s[W];
+  ap_load<W>(s_addr, s);
+  uint32_t pk[W / 2];
+  float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+#pragma unroll
+  for (int j = 0; j < W / 2; ++j) {
+    float a = __uint_as_float(s[2 * j]), b = __uint_as_float(s[2 * j + 1]);
+    if (MASKED) {
+      const int j0 = 2 * j, j1 = 2 * j + 1;
+      if (!(((j0 < 32 ? live_lo : live_hi) >> (j0 & 31)) & 1u)) a = -INFINITY;
+      if (!(((j1 < 32 ? live_lo : live_hi) >> (j1 & 31)) & 1u)) b = -INFINITY;
+    }
+    const float e0 = ex2_approx(fmaf(a, scale_log2, -m_scaled));
+    const float e1 = ex2_approx(fmaf(b, scale_log2, -m_scaled));
+    if (j & 1) { sum2 += e0; sum3 += e1; } else { sum0 += e0; sum1 += e1; }
+    pk[j] = pack_bf16x2(e0, e1);
+  }
+  if (W == 64) tmem_st32(p_addr, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+  else         tmem_st8(p_addr, *reinterpret_cast<uint32_t(*)[8]>(&pk[0]));
+  return (sum0 + sum1) + (sum2 + sum3);
+}
+
+// live-column bits of the W-wide chunk starting at key c0: key < T, and (BERT) coalition bit set
+__device__ __forceinline__ void ap_live_bits(const uint32_t* mrow, int words, int mode, int T, int c0, int W,
+                                             uint32_t& lo, uint32_t& hi) {
+  const int nvalid = min(max(T - c0, 0), W);
+  const uint64_t valid = nvalid >= 64 ? ~0ull : ((1ull << nvalid) - 1ull);
+  uint64_t live = valid;
+  if (mode == AGB_MASK_NEGINF) {
+    const int w0 = c0 >> 5;              // c0 is a multiple of 16; chunks of 64 start on a word boundary
+    uint64_t bits = 0;
+    if ((c0 & 31) == 0) {
+      bits = (w0 < words ? (uint64_t)__ldg(mrow + w0) : 0ull) | ((w0 + 1 < words ? (uint64_t)__ldg(mrow + w0 + 1) : 0ull) << 32);
+    } else {
+      bits = (w0 < words ? (uint64_t)(__ldg(mrow + w0) >> 16) : 0ull) |
+             ((w0 + 1 < words ? (uint64_t)__ldg(mrow + w0 + 1) : 0ull) << 16);
+    }
+    live &= bits;
+  }
+  lo = (uint32_t)live;
+  hi = (uint32_t)(live >> 32);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(AP_THREADS, 1)
+attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                      const AttPipeParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int kvb = p.NK * 128;                  // bytes of one K (or V) tile
+  uint8_t* sQ = smem;                          // [2][128 x 128 B]
+  uint8_t* sKV = smem + 2 * 16384;             // [AP_KV_RING][K | V]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + AP_KV_RING * 2 * kvb);
+  uint64_t* q_full = bars;                     // [2]
+  uint64_t* q_empty = bars + 2;                // [2]
+  uint64_t* kv_full = bars + 4;                // [3]
+  uint64_t* kv_prep = bars + 7;                // [3]
+  uint64_t* kv_empty = bars + 10;              // [3]
+  uint64_t* s_full = bars + 13;                // [2]
+  uint64_t* p_full = bars + 15;                // [2]
+  uint64_t* o_full = bars + 17;                // [2]
+  uint64_t* o_free = bars + 19;                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+
+  const int warp = warp_idx_uniform();
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&q_full[i]), 1);
+      mbar_init(smem_u32(&q_empty[i]), 1);
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&p_full[i]), 4);
+      mbar_init(smem_u32(&o_full[i]), 1);
+      mbar_init(smem_u32(&o_free[i]), 4);
+    }
+    for (int i = 0; i < AP_KV_RING; ++i) {
+      mbar_init(smem_u32(&kv_full[i]), 1);
+      mbar_init(smem_u32(&kv_prep[i]), AP_PREP_THREADS);
+      mbar_init(smem_u32(&kv_empty[i]), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), AP_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int H = p.H, T = p.T, NK = p.NK, mt = p.mtiles;
+  const int grid = gridDim.x;
+  const int nu = (p.units - (int)blockIdx.x + grid - 1) / grid;   // units of this CTA
+  const int n_items = nu * mt;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    const uint32_t e = elect_one();
+    for (int k = 0; k < n_items; ++k) {
+      const int ui = k / mt, m = k - ui * mt;
+      const int u = blockIdx.x + ui * grid;
+      const int row = u / p.heads, head = u - row * p.heads;
+      if (m == 0) {
+        const int b = ui % AP_KV_RING, n = ui / AP_KV_RING;
+        if (n > 0) mbar_wait(smem_u32(&kv_empty[b]), (n - 1) & 1);
+        const uint32_t bar = smem_u32(&kv_full[b]);
+        mbar_arrive_expect_tx_e(e, bar, 2 * kvb);
+        const uint32_t dst = smem_u32(sKV + b * 2 * kvb);
+        tma_load_3d_e(e, dst, &tmKV, bar, H + head * AP_D, 0, row);
+        tma_load_3d_e(e, dst + kvb, &tmKV, bar, 2 * H + head * AP_D, 0, row);
+        AP_TRACE(k, 0);
+      }
+      const int qb = k & 1, nq = k >> 1;
+      if (nq > 0) mbar_wait(smem_u32(&q_empty[qb]), (nq - 1) & 1);
+      const uint32_t qbar = smem_u32(&q_full[qb]);
+      mbar_arrive_expect_tx_e(e, qbar, 16384);
+      tma_load_3d_e(e, smem_u32(sQ + qb * 16384), &tmQ, qbar, head * AP_D, m * 128, row);
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    const uint32_t e = elect_one();
+    const uint32_t idesc_s = make_idesc_bf16(128, NK, 0, 0);
+    const uint64_t dk0 = make_smem_desc_sw128(0, 16, 1024);       // K-major operands (Q, K)
+    const uint32_t sq0 = smem_u32(sQ) >> 4, skv0 = smem_u32(sKV) >> 4;
+    const uint32_t kvb16 = (uint32_t)kvb >> 4;
+
+    // S issuer.  S_k reuses the TMEM region of item k-2: o_free (that item's epilogue has drained O) implies its
+    // PV has completed, so no ordering with the PV issuer (warp 2) is needed beyond the barriers.
+    for (int k = 0; k < n_items; ++k) {
+      const int ui = k / mt, m = k - ui * mt;
+      const int b = ui % AP_KV_RING, g = k & 1, n = k >> 1;
+      if (m == 0) mbar_wait(smem_u32(&kv_prep[b]), (ui / AP_KV_RING) & 1);
+      mbar_wait(smem_u32(&q_full[g]), n & 1);
+      if (n > 0) mbar_wait(smem_u32(&o_free[g]), (n - 1) & 1);
+      tc_fence_after();
+      const uint32_t aq = sq0 + g * (16384 >> 4);
+      const uint32_t ak = skv0 + b * 2 * kvb16;
+#pragma unroll
+      for (int kk = 0; kk < AP_D / 16; ++kk)
+        umma_ss_e<1>(e, tmem_base + g * 256, dk0 + (aq + kk * 2), dk0 + (ak + kk * 2), idesc_s, kk != 0 ? 1u : 0u);
+      umma_commit_e<1>(e, smem_u32(&s_full[g]));
+      umma_commit_e<1>(e, smem_u32(&q_empty[g]));
+      AP_TRACE(k, 1);
+    }
+  } else if (warp == 2) {
+    // ------------------------------ PV issuer: O_k = P_k V as soon as group k&1 has written P_k ------------------------------
+    const uint32_t e = elect_one();
+    const uint32_t idesc_o = make_idesc_bf16(128, AP_D, 0, 1);
+    const uint64_t dv0 = make_smem_desc_sw128(0, 8192, 1024);     // MN-major V, one 64-column atom (LBO unused)
+    const uint32_t skv0 = smem_u32(sKV) >> 4;
+    const uint32_t kvb16 = (uint32_t)kvb >> 4;
+    for (int k = 0; k < n_items; ++k) {
+      const int ui = k / mt, m = k - ui * mt;
+      const int b = ui % AP_KV_RING, g = k & 1, n = k >> 1;
+      mbar_wait(smem_u32(&p_full[g]), n & 1);
+      AP_TRACE(k, 2);
+      tc_fence_after();
+      const uint32_t av = skv0 + b * 2 * kvb16 + kvb16;
+      const uint32_t d_o = tmem_base + g * 256 + AP_O_COL, a_p = tmem_base + g * 256;
+      const uint64_t dv = dv0 + av;
+      const int nks = NK / 16;
+#pragma unroll 4
+      for (int ks = 0; ks < nks; ++ks)
+        umma_ts_e(e, d_o, a_p + ks * 8, dv + ks * (2048 >> 4), idesc_o, ks != 0 ? 1u : 0u);
+      umma_commit_e<1>(e, smem_u32(&o_full[g]));
+      if (m == mt - 1) umma_commit_e<1>(e, smem_u32(&kv_empty[b]));
+      AP_TRACE(k, 3);
+    }
+  } else if (warp == 3) {
+    // ------------------------------ mask prep (ViT: zero masked K rows) ------------------------------
+    const int tid = lane;
+    for (int ui = 0; ui < nu; ++ui) {
+      const int b = ui % AP_KV_RING, n = ui / AP_KV_RING;
+      mbar_wait(smem_u32(&kv_full[b]), n & 1);
+      if (MODE == AGB_MASK_MUL0) {
+        const int u = blockIdx.x + ui * grid;
+        const int row = u / p.heads;
+        const uint32_t* mrow = p.mask + (long long)row * p.words;
+        uint8_t* sK = sKV + b * 2 * kvb;
+        for (int j = tid; j < T; j += AP_PREP_THREADS) {
+          if (!((__ldg(mrow + (j >> 5)) >> (j & 31)) & 1u)) {
+            uint4* kr = reinterpret_cast<uint4*>(sK + j * 128);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) kr[c] = make_uint4(0, 0, 0, 0);
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(smem_u32(&kv_prep[b]));
+    }
+  } else {
+    // ------------------------------ softmax + epilogue (2 groups x 128 threads) ------------------------------
+    const int g = (warp - 4) >> 2;
+    const int qd = warp & 3;                        // TMEM lane quarter this warp may touch
+    const int r = qd * 32 + lane;                   // query row within the tile = TMEM lane
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + g * 256;
+    const float scale_log2 = 0.125f * 1.4426950408889634f;
+    for (int k = g; k < n_items; k += 2) {
+      const int n = k >> 1;
+      const int ui = k / mt, m = k - ui * mt;
+      const int u = blockIdx.x + ui * grid;
+      const int row = u / p.heads, head = u - row * p.heads;
+      const uint32_t* mrow = p.mask + (long long)row * p.words;
+      const bool warp_live = (m * 128 + qd * 32) < T;     // warp-uniform: any real query row in this warp?
+      mbar_wait(smem_u32(&s_full[g]), n & 1);
+      if (qd == 0) AP_TRACE(k, 4);
+      tc_fence_after();
+      float inv = 0.f;
+      if (warp_live) {
+        // ViT: keys [0, n_fast) are all live (masked keys keep their exact-0 logit) -> no per-element selects;
+        // the chunk holding the T boundary (and every BERT chunk) takes the masked variant.
+        const int n_fast = (MODE == AGB_MASK_MUL0) ? (T / 64) * 64 : 0;
+        // pass 1: row maximum
+        float mx = -INFINITY;
+        int c0 = 0;
+        for (; c0 < n_fast; c0 += 64) mx = ap_max_chunk<64, false>(lane_addr + c0, mx, 0u, 0u);
+        for (; c0 + 64 <= NK; c0 += 64) {
+          uint32_t lo, hi;
+          ap_live_bits(mrow, p.words, MODE, T, c0, 64, lo, hi);
+          mx = ap_max_chunk<64, true>(lane_addr + c0, mx, lo, hi);
+        }
+        for (; c0 < NK; c0 += 16) {
+          uint32_t lo, hi;
+          ap_live_bits(mrow, p.words, MODE, T, c0, 16, lo, hi);
+          mx = ap_max_chunk<16, true>(lane_addr + c0, mx, lo, hi);
+        }
+        const float m_scaled = mx * scale_log2;
+        // pass 2: P = exp2(s*scale - max*scale) -> bf16 pairs -> TMEM (overlaying consumed S columns)
+        float sum = 0.f;
+        c0 = 0;
+        for (; c0 < n_fast; c0 += 64)
+          sum += ap_exp_chunk<64, false>(lane_addr + c0, lane_addr + (c0 >> 1), scale_log2, m_scaled, 0u, 0u);
+        for (; c0 + 64 <= NK; c0 += 64) {
+          uint32_t lo, hi;
+          ap_live_bits(mrow, p.words, MODE, T, c0, 64, lo, hi);
+          sum += ap_exp_chunk<64, true>(lane_addr + c0, lane_addr + (c0 >> 1), scale_log2, m_scaled, lo, hi);
+        }
+        for (; c0 < NK; c0 += 16) {
+          uint32_t lo, hi;
+          ap_live_bits(mrow, p.words, MODE, T, c0, 16, lo, hi);
+          sum += ap_exp_chunk<16, true>(lane_addr + c0, lane_addr + (c0 >> 1), scale_log2, m_scaled, lo, hi);
+        }
+        tmem_wait_st();
+        inv = 1.0f / sum;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&p_full[g]));
+      if (qd == 0) AP_TRACE(k, 5);
+      // epilogue: O / rowsum -> bf16 ctx
+      mbar_wait(smem_u32(&o_full[g]), n & 1);
+      if (qd == 0) AP_TRACE(k, 6);
+      tc_fence_after();
+      uint32_t o[64];
+      if (warp_live) ap_load<64>(lane_addr + AP_O_COL, o);
+      // O is in registers: release the TMEM region (the next S_k+2 may overwrite it) BEFORE scaling / storing
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&o_free[g]));
+      if (qd == 0) AP_TRACE(k, 7);
+      if (warp_live) {
+        const int tq = m * 128 + r;
+        if (tq < T) {
+          bf16* dst = p.ctx + ((long long)row * T + tq) * H + head * AP_D;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(o[8 * c + 0]) * inv, __uint_as_float(o[8 * c + 1]) * inv);
+            w.y = pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv);
+            w.z = pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv);
+            w.w = pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv);
+            *reinterpret_cast<uint4*>(dst + 8 * c) = w;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, AP_TMEM_COLS);
+}
+
+static long long* g_attention_trace = nullptr;
+void set_attention_trace(long long* t) { g_attention_trace = t; }
+static int g_attention_variant = 0;   // 0 auto (pipelined), 1 first-generation kernel
+void set_attention_variant(int v) { g_attention_variant = v; }
+int get_attention_variant() { return g_attention_variant; }
+
+int attention_pipe(const bf16* qkv, const uint32_t* mask, int words, int rows, int T, int H, int heads, int mode,
+                   bf16* ctx, cudaStream_t stream) {
+  if (g_attention_variant == 1) return AGB_ERR_UNSUPPORTED;
+  AttPipeParams p;
+  p.mask = mask; p.words = words; p.rows = rows; p.T = T; p.H = H; p.heads = heads; p.mode = mode;
+  p.NK = (T + 15) / 16 * 16;
+  p.units = rows * heads;
+  p.mtiles = (T + 127) / 128;
+  p.ctx = ctx;
+  p.trace = g_attention_trace;
+  CUtensorMap tmQ, tmKV;
+  int rc = encode_tmap_3d_bf16(&tmQ, qkv, 3 * (uint64_t)H, T, rows, (uint64_t)3 * H * 2, (uint64_t)T * 3 * H * 2,
+                               AP_D, 128, 1);
+  if (rc != AGB_OK) return rc;
+  rc = encode_tmap_3d_bf16(&tmKV, qkv, 3 * (uint64_t)H, T, rows, (uint64_t)3 * H * 2, (uint64_t)T * 3 * H * 2,
+                           AP_D, p.NK, 1);
+  if (rc != AGB_OK) return rc;
+  const int smem = 1024 + 2 * 16384 + AP_KV_RING * 2 * p.NK * 128 + 256;
+  static int configured_smem = 0;
+  if (smem > configured_smem) {
+    AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<AGB_MASK_MUL0>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<AGB_MASK_NEGINF>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured_smem = smem;
+  }
+  const int grid = p.units < sm_count() ? p.units : sm_count();
+  if (mode == AGB_MASK_MUL0) attention_pipe_kernel<AGB_MASK_MUL0><<<grid, AP_THREADS, smem, stream>>>(tmQ, tmKV, p);
+  else                       attention_pipe_kernel<AGB_MASK_NEGINF><<<grid, AP_THREADS, smem, stream>>>(tmQ, tmKV, p);
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+}  // namespace agb

@@ -247,6 +247,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, ATT_TMEM_COLS);
 }
 
+int attention_pipe(const bf16* qkv, const uint32_t* mask, int words, int rows, int T, int H, int heads, int mode,
+                   bf16* ctx, cudaStream_t stream);
+
 int attention_tc(const bf16* qkv, const uint32_t* mask, int words, int rows, int T, int H, int heads,
                  int mode, bf16* ctx, cudaStream_t stream) {
   AGB_REQUIRE(rows >= 0 && T > 0 && heads > 0 && H == heads * ATT_D, "tensor-core attention needs head dim 64");
@@ -259,6 +262,10 @@ int attention_tc(const bf16* qkv, const uint32_t* mask, int words, int rows, int
   if (rows == 0) return AGB_OK;
   AGB_REQUIRE(qkv && mask && ctx, "null pointer");
   AGB_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(ctx) & 15) == 0, "alignment");
+  {  // second-generation pipelined kernel (agb_attention_pipe.cu); this file keeps the first generation
+    const int rc2 = attention_pipe(qkv, mask, words, rows, T, H, heads, mode, ctx, stream);
+    if (rc2 != AGB_ERR_UNSUPPORTED) return rc2;
+  }
   AttParams p;
   p.mask = mask; p.words = words; p.rows = rows; p.T = T; p.H = H; p.heads = heads; p.mode = mode;
   p.NK = (T + 15) / 16 * 16;

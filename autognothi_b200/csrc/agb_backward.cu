@@ -411,6 +411,12 @@ attention_bwd_f32_kernel(const float* __restrict__ qkv, const float* __restrict_
   }
 }
 
+int attention_bwd_tc(const bf16* qkv, const bf16* dctx, const uint32_t* mask, int words, int rows, int T, int H,
+                     int heads, int mode, bf16* dqkv, cudaStream_t stream);
+static int g_attention_bwd_variant = 0;   // 0 auto (tensor cores for bf16), 1 CUDA-core kernel only
+void set_attention_bwd_variant(int v) { g_attention_bwd_variant = v; }
+int get_attention_bwd_variant() { return g_attention_bwd_variant; }
+
 int attention_bwd(const void* qkv, const void* dctx, int io_bf16, const uint32_t* mask, int words, int rows, int T,
                   int H, int heads, int mode, void* dqkv, cudaStream_t st) {
   AGB_REQUIRE(rows >= 0 && T > 0 && heads > 0 && H == heads * AB_D, "attention backward needs head dim 64");
@@ -422,6 +428,11 @@ int attention_bwd(const void* qkv, const void* dctx, int io_bf16, const uint32_t
   }
   if (rows == 0) return AGB_OK;
   AGB_REQUIRE(qkv && dctx && mask && dqkv, "null pointer");
+  if (io_bf16 && g_attention_bwd_variant == 0) {
+    const int rc2 = attention_bwd_tc(static_cast<const bf16*>(qkv), static_cast<const bf16*>(dctx), mask, words, rows, T, H,
+                                     heads, mode, static_cast<bf16*>(dqkv), st);
+    if (rc2 != AGB_ERR_UNSUPPORTED) return rc2;
+  }
   const int nw = 8;
   if (io_bf16) {
     const size_t smem = (size_t)4 * T * AB_LD * 2 + (size_t)2 * T * 4 + (size_t)nw * 2 * T * 4;

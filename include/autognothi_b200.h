@@ -120,6 +120,14 @@ int agb_masked_attention_simt(const void* qkv, int io_is_bf16, const uint32_t* m
 int agb_masked_attention_bf16(const void* qkv, const uint32_t* mask, int words, int rows, int T,
                               int H, int heads, int mode, void* ctx, void* stream);
 
+/* Kernel selection for agb_masked_attention_bf16 (diagnostics): 0 = automatic (pipelined, one CTA per SM),
+ * 1 = first-generation kernel.  Returns the previous setting. */
+int agb_attention_set_variant(int variant);
+/* Same for agb_masked_attention_bwd: 0 = automatic (tcgen05 kernel for bf16), 1 = CUDA-core kernel. */
+int agb_attention_bwd_set_variant(int variant);
+/* Diagnostics: device buffer of 64 x 8 int64 receiving clock64() pipeline timestamps of CTA 0 (NULL = off). */
+int agb_attention_set_trace(void* trace);
+
 /* ---- explainer head + efficiency normalisation (reference models/vanilla_vit.py:123-129,
  *      models/shapley.py:82-93) --------------------------------------------------------------- */
 /* h (B*T, E) fp32|bf16, W (C,E), bias (C), grand (B,C), null (C) -> phi (B,C,T-1); pred (B,T,C)
