@@ -15,6 +15,12 @@ void set_attention_bwd_variant(int v);
 int get_attention_bwd_variant();
 void set_attention_trace(long long* t);
 int get_attention_variant();
+int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, int M, int N, int K,
+                      float alpha, const float* bias, int act, const bf16* res_bf16, const float* res_f32, int ldr,
+                      void* out, int ldo, int out_f32, const float* ln_stats, int ln_parts, const float* ln_colsum,
+                      float ln_eps, bf16* out16, int ldo16, float* stats_out, cudaStream_t stream);
+int rowstats_cast(const float* x, long long ldx, int rows, int H, bf16* out, long long ldo, float* stats,
+                  cudaStream_t st);
 void set_gemm_variant(int v);
 int get_gemm_variant();
 int gemm_f32(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, int M, int N, int K, float alpha,
@@ -109,6 +115,27 @@ int agb_attention_bwd_set_variant(int variant) {
   const int prev = agb::get_attention_bwd_variant();
   agb::set_attention_bwd_variant(variant);
   return prev;
+}
+
+int agb_gemm_bf16_fused(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias,
+                        int act, const float* residual_f32, int ldr, void* out, int ldo, int out_is_f32,
+                        const float* ln_stats, int ln_parts, const float* ln_colsum, float ln_eps,
+                        void* out_bf16_copy, int ldo_copy, float* stats_out, void* stream) {
+  AGB_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && out, "operands");
+  AGB_REQUIRE((N % 4) == 0 && (lda % 8) == 0 && (ldb % 8) == 0, "alignment");
+  AGB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0, "alignment");
+  const int rc = agb::gemm_bf16_pair_ex(static_cast<const bf16*>(A), lda, 0, static_cast<const bf16*>(B), ldb, 0, M, N, K,
+                                        1.0f, bias, act, nullptr, residual_f32, ldr, out, ldo, out_is_f32, ln_stats,
+                                        ln_parts, ln_colsum, ln_eps, static_cast<bf16*>(out_bf16_copy), ldo_copy,
+                                        stats_out, ST(stream));
+  if (rc == AGB_ERR_UNSUPPORTED)
+    agb::set_last_error("agb_gemm_bf16_fused: shape / epilogue combination not covered (M=%d N=%d K=%d act=%d)", M, N, K, act);
+  return rc;
+}
+int agb_gemm_stats_parts(int N) { return 2 * ((N + 255) / 256); }
+int agb_rowstats_cast(const float* x, long long ldx, int rows, int H, void* out_bf16, long long ldo, float* stats,
+                      void* stream) {
+  return agb::rowstats_cast(x, ldx, rows, H, static_cast<bf16*>(out_bf16), ldo, stats, ST(stream));
 }
 
 int agb_gemm_set_variant(int variant) {

@@ -148,6 +148,44 @@ int layernorm(const void* x, int in_bf16, long long in_stride, int rows, int H, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Entry point of the LayerNorm-folded GEMM chain (agb_gemm_bf16_fused): bf16 copy of the fp32 residual
+// stream + per-row (sum, sum of squares).  One warp per row, the row is read from HBM once.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rowstats_cast_kernel(const float* __restrict__ x, long long ldx, int rows, int H, bf16* __restrict__ out,
+                     long long ldo, float2* __restrict__ stats) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + (long long)row * ldx;
+  float s = 0.f, ss = 0.f;
+  for (int c = lane * 4; c < H; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    s += (v.x + v.y) + (v.z + v.w);
+    ss = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ss))));
+    uint2 pk;
+    pk.x = pack_bf16x2(v.x, v.y);
+    pk.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + (long long)row * ldo + c) = pk;
+  }
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  if (lane == 0) stats[row] = make_float2(s, ss);
+}
+
+int rowstats_cast(const float* x, long long ldx, int rows, int H, bf16* out, long long ldo, float* stats,
+                  cudaStream_t st) {
+  AGB_REQUIRE(rows >= 0 && H > 0 && (H % 4) == 0 && (ldx % 4) == 0 && (ldo % 4) == 0, "row width / strides must be multiples of 4");
+  if (rows == 0) return AGB_OK;
+  AGB_REQUIRE(x && out && stats, "null pointer");
+  const int warps = 8;
+  rowstats_cast_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, st>>>(x, ldx, rows, H, out, ldo,
+                                                                          reinterpret_cast<float2*>(stats));
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // fp32 -> bf16 cast (weights, once per load) and bf16 -> fp32
 // ------------------------------------------------------------------------------------------------
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n) {

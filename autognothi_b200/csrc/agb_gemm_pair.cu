@@ -33,14 +33,26 @@ struct PairGemmParams {
   const float* bias;  // [N] fp32 or nullptr
   float alpha;
   int a_mn, b_mn;     // operand majorness (0 = K-major, 1 = MN-major)
+  // LNIN: LayerNorm folded into this GEMM.  A holds the UN-normalised rows (bf16 copy of x), B = gamma-scaled
+  // weights, bias already includes W beta; per-row statistics arrive as ln_parts partial (sum, sum of squares)
+  // pairs and the epilogue applies  rstd_i * (acc_ij - mean_i * colsum_j) + bias_j.
+  const float* ln_stats;   // [M][ln_parts][2]
+  int ln_parts;
+  const float* ln_colsum;  // [N]  sum_k B[j][k] (of the bf16-rounded, gamma-scaled weights)
+  float ln_eps;
+  // STATS: besides the fp32 output, emit a bf16 copy (tmOut2) and this GEMM's own per-row partial statistics
+  float* stats_out;        // [M][2 * tiles_n][2]
 };
 
-template <int CG, int STAGES, int NBUF, int ACT, int RES, int OUT_F32>
+template <int CG, int STAGES, int NBUF, int ACT, int RES, int OUT_F32, int LNIN, int STATS>
 __global__ void __launch_bounds__(PG_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
-                 const PairGemmParams p) {
+                 const __grid_constant__ CUtensorMap tmOut2, const PairGemmParams p) {
   static_assert(RES == 0 || OUT_F32 == 1, "fp32 residual pairs with fp32 output");
+  static_assert(!STATS || (RES == 2 && OUT_F32 == 1), "statistics ride the fp32 residual epilogue");
+  static_assert(!LNIN || (RES == 0 && OUT_F32 == 0), "folded LayerNorm feeds the bf16-output epilogues");
+  constexpr int NBOX = NBUF + (STATS ? 1 : 0);        // staging boxes per epilogue warp
   constexpr int B_ROWS = PG_BN / CG;                 // B rows staged by this CTA
   constexpr int A_BYTES = PG_BM * PG_BK * 2;
   constexpr int B_BYTES = B_ROWS * PG_BK * 2;
@@ -54,7 +66,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* stg_base = smem + STAGES * STAGE_BYTES;                            // [EPI_WARPS][NBUF][4096]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + PG_EPI_WARPS * NBUF * PG_BOX_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + PG_EPI_WARPS * NBOX * PG_BOX_BYTES);
   uint64_t* bar_full = bars;
   uint64_t* bar_empty = bars + STAGES;
   uint64_t* bar_tfull = bars + 2 * STAGES;
@@ -79,6 +91,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
     if (RES) tma_prefetch_desc(&tmRes);
+    if (STATS) tma_prefetch_desc(&tmOut2);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
@@ -186,7 +199,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int e = warp - 2;
     const int q = warp & 3;                 // TMEM lane quarter this warp may touch (rows q*32 .. +31)
     const int h = e >> 2;                   // column half (128 columns)
-    const uint32_t stg_u32 = smem_u32(stg_base + e * NBUF * PG_BOX_BYTES);
+    const uint32_t stg_u32 = smem_u32(stg_base + e * NBOX * PG_BOX_BYTES);
+    const uint32_t buf16 = stg_u32 + NBUF * PG_BOX_BYTES;     // STATS: bf16 copy box (64 columns x 32 rows)
     const uint32_t row_off = lane * 128;
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
     uint64_t* my_res = bar_res + e * NBUF;
@@ -222,6 +236,25 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row0 = (t / tiles_n) * (PG_BM * CG) + (int)cta_rank * PG_BM + q * 32;
       const int tcol0 = (t % tiles_n) * PG_BN + h * (PG_BN / 2);
       const bool row_ok = row0 < p.M;
+      float ln_rstd = 1.f, ln_nmr = 0.f;      // LNIN: rstd_i and -mean_i * rstd_i of this thread's row
+      if (LNIN) {
+        const int my_row = row0 + lane;
+        if (my_row < p.M) {
+          const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + (long long)my_row * p.ln_parts;
+          float s1 = 0.f, s2 = 0.f;
+          for (int i = 0; i < p.ln_parts; ++i) {
+            const float2 v = __ldg(sp + i);
+            s1 += v.x;
+            s2 += v.y;
+          }
+          const float invk = 1.0f / (float)p.K;
+          const float mean = s1 * invk;
+          const float var = fmaxf(fmaf(-mean, mean, s2 * invk), 0.f);
+          ln_rstd = rsqrtf(var + p.ln_eps);
+          ln_nmr = -mean * ln_rstd;
+        }
+      }
+      float st_sum = 0.f, st_sq = 0.f;        // STATS: this thread's row over the warp's 128 columns
       mbar_wait(tfull0 + acc * 8, acc_phase);
       tc_fence_after();
       const uint32_t tm_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * PG_BN + h * (PG_BN / 2);
@@ -283,10 +316,33 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
                            "f"(v.w)
                            : "memory");
+              if (STATS) {
+                st_sum += (v.x + v.y) + (v.z + v.w);
+                st_sq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, st_sq))));
+                // bf16 copy: chunk c fills the left (even c) or right (odd c) 64 bytes of the 128-byte row;
+                // 8-byte piece j of this chunk = columns 4j..4j+3
+                const uint32_t pos = static_cast<uint32_t>((c & 1) * 64 + j * 8);              // byte offset in the row
+                const uint32_t a16 = buf16 + row_off + ((((pos >> 4) ^ sw) << 4) | (pos & 8u));
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a16), "r"(pack_bf16x2(v.x, v.y)),
+                             "r"(pack_bf16x2(v.z, v.w))
+                             : "memory");
+              }
             } else {
               const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias_c + min(8 * j, n_last)));
               const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias_c + min(8 * j + 4, n_last)));
               float v[8];
+              if (LNIN) {
+                const float4 c0 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0 + min(8 * j, n_last)));
+                const float4 c1 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0 + min(8 * j + 4, n_last)));
+                v[0] = fmaf(__uint_as_float(r[8 * j + 0]), ln_rstd, fmaf(ln_nmr, c0.x, b0.x));
+                v[1] = fmaf(__uint_as_float(r[8 * j + 1]), ln_rstd, fmaf(ln_nmr, c0.y, b0.y));
+                v[2] = fmaf(__uint_as_float(r[8 * j + 2]), ln_rstd, fmaf(ln_nmr, c0.z, b0.z));
+                v[3] = fmaf(__uint_as_float(r[8 * j + 3]), ln_rstd, fmaf(ln_nmr, c0.w, b0.w));
+                v[4] = fmaf(__uint_as_float(r[8 * j + 4]), ln_rstd, fmaf(ln_nmr, c1.x, b1.x));
+                v[5] = fmaf(__uint_as_float(r[8 * j + 5]), ln_rstd, fmaf(ln_nmr, c1.y, b1.y));
+                v[6] = fmaf(__uint_as_float(r[8 * j + 6]), ln_rstd, fmaf(ln_nmr, c1.z, b1.z));
+                v[7] = fmaf(__uint_as_float(r[8 * j + 7]), ln_rstd, fmaf(ln_nmr, c1.w, b1.w));
+              } else {
               v[0] = fmaf(__uint_as_float(r[8 * j + 0]), p.alpha, b0.x);
               v[1] = fmaf(__uint_as_float(r[8 * j + 1]), p.alpha, b0.y);
               v[2] = fmaf(__uint_as_float(r[8 * j + 2]), p.alpha, b0.z);
@@ -295,6 +351,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               v[5] = fmaf(__uint_as_float(r[8 * j + 5]), p.alpha, b1.y);
               v[6] = fmaf(__uint_as_float(r[8 * j + 6]), p.alpha, b1.z);
               v[7] = fmaf(__uint_as_float(r[8 * j + 7]), p.alpha, b1.w);
+              }
               if (ACT == 1) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = gelu_erf_tanhform(v[i]);
@@ -308,12 +365,19 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&tmOut, buf, col0, row0);
+            if (STATS && (c & 1)) tma_store_2d(&tmOut2, buf16, col0 - CHUNK_COLS, row0);   // 64 bf16 columns
             bulk_commit();
-            if (RES) bulk_wait_read<0>();   // box handed to the store engine: free for the next residual
+            if (RES) bulk_wait_read<0>();   // boxes handed to the store engine: free for the next residual / copy
           }
         }
         if (RES && lane == 0) issue_res(g + NBUF);   // residual NBUF chunks ahead (crosses tile boundaries)
         __syncwarp();
+      }
+      if (STATS) {
+        const int my_row = row0 + lane;
+        if (my_row < p.M)
+          reinterpret_cast<float2*>(p.stats_out)[(long long)my_row * (2 * tiles_n) + (t % tiles_n) * 2 + h] =
+              make_float2(st_sum, st_sq);
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -330,18 +394,19 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int CG, int STAGES, int NBUF>
+template <int CG, int STAGES, int NBUF, int STATS>
 constexpr int pair_smem_bytes() {
-  return STAGES * (PG_BM * PG_BK * 2 + (PG_BN / CG) * PG_BK * 2) + PG_EPI_WARPS * NBUF * PG_BOX_BYTES +
+  return STAGES * (PG_BM * PG_BK * 2 + (PG_BN / CG) * PG_BK * 2) + PG_EPI_WARPS * (NBUF + STATS) * PG_BOX_BYTES +
          (2 * STAGES + 4 + PG_EPI_WARPS * NBUF) * 8 + 16 + 1024;
 }
 
-template <int CG, int STAGES, int NBUF, int ACT, int RES, int OUT_F32>
+template <int CG, int STAGES, int NBUF, int ACT, int RES, int OUT_F32, int LNIN, int STATS>
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
-                       const CUtensorMap& tmRes, const PairGemmParams& p, cudaStream_t stream) {
-  constexpr int SMEM = pair_smem_bytes<CG, STAGES, NBUF>();
+                       const CUtensorMap& tmRes, const CUtensorMap& tmOut2, const PairGemmParams& p,
+                       cudaStream_t stream) {
+  constexpr int SMEM = pair_smem_bytes<CG, STAGES, NBUF, STATS>();
   static_assert(SMEM <= 232448, "shared memory budget");
-  auto kern = gemm_pair_kernel<CG, STAGES, NBUF, ACT, RES, OUT_F32>;
+  auto kern = gemm_pair_kernel<CG, STAGES, NBUF, ACT, RES, OUT_F32, LNIN, STATS>;
   static int max_pairs = 0;   // co-resident CTAs (CG = 1) or clusters (CG = 2)
   if (max_pairs == 0) {
     AGB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -373,7 +438,7 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  AGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmRes, p));
+  AGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmRes, tmOut2, p));
   return AGB_OK;
 }
 
@@ -383,15 +448,27 @@ int get_gemm_variant() { return g_gemm_variant; }
 
 // Returns AGB_ERR_UNSUPPORTED when this kernel does not cover the request (the caller then uses the
 // first-generation kernel): narrow N, bf16 residual, fp32 residual with bf16 output, GELU + residual.
-int gemm_bf16_pair(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, int M, int N, int K,
-                   float alpha, const float* bias, int act, const bf16* res_bf16, const float* res_f32, int ldr,
-                   void* out, int ldo, int out_f32, cudaStream_t stream) {
+// Optional fusions (nullptr = off):
+//   ln_stats / ln_colsum : LayerNorm of the A rows folded into the epilogue (bf16 output only, no residual)
+//   out16 / stats_out    : with an fp32 residual epilogue, also emit a bf16 copy of the output and its per-row
+//                          partial (sum, sum of squares) over each 128-column slab: stats_out [M][2*ceil(N/256)][2]
+int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, int M, int N, int K,
+                      float alpha, const float* bias, int act, const bf16* res_bf16, const float* res_f32, int ldr,
+                      void* out, int ldo, int out_f32, const float* ln_stats, int ln_parts, const float* ln_colsum,
+                      float ln_eps, bf16* out16, int ldo16, float* stats_out, cudaStream_t stream) {
+  const bool lnin = ln_stats != nullptr, stats = stats_out != nullptr;
   if (g_gemm_variant == 1) return AGB_ERR_UNSUPPORTED;
   if (N < 192 || res_bf16 != nullptr) return AGB_ERR_UNSUPPORTED;
   if (res_f32 != nullptr && (!out_f32 || act != 0)) return AGB_ERR_UNSUPPORTED;
   const int oes = out_f32 ? 4 : 2;
   if (((long long)ldo * oes) % 16 != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0) return AGB_ERR_UNSUPPORTED;
   if (res_f32 && ((((long long)ldr * 4) % 16) != 0 || (reinterpret_cast<uintptr_t>(res_f32) & 15) != 0))
+    return AGB_ERR_UNSUPPORTED;
+  if (lnin && (out_f32 || res_f32 || a_mn || ln_colsum == nullptr || ln_parts <= 0 || alpha != 1.0f ||
+               (reinterpret_cast<uintptr_t>(ln_colsum) & 15) != 0))
+    return AGB_ERR_UNSUPPORTED;
+  if (stats && (!res_f32 || out16 == nullptr || (N % PG_BN) != 0 || (ldo16 % 8) != 0 ||
+                (reinterpret_cast<uintptr_t>(out16) & 15) != 0))
     return AGB_ERR_UNSUPPORTED;
 
   // CTA pairs pay off once there is at least ~one full wave of 256-row tiles; small problems keep CG = 1
@@ -400,7 +477,7 @@ int gemm_bf16_pair(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int
   if (g_gemm_variant == 2) cg = 1;
   if (g_gemm_variant == 3) cg = 2;
 
-  CUtensorMap tmA, tmB, tmOut, tmRes;
+  CUtensorMap tmA, tmB, tmOut, tmRes, tmOut2;
   int rc;
   if (!a_mn) rc = encode_tmap_2d_bf16(&tmA, A, K, M, (uint64_t)lda * 2, PG_BK, PG_BM);
   else       rc = encode_tmap_2d_bf16(&tmA, A, M, K, (uint64_t)lda * 2, 64, PG_BK);
@@ -412,6 +489,9 @@ int gemm_bf16_pair(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int
   if (rc != AGB_OK) return rc;
   if (res_f32) rc = encode_tmap_2d(&tmRes, res_f32, 4, N, M, (uint64_t)ldr * 4, 32, 32);
   else         tmRes = tmOut;
+  if (rc != AGB_OK) return rc;
+  if (stats) rc = encode_tmap_2d(&tmOut2, out16, 2, N, M, (uint64_t)ldo16 * 2, 64, 32);
+  else       tmOut2 = tmOut;
   if (rc != AGB_OK) return rc;
 
   if (bias == nullptr) {   // the epilogue reads bias unconditionally: substitute zeros
@@ -426,19 +506,33 @@ int gemm_bf16_pair(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int
   }
   PairGemmParams p;
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.alpha = alpha; p.a_mn = a_mn; p.b_mn = b_mn;
+  p.ln_stats = ln_stats; p.ln_parts = ln_parts; p.ln_colsum = ln_colsum; p.ln_eps = ln_eps; p.stats_out = stats_out;
   const int res = res_f32 ? 2 : 0;
-#define AGB_PAIR_CASE(A_, R_, O_)                                                                        \
-  if (act == A_ && res == R_ && out_f32 == O_) {                                                         \
-    if (cg == 2) return launch_pair<2, (R_ ? 4 : 5), (R_ ? 3 : 2), A_, R_, O_>(tmA, tmB, tmOut, tmRes, p, stream); \
-    return launch_pair<1, 3, 2, A_, R_, O_>(tmA, tmB, tmOut, tmRes, p, stream);                         \
+  // (stages, residual ring) per configuration: CTA pairs stage 32 KB per k-block, single CTAs 48 KB
+#define AGB_PAIR_CASE(A_, R_, O_, L_, S_)                                                                          \
+  if (act == A_ && res == R_ && out_f32 == O_ && (int)lnin == L_ && (int)stats == S_) {                            \
+    if (cg == 2)                                                                                                   \
+      return launch_pair<2, (R_ ? 4 : 5), (R_ ? (S_ ? 2 : 3) : 2), A_, R_, O_, L_, S_>(tmA, tmB, tmOut, tmRes, tmOut2, p, \
+                                                                                       stream);                    \
+    return launch_pair<1, 3, (S_ ? 1 : 2), A_, R_, O_, L_, S_>(tmA, tmB, tmOut, tmRes, tmOut2, p, stream);         \
   }
-  AGB_PAIR_CASE(0, 0, 0)
-  AGB_PAIR_CASE(0, 0, 1)
-  AGB_PAIR_CASE(0, 2, 1)
-  AGB_PAIR_CASE(1, 0, 0)
-  AGB_PAIR_CASE(1, 0, 1)
+  AGB_PAIR_CASE(0, 0, 0, 0, 0)
+  AGB_PAIR_CASE(0, 0, 1, 0, 0)
+  AGB_PAIR_CASE(0, 2, 1, 0, 0)
+  AGB_PAIR_CASE(1, 0, 0, 0, 0)
+  AGB_PAIR_CASE(1, 0, 1, 0, 0)
+  AGB_PAIR_CASE(0, 0, 0, 1, 0)
+  AGB_PAIR_CASE(1, 0, 0, 1, 0)
+  AGB_PAIR_CASE(0, 2, 1, 0, 1)
 #undef AGB_PAIR_CASE
   return AGB_ERR_UNSUPPORTED;
+}
+
+int gemm_bf16_pair(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, int M, int N, int K,
+                   float alpha, const float* bias, int act, const bf16* res_bf16, const float* res_f32, int ldr,
+                   void* out, int ldo, int out_f32, cudaStream_t stream) {
+  return gemm_bf16_pair_ex(A, lda, a_mn, B, ldb, b_mn, M, N, K, alpha, bias, act, res_bf16, res_f32, ldr, out, ldo,
+                           out_f32, nullptr, 0, nullptr, 0.f, nullptr, 0, nullptr, stream);
 }
 
 }  // namespace agb

@@ -20,6 +20,10 @@ from . import ops
 
 State = Dict[str, Tensor]
 
+# bf16 ViT backbone: fold every LayerNorm into the neighbouring tcgen05 GEMMs (no LayerNorm kernels, the fp32
+# residual stream is read once per GEMM instead of once more per LayerNorm).  Off = the LayerNorm-kernel path.
+FUSE_LAYERNORM = True
+
 
 def _is_vit(cfg) -> bool:
     return hasattr(cfg, "img_px_size")
@@ -84,6 +88,20 @@ class LayerWeights:
         n2 = prefix + (".layernorm_after" if vit else ".output.LayerNorm")
         self.ln1 = (_f32(sd[n1 + ".weight"]), _f32(sd[n1 + ".bias"])) if (n1 + ".weight") in sd else None
         self.ln2 = (_f32(sd[n2 + ".weight"]), _f32(sd[n2 + ".bias"])) if (n2 + ".weight") in sd else None
+        # pre-LN blocks in bf16 mode: LayerNorm folded into the consuming GEMM (ops.gemm_bf16_fused).
+        #   W' = W * gamma (bf16), b' = b + W beta, colsum_j = sum_k W'_jk of the ROUNDED weights
+        self.folded = None
+        if vit and pol.bf16 and self.ln1 is not None and self.ln2 is not None:
+            wqkv32 = torch.cat([sd[sa + "query.weight"], sd[sa + "key.weight"], sd[sa + "value.weight"]], 0).detach().float()
+            w132 = sd[prefix + ".intermediate.dense.weight"].detach().float()
+            g1, b1 = self.ln1
+            g2, b2 = self.ln2
+            wq = ops.to_bf16((wqkv32 * g1[None, :]).contiguous())
+            w1 = ops.to_bf16((w132 * g2[None, :]).contiguous())
+            self.folded = {
+                "wqkv": wq, "bqkv": (self.bqkv + wqkv32 @ b1).contiguous(), "cqkv": wq.float().sum(1).contiguous(),
+                "w1": w1, "b1": (self.b1 + w132 @ b2).contiguous(), "c1": w1.float().sum(1).contiguous(),
+            }
 
 
 class BackboneWeights:
@@ -135,6 +153,23 @@ def vit_layer(pol: _Policy, lw: LayerWeights, x: Tensor, masks: Tensor, T: int, 
     return x
 
 
+def vit_layer_fused(lw: LayerWeights, x: Tensor, x16: Tensor, stats: Tensor, masks: Tensor, T: int, heads: int, eps: float,
+                    last: bool) -> Tuple[Tensor, Optional[Tensor], Optional[Tensor]]:
+    """Same block as vit_layer (bf16 mode) without LayerNorm kernels: x16 / stats are the bf16 copy and per-row
+    (sum, sum of squares) partials of the fp32 residual stream x, produced by the previous residual GEMM's epilogue
+    (or ops.rowstats_cast at the entry).  Returns (x, x16, stats) for the next block."""
+    f = lw.folded
+    qkv, _, _ = ops.gemm_bf16_fused(x16, f["wqkv"], f["bqkv"], ln=(stats, f["cqkv"], eps))
+    ctx = ops.masked_attention(qkv, masks, T, heads, ops.MASK_MUL0)
+    _, y16, ystats = ops.gemm_bf16_fused(ctx, lw.wo, lw.bo, residual=x, out=x, emit_copy_stats=True)
+    h = ops.gemm_bf16_fused(y16, f["w1"], f["b1"], act=ops.ACT_GELU, ln=(ystats, f["c1"], eps))[0]
+    if last:
+        ops.gemm_bf16(h, lw.w2, lw.b2, residual=x, out=x, out_dtype=torch.float32)
+        return x, None, None
+    _, x16n, statsn = ops.gemm_bf16_fused(h, lw.w2, lw.b2, residual=x, out=x, emit_copy_stats=True)
+    return x, x16n, statsn
+
+
 def bert_layer(pol: _Policy, lw: LayerWeights, x: Tensor, xa: Tensor, masks: Tensor, T: int, heads: int, eps: float
                ) -> Tuple[Tensor, Tensor]:
     """post-LN block; x fp32 residual stream, xa its activation-dtype copy.
@@ -162,6 +197,12 @@ def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tens
     assert masks.shape[0] == rows, f"need one packed mask row per (input, coalition): {masks.shape[0]} vs {rows}"
     x = x3.reshape(rows * T, H)
     if bw.vit:
+        fused = FUSE_LAYERNORM and pol.bf16 and H % 256 == 0 and all(lw.folded is not None for lw in bw.layers)
+        if fused:
+            x16, stats = ops.rowstats_cast(x)
+            for i, lw in enumerate(bw.layers):
+                x, x16, stats = vit_layer_fused(lw, x, x16, stats, masks, T, heads, eps, last=(i == len(bw.layers) - 1))
+            return x, None
         for lw in bw.layers:
             x = vit_layer(pol, lw, x, masks, T, heads, eps)
         return x, None

@@ -108,6 +108,55 @@ def gemm_bf16(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, act: int =
     return out
 
 
+def gemm_stats_parts(N: int) -> int:
+    return 2 * ((N + 255) // 256)
+
+
+def gemm_bf16_fused(a: Tensor, w: Tensor, bias: Optional[Tensor], *, act: int = ACT_NONE, residual: Optional[Tensor] = None,
+                    out: Optional[Tensor] = None, out_dtype=torch.bfloat16,
+                    ln: Optional[Tuple[Tensor, Tensor, float]] = None, emit_copy_stats: bool = False
+                    ) -> Tuple[Tensor, Optional[Tensor], Optional[Tensor]]:
+    """LayerNorm-folded GEMM chain (agb_gemm_bf16_fused).  ln = (row stats [M, parts, 2], colsum [N], eps) applies
+    Linear(LayerNorm(x)) to the UN-normalised bf16 rows `a` (w pre-scaled by gamma, bias pre-shifted by W beta).
+    emit_copy_stats (fp32 residual epilogue) also returns a bf16 copy of the output and its row statistics."""
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    copy16 = stats = None
+    if emit_copy_stats:
+        assert residual is not None and out.dtype == torch.float32
+        copy16 = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+        stats = torch.empty((M, gemm_stats_parts(N), 2), dtype=torch.float32, device=a.device)
+    ln_stats = ln_colsum = None
+    ln_parts, ln_eps = 0, 0.0
+    if ln is not None:
+        ln_stats, ln_colsum, ln_eps = ln
+        assert ln_stats.dtype == torch.float32 and ln_stats.is_contiguous() and ln_stats.shape[0] == M and ln_stats.shape[2] == 2
+        assert ln_colsum.dtype == torch.float32 and ln_colsum.numel() == N
+        ln_parts = ln_stats.shape[1]
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.stride(1) == 1
+    nat.NEXT_META = 2.0 * M * N * K
+    nat.call("agb_gemm_bf16_fused", nat.ptr(a), a.stride(0), nat.ptr(w), w.stride(0), M, N, K, nat.ptr(bias), act,
+             nat.ptr(residual), residual.stride(0) if residual is not None else 0, nat.ptr(out), out.stride(0),
+             1 if out.dtype == torch.float32 else 0, nat.ptr(ln_stats), ln_parts, nat.ptr(ln_colsum), float(ln_eps),
+             nat.ptr(copy16), N if copy16 is not None else 0, nat.ptr(stats), nat.stream())
+    return out, copy16, stats
+
+
+def rowstats_cast(x: Tensor) -> Tuple[Tensor, Tensor]:
+    """fp32 (rows, H) -> (bf16 copy, stats (rows, 1, 2) = per-row (sum, sum of squares))."""
+    assert x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1
+    rows, H = x.shape
+    out = torch.empty((rows, H), dtype=torch.bfloat16, device=x.device)
+    stats = torch.empty((rows, 1, 2), dtype=torch.float32, device=x.device)
+    nat.call("agb_rowstats_cast", nat.ptr(x), x.stride(0), rows, H, nat.ptr(out), H, nat.ptr(stats), nat.stream())
+    return out, stats
+
+
 def gemm_f32(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, act: int = ACT_NONE,
              residual: Optional[Tensor] = None, out: Optional[Tensor] = None, alpha: float = 1.0,
              a_mn: bool = False, w_mn: bool = False) -> Tensor:

@@ -210,33 +210,41 @@ def run_ours(args):
     # and the D2H of step i-1 overlap the kernels of step i instead of idling the SMs.
     copy_stream = torch.cuda.Stream(device=dev)
     host_out = [torch.empty((rows, C), dtype=torch.float32).pin_memory() for _ in range(2)]
+    xs_bufs = [torch.empty((B, 3, 224, 224), device=dev) for _ in range(2)]     # device-side input double buffer
 
     def e2e_loop(first, count):
         main = torch.cuda.current_stream()
-        ready = torch.cuda.Event()
-        with torch.cuda.stream(copy_stream):
-            xs_next = images_host.to(dev, non_blocking=True)
-            ready.record(copy_stream)
-        done = [None, None]
+        consumed = [None, None]      # main-stream event: the kernels that read xs_bufs[k] have been issued/finished
+        done = [None, None]          # main-stream event: host_out[k] holds its step's probabilities
+        ready = [None, None]         # copy-stream event: xs_bufs[k] holds its step's images
+
+        def prefetch(j):
+            k = j & 1
+            with torch.cuda.stream(copy_stream):
+                if consumed[k] is not None:
+                    copy_stream.wait_event(consumed[k])
+                xs_bufs[k].copy_(images_host, non_blocking=True)
+                ready[k] = torch.cuda.Event()
+                ready[k].record(copy_stream)
+
         checksum = 0.0
+        prefetch(0)
         for j in range(count):
-            main.wait_event(ready)
-            xs = xs_next
-            xs.record_stream(main)
+            k = j & 1
             if j + 1 < count:
-                ready = torch.cuda.Event()
-                with torch.cuda.stream(copy_stream):
-                    xs_next = images_host.to(dev, non_blocking=True)
-                    ready.record(copy_stream)
+                prefetch(j + 1)
+            main.wait_event(ready[k])
             pm = ash.mask_shapley_new(rows, n, device=dev, rng="philox", seed=3407 + rank, offset=(first + j) * rows,
                                       packed=True)
-            probs, _ = rec.fw_surrogate(surrogate, xs, pm)
-            if done[j & 1] is not None:              # the host buffer about to be reused has been consumed
-                done[j & 1].synchronize()
-                checksum += float(host_out[j & 1][0, 0])
-            host_out[j & 1].copy_(probs, non_blocking=True)
-            done[j & 1] = torch.cuda.Event()
-            done[j & 1].record(main)
+            probs, _ = rec.fw_surrogate(surrogate, xs_bufs[k], pm)
+            consumed[k] = torch.cuda.Event()
+            consumed[k].record(main)
+            if done[k] is not None:                  # the host buffer about to be reused has been consumed
+                done[k].synchronize()
+                checksum += float(host_out[k][0, 0])
+            host_out[k].copy_(probs, non_blocking=True)
+            done[k] = torch.cuda.Event()
+            done[k].record(main)
         for ev, buf in zip(done, host_out):
             if ev is not None:
                 ev.synchronize()
@@ -338,11 +346,17 @@ def run_ours(args):
         acc = by_kernel.setdefault(name, [0.0, 0.0, 0])
         acc[0] += t; acc[1] += (meta or 0.0); acc[2] += 1
     peaks = load_peaks()
-    gemm = by_kernel.get("agb_gemm_bf16", [1e-9, 0.0, 1])
+    # the dominant kernel is the tcgen05 GEMM (gemm_pair_kernel): plain launches + the LayerNorm-folded chain
+    gemm = [0.0, 0.0, 0]
+    for gname in ("agb_gemm_bf16", "agb_gemm_bf16_fused"):
+        for i, v in enumerate(by_kernel.get(gname, [0.0, 0.0, 0])):
+            gemm[i] += v
+    if gemm[2] == 0:
+        gemm = [1e-9, 0.0, 1]
     achieved = gemm[1] / (gemm[0] * 1e-3) * 1e-12
     total_t = sum(v[0] for v in by_kernel.values())
     roofline = {
-        "bound": "tensor", "kernel": "gemm_tc_kernel (agb_gemm_bf16)", "achieved": achieved,
+        "bound": "tensor", "kernel": "gemm_pair_kernel (agb_gemm_bf16 + agb_gemm_bf16_fused)", "achieved": achieved,
         "peak": peaks["bf16_tflops_sustained"], "peak_kind": f"bf16_tflops_sustained, {peaks['source']}",
         "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
         "frac_of_burst_peak": achieved / peaks["bf16_tflops"], "traffic": None,

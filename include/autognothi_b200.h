@@ -49,6 +49,23 @@ int agb_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb
                   const void* residual_bf16, const float* residual_f32, int ldr, int res_group,
                   int res_rows, void* out, int ldo, int out_is_f32, void* stream);
 
+/* LayerNorm-folded GEMM chain for pre-LN blocks (reference models/vanilla_vit.py:364-377: x + Attn(LN1(x)), then
+ * y + W2 GELU(W1 LN2(y))).  Instead of a LayerNorm kernel between the GEMMs,
+ *   - a residual GEMM (residual_f32 != NULL, fp32 out) can ALSO emit a bf16 copy of its output and per-row partial
+ *     statistics: stats_out [M][agb_gemm_stats_parts(N)][2] = (sum, sum of squares) over each 128-column slab;
+ *   - the consuming GEMM (bf16 out, no residual) takes that copy as A together with ln_stats / ln_parts, weights
+ *     pre-scaled by gamma (B = W * gamma), bias' = b + W beta and ln_colsum[j] = sum_k B[j][k], and applies
+ *     rstd_i * (acc_ij - mean_i * ln_colsum[j]) + bias'_j in its epilogue  ==  Linear(LayerNorm(x)).
+ * All operands K-major ([rows, K]); returns AGB_ERR_UNSUPPORTED for shapes the tcgen05 pair kernel does not cover. */
+int agb_gemm_bf16_fused(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias,
+                        int act, const float* residual_f32, int ldr, void* out, int ldo, int out_is_f32,
+                        const float* ln_stats, int ln_parts, const float* ln_colsum, float ln_eps,
+                        void* out_bf16_copy, int ldo_copy, float* stats_out, void* stream);
+int agb_gemm_stats_parts(int N);
+/* bf16 copy + one (sum, sum of squares) pair per row of an fp32 matrix: the entry of the chain above. */
+int agb_rowstats_cast(const float* x, long long ldx, int rows, int H, void* out_bf16, long long ldo, float* stats,
+                      void* stream);
+
 /* Kernel selection for agb_gemm_bf16 (diagnostics / benchmarking): 0 = automatic, 1 = first-generation
  * 1-CTA kernel only, 2 = TMA-epilogue kernel with one CTA per tile, 3 = TMA-epilogue kernel on CTA pairs
  * (tcgen05 cta_group::2).  Returns the previous setting. */

@@ -132,6 +132,73 @@ def test_gemm_bf16(agb, M, N, K, variant):
     torch.testing.assert_close(out.float(), ref, rtol=tol, atol=tol)
 
 
+@pytest.mark.parametrize("M", [300, 6304, 40000])      # one CTA per tile, and CTA pairs (cta_group::2)
+@pytest.mark.parametrize("act", ["none", "gelu"])
+def test_gemm_bf16_layernorm_folded_chain(agb, M, act):
+    """Residual GEMM emitting (bf16 copy, row statistics) -> consuming GEMM with the LayerNorm folded into its
+    epilogue == LayerNorm kernel + plain GEMM (the unfused path), and == the fp32 torch formula."""
+    torch.manual_seed(1)
+    H, N2 = 768, 2304
+    ctx = torch.randn(M, H, device=DEV).bfloat16()
+    wo = (torch.randn(H, H, device=DEV) / H ** 0.5).bfloat16()
+    bo = torch.randn(H, device=DEV) * 0.1
+    x = torch.randn(M, H, device=DEV) * 2.0 + 0.3
+    gamma = 1.0 + 0.2 * torch.randn(H, device=DEV)
+    beta = 0.1 * torch.randn(H, device=DEV)
+    w = torch.randn(N2, H, device=DEV) / H ** 0.5
+    b = torch.randn(N2, device=DEV) * 0.1
+    eps = 1e-12
+    # producer: y = x + ctx Wo^T + bo  (+ bf16 copy + partial row statistics)
+    y, y16, stats = agb.gemm_bf16_fused(ctx, wo, bo, residual=x, emit_copy_stats=True, out_dtype=torch.float32)
+    y_ref = x + ctx.float() @ wo.float().t() + bo
+    torch.testing.assert_close(y, y_ref, rtol=2e-3, atol=2e-3)
+    assert torch.equal(y16, y.bfloat16())
+    assert stats.shape == (M, agb.gemm_stats_parts(H), 2)
+    torch.testing.assert_close(stats[:, :, 0].sum(1), y.sum(1), rtol=1e-4, atol=1e-2)
+    torch.testing.assert_close(stats[:, :, 1].sum(1), (y * y).sum(1), rtol=1e-4, atol=1e-2)
+    # entry kernel gives the same statistics in one part
+    x16e, stats_e = agb.rowstats_cast(y)
+    assert torch.equal(x16e, y16)
+    torch.testing.assert_close(stats_e[:, 0, 0], y.sum(1), rtol=1e-4, atol=1e-2)
+    # consumer: Linear(LayerNorm(y)) with gamma folded into the weights
+    wf = (w * gamma[None, :]).bfloat16()
+    bf = b + w @ beta
+    colsum = wf.float().sum(1).contiguous()
+    a_code = agb.ACT_GELU if act == "gelu" else agb.ACT_NONE
+    out = agb.gemm_bf16_fused(y16, wf, bf, act=a_code, ln=(stats, colsum, eps))[0]
+    ln_ref = torch.nn.functional.layer_norm(y, (H,), gamma, beta, eps)
+    ref = ln_ref @ w.t() + b
+    if act == "gelu":
+        ref = torch.nn.functional.gelu(ref)
+    h16, _ = agb.layernorm(y, gamma, beta, eps, want_bf16=True, want_f32=False)
+    unfused = agb.gemm_bf16(h16, w.bfloat16(), b, act=a_code)
+    err_fused = (out.float() - ref).norm() / ref.norm()
+    err_unfused = (unfused.float() - ref).norm() / ref.norm()
+    assert err_fused < 1e-2 and err_fused < 2.0 * err_unfused + 1e-3, (float(err_fused), float(err_unfused))
+    torch.testing.assert_close(out.float(), ref, rtol=3e-2, atol=3e-2)
+
+
+def test_vit_base_layernorm_folding_matches_layernorm_kernels(agb):
+    """bf16 ViT-B backbone with every LayerNorm folded into the GEMMs vs the LayerNorm-kernel path."""
+    from autognothi_b200 import engine
+    rec, cfgd, srg, exp = _build("vit_base", "bf16")
+    B, S = 2, 8
+    n = rec.n_players(rec.t_config(**cfgd))
+    xs = torch.from_numpy(synth.inputs(cfgd, B, seed=3)).to(DEV)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    masks = (torch.rand((B, S, n), generator=g) > 0.5).to(torch.int64).to(DEV)
+    try:
+        with torch.no_grad():
+            engine.FUSE_LAYERNORM = True
+            p_fused, _ = rec.fw_surrogate(srg, xs, masks)
+            engine.FUSE_LAYERNORM = False
+            p_plain, _ = rec.fw_surrogate(srg, xs, masks)
+    finally:
+        engine.FUSE_LAYERNORM = True
+    assert np.isfinite(_np(p_fused)).all()
+    np.testing.assert_allclose(_np(p_fused), _np(p_plain), atol=5e-3)
+
+
 def test_gemm_bf16_mn_major_operands(agb):
     """dgrad / wgrad operand layouts: dX = dY @ W (W MN-major), dW = dY^T @ X (both MN-major)."""
     torch.manual_seed(1)
