@@ -290,7 +290,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (active) {
           // bias columns past N are clamped to a valid address: those outputs are clipped by the TMA store
           const float* bias_c = p.bias + col0;
-          const int n_last = p.N - 4 - col0;
+          const int n_last = (col0 + CHUNK_COLS <= p.N) ? (1 << 20) : (p.N - 4 - col0);   // no clamp on full chunks
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint32_t addr = buf + row_off + ((static_cast<uint32_t>(j) ^ sw) << 4);
@@ -508,12 +508,19 @@ int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, 
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.alpha = alpha; p.a_mn = a_mn; p.b_mn = b_mn;
   p.ln_stats = ln_stats; p.ln_parts = ln_parts; p.ln_colsum = ln_colsum; p.ln_eps = ln_eps; p.stats_out = stats_out;
   const int res = res_f32 ? 2 : 0;
-  // (stages, residual ring) per configuration: CTA pairs stage 32 KB per k-block, single CTAs 48 KB
+  // (stages, residual ring) per configuration: CTA pairs stage 32 KB per k-block (5 stages: the K = 3072 GEMM was
+  // latency-starved with 4), single CTAs 48 KB (3 stages); the statistics variant trades one ring slot for the copy box
 #define AGB_PAIR_CASE(A_, R_, O_, L_, S_)                                                                          \
   if (act == A_ && res == R_ && out_f32 == O_ && (int)lnin == L_ && (int)stats == S_) {                            \
     if (cg == 2)                                                                                                   \
-      return launch_pair<2, (R_ ? 4 : 5), (R_ ? (S_ ? 2 : 3) : 2), A_, R_, O_, L_, S_>(tmA, tmB, tmOut, tmRes, tmOut2, p, \
-                                                                                       stream);                    \
+    {                                                                                                              \
+      /* long-K residual GEMMs are latency-starved with 4 stages (5 stages, short residual ring); short-K ones are   \
+         HBM-bound and want the deeper residual prefetch instead (4 stages, ring of 2 + copy box / ring of 3) */   \
+      if (R_ && K < 2048)                                                                                          \
+        return launch_pair<2, (R_ ? 4 : 5), (R_ ? (S_ ? 2 : 3) : 2), A_, R_, O_, L_, S_>(tmA, tmB, tmOut, tmRes, tmOut2, p, \
+                                                                                         stream);                  \
+      return launch_pair<2, 5, (S_ ? 1 : 2), A_, R_, O_, L_, S_>(tmA, tmB, tmOut, tmRes, tmOut2, p, stream);       \
+    }                                                                                                              \
     return launch_pair<1, 3, (S_ ? 1 : 2), A_, R_, O_, L_, S_>(tmA, tmB, tmOut, tmRes, tmOut2, p, stream);         \
   }
   AGB_PAIR_CASE(0, 0, 0, 0, 0)

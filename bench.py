@@ -359,7 +359,11 @@ def run_ours(args):
         "bound": "tensor", "kernel": "gemm_pair_kernel (agb_gemm_bf16 + agb_gemm_bf16_fused)", "achieved": achieved,
         "peak": peaks["bf16_tflops_sustained"], "peak_kind": f"bf16_tflops_sustained, {peaks['source']}",
         "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
-        "frac_of_burst_peak": achieved / peaks["bf16_tflops"], "traffic": None,
+        "frac_of_burst_peak": achieved / peaks["bf16_tflops"],
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture of a whole layer at
+        # this exact shape (profiles/r01_layer_ncu_full.txt: QKV 1.197, out-proj 1.814, FC1 1.509, FC2 2.887 GB; mean);
+        # algorithmic bytes per launch of the same four GEMMs (operands + residual + outputs once): 1.24/1.87/1.55/2.80 GB
+        "traffic": 1.852e9 if (B * S * (n + 1) == 201728) else None, "traffic_unit": "bytes per launch (ncu, mean of the 4 layer GEMMs)",
         "avg_launch_us": gemm[0] / gemm[2] * 1e3, "launches": gemm[2], "share_of_step": gemm[0] / total_t,
         "step_shares": {k: round(v[0] / total_t, 4) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1][0])},
     }
