@@ -88,10 +88,15 @@ class LayerWeights:
         n2 = prefix + (".layernorm_after" if vit else ".output.LayerNorm")
         self.ln1 = (_f32(sd[n1 + ".weight"]), _f32(sd[n1 + ".bias"])) if (n1 + ".weight") in sd else None
         self.ln2 = (_f32(sd[n2 + ".weight"]), _f32(sd[n2 + ".bias"])) if (n2 + ".weight") in sd else None
-        # pre-LN blocks in bf16 mode: LayerNorm folded into the consuming GEMM (ops.gemm_bf16_fused).
-        #   W' = W * gamma (bf16), b' = b + W beta, colsum_j = sum_k W'_jk of the ROUNDED weights
+        # pre-LN blocks in bf16 mode: LayerNorm folded into the consuming GEMM (ops.gemm_bf16_fused); built lazily by
+        # fold() because only the inference engines use it (the training tape keeps explicit LayerNorm outputs)
         self.folded = None
-        if vit and pol.bf16 and self.ln1 is not None and self.ln2 is not None:
+        self._fold_src = (sd, sa, prefix) if (vit and pol.bf16 and self.ln1 is not None and self.ln2 is not None) else None
+
+    def fold(self) -> Optional[dict]:
+        """W' = W * gamma (bf16), b' = b + W beta, colsum_j = sum_k W'_jk of the ROUNDED weights."""
+        if self.folded is None and self._fold_src is not None:
+            sd, sa, prefix = self._fold_src
             wqkv32 = torch.cat([sd[sa + "query.weight"], sd[sa + "key.weight"], sd[sa + "value.weight"]], 0).detach().float()
             w132 = sd[prefix + ".intermediate.dense.weight"].detach().float()
             g1, b1 = self.ln1
@@ -102,6 +107,8 @@ class LayerWeights:
                 "wqkv": wq, "bqkv": (self.bqkv + wqkv32 @ b1).contiguous(), "cqkv": wq.float().sum(1).contiguous(),
                 "w1": w1, "b1": (self.b1 + w132 @ b2).contiguous(), "c1": w1.float().sum(1).contiguous(),
             }
+            self._fold_src = None
+        return self.folded
 
 
 class BackboneWeights:
@@ -158,7 +165,7 @@ def vit_layer_fused(lw: LayerWeights, x: Tensor, x16: Tensor, stats: Tensor, mas
     """Same block as vit_layer (bf16 mode) without LayerNorm kernels: x16 / stats are the bf16 copy and per-row
     (sum, sum of squares) partials of the fp32 residual stream x, produced by the previous residual GEMM's epilogue
     (or ops.rowstats_cast at the entry).  Returns (x, x16, stats) for the next block."""
-    f = lw.folded
+    f = lw.fold()
     qkv, _, _ = ops.gemm_bf16_fused(x16, f["wqkv"], f["bqkv"], ln=(stats, f["cqkv"], eps))
     ctx = ops.masked_attention(qkv, masks, T, heads, ops.MASK_MUL0)
     _, y16, ystats = ops.gemm_bf16_fused(ctx, lw.wo, lw.bo, residual=x, out=x, emit_copy_stats=True)
@@ -197,7 +204,7 @@ def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tens
     assert masks.shape[0] == rows, f"need one packed mask row per (input, coalition): {masks.shape[0]} vs {rows}"
     x = x3.reshape(rows * T, H)
     if bw.vit:
-        fused = FUSE_LAYERNORM and pol.bf16 and H % 256 == 0 and all(lw.folded is not None for lw in bw.layers)
+        fused = FUSE_LAYERNORM and pol.bf16 and H % 256 == 0 and all(lw.fold() is not None for lw in bw.layers)
         if fused:
             x16, stats = ops.rowstats_cast(x)
             for i, lw in enumerate(bw.layers):

@@ -305,7 +305,7 @@ def run_ours(args):
         ones = ash.PackedMasks.ones(Bt, n, dev)
         with torch.no_grad():
             null, _ = rec.fw_surrogate(surrogate, rec.gen_null(cfg, None, dev), ash.PackedMasks.ones(1, n, dev))
-        xs_t = images_dev[:Bt]
+        xs_t = images_dev[:Bt] if Bt <= B else torch.randn((Bt, 3, 224, 224), device=dev, generator=g)
 
         def step_train(i):
             pm = ash.mask_shapley_new(Bt * S, n, device=dev, rng="philox", seed=99 + rank, offset=i * Bt * S, packed=True)
