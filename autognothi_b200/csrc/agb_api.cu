@@ -10,6 +10,8 @@ int gemm_bf16_tc(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b
                  int K, float alpha, const float* bias, int act, const bf16* res_bf16,
                  const float* res_f32, int ldr, int res_group, int res_rows, void* out, int ldo,
                  int out_f32, cudaStream_t stream);
+int rank_masks(const float* scores, int use_philox, uint64_t seed, uint64_t offset, int rows, int n, const int* stops,
+               int nstops, int mask_base, uint32_t* packed, int words, int64_t* dense, cudaStream_t st);
 void set_attention_variant(int v);
 void set_attention_bwd_variant(int v);
 int get_attention_bwd_variant();
@@ -99,6 +101,13 @@ int agb_gemm_bf16(const void* A, int lda, int a_mn_major, const void* B, int ldb
                            res_rows, out, ldo, out_is_f32, static_cast<cudaStream_t>(stream));
 }
 
+
+int agb_rank_masks(const float* scores, int use_philox, uint64_t seed, uint64_t offset, int rows, int n_players,
+                   const int* stops, int nstops, int mask_base, uint32_t* packed, int words, int64_t* dense,
+                   void* stream) {
+  return agb::rank_masks(scores, use_philox, seed, offset, rows, n_players, stops, nstops, mask_base, packed, words, dense,
+                         ST(stream));
+}
 
 int agb_attention_set_variant(int variant) {
   const int prev = agb::get_attention_variant();

@@ -152,6 +152,63 @@ __global__ void uniform_masks_kernel(const float* __restrict__ u_players, const 
   packed[gid] = bits;
 }
 
+// Rank masks: the on-device form of two reference mask generators that are python loops there.
+//   * faithfulness insertion / deletion curves (reference scripts/measure_faithfulness.py:225-251,
+//     _get_perturbed_samples): players ranked by attribution, descending; mask_i = base with the top stops[i]
+//     players flipped.  Rank rule = np.argsort(a)[::-1] with a stable sort: a_k ranks before a_j iff
+//     a_k > a_j, or a_k == a_j and k > j.
+//   * fixed-count random masks (reference models/shapley.py:118-128, mask_uniform_selective): scores are
+//     random keys (caller-supplied or Philox), one stop = n_masked, base = 1 -> exactly n_masked players are 0.
+// One block per score row; O(n^2) rank counting from shared memory (n <= 2048), output rows r*nstops + i.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+rank_masks_kernel(const float* __restrict__ scores, uint64_t seed, uint64_t offset, int n,
+                  const int* __restrict__ stops, int nstops, int mask_base, uint32_t* __restrict__ packed, int words,
+                  int64_t* __restrict__ dense) {
+  extern __shared__ float rk_smem[];
+  float* a = rk_smem;                                            // n scores
+  unsigned short* rank = reinterpret_cast<unsigned short*>(a + n);   // n ranks
+  const int row = blockIdx.x;
+  if (MODE == 0) {
+    for (int j = threadIdx.x; j < n; j += blockDim.x) a[j] = scores[(long long)row * n + j];
+  } else {
+    Philox rng(seed);
+    for (int j4 = threadIdx.x; j4 * 4 < n; j4 += blockDim.x) {
+      const uint4 r4 = rng(offset + (uint64_t)row, (uint64_t)j4);
+      const uint32_t rr[4] = {r4.x, r4.y, r4.z, r4.w};
+      for (int i = 0; i < 4; ++i)
+        if (j4 * 4 + i < n) a[j4 * 4 + i] = u24(rr[i]);
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const float aj = a[j];
+    int r = 0;
+    for (int k = 0; k < n; ++k) {
+      const float ak = a[k];
+      r += (ak > aj || (ak == aj && k > j)) ? 1 : 0;
+    }
+    rank[j] = static_cast<unsigned short>(r);
+  }
+  __syncthreads();
+  const uint32_t base = mask_base ? 1u : 0u;
+  for (int e = threadIdx.x; e < nstops * words; e += blockDim.x) {
+    const int i = e / words, w = e % words;
+    const int stop = stops[i];
+    uint32_t bits = 0;
+    for (int b = 0; b < 32; ++b) {
+      const int tok = w * 32 + b, j = tok - 1;
+      if (tok == 0) { bits |= 1u; continue; }
+      if (j < n) {
+        const uint32_t keep = base ^ ((int)rank[j] < stop ? 1u : 0u);
+        bits |= keep << b;
+        if (dense != nullptr) dense[((long long)row * nstops + i) * n + j] = keep;
+      }
+    }
+    packed[((long long)row * nstops + i) * words + w] = bits;
+  }
+}
+
 static inline int blocks_for(long long n, int threads) { return (int)((n + threads - 1) / threads); }
 
 int pack_masks_i64(const int64_t* mask, int rows, int n, int prepend_cls, uint32_t* packed, int words,
@@ -208,6 +265,20 @@ int uniform_masks(const float* u_players, const float* u_row, int use_philox, ui
     AGB_REQUIRE(u_players && u_row, "uniforms required");
     uniform_masks_kernel<0><<<blocks, 128, 0, st>>>(u_players, u_row, 0, 0, rows, n, packed, words, dense);
   }
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+int rank_masks(const float* scores, int use_philox, uint64_t seed, uint64_t offset, int rows, int n, const int* stops,
+               int nstops, int mask_base, uint32_t* packed, int words, int64_t* dense, cudaStream_t st) {
+  AGB_REQUIRE(rows >= 0 && n >= 1 && n <= 2048 && nstops >= 1 && words * 32 >= n + 1, "rank-mask shape (n <= 2048)");
+  if (rows == 0) return AGB_OK;
+  AGB_REQUIRE(packed && stops && (use_philox || scores), "null pointer");
+  const size_t smem = (size_t)n * 4 + (size_t)n * 2;
+  if (use_philox)
+    rank_masks_kernel<1><<<rows, 256, smem, st>>>(nullptr, seed, offset, n, stops, nstops, mask_base, packed, words, dense);
+  else
+    rank_masks_kernel<0><<<rows, 256, smem, st>>>(scores, 0, 0, n, stops, nstops, mask_base, packed, words, dense);
   AGB_CHECK_CUDA(cudaGetLastError());
   return AGB_OK;
 }

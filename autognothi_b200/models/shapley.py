@@ -127,6 +127,29 @@ def mask_purely_uniform(batch_size: int, n_features: int, *, device=None, rng: s
     return PackedMasks(words, n_features) if packed else dense
 
 
+def mask_uniform_selective(batch_size: int, n_features: int, n_masked: int, *, device=None, rng: str = "python",
+                           seed: int = 0, offset: int = 0, packed: bool = False):
+    """reference models/shapley.py:118-128: masks with exactly `n_masked` players masked out.
+    rng="python" replays the reference's own host algorithm (random.shuffle -> identical masks under the same
+    random.seed) and uploads it; rng="philox" draws random keys on the device and masks the n_masked top-ranked ones
+    (same uniform distribution over subsets, no host loop)."""
+    dev = _default_device(device)
+    if rng == "python":
+        import random
+        ret = []
+        for _ in range(batch_size):
+            ids = list(range(n_features))
+            random.shuffle(ids)
+            chosen = set(ids[:n_masked])
+            ret.append([0 if i in chosen else 1 for i in range(n_features)])
+        dense = torch.tensor(ret, dtype=torch.long).reshape(batch_size, n_features).to(dev)
+        return PackedMasks(ops.pack_masks(dense, prepend_cls=True), n_features) if packed else dense
+    stops = torch.tensor([n_masked], dtype=torch.int32)
+    words, dense = ops.rank_masks(None, stops, n_features, 1, rows=batch_size, device=dev, seed=seed, offset=offset,
+                                  want_dense=not packed)
+    return PackedMasks(words, n_features) if packed else dense
+
+
 class _NormalizeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, grand, null):

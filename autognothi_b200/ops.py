@@ -77,6 +77,26 @@ def uniform_masks(rows: int, n_players: int, device, *, u_players: Optional[Tens
     return packed, dense
 
 
+def rank_masks(scores: Optional[Tensor], stops: Tensor, n_players: int, mask_base: int, *, rows: Optional[int] = None,
+               device=None, seed: int = 0, offset: int = 0, want_dense: bool = False) -> Tuple[Tensor, Optional[Tensor]]:
+    """scores (rows, n) fp32 (None -> Philox keys on device) + stops int32 (nstops,) -> packed (rows*nstops, words)
+    [, dense int64 (rows*nstops, n)]: row r*nstops+i = mask_base with the stops[i] top-ranked players flipped."""
+    use_philox = scores is None
+    if not use_philox:
+        scores = _c(scores.float())
+        assert scores.dim() == 2 and scores.shape[1] == n_players
+        rows, device = scores.shape[0], scores.device
+    assert rows is not None and device is not None
+    stops = _c(stops.to(device=device, dtype=torch.int32))
+    nstops = stops.numel()
+    words = mask_words(n_players + 1)
+    packed = torch.empty((rows * nstops, words), dtype=torch.int32, device=device)
+    dense = torch.empty((rows * nstops, n_players), dtype=torch.int64, device=device) if want_dense else None
+    nat.call("agb_rank_masks", nat.ptr(scores), 1 if use_philox else 0, seed, offset, rows, n_players, nat.ptr(stops), nstops,
+             1 if mask_base else 0, nat.ptr(packed), words, nat.ptr(dense), nat.stream())
+    return packed, dense
+
+
 # ------------------------------------------------------------------------------------------------
 # dense
 # ------------------------------------------------------------------------------------------------

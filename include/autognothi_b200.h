@@ -100,6 +100,16 @@ int agb_uniform_masks(const float* u_players, const float* u_row, int use_philox
                       uint64_t offset, int rows, int n_players, uint32_t* packed, int words,
                       int64_t* dense, void* stream);
 
+/* Rank masks: rows of scores (rows, n) fp32 -> packed masks (rows * nstops, words), row r*nstops+i =
+ * `mask_base` with the stops[i] highest-ranked players flipped (rank = descending score, ties: larger index first,
+ * i.e. np.argsort(a)[::-1] with a stable sort).  Replaces the python loops of scripts/measure_faithfulness.py:225-251
+ * (_get_perturbed_samples: scores = attributions, stops = linspace) and models/shapley.py:118-128
+ * (mask_uniform_selective: scores = random keys, one stop = n_masked, base 1; use_philox draws the keys on device).
+ * stops: device int32 [nstops]; dense (optional): int64 (rows * nstops, n), the reference's return layout. */
+int agb_rank_masks(const float* scores, int use_philox, uint64_t seed, uint64_t offset, int rows, int n_players,
+                   const int* stops, int nstops, int mask_base, uint32_t* packed, int words, int64_t* dense,
+                   void* stream);
+
 /* ---- row kernels ---------------------------------------------------------------------------- */
 /* nn.LayerNorm over the last dim (reference models/vanilla_vit.py:94,213,369,373; vanilla_bert.py:
  * 318,548,596).  x fp32 or bf16 [rows, in_stride]; writes bf16 and/or fp32 [rows, out_stride]. */

@@ -129,3 +129,35 @@ def loss_shapley_new(mask: np.ndarray, v_0: np.ndarray, v_s: np.ndarray, phi: np
     dapprox = (dt.type(2.0 * n / (B * S * C)) * resid).reshape(B, S, C)
     dphi = np.einsum("bsc,bsn->bcn", dapprox, m).astype(dt)
     return loss, dphi
+
+
+# ------------------------------------------------------------------------------------------------
+# 8f-1: rank masks for the faithfulness / masked-accuracy evaluators
+# ------------------------------------------------------------------------------------------------
+def descending_ranking(a: np.ndarray) -> np.ndarray:
+    """np.argsort(a)[::-1] as in reference scripts/measure_faithfulness.py:239, with the sort made stable so ties are
+    defined (equal scores: the larger index ranks first)."""
+    return np.argsort(np.asarray(a).reshape(-1), kind="stable")[::-1]
+
+
+def perturbed_samples(explanations: np.ndarray, n_players: int, steps: int, mask_base: int) -> Tuple[np.ndarray, np.ndarray]:
+    """reference scripts/measure_faithfulness.py:225-251 (_get_perturbed_samples): stops = linspace(0, n, steps) as
+    int64; mask_i = mask_base everywhere, XOR 1 on the stops[i] top-ranked players.  -> (stops (steps,), masks (steps, n))"""
+    steps = min(n_players, steps)
+    ranking = descending_ranking(explanations)
+    stops = np.linspace(0, n_players, steps, dtype=np.int64)
+    masks = np.ones((steps, n_players), dtype=np.int64) * mask_base
+    for r, i in enumerate(stops):
+        masks[r, ranking[:i]] ^= 1
+    return stops, masks
+
+
+def selective_masks_from_keys(keys: np.ndarray, n_masked: int) -> np.ndarray:
+    """Fixed-count masks (reference models/shapley.py:118-128 draws the masked subset with random.shuffle): here the
+    subset is the n_masked top-ranked random keys, which is the same uniform distribution over subsets.
+    keys (rows, n) float32 -> (rows, n) int64 with exactly n_masked zeros per row."""
+    keys = np.asarray(keys, dtype=np.float32)
+    out = np.ones(keys.shape, dtype=np.int64)
+    for r in range(keys.shape[0]):
+        out[r, descending_ranking(keys[r])[:n_masked]] = 0
+    return out

@@ -567,3 +567,91 @@ def test_kernel_shap_recipe_end_to_end(agb):
     assert logits.shape == (2, 2) and attr.shape == (2, 2, n) and torch.isfinite(attr).all()
     with pytest.raises(NotImplementedError):
         rec.fw_explainer(exp, xs, None, None, None)
+
+
+# ------------------------------------------------------------------------------------------------
+# 8f-1: evaluators — rank masks on device, batched faithfulness curves, masked accuracy
+# ------------------------------------------------------------------------------------------------
+def test_perturbed_samples_bit_exact_vs_reference_golden(agb, golden_dir):
+    from autognothi_b200 import evaluators as ev
+    g = _load(golden_dir, "evaluators.npz")
+    for idx, (n, steps, base) in enumerate(g["perturb_cases"]):
+        attr = torch.from_numpy(g[f"perturb_{idx}_attr"]).to(DEV)
+        stops, masks = ev.get_perturbed_samples(attr, int(n), int(steps), int(base))
+        assert masks.dtype == torch.int64 and stops.dtype == torch.int64
+        np.testing.assert_array_equal(stops.cpu().numpy(), g[f"perturb_{idx}_stops"])
+        np.testing.assert_array_equal(masks.cpu().numpy(), g[f"perturb_{idx}_masks"].astype(np.int64))
+        _, pm = ev.get_perturbed_samples(attr, int(n), int(steps), int(base), packed=True)
+        np.testing.assert_array_equal(pm.dense().cpu().numpy(), g[f"perturb_{idx}_masks"].astype(np.int64))
+
+
+def test_rank_masks_many_rows_with_ties_vs_oracle(agb):
+    rng = np.random.RandomState(3)
+    n, R = 196, 37
+    scores = np.round(rng.randn(R, n), 1).astype(np.float32)         # rounding creates many ties
+    stops = np.array([0, 1, 17, 100, 195, 196], dtype=np.int32)
+    packed, dense = agb.rank_masks(torch.from_numpy(scores).to(DEV), torch.from_numpy(stops), n, 1, want_dense=True)
+    want = np.ones((R, len(stops), n), dtype=np.int64)
+    for r in range(R):
+        ranking = osh.descending_ranking(scores[r])
+        for i, s in enumerate(stops):
+            want[r, i, ranking[:s]] = 0
+    np.testing.assert_array_equal(dense.cpu().numpy().reshape(R, len(stops), n), want)
+    np.testing.assert_array_equal(agb.unpack_masks(packed, n, skip=1).cpu().numpy().reshape(R, len(stops), n), want)
+
+
+def test_mask_uniform_selective(agb, golden_dir):
+    import random
+    from autognothi_b200.models import shapley as ash
+    g = _load(golden_dir, "evaluators.npz")
+    random.seed(1234)                                                # same host stream as the golden generator
+    for idx, (b, n, k) in enumerate(g["selective_cases"]):
+        m = ash.mask_uniform_selective(int(b), int(n), int(k), device=DEV)
+        np.testing.assert_array_equal(m.cpu().numpy(), g[f"selective_{idx}"].astype(np.int64))
+    # device RNG: exact count per row, different rows differ, reproducible per (seed, offset)
+    m1 = ash.mask_uniform_selective(64, 196, 50, device=DEV, rng="philox", seed=5, offset=0)
+    m2 = ash.mask_uniform_selective(64, 196, 50, device=DEV, rng="philox", seed=5, offset=0)
+    m3 = ash.mask_uniform_selective(64, 196, 50, device=DEV, rng="philox", seed=5, offset=64)
+    assert m1.shape == (64, 196) and m1.dtype == torch.int64
+    assert bool(((m1 == 0).sum(dim=1) == 50).all())
+    assert torch.equal(m1, m2) and not torch.equal(m1, m3)
+    assert len({tuple(r) for r in m1.cpu().numpy().tolist()}) == 64
+    freq = (ash.mask_uniform_selective(4096, 32, 8, device=DEV, rng="philox", seed=9) == 0).float().mean(dim=0)
+    assert float((freq - 0.25).abs().max()) < 0.04                   # every player equally likely to be masked
+
+
+def test_faithfulness_infer_matches_row_by_row_evaluation(agb):
+    """Batched, on-device version == the reference's loop (one surrogate call per perturbed mask row)."""
+    from autognothi_b200 import evaluators as ev
+    rec, cfgd, srg, exp = _build("vit_mini", "fp32")
+    n = rec.n_players(rec.t_config(**cfgd))
+    xs = torch.from_numpy(synth.inputs(cfgd, 1, seed=4)).to(DEV)
+    C = cfgd["num_labels"]
+    explanation = torch.randn(1, C, n, device=DEV)
+    steps, base = 9, 1
+    curves = ev.faithfulness_infer(rec, srg, xs, explanation, steps, base, batch_size=4)
+    assert sorted(curves.keys()) == list(range(C))
+    for c in range(C):
+        stops, masks = osh.perturbed_samples(_np(explanation[0, c]), n, steps, base)
+        with torch.no_grad():
+            ys, _ = rec.fw_surrogate(srg, xs.repeat_interleave(len(stops), dim=0), torch.from_numpy(masks).to(DEV))
+        want = {int(s): float(ys[i, c]) for i, s in enumerate(stops)}
+        assert curves[c].keys() == want.keys()
+        for s in want:
+            assert abs(curves[c][s] - want[s]) <= 1e-6 + 1e-5 * abs(want[s])
+
+
+def test_measure_surrogate_accuracy(agb):
+    from autognothi_b200 import evaluators as ev
+    rec, cfgd, srg, exp = _build("vit_mini", "fp32")
+    n = rec.n_players(rec.t_config(**cfgd))
+    xs = torch.from_numpy(synth.inputs(cfgd, 6, seed=2)).to(DEV)
+    with torch.no_grad():
+        full, _ = rec.fw_surrogate(srg, xs, torch.ones((6, n), dtype=torch.int64, device=DEV))
+    labels = full.argmax(dim=1)
+    # nothing masked: the surrogate agrees with its own unmasked prediction on every input
+    assert ev.measure_surrogate_accuracy(rec, srg, [(xs[:3], labels[:3]), (xs[3:], labels[3:])], n, 0) == 1.0
+    acc = ev.measure_surrogate_accuracy(rec, srg, [(xs, (labels + 1) % cfgd["num_labels"])], n, 0)
+    assert acc == 0.0
+    acc_m = ev.measure_surrogate_accuracy(rec, srg, [(xs, labels)], n, n // 2, seed=3)
+    assert 0.0 <= acc_m <= 1.0

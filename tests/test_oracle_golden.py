@@ -149,3 +149,27 @@ def test_vit_masked_keys_still_contribute_bert_masked_keys_do_not():
     ids2 = ids.copy(); ids2[0, 4:10] = 7  # tokens 4..9 = players 3..8, all masked
     b = otr.fw_surrogate(sdb, cfgb, ids2, maskb)
     np.testing.assert_array_equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------
+# 8f-1: evaluator mask generators (goldens from scripts/measure_faithfulness.py and models/shapley.py)
+# ------------------------------------------------------------------------------------------------
+def test_perturbed_samples_bit_exact(golden_dir):
+    g = _load(golden_dir, "evaluators.npz")
+    for idx, (n, steps, base) in enumerate(g["perturb_cases"]):
+        stops, masks = osh.perturbed_samples(g[f"perturb_{idx}_attr"], int(n), int(steps), int(base))
+        np.testing.assert_array_equal(stops, g[f"perturb_{idx}_stops"])
+        np.testing.assert_array_equal(masks, g[f"perturb_{idx}_masks"].astype(np.int64))
+        # stop i flips exactly stops[i] players of the base mask
+        np.testing.assert_array_equal((masks != base).sum(axis=1), stops)
+
+
+def test_selective_masks_have_the_reference_shape_and_counts(golden_dir):
+    g = _load(golden_dir, "evaluators.npz")
+    rng = np.random.RandomState(0)
+    for idx, (b, n, k) in enumerate(g["selective_cases"]):
+        ref = g[f"selective_{idx}"].astype(np.int64)
+        assert ref.shape == (b, n) and ((ref == 0).sum(axis=1) == k).all()       # what the reference guarantees
+        mine = osh.selective_masks_from_keys(rng.rand(int(b), int(n)).astype(np.float32), int(k))
+        assert mine.shape == ref.shape and mine.dtype == np.int64
+        assert ((mine == 0).sum(axis=1) == k).all() and set(np.unique(mine)) <= {0, 1}
