@@ -113,6 +113,14 @@ def mask_shapley_new(n_mask_samples: int, n_players: int, *, device=None, rng: s
     return PackedMasks(words, n_players) if packed else dense
 
 
+def loss_logits_kl_divergence(ref: Tensor, current: Tensor) -> Tensor:
+    """reference models/shapley.py:96-106 — the surrogate-training objective: batch-mean KL divergence with
+    log_softmax(ref) as the input and softmax(current) as the target (both arguments are the models' outputs, which
+    are already probabilities there).  (B, C) tensors: stays in torch autograd."""
+    import torch.nn.functional as F
+    return F.kl_div(input=F.log_softmax(ref, dim=-1), target=F.softmax(current, dim=-1), reduction="batchmean")
+
+
 def mask_purely_uniform(batch_size: int, n_features: int, *, device=None, rng: str = "torch", seed: int = 0,
                         offset: int = 0, packed: bool = False):
     """reference models/shapley.py:109-115"""

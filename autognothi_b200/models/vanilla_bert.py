@@ -84,6 +84,16 @@ class VanillaBertSurrogate(VanillaBertClassifier):
         nn.Module.train(self, mode)
         return self
 
+    def forward(self, input_ids: Tensor, attention_mask: MaskLike, token_type_ids: Optional[Tensor] = None,
+                n_mask_samples: int = 1) -> Tensor:
+        # surrogate training (reference scripts/train_surrogate.py:131-150): differentiable w.r.t. the parameters
+        if n_mask_samples == 1 and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .. import training
+            _check_token_types(token_type_ids)
+            words = pack_token_mask(attention_mask, input_ids.shape[0], engine.n_players_of(self.config))
+            return training.surrogate_forward_train(self, input_ids, words)
+        return super().forward(input_ids, attention_mask, token_type_ids, n_mask_samples)
+
 
 class VanillaBertExplainer(_EngineModule):
     """reference models/vanilla_bert.py:90-164"""

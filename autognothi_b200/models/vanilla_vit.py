@@ -97,6 +97,14 @@ class VanillaViTSurrogate(VanillaViTClassifier):
         nn.Module.train(self, mode)
         return self
 
+    def forward(self, x: Tensor, attention_mask: MaskLike, n_mask_samples: int = 1) -> Tensor:
+        # surrogate training (reference scripts/train_surrogate.py:131-150): differentiable w.r.t. the parameters
+        if n_mask_samples == 1 and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .. import training
+            words = pack_token_mask(attention_mask, x.shape[0], engine.n_players_of(self.config))
+            return training.surrogate_forward_train(self, x, words)
+        return super().forward(x, attention_mask, n_mask_samples)
+
 
 class VanillaViTExplainer(_EngineModule):
     """reference models/vanilla_vit.py:69-132"""

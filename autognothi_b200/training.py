@@ -140,6 +140,50 @@ def bert_layer_bwd(pol, lw: LayerWeights, prefix: str, t: dict, dy: Tensor, mask
     return _dgrad(pol, dqkv, lw.wqkv, out_f32=True, residual=d_apre)
 
 
+def _embed_fwd(tp, bw, cfg, pol, xs: Tensor):
+    """Embeddings with S = 1 (one mask row per input); keeps what the adjoint needs on the tape."""
+    T, H, eps = tp.T, cfg.hidden_size, cfg.layer_norm_eps
+    B = xs.shape[0]
+    if bw.vit:
+        tp.patches = ops.vit_im2col(xs.float(), cfg.img_patch_size, pol.act_dtype)
+        pe = pol.linear(tp.patches, bw.w_patch, bw.b_patch, out_f32=True)
+        return ops.vit_assemble(pe, bw.cls_token, bw.pos_emb, B, 1, T, H).reshape(B * T, H), None
+    x = ops.bert_embed(xs, bw.word, bw.pos, bw.type0, bw.emb_ln[0], bw.emb_ln[1], eps, 1).reshape(B * T, H)
+    return x, pol.act(x)
+
+
+def _embed_bwd(tp, dx: Tensor, grads: Grads) -> None:
+    """Adjoint of the embeddings (reference models/vanilla_vit.py:242-253, models/vanilla_bert.py:307-325)."""
+    pol, cfg, bw = tp.pol, tp.cfg, tp.bw
+    vit = bw.vit
+    T, B = tp.T, tp.B
+    H, eps = cfg.hidden_size, cfg.layer_norm_eps
+    if vit:
+        dpos = torch.zeros((T, H), dtype=torch.float32, device=dx.device)
+        dcls = torch.zeros((H,), dtype=torch.float32, device=dx.device)
+        dpatch = ops.vit_embed_bwd(dx, B, T, H, dpos, dcls, pol.act_dtype)
+        e = "vit.embeddings."
+        grads[e + "position_embeddings"] = dpos.reshape(1, T, H)
+        grads[e + "cls_token"] = dcls.reshape(1, 1, H)
+        dwp = _wgrad(pol, dpatch, tp.patches)
+        P = cfg.img_patch_size
+        grads[e + "patch_embeddings.projection.weight"] = dwp.reshape(H, cfg.img_channels, P, P)
+        grads[e + "patch_embeddings.projection.bias"] = _bias_grad(dpatch)
+    else:
+        e = "bert.embeddings."
+        pre = ops.bert_embed_sum(tp.xs, bw.word, bw.pos, bw.type0)
+        dsum = _ln_bwd(grads, e + "LayerNorm", pre, dx, bw.emb_ln[0], eps, None)
+        dword = torch.zeros_like(bw.word)
+        dpos = torch.zeros_like(bw.pos)
+        dtype0 = torch.zeros((H,), dtype=torch.float32, device=dx.device)
+        ops.bert_embed_scatter(tp.xs, dsum, cfg.pad_token_id, dword, dpos, dtype0)
+        dtt = torch.zeros((cfg.type_vocab_size, H), dtype=torch.float32, device=dx.device)
+        dtt[0] = dtype0
+        grads[e + "word_embeddings.weight"] = dword
+        grads[e + "position_embeddings.weight"] = dpos
+        grads[e + "token_type_embeddings.weight"] = dtt
+
+
 # ------------------------------------------------------------------------------------------------
 # whole explainer
 # ------------------------------------------------------------------------------------------------
@@ -158,15 +202,7 @@ def forward_train(sd: Dict[str, Tensor], cfg, precision: str, xs: Tensor, masks:
     B = xs.shape[0]
     tp.bw, tp.T, tp.B = bw, T, B
     root = "vit" if vit else "bert"
-    # embeddings
-    if vit:
-        tp.patches = ops.vit_im2col(xs.float(), cfg.img_patch_size, pol.act_dtype)
-        pe = pol.linear(tp.patches, bw.w_patch, bw.b_patch, out_f32=True)
-        x = ops.vit_assemble(pe, bw.cls_token, bw.pos_emb, B, 1, T, H).reshape(B * T, H)
-        xa = None
-    else:
-        x = ops.bert_embed(xs, bw.word, bw.pos, bw.type0, bw.emb_ln[0], bw.emb_ln[1], eps, 1).reshape(B * T, H)
-        xa = pol.act(x)
+    x, xa = _embed_fwd(tp, bw, cfg, pol, xs)
     tp.layers = []
     for i, lw in enumerate(bw.layers):
         prefix = f"{root}.encoder.layers.{i}"
@@ -234,31 +270,7 @@ def backward_train(tp: _Tape, dphi: Tensor) -> Grads:
             dx = vit_layer_bwd(pol, lw, prefix, t, dx, tp.masks, T, heads, eps, grads)
         else:
             dx = bert_layer_bwd(pol, lw, prefix, t, dx, tp.masks, T, heads, eps, grads)
-    # embeddings
-    if vit:
-        dpos = torch.zeros((T, H), dtype=torch.float32, device=dx.device)
-        dcls = torch.zeros((H,), dtype=torch.float32, device=dx.device)
-        dpatch = ops.vit_embed_bwd(dx, B, T, H, dpos, dcls, pol.act_dtype)
-        e = "vit.embeddings."
-        grads[e + "position_embeddings"] = dpos.reshape(1, T, H)
-        grads[e + "cls_token"] = dcls.reshape(1, 1, H)
-        dwp = _wgrad(pol, dpatch, tp.patches)
-        P = cfg.img_patch_size
-        grads[e + "patch_embeddings.projection.weight"] = dwp.reshape(H, cfg.img_channels, P, P)
-        grads[e + "patch_embeddings.projection.bias"] = _bias_grad(dpatch)
-    else:
-        e = "bert.embeddings."
-        pre = ops.bert_embed_sum(tp.xs, bw.word, bw.pos, bw.type0)
-        dsum = _ln_bwd(grads, e + "LayerNorm", pre, dx, bw.emb_ln[0], eps, None)
-        dword = torch.zeros_like(bw.word)
-        dpos = torch.zeros_like(bw.pos)
-        dtype0 = torch.zeros((H,), dtype=torch.float32, device=dx.device)
-        ops.bert_embed_scatter(tp.xs, dsum, cfg.pad_token_id, dword, dpos, dtype0)
-        dtt = torch.zeros((cfg.type_vocab_size, H), dtype=torch.float32, device=dx.device)
-        dtt[0] = dtype0
-        grads[e + "word_embeddings.weight"] = dword
-        grads[e + "position_embeddings.weight"] = dpos
-        grads[e + "token_type_embeddings.weight"] = dtt
+    _embed_bwd(tp, dx, grads)
     return grads
 
 
@@ -294,3 +306,89 @@ def explainer_forward_train(model, xs: Tensor, words: Tensor, grand: Optional[Te
     g = grand.detach() if grand is not None else None
     nl = null.detach() if null is not None else None
     return _ExplainerTrainFn.apply(xs, words, g, nl, model.config, model.agb_precision, names, *params)
+
+
+# ------------------------------------------------------------------------------------------------
+# surrogate training (reference scripts/train_surrogate.py:131-150): the masked backbone is ONE
+# autograd node returning the CLS rows of the last hidden state; the tiny head (final LayerNorm / pooler, Linear,
+# Softmax on B rows) and loss_logits_kl_divergence stay in torch autograd.
+# ------------------------------------------------------------------------------------------------
+def backbone_forward_train(sd: Dict[str, Tensor], cfg, precision: str, xs: Tensor, masks: Tensor) -> Tuple[Tensor, _Tape]:
+    """-> (x_cls (B, H) fp32: ViT = last block output BEFORE vit.layernorm, BERT = last block output; tape)"""
+    pol = _Policy(precision)
+    tp = _Tape()
+    tp.pol, tp.cfg, tp.masks, tp.xs = pol, cfg, masks, xs
+    bw = engine.BackboneWeights(sd, cfg, pol)
+    T = n_players_of(cfg) + 1
+    heads, eps = cfg.num_attention_heads, cfg.layer_norm_eps
+    tp.bw, tp.T, tp.B = bw, T, xs.shape[0]
+    assert masks.shape[0] == tp.B, "surrogate training takes one mask row per input"
+    root = "vit" if bw.vit else "bert"
+    x, xa = _embed_fwd(tp, bw, cfg, pol, xs)
+    tp.layers = []
+    for i, lw in enumerate(bw.layers):
+        if bw.vit:
+            x, t = vit_layer_fwd(pol, lw, x, masks, T, heads, eps)
+        else:
+            x, xa, t = bert_layer_fwd(pol, lw, x, xa, masks, T, heads, eps)
+        tp.layers.append((f"{root}.encoder.layers.{i}", lw, t))
+    return x.reshape(tp.B, T, -1)[:, 0, :].contiguous(), tp
+
+
+def backbone_backward_train(tp: _Tape, dx_cls: Tensor) -> Grads:
+    pol, cfg, bw = tp.pol, tp.cfg, tp.bw
+    T, B = tp.T, tp.B
+    H, heads, eps = cfg.hidden_size, cfg.num_attention_heads, cfg.layer_norm_eps
+    grads: Grads = {}
+    dx = torch.zeros((B, T, H), dtype=torch.float32, device=dx_cls.device)
+    dx[:, 0, :] = dx_cls
+    dx = dx.reshape(B * T, H)
+    for prefix, lw, t in reversed(tp.layers):
+        if bw.vit:
+            dx = vit_layer_bwd(pol, lw, prefix, t, dx, tp.masks, T, heads, eps, grads)
+        else:
+            dx = bert_layer_bwd(pol, lw, prefix, t, dx, tp.masks, T, heads, eps, grads)
+    _embed_bwd(tp, dx, grads)
+    return grads
+
+
+class _BackboneTrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xs, masks, cfg, precision, names, *params):
+        sd = {n: p.detach() for n, p in zip(names, params)}
+        with torch.no_grad():
+            x_cls, tape = backbone_forward_train(sd, cfg, precision, xs, masks)
+        ctx.tape, ctx.names = tape, names
+        ctx.shapes = [p.shape for p in params]
+        return x_cls
+
+    @staticmethod
+    def backward(ctx, dx_cls):
+        with torch.no_grad():
+            grads = backbone_backward_train(ctx.tape, dx_cls.contiguous().float())
+        ctx.tape = None
+        out = []
+        for n, shp in zip(ctx.names, ctx.shapes):
+            g = grads.get(n)
+            out.append(g.reshape(shp) if g is not None else None)
+        return (None, None, None, None, None, *out)
+
+
+def surrogate_forward_train(model, xs: Tensor, words: Tensor) -> Tensor:
+    """Differentiable (w.r.t. parameters) masked surrogate / classifier forward -> (B, num_labels) probabilities.
+    reference models/vanilla_vit.py:51-56 and models/vanilla_bert.py:61-77 in train() mode, dropout p = 0."""
+    named = dict(model.named_parameters())
+    if next(iter(named.values())).device.type != "cuda":
+        raise RuntimeError("autognothi_b200 models run on CUDA only (no CPU fallback)")
+    cfg = model.config
+    vit = hasattr(cfg, "img_px_size")
+    root = "vit." if vit else "bert."
+    names = [n for n in named if n.startswith(root)]   # vit.layernorm.* ride along unused (their grads come from the torch head)
+    x_cls = _BackboneTrainFn.apply(xs, words, cfg, model.agb_precision, names, *[named[n] for n in names])
+    if vit:
+        h = torch.nn.functional.layer_norm(x_cls, (cfg.hidden_size,), named["vit.layernorm.weight"],
+                                           named["vit.layernorm.bias"], cfg.layer_norm_eps)
+    else:
+        h = torch.tanh(torch.nn.functional.linear(x_cls, named["bert_pooler.dense.weight"], named["bert_pooler.dense.bias"]))
+    logits = torch.nn.functional.linear(h, named["classifier.weight"], named["classifier.bias"])
+    return torch.softmax(logits, dim=-1)

@@ -202,11 +202,59 @@ def gen_train_grads():
         print(f"train_{name}.npz loss={float(loss):.6f} params={len(norms)} stored={len(out) - 3}")
 
 
+def gen_surrogate_train_grads():
+    """One surrogate training step (scripts/train_surrogate.py:131-150): classifier teacher on the full input, masked
+    surrogate student, loss_logits_kl_divergence, parameter gradients from the reference's autograd; eval() mode so
+    that dropout is the identity."""
+    for name, B, S in [("vit_mini", 2, 4), ("bert_mini", 3, 4)]:
+        cfg = ocfg.get_config(name)
+        vit = ocfg.is_vit(cfg)
+        n = ocfg.n_players(cfg)
+        if vit:
+            rcfg = ref_vit.VanillaViTConfig(**cfg)
+            cls, srg, rec = ref_vit.VanillaViTClassifier(rcfg), ref_vit.VanillaViTSurrogate(rcfg), ref_rvit
+        else:
+            rcfg = ref_bert.VanillaBertConfig(**cfg)
+            cls, srg, rec = ref_bert.VanillaBertClassifier(rcfg), ref_bert.VanillaBertSurrogate(rcfg), ref_rbert
+        cls.load_state_dict(to_torch_state(synth.surrogate_state(cfg, seed=5)), strict=True)
+        srg.load_state_dict(to_torch_state(synth.surrogate_state(cfg, seed=0)), strict=True)
+        cls.eval(); srg.eval()
+        g = np.load(os.path.join(HERE, f"model_{name}.npz"))
+        masks = torch.from_numpy(g["masks"].astype(np.int64)).reshape(B, S, n)[:, 1, :].contiguous()   # one row per input
+        xs = torch.from_numpy(synth.inputs(cfg, B, seed=0))
+        ones = torch.ones((B, n), dtype=torch.long)
+        with torch.no_grad():
+            _, orig = rec._fw_classifier(cls, xs, ones)
+        with torch.enable_grad():
+            for p_ in srg.parameters():
+                p_.requires_grad_(True)
+            adapt, _ = rec._fw_surrogate(srg, xs, masks)
+            loss = ref_shapley.loss_logits_kl_divergence(orig, adapt)
+            loss.backward()
+        out = {"loss": loss.detach().numpy(), "orig": orig.numpy(), "adapt": adapt.detach().numpy(),
+               "masks": masks.numpy().astype(np.int8)}
+        norms = {}
+        for k, p_ in srg.named_parameters():
+            gr = p_.grad
+            norms[k] = float(gr.norm()) if gr is not None else 0.0
+            if gr is not None and (gr.numel() <= 1024 or "layers.0.attention.self.key.weight" in k
+                                   or "layers.1.output.dense.weight" in k):
+                out["grad::" + k] = gr.numpy()
+        out["norm_names"] = np.array(list(norms.keys()))
+        out["norm_values"] = np.array(list(norms.values()), dtype=np.float64)
+        np.savez_compressed(os.path.join(HERE, f"train_surrogate_{name}.npz"), **out)
+        print(f"train_surrogate_{name}.npz loss={float(loss):.6e} params={len(norms)} stored={len(out) - 6}")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "train":
         gen_train_grads()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "surrogate":
+        gen_surrogate_train_grads()
         sys.exit(0)
     gen_sampler()
     gen_shapley_math()
     gen_models()
     gen_train_grads()
+    gen_surrogate_train_grads()

@@ -655,3 +655,98 @@ def test_measure_surrogate_accuracy(agb):
     assert acc == 0.0
     acc_m = ev.measure_surrogate_accuracy(rec, srg, [(xs, labels)], n, n // 2, seed=3)
     assert 0.0 <= acc_m <= 1.0
+
+
+# ------------------------------------------------------------------------------------------------
+# 8f-2: surrogate training (masked backbone adjoint + KL objective) vs the reference's autograd
+# ------------------------------------------------------------------------------------------------
+def _surrogate_train_step(golden_dir, name, precision):
+    from autognothi_b200.models import shapley as ash
+    t = _load(golden_dir, f"train_surrogate_{name}.npz")
+    rec, cfgd, srg, _exp = _build(name, precision)
+    cfg = rec.t_config(**cfgd)
+    cls = rec.t_classifier(cfg)
+    cls.load_state_dict({k: torch.from_numpy(v) for k, v in synth.surrogate_state(cfgd, seed=5).items()}, strict=True)
+    cls = cls.to(DEV).eval()
+    cls.agb_precision = precision
+    srg.train()          # dropout is not applied on this path (p = 0); the golden ran the reference in eval()
+    B, n = t["masks"].shape
+    xs = torch.from_numpy(synth.inputs(cfgd, B, seed=0)).to(DEV)
+    masks = torch.from_numpy(t["masks"].astype(np.int64)).to(DEV)
+    ones = torch.ones((B, n), dtype=torch.int64, device=DEV)
+    with torch.no_grad():
+        _, orig = rec.fw_classifier(cls, xs, ones)
+    adapt, _ = rec.fw_surrogate(srg, xs, masks)
+    assert adapt.requires_grad
+    loss = ash.loss_logits_kl_divergence(orig, adapt)
+    loss.backward()
+    return t, srg, orig, adapt, float(loss.detach())
+
+
+@pytest.mark.parametrize("name", ["vit_mini", "bert_mini"])
+def test_surrogate_training_gradients_fp32_vs_reference_autograd(agb, golden_dir, name):
+    t, srg, orig, adapt, loss = _surrogate_train_step(golden_dir, name, "fp32")
+    np.testing.assert_allclose(_np(orig), t["orig"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(_np(adapt), t["adapt"], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(loss, float(t["loss"]), rtol=2e-3)
+    ref_norms = dict(zip([str(s) for s in t["norm_names"]], t["norm_values"]))
+    params = dict(srg.named_parameters())
+    assert set(params) == set(ref_norms)
+    floor = 1e-5 * max(ref_norms.values())
+    for k, p in params.items():
+        if ref_norms[k] == 0.0 and p.grad is None:
+            continue                                   # parameters the objective does not reach on either side
+        assert p.grad is not None, f"no gradient for {k}"
+        got = float(p.grad.norm())
+        assert abs(got - ref_norms[k]) <= 2e-3 * ref_norms[k] + floor, f"{k}: |grad| {got} vs {ref_norms[k]}"
+    for key in t.files:
+        if key.startswith("grad::"):
+            k = key[len("grad::"):]
+            ref = t[key]
+            np.testing.assert_allclose(_np(params[k].grad), ref, rtol=2e-3, atol=2e-3 * np.abs(ref).max() + floor, err_msg=k)
+
+
+@pytest.mark.parametrize("name", ["vit_mini", "bert_mini"])
+def test_surrogate_training_gradients_bf16_tensor_cores(agb, golden_dir, name):
+    t, srg, orig, adapt, loss = _surrogate_train_step(golden_dir, name, "bf16")
+    ref_norms = dict(zip([str(s) for s in t["norm_names"]], t["norm_values"]))
+    params = dict(srg.named_parameters())
+    big = [k for k, v in ref_norms.items() if v >= 1e-2 * max(ref_norms.values())]
+    for k in big:
+        got = float(params[k].grad.norm())
+        assert abs(got - ref_norms[k]) <= 0.1 * ref_norms[k], f"{k}: |grad| {got} vs {ref_norms[k]}"
+    for key in t.files:
+        if key.startswith("grad::") and key[len("grad::"):] in big:
+            k = key[len("grad::"):]
+            a, b = _np(params[k].grad).reshape(-1), t[key].reshape(-1).astype(np.float64)
+            cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30))
+            assert cos > 0.99, f"{k}: cosine {cos}"
+
+
+def test_surrogate_training_loop_reduces_kl(agb):
+    """A few optimizer steps of the reference's surrogate loop body (scripts/train_surrogate.py:131-150) on the
+    drop-in recipe: the KL objective goes down."""
+    from autognothi_b200.models import shapley as ash
+    rec, cfgd, srg, _exp = _build("vit_mini", "bf16")
+    cfg = rec.t_config(**cfgd)
+    n = rec.n_players(cfg)
+    cls = rec.t_classifier(cfg)
+    cls.load_state_dict({k: torch.from_numpy(v) for k, v in synth.surrogate_state(cfgd, seed=5).items()}, strict=True)
+    cls = cls.to(DEV).eval()
+    srg.train()
+    opt = torch.optim.AdamW(srg.parameters(), lr=2e-3)
+    xs = torch.from_numpy(synth.inputs(cfgd, 8, seed=1)).to(DEV)
+    ones = torch.ones((8, n), dtype=torch.int64, device=DEV)
+    with torch.no_grad():
+        _, orig = rec.fw_classifier(cls, xs, ones)
+    losses = []
+    for step in range(12):
+        masks = ash.mask_purely_uniform(8, n, device=DEV, rng="philox", seed=11, offset=0)    # same masks every step
+        opt.zero_grad()
+        adapt, _ = rec.fw_surrogate(srg, xs, masks)
+        loss = ash.loss_logits_kl_divergence(orig, adapt)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert np.isfinite(losses).all()
+    assert losses[-1] < 0.7 * losses[0], losses
