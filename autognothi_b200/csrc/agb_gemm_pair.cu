@@ -42,6 +42,9 @@ struct PairGemmParams {
   float ln_eps;
   // STATS: besides the fp32 output, emit a bf16 copy (tmOut2) and this GEMM's own per-row partial statistics
   float* stats_out;        // [M][2 * tiles_n][2]
+  // split-K (wgrad: few output tiles, very long K): tile t = (split, m, n); split sp covers k-blocks
+  // [sp * kb_per_split, ...) and stores its fp32 partial at output rows sp * M + m (reduced by splitk_reduce_kernel)
+  int splits, kb_per_split;
 };
 
 template <int CG, int STAGES, int NBUF, int ACT, int RES, int OUT_F32, int LNIN, int STATS>
@@ -83,7 +86,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_pairs = gridDim.x / CG;
   const int tiles_m = (p.M + PG_BM * CG - 1) / (PG_BM * CG);
   const int tiles_n = (p.N + PG_BN - 1) / PG_BN;
-  const int num_tiles = tiles_m * tiles_n;
+  const int tiles_mn = tiles_m * tiles_n;
+  const int num_tiles = tiles_mn * p.splits;
   const int num_kb = (p.K + PG_BK - 1) / PG_BK;
 
   if (warp == 0 && lane == 0) {
@@ -120,9 +124,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]);
     uint32_t stage = 0, phase = 0;
     for (int t = pair; t < num_tiles; t += num_pairs) {
-      const int m0 = (t / tiles_n) * (PG_BM * CG) + (int)cta_rank * PG_BM;
-      const int n0 = (t % tiles_n) * PG_BN + (int)cta_rank * B_ROWS;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int sp = t / tiles_mn, tt = t - sp * tiles_mn;
+      const int m0 = (tt / tiles_n) * (PG_BM * CG) + (int)cta_rank * PG_BM;
+      const int n0 = (tt % tiles_n) * PG_BN + (int)cta_rank * B_ROWS;
+      const int kb_end = min(num_kb, (sp + 1) * p.kb_per_split);
+      for (int kb = sp * p.kb_per_split; kb < kb_end; ++kb) {
         mbar_wait(empty0 + stage * 8, phase ^ 1);
         const uint32_t full = full0 + stage * 8;
         if (leader) mbar_arrive_expect_tx_e(e, full, STAGE_BYTES * CG);   // both CTAs' bytes land on the leader
@@ -176,7 +182,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(tempty0 + acc * 8, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * PG_BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int sp = t / tiles_mn;
+        const int kb_begin = sp * p.kb_per_split, kb_end = min(num_kb, (sp + 1) * p.kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(full0 + stage * 8, phase);
           tc_fence_after();
           const uint32_t sa = (smem_base + stage * STAGE_BYTES) >> 4;
@@ -184,10 +192,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < PG_BK / 16; ++k) {
             umma_ss_e<CG>(e, d_tmem, da0 + (sa + k * a_kstep), db0 + (sb + k * b_kstep), idesc,
-                          (kb | k) != 0 ? 1u : 0u);
+                          ((kb - kb_begin) | k) != 0 ? 1u : 0u);
           }
           umma_commit_e<CG>(e, empty0 + stage * 8);
-          if (kb == num_kb - 1) umma_commit_e<CG>(e, tfull0 + acc * 8);
+          if (kb == kb_end - 1) umma_commit_e<CG>(e, tfull0 + acc * 8);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         acc ^= 1;
@@ -211,8 +219,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto chunk_coords = [&](int g, int& row0, int& col0) -> bool {
       const int t = pair + (g / NCHUNK) * num_pairs;
       if (t >= num_tiles) return false;
-      row0 = (t / tiles_n) * (PG_BM * CG) + (int)cta_rank * PG_BM + q * 32;
-      col0 = (t % tiles_n) * PG_BN + h * (PG_BN / 2) + (g % NCHUNK) * CHUNK_COLS;
+      const int tt = t % tiles_mn;     // (residual loads are never combined with split-K)
+      row0 = (tt / tiles_n) * (PG_BM * CG) + (int)cta_rank * PG_BM + q * 32;
+      col0 = (tt % tiles_n) * PG_BN + h * (PG_BN / 2) + (g % NCHUNK) * CHUNK_COLS;
       return row0 < p.M && col0 < p.N;
     };
     auto issue_res = [&](int g) {  // lane 0 only
@@ -233,9 +242,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tfull0 = smem_u32(&bar_tfull[0]);
     int g = 0;
     for (int t = pair; t < num_tiles; t += num_pairs) {
-      const int row0 = (t / tiles_n) * (PG_BM * CG) + (int)cta_rank * PG_BM + q * 32;
-      const int tcol0 = (t % tiles_n) * PG_BN + h * (PG_BN / 2);
+      const int sp = t / tiles_mn, tt = t - sp * tiles_mn;
+      const int row0 = (tt / tiles_n) * (PG_BM * CG) + (int)cta_rank * PG_BM + q * 32;
+      const int tcol0 = (tt % tiles_n) * PG_BN + h * (PG_BN / 2);
       const bool row_ok = row0 < p.M;
+      const int out_row0 = row0 + sp * p.M;     // split-K partials are stacked along the rows of the workspace
       float ln_rstd = 1.f, ln_nmr = 0.f;      // LNIN: rstd_i and -mean_i * rstd_i of this thread's row
       if (LNIN) {
         const int my_row = row0 + lane;
@@ -364,7 +375,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmOut, buf, col0, row0);
+            tma_store_2d(&tmOut, buf, col0, out_row0);
             if (STATS && (c & 1)) tma_store_2d(&tmOut2, buf16, col0 - CHUNK_COLS, row0);   // 64 bf16 columns
             bulk_commit();
             if (RES) bulk_wait_read<0>();   // boxes handed to the store engine: free for the next residual / copy
@@ -376,7 +387,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (STATS) {
         const int my_row = row0 + lane;
         if (my_row < p.M)
-          reinterpret_cast<float2*>(p.stats_out)[(long long)my_row * (2 * tiles_n) + (t % tiles_n) * 2 + h] =
+          reinterpret_cast<float2*>(p.stats_out)[(long long)my_row * (2 * tiles_n) + (tt % tiles_n) * 2 + h] =
               make_float2(st_sum, st_sq);
       }
       acc ^= 1;
@@ -427,7 +438,7 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
       max_pairs = sm_count();
     }
   }
-  const int tiles = ((p.M + PG_BM * CG - 1) / (PG_BM * CG)) * ((p.N + PG_BN - 1) / PG_BN);
+  const int tiles = ((p.M + PG_BM * CG - 1) / (PG_BM * CG)) * ((p.N + PG_BN - 1) / PG_BN) * p.splits;
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(pairs * CG, 1, 1);
@@ -441,6 +452,22 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   AGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmRes, tmOut2, p));
   return AGB_OK;
 }
+
+// fixed-order sum of the split-K partials: out[m][n] = sum_sp ws[sp][m][n]  (float4 per thread; deterministic)
+__global__ void splitk_reduce_kernel(const float4* __restrict__ ws, int splits, long long mn4, long long ld4,
+                                     long long n4, float4* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= mn4) return;
+  float4 a = ws[i];
+  for (int s = 1; s < splits; ++s) {
+    const float4 b = ws[(long long)s * mn4 + i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  out[(i / n4) * ld4 + (i % n4)] = a;
+}
+
+static float* g_splitk_ws = nullptr;      // grow-only workspace (single-stream use, like the rest of the library)
+static size_t g_splitk_ws_bytes = 0;
 
 static int g_gemm_variant = 0;  // 0 auto, 1 legacy kernel only, 2 force CG=1, 3 force CG=2
 void set_gemm_variant(int v) { g_gemm_variant = v; }
@@ -477,6 +504,37 @@ int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, 
   if (g_gemm_variant == 2) cg = 1;
   if (g_gemm_variant == 3) cg = 2;
 
+  // split-K: few output tiles and a very long K (the wgrad GEMMs dW = dY^T X with K = rows of the batch)
+  int splits = 1;
+  const int num_kb = (K + PG_BK - 1) / PG_BK;
+  void* final_out = out;
+  const int final_ldo = ldo;
+  if (cg == 1 && out_f32 && !res_f32 && !lnin && !stats && act == 0 && bias == nullptr && alpha == 1.0f &&
+      (M % PG_BM) == 0 && (N % 4) == 0 && (ldo % 4) == 0 && num_kb >= 32 && g_gemm_variant == 0) {
+    const long long tiles1 = (long long)(M / PG_BM) * ((N + PG_BN - 1) / PG_BN);
+    int want = (int)(sm_count() / tiles1);
+    if (want > 16) want = 16;
+    if (want > num_kb / 8) want = num_kb / 8;
+    if (want >= 2) {
+      const size_t need = (size_t)want * M * N * sizeof(float);
+      if (need > g_splitk_ws_bytes && need <= ((size_t)1 << 30)) {
+        if (g_splitk_ws != nullptr) {
+          AGB_CHECK_CUDA(cudaStreamSynchronize(stream));
+          AGB_CHECK_CUDA(cudaFree(g_splitk_ws));
+        }
+        AGB_CHECK_CUDA(cudaMalloc(&g_splitk_ws, need));
+        g_splitk_ws_bytes = need;
+      }
+      if (need <= g_splitk_ws_bytes) {
+        splits = want;
+        out = g_splitk_ws;
+        ldo = N;
+      }
+    }
+  }
+  int kb_per_split = (num_kb + splits - 1) / splits;
+  splits = (num_kb + kb_per_split - 1) / kb_per_split;      // no empty splits
+
   CUtensorMap tmA, tmB, tmOut, tmRes, tmOut2;
   int rc;
   if (!a_mn) rc = encode_tmap_2d_bf16(&tmA, A, K, M, (uint64_t)lda * 2, PG_BK, PG_BM);
@@ -485,7 +543,7 @@ int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, 
   if (!b_mn) rc = encode_tmap_2d_bf16(&tmB, B, K, N, (uint64_t)ldb * 2, PG_BK, PG_BN / cg);
   else       rc = encode_tmap_2d_bf16(&tmB, B, N, K, (uint64_t)ldb * 2, 64, PG_BK);
   if (rc != AGB_OK) return rc;
-  rc = encode_tmap_2d(&tmOut, out, oes, N, M, (uint64_t)ldo * oes, out_f32 ? 32 : 64, 32);
+  rc = encode_tmap_2d(&tmOut, out, oes, N, (uint64_t)M * splits, (uint64_t)ldo * oes, out_f32 ? 32 : 64, 32);
   if (rc != AGB_OK) return rc;
   if (res_f32) rc = encode_tmap_2d(&tmRes, res_f32, 4, N, M, (uint64_t)ldr * 4, 32, 32);
   else         tmRes = tmOut;
@@ -506,10 +564,19 @@ int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, 
   }
   PairGemmParams p;
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.alpha = alpha; p.a_mn = a_mn; p.b_mn = b_mn;
+  p.splits = splits; p.kb_per_split = kb_per_split;
   p.ln_stats = ln_stats; p.ln_parts = ln_parts; p.ln_colsum = ln_colsum; p.ln_eps = ln_eps; p.stats_out = stats_out;
   const int res = res_f32 ? 2 : 0;
   // (stages, residual ring) per configuration: CTA pairs stage 32 KB per k-block (5 stages: the K = 3072 GEMM was
   // latency-starved with 4), single CTAs 48 KB (3 stages); the statistics variant trades one ring slot for the copy box
+  auto finish = [&](int lrc) -> int {
+    if (lrc != AGB_OK || splits == 1) return lrc;
+    const long long mn4 = (long long)M * N / 4;
+    splitk_reduce_kernel<<<(unsigned)((mn4 + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const float4*>(g_splitk_ws), splits, mn4, final_ldo / 4, N / 4, reinterpret_cast<float4*>(final_out));
+    AGB_CHECK_CUDA(cudaGetLastError());
+    return AGB_OK;
+  };
 #define AGB_PAIR_CASE(A_, R_, O_, L_, S_)                                                                          \
   if (act == A_ && res == R_ && out_f32 == O_ && (int)lnin == L_ && (int)stats == S_) {                            \
     if (cg == 2)                                                                                                   \
@@ -521,7 +588,7 @@ int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, 
                                                                                          stream);                  \
       return launch_pair<2, 5, (S_ ? 1 : 2), A_, R_, O_, L_, S_>(tmA, tmB, tmOut, tmRes, tmOut2, p, stream);       \
     }                                                                                                              \
-    return launch_pair<1, 3, (S_ ? 1 : 2), A_, R_, O_, L_, S_>(tmA, tmB, tmOut, tmRes, tmOut2, p, stream);         \
+    return finish(launch_pair<1, 3, (S_ ? 1 : 2), A_, R_, O_, L_, S_>(tmA, tmB, tmOut, tmRes, tmOut2, p, stream)); \
   }
   AGB_PAIR_CASE(0, 0, 0, 0, 0)
   AGB_PAIR_CASE(0, 0, 1, 0, 0)

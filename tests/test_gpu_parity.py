@@ -199,6 +199,50 @@ def test_vit_base_layernorm_folding_matches_layernorm_kernels(agb):
     np.testing.assert_allclose(_np(p_fused), _np(p_plain), atol=5e-3)
 
 
+@pytest.mark.parametrize("M,N,K", [(768, 768, 6304), (2304, 768, 25216), (768, 3072, 6304), (128, 256, 4096)])
+def test_gemm_bf16_wgrad_split_k(agb, M, N, K):
+    """dW = dY^T X with both operands MN-major: few output tiles, very long K -> split-K partials + ordered reduce."""
+    torch.manual_seed(2)
+    dy = (torch.randn(K, M, device=DEV) * 0.1).bfloat16()       # [rows, N_out]
+    x = torch.randn(K, N, device=DEV).bfloat16()                # [rows, K_in]
+    out = agb.gemm_bf16(dy, x, a_mn=True, w_mn=True, out_dtype=torch.float32)
+    ref = dy.float().t() @ x.float()
+    torch.testing.assert_close(out, ref, rtol=2e-3, atol=2e-3 * float(ref.abs().max()))
+    out2 = agb.gemm_bf16(dy, x, a_mn=True, w_mn=True, out_dtype=torch.float32)
+    assert torch.equal(out, out2)                               # fixed-order reduction: bit-reproducible
+
+
+@pytest.mark.parametrize("rows,H", [(6304, 768), (1000, 1024), (77, 128), (500, 192)])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_layernorm_backward_vs_torch_autograd(agb, rows, H, with_res):
+    torch.manual_seed(3)
+    x = (torch.randn(rows, H, device=DEV) * 2 + 0.5).requires_grad_(True)
+    gamma = (1 + 0.2 * torch.randn(H, device=DEV)).requires_grad_(True)
+    beta = (0.1 * torch.randn(H, device=DEV)).requires_grad_(True)
+    dy = torch.randn(rows, H, device=DEV)
+    dres = torch.randn(rows, H, device=DEV) if with_res else None
+    eps = 1e-12
+    y = torch.nn.functional.layer_norm(x, (H,), gamma, beta, eps)
+    y.backward(dy)
+    dg, db = torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)
+    dx = agb.layernorm_bwd(x.detach(), dy, gamma.detach(), eps, dres, dg, db)
+    want = x.grad + (dres if with_res else 0)
+    torch.testing.assert_close(dx, want, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(dg, gamma.grad, rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(db, beta.grad, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("M,N,dt", [(6304, 768, "bf16"), (25216, 3072, "bf16"), (100, 2304, "bf16"), (999, 770, "bf16"),
+                                    (6304, 768, "f32")])
+def test_colsum_bias_gradient(agb, M, N, dt):
+    torch.manual_seed(4)
+    y = torch.randn(M, N, device=DEV)
+    y = y.bfloat16() if dt == "bf16" else y
+    out = torch.full((N,), 0.5, device=DEV)
+    agb.colsum_into(y, out)                                     # accumulates
+    torch.testing.assert_close(out, 0.5 + y.float().sum(0), rtol=1e-4, atol=1e-2)
+
+
 def test_gemm_bf16_mn_major_operands(agb):
     """dgrad / wgrad operand layouts: dX = dY @ W (W MN-major), dW = dY^T @ X (both MN-major)."""
     torch.manual_seed(1)

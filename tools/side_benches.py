@@ -1,0 +1,124 @@
+#!/usr/bin/env python
+"""Throughput of the non-headline configurations of BASELINE.json (parity-test cases, measured once for the record):
+KernelSHAP batched Gram + Cholesky solve, BERT-base T=128 masked evaluation, surrogate training.
+Test infrastructure; run under gpurun:  python tools/side_benches.py"""
+import sys
+
+import torch
+
+sys.path.insert(0, __file__.rsplit("/", 2)[0])
+from autognothi_b200 import ops  # noqa: E402
+from autognothi_b200.models import shapley as ash  # noqa: E402
+from oracle import configs as ocfg  # noqa: E402  (test infrastructure: config tables only)
+
+
+def timed(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def kernelshap():
+    dev = torch.device("cuda:0")
+    for d, S, C, B in ((128, 2048, 2, 256), (197, 2048, 10, 128), (512, 2048, 2, 32)):
+        n = d
+        dense = (torch.rand(B * S, n - 1, device=dev) > 0.5).to(torch.int64)
+        Zp = ops.pack_masks(dense, prepend_cls=True).reshape(B, S, -1)
+        w = torch.rand(B, S, device=dev) + 0.1
+        probs = torch.rand(B, S, C, device=dev) * 0.9 + 0.05
+        fx = torch.rand(B, C, device=dev) * 0.9 + 0.05
+        fnull = torch.rand(C, device=dev) * 0.9 + 0.05
+        ms = timed(lambda: ops.kernelshap_solve(Zp, w, probs, fx, fnull, d))
+        bytes_s = S * Zp.shape[2] * 4 + S * C * 8 + S * 8 + (d - 1) * (d - 1) * 8
+        flops = 2.0 * S * (d - 1) ** 2 + (d - 1) ** 3 / 3.0
+        print(f"kernelshap d={d} S={S} C={C} B={B}: {ms:8.3f} ms  {B / ms * 1e3:10.0f} solves/s  "
+              f"{B * bytes_s / ms * 1e-6:7.1f} GB/s algorithmic  {B * flops / ms * 1e-9:7.2f} TFLOP/s (fp64 CUDA cores)")
+
+
+def bert_eval():
+    from autognothi_b200.recipes.vanilla_bert import vanilla_bert_recipe
+    dev = torch.device("cuda:0")
+    rec = vanilla_bert_recipe()
+    cfgd = dict(ocfg.get_config("bert_base_128"))
+    cfg = rec.t_config(**cfgd)
+    n = rec.n_players(cfg)
+    torch.manual_seed(3407)
+    srg = rec.t_surrogate(cfg).to(dev).eval()
+    srg.agb_precision = "bf16"
+    B, S = 32, 32
+    ids = torch.randint(1000, 30000, (B, n + 1), device=dev)
+    ids[:, 0] = 101
+
+    def step():
+        pm = ash.mask_shapley_new(B * S, n, device=dev, rng="philox", seed=1, offset=0, packed=True)
+        with torch.no_grad():
+            return rec.fw_surrogate(srg, ids, pm)[0]
+
+    ms = timed(step, iters=8, warm=3)
+    T, H, I, L = n + 1, cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers
+    fl = L * (2 * T * H * 3 * H + 2 * T * H * H + 4 * T * H * I + 4 * T * T * H) + 2 * H * H
+    print(f"bert_base T={T}: {B * S} masked evals in {ms:7.2f} ms  {B * S / ms * 1e3:9.0f} evals/s  "
+          f"{B * S * fl / ms * 1e-9:7.1f} TFLOP/s ({fl * 1e-9:.2f} GFLOP/eval)")
+
+
+def surrogate_training():
+    import bench
+    from autognothi_b200.recipes.vanilla_vit import vanilla_vit_recipe
+    dev = torch.device("cuda:0")
+    rec = vanilla_vit_recipe()
+    cfgd = dict(bench.VIT_BASE)
+    cfg = rec.t_config(**cfgd)
+    n = rec.n_players(cfg)
+    torch.manual_seed(3407)
+    cls = rec.t_classifier(cfg).to(dev).eval()
+    srg = rec.t_surrogate(cfg).to(dev).train()
+    cls.agb_precision = srg.agb_precision = "bf16"
+    opt = torch.optim.AdamW(srg.parameters(), lr=1e-5, fused=True)
+    B = 128
+    xs = torch.randn(B, 3, 224, 224, device=dev)
+    ones = ash.PackedMasks.ones(B, n, dev)
+    state = {"i": 0}
+
+    def step():
+        masks = ash.mask_purely_uniform(B, n, device=dev, rng="philox", seed=3, offset=state["i"] * B, packed=True)
+        state["i"] += 1
+        with torch.no_grad():
+            _, orig = rec.fw_classifier(cls, xs, ones)
+        opt.zero_grad(set_to_none=True)
+        adapt, _ = rec.fw_surrogate(srg, xs, masks)
+        loss = ash.loss_logits_kl_divergence(orig, adapt)
+        loss.backward()
+        opt.step()
+        return loss
+
+    ms = timed(step, iters=5, warm=2)
+    if "profile" in sys.argv:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+        rows = [(k.key, k.device_time_total / 3e3, k.count // 3) for k in prof.key_averages() if k.device_time_total > 0]
+        rows.sort(key=lambda r: -r[1])
+        for k, t, c in rows[:28]:
+            print(f"  {t:8.3f} ms  x{c:<4d} {k[:120]}")
+    fl = 4 * bench.flops_per_eval(cfgd)     # teacher forward + student forward + backward (2x)
+    print(f"surrogate training ViT-B/16: {B} samples in {ms:7.2f} ms  {B / ms * 1e3:8.0f} samples/s  "
+          f"{B * fl / ms * 1e-9:7.1f} TFLOP/s (4 x 35.1 GFLOP per sample)")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["kernelshap", "bert", "surrogate"]
+    if "kernelshap" in which:
+        kernelshap()
+    if "bert" in which:
+        bert_eval()
+    if "surrogate" in which:
+        surrogate_training()
