@@ -12,6 +12,9 @@ int gemm_bf16_tc(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b
                  int out_f32, cudaStream_t stream);
 int rank_masks(const float* scores, int use_philox, uint64_t seed, uint64_t offset, int rows, int n, const int* stops,
                int nstops, int mask_base, uint32_t* packed, int words, int64_t* dense, cudaStream_t st);
+int cls_attention(const void* q, long long ldq, const void* kv, long long ldkv, int k_off, int v_off, int io_bf16,
+                  const uint32_t* mask, int words, int rows, int T, int H, int heads, int mode, void* ctx, long long ldc,
+                  cudaStream_t st);
 void set_attention_variant(int v);
 void set_attention_bwd_variant(int v);
 int get_attention_bwd_variant();
@@ -107,6 +110,13 @@ int agb_rank_masks(const float* scores, int use_philox, uint64_t seed, uint64_t 
                    void* stream) {
   return agb::rank_masks(scores, use_philox, seed, offset, rows, n_players, stops, nstops, mask_base, packed, words, dense,
                          ST(stream));
+}
+
+int agb_cls_attention(const void* q, long long ldq, const void* kv, long long ldkv, int k_off, int v_off, int io_is_bf16,
+                      const uint32_t* mask, int words, int rows, int T, int H, int heads, int mode, void* ctx,
+                      long long ldc, void* stream) {
+  return agb::cls_attention(q, ldq, kv, ldkv, k_off, v_off, io_is_bf16, mask, words, rows, T, H, heads, mode, ctx, ldc,
+                            ST(stream));
 }
 
 int agb_attention_set_variant(int variant) {

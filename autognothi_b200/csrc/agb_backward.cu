@@ -298,27 +298,28 @@ int layernorm_bwd(const void* x, int x_bf16, const void* dy, int dy_bf16, const 
   AGB_REQUIRE(x && dy && gamma && dx, "null pointer");
   const int blocks = min((rows + 7) / 8, 4 * sm_count());
   const size_t smem = 2 * (size_t)H * sizeof(float);
-  if (!x_bf16 && !dy_bf16 && (H % 128) == 0 && H <= 1024 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
-      (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0 &&
-      (dres == nullptr || (reinterpret_cast<uintptr_t>(dres) & 15) == 0)) {
+  const int nv4 = H / 128;
+  const bool reg_ok = !x_bf16 && !dy_bf16 && (H % 128) == 0 && (nv4 <= 4 || nv4 == 6 || nv4 == 8) &&
+                      (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(dx) & 15) == 0 &&
+                      (dres == nullptr || (reinterpret_cast<uintptr_t>(dres) & 15) == 0);
+  if (reg_ok) {
     const int rb = min((rows + 7) / 8, 2 * sm_count());
 #define LNR(NV4)                                                                                              \
   layernorm_bwd_reg_kernel<NV4><<<rb, 256, smem, st>>>(static_cast<const float*>(x), static_cast<const float*>(dy), \
                                                        gamma, dres, rows, H, eps, dx, dgamma, dbeta)
-    switch (H / 128) {
+    switch (nv4) {
       case 1: LNR(1); break;
       case 2: LNR(2); break;
       case 3: LNR(3); break;
       case 4: LNR(4); break;
       case 6: LNR(6); break;
-      case 8: LNR(8); break;
-      default: goto generic;
+      default: LNR(8); break;
     }
 #undef LNR
     AGB_CHECK_CUDA(cudaGetLastError());
     return AGB_OK;
   }
-generic:
 #define LNB(TX, TDY)                                                                                   \
   layernorm_bwd_kernel<TX, TDY><<<blocks, 256, smem, st>>>(static_cast<const TX*>(x), static_cast<const TDY*>(dy), \
                                                            gamma, dres, rows, H, eps, dx, dgamma, dbeta)

@@ -155,6 +155,171 @@ __global__ void attention_simt_kernel(const TIO* __restrict__ qkv, const uint32_
     if (lane + 32 * i < d) stf<TIO>(op + lane + 32 * i, o[i]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// CLS-query attention for the LAST encoder block of a surrogate / classifier: the head reads only token 0
+// (reference models/vanilla_vit.py:51-56 `[:, 0, :]`, models/vanilla_bert.py:615-619 pooler), so in the last block
+// only the CLS query row is needed — its keys / values still come from every token.  Exact work-skipping.
+//   q  : (rows, ldq)       the CLS query of each row, heads along the columns
+//   kv : (rows * T, ldkv)  per-token keys at column k_off + head*d and values at v_off + head*d
+// Same arithmetic (order of operations) as attention_simt_kernel for query 0.  One warp per (row, head).
+// ------------------------------------------------------------------------------------------------
+template <typename TIO, int MAXD32>
+__global__ void cls_attention_kernel(const TIO* __restrict__ q, long long ldq, const TIO* __restrict__ kv, long long ldkv,
+                                     int k_off, int v_off, const uint32_t* __restrict__ mask, int words, int T, int H,
+                                     int heads, int mode, TIO* __restrict__ ctx, long long ldc) {
+  extern __shared__ float sc_all[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int d = H / heads;
+  const int row = blockIdx.y, head = blockIdx.x * nw + warp;
+  if (head >= heads) return;
+  float* sc = sc_all + warp * T;
+  const TIO* qp = q + (long long)row * ldq + head * d;
+  const TIO* kvr = kv + (long long)row * T * ldkv;
+  const uint32_t* mrow = mask + (long long)row * words;
+  float qreg[MAXD32];
+#pragma unroll
+  for (int i = 0; i < MAXD32; ++i) qreg[i] = (lane + 32 * i < d) ? ldf<TIO>(qp + lane + 32 * i) : 0.f;
+  float mx = -INFINITY;
+  for (int j = 0; j < T; ++j) {
+    const TIO* kp = kvr + (long long)j * ldkv + k_off + head * d;
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXD32; ++i)
+      if (lane + 32 * i < d) a = fmaf(qreg[i], ldf<TIO>(kp + lane + 32 * i), a);
+    a = warp_sum(a);
+    float s = a / sqrtf((float)d);
+    const uint32_t keep = (mrow[j >> 5] >> (j & 31)) & 1u;
+    if (mode == AGB_MASK_MUL0) s = keep ? s : 0.f;
+    else s = keep ? s : s + (-3.402823466e+38f);
+    if (lane == 0) sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  __syncwarp();
+  float z = 0.f;
+  for (int j = lane; j < T; j += 32) {
+    const float e = expf(sc[j] - mx);
+    sc[j] = e;
+    z += e;
+  }
+  z = warp_sum(z);
+  __syncwarp();
+  float o[MAXD32];
+#pragma unroll
+  for (int i = 0; i < MAXD32; ++i) o[i] = 0.f;
+  for (int j = 0; j < T; ++j) {
+    const float pj = sc[j] / z;
+    const TIO* vp = kvr + (long long)j * ldkv + v_off + head * d;
+#pragma unroll
+    for (int i = 0; i < MAXD32; ++i)
+      if (lane + 32 * i < d) o[i] = fmaf(pj, ldf<TIO>(vp + lane + 32 * i), o[i]);
+  }
+  TIO* op = ctx + (long long)row * ldc + head * d;
+#pragma unroll
+  for (int i = 0; i < MAXD32; ++i)
+    if (lane + 32 * i < d) stf<TIO>(op + lane + 32 * i, o[i]);
+}
+
+// bf16, head dim 64 fast path: lane = key for the logits (each lane reads whole 128-byte K rows with 16-byte loads, all
+// independent -> memory-level parallelism), lane = 2 output dims for P V (coalesced 128-byte V rows).  fp32 math.
+__global__ void __launch_bounds__(128)
+cls_attention_d64_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restrict__ kv, long long ldkv, int k_off,
+                         int v_off, const uint32_t* __restrict__ mask, int words, int T, int heads, int mode,
+                         bf16* __restrict__ ctx, long long ldc) {
+  extern __shared__ float sc_all[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int row = blockIdx.y, head = blockIdx.x * nw + warp;
+  if (head >= heads) return;
+  float* sq = sc_all + warp * (64 + ((T + 3) & ~3));   // [64] the query (16-byte aligned), then [T] probabilities
+  float* sc = sq + 64;
+  const bf16* qp = q + (long long)row * ldq + head * 64;
+  const bf16* kvr = kv + (long long)row * T * ldkv;
+  const uint32_t* mrow = mask + (long long)row * words;
+  {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(qp + 2 * lane);
+    sq[2 * lane] = bf16_lo(w);
+    sq[2 * lane + 1] = bf16_hi(w);
+  }
+  __syncwarp();
+  float mx = -INFINITY;
+  for (int j = lane; j < T; j += 32) {
+    const uint4* kp = reinterpret_cast<const uint4*>(kvr + (long long)j * ldkv + k_off + head * 64);
+    uint4 kk[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) kk[c] = __ldg(kp + c);
+    float a = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float4 q0 = *reinterpret_cast<const float4*>(sq + 8 * c);
+      const float4 q1 = *reinterpret_cast<const float4*>(sq + 8 * c + 4);
+      a = fmaf(q0.x, bf16_lo(kk[c].x), a); a = fmaf(q0.y, bf16_hi(kk[c].x), a);
+      a = fmaf(q0.z, bf16_lo(kk[c].y), a); a = fmaf(q0.w, bf16_hi(kk[c].y), a);
+      a = fmaf(q1.x, bf16_lo(kk[c].z), a); a = fmaf(q1.y, bf16_hi(kk[c].z), a);
+      a = fmaf(q1.z, bf16_lo(kk[c].w), a); a = fmaf(q1.w, bf16_hi(kk[c].w), a);
+    }
+    float sv = a * 0.125f;
+    const uint32_t keep = (__ldg(mrow + (j >> 5)) >> (j & 31)) & 1u;
+    if (mode == AGB_MASK_MUL0) sv = keep ? sv : 0.f;
+    else sv = keep ? sv : -INFINITY;
+    sc[j] = sv;
+    mx = fmaxf(mx, sv);
+  }
+  mx = warp_max(mx);
+  float z = 0.f;
+  for (int j = lane; j < T; j += 32) {
+    const float e = __expf(sc[j] - mx);
+    sc[j] = e;
+    z += e;
+  }
+  z = warp_sum(z);
+  __syncwarp();
+  const float inv = 1.0f / z;
+  float o0 = 0.f, o1 = 0.f;
+  const bf16* vp = kvr + v_off + head * 64 + 2 * lane;
+#pragma unroll 4
+  for (int j = 0; j < T; ++j) {
+    const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(vp + (long long)j * ldkv));
+    const float pj = sc[j];
+    o0 = fmaf(pj, bf16_lo(w), o0);
+    o1 = fmaf(pj, bf16_hi(w), o1);
+  }
+  *reinterpret_cast<uint32_t*>(ctx + (long long)row * ldc + head * 64 + 2 * lane) = pack_bf16x2(o0 * inv, o1 * inv);
+}
+
+int cls_attention(const void* q, long long ldq, const void* kv, long long ldkv, int k_off, int v_off, int io_bf16,
+                  const uint32_t* mask, int words, int rows, int T, int H, int heads, int mode, void* ctx, long long ldc,
+                  cudaStream_t st) {
+  AGB_REQUIRE(rows >= 0 && T > 0 && heads > 0 && H % heads == 0, "attention shape");
+  AGB_REQUIRE(words * 32 >= T, "mask words");
+  AGB_REQUIRE(mode == AGB_MASK_MUL0 || mode == AGB_MASK_NEGINF, "mask mode");
+  AGB_REQUIRE(H / heads <= 128, "head dim <= 128");
+  if (rows == 0) return AGB_OK;
+  AGB_REQUIRE(q && kv && mask && ctx, "null pointer");
+  AGB_REQUIRE(rows <= 65535, "grid limits (chunk the rows)");
+  const int nw = 4;
+  dim3 grid((heads + nw - 1) / nw, rows);
+  if (io_bf16 && H == heads * 64 && (ldq % 2) == 0 && (ldkv % 8) == 0 && (k_off % 8) == 0 && (v_off % 8) == 0 &&
+      (ldc % 2) == 0 && (reinterpret_cast<uintptr_t>(q) & 3) == 0 && (reinterpret_cast<uintptr_t>(kv) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(ctx) & 3) == 0) {
+    const size_t smem64 = (size_t)nw * (64 + ((T + 3) & ~3)) * sizeof(float);
+    cls_attention_d64_kernel<<<grid, nw * 32, smem64, st>>>(static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(kv), ldkv,
+                                                            k_off, v_off, mask, words, T, heads, mode,
+                                                            static_cast<bf16*>(ctx), ldc);
+    AGB_CHECK_CUDA(cudaGetLastError());
+    return AGB_OK;
+  }
+  const size_t smem = (size_t)nw * T * sizeof(float);
+  if (io_bf16)
+    cls_attention_kernel<bf16, 4><<<grid, nw * 32, smem, st>>>(static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(kv),
+                                                              ldkv, k_off, v_off, mask, words, T, H, heads, mode,
+                                                              static_cast<bf16*>(ctx), ldc);
+  else
+    cls_attention_kernel<float, 4><<<grid, nw * 32, smem, st>>>(static_cast<const float*>(q), ldq,
+                                                               static_cast<const float*>(kv), ldkv, k_off, v_off, mask, words,
+                                                               T, H, heads, mode, static_cast<float*>(ctx), ldc);
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
 int attention_simt(const void* qkv, int io_bf16, const uint32_t* mask, int words, int rows, int T, int H,
                    int heads, int mode, void* ctx, cudaStream_t st) {
   AGB_REQUIRE(rows >= 0 && T > 0 && heads > 0 && H % heads == 0, "attention shape");

@@ -194,8 +194,55 @@ def bert_layer(pol: _Policy, lw: LayerWeights, x: Tensor, xa: Tensor, masks: Ten
     return y, ya
 
 
-def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tensor, S: int) -> Tuple[Tensor, Optional[Tensor]]:
-    """-> (x (rows*T, H) fp32 after the encoder stack [ViT: BEFORE the final LayerNorm], activation copy | None)"""
+# Exact work-skipping for surrogate / classifier evaluation: the heads read only token 0 of the last hidden state
+# (reference models/vanilla_vit.py:51-56, models/vanilla_bert.py:615-619), so the LAST block needs keys / values for
+# every token but the query, the attention output, the output projection and the whole MLP only for the CLS row.
+# (The explainer reads all tokens and never takes this path.)  Off = every block runs on all T tokens.
+CLS_ONLY_LAST_BLOCK = True
+
+
+def last_block_cls_only(pol: _Policy, lw: LayerWeights, vit: bool, x: Tensor, xa: Optional[Tensor], x16: Optional[Tensor],
+                        stats: Optional[Tensor], masks: Tensor, T: int, heads: int, eps: float) -> Tuple[Tensor, Optional[Tensor]]:
+    """Last encoder block restricted to the CLS query.  x (rows*T, H) fp32 residual stream; ViT fused path passes
+    (x16, stats) for the folded LayerNorm, otherwise they are None; BERT passes xa (activation-dtype copy of x).
+    -> (x_cls (rows, H) fp32 after the block, activation copy | None)"""
+    rows, H = masks.shape[0], x.shape[1]
+    x_cls = x.view(rows, T, H)[:, 0, :].contiguous()
+    wq, wkv, bq, bkv = lw.wqkv[:H], lw.wqkv[H:], lw.bqkv[:H], lw.bqkv[H:]
+    if vit:
+        if x16 is not None:
+            f = lw.fold()
+            kv = ops.gemm_bf16_fused(x16, f["wqkv"][H:], f["bqkv"][H:], ln=(stats, f["cqkv"][H:], eps))[0]
+            x16_cls = x16.view(rows, T, H)[:, 0, :].contiguous()
+            st_cls = stats.view(rows, T, stats.shape[1], 2)[:, 0].contiguous()
+            q = ops.gemm_bf16_fused(x16_cls, f["wqkv"][:H], f["bqkv"][:H], ln=(st_cls, f["cqkv"][:H], eps))[0]
+        else:
+            h = pol.ln(x, lw.ln1[0], lw.ln1[1], eps)[0] if lw.ln1 is not None else pol.act(x)
+            kv = pol.linear(h, wkv, bkv)
+            q = pol.linear(h.view(rows, T, H)[:, 0, :].contiguous(), wq, bq)
+        ctx = ops.cls_attention(q, kv, 0, H, masks, T, heads, ops.MASK_MUL0)
+        y = pol.linear(ctx, lw.wo, lw.bo, residual=x_cls, out_f32=True)
+        h2 = pol.ln(y, lw.ln2[0], lw.ln2[1], eps)[0]
+        ff = pol.linear(h2, lw.w1, lw.b1, act=ops.ACT_GELU)
+        return pol.linear(ff, lw.w2, lw.b2, residual=y, out_f32=True), None
+    kv = pol.linear(xa, wkv, bkv)
+    q = pol.linear(xa.view(rows, T, H)[:, 0, :].contiguous(), wq, bq)
+    ctx = ops.cls_attention(q, kv, 0, H, masks, T, heads, ops.MASK_NEGINF)
+    a = pol.linear(ctx, lw.wo, lw.bo, residual=x_cls, out_f32=True)
+    if lw.ln1 is not None:
+        aa, a = pol.ln(a, lw.ln1[0], lw.ln1[1], eps, want_f32=True)
+    else:
+        aa = pol.act(a)
+    ff = pol.linear(aa, lw.w1, lw.b1, act=ops.ACT_GELU)
+    y = pol.linear(ff, lw.w2, lw.b2, residual=a, out_f32=True)
+    ya, y = pol.ln(y, lw.ln2[0], lw.ln2[1], eps, want_f32=True)
+    return y, ya
+
+
+def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tensor, S: int, cls_only: bool = False
+                 ) -> Tuple[Tensor, Optional[Tensor]]:
+    """-> (x (rows*T, H) fp32 after the encoder stack [ViT: BEFORE the final LayerNorm], activation copy | None).
+    cls_only (surrogate / classifier heads): the last block runs for the CLS query only and x is (rows, H)."""
     T = n_players_of(cfg) + 1
     H, heads, eps = cfg.hidden_size, cfg.num_attention_heads, cfg.layer_norm_eps
     x3 = embed(bw, cfg, pol, xs, S)
@@ -203,19 +250,28 @@ def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tens
     rows = x3.shape[0]
     assert masks.shape[0] == rows, f"need one packed mask row per (input, coalition): {masks.shape[0]} vs {rows}"
     x = x3.reshape(rows * T, H)
+    cls_only = cls_only and CLS_ONLY_LAST_BLOCK and len(bw.layers) > 0
+    full = bw.layers[:-1] if cls_only else bw.layers
     if bw.vit:
         fused = FUSE_LAYERNORM and pol.bf16 and H % 256 == 0 and all(lw.fold() is not None for lw in bw.layers)
         if fused:
             x16, stats = ops.rowstats_cast(x)
-            for i, lw in enumerate(bw.layers):
-                x, x16, stats = vit_layer_fused(lw, x, x16, stats, masks, T, heads, eps, last=(i == len(bw.layers) - 1))
+            for i, lw in enumerate(full):
+                x, x16, stats = vit_layer_fused(lw, x, x16, stats, masks, T, heads, eps,
+                                                last=(not cls_only and i == len(full) - 1))
+            if cls_only:
+                return last_block_cls_only(pol, bw.layers[-1], True, x, None, x16, stats, masks, T, heads, eps)
             return x, None
-        for lw in bw.layers:
+        for lw in full:
             x = vit_layer(pol, lw, x, masks, T, heads, eps)
+        if cls_only:
+            return last_block_cls_only(pol, bw.layers[-1], True, x, None, None, None, masks, T, heads, eps)
         return x, None
     xa = pol.act(x)
-    for lw in bw.layers:
+    for lw in full:
         x, xa = bert_layer(pol, lw, x, xa, masks, T, heads, eps)
+    if cls_only:
+        return last_block_cls_only(pol, bw.layers[-1], False, x, xa, None, None, masks, T, heads, eps)
     return x, xa
 
 
@@ -241,8 +297,8 @@ class SurrogateEngine:
         outs: List[Tensor] = []
         for b0 in range(0, B, per):
             b1 = min(B, b0 + per)
-            x, _ = run_backbone(self.bw, cfg, self.pol, xs[b0:b1], masks[b0 * S:b1 * S], S)
-            x3 = x.reshape((b1 - b0) * S, T, cfg.hidden_size)
+            x, _ = run_backbone(self.bw, cfg, self.pol, xs[b0:b1], masks[b0 * S:b1 * S], S, cls_only=True)
+            x3 = x.reshape((b1 - b0) * S, -1, cfg.hidden_size)       # (rows, 1, H) with the CLS-only last block, else (rows, T, H)
             if self.bw.vit:
                 outs.append(ops.cls_head(x3, 0, self.w_cls, self.b_cls, ln=(self.bw.final_ln[0], self.bw.final_ln[1], cfg.layer_norm_eps)))
             else:

@@ -287,6 +287,22 @@ def masked_attention(qkv: Tensor, packed_mask: Tensor, T: int, heads: int, mode:
     return ctx
 
 
+def cls_attention(q: Tensor, kv: Tensor, k_off: int, v_off: int, packed_mask: Tensor, T: int, heads: int, mode: int) -> Tensor:
+    """CLS-query attention of the last block: q (rows, H), kv (rows*T, ld) with keys at columns [k_off, k_off+H) and
+    values at [v_off, v_off+H) -> ctx (rows, H), same dtype (fp32 math)."""
+    assert q.dim() == 2 and kv.dim() == 2 and q.dtype == kv.dtype and q.stride(1) == 1 and kv.stride(1) == 1
+    rows, H = q.shape
+    assert kv.shape[0] == rows * T and packed_mask.shape[0] == rows and packed_mask.dtype == torch.int32
+    ctx = torch.empty((rows, H), dtype=q.dtype, device=q.device)
+    step = 65535
+    for r0 in range(0, rows, step):
+        r1 = min(rows, r0 + step)
+        nat.call("agb_cls_attention", nat.ptr(q[r0:r1]), q.stride(0), nat.ptr(kv[r0 * T:r1 * T]), kv.stride(0), k_off, v_off,
+                 _is_bf16(q), nat.ptr(_c(packed_mask[r0:r1])), packed_mask.shape[1], r1 - r0, T, H, heads, mode,
+                 nat.ptr(ctx[r0:r1]), H, nat.stream())
+    return ctx
+
+
 # ------------------------------------------------------------------------------------------------
 # explainer head / loss
 # ------------------------------------------------------------------------------------------------

@@ -147,6 +147,14 @@ int agb_masked_attention_simt(const void* qkv, int io_is_bf16, const uint32_t* m
 int agb_masked_attention_bf16(const void* qkv, const uint32_t* mask, int words, int rows, int T,
                               int H, int heads, int mode, void* ctx, void* stream);
 
+/* CLS-query attention for the LAST encoder block of a surrogate / classifier (exact work-skipping: the heads read only
+ * token 0 — reference models/vanilla_vit.py:51-56, models/vanilla_bert.py:615-619 — so only the CLS query row of the last
+ * block is needed; keys / values still come from all T tokens).  q (rows, ldq); kv (rows*T, ldkv) with keys at column
+ * k_off + head*d and values at v_off + head*d; ctx (rows, ldc).  fp32 math, fp32 or bf16 I/O, same mask semantics. */
+int agb_cls_attention(const void* q, long long ldq, const void* kv, long long ldkv, int k_off, int v_off, int io_is_bf16,
+                      const uint32_t* mask, int words, int rows, int T, int H, int heads, int mode, void* ctx,
+                      long long ldc, void* stream);
+
 /* Kernel selection for agb_masked_attention_bf16 (diagnostics): 0 = automatic (pipelined, one CTA per SM),
  * 1 = first-generation kernel.  Returns the previous setting. */
 int agb_attention_set_variant(int variant);

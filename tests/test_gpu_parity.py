@@ -436,6 +436,33 @@ def test_full_path_bf16_tensor_cores_vs_reference_golden(agb, golden_dir, name):
     assert l2 <= 1e-2, f"relative L2 {l2}"
 
 
+@pytest.mark.parametrize("name,precision", [("vit_mini", "fp32"), ("bert_mini", "fp32"), ("vit_tiny", "fp32"),
+                                            ("vit_base", "bf16"), ("bert_base_128", "bf16"), ("vit_tiny", "bf16")])
+def test_cls_only_last_block_is_exact_work_skipping(agb, golden_dir, name, precision):
+    """Surrogate heads read only token 0, so the last block may run for the CLS query alone: same probabilities as
+    running every block on all T tokens (fp32: same arithmetic for that row; bf16: the CLS row's attention is
+    computed in fp32 instead of on the tensor cores, hence a small tolerance)."""
+    from autognothi_b200 import engine
+    g = _load(golden_dir, f"model_{name}.npz")
+    B, S, n = (int(v) for v in g["meta"])
+    rec, cfgd, srg, exp = _build(name, precision)
+    xs = torch.from_numpy(synth.inputs(cfgd, B, seed=0)).to(DEV)
+    masks = torch.from_numpy(g["masks"].astype(np.int64)).to(DEV).reshape(B, S, n)
+    try:
+        with torch.no_grad():
+            engine.CLS_ONLY_LAST_BLOCK = True
+            p_skip, _ = rec.fw_surrogate(srg, xs, masks)
+            engine.CLS_ONLY_LAST_BLOCK = False
+            p_full, _ = rec.fw_surrogate(srg, xs, masks)
+    finally:
+        engine.CLS_ONLY_LAST_BLOCK = True
+    if precision == "fp32":
+        np.testing.assert_allclose(_np(p_skip), _np(p_full), rtol=1e-5, atol=1e-7)
+    else:
+        np.testing.assert_allclose(_np(p_skip), _np(p_full), atol=3e-3)
+    np.testing.assert_allclose(_np(p_skip), g["v_s"], **({"rtol": 1e-4, "atol": 2e-6} if precision == "fp32" else {"atol": 2e-2}))
+
+
 def test_final_coherency(agb):
     """The reference's only numerical self-check (scripts/train_all.py:166-218): the bundled Final model
     agrees with the separate classifier / surrogate / explainer on the same input."""
