@@ -68,7 +68,7 @@ int cls_head(const float* x, long long row_stride, int rows, int H, int C, int m
              const float* bc, float* probs, float* logits_out, cudaStream_t st);
 int attention_simt(const void* qkv, int io_bf16, const uint32_t* mask, int words, int rows, int T, int H,
                    int heads, int mode, void* ctx, cudaStream_t st);
-int attention_tc(const bf16* qkv, const uint32_t* mask, int words, int rows, int T, int H, int heads,
+int attention_tc(const bf16* qkv, const uint32_t* mask, int words, int rows, int share, int T, int H, int heads,
                  int mode, bf16* ctx, cudaStream_t st);
 int explainer_head_fwd(const void* h, int h_bf16, int B, int T, int E, int C, const float* W,
                        const float* bias, const float* grand, const float* null_v, int normalize,
@@ -254,7 +254,12 @@ int agb_masked_attention_simt(const void* qkv, int io_is_bf16, const uint32_t* m
 }
 int agb_masked_attention_bf16(const void* qkv, const uint32_t* mask, int words, int rows, int T,
                               int H, int heads, int mode, void* ctx, void* stream) {
-  return agb::attention_tc(static_cast<const bf16*>(qkv), mask, words, rows, T, H, heads, mode,
+  return agb::attention_tc(static_cast<const bf16*>(qkv), mask, words, rows, 1, T, H, heads, mode,
+                           static_cast<bf16*>(ctx), ST(stream));
+}
+int agb_masked_attention_bf16_shared(const void* qkv, const uint32_t* mask, int words, int rows, int share, int T,
+                                     int H, int heads, int mode, void* ctx, void* stream) {
+  return agb::attention_tc(static_cast<const bf16*>(qkv), mask, words, rows, share, T, H, heads, mode,
                            static_cast<bf16*>(ctx), ST(stream));
 }
 int agb_explainer_head_fwd(const void* h, int h_is_bf16, int B, int T, int E, int C, const float* W,

@@ -34,6 +34,7 @@ struct AttPipeParams {
   int NK;            // keys padded to a multiple of 16
   int units;         // rows * heads
   int mtiles;        // ceil(T / 128)
+  int share;         // consecutive mask rows that read the SAME qkv row (first block: one projection per input)
   bf16* ctx;
   long long* trace;  // optional [items][8] clock64 timestamps of CTA 0 (diagnostics), or nullptr
 };
@@ -184,15 +185,15 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const uint32_t bar = smem_u32(&kv_full[b]);
         mbar_arrive_expect_tx_e(e, bar, 2 * kvb);
         const uint32_t dst = smem_u32(sKV + b * 2 * kvb);
-        tma_load_3d_e(e, dst, &tmKV, bar, H + head * AP_D, 0, row);
-        tma_load_3d_e(e, dst + kvb, &tmKV, bar, 2 * H + head * AP_D, 0, row);
+        tma_load_3d_e(e, dst, &tmKV, bar, H + head * AP_D, 0, row / p.share);
+        tma_load_3d_e(e, dst + kvb, &tmKV, bar, 2 * H + head * AP_D, 0, row / p.share);
         AP_TRACE(k, 0);
       }
       const int qb = k & 1, nq = k >> 1;
       if (nq > 0) mbar_wait(smem_u32(&q_empty[qb]), (nq - 1) & 1);
       const uint32_t qbar = smem_u32(&q_full[qb]);
       mbar_arrive_expect_tx_e(e, qbar, 16384);
-      tma_load_3d_e(e, smem_u32(sQ + qb * 16384), &tmQ, qbar, head * AP_D, m * 128, row);
+      tma_load_3d_e(e, smem_u32(sQ + qb * 16384), &tmQ, qbar, head * AP_D, m * 128, row / p.share);
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
@@ -365,21 +366,23 @@ static int g_attention_variant = 0;   // 0 auto (pipelined), 1 first-generation 
 void set_attention_variant(int v) { g_attention_variant = v; }
 int get_attention_variant() { return g_attention_variant; }
 
-int attention_pipe(const bf16* qkv, const uint32_t* mask, int words, int rows, int T, int H, int heads, int mode,
-                   bf16* ctx, cudaStream_t stream) {
+int attention_pipe(const bf16* qkv, const uint32_t* mask, int words, int rows, int share, int T, int H, int heads,
+                   int mode, bf16* ctx, cudaStream_t stream) {
   if (g_attention_variant == 1) return AGB_ERR_UNSUPPORTED;
+  const int qrows = rows / share;
   AttPipeParams p;
   p.mask = mask; p.words = words; p.rows = rows; p.T = T; p.H = H; p.heads = heads; p.mode = mode;
   p.NK = (T + 15) / 16 * 16;
   p.units = rows * heads;
   p.mtiles = (T + 127) / 128;
+  p.share = share;
   p.ctx = ctx;
   p.trace = g_attention_trace;
   CUtensorMap tmQ, tmKV;
-  int rc = encode_tmap_3d_bf16(&tmQ, qkv, 3 * (uint64_t)H, T, rows, (uint64_t)3 * H * 2, (uint64_t)T * 3 * H * 2,
+  int rc = encode_tmap_3d_bf16(&tmQ, qkv, 3 * (uint64_t)H, T, qrows, (uint64_t)3 * H * 2, (uint64_t)T * 3 * H * 2,
                                AP_D, 128, 1);
   if (rc != AGB_OK) return rc;
-  rc = encode_tmap_3d_bf16(&tmKV, qkv, 3 * (uint64_t)H, T, rows, (uint64_t)3 * H * 2, (uint64_t)T * 3 * H * 2,
+  rc = encode_tmap_3d_bf16(&tmKV, qkv, 3 * (uint64_t)H, T, qrows, (uint64_t)3 * H * 2, (uint64_t)T * 3 * H * 2,
                            AP_D, p.NK, 1);
   if (rc != AGB_OK) return rc;
   const int smem = 1024 + 2 * 16384 + AP_KV_RING * 2 * p.NK * 128 + 256;

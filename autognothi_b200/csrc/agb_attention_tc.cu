@@ -247,11 +247,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, ATT_TMEM_COLS);
 }
 
-int attention_pipe(const bf16* qkv, const uint32_t* mask, int words, int rows, int T, int H, int heads, int mode,
-                   bf16* ctx, cudaStream_t stream);
+int attention_pipe(const bf16* qkv, const uint32_t* mask, int words, int rows, int share, int T, int H, int heads,
+                   int mode, bf16* ctx, cudaStream_t stream);
 
-int attention_tc(const bf16* qkv, const uint32_t* mask, int words, int rows, int T, int H, int heads,
+int attention_tc(const bf16* qkv, const uint32_t* mask, int words, int rows, int share, int T, int H, int heads,
                  int mode, bf16* ctx, cudaStream_t stream) {
+  AGB_REQUIRE(share >= 1 && rows % share == 0, "share must divide the number of mask rows");
   AGB_REQUIRE(rows >= 0 && T > 0 && heads > 0 && H == heads * ATT_D, "tensor-core attention needs head dim 64");
   AGB_REQUIRE(words * 32 >= T, "mask words");
   AGB_REQUIRE(mode == AGB_MASK_MUL0 || mode == AGB_MASK_NEGINF, "mask mode");
@@ -263,8 +264,12 @@ int attention_tc(const bf16* qkv, const uint32_t* mask, int words, int rows, int
   AGB_REQUIRE(qkv && mask && ctx, "null pointer");
   AGB_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(ctx) & 15) == 0, "alignment");
   {  // second-generation pipelined kernel (agb_attention_pipe.cu); this file keeps the first generation
-    const int rc2 = attention_pipe(qkv, mask, words, rows, T, H, heads, mode, ctx, stream);
+    const int rc2 = attention_pipe(qkv, mask, words, rows, share, T, H, heads, mode, ctx, stream);
     if (rc2 != AGB_ERR_UNSUPPORTED) return rc2;
+  }
+  if (share != 1) {
+    set_last_error("shared-qkv attention needs the pipelined kernel (agb_attention_set_variant(0))");
+    return AGB_ERR_UNSUPPORTED;
   }
   AttParams p;
   p.mask = mask; p.words = words; p.rows = rows; p.T = T; p.H = H; p.heads = heads; p.mode = mode;

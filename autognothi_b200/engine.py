@@ -147,12 +147,14 @@ def embed(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, S: int) -> Tensor:
     return ops.bert_embed(xs, bw.word, bw.pos, bw.type0, bw.emb_ln[0], bw.emb_ln[1], cfg.layer_norm_eps, S)
 
 
-def vit_layer(pol: _Policy, lw: LayerWeights, x: Tensor, masks: Tensor, T: int, heads: int, eps: float) -> Tensor:
+def vit_layer(pol: _Policy, lw: LayerWeights, x: Tensor, masks: Tensor, T: int, heads: int, eps: float,
+              ctx: Optional[Tensor] = None) -> Tensor:
     """pre-LN block on the fp32 residual stream x (rows*T, H); updates x in place.
-    reference models/vanilla_vit.py:364-377"""
-    h = pol.ln(x, lw.ln1[0], lw.ln1[1], eps)[0] if lw.ln1 is not None else pol.act(x)
-    qkv = pol.linear(h, lw.wqkv, lw.bqkv)
-    ctx = ops.masked_attention(qkv, masks, T, heads, ops.MASK_MUL0)
+    reference models/vanilla_vit.py:364-377.  ctx: attention output computed by the caller (first-block sharing)."""
+    if ctx is None:
+        h = pol.ln(x, lw.ln1[0], lw.ln1[1], eps)[0] if lw.ln1 is not None else pol.act(x)
+        qkv = pol.linear(h, lw.wqkv, lw.bqkv)
+        ctx = ops.masked_attention(qkv, masks, T, heads, ops.MASK_MUL0)
     pol.linear(ctx, lw.wo, lw.bo, residual=x, out_f32=True, out=x)
     h = pol.ln(x, lw.ln2[0], lw.ln2[1], eps)[0]
     f = pol.linear(h, lw.w1, lw.b1, act=ops.ACT_GELU)
@@ -160,14 +162,16 @@ def vit_layer(pol: _Policy, lw: LayerWeights, x: Tensor, masks: Tensor, T: int, 
     return x
 
 
-def vit_layer_fused(lw: LayerWeights, x: Tensor, x16: Tensor, stats: Tensor, masks: Tensor, T: int, heads: int, eps: float,
-                    last: bool) -> Tuple[Tensor, Optional[Tensor], Optional[Tensor]]:
+def vit_layer_fused(lw: LayerWeights, x: Tensor, x16: Optional[Tensor], stats: Optional[Tensor], masks: Tensor, T: int,
+                    heads: int, eps: float, last: bool, ctx: Optional[Tensor] = None
+                    ) -> Tuple[Tensor, Optional[Tensor], Optional[Tensor]]:
     """Same block as vit_layer (bf16 mode) without LayerNorm kernels: x16 / stats are the bf16 copy and per-row
     (sum, sum of squares) partials of the fp32 residual stream x, produced by the previous residual GEMM's epilogue
     (or ops.rowstats_cast at the entry).  Returns (x, x16, stats) for the next block."""
     f = lw.fold()
-    qkv, _, _ = ops.gemm_bf16_fused(x16, f["wqkv"], f["bqkv"], ln=(stats, f["cqkv"], eps))
-    ctx = ops.masked_attention(qkv, masks, T, heads, ops.MASK_MUL0)
+    if ctx is None:
+        qkv, _, _ = ops.gemm_bf16_fused(x16, f["wqkv"], f["bqkv"], ln=(stats, f["cqkv"], eps))
+        ctx = ops.masked_attention(qkv, masks, T, heads, ops.MASK_MUL0)
     _, y16, ystats = ops.gemm_bf16_fused(ctx, lw.wo, lw.bo, residual=x, out=x, emit_copy_stats=True)
     h = ops.gemm_bf16_fused(y16, f["w1"], f["b1"], act=ops.ACT_GELU, ln=(ystats, f["c1"], eps))[0]
     if last:
@@ -177,12 +181,13 @@ def vit_layer_fused(lw: LayerWeights, x: Tensor, x16: Tensor, stats: Tensor, mas
     return x, x16n, statsn
 
 
-def bert_layer(pol: _Policy, lw: LayerWeights, x: Tensor, xa: Tensor, masks: Tensor, T: int, heads: int, eps: float
-               ) -> Tuple[Tensor, Tensor]:
+def bert_layer(pol: _Policy, lw: LayerWeights, x: Tensor, xa: Optional[Tensor], masks: Tensor, T: int, heads: int, eps: float,
+               ctx: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     """post-LN block; x fp32 residual stream, xa its activation-dtype copy.
-    reference models/vanilla_bert.py:396-427, 556-560, 600-604"""
-    qkv = pol.linear(xa, lw.wqkv, lw.bqkv)
-    ctx = ops.masked_attention(qkv, masks, T, heads, ops.MASK_NEGINF)
+    reference models/vanilla_bert.py:396-427, 556-560, 600-604.  ctx: attention output computed by the caller."""
+    if ctx is None:
+        qkv = pol.linear(xa, lw.wqkv, lw.bqkv)
+        ctx = ops.masked_attention(qkv, masks, T, heads, ops.MASK_NEGINF)
     a = pol.linear(ctx, lw.wo, lw.bo, residual=x, out_f32=True)
     if lw.ln1 is not None:
         aa, a = pol.ln(a, lw.ln1[0], lw.ln1[1], eps, want_f32=True)
@@ -199,6 +204,8 @@ def bert_layer(pol: _Policy, lw: LayerWeights, x: Tensor, xa: Tensor, masks: Ten
 # every token but the query, the attention output, the output projection and the whole MLP only for the CLS row.
 # (The explainer reads all tokens and never takes this path.)  Off = every block runs on all T tokens.
 CLS_ONLY_LAST_BLOCK = True
+# Exact work-skipping, first block: LayerNorm + QKV projection once per input instead of once per coalition (bf16 path).
+SHARE_FIRST_BLOCK = True
 
 
 def last_block_cls_only(pol: _Policy, lw: LayerWeights, vit: bool, x: Tensor, xa: Optional[Tensor], x16: Optional[Tensor],
@@ -245,32 +252,59 @@ def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tens
     cls_only (surrogate / classifier heads): the last block runs for the CLS query only and x is (rows, H)."""
     T = n_players_of(cfg) + 1
     H, heads, eps = cfg.hidden_size, cfg.num_attention_heads, cfg.layer_norm_eps
-    x3 = embed(bw, cfg, pol, xs, S)
+    cls_only = cls_only and CLS_ONLY_LAST_BLOCK and len(bw.layers) > 0
+    full = bw.layers[:-1] if cls_only else bw.layers
+    fused = bw.vit and FUSE_LAYERNORM and pol.bf16 and H % 256 == 0 and all(lw.fold() is not None for lw in bw.layers)
+    # First-block sharing (exact): before the first attention all S coalitions of an input hold identical activations,
+    # so that block's LayerNorm + QKV projection runs once per input and the attention kernel reads the shared rows.
+    share = (SHARE_FIRST_BLOCK and S > 1 and pol.bf16 and len(full) > 0 and T <= 256 and H == heads * 64)
+    ctx0 = None
+    if share:
+        x_img = embed(bw, cfg, pol, xs, 1)                                   # (B, T, H) fp32, one row block per input
+        assert x_img.shape[1] == T, f"sequence length {x_img.shape[1]} != n_players + 1 = {T}"
+        lw0 = full[0]
+        xi = x_img.reshape(-1, H)
+        if fused:
+            xi16, sti = ops.rowstats_cast(xi)
+            f0 = lw0.fold()
+            qkv0 = ops.gemm_bf16_fused(xi16, f0["wqkv"], f0["bqkv"], ln=(sti, f0["cqkv"], eps))[0]
+        elif bw.vit:
+            h0 = pol.ln(xi, lw0.ln1[0], lw0.ln1[1], eps)[0] if lw0.ln1 is not None else pol.act(xi)
+            qkv0 = pol.linear(h0, lw0.wqkv, lw0.bqkv)
+        else:
+            qkv0 = pol.linear(pol.act(xi), lw0.wqkv, lw0.bqkv)
+        ctx0 = ops.masked_attention(qkv0, masks, T, heads, ops.MASK_MUL0 if bw.vit else ops.MASK_NEGINF, share=S)
+        x3 = x_img.repeat_interleave(S, dim=0)                               # the residual stream of every coalition
+    else:
+        x3 = embed(bw, cfg, pol, xs, S)
     assert x3.shape[1] == T, f"sequence length {x3.shape[1]} != n_players + 1 = {T}"
     rows = x3.shape[0]
     assert masks.shape[0] == rows, f"need one packed mask row per (input, coalition): {masks.shape[0]} vs {rows}"
     x = x3.reshape(rows * T, H)
-    cls_only = cls_only and CLS_ONLY_LAST_BLOCK and len(bw.layers) > 0
-    full = bw.layers[:-1] if cls_only else bw.layers
     if bw.vit:
-        fused = FUSE_LAYERNORM and pol.bf16 and H % 256 == 0 and all(lw.fold() is not None for lw in bw.layers)
         if fused:
-            x16, stats = ops.rowstats_cast(x)
+            x16 = stats = None
+            if ctx0 is None:
+                x16, stats = ops.rowstats_cast(x)
             for i, lw in enumerate(full):
                 x, x16, stats = vit_layer_fused(lw, x, x16, stats, masks, T, heads, eps,
-                                                last=(not cls_only and i == len(full) - 1))
+                                                last=(not cls_only and i == len(full) - 1), ctx=ctx0 if i == 0 else None)
             if cls_only:
+                if x16 is None:      # single-block model: the CLS-only block is also the first one
+                    x16, stats = ops.rowstats_cast(x)
                 return last_block_cls_only(pol, bw.layers[-1], True, x, None, x16, stats, masks, T, heads, eps)
             return x, None
-        for lw in full:
-            x = vit_layer(pol, lw, x, masks, T, heads, eps)
+        for i, lw in enumerate(full):
+            x = vit_layer(pol, lw, x, masks, T, heads, eps, ctx=ctx0 if i == 0 else None)
         if cls_only:
             return last_block_cls_only(pol, bw.layers[-1], True, x, None, None, None, masks, T, heads, eps)
         return x, None
-    xa = pol.act(x)
-    for lw in full:
-        x, xa = bert_layer(pol, lw, x, xa, masks, T, heads, eps)
+    xa = pol.act(x) if ctx0 is None else None
+    for i, lw in enumerate(full):
+        x, xa = bert_layer(pol, lw, x, xa, masks, T, heads, eps, ctx=ctx0 if i == 0 else None)
     if cls_only:
+        if xa is None:
+            xa = pol.act(x)
         return last_block_cls_only(pol, bw.layers[-1], False, x, xa, None, None, masks, T, heads, eps)
     return x, xa
 

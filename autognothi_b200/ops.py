@@ -263,21 +263,29 @@ def cls_head(x: Tensor, mode: int, w_cls: Tensor, b_cls: Tensor, *, ln: Optional
     return (probs, logits) if want_logits else probs
 
 
-def masked_attention(qkv: Tensor, packed_mask: Tensor, T: int, heads: int, mode: int, *, force_simt: bool = False) -> Tensor:
+def masked_attention(qkv: Tensor, packed_mask: Tensor, T: int, heads: int, mode: int, *, force_simt: bool = False,
+                     share: int = 1) -> Tensor:
     """qkv (rows*T, 3H) fused projections -> ctx (rows*T, H), same dtype.  bf16 + head dim 64 + T <= 256 runs
-    the tcgen05 kernel; fp32 (the exact mode) and the remaining shapes run the CUDA-core kernel."""
+    the tcgen05 kernel; fp32 (the exact mode) and the remaining shapes run the CUDA-core kernel.
+    share > 1 (tcgen05 kernel only): qkv is (rows/share*T, 3H) and `share` consecutive mask rows read the same
+    projections (the coalitions of one input in the first block)."""
     assert qkv.is_contiguous() and packed_mask.is_contiguous() and packed_mask.dtype == torch.int32
-    rows = qkv.shape[0] // T
+    rows = packed_mask.shape[0]
+    assert rows % share == 0 and qkv.shape[0] == (rows // share) * T, "one qkv row block per `share` mask rows"
     H = qkv.shape[1] // 3
     words = packed_mask.shape[1]
-    assert packed_mask.shape[0] == rows, "one mask row per input row"
     ctx = torch.empty((rows * T, H), dtype=qkv.dtype, device=qkv.device)
     tc_ok = qkv.dtype == torch.bfloat16 and H == heads * 64 and T <= 256 and not force_simt
     if tc_ok:
         nat.NEXT_META = 4.0 * rows * T * T * H
-        nat.call("agb_masked_attention_bf16", nat.ptr(qkv), nat.ptr(packed_mask), words, rows, T, H, heads, mode,
-                 nat.ptr(ctx), nat.stream())
+        if share == 1:
+            nat.call("agb_masked_attention_bf16", nat.ptr(qkv), nat.ptr(packed_mask), words, rows, T, H, heads, mode,
+                     nat.ptr(ctx), nat.stream())
+        else:
+            nat.call("agb_masked_attention_bf16_shared", nat.ptr(qkv), nat.ptr(packed_mask), words, rows, share, T, H, heads,
+                     mode, nat.ptr(ctx), nat.stream())
     else:
+        assert share == 1, "shared projections need the tcgen05 attention kernel"
         step = 65535
         for r0 in range(0, rows, step):
             r1 = min(rows, r0 + step)

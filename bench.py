@@ -46,15 +46,19 @@ def flops_per_eval(c):
     return float(L * layer + 2 * H * C + 2 * (T - 1) * H * c["img_channels"] * c["img_patch_size"] ** 2)
 
 
-def flops_per_eval_executed(c):
-    """FLOPs actually executed per masked evaluation: the surrogate head reads only token 0, so the last block runs its
-    query / attention output / output projection / MLP for the CLS row alone (keys and values still for all T tokens) —
-    exact work-skipping (engine.CLS_ONLY_LAST_BLOCK).  SURVEY.md 8d asks for both figures when work is skipped."""
+def flops_per_eval_executed(c, S=S_COALITIONS):
+    """FLOPs actually executed per masked evaluation with the two exact work-skipping steps of the engine (SURVEY.md 8d
+    asks for both figures when work is skipped):
+      * CLS_ONLY_LAST_BLOCK — the head reads only token 0, so the last block runs its query / attention output / output
+        projection / MLP for the CLS row alone (keys and values still for all T tokens);
+      * SHARE_FIRST_BLOCK — the first block's QKV projection (and the patch embedding) run once per input, not per coalition."""
     H, I = c["hidden_size"], c["intermediate_size"]
     T = (c["img_px_size"] // c["img_patch_size"]) ** 2 + 1
     layer = 2 * T * H * 3 * H + 2 * T * H * H + 4 * T * H * I + 4 * T * T * H
     last = 2 * T * H * 2 * H + (2 * H * H + 2 * H * H + 4 * H * I) + 4 * T * H
-    return flops_per_eval(c) - float(layer - last)
+    patch = 2 * (T - 1) * H * c["img_channels"] * c["img_patch_size"] ** 2
+    shared = (2 * T * H * 3 * H + patch) * (1.0 - 1.0 / S)
+    return flops_per_eval(c) - float(layer - last) - float(shared)
 
 
 def load_peaks():
@@ -387,8 +391,9 @@ def run_ours(args):
              "frac_of_burst_peak": value / world * flops_exec * 1e-12 / peaks["bf16_tflops"],
              "flops_per_eval_executed": flops_exec, "flops_per_eval_dense": flops_eval,
              "dense_equivalent_tflops_per_gpu": value / world * flops_eval * 1e-12,
-             "work_skipping": "exact: last encoder block evaluated for the CLS query only (the head reads token 0); "
-                              "K/V of the last block still computed for all tokens"}
+             "work_skipping": "exact: (1) last encoder block evaluated for the CLS query only (the head reads token 0; its "
+                              "K/V still computed for all tokens); (2) first block's QKV projection and the patch embedding "
+                              "computed once per image instead of once per coalition"}
 
     if rank == 0:
         cpu = None

@@ -147,6 +147,12 @@ int agb_masked_attention_simt(const void* qkv, int io_is_bf16, const uint32_t* m
 int agb_masked_attention_bf16(const void* qkv, const uint32_t* mask, int words, int rows, int T,
                               int H, int heads, int mode, void* ctx, void* stream);
 
+/* First-block form: `share` consecutive mask rows (the coalitions of one input) read the SAME projections, qkv
+ * (rows / share, T, 3H) — before the first attention every coalition of an input holds identical activations, so its
+ * LayerNorm + QKV projection is computed once per input (exact work-skipping).  ctx (rows, T, H) as above. */
+int agb_masked_attention_bf16_shared(const void* qkv, const uint32_t* mask, int words, int rows, int share, int T,
+                                     int H, int heads, int mode, void* ctx, void* stream);
+
 /* CLS-query attention for the LAST encoder block of a surrogate / classifier (exact work-skipping: the heads read only
  * token 0 — reference models/vanilla_vit.py:51-56, models/vanilla_bert.py:615-619 — so only the CLS query row of the last
  * block is needed; keys / values still come from all T tokens).  q (rows, ldq); kv (rows*T, ldkv) with keys at column

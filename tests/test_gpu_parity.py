@@ -463,6 +463,28 @@ def test_cls_only_last_block_is_exact_work_skipping(agb, golden_dir, name, preci
     np.testing.assert_allclose(_np(p_skip), g["v_s"], **({"rtol": 1e-4, "atol": 2e-6} if precision == "fp32" else {"atol": 2e-2}))
 
 
+@pytest.mark.parametrize("name", ["vit_base", "bert_base_128", "vit_tiny", "vit_mini", "bert_mini"])
+def test_first_block_projection_sharing_is_exact(agb, golden_dir, name):
+    """Before the first attention every coalition of an input holds identical activations: computing that block's
+    LayerNorm + QKV once per input (and letting the attention kernel read the shared rows) changes nothing."""
+    from autognothi_b200 import engine
+    g = _load(golden_dir, f"model_{name}.npz")
+    B, S, n = (int(v) for v in g["meta"])
+    rec, cfgd, srg, exp = _build(name, "bf16")
+    xs = torch.from_numpy(synth.inputs(cfgd, B, seed=0)).to(DEV)
+    masks = torch.from_numpy(g["masks"].astype(np.int64)).to(DEV).reshape(B, S, n)
+    try:
+        with torch.no_grad():
+            engine.SHARE_FIRST_BLOCK = True
+            p_share, _ = rec.fw_surrogate(srg, xs, masks)
+            engine.SHARE_FIRST_BLOCK = False
+            p_plain, _ = rec.fw_surrogate(srg, xs, masks)
+    finally:
+        engine.SHARE_FIRST_BLOCK = True
+    np.testing.assert_allclose(_np(p_share), _np(p_plain), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(_np(p_share), g["v_s"], atol=2e-2)
+
+
 def test_final_coherency(agb):
     """The reference's only numerical self-check (scripts/train_all.py:166-218): the bundled Final model
     agrees with the separate classifier / surrogate / explainer on the same input."""
