@@ -17,6 +17,8 @@
 //   * GELU costs one MUFU and 8 issue slots (gelu_erf_tanhform) instead of two MUFU and ~16.
 //   * producer and MMA warps run convergently with elected-lane predication (uniform-register operands).
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (leader CTA only) + TMEM owner, 2..9 = epilogue.
+#include <type_traits>
+
 #include "agb_common.cuh"
 
 namespace agb {
@@ -248,26 +250,26 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool row_ok = row0 < p.M;
       const int out_row0 = row0 + sp * p.M;     // split-K partials are stacked along the rows of the workspace
       float ln_rstd = 1.f, ln_nmr = 0.f;      // LNIN: rstd_i and -mean_i * rstd_i of this thread's row
+      float2 ln_part[LNIN ? 8 : 1];           // partial (sum, sumsq): loads are issued here, consumed after the TMEM wait
       if (LNIN) {
         const int my_row = row0 + lane;
-        if (my_row < p.M) {
-          const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + (long long)my_row * p.ln_parts;
-          float s1 = 0.f, s2 = 0.f;
-          for (int i = 0; i < p.ln_parts; ++i) {
-            const float2 v = __ldg(sp + i);
-            s1 += v.x;
-            s2 += v.y;
-          }
-          const float invk = 1.0f / (float)p.K;
-          const float mean = s1 * invk;
-          const float var = fmaxf(fmaf(-mean, mean, s2 * invk), 0.f);
-          ln_rstd = rsqrtf(var + p.ln_eps);
-          ln_nmr = -mean * ln_rstd;
-        }
+        const float2* sp = reinterpret_cast<const float2*>(p.ln_stats) + (long long)min(my_row, p.M - 1) * p.ln_parts;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ln_part[i] = (i < p.ln_parts) ? __ldg(sp + i) : make_float2(0.f, 0.f);
       }
       float st_sum = 0.f, st_sq = 0.f;        // STATS: this thread's row over the warp's 128 columns
       mbar_wait(tfull0 + acc * 8, acc_phase);
       tc_fence_after();
+      if (LNIN) {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s1 += ln_part[i].x; s2 += ln_part[i].y; }
+        const float invk = 1.0f / (float)p.K;
+        const float mean = s1 * invk;
+        const float var = fmaxf(fmaf(-mean, mean, s2 * invk), 0.f);
+        ln_rstd = rsqrtf(var + p.ln_eps);
+        ln_nmr = -mean * ln_rstd;
+      }
       const uint32_t tm_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * PG_BN + h * (PG_BN / 2);
 #pragma unroll 1
       for (int c = 0; c < NCHUNK; ++c, ++g) {
@@ -299,14 +301,17 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         if (active) {
-          // bias columns past N are clamped to a valid address: those outputs are clipped by the TMA store
+          // bias / colsum columns past N are clamped to a valid address (those outputs are clipped by the TMA store);
+          // full chunks — every chunk of the hot shapes — take the copy of the loop with immediate offsets
           const float* bias_c = p.bias + col0;
-          const int n_last = (col0 + CHUNK_COLS <= p.N) ? (1 << 20) : (p.N - 4 - col0);   // no clamp on full chunks
+          const int n_last = p.N - 4 - col0;
+          auto chunk_math = [&](auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint32_t addr = buf + row_off + ((static_cast<uint32_t>(j) ^ sw) << 4);
             if (OUT_F32) {
-              const float4 bias4 = __ldg(reinterpret_cast<const float4*>(bias_c + min(4 * j, n_last)));
+              const float4 bias4 = __ldg(reinterpret_cast<const float4*>(bias_c + (FULL ? 4 * j : min(4 * j, n_last))));
               float4 v;
               v.x = fmaf(__uint_as_float(r[4 * j + 0]), p.alpha, bias4.x);
               v.y = fmaf(__uint_as_float(r[4 * j + 1]), p.alpha, bias4.y);
@@ -339,12 +344,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                              : "memory");
               }
             } else {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias_c + min(8 * j, n_last)));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias_c + min(8 * j + 4, n_last)));
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias_c + (FULL ? 8 * j : min(8 * j, n_last))));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias_c + (FULL ? 8 * j + 4 : min(8 * j + 4, n_last))));
               float v[8];
               if (LNIN) {
-                const float4 c0 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0 + min(8 * j, n_last)));
-                const float4 c1 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0 + min(8 * j + 4, n_last)));
+                const float4 c0 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0 + (FULL ? 8 * j : min(8 * j, n_last))));
+                const float4 c1 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col0 + (FULL ? 8 * j + 4 : min(8 * j + 4, n_last))));
                 v[0] = fmaf(__uint_as_float(r[8 * j + 0]), ln_rstd, fmaf(ln_nmr, c0.x, b0.x));
                 v[1] = fmaf(__uint_as_float(r[8 * j + 1]), ln_rstd, fmaf(ln_nmr, c0.y, b0.y));
                 v[2] = fmaf(__uint_as_float(r[8 * j + 2]), ln_rstd, fmaf(ln_nmr, c0.z, b0.z));
@@ -372,6 +377,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                            : "memory");
             }
           }
+          };
+          if (col0 + CHUNK_COLS <= p.N) chunk_math(std::true_type{});
+          else chunk_math(std::false_type{});
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -491,7 +499,7 @@ int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, 
   if (((long long)ldo * oes) % 16 != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0) return AGB_ERR_UNSUPPORTED;
   if (res_f32 && ((((long long)ldr * 4) % 16) != 0 || (reinterpret_cast<uintptr_t>(res_f32) & 15) != 0))
     return AGB_ERR_UNSUPPORTED;
-  if (lnin && (out_f32 || res_f32 || a_mn || ln_colsum == nullptr || ln_parts <= 0 || alpha != 1.0f ||
+  if (lnin && (out_f32 || res_f32 || a_mn || ln_colsum == nullptr || ln_parts <= 0 || ln_parts > 8 || alpha != 1.0f ||
                (reinterpret_cast<uintptr_t>(ln_colsum) & 15) != 0))
     return AGB_ERR_UNSUPPORTED;
   if (stats && (!res_f32 || out16 == nullptr || (N % PG_BN) != 0 || (ldo16 % 8) != 0 ||
