@@ -456,6 +456,168 @@ attention_bwd_kernel(const TIO* __restrict__ qkv, const TIO* __restrict__ dctx, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Long sequences (256 < T <= 512, e.g. the reference's checked-in BERT configuration with 512 positions): the four
+// T x 64 operands no longer fit in shared memory together, so the two passes become two kernels.
+//   A (query-owned): K, V of the unit staged + a 64-query block -> row statistics (to a global scratch), dQ
+//   B (key-owned)  : Q, dO of the unit staged + a 64-key block  -> dK, dV   (re-computes the scores)
+// Same arithmetic as attention_bwd_kernel.  grid = (ceil(T / 64), rows * heads).
+// ------------------------------------------------------------------------------------------------
+constexpr int ABL_BLK = 64;
+
+template <typename TIO>
+__global__ void __launch_bounds__(256)
+attention_bwd_long_a_kernel(const TIO* __restrict__ qkv, const TIO* __restrict__ dctx, const uint32_t* __restrict__ mask,
+                            int words, int T, int H, int heads, int mode, TIO* __restrict__ dqkv,
+                            float* __restrict__ stat /* [rows*heads][2][T] */) {
+  extern __shared__ uint8_t smraw[];
+  bf16* sK = reinterpret_cast<bf16*>(smraw);
+  bf16* sV = sK + T * AB_LD;
+  bf16* sQ = sV + T * AB_LD;                 // ABL_BLK rows
+  bf16* sdO = sQ + ABL_BLK * AB_LD;          // ABL_BLK rows
+  float* strips = reinterpret_cast<float*>(sdO + ABL_BLK * AB_LD);   // nw * 2 * T
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int unit = blockIdx.y, row = unit / heads, head = unit % heads;
+  const int i0 = blockIdx.x * ABL_BLK, i1 = min(T, i0 + ABL_BLK);
+  const long long base = (long long)row * T * 3 * H;
+  const uint32_t* mrow = mask + (long long)row * words;
+  const float scale = 0.125f;
+  for (int e = threadIdx.x; e < T * AB_D; e += blockDim.x) {
+    const int t = e / AB_D, c = e % AB_D;
+    const TIO* p = qkv + base + (long long)t * 3 * H + head * AB_D + c;
+    sK[t * AB_LD + c] = __float2bfloat16(ld1<TIO>(p + H));
+    sV[t * AB_LD + c] = __float2bfloat16(ld1<TIO>(p + 2 * H));
+  }
+  for (int e = threadIdx.x; e < (i1 - i0) * AB_D; e += blockDim.x) {
+    const int t = e / AB_D, c = e % AB_D;
+    sQ[t * AB_LD + c] = __float2bfloat16(ld1<TIO>(qkv + base + (long long)(i0 + t) * 3 * H + head * AB_D + c));
+    sdO[t * AB_LD + c] = __float2bfloat16(ld1<TIO>(dctx + ((long long)row * T + i0 + t) * H + head * AB_D + c));
+  }
+  __syncthreads();
+  float* s0 = strips + warp * 2 * T;
+  float* s1 = s0 + T;
+  for (int i = i0 + warp; i < i1; i += nw) {
+    const int il = i - i0;
+    float mx = -INFINITY;
+    for (int j = lane; j < T; j += 32) {
+      float a = 0.f, b = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < AB_D; ++c) {
+        a = fmaf(__bfloat162float(sQ[il * AB_LD + c]), __bfloat162float(sK[j * AB_LD + c]), a);
+        b = fmaf(__bfloat162float(sdO[il * AB_LD + c]), __bfloat162float(sV[j * AB_LD + c]), b);
+      }
+      const uint32_t keep = (mrow[j >> 5] >> (j & 31)) & 1u;
+      float x = a * scale;
+      if (!keep) x = (mode == AGB_MASK_MUL0) ? 0.f : -INFINITY;
+      s0[j] = x;
+      s1[j] = b;
+      mx = fmaxf(mx, x);
+    }
+    mx = warp_max(mx);
+    float z = 0.f;
+    for (int j = lane; j < T; j += 32) z += expf(s0[j] - mx);
+    z = warp_sum(z);
+    const float l = mx + logf(z);
+    float dsum = 0.f;
+    for (int j = lane; j < T; j += 32) {
+      const float pj = expf(s0[j] - l);
+      dsum += pj * s1[j];
+      s0[j] = pj;
+    }
+    dsum = warp_sum(dsum);
+    if (lane == 0) {
+      stat[((long long)unit * 2 + 0) * T + i] = l;
+      stat[((long long)unit * 2 + 1) * T + i] = dsum;
+    }
+    __syncwarp();
+    for (int j = lane; j < T; j += 32) {
+      const uint32_t keep = (mrow[j >> 5] >> (j & 31)) & 1u;
+      s0[j] = keep ? s0[j] * (s1[j] - dsum) * scale : 0.f;
+    }
+    __syncwarp();
+    float q0 = 0.f, q1 = 0.f;
+    for (int j = 0; j < T; ++j) {
+      const float ds = s0[j];
+      q0 = fmaf(ds, __bfloat162float(sK[j * AB_LD + lane]), q0);
+      q1 = fmaf(ds, __bfloat162float(sK[j * AB_LD + lane + 32]), q1);
+    }
+    TIO* dq = dqkv + base + (long long)i * 3 * H + head * AB_D;
+    st1<TIO>(dq + lane, q0);
+    st1<TIO>(dq + lane + 32, q1);
+    __syncwarp();
+  }
+}
+
+template <typename TIO>
+__global__ void __launch_bounds__(256)
+attention_bwd_long_b_kernel(const TIO* __restrict__ qkv, const TIO* __restrict__ dctx, const uint32_t* __restrict__ mask,
+                            int words, int T, int H, int heads, int mode, TIO* __restrict__ dqkv,
+                            const float* __restrict__ stat) {
+  extern __shared__ uint8_t smraw[];
+  bf16* sQ = reinterpret_cast<bf16*>(smraw);
+  bf16* sdO = sQ + T * AB_LD;
+  bf16* sK = sdO + T * AB_LD;                // ABL_BLK rows
+  bf16* sV = sK + ABL_BLK * AB_LD;           // ABL_BLK rows
+  float* lse = reinterpret_cast<float*>(sV + ABL_BLK * AB_LD);   // T
+  float* Dv = lse + T;                                            // T
+  float* strips = Dv + T;                                         // nw * 2 * T
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int unit = blockIdx.y, row = unit / heads, head = unit % heads;
+  const int j0 = blockIdx.x * ABL_BLK, j1 = min(T, j0 + ABL_BLK);
+  const long long base = (long long)row * T * 3 * H;
+  const uint32_t* mrow = mask + (long long)row * words;
+  const float scale = 0.125f;
+  for (int e = threadIdx.x; e < T * AB_D; e += blockDim.x) {
+    const int t = e / AB_D, c = e % AB_D;
+    sQ[t * AB_LD + c] = __float2bfloat16(ld1<TIO>(qkv + base + (long long)t * 3 * H + head * AB_D + c));
+    sdO[t * AB_LD + c] = __float2bfloat16(ld1<TIO>(dctx + ((long long)row * T + t) * H + head * AB_D + c));
+  }
+  for (int e = threadIdx.x; e < (j1 - j0) * AB_D; e += blockDim.x) {
+    const int t = e / AB_D, c = e % AB_D;
+    const TIO* p = qkv + base + (long long)(j0 + t) * 3 * H + head * AB_D + c;
+    sK[t * AB_LD + c] = __float2bfloat16(ld1<TIO>(p + H));
+    sV[t * AB_LD + c] = __float2bfloat16(ld1<TIO>(p + 2 * H));
+  }
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    lse[t] = stat[((long long)unit * 2 + 0) * T + t];
+    Dv[t] = stat[((long long)unit * 2 + 1) * T + t];
+  }
+  __syncthreads();
+  float* s0 = strips + warp * 2 * T;
+  float* s1 = s0 + T;
+  for (int j = j0 + warp; j < j1; j += nw) {
+    const int jl = j - j0;
+    const uint32_t keep = (mrow[j >> 5] >> (j & 31)) & 1u;
+    for (int i = lane; i < T; i += 32) {
+      float a = 0.f, b = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < AB_D; ++c) {
+        a = fmaf(__bfloat162float(sQ[i * AB_LD + c]), __bfloat162float(sK[jl * AB_LD + c]), a);
+        b = fmaf(__bfloat162float(sdO[i * AB_LD + c]), __bfloat162float(sV[jl * AB_LD + c]), b);
+      }
+      float x = a * scale;
+      if (!keep) x = (mode == AGB_MASK_MUL0) ? 0.f : -INFINITY;
+      const float pij = expf(x - lse[i]);
+      s0[i] = pij;
+      s1[i] = keep ? pij * (b - Dv[i]) * scale : 0.f;
+    }
+    __syncwarp();
+    float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
+    for (int i = 0; i < T; ++i) {
+      const float pij = s0[i], ds = s1[i];
+      k0 = fmaf(ds, __bfloat162float(sQ[i * AB_LD + lane]), k0);
+      k1 = fmaf(ds, __bfloat162float(sQ[i * AB_LD + lane + 32]), k1);
+      v0 = fmaf(pij, __bfloat162float(sdO[i * AB_LD + lane]), v0);
+      v1 = fmaf(pij, __bfloat162float(sdO[i * AB_LD + lane + 32]), v1);
+    }
+    TIO* dk = dqkv + base + (long long)j * 3 * H + H + head * AB_D;
+    TIO* dv = dqkv + base + (long long)j * 3 * H + 2 * H + head * AB_D;
+    st1<TIO>(dk + lane, k0); st1<TIO>(dk + lane + 32, k1);
+    st1<TIO>(dv + lane, v0); st1<TIO>(dv + lane + 32, v1);
+    __syncwarp();
+  }
+}
+
 // fp32-exact variant: same algorithm with float staging (used by the fp32 verification mode).
 __global__ void __launch_bounds__(256)
 attention_bwd_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ dctx,
@@ -574,8 +736,8 @@ int attention_bwd(const void* qkv, const void* dctx, int io_bf16, const uint32_t
   AGB_REQUIRE(rows >= 0 && T > 0 && heads > 0 && H == heads * AB_D, "attention backward needs head dim 64");
   AGB_REQUIRE(words * 32 >= T, "mask words");
   AGB_REQUIRE(mode == AGB_MASK_MUL0 || mode == AGB_MASK_NEGINF, "mask mode");
-  if (T > 256) {
-    set_last_error("agb_masked_attention_bwd supports T <= 256 (got %d)", T);
+  if (T > 512) {
+    set_last_error("agb_masked_attention_bwd supports T <= 512 (got %d)", T);
     return AGB_ERR_UNSUPPORTED;
   }
   if (rows == 0) return AGB_OK;
@@ -584,6 +746,39 @@ int attention_bwd(const void* qkv, const void* dctx, int io_bf16, const uint32_t
     const int rc2 = attention_bwd_tc(static_cast<const bf16*>(qkv), static_cast<const bf16*>(dctx), mask, words, rows, T, H,
                                      heads, mode, static_cast<bf16*>(dqkv), st);
     if (rc2 != AGB_ERR_UNSUPPORTED) return rc2;
+  }
+  if (T > 256) {
+    // two-kernel form (operands staged in bf16, fp32 math): fp32 I/O is accepted but is not the exact mode here
+    AGB_REQUIRE(rows * heads <= 65535, "grid limits (chunk the rows)");
+    static float* stat = nullptr;           // grow-only scratch for the row statistics (single-stream use)
+    static size_t stat_elems = 0;
+    const size_t need = (size_t)rows * heads * 2 * T;
+    if (need > stat_elems) {
+      if (stat != nullptr) {
+        AGB_CHECK_CUDA(cudaStreamSynchronize(st));
+        AGB_CHECK_CUDA(cudaFree(stat));
+      }
+      AGB_CHECK_CUDA(cudaMalloc(&stat, need * sizeof(float)));
+      stat_elems = need;
+    }
+    const int nwl = 8;
+    const size_t smem_l = (size_t)2 * T * AB_LD * 2 + (size_t)2 * ABL_BLK * AB_LD * 2 + (size_t)2 * T * 4 +
+                          (size_t)nwl * 2 * T * 4;
+    dim3 grid((T + ABL_BLK - 1) / ABL_BLK, rows * heads);
+#define ABL_LAUNCH(TIO)                                                                                               \
+  do {                                                                                                                \
+    AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_long_a_kernel<TIO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l)); \
+    AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_long_b_kernel<TIO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l)); \
+    attention_bwd_long_a_kernel<TIO><<<grid, nwl * 32, smem_l, st>>>(static_cast<const TIO*>(qkv), static_cast<const TIO*>(dctx), \
+                                                                     mask, words, T, H, heads, mode, static_cast<TIO*>(dqkv), stat); \
+    attention_bwd_long_b_kernel<TIO><<<grid, nwl * 32, smem_l, st>>>(static_cast<const TIO*>(qkv), static_cast<const TIO*>(dctx), \
+                                                                     mask, words, T, H, heads, mode, static_cast<TIO*>(dqkv), stat); \
+  } while (0)
+    if (io_bf16) ABL_LAUNCH(bf16);
+    else ABL_LAUNCH(float);
+#undef ABL_LAUNCH
+    AGB_CHECK_CUDA(cudaGetLastError());
+    return AGB_OK;
   }
   const int nw = 8;
   if (io_bf16) {

@@ -60,6 +60,8 @@ CONFIGS: Dict[str, Dict[str, Any]] = {
     # reference experiments/vit_large_imagenette_vanilla/.hparams.json:20-35
     "vit_large": _vit(1024, 16, 24, 4096, 4096),
     "bert_mini": _bert(128, 2, 2, 256, 192, max_pos=32, vocab=1000),
+    # long-sequence edge case: the reference's checked-in BERT configuration has 512 positions
+    "bert_mini_512": _bert(128, 2, 2, 256, 192, max_pos=512, vocab=1000),
     # reference experiments/bert_base_tayp_vanilla/.hparams.json:14-30 with max_position_embeddings=128
     # (BASELINE.json "128-token" configuration)
     "bert_base_128": _bert(768, 12, 12, 3072, 3072, max_pos=128),

@@ -113,12 +113,19 @@ MODEL_CASES = [
     ("vit_base", 1, 2),
     ("bert_mini", 3, 4),
     ("bert_base_128", 1, 2),
+    ("bert_mini_512", 2, 2),
 ]
 
 
-def gen_models():
+def gen_models(only=None):
     keys = {}
+    keys_path = os.path.join(HERE, "state_dict_keys.json")
+    if only and os.path.exists(keys_path):
+        with open(keys_path) as f:
+            keys = json.load(f)
     for name, B, S in MODEL_CASES:
+        if only and name not in only:
+            continue
         cfg = ocfg.get_config(name)
         vit = ocfg.is_vit(cfg)
         n = ocfg.n_players(cfg)
@@ -161,10 +168,12 @@ def gen_models():
         json.dump(keys, f, indent=0, sort_keys=True)
 
 
-def gen_train_grads():
+def gen_train_grads(only=None):
     """One explainer training step's loss and parameter gradients from the reference's autograd
     (scripts/train_explainer.py:182-197 semantics), in eval() mode so that dropout is the identity."""
-    for name, B, S in [("vit_mini", 2, 4), ("vit_mini_px64", 3, 4), ("bert_mini", 3, 4)]:
+    for name, B, S in [("vit_mini", 2, 4), ("vit_mini_px64", 3, 4), ("bert_mini", 3, 4), ("bert_mini_512", 2, 2)]:
+        if only and name not in only:
+            continue
         cfg = ocfg.get_config(name)
         vit = ocfg.is_vit(cfg)
         n = ocfg.n_players(cfg)
@@ -248,7 +257,10 @@ def gen_surrogate_train_grads():
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "train":
-        gen_train_grads()
+        gen_train_grads(only=sys.argv[2:] or None)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "model":
+        gen_models(only=sys.argv[2:] or None)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "surrogate":
         gen_surrogate_train_grads()

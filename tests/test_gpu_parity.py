@@ -385,7 +385,7 @@ def _build(name, precision):
     return rec, cfgd, srg, exp
 
 
-FP32_CASES = ["vit_mini", "vit_mini_px64", "bert_mini", "vit_tiny"]
+FP32_CASES = ["vit_mini", "vit_mini_px64", "bert_mini", "vit_tiny", "bert_mini_512"]   # bert_mini_512: T = 512 edge case
 
 
 @pytest.mark.parametrize("name", FP32_CASES + ["vit_base", "bert_base_128"])
@@ -416,7 +416,7 @@ def test_full_path_fp32_vs_reference_golden(agb, golden_dir, name):
     np.testing.assert_allclose(_np(phi_m), g["phi_masked"], rtol=1e-4, atol=1e-4 * scale)
 
 
-@pytest.mark.parametrize("name", ["vit_mini", "bert_mini", "vit_tiny", "vit_base", "bert_base_128"])
+@pytest.mark.parametrize("name", ["vit_mini", "bert_mini", "vit_tiny", "vit_base", "bert_base_128", "bert_mini_512"])
 def test_full_path_bf16_tensor_cores_vs_reference_golden(agb, golden_dir, name):
     g = _load(golden_dir, f"model_{name}.npz")
     B, S, n = (int(v) for v in g["meta"])
@@ -561,7 +561,7 @@ def test_training_gradients_fp32_vs_reference_autograd(agb, golden_dir, name):
             np.testing.assert_allclose(_np(params[k].grad), ref, rtol=2e-3, atol=2e-3 * np.abs(ref).max() + floor, err_msg=k)
 
 
-@pytest.mark.parametrize("name", ["vit_mini", "bert_mini"])
+@pytest.mark.parametrize("name", ["vit_mini", "bert_mini", "bert_mini_512"])   # 512: two-pass long-sequence adjoint
 def test_training_gradients_bf16_tensor_cores(agb, golden_dir, name):
     t = _load(golden_dir, f"train_{name}.npz")
     exp, loss = _train_step_grads(golden_dir, name, "bf16")

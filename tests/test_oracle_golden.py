@@ -99,7 +99,7 @@ def test_state_dict_keys_match_reference(golden_dir):
         assert mine_e == kinds["explainer"], name
 
 
-MODEL_CASES = ["vit_mini", "vit_mini_px64", "vit_tiny", "bert_mini", "vit_base", "bert_base_128"]
+MODEL_CASES = ["vit_mini", "vit_mini_px64", "vit_tiny", "bert_mini", "vit_base", "bert_base_128", "bert_mini_512"]
 
 
 @pytest.mark.parametrize("name", MODEL_CASES)
