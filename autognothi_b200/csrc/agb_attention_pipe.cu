@@ -1,7 +1,7 @@
 // Fused key-masked attention, second generation: a warp-specialised software pipeline per SM.
 //
 // Same contract as agb_attention_tc.cu (reference models/vanilla_vit.py:444-463, models/vanilla_bert.py:
-// 517-537; bf16 in/out, head dim 64, T <= 256) — the (N,h,T,T) score tensor never leaves the SM and
+// 517-537; bf16 in/out, head dim 64, T <= 512) — the (N,h,T,T) score tensor never leaves the SM and
 // masked copies of the input are never built.  Round-1 measurement: the first-generation kernel ran one
 // (row, head, m-tile) at a time per CTA and spent 18 % of the step on 4 % of the FLOPs, ~3x off its MUFU
 // bound, because load -> mask -> QK^T -> softmax -> PV -> store were serialised and only overlapped
@@ -35,6 +35,9 @@ struct AttPipeParams {
   int units;         // rows * heads
   int mtiles;        // ceil(T / 128)
   int share;         // consecutive mask rows that read the SAME qkv row (first block: one projection per input)
+  int groups;        // softmax groups / TMEM regions in flight: 2 (NK <= 256) or 1 (256 < NK <= 512: S needs all 512 columns)
+  int ring;          // K/V ring depth (units), limited by shared memory
+  int kvb;           // bytes reserved per K (or V) tile: NK * 128, or 2 x 256-row TMA boxes when NK > 256
   bf16* ctx;
   long long* trace;  // optional [items][8] clock64 timestamps of CTA 0 (diagnostics), or nullptr
 };
@@ -115,17 +118,20 @@ __device__ __forceinline__ void ap_live_bits(const uint32_t* mrow, int words, in
   hi = (uint32_t)(live >> 32);
 }
 
-template <int MODE>
+template <int MODE, int G>
 __global__ void __launch_bounds__(AP_THREADS, 1)
 attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                       const AttPipeParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  const int kvb = p.NK * 128;                  // bytes of one K (or V) tile
+  const int kvb = p.kvb;                       // bytes of one K (or V) tile
+  const int R = (G == 2) ? AP_KV_RING : p.ring;   // two groups <=> NK <= 256 <=> the full ring always fits
+  constexpr int rstride = 512 / G;             // TMEM columns per group region
+  constexpr int o_col = (G == 2) ? AP_O_COL : 256; // O accumulator overlays S columns the softmax has already consumed
   uint8_t* sQ = smem;                          // [2][128 x 128 B]
-  uint8_t* sKV = smem + 2 * 16384;             // [AP_KV_RING][K | V]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + AP_KV_RING * 2 * kvb);
+  uint8_t* sKV = smem + 2 * 16384;             // [ring][K | V]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + p.ring * 2 * p.kvb);
   uint64_t* q_full = bars;                     // [2]
   uint64_t* q_empty = bars + 2;                // [2]
   uint64_t* kv_full = bars + 4;                // [3]
@@ -180,13 +186,18 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const int u = blockIdx.x + ui * grid;
       const int row = u / p.heads, head = u - row * p.heads;
       if (m == 0) {
-        const int b = ui % AP_KV_RING, n = ui / AP_KV_RING;
+        const int b = ui % R, n = ui / R;
         if (n > 0) mbar_wait(smem_u32(&kv_empty[b]), (n - 1) & 1);
         const uint32_t bar = smem_u32(&kv_full[b]);
         mbar_arrive_expect_tx_e(e, bar, 2 * kvb);
         const uint32_t dst = smem_u32(sKV + b * 2 * kvb);
+        // one TMA box per tile (NK <= 256 rows) or two 256-row boxes (rows past T are zero-filled)
         tma_load_3d_e(e, dst, &tmKV, bar, H + head * AP_D, 0, row / p.share);
         tma_load_3d_e(e, dst + kvb, &tmKV, bar, 2 * H + head * AP_D, 0, row / p.share);
+        if (G == 1) {       // second 256-row box
+          tma_load_3d_e(e, dst + 256 * 128, &tmKV, bar, H + head * AP_D, 256, row / p.share);
+          tma_load_3d_e(e, dst + kvb + 256 * 128, &tmKV, bar, 2 * H + head * AP_D, 256, row / p.share);
+        }
         AP_TRACE(k, 0);
       }
       const int qb = k & 1, nq = k >> 1;
@@ -198,27 +209,35 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
     const uint32_t e = elect_one();
-    const uint32_t idesc_s = make_idesc_bf16(128, NK, 0, 0);
+    const int n0 = NK > 256 ? 256 : NK, n1 = NK - n0;                // S = Q K^T is issued in key chunks of <= 256 (UMMA N limit)
+    const uint32_t idesc_s0 = make_idesc_bf16(128, n0, 0, 0);
+    const uint32_t idesc_s1 = make_idesc_bf16(128, n1 > 0 ? n1 : 16, 0, 0);
     const uint64_t dk0 = make_smem_desc_sw128(0, 16, 1024);       // K-major operands (Q, K)
     const uint32_t sq0 = smem_u32(sQ) >> 4, skv0 = smem_u32(sKV) >> 4;
     const uint32_t kvb16 = (uint32_t)kvb >> 4;
 
-    // S issuer.  S_k reuses the TMEM region of item k-2: o_free (that item's epilogue has drained O) implies its
+    // S issuer.  S_k reuses the TMEM region of item k-G: o_free (that item's epilogue has drained O) implies its
     // PV has completed, so no ordering with the PV issuer (warp 2) is needed beyond the barriers.
     for (int k = 0; k < n_items; ++k) {
       const int ui = k / mt, m = k - ui * mt;
-      const int b = ui % AP_KV_RING, g = k & 1, n = k >> 1;
-      if (m == 0) mbar_wait(smem_u32(&kv_prep[b]), (ui / AP_KV_RING) & 1);
-      mbar_wait(smem_u32(&q_full[g]), n & 1);
+      const int b = ui % R, g = k % G, n = k / G, qb = k & 1, nq = k >> 1;
+      if (m == 0) mbar_wait(smem_u32(&kv_prep[b]), (ui / R) & 1);
+      mbar_wait(smem_u32(&q_full[qb]), nq & 1);
       if (n > 0) mbar_wait(smem_u32(&o_free[g]), (n - 1) & 1);
       tc_fence_after();
-      const uint32_t aq = sq0 + g * (16384 >> 4);
+      const uint32_t aq = sq0 + qb * (16384 >> 4);
       const uint32_t ak = skv0 + b * 2 * kvb16;
 #pragma unroll
       for (int kk = 0; kk < AP_D / 16; ++kk)
-        umma_ss_e<1>(e, tmem_base + g * 256, dk0 + (aq + kk * 2), dk0 + (ak + kk * 2), idesc_s, kk != 0 ? 1u : 0u);
+        umma_ss_e<1>(e, tmem_base + g * rstride, dk0 + (aq + kk * 2), dk0 + (ak + kk * 2), idesc_s0, kk != 0 ? 1u : 0u);
+      if (G == 1 && n1 > 0) {
+#pragma unroll
+        for (int kk = 0; kk < AP_D / 16; ++kk)
+          umma_ss_e<1>(e, tmem_base + g * rstride + 256, dk0 + (aq + kk * 2), dk0 + (ak + (256 * 128 >> 4) + kk * 2), idesc_s1,
+                       kk != 0 ? 1u : 0u);
+      }
       umma_commit_e<1>(e, smem_u32(&s_full[g]));
-      umma_commit_e<1>(e, smem_u32(&q_empty[g]));
+      umma_commit_e<1>(e, smem_u32(&q_empty[qb]));
       AP_TRACE(k, 1);
     }
   } else if (warp == 2) {
@@ -230,12 +249,12 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const uint32_t kvb16 = (uint32_t)kvb >> 4;
     for (int k = 0; k < n_items; ++k) {
       const int ui = k / mt, m = k - ui * mt;
-      const int b = ui % AP_KV_RING, g = k & 1, n = k >> 1;
+      const int b = ui % R, g = k % G, n = k / G;
       mbar_wait(smem_u32(&p_full[g]), n & 1);
       AP_TRACE(k, 2);
       tc_fence_after();
       const uint32_t av = skv0 + b * 2 * kvb16 + kvb16;
-      const uint32_t d_o = tmem_base + g * 256 + AP_O_COL, a_p = tmem_base + g * 256;
+      const uint32_t d_o = tmem_base + g * rstride + o_col, a_p = tmem_base + g * rstride;
       const uint64_t dv = dv0 + av;
       const int nks = NK / 16;
 #pragma unroll 4
@@ -249,7 +268,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     // ------------------------------ mask prep (ViT: zero masked K rows) ------------------------------
     const int tid = lane;
     for (int ui = 0; ui < nu; ++ui) {
-      const int b = ui % AP_KV_RING, n = ui / AP_KV_RING;
+      const int b = ui % R, n = ui / R;
       mbar_wait(smem_u32(&kv_full[b]), n & 1);
       if (MODE == AGB_MASK_MUL0) {
         const int u = blockIdx.x + ui * grid;
@@ -272,10 +291,10 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int g = (warp - 4) >> 2;
     const int qd = warp & 3;                        // TMEM lane quarter this warp may touch
     const int r = qd * 32 + lane;                   // query row within the tile = TMEM lane
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + g * 256;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + g * rstride;
     const float scale_log2 = 0.125f * 1.4426950408889634f;
-    for (int k = g; k < n_items; k += 2) {
-      const int n = k >> 1;
+    for (int k = g; k < n_items && g < G; k += G) {     // with one group (long sequences) warps 8-11 have nothing to do
+      const int n = k / G;
       const int ui = k / mt, m = k - ui * mt;
       const int u = blockIdx.x + ui * grid;
       const int row = u / p.heads, head = u - row * p.heads;
@@ -331,7 +350,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       if (qd == 0) AP_TRACE(k, 6);
       tc_fence_after();
       uint32_t o[64];
-      if (warp_live) ap_load<64>(lane_addr + AP_O_COL, o);
+      if (warp_live) ap_load<64>(lane_addr + o_col, o);
       // O is in registers: release the TMEM region (the next S_k+2 may overwrite it) BEFORE scaling / storing
       tc_fence_before();
       __syncwarp();
@@ -378,25 +397,43 @@ int attention_pipe(const bf16* qkv, const uint32_t* mask, int words, int rows, i
   p.share = share;
   p.ctx = ctx;
   p.trace = g_attention_trace;
+  // NK <= 256: two softmax groups ping-pong over 2 x 256 TMEM columns, one TMA box per K / V tile, K/V ring of 3 units.
+  // 256 < NK <= 512: S needs all 512 columns (one group), K / V arrive as two 256-row boxes, ring as deep as smem allows.
+  const int box_rows = p.NK > 256 ? 256 : p.NK;
+  p.groups = p.NK > 256 ? 1 : 2;
+  p.kvb = p.NK > 256 ? 2 * 256 * 128 : p.NK * 128;
+  const int smem_budget = 227 * 1024 - (1024 + 2 * 16384 + 256);
+  p.ring = smem_budget / (2 * p.kvb);
+  if (p.ring > AP_KV_RING) p.ring = AP_KV_RING;
+  if (p.ring < 1) return AGB_ERR_UNSUPPORTED;
   CUtensorMap tmQ, tmKV;
   int rc = encode_tmap_3d_bf16(&tmQ, qkv, 3 * (uint64_t)H, T, qrows, (uint64_t)3 * H * 2, (uint64_t)T * 3 * H * 2,
                                AP_D, 128, 1);
   if (rc != AGB_OK) return rc;
   rc = encode_tmap_3d_bf16(&tmKV, qkv, 3 * (uint64_t)H, T, qrows, (uint64_t)3 * H * 2, (uint64_t)T * 3 * H * 2,
-                           AP_D, p.NK, 1);
+                           AP_D, box_rows, 1);
   if (rc != AGB_OK) return rc;
-  const int smem = 1024 + 2 * 16384 + AP_KV_RING * 2 * p.NK * 128 + 256;
+  const int smem = 1024 + 2 * 16384 + p.ring * 2 * p.kvb + 256;
   static int configured_smem = 0;
   if (smem > configured_smem) {
-    AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<AGB_MASK_MUL0>,
+    AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<AGB_MASK_MUL0, 2>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<AGB_MASK_NEGINF>,
+    AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<AGB_MASK_NEGINF, 2>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<AGB_MASK_MUL0, 1>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<AGB_MASK_NEGINF, 1>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured_smem = smem;
   }
   const int grid = p.units < sm_count() ? p.units : sm_count();
-  if (mode == AGB_MASK_MUL0) attention_pipe_kernel<AGB_MASK_MUL0><<<grid, AP_THREADS, smem, stream>>>(tmQ, tmKV, p);
-  else                       attention_pipe_kernel<AGB_MASK_NEGINF><<<grid, AP_THREADS, smem, stream>>>(tmQ, tmKV, p);
+  if (p.groups == 2) {
+    if (mode == AGB_MASK_MUL0) attention_pipe_kernel<AGB_MASK_MUL0, 2><<<grid, AP_THREADS, smem, stream>>>(tmQ, tmKV, p);
+    else                       attention_pipe_kernel<AGB_MASK_NEGINF, 2><<<grid, AP_THREADS, smem, stream>>>(tmQ, tmKV, p);
+  } else {
+    if (mode == AGB_MASK_MUL0) attention_pipe_kernel<AGB_MASK_MUL0, 1><<<grid, AP_THREADS, smem, stream>>>(tmQ, tmKV, p);
+    else                       attention_pipe_kernel<AGB_MASK_NEGINF, 1><<<grid, AP_THREADS, smem, stream>>>(tmQ, tmKV, p);
+  }
   AGB_CHECK_CUDA(cudaGetLastError());
   return AGB_OK;
 }

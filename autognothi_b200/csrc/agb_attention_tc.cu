@@ -256,8 +256,8 @@ int attention_tc(const bf16* qkv, const uint32_t* mask, int words, int rows, int
   AGB_REQUIRE(rows >= 0 && T > 0 && heads > 0 && H == heads * ATT_D, "tensor-core attention needs head dim 64");
   AGB_REQUIRE(words * 32 >= T, "mask words");
   AGB_REQUIRE(mode == AGB_MASK_MUL0 || mode == AGB_MASK_NEGINF, "mask mode");
-  if (T > 256) {
-    set_last_error("agb_masked_attention_bf16 supports T <= 256 (got %d); use agb_masked_attention_simt", T);
+  if (T > 512) {
+    set_last_error("agb_masked_attention_bf16 supports T <= 512 (got %d); use agb_masked_attention_simt", T);
     return AGB_ERR_UNSUPPORTED;
   }
   if (rows == 0) return AGB_OK;
@@ -267,8 +267,8 @@ int attention_tc(const bf16* qkv, const uint32_t* mask, int words, int rows, int
     const int rc2 = attention_pipe(qkv, mask, words, rows, share, T, H, heads, mode, ctx, stream);
     if (rc2 != AGB_ERR_UNSUPPORTED) return rc2;
   }
-  if (share != 1) {
-    set_last_error("shared-qkv attention needs the pipelined kernel (agb_attention_set_variant(0))");
+  if (share != 1 || T > 256) {
+    set_last_error("shared-qkv attention and T > 256 need the pipelined kernel (agb_attention_set_variant(0))");
     return AGB_ERR_UNSUPPORTED;
   }
   AttParams p;

@@ -257,7 +257,7 @@ def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tens
     fused = bw.vit and FUSE_LAYERNORM and pol.bf16 and H % 256 == 0 and all(lw.fold() is not None for lw in bw.layers)
     # First-block sharing (exact): before the first attention all S coalitions of an input hold identical activations,
     # so that block's LayerNorm + QKV projection runs once per input and the attention kernel reads the shared rows.
-    share = (SHARE_FIRST_BLOCK and S > 1 and pol.bf16 and len(full) > 0 and T <= 256 and H == heads * 64)
+    share = (SHARE_FIRST_BLOCK and S > 1 and pol.bf16 and len(full) > 0 and T <= 512 and H == heads * 64)
     ctx0 = None
     if share:
         x_img = embed(bw, cfg, pol, xs, 1)                                   # (B, T, H) fp32, one row block per input

@@ -265,7 +265,7 @@ def cls_head(x: Tensor, mode: int, w_cls: Tensor, b_cls: Tensor, *, ln: Optional
 
 def masked_attention(qkv: Tensor, packed_mask: Tensor, T: int, heads: int, mode: int, *, force_simt: bool = False,
                      share: int = 1) -> Tensor:
-    """qkv (rows*T, 3H) fused projections -> ctx (rows*T, H), same dtype.  bf16 + head dim 64 + T <= 256 runs
+    """qkv (rows*T, 3H) fused projections -> ctx (rows*T, H), same dtype.  bf16 + head dim 64 + T <= 512 runs
     the tcgen05 kernel; fp32 (the exact mode) and the remaining shapes run the CUDA-core kernel.
     share > 1 (tcgen05 kernel only): qkv is (rows/share*T, 3H) and `share` consecutive mask rows read the same
     projections (the coalitions of one input in the first block)."""
@@ -275,7 +275,7 @@ def masked_attention(qkv: Tensor, packed_mask: Tensor, T: int, heads: int, mode:
     H = qkv.shape[1] // 3
     words = packed_mask.shape[1]
     ctx = torch.empty((rows * T, H), dtype=qkv.dtype, device=qkv.device)
-    tc_ok = qkv.dtype == torch.bfloat16 and H == heads * 64 and T <= 256 and not force_simt
+    tc_ok = qkv.dtype == torch.bfloat16 and H == heads * 64 and T <= 512 and not force_simt
     if tc_ok:
         nat.NEXT_META = 4.0 * rows * T * T * H
         if share == 1:

@@ -143,7 +143,7 @@ int agb_cls_head(const float* x, long long row_stride, int rows, int H, int C, i
  * mode AGB_MASK_MUL0 / AGB_MASK_NEGINF.  Scores are never written to HBM. */
 int agb_masked_attention_simt(const void* qkv, int io_is_bf16, const uint32_t* mask, int words,
                               int rows, int T, int H, int heads, int mode, void* ctx, void* stream);
-/* tcgen05/TMA version: bf16 in/out, head dim 64, T <= 512. */
+/* tcgen05/TMA version: bf16 in/out, head dim 64, T <= 512 (two softmax groups up to 256 keys, one group beyond). */
 int agb_masked_attention_bf16(const void* qkv, const uint32_t* mask, int words, int rows, int T,
                               int H, int heads, int mode, void* ctx, void* stream);
 
