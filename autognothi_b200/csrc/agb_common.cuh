@@ -244,15 +244,6 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
 // The pair's TMA loads land in the issuing CTA's smem but complete on the LEADER's mbarrier: clearing
 // the peer bit of a shared::cta address names the same offset in the even CTA of the pair.
 constexpr uint32_t PAIR_LEADER_MASK = 0xFEFFFFFFu;
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar,
-                                                 int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];"
-      :
-      : "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & PAIR_LEADER_MASK), "r"(c0), "r"(c1)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_result_addr, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result_addr),
                "r"(ncols)
@@ -264,26 +255,6 @@ __device__ __forceinline__ void tmem_relinquish_pair() {
 __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// D[tmem of both CTAs] (+)= A[smem, 128 rows per CTA] * B[smem, N/2 rows per CTA]; leader CTA issues.
-__device__ __forceinline__ void umma_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-      :
-      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrive (once) on the barrier at this smem offset in BOTH CTAs of the pair when the MMAs retire
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
-  asm volatile(
-      "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}\n"
-      :
-      : "r"(bar)
-      : "memory");
-}
-
 // ---------------------------------------------------------------------------------------------
 // "Elected" forms for the single-thread roles.  The whole warp executes these convergently with
 // warp-uniform operands and only the instruction itself is predicated on the elected lane (e != 0 in
@@ -452,22 +423,6 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float erf_v = copysignf(erf_abs, x);
   const float hx = 0.5f * x;
   return fmaf(hx, erf_v, hx);
-}
-
-// erf-GELU for the tensor-core epilogues with ONE MUFU op:  gelu(x) = max(x,0) - |x| * Phi(-|x|)  and
-//   Phi(-t) ~= 0.5 / (1 + t(c1 + t(c2 + t(c3 + t(c4 + t c5)))))^16      (fitted on t in [0,8], A&S 7.1.28 form)
-// max |gelu error| 1.8e-6, max |Phi error| 1e-5 — far below bf16 resolution; for t > 8 the power
-// overflows to +inf and the reciprocal is exactly 0, so gelu(x) = max(x,0).  13 issue slots.
-__device__ __forceinline__ float gelu_erf_rational(float x) {
-  const float t = fabsf(x);
-  float p = fmaf(9.285284751883197e-05f, t, -9.362633048630915e-05f);
-  p = fmaf(p, t, 0.003455584071090405f);
-  p = fmaf(p, t, 0.02103458463851493f);
-  p = fmaf(p, t, 0.04988919561503405f);
-  p = fmaf(p, t, 1.0f);
-  p *= p; p *= p; p *= p; p *= p;
-  const float r = rcp_approx(p);
-  return fmaf(-0.5f * t, r, fmaxf(x, 0.f));
 }
 
 // erf-GELU with ONE MUFU and 5 FMA-pipe ops:  gelu(x) = 0.5 x (1 + tanh(x (a + b x^2))), the tanh-form REFITTED to the
