@@ -94,10 +94,11 @@ def stream():
 LAUNCHES = 0       # number of kernel-launching C-ABI calls made through `call` (bench.py's gpu_launches)
 PROFILE = None     # when a list: every call appends (name, meta, start_event, end_event) — bench.py's roofline leg
 NEXT_META = None   # set by ops wrappers right before `call` (e.g. algorithmic FLOPs of a GEMM)
+NEXT_INFO = None   # optional (shape tag, algorithmic bytes) of the same call, for bench.py's per-shape roofline
 
 
 def call(name: str, *args) -> None:
-    global LAUNCHES, NEXT_META
+    global LAUNCHES, NEXT_META, NEXT_INFO
     LAUNCHES += 1
     if PROFILE is None:
         check(getattr(lib, name)(*args), name)
@@ -107,5 +108,6 @@ def call(name: str, *args) -> None:
     e0.record()
     check(getattr(lib, name)(*args), name)
     e1.record()
-    PROFILE.append((name, NEXT_META, e0, e1))
+    PROFILE.append((name, NEXT_META, e0, e1, NEXT_INFO))
     NEXT_META = None
+    NEXT_INFO = None

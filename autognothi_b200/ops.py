@@ -122,6 +122,8 @@ def gemm_bf16(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, act: int =
         assert bias.dtype == torch.float32 and bias.numel() == N
     ldr = residual.stride(0) if residual is not None else 0
     nat.NEXT_META = 2.0 * M * N * K
+    nat.NEXT_INFO = (f"M{M} N{N} K{K}" + (" +res" if residual is not None else "") + (" gelu" if act else ""),
+                     2.0 * M * K + 2.0 * N * K + M * N * out.element_size() + (M * N * residual.element_size() if residual is not None else 0))
     nat.call("agb_gemm_bf16", nat.ptr(a), a.stride(0), 1 if a_mn else 0, nat.ptr(w), w.stride(0), 1 if w_mn else 0,
              M, N, K, float(alpha), nat.ptr(bias), act, nat.ptr(res_bf16), nat.ptr(res_f32), ldr, res_group, res_rows,
              nat.ptr(out), out.stride(0), 1 if out.dtype == torch.float32 else 0, nat.stream())
@@ -160,6 +162,10 @@ def gemm_bf16_fused(a: Tensor, w: Tensor, bias: Optional[Tensor], *, act: int = 
     if residual is not None:
         assert residual.dtype == torch.float32 and residual.stride(1) == 1
     nat.NEXT_META = 2.0 * M * N * K
+    nat.NEXT_INFO = (f"M{M} N{N} K{K}" + (" +res" if residual is not None else "") + (" gelu" if act else "") +
+                     (" ln-folded" if ln is not None else "") + (" +copy+stats" if emit_copy_stats else ""),
+                     2.0 * M * K + 2.0 * N * K + M * N * out.element_size() + (4.0 * M * N if residual is not None else 0) +
+                     (2.0 * M * N + 8.0 * M * gemm_stats_parts(N) if emit_copy_stats else 0) + (8.0 * M * ln_parts if ln is not None else 0))
     nat.call("agb_gemm_bf16_fused", nat.ptr(a), a.stride(0), nat.ptr(w), w.stride(0), M, N, K, nat.ptr(bias), act,
              nat.ptr(residual), residual.stride(0) if residual is not None else 0, nat.ptr(out), out.stride(0),
              1 if out.dtype == torch.float32 else 0, nat.ptr(ln_stats), ln_parts, nat.ptr(ln_colsum), float(ln_eps),

@@ -356,7 +356,7 @@ def run_ours(args):
 
     # roofline of the dominant kernel (the tcgen05 GEMM): algorithmic FLOPs / CUDA-event duration
     by_kernel = {}
-    for name, meta, a, b in prof:
+    for name, meta, a, b, *_ in prof:
         t = a.elapsed_time(b)
         acc = by_kernel.setdefault(name, [0.0, 0.0, 0])
         acc[0] += t; acc[1] += (meta or 0.0); acc[2] += 1
@@ -382,6 +382,20 @@ def run_ours(args):
         "avg_launch_us": gemm[0] / gemm[2] * 1e3, "launches": gemm[2], "share_of_step": gemm[0] / total_t,
         "step_shares": {k: round(v[0] / total_t, 4) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1][0])},
     }
+    # per-shape view of the same launches: tensor-bound shapes against the bf16 peak, the residual GEMM with K = H
+    # (out-proj, 9.3 KB/row of fp32 residual in/out + bf16 copy) against the measured HBM bandwidth
+    shapes = {}
+    for name, meta, a, b, *rest in prof:
+        info = rest[0] if rest else None
+        if info is None or not name.startswith("agb_gemm_bf16"):
+            continue
+        acc = shapes.setdefault(info[0], [0.0, 0.0, 0.0, 0])
+        acc[0] += a.elapsed_time(b); acc[1] += (meta or 0.0); acc[2] += info[1]; acc[3] += 1
+    roofline["by_shape"] = [
+        {"gemm": k, "launches": v[3], "avg_us": round(v[0] / v[3] * 1e3, 1), "tflops": round(v[1] / (v[0] * 1e-3) * 1e-12, 1),
+         "frac_tensor": round(v[1] / (v[0] * 1e-3) * 1e-12 / peaks["bf16_tflops_sustained"], 3),
+         "algorithmic_gbs": round(v[2] / (v[0] * 1e-3) * 1e-9, 1), "frac_hbm": round(v[2] / (v[0] * 1e-3) * 1e-9 / peaks["hbm_gbs"], 3)}
+        for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][0]) if v[0] / total_t > 0.01]
     flops_eval = flops_per_eval(cfgd)
     flops_exec = flops_per_eval_executed(cfgd)
     # executed FLOPs are what the roofline fractions use; the dense-equivalent figure (every block on all tokens, what

@@ -39,17 +39,17 @@ def main():
         prof, nat.PROFILE = nat.PROFILE, None
     per_step = len(prof) // 4
     last = prof[-per_step:]
-    tot = sum(a.elapsed_time(b) for _, _, a, b in last)
+    tot = sum(a.elapsed_time(b) for _, _, a, b, *_ in last)
     print(f"{per_step} launches per step, sum of kernel times {tot:.2f} ms (last of 4 profiled steps)")
     # layer 5 window: find the 6th attention call
-    att = [i for i, (nm, _, _, _) in enumerate(last) if nm == "agb_masked_attention_bf16"]
+    att = [i for i, (nm, *_) in enumerate(last) if nm == "agb_masked_attention_bf16"]
     lo, hi = att[5] - 1, att[6] - 1
-    for nm, meta, a, b in last[lo:hi]:
+    for nm, meta, a, b, *_ in last[lo:hi]:
         t = a.elapsed_time(b) * 1e3
         tf = f"{meta / t * 1e-6:8.1f} TFLOP/s" if meta else ""
         print(f"  {nm:32s} {t:9.1f} us {tf}")
     agg = {}
-    for nm, meta, a, b in last:
+    for nm, meta, a, b, *_ in last:
         acc = agg.setdefault(nm, [0.0, 0.0, 0])
         acc[0] += a.elapsed_time(b); acc[1] += meta or 0.0; acc[2] += 1
     for nm, (t, fl, c) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
