@@ -15,6 +15,13 @@ int rank_masks(const float* scores, int use_philox, uint64_t seed, uint64_t offs
 int cls_attention(const void* q, long long ldq, const void* kv, long long ldkv, int k_off, int v_off, int io_bf16,
                   const uint32_t* mask, int words, int rows, int T, int H, int heads, int mode, void* ctx, long long ldc,
                   cudaStream_t st);
+int mask_counts(const uint32_t* packed, int rows, int words, int T, int* counts, cudaStream_t st);
+int packed_token_index(const uint32_t* packed, int rows, int words, int T, int S, const int* cu, long long* src,
+                       cudaStream_t st);
+int attention_varlen(const bf16* qkv, const int* cu, int rows, int max_len, int total_tokens, int H, int heads, bf16* ctx,
+                     cudaStream_t stream);
+int cls_attention_varlen(const void* q, long long ldq, const void* kv, long long ldkv, int k_off, int v_off, int io_bf16,
+                         const int* cu, int rows, int max_len, int H, int heads, void* ctx, long long ldc, cudaStream_t st);
 void set_attention_variant(int v);
 void set_attention_bwd_variant(int v);
 int get_attention_bwd_variant();
@@ -117,6 +124,25 @@ int agb_cls_attention(const void* q, long long ldq, const void* kv, long long ld
                       long long ldc, void* stream) {
   return agb::cls_attention(q, ldq, kv, ldkv, k_off, v_off, io_is_bf16, mask, words, rows, T, H, heads, mode, ctx, ldc,
                             ST(stream));
+}
+
+int agb_mask_counts(const uint32_t* packed, int rows, int words, int T, int* counts, void* stream) {
+  return agb::mask_counts(packed, rows, words, T, counts, ST(stream));
+}
+int agb_packed_token_index(const uint32_t* packed, int rows, int words, int T, int S, const int* cu, int64_t* src,
+                           void* stream) {
+  return agb::packed_token_index(packed, rows, words, T, S, cu, reinterpret_cast<long long*>(src), ST(stream));
+}
+int agb_attention_bf16_varlen(const void* qkv, const int* cu, int rows, int max_len, int total_tokens, int H, int heads,
+                              void* ctx, void* stream) {
+  return agb::attention_varlen(static_cast<const bf16*>(qkv), cu, rows, max_len, total_tokens, H, heads,
+                               static_cast<bf16*>(ctx), ST(stream));
+}
+int agb_cls_attention_varlen(const void* q, long long ldq, const void* kv, long long ldkv, int k_off, int v_off,
+                             int io_is_bf16, const int* cu, int rows, int max_len, int H, int heads, void* ctx,
+                             long long ldc, void* stream) {
+  return agb::cls_attention_varlen(q, ldq, kv, ldkv, k_off, v_off, io_is_bf16, cu, rows, max_len, H, heads, ctx, ldc,
+                                   ST(stream));
 }
 
 int agb_attention_set_variant(int variant) {

@@ -26,6 +26,7 @@ constexpr int AP_TMEM_COLS = 512;
 constexpr int AP_O_COL = 128;      // O accumulator at columns [128, 192) of the group's 256-column region
 constexpr int AP_KV_RING = 3;
 constexpr int AP_PREP_THREADS = 32;
+constexpr int AP_MODE_VARLEN = 2;   // internal third mode: packed variable-length rows, every packed token is a live key
 
 struct AttPipeParams {
   const uint32_t* mask;
@@ -38,6 +39,7 @@ struct AttPipeParams {
   int groups;        // softmax groups / TMEM regions in flight: 2 (NK <= 256) or 1 (256 < NK <= 512: S needs all 512 columns)
   int ring;          // K/V ring depth (units), limited by shared memory
   int kvb;           // bytes reserved per K (or V) tile: NK * 128, or 2 x 256-row TMA boxes when NK > 256
+  const int* cu;     // AP_MODE_VARLEN: row r owns the packed tokens [cu[r], cu[r+1]) of qkv (total_tokens, 3H)
   bf16* ctx;
   long long* trace;  // optional [items][8] clock64 timestamps of CTA 0 (diagnostics), or nullptr
 };
@@ -185,6 +187,10 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const int ui = k / mt, m = k - ui * mt;
       const int u = blockIdx.x + ui * grid;
       const int row = u / p.heads, head = u - row * p.heads;
+      // token coordinate of the unit's first token and batch coordinate of the TMA maps: (0, row / share) for the
+      // fixed-length layout (rows, T, 3H); (cu[row], 0) for packed rows (total_tokens, 3H)
+      const int tok0 = (MODE == AP_MODE_VARLEN) ? __ldg(p.cu + row) : 0;
+      const int brow = (MODE == AP_MODE_VARLEN) ? 0 : row / p.share;
       if (m == 0) {
         const int b = ui % R, n = ui / R;
         if (n > 0) mbar_wait(smem_u32(&kv_empty[b]), (n - 1) & 1);
@@ -192,11 +198,11 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         mbar_arrive_expect_tx_e(e, bar, 2 * kvb);
         const uint32_t dst = smem_u32(sKV + b * 2 * kvb);
         // one TMA box per tile (NK <= 256 rows) or two 256-row boxes (rows past T are zero-filled)
-        tma_load_3d_e(e, dst, &tmKV, bar, H + head * AP_D, 0, row / p.share);
-        tma_load_3d_e(e, dst + kvb, &tmKV, bar, 2 * H + head * AP_D, 0, row / p.share);
+        tma_load_3d_e(e, dst, &tmKV, bar, H + head * AP_D, tok0, brow);
+        tma_load_3d_e(e, dst + kvb, &tmKV, bar, 2 * H + head * AP_D, tok0, brow);
         if (G == 1) {       // second 256-row box
-          tma_load_3d_e(e, dst + 256 * 128, &tmKV, bar, H + head * AP_D, 256, row / p.share);
-          tma_load_3d_e(e, dst + kvb + 256 * 128, &tmKV, bar, 2 * H + head * AP_D, 256, row / p.share);
+          tma_load_3d_e(e, dst + 256 * 128, &tmKV, bar, H + head * AP_D, tok0 + 256, brow);
+          tma_load_3d_e(e, dst + kvb + 256 * 128, &tmKV, bar, 2 * H + head * AP_D, tok0 + 256, brow);
         }
         AP_TRACE(k, 0);
       }
@@ -204,7 +210,7 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       if (nq > 0) mbar_wait(smem_u32(&q_empty[qb]), (nq - 1) & 1);
       const uint32_t qbar = smem_u32(&q_full[qb]);
       mbar_arrive_expect_tx_e(e, qbar, 16384);
-      tma_load_3d_e(e, smem_u32(sQ + qb * 16384), &tmQ, qbar, head * AP_D, m * 128, row / p.share);
+      tma_load_3d_e(e, smem_u32(sQ + qb * 16384), &tmQ, qbar, head * AP_D, tok0 + m * 128, brow);
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
@@ -299,7 +305,12 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const int u = blockIdx.x + ui * grid;
       const int row = u / p.heads, head = u - row * p.heads;
       const uint32_t* mrow = p.mask + (long long)row * p.words;
-      const bool warp_live = (m * 128 + qd * 32) < T;     // warp-uniform: any real query row in this warp?
+      int tok0 = 0, Tr = T;                                // first token / length of this row
+      if (MODE == AP_MODE_VARLEN) {
+        tok0 = __ldg(p.cu + row);
+        Tr = __ldg(p.cu + row + 1) - tok0;
+      }
+      const bool warp_live = (m * 128 + qd * 32) < Tr;    // warp-uniform: any real query row in this warp?
       mbar_wait(smem_u32(&s_full[g]), n & 1);
       if (qd == 0) AP_TRACE(k, 4);
       tc_fence_after();
@@ -307,19 +318,19 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       if (warp_live) {
         // ViT: keys [0, n_fast) are all live (masked keys keep their exact-0 logit) -> no per-element selects;
         // the chunk holding the T boundary (and every BERT chunk) takes the masked variant.
-        const int n_fast = (MODE == AGB_MASK_MUL0) ? (T / 64) * 64 : 0;
+        const int n_fast = (MODE != AGB_MASK_NEGINF) ? (Tr / 64) * 64 : 0;
         // pass 1: row maximum
         float mx = -INFINITY;
         int c0 = 0;
         for (; c0 < n_fast; c0 += 64) mx = ap_max_chunk<64, false>(lane_addr + c0, mx, 0u, 0u);
         for (; c0 + 64 <= NK; c0 += 64) {
           uint32_t lo, hi;
-          ap_live_bits(mrow, p.words, MODE, T, c0, 64, lo, hi);
+          ap_live_bits(mrow, p.words, MODE, Tr, c0, 64, lo, hi);
           mx = ap_max_chunk<64, true>(lane_addr + c0, mx, lo, hi);
         }
         for (; c0 < NK; c0 += 16) {
           uint32_t lo, hi;
-          ap_live_bits(mrow, p.words, MODE, T, c0, 16, lo, hi);
+          ap_live_bits(mrow, p.words, MODE, Tr, c0, 16, lo, hi);
           mx = ap_max_chunk<16, true>(lane_addr + c0, mx, lo, hi);
         }
         const float m_scaled = mx * scale_log2;
@@ -330,12 +341,12 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           sum += ap_exp_chunk<64, false>(lane_addr + c0, lane_addr + (c0 >> 1), scale_log2, m_scaled, 0u, 0u);
         for (; c0 + 64 <= NK; c0 += 64) {
           uint32_t lo, hi;
-          ap_live_bits(mrow, p.words, MODE, T, c0, 64, lo, hi);
+          ap_live_bits(mrow, p.words, MODE, Tr, c0, 64, lo, hi);
           sum += ap_exp_chunk<64, true>(lane_addr + c0, lane_addr + (c0 >> 1), scale_log2, m_scaled, lo, hi);
         }
         for (; c0 < NK; c0 += 16) {
           uint32_t lo, hi;
-          ap_live_bits(mrow, p.words, MODE, T, c0, 16, lo, hi);
+          ap_live_bits(mrow, p.words, MODE, Tr, c0, 16, lo, hi);
           sum += ap_exp_chunk<16, true>(lane_addr + c0, lane_addr + (c0 >> 1), scale_log2, m_scaled, lo, hi);
         }
         tmem_wait_st();
@@ -358,8 +369,8 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       if (qd == 0) AP_TRACE(k, 7);
       if (warp_live) {
         const int tq = m * 128 + r;
-        if (tq < T) {
-          bf16* dst = p.ctx + ((long long)row * T + tq) * H + head * AP_D;
+        if (tq < Tr) {
+          bf16* dst = p.ctx + ((MODE == AP_MODE_VARLEN ? (long long)tok0 : (long long)row * T) + tq) * H + head * AP_D;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             uint4 w;
@@ -385,16 +396,16 @@ static int g_attention_variant = 0;   // 0 auto (pipelined), 1 first-generation 
 void set_attention_variant(int v) { g_attention_variant = v; }
 int get_attention_variant() { return g_attention_variant; }
 
-int attention_pipe(const bf16* qkv, const uint32_t* mask, int words, int rows, int share, int T, int H, int heads,
-                   int mode, bf16* ctx, cudaStream_t stream) {
-  if (g_attention_variant == 1) return AGB_ERR_UNSUPPORTED;
-  const int qrows = rows / share;
+// T = sequence length (fixed layout) or an upper bound of the row lengths (packed layout, cu != nullptr)
+static int attention_pipe_launch(const bf16* qkv, const uint32_t* mask, int words, int rows, int share, int T, int H,
+                                 int heads, int mode, bf16* ctx, const int* cu, int total_tokens, cudaStream_t stream) {
   AttPipeParams p;
   p.mask = mask; p.words = words; p.rows = rows; p.T = T; p.H = H; p.heads = heads; p.mode = mode;
   p.NK = (T + 15) / 16 * 16;
   p.units = rows * heads;
   p.mtiles = (T + 127) / 128;
   p.share = share;
+  p.cu = cu;
   p.ctx = ctx;
   p.trace = g_attention_trace;
   // NK <= 256: two softmax groups ping-pong over 2 x 256 TMEM columns, one TMA box per K / V tile, K/V ring of 3 units.
@@ -406,36 +417,57 @@ int attention_pipe(const bf16* qkv, const uint32_t* mask, int words, int rows, i
   p.ring = smem_budget / (2 * p.kvb);
   if (p.ring > AP_KV_RING) p.ring = AP_KV_RING;
   if (p.ring < 1) return AGB_ERR_UNSUPPORTED;
+  // fixed layout: (rows / share, T, 3H); packed layout: one "batch" of total_tokens rows
+  const uint64_t tok_dim = cu ? (uint64_t)total_tokens : (uint64_t)T;
+  const uint64_t batch_dim = cu ? 1 : (uint64_t)(rows / share);
   CUtensorMap tmQ, tmKV;
-  int rc = encode_tmap_3d_bf16(&tmQ, qkv, 3 * (uint64_t)H, T, qrows, (uint64_t)3 * H * 2, (uint64_t)T * 3 * H * 2,
+  int rc = encode_tmap_3d_bf16(&tmQ, qkv, 3 * (uint64_t)H, tok_dim, batch_dim, (uint64_t)3 * H * 2, tok_dim * 3 * H * 2,
                                AP_D, 128, 1);
   if (rc != AGB_OK) return rc;
-  rc = encode_tmap_3d_bf16(&tmKV, qkv, 3 * (uint64_t)H, T, qrows, (uint64_t)3 * H * 2, (uint64_t)T * 3 * H * 2,
+  rc = encode_tmap_3d_bf16(&tmKV, qkv, 3 * (uint64_t)H, tok_dim, batch_dim, (uint64_t)3 * H * 2, tok_dim * 3 * H * 2,
                            AP_D, box_rows, 1);
   if (rc != AGB_OK) return rc;
   const int smem = 1024 + 2 * 16384 + p.ring * 2 * p.kvb + 256;
   static int configured_smem = 0;
   if (smem > configured_smem) {
-    AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<AGB_MASK_MUL0, 2>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<AGB_MASK_NEGINF, 2>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<AGB_MASK_MUL0, 1>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<AGB_MASK_NEGINF, 1>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+#define AP_SET(M_, G_) \
+  AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<M_, G_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))
+    AP_SET(AGB_MASK_MUL0, 2); AP_SET(AGB_MASK_NEGINF, 2); AP_SET(AP_MODE_VARLEN, 2);
+    AP_SET(AGB_MASK_MUL0, 1); AP_SET(AGB_MASK_NEGINF, 1); AP_SET(AP_MODE_VARLEN, 1);
+#undef AP_SET
     configured_smem = smem;
   }
   const int grid = p.units < sm_count() ? p.units : sm_count();
+#define AP_GO(M_, G_) attention_pipe_kernel<M_, G_><<<grid, AP_THREADS, smem, stream>>>(tmQ, tmKV, p)
+  const int kmode = cu ? AP_MODE_VARLEN : mode;
   if (p.groups == 2) {
-    if (mode == AGB_MASK_MUL0) attention_pipe_kernel<AGB_MASK_MUL0, 2><<<grid, AP_THREADS, smem, stream>>>(tmQ, tmKV, p);
-    else                       attention_pipe_kernel<AGB_MASK_NEGINF, 2><<<grid, AP_THREADS, smem, stream>>>(tmQ, tmKV, p);
+    if (kmode == AGB_MASK_MUL0) AP_GO(AGB_MASK_MUL0, 2);
+    else if (kmode == AGB_MASK_NEGINF) AP_GO(AGB_MASK_NEGINF, 2);
+    else AP_GO(AP_MODE_VARLEN, 2);
   } else {
-    if (mode == AGB_MASK_MUL0) attention_pipe_kernel<AGB_MASK_MUL0, 1><<<grid, AP_THREADS, smem, stream>>>(tmQ, tmKV, p);
-    else                       attention_pipe_kernel<AGB_MASK_NEGINF, 1><<<grid, AP_THREADS, smem, stream>>>(tmQ, tmKV, p);
+    if (kmode == AGB_MASK_MUL0) AP_GO(AGB_MASK_MUL0, 1);
+    else if (kmode == AGB_MASK_NEGINF) AP_GO(AGB_MASK_NEGINF, 1);
+    else AP_GO(AP_MODE_VARLEN, 1);
   }
+#undef AP_GO
   AGB_CHECK_CUDA(cudaGetLastError());
   return AGB_OK;
+}
+
+int attention_pipe(const bf16* qkv, const uint32_t* mask, int words, int rows, int share, int T, int H, int heads,
+                   int mode, bf16* ctx, cudaStream_t stream) {
+  if (g_attention_variant == 1) return AGB_ERR_UNSUPPORTED;
+  return attention_pipe_launch(qkv, mask, words, rows, share, T, H, heads, mode, ctx, nullptr, 0, stream);
+}
+
+// Packed variable-length rows (masked-token dropping): plain attention inside each segment [cu[r], cu[r+1]).
+int attention_varlen(const bf16* qkv, const int* cu, int rows, int max_len, int total_tokens, int H, int heads, bf16* ctx,
+                     cudaStream_t stream) {
+  AGB_REQUIRE(rows >= 0 && max_len > 0 && max_len <= 512 && heads > 0 && H == heads * AP_D, "varlen attention shape");
+  if (rows == 0 || total_tokens == 0) return AGB_OK;
+  AGB_REQUIRE(qkv && cu && ctx, "null pointer");
+  AGB_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(ctx) & 15) == 0, "alignment");
+  return attention_pipe_launch(qkv, nullptr, 0, rows, 1, max_len, H, heads, AGB_MASK_NEGINF, ctx, cu, total_tokens, stream);
 }
 
 }  // namespace agb

@@ -209,6 +209,42 @@ rank_masks_kernel(const float* __restrict__ scores, uint64_t seed, uint64_t offs
   }
 }
 
+// Masked-token dropping for BERT-style (additive -inf) masks: a masked token has probability 0 as a key in every
+// block and the head reads only token 0, so masked tokens cannot influence the surrogate output (SURVEY.md 8a-a8 /
+// 8f-3).  The kept tokens of each row are packed back to back; these two kernels build the packing.
+//   counts[r]            = number of kept tokens of row r (bits < T)
+//   src[cu[r] + k]       = (r / S) * T + (position of the k-th kept token): row of the per-input embedding to gather
+__global__ void mask_counts_kernel(const uint32_t* __restrict__ packed, int rows, int words, int T, int* __restrict__ counts) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  int c = 0;
+  for (int w = 0; w < words; ++w) {
+    uint32_t bits = packed[(long long)r * words + w];
+    const int base = w * 32;
+    if (base >= T) bits = 0;
+    else if (T - base < 32) bits &= (1u << (T - base)) - 1u;
+    c += __popc(bits);
+  }
+  counts[r] = c;
+}
+
+__global__ void packed_token_index_kernel(const uint32_t* __restrict__ packed, int rows, int words, int T, int S,
+                                          const int* __restrict__ cu, long long* __restrict__ src) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // one warp per row
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  int out = cu[r];
+  const long long base_row = (long long)(r / S) * T;
+  for (int w = 0; w < words; ++w) {
+    uint32_t bits = packed[(long long)r * words + w];
+    const int base = w * 32;
+    if (base >= T) bits = 0;
+    else if (T - base < 32) bits &= (1u << (T - base)) - 1u;
+    if ((bits >> lane) & 1u) src[out + __popc(bits & ((1u << lane) - 1u))] = base_row + base + lane;
+    out += __popc(bits);
+  }
+}
+
 static inline int blocks_for(long long n, int threads) { return (int)((n + threads - 1) / threads); }
 
 int pack_masks_i64(const int64_t* mask, int rows, int n, int prepend_cls, uint32_t* packed, int words,
@@ -279,6 +315,25 @@ int rank_masks(const float* scores, int use_philox, uint64_t seed, uint64_t offs
     rank_masks_kernel<1><<<rows, 256, smem, st>>>(nullptr, seed, offset, n, stops, nstops, mask_base, packed, words, dense);
   else
     rank_masks_kernel<0><<<rows, 256, smem, st>>>(scores, 0, 0, n, stops, nstops, mask_base, packed, words, dense);
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+int mask_counts(const uint32_t* packed, int rows, int words, int T, int* counts, cudaStream_t st) {
+  AGB_REQUIRE(rows >= 0 && words > 0 && T > 0 && words * 32 >= T, "mask shape");
+  if (rows == 0) return AGB_OK;
+  AGB_REQUIRE(packed && counts, "null pointer");
+  mask_counts_kernel<<<blocks_for(rows, 128), 128, 0, st>>>(packed, rows, words, T, counts);
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+int packed_token_index(const uint32_t* packed, int rows, int words, int T, int S, const int* cu, long long* src,
+                       cudaStream_t st) {
+  AGB_REQUIRE(rows >= 0 && words > 0 && T > 0 && S >= 1 && words * 32 >= T, "mask shape");
+  if (rows == 0) return AGB_OK;
+  AGB_REQUIRE(packed && cu && src, "null pointer");
+  packed_token_index_kernel<<<blocks_for((long long)rows * 32, 256), 256, 0, st>>>(packed, rows, words, T, S, cu, src);
   AGB_CHECK_CUDA(cudaGetLastError());
   return AGB_OK;
 }

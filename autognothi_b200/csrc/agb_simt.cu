@@ -224,7 +224,7 @@ __global__ void cls_attention_kernel(const TIO* __restrict__ q, long long ldq, c
 __global__ void __launch_bounds__(128)
 cls_attention_d64_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restrict__ kv, long long ldkv, int k_off,
                          int v_off, const uint32_t* __restrict__ mask, int words, int T, int heads, int mode,
-                         bf16* __restrict__ ctx, long long ldc) {
+                         bf16* __restrict__ ctx, long long ldc, const int* __restrict__ cu) {
   extern __shared__ float sc_all[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int row = blockIdx.y, head = blockIdx.x * nw + warp;
@@ -232,8 +232,10 @@ cls_attention_d64_kernel(const bf16* __restrict__ q, long long ldq, const bf16* 
   float* sq = sc_all + warp * (64 + ((T + 3) & ~3));   // [64] the query (16-byte aligned), then [T] probabilities
   float* sc = sq + 64;
   const bf16* qp = q + (long long)row * ldq + head * 64;
-  const bf16* kvr = kv + (long long)row * T * ldkv;
-  const uint32_t* mrow = mask + (long long)row * words;
+  // packed rows (cu != nullptr): this row's tokens are kv rows [cu[row], cu[row+1]) and every one is a live key
+  const bf16* kvr = kv + (cu ? (long long)cu[row] : (long long)row * T) * ldkv;
+  const uint32_t* mrow = cu ? nullptr : mask + (long long)row * words;
+  if (cu) T = cu[row + 1] - cu[row];
   {
     const uint32_t w = *reinterpret_cast<const uint32_t*>(qp + 2 * lane);
     sq[2 * lane] = bf16_lo(w);
@@ -257,7 +259,7 @@ cls_attention_d64_kernel(const bf16* __restrict__ q, long long ldq, const bf16* 
       a = fmaf(q1.z, bf16_lo(kk[c].w), a); a = fmaf(q1.w, bf16_hi(kk[c].w), a);
     }
     float sv = a * 0.125f;
-    const uint32_t keep = (__ldg(mrow + (j >> 5)) >> (j & 31)) & 1u;
+    const uint32_t keep = mrow ? ((__ldg(mrow + (j >> 5)) >> (j & 31)) & 1u) : 1u;
     if (mode == AGB_MASK_MUL0) sv = keep ? sv : 0.f;
     else sv = keep ? sv : -INFINITY;
     sc[j] = sv;
@@ -303,7 +305,7 @@ int cls_attention(const void* q, long long ldq, const void* kv, long long ldkv, 
     const size_t smem64 = (size_t)nw * (64 + ((T + 3) & ~3)) * sizeof(float);
     cls_attention_d64_kernel<<<grid, nw * 32, smem64, st>>>(static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(kv), ldkv,
                                                             k_off, v_off, mask, words, T, heads, mode,
-                                                            static_cast<bf16*>(ctx), ldc);
+                                                            static_cast<bf16*>(ctx), ldc, nullptr);
     AGB_CHECK_CUDA(cudaGetLastError());
     return AGB_OK;
   }
@@ -339,6 +341,25 @@ int attention_simt(const void* qkv, int io_bf16, const uint32_t* mask, int words
   else
     attention_simt_kernel<float, 4><<<grid, nw * 32, smem, st>>>(static_cast<const float*>(qkv), mask, words, T, H,
                                                                  heads, mode, static_cast<float*>(ctx));
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+int cls_attention_varlen(const void* q, long long ldq, const void* kv, long long ldkv, int k_off, int v_off, int io_bf16,
+                         const int* cu, int rows, int max_len, int H, int heads, void* ctx, long long ldc, cudaStream_t st) {
+  AGB_REQUIRE(rows >= 0 && max_len > 0 && heads > 0, "attention shape");
+  AGB_REQUIRE(io_bf16 && H == heads * 64, "packed CLS attention: bf16, head dim 64");
+  AGB_REQUIRE((ldq % 2) == 0 && (ldkv % 8) == 0 && (k_off % 8) == 0 && (v_off % 8) == 0 && (ldc % 2) == 0 &&
+                  (reinterpret_cast<uintptr_t>(kv) & 15) == 0, "alignment");
+  if (rows == 0) return AGB_OK;
+  AGB_REQUIRE(q && kv && cu && ctx, "null pointer");
+  AGB_REQUIRE(rows <= 65535, "grid limits (chunk the rows)");
+  const int nw = 4;
+  dim3 grid((heads + nw - 1) / nw, rows);
+  const size_t smem64 = (size_t)nw * (64 + ((max_len + 3) & ~3)) * sizeof(float);
+  cls_attention_d64_kernel<<<grid, nw * 32, smem64, st>>>(static_cast<const bf16*>(q), ldq, static_cast<const bf16*>(kv), ldkv,
+                                                          k_off, v_off, nullptr, 0, max_len, heads, AGB_MASK_NEGINF,
+                                                          static_cast<bf16*>(ctx), ldc, cu);
   AGB_CHECK_CUDA(cudaGetLastError());
   return AGB_OK;
 }

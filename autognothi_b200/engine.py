@@ -206,6 +206,10 @@ def bert_layer(pol: _Policy, lw: LayerWeights, x: Tensor, xa: Optional[Tensor], 
 CLS_ONLY_LAST_BLOCK = True
 # Exact work-skipping, first block: LayerNorm + QKV projection once per input instead of once per coalition (bf16 path).
 SHARE_FIRST_BLOCK = True
+# Exact work-skipping for additive (-inf) masks (BERT surrogate / classifier heads, bf16 path): masked tokens are never
+# attended to and the head reads only token 0, so only the kept tokens of every row are carried through the encoder
+# (packed back to back; variable-length attention).  SURVEY.md 8f-3.
+DROP_MASKED_TOKENS = True
 
 
 def last_block_cls_only(pol: _Policy, lw: LayerWeights, vit: bool, x: Tensor, xa: Optional[Tensor], x16: Optional[Tensor],
@@ -246,6 +250,38 @@ def last_block_cls_only(pol: _Policy, lw: LayerWeights, vit: bool, x: Tensor, xa
     return y, ya
 
 
+def run_bert_packed(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tensor, S: int) -> Tuple[Tensor, Tensor]:
+    """BERT surrogate / classifier evaluation on the kept tokens only -> (x_cls (rows, H) fp32, activation copy).
+    Every block but the last runs on the packed tokens; the last one on the CLS query (see last_block_cls_only)."""
+    T = n_players_of(cfg) + 1
+    H, heads, eps = cfg.hidden_size, cfg.num_attention_heads, cfg.layer_norm_eps
+    rows = masks.shape[0]
+    cu, src, total = ops.pack_kept_tokens(masks, T, S)
+    x_img = embed(bw, cfg, pol, xs, 1).reshape(-1, H)                       # (B*T, H): embeddings once per input
+    x = x_img.index_select(0, src)                                           # (total, H) packed residual stream
+    xa = pol.act(x)
+    for lw in bw.layers[:-1]:
+        qkv = pol.linear(xa, lw.wqkv, lw.bqkv)
+        ctx = ops.attention_varlen(qkv, cu, T, heads)
+        x, xa = bert_layer(pol, lw, x, xa, masks, T, heads, eps, ctx=ctx)
+    lw = bw.layers[-1]
+    first = cu[:-1].long()                                                   # packed index of every row's CLS token
+    x_cls, xa_cls = x.index_select(0, first), xa.index_select(0, first)
+    kv = pol.linear(xa, lw.wqkv[H:], lw.bqkv[H:])
+    q = pol.linear(xa_cls, lw.wqkv[:H], lw.bqkv[:H])
+    ctx = ops.cls_attention_varlen(q, kv, 0, H, cu, T, heads)
+    a = pol.linear(ctx, lw.wo, lw.bo, residual=x_cls, out_f32=True)
+    if lw.ln1 is not None:
+        aa, a = pol.ln(a, lw.ln1[0], lw.ln1[1], eps, want_f32=True)
+    else:
+        aa = pol.act(a)
+    ff = pol.linear(aa, lw.w1, lw.b1, act=ops.ACT_GELU)
+    y = pol.linear(ff, lw.w2, lw.b2, residual=a, out_f32=True)
+    ya, y = pol.ln(y, lw.ln2[0], lw.ln2[1], eps, want_f32=True)
+    assert y.shape[0] == rows
+    return y, ya
+
+
 def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tensor, S: int, cls_only: bool = False
                  ) -> Tuple[Tensor, Optional[Tensor]]:
     """-> (x (rows*T, H) fp32 after the encoder stack [ViT: BEFORE the final LayerNorm], activation copy | None).
@@ -253,6 +289,9 @@ def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tens
     T = n_players_of(cfg) + 1
     H, heads, eps = cfg.hidden_size, cfg.num_attention_heads, cfg.layer_norm_eps
     cls_only = cls_only and CLS_ONLY_LAST_BLOCK and len(bw.layers) > 0
+    if (cls_only and not bw.vit and DROP_MASKED_TOKENS and pol.bf16 and T <= 512 and H == heads * 64
+            and all(lw.ln2 is not None for lw in bw.layers)):
+        return run_bert_packed(bw, cfg, pol, xs, masks, S)
     full = bw.layers[:-1] if cls_only else bw.layers
     fused = bw.vit and FUSE_LAYERNORM and pol.bf16 and H % 256 == 0 and all(lw.fold() is not None for lw in bw.layers)
     # First-block sharing (exact): before the first attention all S coalitions of an input hold identical activations,

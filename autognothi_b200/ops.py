@@ -317,6 +317,47 @@ def cls_attention(q: Tensor, kv: Tensor, k_off: int, v_off: int, packed_mask: Te
     return ctx
 
 
+def pack_kept_tokens(packed_mask: Tensor, T: int, S: int) -> Tuple[Tensor, Tensor, int]:
+    """Masked-token dropping (additive masks): -> (cu (rows+1,) int32 exclusive prefix of the kept-token counts,
+    src (total,) int64 = row of the per-input (B*T, H) embedding each packed token comes from, total kept tokens).
+    One device->host read of the total (buffer sizes and GEMM shapes depend on it)."""
+    assert packed_mask.dtype == torch.int32 and packed_mask.is_contiguous()
+    rows, words = packed_mask.shape
+    counts = torch.empty((rows,), dtype=torch.int32, device=packed_mask.device)
+    nat.call("agb_mask_counts", nat.ptr(packed_mask), rows, words, T, nat.ptr(counts), nat.stream())
+    cu = torch.zeros((rows + 1,), dtype=torch.int32, device=packed_mask.device)
+    torch.cumsum(counts, 0, out=cu[1:])
+    total = int(cu[-1].item())
+    src = torch.empty((total,), dtype=torch.int64, device=packed_mask.device)
+    nat.call("agb_packed_token_index", nat.ptr(packed_mask), rows, words, T, S, nat.ptr(cu), nat.ptr(src), nat.stream())
+    return cu, src, total
+
+
+def attention_varlen(qkv: Tensor, cu: Tensor, max_len: int, heads: int) -> Tensor:
+    """qkv (total_tokens, 3H) bf16 packed rows, row r = tokens [cu[r], cu[r+1]) -> ctx (total_tokens, H)."""
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and cu.dtype == torch.int32
+    total, H3 = qkv.shape
+    H = H3 // 3
+    ctx = torch.empty((total, H), dtype=torch.bfloat16, device=qkv.device)
+    nat.NEXT_META = None
+    nat.call("agb_attention_bf16_varlen", nat.ptr(qkv), nat.ptr(cu), cu.numel() - 1, max_len, total, H, heads, nat.ptr(ctx),
+             nat.stream())
+    return ctx
+
+
+def cls_attention_varlen(q: Tensor, kv: Tensor, k_off: int, v_off: int, cu: Tensor, max_len: int, heads: int) -> Tensor:
+    """CLS-query attention over packed rows: q (rows, H), kv (total_tokens, ld) -> ctx (rows, H) bf16."""
+    assert q.dtype == torch.bfloat16 and kv.dtype == torch.bfloat16 and q.stride(1) == 1 and kv.stride(1) == 1
+    rows, H = q.shape
+    ctx = torch.empty((rows, H), dtype=torch.bfloat16, device=q.device)
+    step = 65535
+    for r0 in range(0, rows, step):
+        r1 = min(rows, r0 + step)
+        nat.call("agb_cls_attention_varlen", nat.ptr(q[r0:r1]), q.stride(0), nat.ptr(kv), kv.stride(0), k_off, v_off, 1,
+                 nat.ptr(cu[r0:r1 + 1]), r1 - r0, max_len, H, heads, nat.ptr(ctx[r0:r1]), H, nat.stream())
+    return ctx
+
+
 # ------------------------------------------------------------------------------------------------
 # explainer head / loss
 # ------------------------------------------------------------------------------------------------

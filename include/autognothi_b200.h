@@ -110,6 +110,18 @@ int agb_rank_masks(const float* scores, int use_philox, uint64_t seed, uint64_t 
                    const int* stops, int nstops, int mask_base, uint32_t* packed, int words, int64_t* dense,
                    void* stream);
 
+/* Masked-token dropping for additive (-inf) masks (reference models/vanilla_bert.py:520-523): a masked
+ * token is never attended to and the surrogate head reads only token 0, so masked tokens cannot influence the output and
+ * each row's kept tokens may be packed back to back (exact).  counts[r] = kept tokens of row r among the first T bits;
+ * src[cu[r] + k] = (r / S) * T + position of the k-th kept token (cu = exclusive prefix sum of counts, rows + 1 ints). */
+int agb_mask_counts(const uint32_t* packed, int rows, int words, int T, int* counts, void* stream);
+int agb_packed_token_index(const uint32_t* packed, int rows, int words, int T, int S, const int* cu, int64_t* src,
+                           void* stream);
+/* Attention over packed variable-length rows: qkv (total_tokens, 3H) bf16, row r = tokens [cu[r], cu[r+1]) (every packed
+ * token is a live key), max_len >= every row length (<= 512); ctx (total_tokens, H).  tcgen05 kernel, head dim 64. */
+int agb_attention_bf16_varlen(const void* qkv, const int* cu, int rows, int max_len, int total_tokens, int H, int heads,
+                              void* ctx, void* stream);
+
 /* ---- row kernels ---------------------------------------------------------------------------- */
 /* nn.LayerNorm over the last dim (reference models/vanilla_vit.py:94,213,369,373; vanilla_bert.py:
  * 318,548,596).  x fp32 or bf16 [rows, in_stride]; writes bf16 and/or fp32 [rows, out_stride]. */
@@ -160,6 +172,10 @@ int agb_masked_attention_bf16_shared(const void* qkv, const uint32_t* mask, int 
 int agb_cls_attention(const void* q, long long ldq, const void* kv, long long ldkv, int k_off, int v_off, int io_is_bf16,
                       const uint32_t* mask, int words, int rows, int T, int H, int heads, int mode, void* ctx,
                       long long ldc, void* stream);
+/* Same over packed variable-length rows (every packed token is a live key): kv rows [cu[r], cu[r+1]) belong to row r. */
+int agb_cls_attention_varlen(const void* q, long long ldq, const void* kv, long long ldkv, int k_off, int v_off,
+                             int io_is_bf16, const int* cu, int rows, int max_len, int H, int heads, void* ctx,
+                             long long ldc, void* stream);
 
 /* Kernel selection for agb_masked_attention_bf16 (diagnostics): 0 = automatic (pipelined, one CTA per SM),
  * 1 = first-generation kernel.  Returns the previous setting. */

@@ -485,6 +485,51 @@ def test_first_block_projection_sharing_is_exact(agb, golden_dir, name):
     np.testing.assert_allclose(_np(p_share), g["v_s"], atol=2e-2)
 
 
+@pytest.mark.parametrize("name", ["bert_mini", "bert_base_128", "bert_mini_512"])
+def test_bert_masked_token_dropping_is_exact(agb, golden_dir, name):
+    """Additive-mask semantics: masked tokens are never attended to and the head reads token 0 only, so carrying just
+    the kept tokens (packed, variable-length attention) gives the same probabilities."""
+    from autognothi_b200 import engine
+    g = _load(golden_dir, f"model_{name}.npz")
+    B, S, n = (int(v) for v in g["meta"])
+    rec, cfgd, srg, exp = _build(name, "bf16")
+    xs = torch.from_numpy(synth.inputs(cfgd, B, seed=0)).to(DEV)
+    masks = torch.from_numpy(g["masks"].astype(np.int64)).to(DEV).reshape(B, S, n)
+    edge = masks.clone()
+    edge[0, 0, :] = 0            # only CLS kept
+    edge[0, 1, :] = 1            # everything kept
+    for m in (masks, edge):
+        try:
+            with torch.no_grad():
+                engine.DROP_MASKED_TOKENS = True
+                p_drop, _ = rec.fw_surrogate(srg, xs, m)
+                engine.DROP_MASKED_TOKENS = False
+                p_full, _ = rec.fw_surrogate(srg, xs, m)
+        finally:
+            engine.DROP_MASKED_TOKENS = True
+        assert np.isfinite(_np(p_drop)).all()
+        np.testing.assert_allclose(_np(p_drop), _np(p_full), atol=3e-3)
+    with torch.no_grad():
+        p_ref, _ = rec.fw_surrogate(srg, xs, masks)
+    np.testing.assert_allclose(_np(p_ref), g["v_s"], atol=2e-2)
+
+
+def test_pack_kept_tokens_vs_numpy(agb):
+    rng = np.random.RandomState(0)
+    rows, T, S = 12, 130, 3
+    dense = (rng.rand(rows, T) > 0.5).astype(np.int64)
+    dense[:, 0] = 1
+    dense[3, 1:] = 0
+    dense[4, :] = 1
+    packed = agb.pack_masks(torch.from_numpy(dense[:, 1:]).to(DEV), prepend_cls=True)
+    cu, src, total = agb.pack_kept_tokens(packed, T, S)
+    counts = dense.sum(1)
+    np.testing.assert_array_equal(cu.cpu().numpy(), np.concatenate([[0], np.cumsum(counts)]))
+    want = np.concatenate([(r // S) * T + np.nonzero(dense[r])[0] for r in range(rows)])
+    assert total == want.size
+    np.testing.assert_array_equal(src.cpu().numpy(), want)
+
+
 def test_final_coherency(agb):
     """The reference's only numerical self-check (scripts/train_all.py:166-218): the bundled Final model
     agrees with the separate classifier / surrogate / explainer on the same input."""
