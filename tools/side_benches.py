@@ -9,7 +9,6 @@ import torch
 sys.path.insert(0, __file__.rsplit("/", 2)[0])
 from autognothi_b200 import ops  # noqa: E402
 from autognothi_b200.models import shapley as ash  # noqa: E402
-from oracle import configs as ocfg  # noqa: E402  (test infrastructure: config tables only)
 
 
 def timed(fn, iters=5, warm=2):
@@ -46,7 +45,11 @@ def bert_eval():
     from autognothi_b200.recipes.vanilla_bert import vanilla_bert_recipe
     dev = torch.device("cuda:0")
     rec = vanilla_bert_recipe()
-    cfgd = dict(ocfg.get_config("bert_base_128"))
+    # reference experiments/bert_base_tayp_vanilla/.hparams.json:14-30 with max_position_embeddings = 128
+    cfgd = dict(attention_probs_dropout_prob=0.1, explainer_attn_num_layers=1, explainer_head_hidden_size=3072,
+                explainer_normalize=True, hidden_dropout_prob=0.1, hidden_size=768, intermediate_size=3072, layer_norm_eps=1e-12,
+                max_position_embeddings=128, num_attention_heads=12, num_hidden_layers=12, num_labels=2, pad_token_id=0,
+                type_vocab_size=2, vocab_size=30522)
     cfg = rec.t_config(**cfgd)
     n = rec.n_players(cfg)
     torch.manual_seed(3407)
