@@ -7,68 +7,84 @@
 // come out, all on the device and in float64:
 //     y = link(p) - link(f0),  delta = link(f) - link(f0)
 //     E = Z[:, :-1] - Z[:, -1:],  y~ = y - Z[:, -1:] delta           (efficiency constraint eliminated)
-//     A = E^T W E  ((d-1) x (d-1) Gram),  R = E^T W y~                (kernel 1: tiled accumulation)
-//     A = L L^T (Cholesky), phi[:-1] = A^-1 R, phi[-1] = delta - sum  (kernel 2: one CTA per sample)
+//     A = E^T W E  ((d-1) x (d-1) Gram),  R = E^T W y~                (kernel 1: register-tiled fp64 accumulation)
+//     A = L L^T (Cholesky), phi[:-1] = A^-1 R, phi[-1] = delta - sum  (kernel 2: blocked, one CTA per sample)
 // shap's optional l1_reg feature pre-selection is NOT part of this path (documented in oracle/kernelshap.py).
 // Bytes per sample (S=2048, d=127, C=2): packed Z 32 KB + p 16 KB in, A 127 KB out/in, phi 2 KB out.
 #include "agb_common.cuh"
 
 namespace agb {
 
-constexpr int KS_TILE = 32;
+constexpr int KG_T = 64;         // Gram tile edge
+constexpr int KG_CH = 32;        // coalitions staged per shared-memory chunk
+constexpr int KG_THREADS = 128;  // 8 x 16 threads, 8 x 4 accumulators each
 
 __device__ __forceinline__ double ks_link(double p, int link) {
   return link ? log(p / (1.0 - p)) : p;
 }
 
-// grid: (tiles_j * tiles_k [+ rhs tiles], B).  Each CTA owns a 32x32 tile of A (or a 32 x C strip of R) and
-// streams the S coalitions through shared memory in chunks.
-__global__ void __launch_bounds__(KS_TILE * KS_TILE)
+// grid: (lower-triangle 64x64 tiles of A + one 64 x C strip of R per tile row, B).  fp64 FMA-pipe bound: the chunk is
+// staged as doubles (w_s * E[s,j] and E[s,k]); each thread keeps an 8 x 4 block of the tile in registers, so one
+// shared-memory wavefront feeds about five DFMAs.  E takes values in {-1, 0, 1}; columns >= d-1 are zero.
+__global__ void __launch_bounds__(KG_THREADS)
 kernelshap_gram_kernel(const uint32_t* __restrict__ Z, int words, const double* __restrict__ w,
                        const double* __restrict__ probs, const double* __restrict__ fx,
                        const double* __restrict__ f0, int S, int d, int C, int link, double* __restrict__ A,
                        double* __restrict__ R) {
   const int n = d - 1;
-  const int tiles = (n + KS_TILE - 1) / KS_TILE;
+  const int tiles = (n + KG_T - 1) / KG_T;
+  const int n_lower = tiles * (tiles + 1) / 2;
   const int b = blockIdx.y;
   const int tile = blockIdx.x;
-  const bool is_rhs = tile >= tiles * tiles;
-  const int tj = is_rhs ? (tile - tiles * tiles) : tile / tiles;
-  const int tk = is_rhs ? 0 : tile % tiles;
-  if (!is_rhs && tk > tj) return;  // symmetric: lower triangle only, mirrored by the solve kernel's reads
-  const int tx = threadIdx.x % KS_TILE, ty = threadIdx.x / KS_TILE;
-  const int j = tj * KS_TILE + ty;      // row of A / row of R
-  const int k = tk * KS_TILE + tx;      // col of A, or class index for the rhs strip
-  constexpr int CH = 96;                // coalitions per shared-memory chunk
-  __shared__ float ej[CH][KS_TILE + 1];   // E[s, j-tile] in {-1,0,1}
-  __shared__ float ek[CH][KS_TILE + 1];   // E[s, k-tile]
-  __shared__ double ws[CH];
-  __shared__ double yt[CH][16];           // y~[s, c] for the rhs strip (C <= 16)
+  const bool is_rhs = tile >= n_lower;
+  int tj = 0, tk = 0;                      // tile row, tile column (tk <= tj: lower triangle, symmetric matrix)
+  if (is_rhs) {
+    tj = tk = tile - n_lower;
+  } else {
+    while ((tj + 1) * (tj + 2) / 2 <= tile) ++tj;
+    tk = tile - tj * (tj + 1) / 2;
+  }
+  __shared__ __align__(16) double wej[KG_CH][KG_T];   // w_s * E[s, j-tile]
+  __shared__ __align__(16) double ek[KG_CH][KG_T];    // E[s, k-tile]
+  __shared__ double yt[KG_CH][16];                    // y~[s, c] for the rhs strip (C <= 16)
+  const int t = threadIdx.x;
+  const int ty = t >> 4, tx = t & 15;
   const uint32_t* Zb = Z + (long long)b * S * words;
   const int last = d - 1;
-  double acc = 0.0;
-  for (int s0 = 0; s0 < S; s0 += CH) {
+  double acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[i][q] = 0.0;
+  if (is_rhs)
+    for (int e = t; e < KG_CH * 16; e += KG_THREADS) yt[e >> 4][e & 15] = 0.0;
+  for (int s0 = 0; s0 < S; s0 += KG_CH) {
     __syncthreads();
-    for (int e = threadIdx.x; e < CH * KS_TILE; e += blockDim.x) {
-      const int ss = e / KS_TILE, c = e % KS_TILE;
+    for (int e = t; e < KG_CH * 8; e += KG_THREADS) {
+      const int ss = e >> 3, g = e & 7;       // coalition in the chunk, group of 8 columns
       const int s = s0 + ss;
-      float vj = 0.f, vk = 0.f;
-      if (s < S) {
+      const int cj = tj * KG_T + g * 8, ck = tk * KG_T + g * 8;
+      uint32_t bj = 0, bk = 0;
+      int zl = 0;
+      double wv = 0.0;
+      const bool live = s < S;
+      if (live) {
         const uint32_t* zr = Zb + (long long)s * words;
-        const int zl = (zr[last >> 5] >> (last & 31)) & 1;
-        const int fj = tj * KS_TILE + c, fk = tk * KS_TILE + c;
-        if (fj < n) vj = (float)((int)((zr[fj >> 5] >> (fj & 31)) & 1) - zl);
-        if (fk < n) vk = (float)((int)((zr[fk >> 5] >> (fk & 31)) & 1) - zl);
+        zl = (zr[last >> 5] >> (last & 31)) & 1;
+        wv = w[(long long)b * S + s];
+        if (cj < d) bj = (zr[cj >> 5] >> (cj & 31)) & 0xFFu;
+        if (ck < d) bk = (zr[ck >> 5] >> (ck & 31)) & 0xFFu;
       }
-      ej[ss][c] = vj;
-      ek[ss][c] = vk;
-    }
-    for (int ss = threadIdx.x; ss < CH; ss += blockDim.x) {
-      const int s = s0 + ss;
-      ws[ss] = (s < S) ? w[(long long)b * S + s] : 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int evj = (live && cj + q < n) ? (int)((bj >> q) & 1u) - zl : 0;
+        const int evk = (live && ck + q < n) ? (int)((bk >> q) & 1u) - zl : 0;
+        wej[ss][g * 8 + q] = wv * (double)evj;
+        ek[ss][g * 8 + q] = (double)evk;
+      }
     }
     if (is_rhs) {
-      for (int e = threadIdx.x; e < CH * C; e += blockDim.x) {
+      for (int e = t; e < KG_CH * C; e += KG_THREADS) {
         const int ss = e / C, c = e % C;
         const int s = s0 + ss;
         double v = 0.0;
@@ -85,76 +101,250 @@ kernelshap_gram_kernel(const uint32_t* __restrict__ Z, int words, const double* 
     }
     __syncthreads();
     if (!is_rhs) {
-#pragma unroll 8
-      for (int ss = 0; ss < CH; ++ss) acc += ws[ss] * (double)(ej[ss][ty] * ek[ss][tx]);
-    } else if (tx < C) {
-#pragma unroll 8
-      for (int ss = 0; ss < CH; ++ss) acc += ws[ss] * (double)ej[ss][ty] * yt[ss][tx];
+#pragma unroll 4
+      for (int ss = 0; ss < KG_CH; ++ss) {
+        const double2* pa = reinterpret_cast<const double2*>(&wej[ss][ty * 8]);
+        const double2 a01 = pa[0], a23 = pa[1], a45 = pa[2], a67 = pa[3];
+        const double av[8] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y, a67.x, a67.y};
+        double bv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bv[q] = ek[ss][tx + 16 * q];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[i][q] = fma(av[i], bv[q], acc[i][q]);
+      }
+    } else {
+      // rhs strip: thread (row j = t % 64, class half = t / 64) accumulates 8 classes in acc[0..7][0]
+      const int jl = t & 63, c0 = (t >> 6) * 8;
+#pragma unroll 4
+      for (int ss = 0; ss < KG_CH; ++ss) {
+        const double a = wej[ss][jl];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c][0] = fma(a, yt[ss][c0 + c], acc[c][0]);
+      }
     }
   }
-  if (j < n) {
-    if (!is_rhs) {
-      if (k < n) A[((long long)b * n + j) * n + k] = acc;
-    } else if (tx < C) {
-      R[((long long)b * n + j) * C + tx] = acc;
+  if (!is_rhs) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = tj * KG_T + ty * 8 + i;
+      if (j >= n) continue;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = tk * KG_T + tx + 16 * q;
+        if (k < n) A[((long long)b * n + j) * n + k] = acc[i][q];
+      }
+    }
+  } else {
+    const int j = tj * KG_T + (t & 63), c0 = (t >> 6) * 8;
+    if (j < n) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c0 + c < C) R[((long long)b * n + j) * C + c0 + c] = acc[c][0];
     }
   }
 }
 
-// One CTA per sample: in-place Cholesky of the lower triangle (right-looking, column by column), forward and
-// backward substitution for the C right-hand sides, then the eliminated feature.  The matrix stays in L1/L2.
-__global__ void __launch_bounds__(256)
+// One CTA per sample: blocked right-looking Cholesky of the lower triangle (32-column panels), with the C right-hand
+// sides carried as C extra rows below the matrix so that the forward substitution L z = R falls out of the panel
+// solves and trailing updates; then a blocked backward substitution L^T x = z and the eliminated feature.
+//   per panel: (1) 32x32 diagonal block factored in shared memory; (2) every row below it solved against the block,
+//   one thread per row, the result kept in shared memory transposed (Pt[c][row]); (3) trailing matrix (and the extra
+//   rows) updated in 64x64 tiles with 4x4 register blocks, read-modify-write in L2.
+constexpr int KC_NB = 32;
+constexpr int KC_LD = KC_NB + 1;
+constexpr int KC_THREADS = 256;
+
+__host__ __device__ inline int kc_ldp(int n, int C) { return ((n + C + 63) / 64) * 64; }
+__host__ __device__ inline size_t kc_smem_doubles(int n, int C) {
+  const size_t panel = (size_t)KC_NB * kc_ldp(n, C);
+  const size_t back = (size_t)n * C + (size_t)(KC_THREADS / 32) * KC_NB * 16;
+  return (size_t)KC_NB * KC_LD + KC_NB + (panel > back ? panel : back);
+}
+
+__global__ void __launch_bounds__(KC_THREADS)
 kernelshap_solve_kernel(double* __restrict__ A, double* __restrict__ R, const double* __restrict__ fx,
                         const double* __restrict__ f0, int d, int C, int link, double* __restrict__ phi,
                         int* __restrict__ info) {
+  extern __shared__ __align__(16) double ks_smem[];
   const int n = d - 1;
   const int b = blockIdx.x;
+  const int t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
   double* a = A + (long long)b * n * n;
   double* r = R + (long long)b * n * C;
-  __shared__ double piv;
+  double* Lkk = ks_smem;                       // [32][33] diagonal block (identity padded)
+  double* invd = Lkk + KC_NB * KC_LD;          // [32] reciprocals of its diagonal
+  double* Pt = invd + KC_NB;                   // [32][ldp] panel, transposed   (16-byte aligned: 1088 doubles before)
+  const int ldp = kc_ldp(n, C);
+  const int next = n + C;                      // rows incl. the right-hand sides
   __shared__ int bad;
-  if (threadIdx.x == 0) bad = 0;
-  __syncthreads();
-  for (int k = 0; k < n; ++k) {
-    if (threadIdx.x == 0) {
-      const double v = a[(long long)k * n + k];
-      if (!(v > 0.0)) { bad = k + 1; piv = 1.0; }
-      else piv = sqrt(v);
-      a[(long long)k * n + k] = piv;
+  if (t == 0) bad = 0;
+  // element (i, j) of the extended matrix: rows >= n are the right-hand sides, stored (n, C) row-major
+  auto at = [&](int i, int j) -> double* { return i < n ? a + (long long)i * n + j : r + (long long)j * C + (i - n); };
+
+  for (int kb = 0; kb < n; kb += KC_NB) {
+    const int nb = min(KC_NB, n - kb);
+    __syncthreads();
+    for (int e = t; e < KC_NB * KC_NB; e += KC_THREADS) {
+      const int i = e >> 5, j = e & 31;
+      double v = (i == j) ? 1.0 : 0.0;
+      if (i < nb && j < nb) v = (j <= i) ? a[(long long)(kb + i) * n + kb + j] : 0.0;
+      Lkk[i * KC_LD + j] = v;
     }
     __syncthreads();
-    const double inv = 1.0 / piv;
-    for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x) a[(long long)i * n + k] *= inv;
+    for (int k = 0; k < nb; ++k) {
+      const double v = Lkk[k * KC_LD + k];
+      const bool ok = v > 0.0;
+      const double piv = ok ? sqrt(v) : 1.0;
+      const double inv = 1.0 / piv;
+      if (!ok && t == 0 && bad == 0) bad = kb + k + 1;
+      double upd[KC_NB * KC_NB / KC_THREADS];
+#pragma unroll
+      for (int u = 0; u < KC_NB * KC_NB / KC_THREADS; ++u) {
+        const int e = t + u * KC_THREADS;
+        const int i = e >> 5, j = e & 31;
+        upd[u] = 0.0;
+        if (j > k && j <= i && i < nb) upd[u] = (Lkk[i * KC_LD + k] * inv) * (Lkk[j * KC_LD + k] * inv);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < KC_NB * KC_NB / KC_THREADS; ++u) {
+        const int e = t + u * KC_THREADS;
+        const int i = e >> 5, j = e & 31;
+        if (j > k && j <= i && i < nb) Lkk[i * KC_LD + j] -= upd[u];
+      }
+      if (t == k) Lkk[k * KC_LD + k] = piv;
+      else if (t > k && t < nb) Lkk[t * KC_LD + k] *= inv;
+      __syncthreads();
+    }
+    for (int e = t; e < KC_NB * KC_NB; e += KC_THREADS) {
+      const int i = e >> 5, j = e & 31;
+      if (i < nb && j <= i) a[(long long)(kb + i) * n + kb + j] = Lkk[i * KC_LD + j];
+    }
+    if (t < KC_NB) invd[t] = 1.0 / Lkk[t * KC_LD + t];
     __syncthreads();
-    // trailing update of the lower triangle: a[i][j] -= a[i][k] * a[j][k],  k < j <= i < n
-    const int m = n - k - 1;
-    for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
-      const int i = k + 1 + e / m, jj = k + 1 + e % m;
-      if (jj <= i) a[(long long)i * n + jj] -= a[(long long)i * n + k] * a[(long long)jj * n + k];
+    const int r0 = kb + nb;
+    const int mext = next - r0;                // rows below the block (matrix rows + right-hand sides)
+    const int m = n - r0;                      // trailing columns
+    for (int row = t; row < mext; row += KC_THREADS) {
+      const int i = r0 + row;
+      double x[KC_NB];
+#pragma unroll
+      for (int c = 0; c < KC_NB; ++c) x[c] = (c < nb) ? *at(i, kb + c) : 0.0;
+#pragma unroll
+      for (int c = 0; c < KC_NB; ++c) {
+        double s = x[c];
+#pragma unroll
+        for (int p = 0; p < c; ++p) s = fma(-x[p], Lkk[c * KC_LD + p], s);
+        x[c] = s * invd[c];
+      }
+#pragma unroll
+      for (int c = 0; c < KC_NB; ++c) {
+        if (c < nb) *at(i, kb + c) = x[c];
+        Pt[c * ldp + row] = x[c];
+      }
+    }
+    __syncthreads();
+    if (m <= 0) continue;
+    const int ty = t >> 4, tx = t & 15;
+    for (int ti = 0; ti < mext; ti += 64) {
+      const int jmax = min(ti + 64, m);        // tiles entirely above the diagonal are skipped
+      for (int tc = 0; tc < jmax; tc += 64) {
+        double acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[i][q] = 0.0;
+#pragma unroll 8
+        for (int c = 0; c < KC_NB; ++c) {
+          const double2* pr = reinterpret_cast<const double2*>(Pt + c * ldp + ti + ty * 4);
+          const double2 r01 = pr[0], r23 = pr[1];
+          const double rv[4] = {r01.x, r01.y, r23.x, r23.y};
+          double cv[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) cv[q] = Pt[c * ldp + tc + tx + 16 * q];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[i][q] = fma(rv[i], cv[q], acc[i][q]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int gi = r0 + ti + ty * 4 + i;
+          if (gi >= next) continue;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int gj = r0 + tc + tx + 16 * q;
+            if (gj < n && (gi >= n || gj <= gi)) *at(gi, gj) -= acc[i][q];
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- backward substitution L^T x = z (z sits in r), 32-row blocks from the bottom up ----
+  double* xs = Pt;                             // x[j][c], (n, C)
+  double* part = Pt + (size_t)n * C;           // [8 warps][32 columns][16 classes] partial dot products
+  const int nblk = (n + KC_NB - 1) / KC_NB;
+  for (int blk = nblk - 1; blk >= 0; --blk) {
+    const int kb = blk * KC_NB;
+    const int nb = min(KC_NB, n - kb);
+    // partial sums over the rows below: warp w takes rows r0 + w, r0 + w + 8, ...; lane = column of the block
+    double pacc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) pacc[c] = 0.0;
+    for (int i = kb + nb + warp; i < n; i += KC_THREADS / 32) {
+      const double lv = (lane < nb) ? a[(long long)i * n + kb + lane] : 0.0;
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        if (c < C) pacc[c] = fma(lv, xs[(size_t)i * C + c], pacc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) part[(warp * KC_NB + lane) * 16 + c] = pacc[c];
+    for (int e = t; e < KC_NB * KC_NB; e += KC_THREADS) {
+      const int i = e >> 5, j = e & 31;
+      double v = (i == j) ? 1.0 : 0.0;
+      if (i < nb && j < nb) v = (j <= i) ? a[(long long)(kb + i) * n + kb + j] : 0.0;
+      Lkk[i * KC_LD + j] = v;
+    }
+    __syncthreads();
+    if (t < KC_NB) invd[t] = 1.0 / Lkk[t * KC_LD + t];
+    __syncthreads();
+    for (int c = warp; c < C; c += KC_THREADS / 32) {      // one warp per class, lane = row of the block
+      double zv = 0.0, xv = 0.0;
+      if (lane < nb) {
+        zv = r[(long long)(kb + lane) * C + c];
+#pragma unroll
+        for (int ww = 0; ww < KC_THREADS / 32; ++ww) zv -= part[(ww * KC_NB + lane) * 16 + c];
+      }
+      for (int q = nb - 1; q >= 0; --q) {
+        const double xq = __shfl_sync(0xffffffffu, zv, q) * invd[q];
+        if (lane == q) xv = xq;
+        if (lane < q) zv = fma(-Lkk[q * KC_LD + lane], xq, zv);
+      }
+      if (lane < nb) xs[(size_t)(kb + lane) * C + c] = xv;
     }
     __syncthreads();
   }
-  // L z = R (forward), L^T x = z (backward); one thread per class, columns are short (n <= 511)
-  if (threadIdx.x < C) {
-    const int c = threadIdx.x;
-    for (int i = 0; i < n; ++i) {
-      double s = r[(long long)i * C + c];
-      for (int jj = 0; jj < i; ++jj) s -= a[(long long)i * n + jj] * r[(long long)jj * C + c];
-      r[(long long)i * C + c] = s / a[(long long)i * n + i];
-    }
-    for (int i = n - 1; i >= 0; --i) {
-      double s = r[(long long)i * C + c];
-      for (int jj = i + 1; jj < n; ++jj) s -= a[(long long)jj * n + i] * r[(long long)jj * C + c];
-      r[(long long)i * C + c] = s / a[(long long)i * n + i];
-    }
-    double tot = 0.0;
+  for (int c = warp; c < C; c += KC_THREADS / 32) {
     double* out = phi + ((long long)b * C + c) * d;
-    for (int i = 0; i < n; ++i) { out[i] = r[(long long)i * C + c]; tot += out[i]; }
-    const double l0 = ks_link(f0[c], link);
-    out[n] = (ks_link(fx[(long long)b * C + c], link) - l0) - tot;
+    double tot = 0.0;
+    for (int i = lane; i < n; i += 32) {
+      const double v = xs[(size_t)i * C + c];
+      out[i] = v;
+      tot += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0) {
+      const double l0 = ks_link(f0[c], link);
+      out[n] = (ks_link(fx[(long long)b * C + c], link) - l0) - tot;
+    }
   }
-  __syncthreads();
-  if (threadIdx.x == 0 && info) info[b] = bad;
+  if (t == 0 && info) info[b] = bad;
 }
 
 int kernelshap_solve(const uint32_t* Z, int words, const double* w, const double* probs, const double* fx,
@@ -164,13 +354,16 @@ int kernelshap_solve(const uint32_t* Z, int words, const double* w, const double
   AGB_REQUIRE(words * 32 >= d, "mask words");
   if (B == 0) return AGB_OK;
   AGB_REQUIRE(Z && w && probs && fx && f0 && A && R && phi, "null pointer");
-  const int n = d - 1;
-  const int tiles = (n + KS_TILE - 1) / KS_TILE;
-  dim3 grid(tiles * tiles + tiles, B);
   AGB_REQUIRE(B <= 65535, "batch too large (chunk it)");
-  kernelshap_gram_kernel<<<grid, KS_TILE * KS_TILE, 0, st>>>(Z, words, w, probs, fx, f0, S, d, C, link, A, R);
+  const int n = d - 1;
+  const size_t smem = kc_smem_doubles(n, C) * sizeof(double);
+  AGB_REQUIRE(smem <= 227 * 1024, "KernelSHAP: d too large for the shared-memory panel (d <= 1024)");
+  const int tiles = (n + KG_T - 1) / KG_T;
+  dim3 grid(tiles * (tiles + 1) / 2 + tiles, B);
+  kernelshap_gram_kernel<<<grid, KG_THREADS, 0, st>>>(Z, words, w, probs, fx, f0, S, d, C, link, A, R);
   AGB_CHECK_CUDA(cudaGetLastError());
-  kernelshap_solve_kernel<<<B, 256, 0, st>>>(A, R, fx, f0, d, C, link, phi, info);
+  AGB_CHECK_CUDA(cudaFuncSetAttribute(kernelshap_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kernelshap_solve_kernel<<<B, KC_THREADS, smem, st>>>(A, R, fx, f0, d, C, link, phi, info);
   AGB_CHECK_CUDA(cudaGetLastError());
   return AGB_OK;
 }

@@ -36,6 +36,12 @@ VIT_BASE = dict(attention_probs_dropout_prob=0.1, explainer_attn_num_layers=1, e
                 explainer_normalize=True, hidden_dropout_prob=0.1, hidden_size=768, intermediate_size=3072,
                 layer_norm_eps=1e-12, num_attention_heads=12, num_hidden_layers=12, num_labels=10, img_channels=3,
                 img_px_size=224, img_patch_size=16)
+# reference experiments/vit_large_imagenette_vanilla/.hparams.json:20-35 — BASELINE.json configs[4]; `--model vit_large`
+# runs the same legs on it (a side configuration: the default line stays ViT-Base/16, the metric's own config)
+VIT_LARGE = dict(VIT_BASE, explainer_head_hidden_size=4096, hidden_size=1024, intermediate_size=4096,
+                 num_attention_heads=16, num_hidden_layers=24)
+MODELS = {"vit_base": ("vit_base_imagenette_vanilla", "ViT-Base/16", VIT_BASE),
+          "vit_large": ("vit_large_imagenette_vanilla", "ViT-Large/16", VIT_LARGE)}
 
 
 def flops_per_eval(c):
@@ -198,7 +204,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     rec = vanilla_vit_recipe()
-    cfgd = dict(VIT_BASE)
+    workload, model_name, model_cfg = MODELS[args.model]
+    cfgd = dict(model_cfg)
     cfg = rec.t_config(**cfgd)
     n = rec.n_players(cfg)
     torch.manual_seed(3407)                       # the reference's checked-in seed (.hparams.json:3)
@@ -378,7 +385,7 @@ def run_ours(args):
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture of a whole layer at
         # this exact shape (profiles/r01_layer_ncu_full.txt: QKV 1.197, out-proj 1.814, FC1 1.509, FC2 2.887 GB; mean);
         # algorithmic bytes per launch of the same four GEMMs (operands + residual + outputs once): 1.24/1.87/1.55/2.80 GB
-        "traffic": 1.852e9 if (B * S * (n + 1) == 201728) else None, "traffic_unit": "bytes per launch (ncu, mean of the 4 layer GEMMs)",
+        "traffic": 1.852e9 if (B * S * (n + 1) == 201728 and args.model == "vit_base") else None, "traffic_unit": "bytes per launch (ncu, mean of the 4 layer GEMMs)",
         "avg_launch_us": gemm[0] / gemm[2] * 1e3, "launches": gemm[2], "share_of_step": gemm[0] / total_t,
         "step_shares": {k: round(v[0] / total_t, 4) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1][0])},
     }
@@ -411,7 +418,7 @@ def run_ours(args):
 
     if rank == 0:
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.model == "vit_base":
             cores = os.cpu_count() or 1
             v, _ = time_cpu_reference(1, 16, 2, 1)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
@@ -421,7 +428,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "surrogate": "ViT-Base/16 (random init, seed 3407)",
+            "config": {"workload": workload, "surrogate": f"{model_name} (random init, seed 3407)",
                        "images_per_gpu_per_step": B, "coalitions_per_image": S, "evals_per_gpu_per_step": rows,
                        "parallelism": f"dp{world} (images sharded, final all_gather of probabilities)",
                        "l2": "activations per step (>3 GB) exceed L2 (126 MB); no explicit flush"},
@@ -445,6 +452,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=32, help="images per GPU per step (x32 coalitions each)")
+    ap.add_argument("--model", default="vit_base", choices=sorted(MODELS), help="vit_base = the metric's config (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the explainer-training leg")
     ap.add_argument("--train-images", type=int, default=32, help="images per GPU per training step")

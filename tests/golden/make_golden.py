@@ -111,6 +111,7 @@ MODEL_CASES = [
     ("vit_mini_px64", 3, 4),
     ("vit_tiny", 2, 4),
     ("vit_base", 1, 2),
+    ("vit_large", 1, 2),
     ("bert_mini", 3, 4),
     ("bert_base_128", 1, 2),
     ("bert_mini_512", 2, 2),

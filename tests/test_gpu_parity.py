@@ -388,7 +388,7 @@ def _build(name, precision):
 FP32_CASES = ["vit_mini", "vit_mini_px64", "bert_mini", "vit_tiny", "bert_mini_512"]   # bert_mini_512: T = 512 edge case
 
 
-@pytest.mark.parametrize("name", FP32_CASES + ["vit_base", "bert_base_128"])
+@pytest.mark.parametrize("name", FP32_CASES + ["vit_base", "bert_base_128", "vit_large"])
 def test_full_path_fp32_vs_reference_golden(agb, golden_dir, name):
     g = _load(golden_dir, f"model_{name}.npz")
     B, S, n = (int(v) for v in g["meta"])
@@ -416,7 +416,7 @@ def test_full_path_fp32_vs_reference_golden(agb, golden_dir, name):
     np.testing.assert_allclose(_np(phi_m), g["phi_masked"], rtol=1e-4, atol=1e-4 * scale)
 
 
-@pytest.mark.parametrize("name", ["vit_mini", "bert_mini", "vit_tiny", "vit_base", "bert_base_128", "bert_mini_512"])
+@pytest.mark.parametrize("name", ["vit_mini", "bert_mini", "vit_tiny", "vit_base", "bert_base_128", "bert_mini_512", "vit_large"])
 def test_full_path_bf16_tensor_cores_vs_reference_golden(agb, golden_dir, name):
     g = _load(golden_dir, f"model_{name}.npz")
     B, S, n = (int(v) for v in g["meta"])
