@@ -725,6 +725,138 @@ attention_bwd_f32_kernel(const float* __restrict__ qkv, const float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Narrow heads (head dim 8 / 16 / 32: the side ladders of the LTT variants, hidden size s_attn_hidden_size split over the
+// backbone's head count, reference models/ltt_vit.py:386-396).  Same two passes and the same arithmetic as
+// attention_bwd_kernel with the operands staged as fp32 (so fp32 I/O is the exact mode here too); the head dim no
+// longer fills a warp, so 32 / D lane groups split the reduction index and are folded with shuffles.
+// ------------------------------------------------------------------------------------------------
+template <typename TIO, int D>
+__global__ void __launch_bounds__(256)
+attention_bwd_small_kernel(const TIO* __restrict__ qkv, const TIO* __restrict__ dctx, const uint32_t* __restrict__ mask,
+                           int words, int T, int H, int heads, int mode, float scale, TIO* __restrict__ dqkv) {
+  constexpr int LD = D + 1;
+  constexpr int G = 32 / D;
+  extern __shared__ uint8_t smraw[];
+  float* sQ = reinterpret_cast<float*>(smraw);
+  float* sK = sQ + T * LD;
+  float* sV = sK + T * LD;
+  float* sdO = sV + T * LD;
+  float* lse = sdO + T * LD;   // T   (max + log-sum)
+  float* Dv = lse + T;         // T
+  float* strips = Dv + T;      // nw * 2 * T
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int row = blockIdx.x / heads, head = blockIdx.x % heads;
+  const long long base = (long long)row * T * 3 * H;
+  const uint32_t* mrow = mask + (long long)row * words;
+  for (int e = threadIdx.x; e < T * D; e += blockDim.x) {
+    const int t = e / D, c = e % D;
+    const TIO* p = qkv + base + (long long)t * 3 * H + head * D + c;
+    sQ[t * LD + c] = ld1<TIO>(p);
+    sK[t * LD + c] = ld1<TIO>(p + H);
+    sV[t * LD + c] = ld1<TIO>(p + 2 * H);
+    sdO[t * LD + c] = ld1<TIO>(dctx + ((long long)row * T + t) * H + head * D + c);
+  }
+  __syncthreads();
+  float* s0 = strips + warp * 2 * T;
+  float* s1 = s0 + T;
+  const int c = lane % D, g = lane / D;
+  // ---------------- pass A: query-owned (row statistics, dQ) ----------------
+  for (int i = warp; i < T; i += nw) {
+    float mx = -INFINITY;
+    for (int j = lane; j < T; j += 32) {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        a = fmaf(sQ[i * LD + k], sK[j * LD + k], a);
+        b = fmaf(sdO[i * LD + k], sV[j * LD + k], b);
+      }
+      const uint32_t keep = (mrow[j >> 5] >> (j & 31)) & 1u;
+      float x = a * scale;
+      if (!keep) x = (mode == AGB_MASK_MUL0) ? 0.f : -INFINITY;
+      s0[j] = x;
+      s1[j] = b;
+      mx = fmaxf(mx, x);
+    }
+    mx = warp_max(mx);
+    float z = 0.f;
+    for (int j = lane; j < T; j += 32) z += expf(s0[j] - mx);
+    z = warp_sum(z);
+    const float l = mx + logf(z);
+    float dsum = 0.f;
+    for (int j = lane; j < T; j += 32) {
+      const float pj = expf(s0[j] - l);
+      dsum += pj * s1[j];
+      s0[j] = pj;
+    }
+    dsum = warp_sum(dsum);
+    if (lane == 0) { lse[i] = l; Dv[i] = dsum; }
+    __syncwarp();
+    for (int j = lane; j < T; j += 32) {
+      const uint32_t keep = (mrow[j >> 5] >> (j & 31)) & 1u;
+      s0[j] = keep ? s0[j] * (s1[j] - dsum) * scale : 0.f;
+    }
+    __syncwarp();
+    float q = 0.f;
+    for (int j = g; j < T; j += G) q = fmaf(s0[j], sK[j * LD + c], q);
+#pragma unroll
+    for (int o = D; o < 32; o <<= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (g == 0) st1<TIO>(dqkv + base + (long long)i * 3 * H + head * D + c, q);
+    __syncwarp();
+  }
+  __syncthreads();
+  // ---------------- pass B: key-owned (dK, dV; scores recomputed) ----------------
+  for (int j = warp; j < T; j += nw) {
+    const uint32_t keep = (mrow[j >> 5] >> (j & 31)) & 1u;
+    for (int i = lane; i < T; i += 32) {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        a = fmaf(sQ[i * LD + k], sK[j * LD + k], a);
+        b = fmaf(sdO[i * LD + k], sV[j * LD + k], b);
+      }
+      float x = a * scale;
+      if (!keep) x = (mode == AGB_MASK_MUL0) ? 0.f : -INFINITY;
+      const float pij = expf(x - lse[i]);
+      s0[i] = pij;                                               // for dV
+      s1[i] = keep ? pij * (b - Dv[i]) * scale : 0.f;            // dS for dK
+    }
+    __syncwarp();
+    float kk = 0.f, vv = 0.f;
+    for (int i = g; i < T; i += G) {
+      kk = fmaf(s1[i], sQ[i * LD + c], kk);
+      vv = fmaf(s0[i], sdO[i * LD + c], vv);
+    }
+#pragma unroll
+    for (int o = D; o < 32; o <<= 1) {
+      kk += __shfl_xor_sync(0xffffffffu, kk, o);
+      vv += __shfl_xor_sync(0xffffffffu, vv, o);
+    }
+    if (g == 0) {
+      st1<TIO>(dqkv + base + (long long)j * 3 * H + H + head * D + c, kk);
+      st1<TIO>(dqkv + base + (long long)j * 3 * H + 2 * H + head * D + c, vv);
+    }
+    __syncwarp();
+  }
+}
+
+template <typename TIO, int D>
+static int launch_attention_bwd_small(const void* qkv, const void* dctx, const uint32_t* mask, int words, int rows, int T,
+                                      int H, int heads, int mode, void* dqkv, cudaStream_t st) {
+  const int nw = 8;
+  const size_t smem = ((size_t)4 * T * (D + 1) + 2 * (size_t)T + (size_t)nw * 2 * T) * sizeof(float);
+  if (smem > 227 * 1024) {
+    set_last_error("agb_masked_attention_bwd: T = %d with head dim %d does not fit in shared memory", T, D);
+    return AGB_ERR_UNSUPPORTED;
+  }
+  AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_small_kernel<TIO, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attention_bwd_small_kernel<TIO, D><<<rows * heads, nw * 32, smem, st>>>(
+      static_cast<const TIO*>(qkv), static_cast<const TIO*>(dctx), mask, words, T, H, heads, mode, rsqrtf((float)D),
+      static_cast<TIO*>(dqkv));
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
 int attention_bwd_tc(const bf16* qkv, const bf16* dctx, const uint32_t* mask, int words, int rows, int T, int H,
                      int heads, int mode, bf16* dqkv, cudaStream_t stream);
 static int g_attention_bwd_variant = 0;   // 0 auto (tensor cores for bf16), 1 CUDA-core kernel only
@@ -733,9 +865,20 @@ int get_attention_bwd_variant() { return g_attention_bwd_variant; }
 
 int attention_bwd(const void* qkv, const void* dctx, int io_bf16, const uint32_t* mask, int words, int rows, int T,
                   int H, int heads, int mode, void* dqkv, cudaStream_t st) {
-  AGB_REQUIRE(rows >= 0 && T > 0 && heads > 0 && H == heads * AB_D, "attention backward needs head dim 64");
+  AGB_REQUIRE(rows >= 0 && T > 0 && heads > 0 && H % heads == 0, "attention shape");
   AGB_REQUIRE(words * 32 >= T, "mask words");
   AGB_REQUIRE(mode == AGB_MASK_MUL0 || mode == AGB_MASK_NEGINF, "mask mode");
+  const int hd = H / heads;
+  if (hd != AB_D) {
+    AGB_REQUIRE(hd == 8 || hd == 16 || hd == 32, "attention backward: head dim must be 64, 32, 16 or 8");
+    if (rows == 0) return AGB_OK;
+    AGB_REQUIRE(qkv && dctx && mask && dqkv, "null pointer");
+#define ABS_LAUNCH(D)                                                                                                  \
+  (io_bf16 ? launch_attention_bwd_small<bf16, D>(qkv, dctx, mask, words, rows, T, H, heads, mode, dqkv, st)            \
+           : launch_attention_bwd_small<float, D>(qkv, dctx, mask, words, rows, T, H, heads, mode, dqkv, st))
+    return hd == 8 ? ABS_LAUNCH(8) : (hd == 16 ? ABS_LAUNCH(16) : ABS_LAUNCH(32));
+#undef ABS_LAUNCH
+  }
   if (T > 512) {
     set_last_error("agb_masked_attention_bwd supports T <= 512 (got %d)", T);
     return AGB_ERR_UNSUPPORTED;

@@ -16,17 +16,46 @@
 namespace agb {
 
 constexpr int KG_T = 64;         // Gram tile edge
-constexpr int KG_CH = 32;        // coalitions staged per shared-memory chunk
-constexpr int KG_THREADS = 128;  // 8 x 16 threads, 8 x 4 accumulators each
+constexpr int KG_CH = 32;        // coalitions staged per shared-memory chunk (= bits of one column word)
+constexpr int KG_THREADS = 64;   // 8 x 8 threads, 8 x 8 accumulators each
 
 __device__ __forceinline__ double ks_link(double p, int link) {
   return link ? log(p / (1.0 - p)) : p;
 }
 
-// grid: (lower-triangle 64x64 tiles of A + one 64 x C strip of R per tile row, B).  fp64 FMA-pipe bound: the chunk is
-// staged as doubles (w_s * E[s,j] and E[s,k]); each thread keeps an 8 x 4 block of the tile in registers, so one
-// shared-memory wavefront feeds about five DFMAs.  E takes values in {-1, 0, 1}; columns >= d-1 are zero.
-__global__ void __launch_bounds__(KG_THREADS)
+// high word of the double 1.0 when (bits & mask) != 0, else 0 (the double 0.0): bit test into a predicate + select
+__device__ __forceinline__ int ks_one_if(uint32_t bits, uint32_t mask) {
+  int hi;
+  asm("{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 tt;\n"
+      "and.b32 tt, %1, %2;\n"
+      "setp.ne.u32 p, tt, 0;\n"
+      "selp.b32 %0, 0x3FF00000, 0, p;\n"
+      "}\n"
+      : "=r"(hi)
+      : "r"(bits), "r"(mask));
+  return hi;
+}
+
+// bits of columns [c0, c0 + 32) that belong to the (d-1) x (d-1) system
+__device__ __forceinline__ uint32_t ks_valid_bits(int c0, int n) {
+  if (c0 + 32 <= n) return 0xFFFFFFFFu;
+  if (c0 >= n) return 0u;
+  return (1u << (n - c0)) - 1u;
+}
+
+// grid: (lower-triangle 64x64 tiles of A + one 64 x C strip of R per tile row, B).  fp64-pipe bound.
+// With z' = z XOR z_last (per coalition) the eliminated design matrix is E[s,j] = sigma_s z'[s,j], sigma_s = +-1, so
+//   A[j,k] = sum_s w_s z'[s,j] z'[s,k]          R[j,c] = sum_s (w_s z'[s,j]) (sigma_s y~[s,c])
+// i.e. A accumulates w_s wherever both bits are set: no multiplications and no cancellation.  Per chunk of 32
+// coalitions the j side is staged as doubles (w_s or 0) and the k side as one 32-bit word per column (bit ss = z');
+// each thread keeps an 8 x 8 block in registers and, per coalition and column, turns the column's bit into the double
+// 1.0 / 0.0 with two integer instructions that feed eight DFMAs, so shared memory delivers only the j side: 64 B per
+// thread per coalition for 64 DFMAs (an 8 x 4 block with both sides in shared memory was LSU-bound at 45 % of the
+// fp64 pipe, profiles/r01_kernelshap_ncu.txt).
+template <int CMAX>   // classes carried by the rhs strip (4 or 16)
+__global__ void __launch_bounds__(KG_THREADS, 6)
 kernelshap_gram_kernel(const uint32_t* __restrict__ Z, int words, const double* __restrict__ w,
                        const double* __restrict__ probs, const double* __restrict__ fx,
                        const double* __restrict__ f0, int S, int d, int C, int link, double* __restrict__ A,
@@ -44,84 +73,108 @@ kernelshap_gram_kernel(const uint32_t* __restrict__ Z, int words, const double* 
     while ((tj + 1) * (tj + 2) / 2 <= tile) ++tj;
     tk = tile - tj * (tj + 1) / 2;
   }
-  __shared__ __align__(16) double wej[KG_CH][KG_T];   // w_s * E[s, j-tile]
-  __shared__ __align__(16) double ek[KG_CH][KG_T];    // E[s, k-tile]
-  __shared__ double yt[KG_CH][16];                    // y~[s, c] for the rhs strip (C <= 16)
+  __shared__ __align__(16) double wa[KG_CH][KG_T];    // w_s * z'[s, j-tile]
+  __shared__ uint32_t cbits[KG_T];                    // column k of the k-tile: bit ss = z'[s0 + ss, k]
+  __shared__ double us[KG_CH][CMAX];                  // sigma_s * y~[s, c] for the rhs strip (C <= CMAX)
+  __shared__ double l0s[CMAX], dls[CMAX];             // link(f0[c]) and link(fx[b, c]) - link(f0[c])
   const int t = threadIdx.x;
-  const int ty = t >> 4, tx = t & 15;
+  const int warp = t >> 5, lane = t & 31;
+  const int ty = t >> 3, tx = t & 7;
   const uint32_t* Zb = Z + (long long)b * S * words;
   const int last = d - 1;
-  double acc[8][4];
+  double acc[8][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) acc[i][q] = 0.0;
-  if (is_rhs)
-    for (int e = t; e < KG_CH * 16; e += KG_THREADS) yt[e >> 4][e & 15] = 0.0;
+    for (int q = 0; q < 8; ++q) acc[i][q] = 0.0;
+  if (is_rhs) {
+    for (int e = t; e < KG_CH * CMAX; e += KG_THREADS) us[e / CMAX][e % CMAX] = 0.0;
+    if (t < C) {
+      l0s[t] = ks_link(f0[t], link);
+      dls[t] = ks_link(fx[(long long)b * C + t], link) - l0s[t];
+    }
+  }
+  const int cj = tj * KG_T + warp * 32, ck = tk * KG_T + warp * 32;   // this warp's 32 columns of either tile
+  const uint32_t vj = ks_valid_bits(cj, n), vk = ks_valid_bits(ck, n);
+  // lane = coalition of the chunk: its two column words, XORed with the eliminated feature's bit, and its weight;
+  // fetched one chunk ahead so that the global-memory latency hides behind the DFMAs of the current chunk
+  uint32_t nxt_j = 0, nxt_k = 0;
+  double nxt_w = 0.0;
+  auto fetch = [&](int s0) {
+    const int s = s0 + lane;
+    nxt_j = nxt_k = 0;
+    nxt_w = 0.0;
+    if (s < S) {
+      const uint32_t* zr = Zb + (long long)s * words;
+      const uint32_t flip = ((zr[last >> 5] >> (last & 31)) & 1u) ? 0xFFFFFFFFu : 0u;
+      nxt_w = w[(long long)b * S + s];
+      if (vj) nxt_j = (zr[cj >> 5] ^ flip) & vj;
+      if (vk) nxt_k = (zr[ck >> 5] ^ flip) & vk;
+    }
+  };
+  fetch(0);
   for (int s0 = 0; s0 < S; s0 += KG_CH) {
     __syncthreads();
-    for (int e = t; e < KG_CH * 8; e += KG_THREADS) {
-      const int ss = e >> 3, g = e & 7;       // coalition in the chunk, group of 8 columns
-      const int s = s0 + ss;
-      const int cj = tj * KG_T + g * 8, ck = tk * KG_T + g * 8;
-      uint32_t bj = 0, bk = 0;
-      int zl = 0;
-      double wv = 0.0;
-      const bool live = s < S;
-      if (live) {
-        const uint32_t* zr = Zb + (long long)s * words;
-        zl = (zr[last >> 5] >> (last & 31)) & 1;
-        wv = w[(long long)b * S + s];
-        if (cj < d) bj = (zr[cj >> 5] >> (cj & 31)) & 0xFFu;
-        if (ck < d) bk = (zr[ck >> 5] >> (ck & 31)) & 0xFFu;
+    {
+      const uint32_t wordj = nxt_j, wordk = nxt_k;
+      const double wv = nxt_w;
+      fetch(s0 + KG_CH);
+#pragma unroll 8
+      for (int ss = 0; ss < KG_CH; ++ss) {
+        const uint32_t wj = __shfl_sync(0xffffffffu, wordj, ss);
+        const double ws = __shfl_sync(0xffffffffu, wv, ss);
+        wa[ss][warp * 32 + lane] = ((wj >> lane) & 1u) ? ws : 0.0;
       }
+      if (!is_rhs) {
+        uint32_t mine = 0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int evj = (live && cj + q < n) ? (int)((bj >> q) & 1u) - zl : 0;
-        const int evk = (live && ck + q < n) ? (int)((bk >> q) & 1u) - zl : 0;
-        wej[ss][g * 8 + q] = wv * (double)evj;
-        ek[ss][g * 8 + q] = (double)evk;
-      }
-    }
-    if (is_rhs) {
-      for (int e = t; e < KG_CH * C; e += KG_THREADS) {
-        const int ss = e / C, c = e % C;
-        const int s = s0 + ss;
-        double v = 0.0;
-        if (s < S) {
-          const uint32_t* zr = Zb + (long long)s * words;
-          const double zl = (double)((zr[last >> 5] >> (last & 31)) & 1);
-          const double l0 = ks_link(f0[c], link);
-          const double yv = ks_link(probs[((long long)b * S + s) * C + c], link) - l0;
-          const double dl = ks_link(fx[(long long)b * C + c], link) - l0;
-          v = yv - zl * dl;
+        for (int c = 0; c < 32; ++c) {
+          const uint32_t bal = __ballot_sync(0xffffffffu, (wordk >> c) & 1u);
+          if (lane == c) mine = bal;
         }
-        yt[ss][c] = v;
+        cbits[warp * 32 + lane] = mine;
+      } else {
+        for (int e = t; e < KG_CH * C; e += KG_THREADS) {
+          const int ss = e / C, c = e % C;
+          const int s2 = s0 + ss;
+          double v = 0.0;
+          if (s2 < S) {
+            const uint32_t* zr = Zb + (long long)s2 * words;
+            const double zl = (double)((zr[last >> 5] >> (last & 31)) & 1);
+            const double yv = ks_link(probs[((long long)b * S + s2) * C + c], link) - l0s[c];
+            v = (1.0 - 2.0 * zl) * (yv - zl * dls[c]);
+          }
+          us[ss][c] = v;
+        }
       }
     }
     __syncthreads();
     if (!is_rhs) {
-#pragma unroll 4
+      uint32_t cb[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) cb[q] = cbits[tx + 8 * q];
+#pragma unroll
       for (int ss = 0; ss < KG_CH; ++ss) {
-        const double2* pa = reinterpret_cast<const double2*>(&wej[ss][ty * 8]);
+        const double2* pa = reinterpret_cast<const double2*>(&wa[ss][ty * 8]);
         const double2 a01 = pa[0], a23 = pa[1], a45 = pa[2], a67 = pa[3];
         const double av[8] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y, a67.x, a67.y};
-        double bv[4];
+        // each column's bit as the double 1.0 / 0.0 (two integer instructions, all eight before the DFMAs so that
+        // the integer chains overlap the fp64 pipe), then 8 x 8 DFMAs
+        double bv[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) bv[q] = ek[ss][tx + 16 * q];
+        for (int q = 0; q < 8; ++q) bv[q] = __hiloint2double(ks_one_if(cb[q], 1u << ss), 0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int q = 0; q < 8; ++q)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) acc[i][q] = fma(av[i], bv[q], acc[i][q]);
+          for (int i = 0; i < 8; ++i) acc[i][q] = fma(av[i], bv[q], acc[i][q]);
       }
     } else {
-      // rhs strip: thread (row j = t % 64, class half = t / 64) accumulates 8 classes in acc[0..7][0]
-      const int jl = t & 63, c0 = (t >> 6) * 8;
+      // rhs strip: thread = row j of the tile, CMAX class accumulators in acc[0..1][0..7]
 #pragma unroll 4
       for (int ss = 0; ss < KG_CH; ++ss) {
-        const double a = wej[ss][jl];
+        const double a = wa[ss][t];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c][0] = fma(a, yt[ss][c0 + c], acc[c][0]);
+        for (int c = 0; c < CMAX; ++c) acc[c >> 3][c & 7] = fma(a, us[ss][c], acc[c >> 3][c & 7]);
       }
     }
   }
@@ -131,17 +184,17 @@ kernelshap_gram_kernel(const uint32_t* __restrict__ Z, int words, const double* 
       const int j = tj * KG_T + ty * 8 + i;
       if (j >= n) continue;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int k = tk * KG_T + tx + 16 * q;
+      for (int q = 0; q < 8; ++q) {
+        const int k = tk * KG_T + tx + 8 * q;
         if (k < n) A[((long long)b * n + j) * n + k] = acc[i][q];
       }
     }
   } else {
-    const int j = tj * KG_T + (t & 63), c0 = (t >> 6) * 8;
+    const int j = tj * KG_T + t;
     if (j < n) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        if (c0 + c < C) R[((long long)b * n + j) * C + c0 + c] = acc[c][0];
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) R[((long long)b * n + j) * C + c] = acc[c >> 3][c & 7];
     }
   }
 }
@@ -360,7 +413,8 @@ int kernelshap_solve(const uint32_t* Z, int words, const double* w, const double
   AGB_REQUIRE(smem <= 227 * 1024, "KernelSHAP: d too large for the shared-memory panel (d <= 1024)");
   const int tiles = (n + KG_T - 1) / KG_T;
   dim3 grid(tiles * (tiles + 1) / 2 + tiles, B);
-  kernelshap_gram_kernel<<<grid, KG_THREADS, 0, st>>>(Z, words, w, probs, fx, f0, S, d, C, link, A, R);
+  if (C <= 4) kernelshap_gram_kernel<4><<<grid, KG_THREADS, 0, st>>>(Z, words, w, probs, fx, f0, S, d, C, link, A, R);
+  else        kernelshap_gram_kernel<16><<<grid, KG_THREADS, 0, st>>>(Z, words, w, probs, fx, f0, S, d, C, link, A, R);
   AGB_CHECK_CUDA(cudaGetLastError());
   AGB_CHECK_CUDA(cudaFuncSetAttribute(kernelshap_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kernelshap_solve_kernel<<<B, KC_THREADS, smem, st>>>(A, R, fx, f0, d, C, link, phi, info);

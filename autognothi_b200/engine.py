@@ -282,13 +282,16 @@ def run_bert_packed(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: T
     return y, ya
 
 
-def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tensor, S: int, cls_only: bool = False
-                 ) -> Tuple[Tensor, Optional[Tensor]]:
+def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tensor, S: int, cls_only: bool = False,
+                 layer_hook=None) -> Tuple[Tensor, Optional[Tensor]]:
     """-> (x (rows*T, H) fp32 after the encoder stack [ViT: BEFORE the final LayerNorm], activation copy | None).
-    cls_only (surrogate / classifier heads): the last block runs for the CLS query only and x is (rows, H)."""
+    cls_only (surrogate / classifier heads): the last block runs for the CLS query only and x is (rows, H).
+    layer_hook(i, x, x_act): called after every block with its output (fp32 residual stream, activation-dtype copy or
+    None) — the side ladders of the LTT variants tap the frozen backbone here; x is updated in place by the next block,
+    so the hook must consume it on the same stream."""
     T = n_players_of(cfg) + 1
     H, heads, eps = cfg.hidden_size, cfg.num_attention_heads, cfg.layer_norm_eps
-    cls_only = cls_only and CLS_ONLY_LAST_BLOCK and len(bw.layers) > 0
+    cls_only = cls_only and CLS_ONLY_LAST_BLOCK and len(bw.layers) > 0 and layer_hook is None
     if (cls_only and not bw.vit and DROP_MASKED_TOKENS and pol.bf16 and T <= 512 and H == heads * 64
             and all(lw.ln2 is not None for lw in bw.layers)):
         return run_bert_packed(bw, cfg, pol, xs, masks, S)
@@ -327,7 +330,10 @@ def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tens
                 x16, stats = ops.rowstats_cast(x)
             for i, lw in enumerate(full):
                 x, x16, stats = vit_layer_fused(lw, x, x16, stats, masks, T, heads, eps,
-                                                last=(not cls_only and i == len(full) - 1), ctx=ctx0 if i == 0 else None)
+                                                last=(not cls_only and i == len(full) - 1 and layer_hook is None),
+                                                ctx=ctx0 if i == 0 else None)
+                if layer_hook is not None:
+                    layer_hook(i, x, x16)
             if cls_only:
                 if x16 is None:      # single-block model: the CLS-only block is also the first one
                     x16, stats = ops.rowstats_cast(x)
@@ -335,12 +341,16 @@ def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tens
             return x, None
         for i, lw in enumerate(full):
             x = vit_layer(pol, lw, x, masks, T, heads, eps, ctx=ctx0 if i == 0 else None)
+            if layer_hook is not None:
+                layer_hook(i, x, None)
         if cls_only:
             return last_block_cls_only(pol, bw.layers[-1], True, x, None, None, None, masks, T, heads, eps)
         return x, None
     xa = pol.act(x) if ctx0 is None else None
     for i, lw in enumerate(full):
         x, xa = bert_layer(pol, lw, x, xa, masks, T, heads, eps, ctx=ctx0 if i == 0 else None)
+        if layer_hook is not None:
+            layer_hook(i, x, xa)
     if cls_only:
         if xa is None:
             xa = pol.act(x)
@@ -402,11 +412,16 @@ class ExplainerEngine:
     @torch.no_grad()
     def phi(self, xs: Tensor, masks: Tensor, grand: Optional[Tensor], null: Optional[Tensor], want_pred: bool = False):
         """xs (B,...), masks packed (B, words) -> phi (B, C, n) fp32 [, pred (B,T,C)]"""
+        x, xa = run_backbone(self.bw, self.cfg, self.pol, xs, masks, 1)
+        return self.tail(x, xa, masks, xs.shape[0], grand, null, want_pred)
+
+    @torch.no_grad()
+    def tail(self, x: Tensor, xa: Optional[Tensor], masks: Tensor, B: int, grand: Optional[Tensor], null: Optional[Tensor],
+             want_pred: bool = False):
+        """Everything after the encoder stack: x (B*T, H) fp32 [ViT: before vit.layernorm], xa its activation copy."""
         cfg, pol = self.cfg, self.pol
         T = n_players_of(cfg) + 1
-        H, heads, eps = cfg.hidden_size, cfg.num_attention_heads, cfg.layer_norm_eps
-        B = xs.shape[0]
-        x, xa = run_backbone(self.bw, cfg, pol, xs, masks, 1)
+        heads, eps = cfg.num_attention_heads, cfg.layer_norm_eps
         if self.bw.vit:
             _, x = ops.layernorm(x, self.bw.final_ln[0], self.bw.final_ln[1], eps, want_bf16=False, want_f32=True)
             for lw in self.attn:
@@ -419,3 +434,182 @@ class ExplainerEngine:
         h = pol.linear(h, self.w_a, self.b_a, act=ops.ACT_GELU)
         h = pol.linear(h, self.w_b, self.b_b, act=ops.ACT_GELU)
         return ops.explainer_head_fwd(h, B, T, self.w_c, self.b_c, grand, null, bool(cfg.explainer_normalize), want_pred)
+
+
+class FroyoFinalEngine(ExplainerEngine):
+    """Froyo bundle (reference models/froyo_vit.py:100-171, models/froyo_bert.py:103-204): ONE frozen backbone pass feeds
+    the classifier head, the surrogate head (srg_*) and the explainer tail."""
+
+    def __init__(self, sd: State, cfg, precision: str):
+        super().__init__(sd, cfg, precision)
+        self.w_cls, self.b_cls = _f32(sd["classifier.weight"]), _f32(sd["classifier.bias"])
+        self.w_srg, self.b_srg = _f32(sd["srg_classifier.weight"]), _f32(sd["srg_classifier.bias"])
+        if not self.bw.vit:
+            self.pool = (_f32(sd["bert_pooler.dense.weight"]), _f32(sd["bert_pooler.dense.bias"]))
+            self.srg_pool = (_f32(sd["srg_bert_pooler.dense.weight"]), _f32(sd["srg_bert_pooler.dense.bias"]))
+        self.null = _f32(sd["surrogate_null"])
+
+    @torch.no_grad()
+    def final(self, xs: Tensor, masks: Tensor) -> Tuple[Tensor, Tensor]:
+        cfg = self.cfg
+        B = xs.shape[0]
+        x, xa = run_backbone(self.bw, cfg, self.pol, xs, masks, 1)
+        x3 = x.reshape(B, -1, cfg.hidden_size)
+        if self.bw.vit:
+            ln = (self.bw.final_ln[0], self.bw.final_ln[1], cfg.layer_norm_eps)
+            cls = ops.cls_head(x3, 0, self.w_cls, self.b_cls, ln=ln)
+            grand = ops.cls_head(x3, 0, self.w_srg, self.b_srg, ln=ln) if cfg.explainer_normalize else None
+        else:
+            cls = ops.cls_head(x3, 1, self.w_cls, self.b_cls, pool=self.pool)
+            grand = ops.cls_head(x3, 1, self.w_srg, self.b_srg, pool=self.srg_pool) if cfg.explainer_normalize else None
+        phi = self.tail(x, xa, masks, B, grand, self.null if cfg.explainer_normalize else None)
+        return cls, phi
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# LTT ("ladder side tuning", the paper's method; SURVEY.md 8f-4): the backbone is frozen and every block's output is
+# mapped into a narrow side ladder  s <- block_i^side(s + GELU(W_i h_i))  (reference models/ltt_vit.py:407-440,
+# models/ltt_bert.py:467-499).  Surrogate and explainer are side ladders over the SAME backbone activations, so the
+# bundle evaluates the backbone once.
+# ------------------------------------------------------------------------------------------------------------------
+class SideBranch:
+    """One side ladder in kernel-ready form: H -> Hs maps, Hs-wide blocks, [ViT] its final LayerNorm."""
+
+    def __init__(self, sd: State, cfg, pol: _Policy, vit: bool, b: int):
+        root = "vit" if vit else "bert"
+        L = cfg.num_hidden_layers
+        self.maps = [(pol.weight(sd[f"{root}.encoder.s_attn_maps.{b}_{i}.weight"]),
+                      _f32(sd[f"{root}.encoder.s_attn_maps.{b}_{i}.bias"])) for i in range(L)]
+        self.layers = [LayerWeights(sd, f"{root}.encoder.s_attn_layers.{b}_{i}", pol, vit) for i in range(L)]
+        self.final_ln = (_f32(sd[f"vit.s_attn_layernorm.{b}.weight"]), _f32(sd[f"vit.s_attn_layernorm.{b}.bias"])) if vit else None
+
+
+def run_ltt(bw: BackboneWeights, branches: List[SideBranch], cfg, pol: _Policy, xs: Tensor, masks: Tensor, S: int,
+            freeze_layer: Optional[int] = None):
+    """-> (x, xa of the backbone as run_backbone, [(side state (rows*T, Hs) fp32, activation copy | None) per branch])
+    freeze_layer: reference `_ltt_freeze_layer` — blocks >= it do not feed the ladders."""
+    T = n_players_of(cfg) + 1
+    heads, eps = cfg.num_attention_heads, cfg.layer_norm_eps
+    L = len(bw.layers)
+    stop = L if freeze_layer is None else max(1, min(L, int(freeze_layer)))
+    side: List[Optional[Tensor]] = [None] * len(branches)
+    side_a: List[Optional[Tensor]] = [None] * len(branches)
+
+    def hook(i: int, x: Tensor, x_act: Optional[Tensor]) -> None:
+        if i >= stop:
+            return
+        if x_act is None:
+            x_act = pol.act(x)
+        for k, br in enumerate(branches):
+            w, b = br.maps[i]
+            s = pol.linear(x_act, w, b, act=ops.ACT_GELU, residual=side[k], out_f32=True)
+            if bw.vit:
+                side[k] = vit_layer(pol, br.layers[i], s, masks, T, heads, eps)
+            else:
+                side[k], side_a[k] = bert_layer(pol, br.layers[i], s, pol.act(s), masks, T, heads, eps)
+
+    x, xa = run_backbone(bw, cfg, pol, xs, masks, S, layer_hook=hook)
+    return x, xa, list(zip(side, side_a))
+
+
+class LttEngine:
+    """LTT surrogate / explainer / bundle on one backbone pass.  `heads` selects what exists in the state dict:
+    "surrogate" (side ladder 0 + s_attn_classifier), "explainer" (side ladder 0 + s_explainer_*), "final" (ladder 0 =
+    surrogate, ladder 1 = explainer).  reference models/ltt_vit.py:55-287, models/ltt_bert.py:66-327."""
+
+    def __init__(self, sd: State, cfg, precision: str, kind: str):
+        assert kind in ("surrogate", "explainer", "final")
+        self.cfg, self.kind = cfg, kind
+        self.pol = pol = _Policy(precision)
+        self.bw = BackboneWeights(sd, cfg, pol)
+        vit = self.bw.vit
+        self.branches = [SideBranch(sd, cfg, pol, vit, b) for b in range(2 if kind == "final" else 1)]
+        self.w_cls, self.b_cls = _f32(sd["classifier.weight"]), _f32(sd["classifier.bias"])
+        if not vit:
+            self.pool = (_f32(sd["bert_pooler.dense.weight"]), _f32(sd["bert_pooler.dense.bias"]))
+        if kind in ("surrogate", "final"):
+            self.w_srg, self.b_srg = _f32(sd["s_attn_classifier.weight"]), _f32(sd["s_attn_classifier.bias"])
+            if not vit:
+                self.srg_pool = (_f32(sd["bert_s_attn_pooler.dense.weight"]), _f32(sd["bert_s_attn_pooler.dense.bias"]))
+        if kind in ("explainer", "final"):
+            attn = "s_explainer_attn" if vit else "s_attn_attention_layers"     # the two families name them differently
+            self.attn = [LayerWeights(sd, f"{attn}.{i}", pol, vit) for i in range(cfg.explainer_s_attn_num_layers)]
+            if vit:
+                self.mlp_ln = (_f32(sd["s_explainer_mlp.0.weight"]), _f32(sd["s_explainer_mlp.0.bias"]))
+                names = ("s_explainer_mlp.1", "s_explainer_mlp.3", "s_explainer_mlp.5")
+            else:
+                self.mlp_ln = None
+                names = ("s_attn_explainer.0", "s_attn_explainer.2", "s_attn_explainer.4")
+            self.w_a, self.b_a = pol.weight(sd[names[0] + ".weight"]), _f32(sd[names[0] + ".bias"])
+            self.w_b, self.b_b = pol.weight(sd[names[1] + ".weight"]), _f32(sd[names[1] + ".bias"])
+            self.w_c, self.b_c = _f32(sd[names[2] + ".weight"]), _f32(sd[names[2] + ".bias"])
+        if kind == "final":
+            self.null = _f32(sd["surrogate_null"])
+        self.freeze_layer: Optional[int] = None
+
+    def _main_probs(self, x: Tensor, rows: int) -> Tensor:
+        cfg = self.cfg
+        x3 = x.reshape(rows, -1, cfg.hidden_size)
+        if self.bw.vit:
+            return ops.cls_head(x3, 0, self.w_cls, self.b_cls, ln=(self.bw.final_ln[0], self.bw.final_ln[1], cfg.layer_norm_eps))
+        return ops.cls_head(x3, 1, self.w_cls, self.b_cls, pool=self.pool)
+
+    def _side_probs(self, s: Tensor, rows: int) -> Tensor:
+        cfg = self.cfg
+        s3 = s.reshape(rows, -1, cfg.s_attn_hidden_size)
+        if self.bw.vit:
+            g, b = self.branches[0].final_ln
+            return ops.cls_head(s3, 0, self.w_srg, self.b_srg, ln=(g, b, cfg.layer_norm_eps))
+        return ops.cls_head(s3, 1, self.w_srg, self.b_srg, pool=self.srg_pool)
+
+    def _explain(self, br: SideBranch, s: Tensor, sa: Optional[Tensor], masks: Tensor, B: int, grand, null) -> Tensor:
+        cfg, pol = self.cfg, self.pol
+        T = n_players_of(cfg) + 1
+        heads, eps = cfg.num_attention_heads, cfg.layer_norm_eps
+        if self.bw.vit:
+            _, s = ops.layernorm(s, br.final_ln[0], br.final_ln[1], eps, want_bf16=False, want_f32=True)
+            for lw in self.attn:
+                s = vit_layer(pol, lw, s, masks, T, heads, eps)
+            h = pol.ln(s, self.mlp_ln[0], self.mlp_ln[1], 1e-5)[0]   # nn.LayerNorm default eps (reference ltt_vit.py:124)
+        else:
+            for lw in self.attn:
+                s, sa = bert_layer(pol, lw, s, sa, masks, T, heads, eps)
+            h = sa
+        h = pol.linear(h, self.w_a, self.b_a, act=ops.ACT_GELU)
+        h = pol.linear(h, self.w_b, self.b_b, act=ops.ACT_GELU)
+        return ops.explainer_head_fwd(h, B, T, self.w_c, self.b_c, grand, null, bool(cfg.explainer_normalize))
+
+    @torch.no_grad()
+    def surrogate(self, xs: Tensor, masks: Tensor, S: int, max_rows: int = 1024) -> Tuple[Tensor, Tensor]:
+        """-> (side-ladder probabilities (B*S, C), backbone probabilities (B*S, C)), row order b*S+s."""
+        B = xs.shape[0]
+        assert masks.shape[0] == B * S
+        per = max(1, max_rows // S)
+        srg, cls = [], []
+        for b0 in range(0, B, per):
+            b1 = min(B, b0 + per)
+            rows = (b1 - b0) * S
+            x, _, sides = run_ltt(self.bw, self.branches[:1], self.cfg, self.pol, xs[b0:b1], masks[b0 * S:b1 * S], S, self.freeze_layer)
+            cls.append(self._main_probs(x, rows))
+            srg.append(self._side_probs(sides[0][0], rows))
+        return (srg[0], cls[0]) if len(srg) == 1 else (torch.cat(srg, 0), torch.cat(cls, 0))
+
+    @torch.no_grad()
+    def explainer(self, xs: Tensor, masks: Tensor, grand: Optional[Tensor], null: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+        """-> (phi (B, C, n), backbone probabilities (B, C))"""
+        B = xs.shape[0]
+        x, _, sides = run_ltt(self.bw, self.branches[:1], self.cfg, self.pol, xs, masks, 1, self.freeze_layer)
+        cls = self._main_probs(x, B)
+        return self._explain(self.branches[0], sides[0][0], sides[0][1], masks, B, grand, null), cls
+
+    @torch.no_grad()
+    def final(self, xs: Tensor, masks: Tensor) -> Tuple[Tensor, Tensor]:
+        """-> (backbone probabilities (B, C), phi (B, C, n)); the surrogate ladder supplies `grand` when normalising."""
+        cfg = self.cfg
+        B = xs.shape[0]
+        use = self.branches if cfg.explainer_normalize else self.branches[1:]
+        x, _, sides = run_ltt(self.bw, use, cfg, self.pol, xs, masks, 1, self.freeze_layer)
+        cls = self._main_probs(x, B)
+        grand = self._side_probs(sides[0][0], B) if cfg.explainer_normalize else None
+        s, sa = sides[-1]
+        return cls, self._explain(self.branches[1], s, sa, masks, B, grand, self.null if cfg.explainer_normalize else None)

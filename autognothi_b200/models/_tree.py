@@ -32,7 +32,7 @@ def _init(name: str, shape: Sequence[int]) -> torch.Tensor:
     kaiming-uniform, nn.LayerNorm ones/zeros, nn.Embedding N(0,1), randn cls/pos tokens)."""
     leaf = name.rsplit(".", 1)[-1]
     lname = name.lower()
-    if "layernorm" in lname or (name.startswith("explainer_mlp.0.") and len(shape) == 1):
+    if "layernorm" in lname or (name.startswith(("explainer_mlp.0.", "s_explainer_mlp.0.")) and len(shape) == 1):
         return torch.ones(shape) if leaf == "weight" else torch.zeros(shape)
     if leaf in ("cls_token", "position_embeddings") or "embeddings.weight" in name or name.endswith("_embeddings.weight"):
         return torch.randn(shape)
@@ -140,4 +140,41 @@ def explainer_extra_shapes(cfg, vit: bool):
         out += [("explainer_mlp.0.weight", (E, H)), ("explainer_mlp.0.bias", (E,)),
                 ("explainer_mlp.2.weight", (E, E)), ("explainer_mlp.2.bias", (E,)),
                 ("explainer_mlp.4.weight", (C, E)), ("explainer_mlp.4.bias", (C,))]
+    return out
+
+
+def ltt_shapes(cfg, vit: bool, kind: str):
+    """Key/shape table of the LTT classes (reference models/ltt_vit.py:55-340, models/ltt_bert.py:66-400).
+    kind: "surrogate" (ladder 0 + side classifier), "explainer" (ladder 0 + side explainer), "final" (ladders 0, 1 + both)."""
+    H, C = cfg.hidden_size, cfg.num_labels
+    Hs, Is, E = cfg.s_attn_hidden_size, cfg.s_attn_intermediate_size, int(cfg.explainer_s_head_hidden_size)
+    root = "vit" if vit else "bert"
+    out = (vit_backbone_shapes(cfg) if vit else bert_backbone_shapes(cfg))
+    for b in range(2 if kind == "final" else 1):
+        for i in range(cfg.num_hidden_layers):
+            out += [(f"{root}.encoder.s_attn_maps.{b}_{i}.weight", (Hs, H)), (f"{root}.encoder.s_attn_maps.{b}_{i}.bias", (Hs,))]
+            out += _layer(f"{root}.encoder.s_attn_layers.{b}_{i}", Hs, Is, vit)
+        if vit:
+            out += [(f"vit.s_attn_layernorm.{b}.weight", (Hs,)), (f"vit.s_attn_layernorm.{b}.bias", (Hs,))]
+    if not vit:
+        out += [("bert_pooler.dense.weight", (H, H)), ("bert_pooler.dense.bias", (H,))]
+    out += [("classifier.weight", (C, H)), ("classifier.bias", (C,))]
+    if kind in ("surrogate", "final"):
+        if not vit:
+            out += [("bert_s_attn_pooler.dense.weight", (Hs, Hs)), ("bert_s_attn_pooler.dense.bias", (Hs,))]
+        out += [("s_attn_classifier.weight", (C, Hs)), ("s_attn_classifier.bias", (C,))]
+    if kind in ("explainer", "final"):
+        attn = "s_explainer_attn" if vit else "s_attn_attention_layers"
+        mlp = "s_explainer_mlp" if vit else "s_attn_explainer"
+        for i in range(cfg.explainer_s_attn_num_layers):
+            out += _layer(f"{attn}.{i}", Hs, Is, vit, ln1=(i != 0), ln2=True)
+        if vit:
+            out += [(f"{mlp}.0.weight", (Hs,)), (f"{mlp}.0.bias", (Hs,)),
+                    (f"{mlp}.1.weight", (E, Hs)), (f"{mlp}.1.bias", (E,)),
+                    (f"{mlp}.3.weight", (E, E)), (f"{mlp}.3.bias", (E,)),
+                    (f"{mlp}.5.weight", (C, E)), (f"{mlp}.5.bias", (C,))]
+        else:
+            out += [(f"{mlp}.0.weight", (E, Hs)), (f"{mlp}.0.bias", (E,)),
+                    (f"{mlp}.2.weight", (E, E)), (f"{mlp}.2.bias", (E,)),
+                    (f"{mlp}.4.weight", (C, E)), (f"{mlp}.4.bias", (C,))]
     return out

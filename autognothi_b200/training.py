@@ -82,7 +82,7 @@ def vit_layer_fwd(pol, lw: LayerWeights, x: Tensor, masks: Tensor, T: int, heads
 
 
 def vit_layer_bwd(pol, lw: LayerWeights, prefix: str, t: dict, dx_out: Tensor, masks: Tensor, T: int, heads: int,
-                  eps: float, grads: Grads) -> Tensor:
+                  eps: float, grads: Grads, need_dx: bool = True) -> Optional[Tensor]:
     H = dx_out.shape[1]
     g = pol.act(dx_out)
     _linear_bwd(pol, grads, prefix + ".output.dense", g, t["f"])
@@ -96,6 +96,8 @@ def vit_layer_bwd(pol, lw: LayerWeights, prefix: str, t: dict, dx_out: Tensor, m
     dctx = _dgrad(pol, g, lw.wo, out_f32=False)
     dqkv = ops.masked_attention_bwd(t["qkv"], dctx, masks, T, heads, ops.MASK_MUL0)
     _qkv_bwd(pol, grads, prefix, dqkv, t["h1"], H)
+    if not need_dx and lw.ln1 is None:
+        return None          # nothing trainable below this block (frozen backbone)
     if lw.ln1 is not None:
         dh1 = _dgrad(pol, dqkv, lw.wqkv, out_f32=True)
         return _ln_bwd(grads, prefix + ".layernorm_before", t["x_in"], dh1, lw.ln1[0], eps, dx_mid)
@@ -121,7 +123,7 @@ def bert_layer_fwd(pol, lw: LayerWeights, x: Tensor, xa: Tensor, masks: Tensor, 
 
 
 def bert_layer_bwd(pol, lw: LayerWeights, prefix: str, t: dict, dy: Tensor, masks: Tensor, T: int, heads: int,
-                   eps: float, grads: Grads) -> Tensor:
+                   eps: float, grads: Grads, need_dx: bool = True) -> Optional[Tensor]:
     H = dy.shape[1]
     d_ypre = _ln_bwd(grads, prefix + ".output.LayerNorm", t["y_pre"], dy, lw.ln2[0], eps, None)
     g = pol.act(d_ypre)
@@ -137,6 +139,8 @@ def bert_layer_bwd(pol, lw: LayerWeights, prefix: str, t: dict, dy: Tensor, mask
     dctx = _dgrad(pol, g, lw.wo, out_f32=False)
     dqkv = ops.masked_attention_bwd(t["qkv"], dctx, masks, T, heads, ops.MASK_NEGINF)
     _qkv_bwd(pol, grads, prefix, dqkv, t["xa"], H)
+    if not need_dx:
+        return None          # nothing trainable below this block (frozen backbone)
     return _dgrad(pol, dqkv, lw.wqkv, out_f32=True, residual=d_apre)
 
 
@@ -191,10 +195,15 @@ class _Tape:
     pass
 
 
-def forward_train(sd: Dict[str, Tensor], cfg, precision: str, xs: Tensor, masks: Tensor, grand, null) -> Tuple[Tensor, _Tape]:
+def forward_train(sd: Dict[str, Tensor], cfg, precision: str, xs: Tensor, masks: Tensor, grand, null,
+                  train_backbone: bool = True) -> Tuple[Tensor, _Tape]:
+    """train_backbone=False (Froyo, reference models/froyo_vit.py:88-97 / froyo_bert.py:92-101: every `vit.` / `bert.`
+    parameter frozen): the encoder stack runs on the inference engine without a tape and the adjoint stops at the
+    first explainer_attn block."""
     pol = _Policy(precision)
     tp = _Tape()
     tp.pol, tp.cfg, tp.masks, tp.xs = pol, cfg, masks, xs
+    tp.train_backbone = train_backbone
     bw = engine.BackboneWeights(sd, cfg, pol)
     vit = bw.vit
     T = n_players_of(cfg) + 1
@@ -202,17 +211,22 @@ def forward_train(sd: Dict[str, Tensor], cfg, precision: str, xs: Tensor, masks:
     B = xs.shape[0]
     tp.bw, tp.T, tp.B = bw, T, B
     root = "vit" if vit else "bert"
-    x, xa = _embed_fwd(tp, bw, cfg, pol, xs)
     tp.layers = []
-    for i, lw in enumerate(bw.layers):
-        prefix = f"{root}.encoder.layers.{i}"
-        if vit:
-            x, t = vit_layer_fwd(pol, lw, x, masks, T, heads, eps)
-        else:
-            x, xa, t = bert_layer_fwd(pol, lw, x, xa, masks, T, heads, eps)
-        tp.layers.append((prefix, lw, t))
+    if train_backbone:
+        x, xa = _embed_fwd(tp, bw, cfg, pol, xs)
+        for i, lw in enumerate(bw.layers):
+            prefix = f"{root}.encoder.layers.{i}"
+            if vit:
+                x, t = vit_layer_fwd(pol, lw, x, masks, T, heads, eps)
+            else:
+                x, xa, t = bert_layer_fwd(pol, lw, x, xa, masks, T, heads, eps)
+            tp.layers.append((prefix, lw, t))
+    else:
+        x, xa = engine.run_backbone(bw, cfg, pol, xs, masks, 1)
+        if not vit and xa is None:
+            xa = pol.act(x)
     if vit:
-        tp.x_pre_final = x
+        tp.x_pre_final = x if train_backbone else None
         _, x = ops.layernorm(x, bw.final_ln[0], bw.final_ln[1], eps, want_bf16=False, want_f32=True)
     for i in range(cfg.explainer_attn_num_layers):
         prefix = f"explainer_attn.{i}"
@@ -260,17 +274,19 @@ def backward_train(tp: _Tape, dphi: Tensor) -> Grads:
     dx = _dgrad(pol, dza, tp.w_a, out_f32=True)
     if vit:
         dx = _ln_bwd(grads, "explainer_mlp.0", tp.x_last, dx, tp.mlp_ln[0], 1e-5, None)
-    n_backbone = len(bw.layers)
+    n_backbone = len(bw.layers) if tp.train_backbone else 0
     for idx in range(len(tp.layers) - 1, -1, -1):
         prefix, lw, t = tp.layers[idx]
-        if vit and idx == n_backbone - 1:
+        if vit and tp.train_backbone and idx == n_backbone - 1:
             # crossing from explainer_attn back into the backbone: adjoint of vit.layernorm
             dx = _ln_bwd(grads, "vit.layernorm", tp.x_pre_final, dx, bw.final_ln[0], eps, None)
+        need_dx = tp.train_backbone or idx > 0
         if vit:
-            dx = vit_layer_bwd(pol, lw, prefix, t, dx, tp.masks, T, heads, eps, grads)
+            dx = vit_layer_bwd(pol, lw, prefix, t, dx, tp.masks, T, heads, eps, grads, need_dx)
         else:
-            dx = bert_layer_bwd(pol, lw, prefix, t, dx, tp.masks, T, heads, eps, grads)
-    _embed_bwd(tp, dx, grads)
+            dx = bert_layer_bwd(pol, lw, prefix, t, dx, tp.masks, T, heads, eps, grads, need_dx)
+    if tp.train_backbone:
+        _embed_bwd(tp, dx, grads)
     return grads
 
 
@@ -278,8 +294,9 @@ class _ExplainerTrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xs, masks, grand, null, cfg, precision, names, *params):
         sd = {n: p.detach() for n, p in zip(names, params)}
+        train_backbone = any(ctx.needs_input_grad[7 + i] for i, n in enumerate(names) if n.startswith(("vit.", "bert.")))
         with torch.no_grad():
-            phi, tape = forward_train(sd, cfg, precision, xs, masks, grand, null)
+            phi, tape = forward_train(sd, cfg, precision, xs, masks, grand, null, train_backbone)
         ctx.tape, ctx.names = tape, names
         ctx.shapes = [p.shape for p in params]
         return phi
@@ -384,7 +401,15 @@ def surrogate_forward_train(model, xs: Tensor, words: Tensor) -> Tensor:
     vit = hasattr(cfg, "img_px_size")
     root = "vit." if vit else "bert."
     names = [n for n in named if n.startswith(root)]   # vit.layernorm.* ride along unused (their grads come from the torch head)
-    x_cls = _BackboneTrainFn.apply(xs, words, cfg, model.agb_precision, names, *[named[n] for n in names])
+    if any(named[n].requires_grad for n in names):
+        x_cls = _BackboneTrainFn.apply(xs, words, cfg, model.agb_precision, names, *[named[n] for n in names])
+    else:
+        # frozen backbone (Froyo surrogate, reference models/froyo_vit.py:76-85): inference engine, CLS row only, no tape
+        with torch.no_grad():
+            pol = _Policy(model.agb_precision)
+            bw = engine.BackboneWeights({n: named[n].detach() for n in names}, cfg, pol)
+            x_cls, _ = engine.run_backbone(bw, cfg, pol, xs, words, 1, cls_only=True)
+            x_cls = x_cls.reshape(xs.shape[0], -1, cfg.hidden_size)[:, 0, :].contiguous()
     if vit:
         h = torch.nn.functional.layer_norm(x_cls, (cfg.hidden_size,), named["vit.layernorm.weight"],
                                            named["vit.layernorm.bias"], cfg.layer_norm_eps)
@@ -392,3 +417,207 @@ def surrogate_forward_train(model, xs: Tensor, words: Tensor) -> Tensor:
         h = torch.tanh(torch.nn.functional.linear(x_cls, named["bert_pooler.dense.weight"], named["bert_pooler.dense.bias"]))
     logits = torch.nn.functional.linear(h, named["classifier.weight"], named["classifier.bias"])
     return torch.softmax(logits, dim=-1)
+
+
+# ------------------------------------------------------------------------------------------------
+# LTT side-ladder training (reference models/ltt_vit.py:407-440, models/ltt_bert.py:467-499 trained by
+# scripts/train_explainer.py / train_surrogate.py with the backbone frozen, models/ltt_vit.py:68-74).  The frozen
+# backbone runs on the inference engine (no tape); each rung keeps the backbone activation it tapped (for the map's
+# weight gradient), its pre-GELU map output and the tape of its narrow block.  No gradient flows into the backbone.
+# ------------------------------------------------------------------------------------------------
+def _ltt_side_forward(tp: _Tape, sd, cfg, pol, xs: Tensor, masks: Tensor, freeze_layer) -> Tuple[Tensor, Optional[Tensor], Tensor]:
+    """-> (side state (B*T, Hs) fp32, its activation copy (BERT) | None, backbone class probabilities (B, C))"""
+    bw = engine.BackboneWeights(sd, cfg, pol)
+    br = engine.SideBranch(sd, cfg, pol, bw.vit, 0)
+    T = n_players_of(cfg) + 1
+    heads, eps = cfg.num_attention_heads, cfg.layer_norm_eps
+    B = xs.shape[0]
+    L = len(bw.layers)
+    stop = L if freeze_layer is None else max(1, min(L, int(freeze_layer)))
+    tp.bw, tp.br, tp.T, tp.B, tp.rungs = bw, br, T, B, []
+    state: Dict[str, Optional[Tensor]] = {"s": None, "sa": None}
+
+    def hook(i: int, x: Tensor, x_act: Optional[Tensor]) -> None:
+        if i >= stop:
+            return
+        if x_act is None:
+            x_act = pol.act(x) if pol.bf16 else x.clone()     # fp32 mode: x is updated in place by the next block
+        w, b = br.maps[i]
+        z = pol.linear(x_act, w, b, out_f32=True)
+        s_in = ops.gelu_fwd(z)
+        if state["s"] is not None:
+            s_in.add_(state["s"])
+        if bw.vit:
+            s_out, t = vit_layer_fwd(pol, br.layers[i], s_in, masks, T, heads, eps)
+            sa = None
+        else:
+            s_out, sa, t = bert_layer_fwd(pol, br.layers[i], s_in, pol.act(s_in), masks, T, heads, eps)
+        tp.rungs.append((i, x_act, z, br.layers[i], t))
+        state["s"], state["sa"] = s_out, sa
+
+    x, _ = engine.run_backbone(bw, cfg, pol, xs, masks, 1, layer_hook=hook)
+    x3 = x.reshape(B, -1, cfg.hidden_size)
+    w_cls, b_cls = _f32(sd["classifier.weight"]), _f32(sd["classifier.bias"])
+    if bw.vit:
+        cls = ops.cls_head(x3, 0, w_cls, b_cls, ln=(bw.final_ln[0], bw.final_ln[1], eps))
+    else:
+        cls = ops.cls_head(x3, 1, w_cls, b_cls, pool=(_f32(sd["bert_pooler.dense.weight"]), _f32(sd["bert_pooler.dense.bias"])))
+    return state["s"], state["sa"], cls
+
+
+def _ltt_rungs_backward(tp: _Tape, dx: Tensor, grads: Grads) -> None:
+    pol, cfg, bw = tp.pol, tp.cfg, tp.bw
+    T, heads, eps = tp.T, cfg.num_attention_heads, cfg.layer_norm_eps
+    root = "vit" if bw.vit else "bert"
+    for i, x_act, z, lw, t in reversed(tp.rungs):
+        prefix = f"{root}.encoder.s_attn_layers.0_{i}"
+        if bw.vit:
+            ds_in = vit_layer_bwd(pol, lw, prefix, t, dx, tp.masks, T, heads, eps, grads)
+        else:
+            ds_in = bert_layer_bwd(pol, lw, prefix, t, dx, tp.masks, T, heads, eps, grads)
+        dz = ops.gelu_bwd(ds_in, z)
+        _linear_bwd(pol, grads, f"{root}.encoder.s_attn_maps.0_{i}", pol.act(dz), x_act)
+        dx = ds_in                                   # s_in = s_prev + GELU(map): the residual passes straight through
+
+
+def ltt_forward_train(sd, cfg, precision: str, xs: Tensor, masks: Tensor, grand, null, kind: str, freeze_layer):
+    """kind "explainer": -> (phi (B, C, n), backbone probabilities, tape);
+       kind "surrogate": -> (CLS rows of the side state (B, Hs) [ViT: before vit.s_attn_layernorm.0], backbone
+                             probabilities, tape) — the tiny side head stays in torch autograd."""
+    pol = _Policy(precision)
+    tp = _Tape()
+    tp.pol, tp.cfg, tp.masks, tp.xs, tp.kind = pol, cfg, masks, xs, kind
+    s, sa, cls = _ltt_side_forward(tp, sd, cfg, pol, xs, masks, freeze_layer)
+    vit = tp.bw.vit
+    T, B = tp.T, tp.B
+    heads, eps = cfg.num_attention_heads, cfg.layer_norm_eps
+    Hs = cfg.s_attn_hidden_size
+    if kind == "surrogate":
+        return s.reshape(B, T, Hs)[:, 0, :].contiguous(), cls, tp
+    tp.layers = []
+    if vit:
+        tp.s_pre_ln = s
+        _, s = ops.layernorm(s, tp.br.final_ln[0], tp.br.final_ln[1], eps, want_bf16=False, want_f32=True)
+    attn = "s_explainer_attn" if vit else "s_attn_attention_layers"
+    mlp = "s_explainer_mlp" if vit else "s_attn_explainer"
+    for i in range(cfg.explainer_s_attn_num_layers):
+        prefix = f"{attn}.{i}"
+        lw = LayerWeights(sd, prefix, pol, vit)
+        if vit:
+            s, t = vit_layer_fwd(pol, lw, s, masks, T, heads, eps)
+        else:
+            s, sa, t = bert_layer_fwd(pol, lw, s, sa, masks, T, heads, eps)
+        tp.layers.append((prefix, lw, t))
+    if vit:
+        tp.mlp_ln_name = mlp + ".0"
+        tp.mlp_ln = (_f32(sd[mlp + ".0.weight"]), _f32(sd[mlp + ".0.bias"]))
+        tp.names = (mlp + ".1", mlp + ".3", mlp + ".5")
+        tp.x_last = s
+        h0 = pol.ln(s, tp.mlp_ln[0], tp.mlp_ln[1], 1e-5)[0]
+    else:
+        tp.names = (mlp + ".0", mlp + ".2", mlp + ".4")
+        h0 = sa
+    na, nb, nc = tp.names
+    tp.w_a, tp.w_b = pol.weight(sd[na + ".weight"]), pol.weight(sd[nb + ".weight"])
+    tp.w_c, b_c = _f32(sd[nc + ".weight"]), _f32(sd[nc + ".bias"])
+    tp.h0 = h0
+    tp.za = pol.linear(h0, tp.w_a, _f32(sd[na + ".bias"]))
+    tp.ha = ops.gelu_fwd(tp.za)
+    tp.zb = pol.linear(tp.ha, tp.w_b, _f32(sd[nb + ".bias"]))
+    tp.hb = ops.gelu_fwd(tp.zb)
+    phi = ops.explainer_head_fwd(tp.hb, B, T, tp.w_c, b_c, grand, null, bool(cfg.explainer_normalize))
+    return phi, cls, tp
+
+
+def ltt_backward_train(tp: _Tape, dout: Tensor) -> Grads:
+    pol, cfg, bw = tp.pol, tp.cfg, tp.bw
+    vit = bw.vit
+    T, B = tp.T, tp.B
+    heads, eps = cfg.num_attention_heads, cfg.layer_norm_eps
+    Hs = cfg.s_attn_hidden_size
+    grads: Grads = {}
+    if tp.kind == "surrogate":
+        dx = torch.zeros((B, T, Hs), dtype=torch.float32, device=dout.device)
+        dx[:, 0, :] = dout
+        _ltt_rungs_backward(tp, dx.reshape(B * T, Hs), grads)
+        return grads
+    na, nb, nc = tp.names
+    dWc, dbc = torch.zeros_like(tp.w_c), torch.zeros((tp.w_c.shape[0],), dtype=torch.float32, device=dout.device)
+    dhb = ops.explainer_head_bwd(dout, tp.hb, B, T, tp.w_c, bool(cfg.explainer_normalize), dWc, dbc)
+    grads[nc + ".weight"], grads[nc + ".bias"] = dWc, dbc
+    dzb = ops.gelu_bwd(dhb, tp.zb)
+    _linear_bwd(pol, grads, nb, dzb, tp.ha)
+    dha = _dgrad(pol, dzb, tp.w_b, out_f32=False)
+    dza = ops.gelu_bwd(dha, tp.za)
+    _linear_bwd(pol, grads, na, dza, tp.h0)
+    dx = _dgrad(pol, dza, tp.w_a, out_f32=True)
+    if vit:
+        dx = _ln_bwd(grads, tp.mlp_ln_name, tp.x_last, dx, tp.mlp_ln[0], 1e-5, None)
+    for prefix, lw, t in reversed(tp.layers):
+        if vit:
+            dx = vit_layer_bwd(pol, lw, prefix, t, dx, tp.masks, T, heads, eps, grads)
+        else:
+            dx = bert_layer_bwd(pol, lw, prefix, t, dx, tp.masks, T, heads, eps, grads)
+    if vit:
+        dx = _ln_bwd(grads, "vit.s_attn_layernorm.0", tp.s_pre_ln, dx, tp.br.final_ln[0], eps, None)
+    _ltt_rungs_backward(tp, dx, grads)
+    return grads
+
+
+class _LttTrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xs, masks, grand, null, cfg, precision, kind, freeze_layer, names, *params):
+        sd = {n: p.detach() for n, p in zip(names, params)}
+        with torch.no_grad():
+            out, cls, tape = ltt_forward_train(sd, cfg, precision, xs, masks, grand, null, kind, freeze_layer)
+        ctx.tape, ctx.names = tape, names
+        ctx.shapes = [p.shape for p in params]
+        ctx.mark_non_differentiable(cls)
+        return out, cls
+
+    @staticmethod
+    def backward(ctx, dout, _dcls):
+        with torch.no_grad():
+            grads = ltt_backward_train(ctx.tape, dout.contiguous().float())
+        ctx.tape = None
+        out = []
+        for i, (n, shp) in enumerate(zip(ctx.names, ctx.shapes)):
+            g = grads.get(n) if ctx.needs_input_grad[9 + i] else None
+            out.append(g.reshape(shp) if g is not None else None)
+        return (None,) * 9 + tuple(out)
+
+
+def _ltt_apply(model, xs, words, grand, null, kind):
+    named = list(model.named_parameters())
+    if named[0][1].device.type != "cuda":
+        raise RuntimeError("autognothi_b200 models run on CUDA only (no CPU fallback)")
+    names = [n for n, _ in named]
+    g = grand.detach() if grand is not None else None
+    nl = null.detach() if null is not None else None
+    return _LttTrainFn.apply(xs, words, g, nl, model.config, model.agb_precision, kind,
+                             getattr(model, "_ltt_freeze_layer", None), names, *[p for _, p in named])
+
+
+def ltt_explainer_forward_train(model, xs: Tensor, words: Tensor, grand: Optional[Tensor], null: Optional[Tensor]
+                                ) -> Tuple[Tensor, Tensor]:
+    """Differentiable (w.r.t. the side ladder and the side explainer) forward of LttViTExplainer / LttBertExplainer
+    -> (phi, backbone probabilities).  The backbone (`*.embeddings`, `*.encoder.layers`, ViT `vit.layernorm`, poolers,
+    `classifier`) never receives gradients on this path: the reference freezes it in train() (models/ltt_vit.py:132-138)."""
+    return _ltt_apply(model, xs, words, grand, null, "explainer")
+
+
+def ltt_surrogate_forward_train(model, xs: Tensor, words: Tensor) -> Tuple[Tensor, Tensor]:
+    """Differentiable forward of LttViTSurrogate / LttBertSurrogate -> (side-ladder probabilities, backbone probabilities).
+    The ladder is one autograd node returning the CLS rows of the side state; the side head (ViT: vit.s_attn_layernorm.0
+    + s_attn_classifier; BERT: bert_s_attn_pooler + s_attn_classifier) and the softmax stay in torch autograd."""
+    s_cls, cls = _ltt_apply(model, xs, words, None, None, "surrogate")
+    named = dict(model.named_parameters())
+    cfg = model.config
+    if hasattr(cfg, "img_px_size"):
+        h = torch.nn.functional.layer_norm(s_cls, (cfg.s_attn_hidden_size,), named["vit.s_attn_layernorm.0.weight"],
+                                           named["vit.s_attn_layernorm.0.bias"], cfg.layer_norm_eps)
+    else:
+        h = torch.tanh(torch.nn.functional.linear(s_cls, named["bert_s_attn_pooler.dense.weight"],
+                                                  named["bert_s_attn_pooler.dense.bias"]))
+    logits = torch.nn.functional.linear(h, named["s_attn_classifier.weight"], named["s_attn_classifier.bias"])
+    return torch.softmax(logits, dim=-1), cls

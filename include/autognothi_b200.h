@@ -224,7 +224,8 @@ int agb_layernorm_bwd(const void* x, int x_is_bf16, const void* dy, int dy_is_bf
                       void* stream);
 /* adjoint of the key-masked attention (reference models/vanilla_vit.py:436-465, vanilla_bert.py:503-537):
  * qkv (rows,T,3H), dctx (rows,T,H) -> dqkv (rows,T,3H); head dim 64, T <= 512 (tcgen05 kernel up to 256, two-pass CUDA-core kernels beyond); a ViT-masked key passes no
- * gradient to Q/K (its logit is the constant 0) but its V row still receives P^T dO. */
+ * gradient to Q/K (its logit is the constant 0) but its V row still receives P^T dO.  Head dims 8 / 16 / 32 (the side
+ * ladders of reference models/ltt_vit.py:386-396, ltt_bert.py:437-451) run a CUDA-core kernel with fp32-staged operands. */
 int agb_masked_attention_bwd(const void* qkv, const void* dctx, int io_is_bf16, const uint32_t* mask, int words,
                              int rows, int T, int H, int heads, int mode, void* dqkv, void* stream);
 /* ViT embedding adjoint (reference models/vanilla_vit.py:242-253): dpos/dcls ACCUMULATED, dpatch (B*(T-1),H) */

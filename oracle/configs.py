@@ -49,6 +49,15 @@ def _bert(hidden, heads, layers, inter, head_hidden, max_pos, vocab=30522, label
     )
 
 
+def _ltt(base: Dict[str, Any], s_hidden: int, s_inter: int, s_head: int, attn_layers: int = 1) -> Dict[str, Any]:
+    """LTT configuration (reference models/ltt_vit.py:14-32, models/ltt_bert.py:20-39) on top of a vanilla one: the explainer_*
+    fields are renamed to explainer_s_* and the side ladder's widths are added."""
+    out = {k: v for k, v in base.items() if k not in ("explainer_attn_num_layers", "explainer_head_hidden_size")}
+    out.update(explainer_s_attn_num_layers=attn_layers, explainer_s_head_hidden_size=s_head, s_attn_hidden_size=s_hidden,
+               s_attn_intermediate_size=s_inter)
+    return out
+
+
 CONFIGS: Dict[str, Dict[str, Any]] = {
     # reduced shapes for fast CPU parity (head dim stays 64, the only size the tensor-core attention tiles)
     "vit_mini": _vit(128, 2, 2, 256, 192),
@@ -67,6 +76,14 @@ CONFIGS: Dict[str, Dict[str, Any]] = {
     "bert_base_128": _bert(768, 12, 12, 3072, 3072, max_pos=128),
     "bert_base_512": _bert(768, 12, 12, 3072, 3072, max_pos=512),
 }
+# LTT (ladder side tuning) variants; side head dim = s_attn_hidden_size / num_attention_heads
+CONFIGS.update({
+    "ltt_vit_mini": _ltt(CONFIGS["vit_mini"], 32, 64, 48),                 # side head dim 16
+    "ltt_vit_tiny": _ltt(CONFIGS["vit_tiny"], 48, 192, 192),               # side head dim 16, 12 ladder rungs
+    "ltt_bert_mini": _ltt(CONFIGS["bert_mini"], 16, 64, 48),               # side head dim 8
+    # reference experiments/bert_base_tayp_ltt/.hparams.json:14-32 with max_position_embeddings = 128 (side head dim 8)
+    "ltt_bert_base_128": _ltt(CONFIGS["bert_base_128"], 96, 384, 3072),
+})
 
 
 def get_config(name: str) -> Dict[str, Any]:

@@ -131,7 +131,7 @@ def explainer_shapes(cfg: Dict[str, Any]) -> List[Tuple[str, Tuple[int, ...]]]:
 def _init_one(name: str, shape: Tuple[int, ...], seed: int) -> np.ndarray:
     u = uniform(name, shape, seed)
     leaf = name.rsplit(".", 1)[-1]
-    if "LayerNorm" in name or "layernorm" in name or (name.startswith("explainer_mlp.0.") and len(shape) == 1):
+    if "LayerNorm" in name or "layernorm" in name or (name.startswith(("explainer_mlp.0.", "s_explainer_mlp.0.")) and len(shape) == 1):
         # LayerNorm affine: weight near 1, bias small (explainer_mlp.0 is a LayerNorm for ViT only,
         # where its parameters are 1-D; for BERT explainer_mlp.0.bias is a Linear bias — same scale)
         return (1.0 + 0.2 * u).astype(np.float32) if leaf == "weight" else (0.1 * u).astype(np.float32)
@@ -145,6 +145,17 @@ def _init_one(name: str, shape: Tuple[int, ...], seed: int) -> np.ndarray:
     return (u * (1.0 / np.sqrt(fan_in))).astype(np.float32)
 
 
+def state_like(shapes: Dict[str, Any], seed: int = 0) -> Dict[str, np.ndarray]:
+    """Synthetic weights for an arbitrary key -> shape table (e.g. `{k: v.shape for k, v in module.state_dict().items()}`):
+    used for the Froyo / LTT classes, whose tables are pinned against the reference by tests/golden/*_keys.json."""
+    out = {name: _init_one(name, tuple(int(d) for d in shape), seed) for name, shape in shapes.items()}
+    if "surrogate_null" in out:
+        C = out["surrogate_null"].shape[-1]
+        out["surrogate_null"] = ((uniform("surrogate_null", out["surrogate_null"].shape, seed) * np.float32(0.5) + np.float32(0.5))
+                                 / np.float32(C)).astype(np.float32)
+    return out
+
+
 def make_state_dict(shapes: List[Tuple[str, Tuple[int, ...]]], seed: int = 0) -> Dict[str, np.ndarray]:
     return {name: _init_one(name, shape, seed) for name, shape in shapes}
 
@@ -155,6 +166,23 @@ def surrogate_state(cfg: Dict[str, Any], seed: int = 0) -> Dict[str, np.ndarray]
 
 def explainer_state(cfg: Dict[str, Any], seed: int = 1) -> Dict[str, np.ndarray]:
     return make_state_dict(explainer_shapes(cfg), seed)
+
+
+def froyo_final_state(cfg: Dict[str, Any], seed: int = 1) -> Dict[str, np.ndarray]:
+    """State dict of the Froyo bundle (reference models/froyo_vit.py:100-138, froyo_bert.py:105-158): backbone and explainer
+    tail from explainer_state(seed), `classifier.*` (+ `bert_pooler.*`) from surrogate_state(seed + 10), the surrogate head
+    `srg_*` from surrogate_state(seed + 20), and a non-trivial `surrogate_null`."""
+    out = dict(explainer_state(cfg, seed))
+    cls, srg = surrogate_state(cfg, seed + 10), surrogate_state(cfg, seed + 20)
+    for k, v in cls.items():
+        if k.startswith(("classifier.", "bert_pooler.")):
+            out[k] = v
+    for k, v in srg.items():
+        if k.startswith(("classifier.", "bert_pooler.")):
+            out["srg_" + k] = v
+    C = cfg["num_labels"]
+    out["surrogate_null"] = (uniform("froyo.surrogate_null", (1, C), seed) * np.float32(0.5) + np.float32(0.5)) / np.float32(C)
+    return out
 
 
 def inputs(cfg: Dict[str, Any], batch: int, seed: int = 0) -> np.ndarray:

@@ -17,3 +17,11 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope="module")
+def agb():
+    """The product's op layer; importing the package raises when the CUDA library is missing (no fallback)."""
+    import autognothi_b200  # noqa: F401
+    from autognothi_b200 import ops
+    return ops

@@ -256,7 +256,137 @@ def gen_surrogate_train_grads():
         print(f"train_surrogate_{name}.npz loss={float(loss):.6e} params={len(norms)} stored={len(out) - 6}")
 
 
+def gen_froyo():
+    """Froyo bundles (reference models/froyo_vit.py:100-171, froyo_bert.py:105-204): one backbone pass, classifier + surrogate
+    heads, explainer tail.  Also the key/shape tables of every Froyo class."""
+    ref_fvit = __import__(f"{REF_NAME}.models.froyo_vit", fromlist=["x"])
+    ref_fbert = __import__(f"{REF_NAME}.models.froyo_bert", fromlist=["x"])
+    keys = {}
+    for name, B in [("vit_mini", 3), ("bert_mini", 3), ("vit_tiny", 2)]:
+        cfg = ocfg.get_config(name)
+        vit = ocfg.is_vit(cfg)
+        n = ocfg.n_players(cfg)
+        mod = ref_fvit if vit else ref_fbert
+        fcfg = (mod.FroyoViTConfig if vit else mod.FroyoBertConfig)(**cfg)
+        final = (mod.FroyoViTFinal if vit else mod.FroyoBertFinal)(fcfg)
+        classes = ("FroyoViT" if vit else "FroyoBert")
+        keys[name] = {"final": {k: list(v.shape) for k, v in final.state_dict().items()}}
+        for role in ("Classifier", "Surrogate", "Explainer"):
+            m = getattr(mod, classes + role)(fcfg)
+            m.train()
+            keys[name][role.lower()] = {k: list(v.shape) for k, v in m.state_dict().items()}
+            keys[name][role.lower() + "_trainable"] = sorted(k for k, p in m.named_parameters() if p.requires_grad)
+        final.load_state_dict(to_torch_state(synth.froyo_final_state(cfg, seed=1)), strict=True)
+        final.eval()
+        xs = torch.from_numpy(synth.inputs(cfg, B, seed=0))
+        torch.manual_seed(3407)
+        masks = ref_shapley.mask_shapley_new(2 * B, n)[:B]
+        out = {}
+        for tag, m in (("ones", torch.ones((B, n), dtype=torch.long)), ("masked", masks)):
+            tok = torch.cat([torch.ones((B, 1), dtype=torch.long), m], dim=1)     # recipes' _fw_xs_preprocess: CLS column
+            if vit:
+                cls, phi = final(xs, tok, None, None)
+            else:
+                cls, phi = final(xs, tok, torch.zeros_like(xs))
+            out[f"{tag}_cls"], out[f"{tag}_phi"] = cls.numpy(), phi.numpy()
+        out["masks"] = masks.numpy().astype(np.int8)
+        np.savez_compressed(os.path.join(HERE, f"froyo_{name}.npz"), **out)
+        print(f"froyo_{name}.npz cls{tuple(out['ones_cls'].shape)} phi{tuple(out['ones_phi'].shape)}")
+    with open(os.path.join(HERE, "froyo_keys.json"), "w") as f:
+        json.dump(keys, f, indent=0, sort_keys=True)
+
+
+def gen_ltt():
+    """LTT variants (reference models/ltt_{vit,bert}.py): surrogate (side + backbone probabilities) on coalition masks,
+    explainer, bundle; side-ladder training gradients from the reference's autograd (eval() mode: dropout = identity);
+    key/shape tables and the trainable sets of every class."""
+    ref_lvit = __import__(f"{REF_NAME}.models.ltt_vit", fromlist=["x"])
+    ref_lbert = __import__(f"{REF_NAME}.models.ltt_bert", fromlist=["x"])
+    keys = {}
+    for name, B, S in [("ltt_vit_mini", 2, 4), ("ltt_bert_mini", 3, 4), ("ltt_vit_tiny", 1, 2), ("ltt_bert_base_128", 1, 2)]:
+        cfg = ocfg.get_config(name)
+        vit = ocfg.is_vit(cfg)
+        n = ocfg.n_players(cfg)
+        mod = ref_lvit if vit else ref_lbert
+        pre = "LttViT" if vit else "LttBert"
+        lcfg = getattr(mod, pre + "Config")(**cfg)
+        models = {r: getattr(mod, pre + r)(lcfg) for r in ("Surrogate", "Explainer", "Final")}
+        keys[name] = {}
+        for r, m in models.items():
+            m.train()
+            keys[name][r.lower()] = {k: list(v.shape) for k, v in m.state_dict().items()}
+            keys[name][r.lower() + "_trainable"] = sorted(k for k, p in m.named_parameters() if p.requires_grad)
+        for i, (r, m) in enumerate(models.items()):
+            m.load_state_dict(to_torch_state(synth.state_like({k: v.shape for k, v in m.state_dict().items()}, seed=30 + i)), strict=True)
+            m.eval()
+        srg, exp, fin = models["Surrogate"], models["Explainer"], models["Final"]
+        xs = torch.from_numpy(synth.inputs(cfg, B, seed=0))
+        torch.manual_seed(3407)
+        masks = ref_shapley.mask_shapley_new(B * S, n)
+        cls_col = lambda m: torch.cat([torch.ones((m.shape[0], 1), dtype=torch.long), m], dim=1)   # noqa: E731
+        xs_ext = xs.repeat_interleave(S, dim=0)
+        ones = torch.ones((B, n), dtype=torch.long)
+        tt = (lambda x: ()) if vit else (lambda x: (torch.zeros_like(x),))
+        v_side, v_main = srg(xs_ext, cls_col(masks), *tt(xs_ext))
+        grand, _ = srg(xs, cls_col(ones), *tt(xs))
+        null = torch.from_numpy(synth.state_like({"surrogate_null": (1, cfg["num_labels"])}, seed=7)["surrogate_null"])
+        phi, e_main = exp(xs, cls_col(ones), *tt(xs), grand, null)
+        phi_m, _ = exp(xs, cls_col(masks.reshape(B, S, n)[:, 0, :]), *tt(xs), grand, null)
+        f_cls, f_phi = fin(xs, cls_col(ones), *tt(xs))
+        out = dict(masks=masks.numpy().astype(np.int8), v_side=v_side.numpy(), v_main=v_main.numpy(), grand=grand.numpy(),
+                   null=null.numpy(), phi=phi.numpy(), e_main=e_main.numpy(), phi_masked=phi_m.numpy(), f_cls=f_cls.numpy(),
+                   f_phi=f_phi.numpy(), meta=np.array([B, S, n], dtype=np.int64))
+        if "mini" in name:
+            # explainer training step: only the side ladder + side explainer receive gradients (train() freezes the rest)
+            exp.train()
+            exp.eval()      # keep the freezes, drop the dropout
+            for k, p_ in exp.named_parameters():
+                p_.requires_grad_(k in keys[name]["explainer_trainable"])
+            with torch.enable_grad():
+                phi_g, _ = exp(xs, cls_col(ones), *tt(xs), grand, null)
+                loss = ref_shapley.loss_shapley_new(B, S, n, masks.reshape(B, S, n), null, v_side, grand, phi_g)
+                loss.backward()
+            out["train_loss"] = loss.detach().numpy()
+            names, vals = [], []
+            for k, p_ in exp.named_parameters():
+                if p_.grad is None:
+                    continue
+                names.append(k); vals.append(float(p_.grad.norm()))
+                if p_.grad.numel() <= 4096:
+                    out["grad::" + k] = p_.grad.numpy()
+            out["norm_names"], out["norm_values"] = np.array(names), np.array(vals, dtype=np.float64)
+            # surrogate training step (KL to the frozen backbone's own prediction, scripts/train_surrogate.py:131-150)
+            srg.train(); srg.eval()
+            for k, p_ in srg.named_parameters():
+                p_.requires_grad_(k in keys[name]["surrogate_trainable"])
+            m1 = masks.reshape(B, S, n)[:, 1, :].contiguous()
+            # teacher distribution: a fixed synthetic one, far from the student, so that the KL and its gradients are
+            # well conditioned (the two ladders' outputs on nearby masks differ by ~1e-3, which makes the KL ~1e-6)
+            target = torch.softmax(3.0 * torch.from_numpy(synth.uniform("ltt.target", (B, cfg["num_labels"]), 5)), dim=-1)
+            with torch.enable_grad():
+                side, main = srg(xs, cls_col(m1), *tt(xs))
+                sloss = ref_shapley.loss_logits_kl_divergence(target, side)
+                sloss.backward()
+            out["srg_loss"], out["srg_side"], out["srg_target"] = sloss.detach().numpy(), side.detach().numpy(), target.numpy()
+            names, vals = [], []
+            for k, p_ in srg.named_parameters():
+                if p_.grad is None:
+                    continue
+                names.append(k); vals.append(float(p_.grad.norm()))
+            out["srg_norm_names"], out["srg_norm_values"] = np.array(names), np.array(vals, dtype=np.float64)
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+        print(f"{name}.npz v_side{tuple(v_side.shape)} phi{tuple(phi.shape)}")
+    with open(os.path.join(HERE, "ltt_keys.json"), "w") as f:
+        json.dump(keys, f, indent=0, sort_keys=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "ltt":
+        gen_ltt()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "froyo":
+        gen_froyo()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "train":
         gen_train_grads(only=sys.argv[2:] or None)
         sys.exit(0)
@@ -271,3 +401,5 @@ if __name__ == "__main__":
     gen_models()
     gen_train_grads()
     gen_surrogate_train_grads()
+    gen_froyo()
+    gen_ltt()

@@ -1,0 +1,190 @@
+"""LTT (ladder side tuning) variants on the GPU vs goldens from the reference's own classes (reference
+models/ltt_{vit,bert}.py, recipes/ltt_{vit,bert}.py).  Goldens: tests/golden/make_golden.py ltt; weights are
+oracle.synth.state_like over the class's own key table (pinned against the reference by tests/test_ltt_host.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import configs as ocfg
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+def _np(t):
+    return t.detach().float().cpu().numpy()
+
+
+def _recipe(name):
+    if "vit" in name:
+        from autognothi_b200.recipes.ltt_vit import ltt_vit_recipe
+        return ltt_vit_recipe()
+    from autognothi_b200.recipes.ltt_bert import ltt_bert_recipe
+    return ltt_bert_recipe()
+
+
+def _models(name, precision):
+    rec = _recipe(name)
+    cfgd = ocfg.get_config(name)
+    cfg = rec.t_config(**cfgd)
+    out = []
+    for i, cls in enumerate((rec.t_surrogate, rec.t_explainer, rec.t_final)):      # seeds 30, 31, 32 as in make_golden.py
+        m = cls(cfg)
+        sd = synth.state_like({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=30 + i)
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+        m = m.to(DEV).eval()
+        m.agb_precision = precision
+        out.append(m)
+    return rec, cfgd, cfg, out
+
+
+def _close_attr(got, ref, precision):
+    if precision == "fp32":
+        np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-4 * np.abs(ref).max())
+    else:
+        a, b = got.reshape(-1).astype(np.float64), ref.reshape(-1).astype(np.float64)
+        r = float(np.corrcoef(a, b)[0, 1])
+        l2 = float(np.linalg.norm(a - b) / np.linalg.norm(b))
+        assert r >= 0.999 and l2 <= 1e-2, (r, l2)
+
+
+@pytest.mark.parametrize("name,precision", [("ltt_vit_mini", "fp32"), ("ltt_bert_mini", "fp32"), ("ltt_vit_tiny", "fp32"),
+                                            ("ltt_bert_base_128", "fp32"), ("ltt_vit_tiny", "bf16"),
+                                            ("ltt_bert_base_128", "bf16"), ("ltt_vit_mini", "bf16")])
+def test_ltt_forward_vs_reference_golden(agb, golden_dir, name, precision):
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    B, S, n = (int(v) for v in g["meta"])
+    rec, cfgd, cfg, (srg, exp, fin) = _models(name, precision)
+    xs = torch.from_numpy(synth.inputs(cfgd, B, seed=0)).to(DEV)
+    masks = torch.from_numpy(g["masks"].astype(np.int64)).to(DEV)
+    ones = torch.ones((B, n), dtype=torch.int64, device=DEV)
+    grand, null = torch.from_numpy(g["grand"]).to(DEV), torch.from_numpy(g["null"]).to(DEV)
+    with torch.no_grad():
+        v_side, v_main = rec.fw_surrogate(srg, xs.repeat_interleave(S, dim=0), masks)      # reference-shaped call
+        v_side2, v_main2 = rec.fw_surrogate(srg, xs, masks.reshape(B, S, n))               # (B, S, n) fast path
+        grand_got, _ = rec.fw_surrogate(srg, xs, ones)
+        phi, e_main = rec.fw_explainer(exp, xs, ones, grand, null)
+        phi_m, _ = rec.fw_explainer(exp, xs, masks.reshape(B, S, n)[:, 0, :].contiguous(), grand, null)
+        f_cls, f_phi = rec.fw_final(fin, xs)
+    ptol = dict(rtol=1e-4, atol=2e-6) if precision == "fp32" else dict(atol=2e-2)
+    if precision == "fp32":
+        assert torch.equal(v_side, v_side2) and torch.equal(v_main, v_main2)
+    else:
+        np.testing.assert_allclose(_np(v_side), _np(v_side2), atol=5e-3)      # first-block sharing reorders bf16 roundings
+    np.testing.assert_allclose(_np(v_side), g["v_side"], **ptol)
+    np.testing.assert_allclose(_np(v_main), g["v_main"], **ptol)
+    np.testing.assert_allclose(_np(grand_got), g["grand"], **ptol)
+    np.testing.assert_allclose(_np(e_main), g["e_main"], **ptol)
+    np.testing.assert_allclose(_np(f_cls), g["f_cls"], **ptol)
+    _close_attr(_np(phi), g["phi"], precision)
+    _close_attr(_np(phi_m), g["phi_masked"], precision)
+    _close_attr(_np(f_phi), g["f_phi"], precision)
+
+
+@pytest.mark.parametrize("name", ["ltt_vit_mini", "ltt_bert_mini"])
+def test_ltt_conversion_chain_and_final_coherency(agb, name):
+    """classifier -> surrogate -> explainer -> bundle through the recipe's conv_* rules; the bundle (ladder 0 = surrogate,
+    ladder 1 = explainer, ONE backbone pass) equals the separate calls (reference scripts/train_all.py:199-215)."""
+    rec = _recipe(name)
+    cfgd = ocfg.get_config(name)
+    cfg = rec.t_config(**cfgd)
+    n = rec.n_players(cfg)
+    from autognothi_b200.recipes.ltt_bert import LttBertMisc
+    misc = LttBertMisc(tokenizer=None) if "bert" in name else None
+    classifier = rec.t_classifier(cfg)
+    sd = synth.state_like({k: tuple(v.shape) for k, v in classifier.state_dict().items()}, seed=41)
+    classifier.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    classifier = classifier.to(DEV).eval()
+    surrogate = rec.conv_classifier_surrogate(cfg, misc, classifier)
+    explainer = rec.conv_surrogate_explainer(cfg, misc, surrogate)
+    with torch.no_grad():     # make the explainer's ladder differ from the surrogate's, as after training
+        for k, p in explainer.named_parameters():
+            if "s_attn_maps" in k and k.endswith("weight"):
+                p.mul_(0.9)
+    for m in (classifier, surrogate, explainer):
+        m.agb_precision = "fp32"
+    final = rec.conv_explainer_final(cfg, misc, classifier, surrogate, explainer).eval()
+    final.agb_precision = "fp32"
+    B = 2
+    xs = torch.from_numpy(synth.inputs(cfgd, B, seed=4)).to(DEV)
+    ones = torch.ones((B, n), dtype=torch.int64, device=DEV)
+    with torch.no_grad():
+        logits, phi = rec.fw_final(final, xs)
+        _, ys = rec.fw_classifier(classifier, xs, ones)
+        grand, _ = rec.fw_surrogate(surrogate, xs, ones)
+        null, _ = rec.fw_surrogate(surrogate, rec.gen_null(cfg, misc, DEV), torch.ones((1, n), dtype=torch.int64, device=DEV))
+        phi_sep, _ = rec.fw_explainer(explainer, xs, ones, grand, null)
+    np.testing.assert_allclose(_np(final.surrogate_null), _np(null), atol=1e-6)
+    np.testing.assert_allclose(_np(logits), _np(ys), atol=1e-5)
+    np.testing.assert_allclose(_np(phi), _np(phi_sep), atol=1e-5 * max(1.0, float(phi_sep.abs().max())))
+
+
+@pytest.mark.parametrize("name,precision", [("ltt_vit_mini", "fp32"), ("ltt_bert_mini", "fp32"), ("ltt_vit_mini", "bf16"),
+                                            ("ltt_bert_mini", "bf16")])
+def test_ltt_explainer_training_gradients(agb, golden_dir, name, precision):
+    """loss.backward() through the side ladder (narrow-head attention adjoint, map wgrads from the frozen backbone's
+    activations) vs the reference's autograd; the backbone receives nothing."""
+    from autognothi_b200.models import shapley as ash
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    B, S, n = (int(v) for v in g["meta"])
+    rec, cfgd, cfg, (srg, exp, fin) = _models(name, precision)
+    exp.train()
+    xs = torch.from_numpy(synth.inputs(cfgd, B, seed=0)).to(DEV)
+    masks = torch.from_numpy(g["masks"].astype(np.int64)).to(DEV).reshape(B, S, n)
+    v_side, grand, null = (torch.from_numpy(g[k]).to(DEV) for k in ("v_side", "grand", "null"))
+    ones = torch.ones((B, n), dtype=torch.int64, device=DEV)
+    phi, main = rec.fw_explainer(exp, xs, ones, grand, null)
+    assert phi.requires_grad and not main.requires_grad
+    loss = ash.loss_shapley_new(B, S, n, masks, null, v_side, grand, phi)
+    loss.backward()
+    ref_loss = float(g["train_loss"])
+    assert abs(float(loss.detach()) - ref_loss) <= (1e-4 if precision == "fp32" else 3e-2) * abs(ref_loss)
+    ref_norms = dict(zip([str(s) for s in g["norm_names"]], g["norm_values"]))
+    floor = 1e-5 * max(ref_norms.values())
+    params = dict(exp.named_parameters())
+    assert {k for k, p in params.items() if p.requires_grad} == set(ref_norms)
+    for k, p in params.items():
+        if k not in ref_norms:
+            assert p.grad is None, k
+            continue
+        assert p.grad is not None, k
+        got = float(p.grad.norm())
+        if precision == "fp32":
+            assert abs(got - ref_norms[k]) <= 2e-3 * ref_norms[k] + floor, f"{k}: |grad| {got} vs {ref_norms[k]}"
+    for key in g.files:
+        if not key.startswith("grad::"):
+            continue
+        k = key[len("grad::"):]
+        ref, got = g[key].reshape(-1).astype(np.float64), _np(params[k].grad).reshape(-1).astype(np.float64)
+        if precision == "fp32":
+            np.testing.assert_allclose(got, ref, rtol=2e-3, atol=2e-3 * np.abs(ref).max() + floor, err_msg=k)
+        elif np.linalg.norm(ref) > 100 * floor:
+            cos = float(ref @ got / (np.linalg.norm(ref) * np.linalg.norm(got) + 1e-30))
+            assert cos > 0.99, f"{k}: cosine {cos}"
+
+
+@pytest.mark.parametrize("name", ["ltt_vit_mini", "ltt_bert_mini"])
+def test_ltt_surrogate_training_gradients(agb, golden_dir, name):
+    from autognothi_b200.models import shapley as ash
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    B, S, n = (int(v) for v in g["meta"])
+    rec, cfgd, cfg, (srg, exp, fin) = _models(name, "fp32")
+    srg.train()
+    xs = torch.from_numpy(synth.inputs(cfgd, B, seed=0)).to(DEV)
+    m1 = torch.from_numpy(g["masks"].astype(np.int64)).to(DEV).reshape(B, S, n)[:, 1, :].contiguous()
+    side, main = rec.fw_surrogate(srg, xs, m1)
+    np.testing.assert_allclose(_np(side), g["srg_side"], rtol=1e-4, atol=2e-6)
+    loss = ash.loss_logits_kl_divergence(torch.from_numpy(g["srg_target"]).to(DEV), side)
+    loss.backward()
+    np.testing.assert_allclose(float(loss.detach()), float(g["srg_loss"]), rtol=1e-4)
+    ref_norms = dict(zip([str(s) for s in g["srg_norm_names"]], g["srg_norm_values"]))
+    floor = 1e-5 * max(ref_norms.values())
+    for k, p in srg.named_parameters():
+        if k not in ref_norms:
+            assert p.grad is None, k
+            continue
+        got = float(p.grad.norm())
+        assert abs(got - ref_norms[k]) <= 2e-3 * ref_norms[k] + floor, f"{k}: |grad| {got} vs {ref_norms[k]}"

@@ -37,13 +37,6 @@ def rel_l2(a, b):
     return float(np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b.astype(np.float64)))
 
 
-@pytest.fixture(scope="module")
-def agb():
-    import autognothi_b200  # noqa: F401  (raises if the CUDA library is missing)
-    from autognothi_b200 import ops
-    return ops
-
-
 # ------------------------------------------------------------------------------------------------
 # masks: bit-exact
 # ------------------------------------------------------------------------------------------------
