@@ -322,6 +322,133 @@ int cls_attention(const void* q, long long ldq, const void* kv, long long ldkv, 
   return AGB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Narrow heads (head dim 8 / 16 / 32, bf16 I/O): the side ladders of the LTT variants (reference models/ltt_vit.py:386-396,
+// hidden size s_attn_hidden_size split over the backbone's head count) evaluated on every coalition row.  One CTA per
+// (row, head): K and V staged once in shared memory as fp32, every thread owns TWO queries and streams the keys with an
+// online softmax (exp2 domain), so each broadcast K/V read feeds 4 D FMAs.  fp32 math throughout; P never leaves registers.
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128)
+attention_narrow_kernel(const bf16* __restrict__ qkv, const uint32_t* __restrict__ mask, int words, int T, int H, int heads,
+                        int mode, float scale_log2, bf16* __restrict__ ctx) {
+  extern __shared__ __align__(16) float sm_n[];
+  float* sK = sm_n;            // T x D
+  float* sV = sK + T * D;      // T x D
+  uint32_t* sM = reinterpret_cast<uint32_t*>(sV + T * D);
+  const int row = blockIdx.x / heads, head = blockIdx.x % heads;
+  const bf16* base = qkv + (long long)row * T * 3 * H + head * D;
+  constexpr int V8 = D / 8;
+  for (int e = threadIdx.x; e < T * V8; e += blockDim.x) {
+    const int t = e / V8, v = e % V8;
+    const uint4 k4 = *reinterpret_cast<const uint4*>(base + (long long)t * 3 * H + H + v * 8);
+    const uint4 v4 = *reinterpret_cast<const uint4*>(base + (long long)t * 3 * H + 2 * H + v * 8);
+    const uint32_t kw[4] = {k4.x, k4.y, k4.z, k4.w}, vw[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      sK[t * D + v * 8 + 2 * u] = __uint_as_float(kw[u] << 16);
+      sK[t * D + v * 8 + 2 * u + 1] = __uint_as_float(kw[u] & 0xFFFF0000u);
+      sV[t * D + v * 8 + 2 * u] = __uint_as_float(vw[u] << 16);
+      sV[t * D + v * 8 + 2 * u + 1] = __uint_as_float(vw[u] & 0xFFFF0000u);
+    }
+  }
+  for (int e = threadIdx.x; e < words; e += blockDim.x) sM[e] = mask[(long long)row * words + e];
+  __syncthreads();
+  const int half = (T + 1) / 2;
+  for (int i0 = threadIdx.x; i0 < half; i0 += blockDim.x) {
+    const int i1 = i0 + half;                 // second query of this thread (may fall off the end)
+    const bool has1 = i1 < T;
+    float q0[D], q1[D], o0[D], o1[D];
+#pragma unroll
+    for (int v = 0; v < V8; ++v) {
+      const uint4 a = *reinterpret_cast<const uint4*>(base + (long long)i0 * 3 * H + v * 8);
+      const uint4 b = has1 ? *reinterpret_cast<const uint4*>(base + (long long)i1 * 3 * H + v * 8) : make_uint4(0, 0, 0, 0);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        q0[v * 8 + 2 * u] = __uint_as_float(aw[u] << 16) * scale_log2;
+        q0[v * 8 + 2 * u + 1] = __uint_as_float(aw[u] & 0xFFFF0000u) * scale_log2;
+        q1[v * 8 + 2 * u] = __uint_as_float(bw[u] << 16) * scale_log2;
+        q1[v * 8 + 2 * u + 1] = __uint_as_float(bw[u] & 0xFFFF0000u) * scale_log2;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) o0[k] = o1[k] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    for (int j = 0; j < T; ++j) {
+      const bool keep = (sM[j >> 5] >> (j & 31)) & 1u;        // uniform over the CTA
+      if (!keep && mode != AGB_MASK_MUL0) continue;            // additive -inf: the key does not exist
+      float s0 = 0.f, s1 = 0.f;
+      if (keep) {
+        const float4* kr = reinterpret_cast<const float4*>(sK + j * D);
+#pragma unroll
+        for (int v = 0; v < D / 4; ++v) {
+          const float4 kk = kr[v];
+          s0 = fmaf(q0[4 * v], kk.x, s0); s0 = fmaf(q0[4 * v + 1], kk.y, s0);
+          s0 = fmaf(q0[4 * v + 2], kk.z, s0); s0 = fmaf(q0[4 * v + 3], kk.w, s0);
+          s1 = fmaf(q1[4 * v], kk.x, s1); s1 = fmaf(q1[4 * v + 1], kk.y, s1);
+          s1 = fmaf(q1[4 * v + 2], kk.z, s1); s1 = fmaf(q1[4 * v + 3], kk.w, s1);
+        }
+      }                                                        // ViT-masked key: logit := 0, its V row still counts
+      if (s0 > m0) {
+        const float c = exp2f(m0 - s0);
+        l0 *= c;
+#pragma unroll
+        for (int k = 0; k < D; ++k) o0[k] *= c;
+        m0 = s0;
+      }
+      if (s1 > m1) {
+        const float c = exp2f(m1 - s1);
+        l1 *= c;
+#pragma unroll
+        for (int k = 0; k < D; ++k) o1[k] *= c;
+        m1 = s1;
+      }
+      const float p0 = exp2f(s0 - m0), p1 = exp2f(s1 - m1);
+      l0 += p0;
+      l1 += p1;
+      const float4* vr = reinterpret_cast<const float4*>(sV + j * D);
+#pragma unroll
+      for (int v = 0; v < D / 4; ++v) {
+        const float4 vv = vr[v];
+        o0[4 * v] = fmaf(p0, vv.x, o0[4 * v]); o0[4 * v + 1] = fmaf(p0, vv.y, o0[4 * v + 1]);
+        o0[4 * v + 2] = fmaf(p0, vv.z, o0[4 * v + 2]); o0[4 * v + 3] = fmaf(p0, vv.w, o0[4 * v + 3]);
+        o1[4 * v] = fmaf(p1, vv.x, o1[4 * v]); o1[4 * v + 1] = fmaf(p1, vv.y, o1[4 * v + 1]);
+        o1[4 * v + 2] = fmaf(p1, vv.z, o1[4 * v + 2]); o1[4 * v + 3] = fmaf(p1, vv.w, o1[4 * v + 3]);
+      }
+    }
+    const float r0 = l0 > 0.f ? 1.f / l0 : 0.f, r1 = l1 > 0.f ? 1.f / l1 : 0.f;
+    bf16* c0 = ctx + ((long long)row * T + i0) * H + head * D;
+    bf16* c1 = ctx + ((long long)row * T + i1) * H + head * D;
+#pragma unroll
+    for (int v = 0; v < V8; ++v) {
+      uint32_t w0[4], w1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(o0[v * 8 + 2 * u] * r0, o0[v * 8 + 2 * u + 1] * r0);
+        const __nv_bfloat162 b = __floats2bfloat162_rn(o1[v * 8 + 2 * u] * r1, o1[v * 8 + 2 * u + 1] * r1);
+        w0[u] = *reinterpret_cast<const uint32_t*>(&a);
+        w1[u] = *reinterpret_cast<const uint32_t*>(&b);
+      }
+      *reinterpret_cast<uint4*>(c0 + v * 8) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+      if (has1) *reinterpret_cast<uint4*>(c1 + v * 8) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+    }
+  }
+}
+
+template <int D>
+static int launch_attention_narrow(const bf16* qkv, const uint32_t* mask, int words, int rows, int T, int H, int heads,
+                                   int mode, bf16* ctx, cudaStream_t st) {
+  const size_t smem = (size_t)2 * T * D * sizeof(float) + (size_t)words * sizeof(uint32_t);
+  if (smem > 227 * 1024) return AGB_ERR_UNSUPPORTED;
+  AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_narrow_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int threads = min(128, (((T + 1) / 2 + 31) / 32) * 32);
+  attention_narrow_kernel<D><<<rows * heads, threads, smem, st>>>(qkv, mask, words, T, H, heads, mode,
+                                                                   rsqrtf((float)D) * 1.4426950408889634f, ctx);
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
 int attention_simt(const void* qkv, int io_bf16, const uint32_t* mask, int words, int rows, int T, int H,
                    int heads, int mode, void* ctx, cudaStream_t st) {
   AGB_REQUIRE(rows >= 0 && T > 0 && heads > 0 && H % heads == 0, "attention shape");
@@ -331,6 +458,15 @@ int attention_simt(const void* qkv, int io_bf16, const uint32_t* mask, int words
   AGB_REQUIRE(d <= 128, "head dim <= 128");
   if (rows == 0) return AGB_OK;
   AGB_REQUIRE(qkv && mask && ctx, "null pointer");
+  if (io_bf16 && (d == 8 || d == 16 || d == 32) && (H % 8) == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(ctx) & 15) == 0) {
+    const bf16* q16 = static_cast<const bf16*>(qkv);
+    bf16* c16 = static_cast<bf16*>(ctx);
+    const int rc = d == 8 ? launch_attention_narrow<8>(q16, mask, words, rows, T, H, heads, mode, c16, st)
+                 : d == 16 ? launch_attention_narrow<16>(q16, mask, words, rows, T, H, heads, mode, c16, st)
+                           : launch_attention_narrow<32>(q16, mask, words, rows, T, H, heads, mode, c16, st);
+    if (rc != AGB_ERR_UNSUPPORTED) return rc;
+  }
   AGB_REQUIRE(rows <= 65535 && heads <= 65535, "grid limits (chunk the rows)");
   const int nw = 4;
   dim3 grid((T + nw - 1) / nw, heads, rows);

@@ -122,11 +122,80 @@ def surrogate_training():
           f"{B * fl / ms * 1e-9:7.1f} TFLOP/s (4 x 35.1 GFLOP per sample)")
 
 
+def ltt():
+    """LTT (ladder side tuning): masked surrogate evals/s through the side ladder and side-ladder explainer training."""
+    import bench
+    from autognothi_b200.recipes.ltt_bert import ltt_bert_recipe
+    from autognothi_b200.recipes.ltt_vit import ltt_vit_recipe
+    dev = torch.device("cuda:0")
+    vit_cfg = {k: v for k, v in bench.VIT_BASE.items() if k not in ("explainer_attn_num_layers", "explainer_head_hidden_size")}
+    vit_cfg.update(explainer_s_attn_num_layers=1, explainer_s_head_hidden_size=3072, s_attn_hidden_size=192, s_attn_intermediate_size=768)
+    # reference experiments/bert_base_tayp_ltt/.hparams.json:14-32 with max_position_embeddings = 128
+    bert_cfg = dict(attention_probs_dropout_prob=0.1, explainer_s_attn_num_layers=1, explainer_s_head_hidden_size=3072,
+                    explainer_normalize=True, hidden_dropout_prob=0.1, hidden_size=768, intermediate_size=3072, layer_norm_eps=1e-12,
+                    max_position_embeddings=128, num_attention_heads=12, num_hidden_layers=12, num_labels=2, pad_token_id=0,
+                    s_attn_hidden_size=96, s_attn_intermediate_size=384, type_vocab_size=2, vocab_size=30522)
+    for tag, rec, cfgd in (("ViT-B/16 + ladder 192", ltt_vit_recipe(), vit_cfg), ("BERT-base T=128 + ladder 96", ltt_bert_recipe(), bert_cfg)):
+        cfg = rec.t_config(**cfgd)
+        n = rec.n_players(cfg)
+        torch.manual_seed(3407)
+        srg = rec.t_surrogate(cfg).to(dev).eval()
+        srg.agb_precision = "bf16"
+        B, S = 32, 32
+        if "ViT" in tag:
+            xs = torch.randn(B, 3, 224, 224, device=dev)
+        else:
+            xs = torch.randint(1000, 30000, (B, n + 1), device=dev)
+            xs[:, 0] = 101
+        ones = ash.PackedMasks.ones(B, n, dev)
+
+        def step_eval():
+            pm = ash.mask_shapley_new(B * S, n, device=dev, rng="philox", seed=1, offset=0, packed=True)
+            with torch.no_grad():
+                return rec.fw_surrogate(srg, xs, pm)[0]
+
+        ms = timed(step_eval, iters=6, warm=3)
+        print(f"ltt {tag}: {B * S} masked evals (side + backbone heads) in {ms:7.2f} ms  {B * S / ms * 1e3:9.0f} evals/s")
+        exp = rec.conv_surrogate_explainer(cfg, None, srg).train()
+        exp.agb_precision = "bf16"
+        opt = torch.optim.AdamW([p for p in exp.parameters() if p.requires_grad], lr=1e-5, fused=True)
+        with torch.no_grad():
+            null = rec.fw_surrogate(srg, rec.gen_null(cfg, type("M", (), {"tokenizer": None})(), dev), ash.PackedMasks.ones(1, n, dev))[0]
+        state = {"i": 0}
+
+        def step_train():
+            pm = ash.mask_shapley_new(B * S, n, device=dev, rng="philox", seed=2, offset=state["i"] * B * S, packed=True)
+            state["i"] += 1
+            with torch.no_grad():
+                v_s = rec.fw_surrogate(srg, xs, pm)[0]
+                grand = rec.fw_surrogate(srg, xs, ones)[0]
+            opt.zero_grad(set_to_none=True)
+            phi, _ = rec.fw_explainer(exp, xs, ones, grand, null)
+            loss = ash.loss_shapley_new(B, S, n, pm, null, v_s, grand, phi)
+            loss.backward()
+            opt.step()
+            return loss
+
+        ms = timed(step_train, iters=4, warm=2)
+        print(f"ltt {tag}: explainer (side ladder) training step, {B} samples x {S} coalitions in {ms:7.2f} ms  {B / ms * 1e3:8.0f} samples/s")
+        if "profile" in sys.argv:
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                step_eval()
+                torch.cuda.synchronize()
+            rows = [(k.key, k.device_time_total / 1e3, k.count) for k in prof.key_averages() if k.device_time_total > 0]
+            rows.sort(key=lambda r: -r[1])
+            for k, t, c in rows[:14]:
+                print(f"  {t:8.3f} ms  x{c:<4d} {k[:110]}")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["kernelshap", "bert", "surrogate"]
+    which = sys.argv[1:] or ["kernelshap", "bert", "surrogate", "ltt"]
     if "kernelshap" in which:
         kernelshap()
     if "bert" in which:
         bert_eval()
     if "surrogate" in which:
         surrogate_training()
+    if "ltt" in which:
+        ltt()
