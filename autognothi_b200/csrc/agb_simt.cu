@@ -335,7 +335,10 @@ attention_narrow_kernel(const bf16* __restrict__ qkv, const uint32_t* __restrict
   extern __shared__ __align__(16) float sm_n[];
   float* sK = sm_n;            // T x D
   float* sV = sK + T * D;      // T x D
-  uint32_t* sM = reinterpret_cast<uint32_t*>(sV + T * D);
+  float* sVm = sV + T * D;     // D: sum of the V rows of the ViT-masked keys
+  int* sIdx = reinterpret_cast<int*>(sVm + D);   // T: indices of the kept keys
+  int* sCnt = sIdx + T;
+  uint32_t* sM = reinterpret_cast<uint32_t*>(sCnt + 1);
   const int row = blockIdx.x / heads, head = blockIdx.x % heads;
   const bf16* base = qkv + (long long)row * T * 3 * H + head * D;
   constexpr int V8 = D / 8;
@@ -353,7 +356,32 @@ attention_narrow_kernel(const bf16* __restrict__ qkv, const uint32_t* __restrict
     }
   }
   for (int e = threadIdx.x; e < words; e += blockDim.x) sM[e] = mask[(long long)row * words + e];
+  for (int e = threadIdx.x; e < D; e += blockDim.x) sVm[e] = 0.f;
   __syncthreads();
+  // kept keys compacted (one warp, ballot prefix); ViT-masked keys all carry the logit 0, so their V rows are summed
+  // once per (row, head) and enter the softmax as ONE virtual key of weight n_masked — exact, and it halves the key
+  // loop at the sampler's average coalition size
+  if (threadIdx.x < 32) {
+    int cnt = 0;
+    for (int j0 = 0; j0 < T; j0 += 32) {
+      const int j = j0 + threadIdx.x;
+      const bool keep = j < T && ((sM[j >> 5] >> (j & 31)) & 1u);
+      const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+      if (keep) sIdx[cnt + __popc(bal & ((1u << threadIdx.x) - 1u))] = j;
+      cnt += __popc(bal);
+    }
+    if (threadIdx.x == 0) *sCnt = cnt;
+  }
+  if (mode == AGB_MASK_MUL0) {
+    const int c = threadIdx.x % D, part = threadIdx.x / D, parts = blockDim.x / D;
+    float acc = 0.f;
+    for (int j = part; j < T; j += parts)
+      if (!((sM[j >> 5] >> (j & 31)) & 1u)) acc += sV[j * D + c];
+    atomicAdd(&sVm[c], acc);
+  }
+  __syncthreads();
+  const int nkept = *sCnt;
+  const int nmasked = (mode == AGB_MASK_MUL0) ? T - nkept : 0;
   const int half = (T + 1) / 2;
   for (int i0 = threadIdx.x; i0 < half; i0 += blockDim.x) {
     const int i1 = i0 + half;                 // second query of this thread (may fall off the end)
@@ -375,21 +403,18 @@ attention_narrow_kernel(const bf16* __restrict__ qkv, const uint32_t* __restrict
 #pragma unroll
     for (int k = 0; k < D; ++k) o0[k] = o1[k] = 0.f;
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-    for (int j = 0; j < T; ++j) {
-      const bool keep = (sM[j >> 5] >> (j & 31)) & 1u;        // uniform over the CTA
-      if (!keep && mode != AGB_MASK_MUL0) continue;            // additive -inf: the key does not exist
+    for (int jj = 0; jj < nkept; ++jj) {
+      const int j = sIdx[jj];
       float s0 = 0.f, s1 = 0.f;
-      if (keep) {
-        const float4* kr = reinterpret_cast<const float4*>(sK + j * D);
+      const float4* kr = reinterpret_cast<const float4*>(sK + j * D);
 #pragma unroll
-        for (int v = 0; v < D / 4; ++v) {
-          const float4 kk = kr[v];
-          s0 = fmaf(q0[4 * v], kk.x, s0); s0 = fmaf(q0[4 * v + 1], kk.y, s0);
-          s0 = fmaf(q0[4 * v + 2], kk.z, s0); s0 = fmaf(q0[4 * v + 3], kk.w, s0);
-          s1 = fmaf(q1[4 * v], kk.x, s1); s1 = fmaf(q1[4 * v + 1], kk.y, s1);
-          s1 = fmaf(q1[4 * v + 2], kk.z, s1); s1 = fmaf(q1[4 * v + 3], kk.w, s1);
-        }
-      }                                                        // ViT-masked key: logit := 0, its V row still counts
+      for (int v = 0; v < D / 4; ++v) {
+        const float4 kk = kr[v];
+        s0 = fmaf(q0[4 * v], kk.x, s0); s0 = fmaf(q0[4 * v + 1], kk.y, s0);
+        s0 = fmaf(q0[4 * v + 2], kk.z, s0); s0 = fmaf(q0[4 * v + 3], kk.w, s0);
+        s1 = fmaf(q1[4 * v], kk.x, s1); s1 = fmaf(q1[4 * v + 1], kk.y, s1);
+        s1 = fmaf(q1[4 * v + 2], kk.z, s1); s1 = fmaf(q1[4 * v + 3], kk.w, s1);
+      }
       if (s0 > m0) {
         const float c = exp2f(m0 - s0);
         l0 *= c;
@@ -417,6 +442,30 @@ attention_narrow_kernel(const bf16* __restrict__ qkv, const uint32_t* __restrict
         o1[4 * v + 2] = fmaf(p1, vv.z, o1[4 * v + 2]); o1[4 * v + 3] = fmaf(p1, vv.w, o1[4 * v + 3]);
       }
     }
+    if (nmasked > 0) {                         // the ViT-masked keys: logit 0, weight n_masked, summed V rows
+      if (0.f > m0) {
+        const float c = exp2f(m0);
+        l0 *= c;
+#pragma unroll
+        for (int k = 0; k < D; ++k) o0[k] *= c;
+        m0 = 0.f;
+      }
+      if (0.f > m1) {
+        const float c = exp2f(m1);
+        l1 *= c;
+#pragma unroll
+        for (int k = 0; k < D; ++k) o1[k] *= c;
+        m1 = 0.f;
+      }
+      const float p0 = exp2f(-m0), p1 = exp2f(-m1);
+      l0 = fmaf(p0, (float)nmasked, l0);
+      l1 = fmaf(p1, (float)nmasked, l1);
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        o0[k] = fmaf(p0, sVm[k], o0[k]);
+        o1[k] = fmaf(p1, sVm[k], o1[k]);
+      }
+    }
     const float r0 = l0 > 0.f ? 1.f / l0 : 0.f, r1 = l1 > 0.f ? 1.f / l1 : 0.f;
     bf16* c0 = ctx + ((long long)row * T + i0) * H + head * D;
     bf16* c1 = ctx + ((long long)row * T + i1) * H + head * D;
@@ -439,7 +488,7 @@ attention_narrow_kernel(const bf16* __restrict__ qkv, const uint32_t* __restrict
 template <int D>
 static int launch_attention_narrow(const bf16* qkv, const uint32_t* mask, int words, int rows, int T, int H, int heads,
                                    int mode, bf16* ctx, cudaStream_t st) {
-  const size_t smem = (size_t)2 * T * D * sizeof(float) + (size_t)words * sizeof(uint32_t);
+  const size_t smem = ((size_t)2 * T * D + D + T + 1) * sizeof(float) + (size_t)words * sizeof(uint32_t);
   if (smem > 227 * 1024) return AGB_ERR_UNSUPPORTED;
   AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_narrow_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int threads = min(128, (((T + 1) / 2 + 31) / 32) * 32);
