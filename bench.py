@@ -358,6 +358,68 @@ def run_ours(args):
         peaks_t = load_peaks()
         train["frac_of_sustained_peak"] = train["tflops_per_gpu"] / peaks_t["bf16_tflops_sustained"]
 
+    # ---- LTT leg (BASELINE.json north_star: "frozen backbone plus side network", "explainer side-network training uses an
+    # NCCL gradient allreduce"; reference models/ltt_vit.py, recipes/ltt_vit.py): the same ViT backbone frozen, a narrow
+    # side ladder per block.  Masked evals/s through the ladder (both heads) and side-network training samples/s (S + 1
+    # ladder surrogate evals per sample, ladder explainer fwd/bwd, all-reduce of the side parameters only, AdamW). ----
+    ltt = None
+    if not args.no_ltt and args.model == "vit_base":
+        from autognothi_b200.dist import GradAllReducer
+        from autognothi_b200.recipes.ltt_vit import ltt_vit_recipe
+        lrec = ltt_vit_recipe()
+        # the reference ships one LTT configuration (experiments/bert_base_tayp_ltt/.hparams.json:14-32): ladder width =
+        # hidden / 8, ladder MLP = 4 x width, side head width = intermediate size; the same ratios on ViT-Base
+        lcfgd = {k: v for k, v in cfgd.items() if k not in ("explainer_attn_num_layers", "explainer_head_hidden_size")}
+        lcfgd.update(explainer_s_attn_num_layers=1, explainer_s_head_hidden_size=cfgd["intermediate_size"],
+                     s_attn_hidden_size=cfgd["hidden_size"] // 8, s_attn_intermediate_size=cfgd["hidden_size"] // 2)
+        lcfg = lrec.t_config(**lcfgd)
+        torch.manual_seed(3407)
+        lsrg = lrec.conv_pretrained_classifier(lcfg, surrogate).to(dev).eval()    # the bench's backbone, fresh ladder
+        lsrg.agb_precision = "bf16"
+        lexp = lrec.conv_surrogate_explainer(lcfg, None, lsrg).train()
+        lexp.agb_precision = "bf16"
+        side_params = [p for p in lexp.parameters() if p.requires_grad]
+        lopt = torch.optim.AdamW(side_params, lr=1e-5, fused=True)
+        lred = GradAllReducer(side_params, bucket_mb=64.0)
+        Bl = args.train_images
+        xs_l = images_dev[:Bl] if Bl <= B else torch.randn((Bl, 3, 224, 224), device=dev, generator=g)
+        ones_l = ash.PackedMasks.ones(Bl, n, dev)
+        with torch.no_grad():
+            lnull, _ = lrec.fw_surrogate(lsrg, lrec.gen_null(lcfg, None, dev), ash.PackedMasks.ones(1, n, dev))
+
+        def step_ltt_eval(i):
+            pm = ash.mask_shapley_new(rows, n, device=dev, rng="philox", seed=777 + rank, offset=i * rows, packed=True)
+            with torch.no_grad():
+                side, _ = lrec.fw_surrogate(lsrg, images_dev, pm)
+            if world > 1:
+                dist.all_gather(gathered, side)
+            return side
+
+        def step_ltt_train(i):
+            pm = ash.mask_shapley_new(Bl * S, n, device=dev, rng="philox", seed=555 + rank, offset=i * Bl * S, packed=True)
+            with torch.no_grad():
+                v_s, _ = lrec.fw_surrogate(lsrg, xs_l, pm)
+                grand, _ = lrec.fw_surrogate(lsrg, xs_l, ones_l)
+            phi, _ = lrec.fw_explainer(lexp, xs_l, ones_l, grand, lnull)
+            loss = ash.loss_shapley_new(Bl, S, n, pm, lnull, v_s, grand, phi)
+            loss.backward()
+            lred.allreduce()
+            lopt.step()
+            lopt.zero_grad(set_to_none=True)
+            return loss
+
+        l_steps = max(2, min(args.steps, 5))
+        ms_le, launches_le, _ = timed(step_ltt_eval, l_steps, 2)
+        ms_lt, launches_lt, _ = timed(step_ltt_train, l_steps, 2)
+        ltt = {"config": {"ladder_hidden": lcfgd["s_attn_hidden_size"], "ladder_intermediate": lcfgd["s_attn_intermediate_size"],
+                          "ladder_head_dim": lcfgd["s_attn_hidden_size"] // cfgd["num_attention_heads"],
+                          "side_head_hidden": lcfgd["explainer_s_head_hidden_size"], "backbone": model_name + " (frozen)"},
+               "masked_evals_per_sec": world * rows * l_steps / (ms_le * 1e-3), "eval_ms_per_step": ms_le / l_steps,
+               "train_samples_per_sec": world * Bl * l_steps / (ms_lt * 1e-3), "train_ms_per_step": ms_lt / l_steps,
+               "trainable_params": int(sum(p.numel() for p in side_params)), "images_per_gpu_per_step": Bl,
+               "coalitions_per_image": S, "gpu_launches": launches_le + launches_lt, "dropout": "p=0 (identity)",
+               "grad_allreduce": f"NCCL, side parameters only, world={world}"}
+
     value = world * rows * args.steps / (ms * 1e-3)
     e2e_value = world * rows * args.steps / (ms_e2e * 1e-3)
 
@@ -438,6 +500,8 @@ def run_ours(args):
         }
         if train is not None:
             line["train"] = train
+        if ltt is not None:
+            line["ltt"] = ltt
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -455,6 +519,7 @@ def main():
     ap.add_argument("--model", default="vit_base", choices=sorted(MODELS), help="vit_base = the metric's config (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the explainer-training leg")
+    ap.add_argument("--no-ltt", action="store_true", help="skip the ladder-side-tuning leg")
     ap.add_argument("--train-images", type=int, default=32, help="images per GPU per training step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
