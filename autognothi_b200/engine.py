@@ -376,6 +376,8 @@ class SurrogateEngine:
         cfg, T = self.cfg, n_players_of(self.cfg) + 1
         B = xs.shape[0]
         assert masks.shape[0] == B * S
+        if B * S == 0:
+            return torch.empty((0, cfg.num_labels), dtype=torch.float32, device=xs.device)
         per = max(1, max_rows // S)
         outs: List[Tensor] = []
         for b0 in range(0, B, per):
@@ -412,6 +414,10 @@ class ExplainerEngine:
     @torch.no_grad()
     def phi(self, xs: Tensor, masks: Tensor, grand: Optional[Tensor], null: Optional[Tensor], want_pred: bool = False):
         """xs (B,...), masks packed (B, words) -> phi (B, C, n) fp32 [, pred (B,T,C)]"""
+        if xs.shape[0] == 0:
+            n, C = n_players_of(self.cfg), self.cfg.num_labels
+            phi = torch.empty((0, C, n), dtype=torch.float32, device=xs.device)
+            return (phi, torch.empty((0, n + 1, C), dtype=torch.float32, device=xs.device)) if want_pred else phi
         x, xa = run_backbone(self.bw, self.cfg, self.pol, xs, masks, 1)
         return self.tail(x, xa, masks, xs.shape[0], grand, null, want_pred)
 
@@ -453,6 +459,8 @@ class FroyoFinalEngine(ExplainerEngine):
     def final(self, xs: Tensor, masks: Tensor) -> Tuple[Tensor, Tensor]:
         cfg = self.cfg
         B = xs.shape[0]
+        if B == 0:
+            return _empty_outputs(cfg, xs.device)
         x, xa = run_backbone(self.bw, cfg, self.pol, xs, masks, 1)
         x3 = x.reshape(B, -1, cfg.hidden_size)
         if self.bw.vit:
@@ -472,6 +480,12 @@ class FroyoFinalEngine(ExplainerEngine):
 # models/ltt_bert.py:467-499).  Surrogate and explainer are side ladders over the SAME backbone activations, so the
 # bundle evaluates the backbone once.
 # ------------------------------------------------------------------------------------------------------------------
+def _empty_outputs(cfg, device) -> Tuple[Tensor, Tensor]:
+    """(probabilities (0, C), attributions (0, C, n)) of an empty batch"""
+    n, C = n_players_of(cfg), cfg.num_labels
+    return (torch.empty((0, C), dtype=torch.float32, device=device), torch.empty((0, C, n), dtype=torch.float32, device=device))
+
+
 class SideBranch:
     """One side ladder in kernel-ready form: H -> Hs maps, Hs-wide blocks, [ViT] its final LayerNorm."""
 
@@ -584,6 +598,9 @@ class LttEngine:
         """-> (side-ladder probabilities (B*S, C), backbone probabilities (B*S, C)), row order b*S+s."""
         B = xs.shape[0]
         assert masks.shape[0] == B * S
+        if B * S == 0:
+            e = _empty_outputs(self.cfg, xs.device)[0]
+            return e, e.clone()
         per = max(1, max_rows // S)
         srg, cls = [], []
         for b0 in range(0, B, per):
@@ -598,6 +615,8 @@ class LttEngine:
     def explainer(self, xs: Tensor, masks: Tensor, grand: Optional[Tensor], null: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
         """-> (phi (B, C, n), backbone probabilities (B, C))"""
         B = xs.shape[0]
+        if B == 0:
+            return _empty_outputs(self.cfg, xs.device)[::-1]
         x, _, sides = run_ltt(self.bw, self.branches[:1], self.cfg, self.pol, xs, masks, 1, self.freeze_layer)
         cls = self._main_probs(x, B)
         return self._explain(self.branches[0], sides[0][0], sides[0][1], masks, B, grand, null), cls
@@ -607,6 +626,8 @@ class LttEngine:
         """-> (backbone probabilities (B, C), phi (B, C, n)); the surrogate ladder supplies `grand` when normalising."""
         cfg = self.cfg
         B = xs.shape[0]
+        if B == 0:
+            return _empty_outputs(cfg, xs.device)
         use = self.branches if cfg.explainer_normalize else self.branches[1:]
         x, _, sides = run_ltt(self.bw, use, cfg, self.pol, xs, masks, 1, self.freeze_layer)
         cls = self._main_probs(x, B)

@@ -1,0 +1,92 @@
+"""Edge cases of the drop-in boundary on the GPU: empty batches, ragged (input, coalition) shapes, row chunking, the
+reference-shaped call vs the additive fast path.  The reference handles these through plain torch broadcasting; here they
+cross hand-sized grids, so each is pinned explicitly."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import configs as ocfg
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+def _np(t):
+    return t.detach().float().cpu().numpy()
+
+
+def _build(name, precision):
+    from autognothi_b200.recipes.vanilla_bert import vanilla_bert_recipe
+    from autognothi_b200.recipes.vanilla_vit import vanilla_vit_recipe
+    cfgd = ocfg.get_config(name)
+    rec = vanilla_vit_recipe() if ocfg.is_vit(cfgd) else vanilla_bert_recipe()
+    cfg = rec.t_config(**cfgd)
+    srg, exp = rec.t_surrogate(cfg), rec.t_explainer(cfg)
+    srg.load_state_dict({k: torch.from_numpy(v) for k, v in synth.surrogate_state(cfgd, seed=0).items()}, strict=True)
+    exp.load_state_dict({k: torch.from_numpy(v) for k, v in synth.explainer_state(cfgd, seed=1).items()}, strict=True)
+    srg, exp = srg.to(DEV).eval(), exp.to(DEV).eval()
+    srg.agb_precision = exp.agb_precision = precision
+    return rec, cfgd, cfg, srg, exp
+
+
+@pytest.mark.parametrize("name,precision", [("vit_mini", "bf16"), ("vit_mini", "fp32"), ("bert_mini", "bf16"), ("bert_mini", "fp32")])
+def test_empty_batch(agb, name, precision):
+    from autognothi_b200.models import shapley as ash
+    rec, cfgd, cfg, srg, exp = _build(name, precision)
+    n, C = rec.n_players(cfg), cfgd["num_labels"]
+    xs = torch.from_numpy(synth.inputs(cfgd, 2, seed=0)).to(DEV)[:0]
+    m0 = torch.zeros((0, n), dtype=torch.int64, device=DEV)
+    with torch.no_grad():
+        ys, _ = rec.fw_surrogate(srg, xs, m0)
+        phi, _ = rec.fw_explainer(exp, xs, m0, torch.zeros((0, C), device=DEV), torch.zeros((1, C), device=DEV))
+    assert ys.shape == (0, C) and phi.shape == (0, C, n)
+    if name.startswith("vit"):       # the LTT / Froyo bundles take the same early exit
+        from autognothi_b200.recipes.froyo_vit import froyo_vit_recipe
+        from autognothi_b200.recipes.ltt_vit import ltt_vit_recipe
+        for r, cname in ((froyo_vit_recipe(), "vit_mini"), (ltt_vit_recipe(), "ltt_vit_mini")):
+            fin = r.t_final(r.t_config(**ocfg.get_config(cname))).to(DEV).eval()
+            with torch.no_grad():
+                lg, at = r.fw_final(fin, xs)
+            assert lg.shape == (0, C) and at.shape == (0, C, n)
+    assert ash.mask_shapley_new(0, n, device=DEV).shape == (0, n)
+    pm = ash.mask_shapley_new(0, n, device=DEV, rng="philox", seed=1, packed=True)
+    assert pm.rows == 0
+
+
+@pytest.mark.parametrize("name", ["vit_mini", "bert_mini"])
+@pytest.mark.parametrize("B,S", [(1, 1), (2, 3), (3, 5), (5, 2)])
+def test_ragged_coalition_shapes_match_the_replicated_call(agb, name, B, S):
+    """(B, S, n) fast path == the reference-shaped call on inputs replicated S times (row order b*S+s), for S odd / B odd,
+    where Shapley pairs straddle inputs (the reference only asserts that B*S is even, models/shapley.py:62)."""
+    rec, cfgd, cfg, srg, exp = _build(name, "fp32")
+    n = rec.n_players(cfg)
+    xs = torch.from_numpy(synth.inputs(cfgd, B, seed=3)).to(DEV)
+    g = torch.Generator(device="cpu").manual_seed(B * 10 + S)
+    masks = (torch.rand((B * S, n), generator=g) > 0.5).to(torch.int64).to(DEV)
+    with torch.no_grad():
+        a, _ = rec.fw_surrogate(srg, xs.repeat_interleave(S, dim=0), masks)
+        b, _ = rec.fw_surrogate(srg, xs, masks.reshape(B, S, n))
+    assert torch.equal(a, b)
+    srg.agb_precision = "bf16"
+    with torch.no_grad():
+        c, _ = rec.fw_surrogate(srg, xs, masks.reshape(B, S, n))
+    np.testing.assert_allclose(_np(c), _np(a), atol=2e-2)
+    np.testing.assert_allclose(_np(c).sum(1), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["vit_mini", "bert_mini"])
+def test_row_chunking_is_invisible(agb, name):
+    """More (input, coalition) rows than the engine's chunk (1024): results equal the per-chunk calls."""
+    rec, cfgd, cfg, srg, exp = _build(name, "bf16")
+    n = rec.n_players(cfg)
+    B, S = 70, 16                      # 1120 rows -> two chunks of 64 and 6 inputs
+    xs = torch.from_numpy(synth.inputs(cfgd, B, seed=5)).to(DEV)
+    from autognothi_b200.models import shapley as ash
+    pm = ash.mask_shapley_new(B * S, n, device=DEV, rng="philox", seed=9, packed=True)
+    with torch.no_grad():
+        full, _ = rec.fw_surrogate(srg, xs, pm)
+        first, _ = rec.fw_surrogate(srg, xs[:64], ash.PackedMasks(pm.words[:64 * S].contiguous(), n))
+        rest, _ = rec.fw_surrogate(srg, xs[64:], ash.PackedMasks(pm.words[64 * S:].contiguous(), n))
+    assert full.shape == (B * S, cfgd["num_labels"])
+    assert torch.equal(full, torch.cat([first, rest], 0))
