@@ -42,8 +42,14 @@ int gelu_bwd(const void* dy, const void* z, void* dz, long long n, int is_bf16, 
 int colsum(const void* y, int is_bf16, long long ld, int M, int N, float* out, cudaStream_t st);
 int layernorm_bwd(const void* x, int x_bf16, const void* dy, int dy_bf16, const float* gamma, const float* dres,
                   int rows, int H, float eps, float* dx, float* dgamma, float* dbeta, cudaStream_t st);
+int dropout(const void* y, int y_bf16, const float* residual, void* out, int out_bf16, long long n, unsigned thr16,
+            unsigned long long seed, unsigned tag, cudaStream_t st);
+int attention_dropout_mask(unsigned char* keep, int rows, int heads, int T, unsigned thr16, unsigned long long seed,
+                           cudaStream_t st);
+int attention_pipe_dropout(const bf16* qkv, const uint32_t* mask, int words, int rows, int T, int H, int heads, int mode,
+                           bf16* ctx, unsigned thr16, unsigned long long seed, cudaStream_t stream);
 int attention_bwd(const void* qkv, const void* dctx, int io_bf16, const uint32_t* mask, int words, int rows, int T,
-                  int H, int heads, int mode, void* dqkv, cudaStream_t st);
+                  int H, int heads, int mode, void* dqkv, cudaStream_t st, unsigned drop_thr, unsigned long long drop_seed);
 int vit_embed_bwd(const float* dx, int B, int T, int H, float* dpos, float* dcls, void* dpatch, int dpatch_bf16,
                   cudaStream_t st);
 int bert_embed_sum(const int64_t* ids, const float* word, const float* pos, const float* type0, int BT, int T, int H,
@@ -74,7 +80,7 @@ int cls_head(const float* x, long long row_stride, int rows, int H, int C, int m
              const float* ln_b, float eps, const float* wp, const float* bp, const float* wc,
              const float* bc, float* probs, float* logits_out, cudaStream_t st);
 int attention_simt(const void* qkv, int io_bf16, const uint32_t* mask, int words, int rows, int T, int H,
-                   int heads, int mode, void* ctx, cudaStream_t st);
+                   int heads, int mode, void* ctx, cudaStream_t st, unsigned drop_thr, unsigned long long drop_seed);
 int attention_tc(const bf16* qkv, const uint32_t* mask, int words, int rows, int share, int T, int H, int heads,
                  int mode, bf16* ctx, cudaStream_t st);
 int explainer_head_fwd(const void* h, int h_bf16, int B, int T, int E, int C, const float* W,
@@ -211,7 +217,27 @@ int agb_layernorm_bwd(const void* x, int x_is_bf16, const void* dy, int dy_is_bf
 }
 int agb_masked_attention_bwd(const void* qkv, const void* dctx, int io_is_bf16, const uint32_t* mask, int words,
                              int rows, int T, int H, int heads, int mode, void* dqkv, void* stream) {
-  return agb::attention_bwd(qkv, dctx, io_is_bf16, mask, words, rows, T, H, heads, mode, dqkv, ST(stream));
+  return agb::attention_bwd(qkv, dctx, io_is_bf16, mask, words, rows, T, H, heads, mode, dqkv, ST(stream), 0, 0);
+}
+int agb_dropout(const void* y, int y_is_bf16, const float* residual, void* out, int out_is_bf16, long long n,
+                int thr16, uint64_t seed, int tag, void* stream) {
+  return agb::dropout(y, y_is_bf16, residual, out, out_is_bf16, n, (unsigned)thr16, seed, (unsigned)tag, ST(stream));
+}
+int agb_attention_dropout_mask(void* keep, int rows, int heads, int T, int thr16, uint64_t seed,
+                               void* stream) {
+  return agb::attention_dropout_mask(static_cast<unsigned char*>(keep), rows, heads, T, (unsigned)thr16, seed, ST(stream));
+}
+int agb_masked_attention_dropout_fwd(const void* qkv, const uint32_t* mask, int words, int rows, int T, int H, int heads,
+                                     int mode, void* ctx, int thr16, uint64_t seed, void* stream) {
+  if (H == heads * 64)
+    return agb::attention_pipe_dropout(static_cast<const bf16*>(qkv), mask, words, rows, T, H, heads, mode,
+                                       static_cast<bf16*>(ctx), (unsigned)thr16, seed, ST(stream));
+  return agb::attention_simt(qkv, 1, mask, words, rows, T, H, heads, mode, ctx, ST(stream), (unsigned)thr16, seed);
+}
+int agb_masked_attention_dropout_bwd(const void* qkv, const void* dctx, const uint32_t* mask, int words, int rows, int T,
+                                     int H, int heads, int mode, void* dqkv, int thr16, uint64_t seed,
+                                     void* stream) {
+  return agb::attention_bwd(qkv, dctx, 1, mask, words, rows, T, H, heads, mode, dqkv, ST(stream), (unsigned)thr16, seed);
 }
 int agb_vit_embed_bwd(const float* dx, int B, int T, int H, float* dpos, float* dcls, void* dpatch,
                       int dpatch_is_bf16, void* stream) {
@@ -276,7 +302,7 @@ int agb_cls_head(const float* x, long long row_stride, int rows, int H, int C, i
 }
 int agb_masked_attention_simt(const void* qkv, int io_is_bf16, const uint32_t* mask, int words,
                               int rows, int T, int H, int heads, int mode, void* ctx, void* stream) {
-  return agb::attention_simt(qkv, io_is_bf16, mask, words, rows, T, H, heads, mode, ctx, ST(stream));
+  return agb::attention_simt(qkv, io_is_bf16, mask, words, rows, T, H, heads, mode, ctx, ST(stream), 0, 0);
 }
 int agb_masked_attention_bf16(const void* qkv, const uint32_t* mask, int words, int rows, int T,
                               int H, int heads, int mode, void* ctx, void* stream) {

@@ -33,6 +33,10 @@ struct AttBwdParams {
   int mtiles;        // ceil(T / 128) query tiles
   int njb;           // ceil(NK / 128) key blocks
   bf16* dqkv;
+  // attention-probability dropout of the forward (DROP instantiation): O = (P o M / (1-p)) V with M regenerated here
+  unsigned drop_thr;
+  unsigned long long drop_seed;
+  float drop_scale;
 };
 
 __device__ __forceinline__ uint32_t bt_live_word(const uint32_t* mrow, int words, int mode, int T, int j0) {
@@ -43,6 +47,7 @@ __device__ __forceinline__ uint32_t bt_live_word(const uint32_t* mrow, int words
   return live;
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(BT_THREADS, 1)
 attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                         const __grid_constant__ CUtensorMap tmdO, const AttBwdParams p) {
@@ -200,6 +205,11 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 
       // ---- phase 0: L_i (log2 domain) and D_i for this thread's row of each query tile ----
       float L[2] = {0.f, 0.f}, Dv[2] = {0.f, 0.f};
+      uint32_t dkey[2] = {0u, 0u};
+      if (DROP) {
+        dkey[0] = agb_drop_key(p.drop_seed, (uint32_t)u, (uint32_t)r);
+        dkey[1] = agb_drop_key(p.drop_seed, (uint32_t)u, (uint32_t)(128 + r));
+      }
       for (int m = 0; m < mt; ++m) {
         mbar_wait(smem_u32(bar_s), cs & 1); ++cs;
         tc_fence_after();
@@ -228,12 +238,16 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             }
             tmem_wait_ld();
             const uint32_t live = bt_live_word(mrow, p.words, p.mode, T, j0);
+            uint32_t xb = 0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
+              if (DROP && (j & 1) == 0) xb = agb_drop_bits(dkey[m], (uint32_t)(j0 + j) >> 1);
               if ((live >> j) & 1u) {
                 const float pe = ex2_approx(fmaf(__uint_as_float(s[j]), c2, -mxs));
                 sum += pe;
-                dsum = fmaf(pe, __uint_as_float(d[j]), dsum);
+                float dj = __uint_as_float(d[j]);
+                if (DROP) dj = (((j & 1) ? (xb >> 16) : (xb & 0xFFFFu)) >= p.drop_thr) ? dj * p.drop_scale : 0.f;
+                dsum = fmaf(pe, dj, dsum);
               }
             }
           }
@@ -272,13 +286,21 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
                 for (int h2 = 0; h2 < 4; ++h2) {
                   float pv[2], dv[2];
+                  const uint32_t xb = DROP ? agb_drop_bits(dkey[m], (uint32_t)(jb * 128 + jc + c8 * 8 + h2 * 2) >> 1) : 0u;
 #pragma unroll
                   for (int o = 0; o < 2; ++o) {
                     const int j = c8 * 8 + h2 * 2 + o;
                     const bool lv = (live >> j) & 1u;
                     const float pe = lv ? ex2_approx(fmaf(__uint_as_float(s[j]), c2, -Li)) : 0.f;
-                    pv[o] = pe;
-                    dv[o] = pe * (__uint_as_float(d[j]) - Di) * 0.125f;
+                    float dj = __uint_as_float(d[j]);
+                    float pk = pe;
+                    if (DROP) {      // dP and the P of dV carry the dropout mask; dS = P (dP o M' - D) keeps the full P
+                      const float mk = ((o ? (xb >> 16) : (xb & 0xFFFFu)) >= p.drop_thr) ? p.drop_scale : 0.f;
+                      dj *= mk;
+                      pk *= mk;
+                    }
+                    pv[o] = pk;
+                    dv[o] = pe * (dj - Di) * 0.125f;
                   }
                   pp[h2] = pack_bf16x2(pv[0], pv[1]);
                   dd[h2] = pack_bf16x2(dv[0], dv[1]);
@@ -371,7 +393,7 @@ attention_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 
 // Returns AGB_ERR_UNSUPPORTED for shapes this kernel does not cover (the caller falls back to the CUDA-core adjoint).
 int attention_bwd_tc(const bf16* qkv, const bf16* dctx, const uint32_t* mask, int words, int rows, int T, int H,
-                     int heads, int mode, bf16* dqkv, cudaStream_t stream) {
+                     int heads, int mode, bf16* dqkv, cudaStream_t stream, unsigned drop_thr, unsigned long long drop_seed) {
   if (T > 256 || H != heads * BT_D) return AGB_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(dctx) & 15) ||
       (reinterpret_cast<uintptr_t>(dqkv) & 15))
@@ -383,6 +405,9 @@ int attention_bwd_tc(const bf16* qkv, const bf16* dctx, const uint32_t* mask, in
   p.mtiles = (T + 127) / 128;
   p.njb = (p.NK + 127) / 128;
   p.dqkv = dqkv;
+  p.drop_thr = drop_thr;
+  p.drop_seed = drop_seed;
+  p.drop_scale = 65536.0f / (65536.0f - (float)drop_thr);
   CUtensorMap tmQ, tmKV, tmdO;
   int rc = encode_tmap_3d_bf16(&tmQ, qkv, 3 * (uint64_t)H, T, rows, (uint64_t)3 * H * 2, (uint64_t)T * 3 * H * 2,
                                BT_D, 128, 1);
@@ -395,11 +420,13 @@ int attention_bwd_tc(const bf16* qkv, const bf16* dctx, const uint32_t* mask, in
   const int smem = 1024 + 8 * BT_TILE + 2 * p.NK * 128 + 128;
   static int configured_smem = 0;
   if (smem > configured_smem) {
-    AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured_smem = smem;
   }
   const int grid = p.units < sm_count() ? p.units : sm_count();
-  attention_bwd_tc_kernel<<<grid, BT_THREADS, smem, stream>>>(tmQ, tmKV, tmdO, p);
+  if (drop_thr > 0) attention_bwd_tc_kernel<true><<<grid, BT_THREADS, smem, stream>>>(tmQ, tmKV, tmdO, p);
+  else attention_bwd_tc_kernel<false><<<grid, BT_THREADS, smem, stream>>>(tmQ, tmKV, tmdO, p);
   AGB_CHECK_CUDA(cudaGetLastError());
   return AGB_OK;
 }

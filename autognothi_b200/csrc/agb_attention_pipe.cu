@@ -42,6 +42,10 @@ struct AttPipeParams {
   const int* cu;     // AP_MODE_VARLEN: row r owns the packed tokens [cu[r], cu[r+1]) of qkv (total_tokens, 3H)
   bf16* ctx;
   long long* trace;  // optional [items][8] clock64 timestamps of CTA 0 (diagnostics), or nullptr
+  // attention-probability dropout (training forward only; DROP instantiations): P kept iff 16 hash bits >= drop_thr
+  unsigned drop_thr;
+  unsigned long long drop_seed;
+  float drop_scale;  // 1 / (1 - p)
 };
 
 #define AP_TRACE(k, slot)                                                             \
@@ -74,9 +78,10 @@ __device__ __forceinline__ float ap_max_chunk(uint32_t addr, float m, uint32_t l
   return m;
 }
 
-template <int W, bool MASKED>
+template <int W, bool MASKED, bool DROP = false>
 __device__ __forceinline__ float ap_exp_chunk(uint32_t s_addr, uint32_t p_addr, float scale_log2, float m_scaled,
-                                              uint32_t live_lo, uint32_t live_hi) {
+                                              uint32_t live_lo, uint32_t live_hi, uint32_t dkey = 0u, uint32_t pair0 = 0u,
+                                              uint32_t dthr = 0u) {
   uint32_t s[W];
   ap_load<W>(s_addr, s);
   uint32_t pk[W / 2];
@@ -92,6 +97,10 @@ __device__ __forceinline__ float ap_exp_chunk(uint32_t s_addr, uint32_t p_addr, 
     const float e0 = ex2_approx(fmaf(a, scale_log2, -m_scaled));
     const float e1 = ex2_approx(fmaf(b, scale_log2, -m_scaled));
     if (j & 1) { sum2 += e0; sum3 += e1; } else { sum0 += e0; sum1 += e1; }
+    if (DROP) {      // the row sum keeps every probability; dropped ones only leave the P V product
+      const uint32_t x = agb_drop_bits(dkey, pair0 + j);
+      pk[j] = pack_bf16x2((x & 0xFFFFu) >= dthr ? e0 : 0.f, (x >> 16) >= dthr ? e1 : 0.f);
+    } else
     pk[j] = pack_bf16x2(e0, e1);
   }
   if (W == 64) tmem_st32(p_addr, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
@@ -120,7 +129,7 @@ __device__ __forceinline__ void ap_live_bits(const uint32_t* mrow, int words, in
   hi = (uint32_t)(live >> 32);
 }
 
-template <int MODE, int G>
+template <int MODE, int G, bool DROP = false>
 __global__ void __launch_bounds__(AP_THREADS, 1)
 attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                       const AttPipeParams p) {
@@ -337,20 +346,24 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         // pass 2: P = exp2(s*scale - max*scale) -> bf16 pairs -> TMEM (overlaying consumed S columns)
         float sum = 0.f;
         c0 = 0;
+        const uint32_t dkey = DROP ? agb_drop_key(p.drop_seed, (uint32_t)u, (uint32_t)(m * 128 + r)) : 0u;
         for (; c0 < n_fast; c0 += 64)
-          sum += ap_exp_chunk<64, false>(lane_addr + c0, lane_addr + (c0 >> 1), scale_log2, m_scaled, 0u, 0u);
+          sum += ap_exp_chunk<64, false, DROP>(lane_addr + c0, lane_addr + (c0 >> 1), scale_log2, m_scaled, 0u, 0u, dkey,
+                                               c0 >> 1, p.drop_thr);
         for (; c0 + 64 <= NK; c0 += 64) {
           uint32_t lo, hi;
           ap_live_bits(mrow, p.words, MODE, Tr, c0, 64, lo, hi);
-          sum += ap_exp_chunk<64, true>(lane_addr + c0, lane_addr + (c0 >> 1), scale_log2, m_scaled, lo, hi);
+          sum += ap_exp_chunk<64, true, DROP>(lane_addr + c0, lane_addr + (c0 >> 1), scale_log2, m_scaled, lo, hi, dkey,
+                                              c0 >> 1, p.drop_thr);
         }
         for (; c0 < NK; c0 += 16) {
           uint32_t lo, hi;
           ap_live_bits(mrow, p.words, MODE, Tr, c0, 16, lo, hi);
-          sum += ap_exp_chunk<16, true>(lane_addr + c0, lane_addr + (c0 >> 1), scale_log2, m_scaled, lo, hi);
+          sum += ap_exp_chunk<16, true, DROP>(lane_addr + c0, lane_addr + (c0 >> 1), scale_log2, m_scaled, lo, hi, dkey,
+                                              c0 >> 1, p.drop_thr);
         }
         tmem_wait_st();
-        inv = 1.0f / sum;
+        inv = (DROP ? p.drop_scale : 1.0f) / sum;
       }
       tc_fence_before();
       __syncwarp();
@@ -398,8 +411,12 @@ int get_attention_variant() { return g_attention_variant; }
 
 // T = sequence length (fixed layout) or an upper bound of the row lengths (packed layout, cu != nullptr)
 static int attention_pipe_launch(const bf16* qkv, const uint32_t* mask, int words, int rows, int share, int T, int H,
-                                 int heads, int mode, bf16* ctx, const int* cu, int total_tokens, cudaStream_t stream) {
+                                 int heads, int mode, bf16* ctx, const int* cu, int total_tokens, cudaStream_t stream,
+                                 unsigned drop_thr = 0, unsigned long long drop_seed = 0) {
   AttPipeParams p;
+  p.drop_thr = drop_thr;
+  p.drop_seed = drop_seed;
+  p.drop_scale = 65536.0f / (65536.0f - (float)drop_thr);
   p.mask = mask; p.words = words; p.rows = rows; p.T = T; p.H = H; p.heads = heads; p.mode = mode;
   p.NK = (T + 15) / 16 * 16;
   p.units = rows * heads;
@@ -435,11 +452,24 @@ static int attention_pipe_launch(const bf16* qkv, const uint32_t* mask, int word
     AP_SET(AGB_MASK_MUL0, 2); AP_SET(AGB_MASK_NEGINF, 2); AP_SET(AP_MODE_VARLEN, 2);
     AP_SET(AGB_MASK_MUL0, 1); AP_SET(AGB_MASK_NEGINF, 1); AP_SET(AP_MODE_VARLEN, 1);
 #undef AP_SET
+    AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<AGB_MASK_MUL0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<AGB_MASK_NEGINF, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured_smem = smem;
   }
   const int grid = p.units < sm_count() ? p.units : sm_count();
 #define AP_GO(M_, G_) attention_pipe_kernel<M_, G_><<<grid, AP_THREADS, smem, stream>>>(tmQ, tmKV, p)
   const int kmode = cu ? AP_MODE_VARLEN : mode;
+  if (drop_thr > 0) {
+    // training forward with attention-probability dropout: fixed layout, T <= 256 (the adjoint's range)
+    if (cu != nullptr || share != 1 || p.groups != 2) {
+      set_last_error("attention dropout: fixed-layout rows with T <= 256 only (T = %d)", T);
+      return AGB_ERR_UNSUPPORTED;
+    }
+    if (kmode == AGB_MASK_MUL0) attention_pipe_kernel<AGB_MASK_MUL0, 2, true><<<grid, AP_THREADS, smem, stream>>>(tmQ, tmKV, p);
+    else attention_pipe_kernel<AGB_MASK_NEGINF, 2, true><<<grid, AP_THREADS, smem, stream>>>(tmQ, tmKV, p);
+    AGB_CHECK_CUDA(cudaGetLastError());
+    return AGB_OK;
+  }
   if (p.groups == 2) {
     if (kmode == AGB_MASK_MUL0) AP_GO(AGB_MASK_MUL0, 2);
     else if (kmode == AGB_MASK_NEGINF) AP_GO(AGB_MASK_NEGINF, 2);
@@ -458,6 +488,11 @@ int attention_pipe(const bf16* qkv, const uint32_t* mask, int words, int rows, i
                    int mode, bf16* ctx, cudaStream_t stream) {
   if (g_attention_variant == 1) return AGB_ERR_UNSUPPORTED;
   return attention_pipe_launch(qkv, mask, words, rows, share, T, H, heads, mode, ctx, nullptr, 0, stream);
+}
+
+int attention_pipe_dropout(const bf16* qkv, const uint32_t* mask, int words, int rows, int T, int H, int heads, int mode,
+                           bf16* ctx, unsigned thr16, unsigned long long seed, cudaStream_t stream) {
+  return attention_pipe_launch(qkv, mask, words, rows, 1, T, H, heads, mode, ctx, nullptr, 0, stream, thr16, seed);
 }
 
 // Packed variable-length rows (masked-token dropping): plain attention inside each segment [cu[r], cu[r+1]).

@@ -4,6 +4,8 @@
 // backward and the embedding adjoints.  The four GEMMs per Linear (dgrad + wgrad) reuse the tcgen05
 // kernel through its MN-major operand modes, so these are the HBM-bound remainder plus the attention
 // adjoint (CUDA-core v1: no score matrix in HBM, no atomics, deterministic).
+#include <algorithm>
+
 #include "agb_common.cuh"
 
 namespace agb {
@@ -726,6 +728,71 @@ attention_bwd_f32_kernel(const float* __restrict__ qkv, const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// nn.Dropout in training mode (reference models/vanilla_vit.py:253,501-503,512-516, vanilla_bert.py:325,559,603):
+//   out = residual + keep * y / (1 - p),   keep = hash bits of (seed, tag, element index) >= thr16
+// The adjoint is the same map applied to the incoming gradient (no residual), so no mask is stored.
+// ------------------------------------------------------------------------------------------------
+template <typename TY, typename TO>
+__global__ void dropout_kernel(const TY* __restrict__ y, const float* __restrict__ res, TO* __restrict__ out, long long n,
+                               uint32_t key, uint32_t thr, float scale) {
+  const long long pairs = (n + 1) / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pairs; i += (long long)gridDim.x * blockDim.x) {
+    const uint32_t x = agb_drop_bits(key, (uint32_t)i);
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      const long long e = 2 * i + o;
+      if (e >= n) break;
+      const bool keep = (o ? (x >> 16) : (x & 0xFFFFu)) >= thr;
+      float v = keep ? ld1<TY>(y + e) * scale : 0.f;
+      if (res) v += res[e];
+      st1<TO>(out + e, v);
+    }
+  }
+}
+
+int dropout(const void* y, int y_bf16, const float* residual, void* out, int out_bf16, long long n, unsigned thr16,
+            unsigned long long seed, unsigned tag, cudaStream_t st) {
+  AGB_REQUIRE(n >= 0 && thr16 < 65536u, "dropout arguments");
+  if (n == 0) return AGB_OK;
+  AGB_REQUIRE(y && out, "null pointer");
+  AGB_REQUIRE(n < (1ll << 32), "dropout: at most 2^32 elements per call");
+  const uint32_t key = agb_drop_key(seed, tag, 0x5bd1e995u);
+  const float scale = 65536.0f / (65536.0f - (float)thr16);
+  const int blocks = (int)std::min<long long>(((n + 1) / 2 + 255) / 256, 8ll * sm_count());
+#define DROP_GO(TY, TO) \
+  dropout_kernel<TY, TO><<<blocks, 256, 0, st>>>(static_cast<const TY*>(y), residual, static_cast<TO*>(out), n, key, thr16, scale)
+  if (y_bf16 && out_bf16) DROP_GO(bf16, bf16);
+  else if (y_bf16) DROP_GO(bf16, float);
+  else if (out_bf16) DROP_GO(float, bf16);
+  else DROP_GO(float, float);
+#undef DROP_GO
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+// dense keep mask of the attention-probability dropout, for tests: keep[(row, head, query, key)] in {0, 1}
+__global__ void attention_dropout_mask_kernel(unsigned char* __restrict__ keep, long long n, int heads, int T, uint32_t thr,
+                                              unsigned long long seed) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(e % T), i = (int)((e / T) % T);
+    const uint32_t unit = (uint32_t)(e / ((long long)T * T));
+    keep[e] = agb_attn_keep(seed, unit, (uint32_t)i, (uint32_t)j, thr) ? 1 : 0;
+  }
+}
+
+int attention_dropout_mask(unsigned char* keep, int rows, int heads, int T, unsigned thr16, unsigned long long seed,
+                           cudaStream_t st) {
+  AGB_REQUIRE(rows >= 0 && heads > 0 && T > 0 && thr16 < 65536u, "arguments");
+  const long long n = (long long)rows * heads * T * T;
+  if (n == 0) return AGB_OK;
+  AGB_REQUIRE(keep, "null pointer");
+  attention_dropout_mask_kernel<<<(int)std::min<long long>((n + 255) / 256, 8ll * sm_count()), 256, 0, st>>>(keep, n, heads, T,
+                                                                                                           thr16, seed);
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Narrow heads (head dim 8 / 16 / 32: the side ladders of the LTT variants, hidden size s_attn_hidden_size split over the
 // backbone's head count, reference models/ltt_vit.py:386-396).  Same two passes and the same arithmetic as
 // attention_bwd_kernel with the operands staged as fp32 (so fp32 I/O is the exact mode here too); the head dim no
@@ -734,7 +801,8 @@ attention_bwd_f32_kernel(const float* __restrict__ qkv, const float* __restrict_
 template <typename TIO, int D>
 __global__ void __launch_bounds__(256)
 attention_bwd_small_kernel(const TIO* __restrict__ qkv, const TIO* __restrict__ dctx, const uint32_t* __restrict__ mask,
-                           int words, int T, int H, int heads, int mode, float scale, TIO* __restrict__ dqkv) {
+                           int words, int T, int H, int heads, int mode, float scale, TIO* __restrict__ dqkv,
+                           unsigned drop_thr, unsigned long long drop_seed, float drop_scale) {
   constexpr int LD = D + 1;
   constexpr int G = 32 / D;
   extern __shared__ uint8_t smraw[];
@@ -774,6 +842,8 @@ attention_bwd_small_kernel(const TIO* __restrict__ qkv, const TIO* __restrict__ 
       const uint32_t keep = (mrow[j >> 5] >> (j & 31)) & 1u;
       float x = a * scale;
       if (!keep) x = (mode == AGB_MASK_MUL0) ? 0.f : -INFINITY;
+      if (drop_thr)      // dP carries the forward's dropout mask: O = (P o M / (1-p)) V
+        b = agb_attn_keep(drop_seed, blockIdx.x, i, j, drop_thr) ? b * drop_scale : 0.f;
       s0[j] = x;
       s1[j] = b;
       mx = fmaxf(mx, x);
@@ -818,8 +888,10 @@ attention_bwd_small_kernel(const TIO* __restrict__ qkv, const TIO* __restrict__ 
       float x = a * scale;
       if (!keep) x = (mode == AGB_MASK_MUL0) ? 0.f : -INFINITY;
       const float pij = expf(x - lse[i]);
-      s0[i] = pij;                                               // for dV
-      s1[i] = keep ? pij * (b - Dv[i]) * scale : 0.f;            // dS for dK
+      float mk = 1.f;
+      if (drop_thr) mk = agb_attn_keep(drop_seed, blockIdx.x, i, j, drop_thr) ? drop_scale : 0.f;
+      s0[i] = pij * mk;                                          // for dV
+      s1[i] = keep ? pij * (b * mk - Dv[i]) * scale : 0.f;       // dS for dK
     }
     __syncwarp();
     float kk = 0.f, vv = 0.f;
@@ -842,7 +914,8 @@ attention_bwd_small_kernel(const TIO* __restrict__ qkv, const TIO* __restrict__ 
 
 template <typename TIO, int D>
 static int launch_attention_bwd_small(const void* qkv, const void* dctx, const uint32_t* mask, int words, int rows, int T,
-                                      int H, int heads, int mode, void* dqkv, cudaStream_t st) {
+                                      int H, int heads, int mode, void* dqkv, cudaStream_t st, unsigned drop_thr,
+                                      unsigned long long drop_seed) {
   const int nw = 8;
   const size_t smem = ((size_t)4 * T * (D + 1) + 2 * (size_t)T + (size_t)nw * 2 * T) * sizeof(float);
   if (smem > 227 * 1024) {
@@ -852,19 +925,19 @@ static int launch_attention_bwd_small(const void* qkv, const void* dctx, const u
   AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_small_kernel<TIO, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   attention_bwd_small_kernel<TIO, D><<<rows * heads, nw * 32, smem, st>>>(
       static_cast<const TIO*>(qkv), static_cast<const TIO*>(dctx), mask, words, T, H, heads, mode, rsqrtf((float)D),
-      static_cast<TIO*>(dqkv));
+      static_cast<TIO*>(dqkv), drop_thr, drop_seed, 65536.0f / (65536.0f - (float)drop_thr));
   AGB_CHECK_CUDA(cudaGetLastError());
   return AGB_OK;
 }
 
 int attention_bwd_tc(const bf16* qkv, const bf16* dctx, const uint32_t* mask, int words, int rows, int T, int H,
-                     int heads, int mode, bf16* dqkv, cudaStream_t stream);
+                     int heads, int mode, bf16* dqkv, cudaStream_t stream, unsigned drop_thr, unsigned long long drop_seed);
 static int g_attention_bwd_variant = 0;   // 0 auto (tensor cores for bf16), 1 CUDA-core kernel only
 void set_attention_bwd_variant(int v) { g_attention_bwd_variant = v; }
 int get_attention_bwd_variant() { return g_attention_bwd_variant; }
 
 int attention_bwd(const void* qkv, const void* dctx, int io_bf16, const uint32_t* mask, int words, int rows, int T,
-                  int H, int heads, int mode, void* dqkv, cudaStream_t st) {
+                  int H, int heads, int mode, void* dqkv, cudaStream_t st, unsigned drop_thr, unsigned long long drop_seed) {
   AGB_REQUIRE(rows >= 0 && T > 0 && heads > 0 && H % heads == 0, "attention shape");
   AGB_REQUIRE(words * 32 >= T, "mask words");
   AGB_REQUIRE(mode == AGB_MASK_MUL0 || mode == AGB_MASK_NEGINF, "mask mode");
@@ -874,8 +947,8 @@ int attention_bwd(const void* qkv, const void* dctx, int io_bf16, const uint32_t
     if (rows == 0) return AGB_OK;
     AGB_REQUIRE(qkv && dctx && mask && dqkv, "null pointer");
 #define ABS_LAUNCH(D)                                                                                                  \
-  (io_bf16 ? launch_attention_bwd_small<bf16, D>(qkv, dctx, mask, words, rows, T, H, heads, mode, dqkv, st)            \
-           : launch_attention_bwd_small<float, D>(qkv, dctx, mask, words, rows, T, H, heads, mode, dqkv, st))
+  (io_bf16 ? launch_attention_bwd_small<bf16, D>(qkv, dctx, mask, words, rows, T, H, heads, mode, dqkv, st, drop_thr, drop_seed) \
+           : launch_attention_bwd_small<float, D>(qkv, dctx, mask, words, rows, T, H, heads, mode, dqkv, st, drop_thr, drop_seed))
     return hd == 8 ? ABS_LAUNCH(8) : (hd == 16 ? ABS_LAUNCH(16) : ABS_LAUNCH(32));
 #undef ABS_LAUNCH
   }
@@ -885,10 +958,14 @@ int attention_bwd(const void* qkv, const void* dctx, int io_bf16, const uint32_t
   }
   if (rows == 0) return AGB_OK;
   AGB_REQUIRE(qkv && dctx && mask && dqkv, "null pointer");
-  if (io_bf16 && g_attention_bwd_variant == 0) {
+  if (io_bf16 && (g_attention_bwd_variant == 0 || drop_thr > 0)) {
     const int rc2 = attention_bwd_tc(static_cast<const bf16*>(qkv), static_cast<const bf16*>(dctx), mask, words, rows, T, H,
-                                     heads, mode, static_cast<bf16*>(dqkv), st);
+                                     heads, mode, static_cast<bf16*>(dqkv), st, drop_thr, drop_seed);
     if (rc2 != AGB_ERR_UNSUPPORTED) return rc2;
+  }
+  if (drop_thr > 0) {
+    set_last_error("attention dropout adjoint: bf16 with head dim 64 and T <= 256, or head dims 8/16/32 (T = %d)", T);
+    return AGB_ERR_UNSUPPORTED;
   }
   if (T > 256) {
     // two-kernel form (operands staged in bf16, fp32 math): fp32 I/O is accepted but is not the exact mode here

@@ -431,6 +431,26 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
 // writes.  Both coefficients are positive, so the argument is monotone and needs no clamp.  (A 3-coefficient fit
 // reaches 2.5e-5 but costs a clamp + one more FMA per element in an epilogue that is issue-bound; the fp32-exact
 // mode uses erff.)
+// ---- dropout (training mode of nn.Dropout; reference models/vanilla_vit.py:253,457,501-503, vanilla_bert.py:325,530,559,603)
+// keep / drop decided by a counter hash, so the adjoint regenerates the mask instead of storing it.  One 32-bit hash
+// serves two neighbouring elements (16 bits each): element kept iff its 16 bits >= thr16 = round(p * 65536).
+__host__ __device__ __forceinline__ uint32_t agb_hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t agb_drop_key(unsigned long long seed, uint32_t a, uint32_t b) {
+  return agb_hash32(agb_hash32((uint32_t)seed ^ (a * 0x85EBCA6Bu)) ^ (uint32_t)(seed >> 32) ^ (b * 0xC2B2AE35u));
+}
+__host__ __device__ __forceinline__ uint32_t agb_drop_bits(uint32_t key, uint32_t pair) {
+  return agb_hash32(pair * 0x9E3779B1u + key);
+}
+// attention-probability dropout: stream of (row * heads + head, query index); pair = key index / 2
+__host__ __device__ __forceinline__ bool agb_attn_keep(unsigned long long seed, uint32_t unit, uint32_t query, uint32_t key_idx,
+                                                       uint32_t thr16) {
+  const uint32_t x = agb_drop_bits(agb_drop_key(seed, unit, query), key_idx >> 1);
+  return ((key_idx & 1u) ? (x >> 16) : (x & 0xFFFFu)) >= thr16;
+}
+
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -331,7 +331,8 @@ int cls_attention(const void* q, long long ldq, const void* kv, long long ldkv, 
 template <int D>
 __global__ void __launch_bounds__(128)
 attention_narrow_kernel(const bf16* __restrict__ qkv, const uint32_t* __restrict__ mask, int words, int T, int H, int heads,
-                        int mode, float scale_log2, bf16* __restrict__ ctx) {
+                        int mode, float scale_log2, bf16* __restrict__ ctx, unsigned drop_thr, unsigned long long drop_seed,
+                        float drop_scale) {
   extern __shared__ __align__(16) float sm_n[];
   float* sK = sm_n;            // T x D
   float* sV = sK + T * D;      // T x D
@@ -365,7 +366,9 @@ attention_narrow_kernel(const bf16* __restrict__ qkv, const uint32_t* __restrict
     int cnt = 0;
     for (int j0 = 0; j0 < T; j0 += 32) {
       const int j = j0 + threadIdx.x;
-      const bool keep = j < T && ((sM[j >> 5] >> (j & 31)) & 1u);
+      // with attention dropout every key is visited on its own (no folding of the ViT-masked ones): their K rows
+      // are zeroed below instead, which gives the same logit 0
+      const bool keep = j < T && (((sM[j >> 5] >> (j & 31)) & 1u) || (drop_thr && mode == AGB_MASK_MUL0));
       const uint32_t bal = __ballot_sync(0xffffffffu, keep);
       if (keep) sIdx[cnt + __popc(bal & ((1u << threadIdx.x) - 1u))] = j;
       cnt += __popc(bal);
@@ -376,12 +379,15 @@ attention_narrow_kernel(const bf16* __restrict__ qkv, const uint32_t* __restrict
     const int c = threadIdx.x % D, part = threadIdx.x / D, parts = blockDim.x / D;
     float acc = 0.f;
     for (int j = part; j < T; j += parts)
-      if (!((sM[j >> 5] >> (j & 31)) & 1u)) acc += sV[j * D + c];
+      if (!((sM[j >> 5] >> (j & 31)) & 1u)) {
+        acc += sV[j * D + c];
+        if (drop_thr) sK[j * D + c] = 0.f;
+      }
     atomicAdd(&sVm[c], acc);
   }
   __syncthreads();
   const int nkept = *sCnt;
-  const int nmasked = (mode == AGB_MASK_MUL0) ? T - nkept : 0;
+  const int nmasked = (mode == AGB_MASK_MUL0 && !drop_thr) ? T - nkept : 0;
   const int half = (T + 1) / 2;
   for (int i0 = threadIdx.x; i0 < half; i0 += blockDim.x) {
     const int i1 = i0 + half;                 // second query of this thread (may fall off the end)
@@ -429,9 +435,13 @@ attention_narrow_kernel(const bf16* __restrict__ qkv, const uint32_t* __restrict
         for (int k = 0; k < D; ++k) o1[k] *= c;
         m1 = s1;
       }
-      const float p0 = exp2f(s0 - m0), p1 = exp2f(s1 - m1);
+      float p0 = exp2f(s0 - m0), p1 = exp2f(s1 - m1);
       l0 += p0;
       l1 += p1;
+      if (drop_thr) {      // the row sums keep every probability; dropped ones only leave the P V product
+        if (!agb_attn_keep(drop_seed, blockIdx.x, i0, j, drop_thr)) p0 = 0.f;
+        if (!agb_attn_keep(drop_seed, blockIdx.x, i1, j, drop_thr)) p1 = 0.f;
+      }
       const float4* vr = reinterpret_cast<const float4*>(sV + j * D);
 #pragma unroll
       for (int v = 0; v < D / 4; ++v) {
@@ -466,7 +476,7 @@ attention_narrow_kernel(const bf16* __restrict__ qkv, const uint32_t* __restrict
         o1[k] = fmaf(p1, sVm[k], o1[k]);
       }
     }
-    const float r0 = l0 > 0.f ? 1.f / l0 : 0.f, r1 = l1 > 0.f ? 1.f / l1 : 0.f;
+    const float r0 = l0 > 0.f ? drop_scale / l0 : 0.f, r1 = l1 > 0.f ? drop_scale / l1 : 0.f;
     bf16* c0 = ctx + ((long long)row * T + i0) * H + head * D;
     bf16* c1 = ctx + ((long long)row * T + i1) * H + head * D;
 #pragma unroll
@@ -487,19 +497,20 @@ attention_narrow_kernel(const bf16* __restrict__ qkv, const uint32_t* __restrict
 
 template <int D>
 static int launch_attention_narrow(const bf16* qkv, const uint32_t* mask, int words, int rows, int T, int H, int heads,
-                                   int mode, bf16* ctx, cudaStream_t st) {
+                                   int mode, bf16* ctx, cudaStream_t st, unsigned drop_thr, unsigned long long drop_seed) {
   const size_t smem = ((size_t)2 * T * D + D + T + 1) * sizeof(float) + (size_t)words * sizeof(uint32_t);
   if (smem > 227 * 1024) return AGB_ERR_UNSUPPORTED;
   AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_narrow_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int threads = min(128, (((T + 1) / 2 + 31) / 32) * 32);
   attention_narrow_kernel<D><<<rows * heads, threads, smem, st>>>(qkv, mask, words, T, H, heads, mode,
-                                                                   rsqrtf((float)D) * 1.4426950408889634f, ctx);
+                                                                   rsqrtf((float)D) * 1.4426950408889634f, ctx, drop_thr,
+                                                                   drop_seed, 65536.0f / (65536.0f - (float)drop_thr));
   AGB_CHECK_CUDA(cudaGetLastError());
   return AGB_OK;
 }
 
 int attention_simt(const void* qkv, int io_bf16, const uint32_t* mask, int words, int rows, int T, int H,
-                   int heads, int mode, void* ctx, cudaStream_t st) {
+                   int heads, int mode, void* ctx, cudaStream_t st, unsigned drop_thr, unsigned long long drop_seed) {
   AGB_REQUIRE(rows >= 0 && T > 0 && heads > 0 && H % heads == 0, "attention shape");
   AGB_REQUIRE(words * 32 >= T, "mask words");
   AGB_REQUIRE(mode == AGB_MASK_MUL0 || mode == AGB_MASK_NEGINF, "mask mode");
@@ -511,10 +522,14 @@ int attention_simt(const void* qkv, int io_bf16, const uint32_t* mask, int words
       (reinterpret_cast<uintptr_t>(ctx) & 15) == 0) {
     const bf16* q16 = static_cast<const bf16*>(qkv);
     bf16* c16 = static_cast<bf16*>(ctx);
-    const int rc = d == 8 ? launch_attention_narrow<8>(q16, mask, words, rows, T, H, heads, mode, c16, st)
-                 : d == 16 ? launch_attention_narrow<16>(q16, mask, words, rows, T, H, heads, mode, c16, st)
-                           : launch_attention_narrow<32>(q16, mask, words, rows, T, H, heads, mode, c16, st);
+    const int rc = d == 8 ? launch_attention_narrow<8>(q16, mask, words, rows, T, H, heads, mode, c16, st, drop_thr, drop_seed)
+                 : d == 16 ? launch_attention_narrow<16>(q16, mask, words, rows, T, H, heads, mode, c16, st, drop_thr, drop_seed)
+                           : launch_attention_narrow<32>(q16, mask, words, rows, T, H, heads, mode, c16, st, drop_thr, drop_seed);
     if (rc != AGB_ERR_UNSUPPORTED) return rc;
+  }
+  if (drop_thr > 0) {
+    set_last_error("attention dropout: bf16 with head dim 64 (T <= 256) or head dims 8/16/32 only");
+    return AGB_ERR_UNSUPPORTED;
   }
   AGB_REQUIRE(rows <= 65535 && heads <= 65535, "grid limits (chunk the rows)");
   const int nw = 4;

@@ -469,6 +469,56 @@ def masked_attention_bwd(qkv: Tensor, dctx: Tensor, packed_mask: Tensor, T: int,
     return dqkv
 
 
+# ---- dropout (training mode; masks are regenerated from a counter hash, never stored) --------------------------------
+def dropout_thr(p: float) -> int:
+    """16-bit threshold of a drop probability: an element is dropped iff its 16 hash bits < round(p * 65536)."""
+    assert 0.0 <= p < 1.0
+    return int(round(p * 65536.0))
+
+
+def dropout(y: Tensor, thr16: int, seed: int, tag: int, *, residual: Optional[Tensor] = None, out_dtype=None) -> Tensor:
+    """out = residual + keep * y / (1 - p)   (agb_dropout); the adjoint is the same call on the gradient."""
+    y = _c(y)
+    out = torch.empty(y.shape, dtype=out_dtype or y.dtype, device=y.device)
+    if residual is not None:
+        residual = _c(residual)
+        assert residual.dtype == torch.float32 and residual.shape == y.shape
+    nat.call("agb_dropout", nat.ptr(y), _is_bf16(y), nat.ptr(residual), nat.ptr(out), _is_bf16(out), y.numel(), thr16,
+             seed & 0xFFFFFFFFFFFFFFFF, tag, nat.stream())
+    return out
+
+
+def masked_attention_dropout(qkv: Tensor, packed_mask: Tensor, T: int, heads: int, mode: int, thr16: int, seed: int) -> Tensor:
+    """masked_attention with dropout on the probabilities (bf16; head dim 64 with T <= 256, or head dims 8/16/32)."""
+    assert qkv.dtype == torch.bfloat16, "attention dropout runs in bf16 mode only (set module.agb_dropout = False for fp32)"
+    qkv = _c(qkv)
+    rows = packed_mask.shape[0]
+    H = qkv.shape[1] // 3
+    ctx = torch.empty((rows * T, H), dtype=torch.bfloat16, device=qkv.device)
+    nat.call("agb_masked_attention_dropout_fwd", nat.ptr(qkv), nat.ptr(packed_mask), packed_mask.shape[1], rows, T, H, heads,
+             mode, nat.ptr(ctx), thr16, seed & 0xFFFFFFFFFFFFFFFF, nat.stream())
+    return ctx
+
+
+def masked_attention_dropout_bwd(qkv: Tensor, dctx: Tensor, packed_mask: Tensor, T: int, heads: int, mode: int, thr16: int,
+                                 seed: int) -> Tensor:
+    qkv, dctx = _c(qkv), _c(dctx)
+    assert qkv.dtype == torch.bfloat16 and dctx.dtype == torch.bfloat16
+    rows = qkv.shape[0] // T
+    H = qkv.shape[1] // 3
+    dqkv = torch.empty_like(qkv)
+    nat.call("agb_masked_attention_dropout_bwd", nat.ptr(qkv), nat.ptr(dctx), nat.ptr(packed_mask), packed_mask.shape[1], rows,
+             T, H, heads, mode, nat.ptr(dqkv), thr16, seed & 0xFFFFFFFFFFFFFFFF, nat.stream())
+    return dqkv
+
+
+def attention_dropout_mask(rows: int, heads: int, T: int, thr16: int, seed: int, device) -> Tensor:
+    """(rows, heads, T, T) uint8 keep mask the attention kernels regenerate (tests / diagnostics)."""
+    keep = torch.empty((rows, heads, T, T), dtype=torch.uint8, device=device)
+    nat.call("agb_attention_dropout_mask", nat.ptr(keep), rows, heads, T, thr16, seed & 0xFFFFFFFFFFFFFFFF, nat.stream())
+    return keep
+
+
 def vit_embed_bwd(dx: Tensor, B: int, T: int, H: int, dpos: Tensor, dcls: Tensor, patch_dtype) -> Tensor:
     dpatch = torch.empty((B * (T - 1), H), dtype=patch_dtype, device=dx.device)
     nat.call("agb_vit_embed_bwd", nat.ptr(_c(dx)), B, T, H, nat.ptr(dpos), nat.ptr(dcls), nat.ptr(dpatch),

@@ -8,9 +8,12 @@ transposed copies), attention / LayerNorm / GELU / head adjoints on their own ke
 reference's loop (`phi = fw_explainer(...); loss = loss_shapley_new(...); loss.backward();
 optimizer.step()`) runs unchanged.
 
-Dropout: the reference keeps hidden/attention dropout (p = 0.1) active while training.  This path
-implements p = 0 (deterministic); bench.py states that setting.  Parity tests compare gradients with the
-reference in eval() mode, where the reference's dropout is the identity.
+Dropout: the reference keeps hidden / attention-probability dropout (p = 0.1 in the checked-in configs) active while
+training.  In train() mode this path applies both (bf16 mode; `_Drop`): elementwise sites through `agb_dropout`, the
+attention probabilities inside the tcgen05 attention forward and adjoint, masks regenerated from a counter hash in the
+backward pass.  `module.agb_dropout = False` gives the deterministic p = 0 path that the parity tests compare with the
+reference run in eval() mode (where its dropout is the identity); the random streams differ from torch's, so dropout
+itself is checked against a torch re-statement that uses the exported masks (tests/test_gpu_dropout.py).
 """
 from __future__ import annotations
 
@@ -23,6 +26,57 @@ from . import engine, ops
 from .engine import LayerWeights, _Policy, _f32, n_players_of
 
 Grads = Dict[str, Tensor]
+
+
+class _Drop:
+    """Dropout state of one training forward (reference: nn.Dropout modules active in train() mode, hidden_dropout_prob on
+    embeddings / attention-output / MLP-output, attention_probs_dropout_prob on the attention probabilities).  Masks come
+    from a counter hash of (seed, site tag, element), so the tape stores two integers per site instead of a mask."""
+
+    def __init__(self, cfg, enabled: bool):
+        self.h = ops.dropout_thr(float(cfg.hidden_dropout_prob)) if enabled else 0
+        self.a = ops.dropout_thr(float(cfg.attention_probs_dropout_prob)) if enabled else 0
+        # CPU generator: follows torch.manual_seed and costs no device synchronisation
+        self.seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (self.h or self.a) else 0
+        self.n = 0
+
+    def tag(self) -> int:
+        self.n += 1
+        return self.n
+
+    def site_seed(self, tag: int) -> int:
+        return (self.seed + tag * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+
+
+_NO_DROP = None
+
+
+def _linear_drop(pol: _Policy, drop, a: Tensor, w: Tensor, b: Tensor, residual: Tensor) -> Tuple[Tensor, int]:
+    """residual + dropout(a @ w^T + b) -> (fp32, site tag | 0): with p = 0 the residual rides in the GEMM epilogue."""
+    if drop is None or not drop.h:
+        return pol.linear(a, w, b, residual=residual, out_f32=True), 0
+    tag = drop.tag()
+    return ops.dropout(pol.linear(a, w, b), drop.h, drop.seed, tag, residual=residual, out_dtype=torch.float32), tag
+
+
+def _act_drop(pol: _Policy, drop, dx: Tensor, tag: int) -> Tensor:
+    """gradient w.r.t. the dense output behind a dropout site, in the activation dtype"""
+    if not tag:
+        return pol.act(dx)
+    return ops.dropout(dx, drop.h, drop.seed, tag, out_dtype=pol.act_dtype)
+
+
+def _attention_fwd(drop, qkv: Tensor, masks: Tensor, T: int, heads: int, mode: int) -> Tuple[Tensor, int]:
+    if drop is None or not drop.a:
+        return ops.masked_attention(qkv, masks, T, heads, mode), 0
+    tag = drop.tag()
+    return ops.masked_attention_dropout(qkv, masks, T, heads, mode, drop.a, drop.site_seed(tag)), tag
+
+
+def _attention_bwd(drop, tag: int, qkv: Tensor, dctx: Tensor, masks: Tensor, T: int, heads: int, mode: int) -> Tensor:
+    if not tag:
+        return ops.masked_attention_bwd(qkv, dctx, masks, T, heads, mode)
+    return ops.masked_attention_dropout_bwd(qkv, dctx, masks, T, heads, mode, drop.a, drop.site_seed(tag))
 
 
 def _wgrad(pol: _Policy, dy: Tensor, x: Tensor) -> Tensor:
@@ -69,32 +123,33 @@ def _ln_bwd(grads: Grads, name: str, x: Tensor, dy: Tensor, gamma: Tensor, eps: 
 # ------------------------------------------------------------------------------------------------
 # ViT block (pre-LN), reference models/vanilla_vit.py:364-377
 # ------------------------------------------------------------------------------------------------
-def vit_layer_fwd(pol, lw: LayerWeights, x: Tensor, masks: Tensor, T: int, heads: int, eps: float):
+def vit_layer_fwd(pol, lw: LayerWeights, x: Tensor, masks: Tensor, T: int, heads: int, eps: float, drop=None):
     h1 = pol.ln(x, lw.ln1[0], lw.ln1[1], eps)[0] if lw.ln1 is not None else pol.act(x)
     qkv = pol.linear(h1, lw.wqkv, lw.bqkv)
-    ctx = ops.masked_attention(qkv, masks, T, heads, ops.MASK_MUL0)
-    x_mid = pol.linear(ctx, lw.wo, lw.bo, residual=x, out_f32=True)
+    ctx, ta = _attention_fwd(drop, qkv, masks, T, heads, ops.MASK_MUL0)
+    x_mid, t1 = _linear_drop(pol, drop, ctx, lw.wo, lw.bo, x)
     h2 = pol.ln(x_mid, lw.ln2[0], lw.ln2[1], eps)[0]
     z = pol.linear(h2, lw.w1, lw.b1)
     f = ops.gelu_fwd(z)
-    x_out = pol.linear(f, lw.w2, lw.b2, residual=x_mid, out_f32=True)
-    return x_out, dict(x_in=x, h1=h1, qkv=qkv, ctx=ctx, x_mid=x_mid, h2=h2, z=z, f=f)
+    x_out, t2 = _linear_drop(pol, drop, f, lw.w2, lw.b2, x_mid)
+    return x_out, dict(x_in=x, h1=h1, qkv=qkv, ctx=ctx, x_mid=x_mid, h2=h2, z=z, f=f, drop=drop, tags=(ta, t1, t2))
 
 
 def vit_layer_bwd(pol, lw: LayerWeights, prefix: str, t: dict, dx_out: Tensor, masks: Tensor, T: int, heads: int,
                   eps: float, grads: Grads, need_dx: bool = True) -> Optional[Tensor]:
     H = dx_out.shape[1]
-    g = pol.act(dx_out)
+    drop, (ta, t1, t2) = t["drop"], t["tags"]
+    g = _act_drop(pol, drop, dx_out, t2)
     _linear_bwd(pol, grads, prefix + ".output.dense", g, t["f"])
     df = _dgrad(pol, g, lw.w2, out_f32=False)
     dz = ops.gelu_bwd(df, t["z"])
     _linear_bwd(pol, grads, prefix + ".intermediate.dense", dz, t["h2"])
     dh2 = _dgrad(pol, dz, lw.w1, out_f32=True)
     dx_mid = _ln_bwd(grads, prefix + ".layernorm_after", t["x_mid"], dh2, lw.ln2[0], eps, dx_out)
-    g = pol.act(dx_mid)
+    g = _act_drop(pol, drop, dx_mid, t1)
     _linear_bwd(pol, grads, prefix + ".attention.output.dense", g, t["ctx"])
     dctx = _dgrad(pol, g, lw.wo, out_f32=False)
-    dqkv = ops.masked_attention_bwd(t["qkv"], dctx, masks, T, heads, ops.MASK_MUL0)
+    dqkv = _attention_bwd(drop, ta, t["qkv"], dctx, masks, T, heads, ops.MASK_MUL0)
     _qkv_bwd(pol, grads, prefix, dqkv, t["h1"], H)
     if not need_dx and lw.ln1 is None:
         return None          # nothing trainable below this block (frozen backbone)
@@ -107,26 +162,27 @@ def vit_layer_bwd(pol, lw: LayerWeights, prefix: str, t: dict, dx_out: Tensor, m
 # ------------------------------------------------------------------------------------------------
 # BERT block (post-LN), reference models/vanilla_bert.py:396-427, 556-560, 600-604
 # ------------------------------------------------------------------------------------------------
-def bert_layer_fwd(pol, lw: LayerWeights, x: Tensor, xa: Tensor, masks: Tensor, T: int, heads: int, eps: float):
+def bert_layer_fwd(pol, lw: LayerWeights, x: Tensor, xa: Tensor, masks: Tensor, T: int, heads: int, eps: float, drop=None):
     qkv = pol.linear(xa, lw.wqkv, lw.bqkv)
-    ctx = ops.masked_attention(qkv, masks, T, heads, ops.MASK_NEGINF)
-    a_pre = pol.linear(ctx, lw.wo, lw.bo, residual=x, out_f32=True)
+    ctx, ta = _attention_fwd(drop, qkv, masks, T, heads, ops.MASK_NEGINF)
+    a_pre, t1 = _linear_drop(pol, drop, ctx, lw.wo, lw.bo, x)
     if lw.ln1 is not None:
         aa, a = pol.ln(a_pre, lw.ln1[0], lw.ln1[1], eps, want_f32=True)
     else:
         a, aa = a_pre, pol.act(a_pre)
     z = pol.linear(aa, lw.w1, lw.b1)
     f = ops.gelu_fwd(z)
-    y_pre = pol.linear(f, lw.w2, lw.b2, residual=a, out_f32=True)
+    y_pre, t2 = _linear_drop(pol, drop, f, lw.w2, lw.b2, a)
     ya, y = pol.ln(y_pre, lw.ln2[0], lw.ln2[1], eps, want_f32=True)
-    return y, ya, dict(xa=xa, qkv=qkv, ctx=ctx, a_pre=a_pre, aa=aa, z=z, f=f, y_pre=y_pre)
+    return y, ya, dict(xa=xa, qkv=qkv, ctx=ctx, a_pre=a_pre, aa=aa, z=z, f=f, y_pre=y_pre, drop=drop, tags=(ta, t1, t2))
 
 
 def bert_layer_bwd(pol, lw: LayerWeights, prefix: str, t: dict, dy: Tensor, masks: Tensor, T: int, heads: int,
                    eps: float, grads: Grads, need_dx: bool = True) -> Optional[Tensor]:
     H = dy.shape[1]
+    drop, (ta, t1, t2) = t["drop"], t["tags"]
     d_ypre = _ln_bwd(grads, prefix + ".output.LayerNorm", t["y_pre"], dy, lw.ln2[0], eps, None)
-    g = pol.act(d_ypre)
+    g = _act_drop(pol, drop, d_ypre, t2)
     _linear_bwd(pol, grads, prefix + ".output.dense", g, t["f"])
     df = _dgrad(pol, g, lw.w2, out_f32=False)
     dz = ops.gelu_bwd(df, t["z"])
@@ -134,26 +190,32 @@ def bert_layer_bwd(pol, lw: LayerWeights, prefix: str, t: dict, dy: Tensor, mask
     da = _dgrad(pol, dz, lw.w1, out_f32=True, residual=d_ypre)
     d_apre = _ln_bwd(grads, prefix + ".attention.output.LayerNorm", t["a_pre"], da, lw.ln1[0], eps, None) \
         if lw.ln1 is not None else da
-    g = pol.act(d_apre)
+    g = _act_drop(pol, drop, d_apre, t1)
     _linear_bwd(pol, grads, prefix + ".attention.output.dense", g, t["ctx"])
     dctx = _dgrad(pol, g, lw.wo, out_f32=False)
-    dqkv = ops.masked_attention_bwd(t["qkv"], dctx, masks, T, heads, ops.MASK_NEGINF)
+    dqkv = _attention_bwd(drop, ta, t["qkv"], dctx, masks, T, heads, ops.MASK_NEGINF)
     _qkv_bwd(pol, grads, prefix, dqkv, t["xa"], H)
     if not need_dx:
         return None          # nothing trainable below this block (frozen backbone)
     return _dgrad(pol, dqkv, lw.wqkv, out_f32=True, residual=d_apre)
 
 
-def _embed_fwd(tp, bw, cfg, pol, xs: Tensor):
-    """Embeddings with S = 1 (one mask row per input); keeps what the adjoint needs on the tape."""
+def _embed_fwd(tp, bw, cfg, pol, xs: Tensor, drop=None):
+    """Embeddings with S = 1 (one mask row per input); keeps what the adjoint needs on the tape.  The embedding dropout
+    (reference models/vanilla_vit.py:253, models/vanilla_bert.py:325) is applied here when `drop` is active."""
     T, H, eps = tp.T, cfg.hidden_size, cfg.layer_norm_eps
     B = xs.shape[0]
+    tp.drop, tp.embed_tag = drop, 0
     if bw.vit:
         tp.patches = ops.vit_im2col(xs.float(), cfg.img_patch_size, pol.act_dtype)
         pe = pol.linear(tp.patches, bw.w_patch, bw.b_patch, out_f32=True)
-        return ops.vit_assemble(pe, bw.cls_token, bw.pos_emb, B, 1, T, H).reshape(B * T, H), None
-    x = ops.bert_embed(xs, bw.word, bw.pos, bw.type0, bw.emb_ln[0], bw.emb_ln[1], eps, 1).reshape(B * T, H)
-    return x, pol.act(x)
+        x = ops.vit_assemble(pe, bw.cls_token, bw.pos_emb, B, 1, T, H).reshape(B * T, H)
+    else:
+        x = ops.bert_embed(xs, bw.word, bw.pos, bw.type0, bw.emb_ln[0], bw.emb_ln[1], eps, 1).reshape(B * T, H)
+    if drop is not None and drop.h:
+        tp.embed_tag = drop.tag()
+        x = ops.dropout(x, drop.h, drop.seed, tp.embed_tag)
+    return x, (None if bw.vit else pol.act(x))
 
 
 def _embed_bwd(tp, dx: Tensor, grads: Grads) -> None:
@@ -162,6 +224,8 @@ def _embed_bwd(tp, dx: Tensor, grads: Grads) -> None:
     vit = bw.vit
     T, B = tp.T, tp.B
     H, eps = cfg.hidden_size, cfg.layer_norm_eps
+    if tp.embed_tag:
+        dx = ops.dropout(dx, tp.drop.h, tp.drop.seed, tp.embed_tag)
     if vit:
         dpos = torch.zeros((T, H), dtype=torch.float32, device=dx.device)
         dcls = torch.zeros((H,), dtype=torch.float32, device=dx.device)
@@ -196,7 +260,7 @@ class _Tape:
 
 
 def forward_train(sd: Dict[str, Tensor], cfg, precision: str, xs: Tensor, masks: Tensor, grand, null,
-                  train_backbone: bool = True) -> Tuple[Tensor, _Tape]:
+                  train_backbone: bool = True, dropout: bool = False) -> Tuple[Tensor, _Tape]:
     """train_backbone=False (Froyo, reference models/froyo_vit.py:88-97 / froyo_bert.py:92-101: every `vit.` / `bert.`
     parameter frozen): the encoder stack runs on the inference engine without a tape and the adjoint stops at the
     first explainer_attn block."""
@@ -204,6 +268,10 @@ def forward_train(sd: Dict[str, Tensor], cfg, precision: str, xs: Tensor, masks:
     tp = _Tape()
     tp.pol, tp.cfg, tp.masks, tp.xs = pol, cfg, masks, xs
     tp.train_backbone = train_backbone
+    # dropout=True: hidden / attention-probability dropout as in the reference's train() mode (the frozen backbone of the
+    # Froyo / LTT variants always runs deterministically on the inference engine)
+    drop = _Drop(cfg, True) if dropout else None
+    tp.drop, tp.embed_tag, tp.head_tag = drop, 0, 0
     bw = engine.BackboneWeights(sd, cfg, pol)
     vit = bw.vit
     T = n_players_of(cfg) + 1
@@ -213,13 +281,13 @@ def forward_train(sd: Dict[str, Tensor], cfg, precision: str, xs: Tensor, masks:
     root = "vit" if vit else "bert"
     tp.layers = []
     if train_backbone:
-        x, xa = _embed_fwd(tp, bw, cfg, pol, xs)
+        x, xa = _embed_fwd(tp, bw, cfg, pol, xs, drop)
         for i, lw in enumerate(bw.layers):
             prefix = f"{root}.encoder.layers.{i}"
             if vit:
-                x, t = vit_layer_fwd(pol, lw, x, masks, T, heads, eps)
+                x, t = vit_layer_fwd(pol, lw, x, masks, T, heads, eps, drop)
             else:
-                x, xa, t = bert_layer_fwd(pol, lw, x, xa, masks, T, heads, eps)
+                x, xa, t = bert_layer_fwd(pol, lw, x, xa, masks, T, heads, eps, drop)
             tp.layers.append((prefix, lw, t))
     else:
         x, xa = engine.run_backbone(bw, cfg, pol, xs, masks, 1)
@@ -232,9 +300,9 @@ def forward_train(sd: Dict[str, Tensor], cfg, precision: str, xs: Tensor, masks:
         prefix = f"explainer_attn.{i}"
         lw = LayerWeights(sd, prefix, pol, vit)
         if vit:
-            x, t = vit_layer_fwd(pol, lw, x, masks, T, heads, eps)
+            x, t = vit_layer_fwd(pol, lw, x, masks, T, heads, eps, drop)
         else:
-            x, xa, t = bert_layer_fwd(pol, lw, x, xa, masks, T, heads, eps)
+            x, xa, t = bert_layer_fwd(pol, lw, x, xa, masks, T, heads, eps, drop)
         tp.layers.append((prefix, lw, t))
     if vit:
         tp.mlp_ln = (_f32(sd["explainer_mlp.0.weight"]), _f32(sd["explainer_mlp.0.bias"]))
@@ -243,7 +311,11 @@ def forward_train(sd: Dict[str, Tensor], cfg, precision: str, xs: Tensor, masks:
         h0 = pol.ln(x, tp.mlp_ln[0], tp.mlp_ln[1], 1e-5)[0]
     else:
         tp.names = ("explainer_mlp.0", "explainer_mlp.2", "explainer_mlp.4")
-        h0 = xa
+        if drop is not None and drop.h:      # explainer_dropout (reference models/vanilla_bert.py:152)
+            tp.head_tag = drop.tag()
+            h0 = ops.dropout(x, drop.h, drop.seed, tp.head_tag, out_dtype=pol.act_dtype)
+        else:
+            h0 = xa
     na, nb, nc = tp.names
     tp.w_a, tp.w_b = pol.weight(sd[na + ".weight"]), pol.weight(sd[nb + ".weight"])
     tp.w_c, b_c = _f32(sd[nc + ".weight"]), _f32(sd[nc + ".bias"])
@@ -274,6 +346,8 @@ def backward_train(tp: _Tape, dphi: Tensor) -> Grads:
     dx = _dgrad(pol, dza, tp.w_a, out_f32=True)
     if vit:
         dx = _ln_bwd(grads, "explainer_mlp.0", tp.x_last, dx, tp.mlp_ln[0], 1e-5, None)
+    elif tp.head_tag:
+        dx = ops.dropout(dx, tp.drop.h, tp.drop.seed, tp.head_tag)
     n_backbone = len(bw.layers) if tp.train_backbone else 0
     for idx in range(len(tp.layers) - 1, -1, -1):
         prefix, lw, t = tp.layers[idx]
@@ -292,11 +366,11 @@ def backward_train(tp: _Tape, dphi: Tensor) -> Grads:
 
 class _ExplainerTrainFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, xs, masks, grand, null, cfg, precision, names, *params):
+    def forward(ctx, xs, masks, grand, null, cfg, precision, dropout, names, *params):
         sd = {n: p.detach() for n, p in zip(names, params)}
-        train_backbone = any(ctx.needs_input_grad[7 + i] for i, n in enumerate(names) if n.startswith(("vit.", "bert.")))
+        train_backbone = any(ctx.needs_input_grad[8 + i] for i, n in enumerate(names) if n.startswith(("vit.", "bert.")))
         with torch.no_grad():
-            phi, tape = forward_train(sd, cfg, precision, xs, masks, grand, null, train_backbone)
+            phi, tape = forward_train(sd, cfg, precision, xs, masks, grand, null, train_backbone, dropout)
         ctx.tape, ctx.names = tape, names
         ctx.shapes = [p.shape for p in params]
         return phi
@@ -310,7 +384,15 @@ class _ExplainerTrainFn(torch.autograd.Function):
         for n, shp in zip(ctx.names, ctx.shapes):
             g = grads.get(n)
             out.append(g.reshape(shp) if g is not None else None)
-        return (None, None, None, None, None, None, None, *out)
+        return (None, None, None, None, None, None, None, None, *out)
+
+
+def _wants_dropout(model) -> bool:
+    """train() mode turns the reference's nn.Dropout modules on; `module.agb_dropout = False` keeps this path
+    deterministic (p = 0), e.g. for gradient parity against the reference run in eval() mode."""
+    cfg = model.config
+    return bool(model.training and getattr(model, "agb_dropout", True)
+                and (cfg.hidden_dropout_prob > 0 or cfg.attention_probs_dropout_prob > 0))
 
 
 def explainer_forward_train(model, xs: Tensor, words: Tensor, grand: Optional[Tensor], null: Optional[Tensor]) -> Tensor:
@@ -322,7 +404,7 @@ def explainer_forward_train(model, xs: Tensor, words: Tensor, grand: Optional[Te
         raise RuntimeError("autognothi_b200 models run on CUDA only (no CPU fallback)")
     g = grand.detach() if grand is not None else None
     nl = null.detach() if null is not None else None
-    return _ExplainerTrainFn.apply(xs, words, g, nl, model.config, model.agb_precision, names, *params)
+    return _ExplainerTrainFn.apply(xs, words, g, nl, model.config, model.agb_precision, _wants_dropout(model), names, *params)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -330,7 +412,8 @@ def explainer_forward_train(model, xs: Tensor, words: Tensor, grand: Optional[Te
 # autograd node returning the CLS rows of the last hidden state; the tiny head (final LayerNorm / pooler, Linear,
 # Softmax on B rows) and loss_logits_kl_divergence stay in torch autograd.
 # ------------------------------------------------------------------------------------------------
-def backbone_forward_train(sd: Dict[str, Tensor], cfg, precision: str, xs: Tensor, masks: Tensor) -> Tuple[Tensor, _Tape]:
+def backbone_forward_train(sd: Dict[str, Tensor], cfg, precision: str, xs: Tensor, masks: Tensor, dropout: bool = False
+                           ) -> Tuple[Tensor, _Tape]:
     """-> (x_cls (B, H) fp32: ViT = last block output BEFORE vit.layernorm, BERT = last block output; tape)"""
     pol = _Policy(precision)
     tp = _Tape()
@@ -341,13 +424,14 @@ def backbone_forward_train(sd: Dict[str, Tensor], cfg, precision: str, xs: Tenso
     tp.bw, tp.T, tp.B = bw, T, xs.shape[0]
     assert masks.shape[0] == tp.B, "surrogate training takes one mask row per input"
     root = "vit" if bw.vit else "bert"
-    x, xa = _embed_fwd(tp, bw, cfg, pol, xs)
+    drop = _Drop(cfg, True) if dropout else None
+    x, xa = _embed_fwd(tp, bw, cfg, pol, xs, drop)
     tp.layers = []
     for i, lw in enumerate(bw.layers):
         if bw.vit:
-            x, t = vit_layer_fwd(pol, lw, x, masks, T, heads, eps)
+            x, t = vit_layer_fwd(pol, lw, x, masks, T, heads, eps, drop)
         else:
-            x, xa, t = bert_layer_fwd(pol, lw, x, xa, masks, T, heads, eps)
+            x, xa, t = bert_layer_fwd(pol, lw, x, xa, masks, T, heads, eps, drop)
         tp.layers.append((f"{root}.encoder.layers.{i}", lw, t))
     return x.reshape(tp.B, T, -1)[:, 0, :].contiguous(), tp
 
@@ -371,10 +455,10 @@ def backbone_backward_train(tp: _Tape, dx_cls: Tensor) -> Grads:
 
 class _BackboneTrainFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, xs, masks, cfg, precision, names, *params):
+    def forward(ctx, xs, masks, cfg, precision, dropout, names, *params):
         sd = {n: p.detach() for n, p in zip(names, params)}
         with torch.no_grad():
-            x_cls, tape = backbone_forward_train(sd, cfg, precision, xs, masks)
+            x_cls, tape = backbone_forward_train(sd, cfg, precision, xs, masks, dropout)
         ctx.tape, ctx.names = tape, names
         ctx.shapes = [p.shape for p in params]
         return x_cls
@@ -388,7 +472,7 @@ class _BackboneTrainFn(torch.autograd.Function):
         for n, shp in zip(ctx.names, ctx.shapes):
             g = grads.get(n)
             out.append(g.reshape(shp) if g is not None else None)
-        return (None, None, None, None, None, *out)
+        return (None, None, None, None, None, None, *out)
 
 
 def surrogate_forward_train(model, xs: Tensor, words: Tensor) -> Tensor:
@@ -401,8 +485,9 @@ def surrogate_forward_train(model, xs: Tensor, words: Tensor) -> Tensor:
     vit = hasattr(cfg, "img_px_size")
     root = "vit." if vit else "bert."
     names = [n for n in named if n.startswith(root)]   # vit.layernorm.* ride along unused (their grads come from the torch head)
+    dropout = _wants_dropout(model)
     if any(named[n].requires_grad for n in names):
-        x_cls = _BackboneTrainFn.apply(xs, words, cfg, model.agb_precision, names, *[named[n] for n in names])
+        x_cls = _BackboneTrainFn.apply(xs, words, cfg, model.agb_precision, dropout, names, *[named[n] for n in names])
     else:
         # frozen backbone (Froyo surrogate, reference models/froyo_vit.py:76-85): inference engine, CLS row only, no tape
         with torch.no_grad():
@@ -415,6 +500,7 @@ def surrogate_forward_train(model, xs: Tensor, words: Tensor) -> Tensor:
                                            named["vit.layernorm.bias"], cfg.layer_norm_eps)
     else:
         h = torch.tanh(torch.nn.functional.linear(x_cls, named["bert_pooler.dense.weight"], named["bert_pooler.dense.bias"]))
+        h = torch.nn.functional.dropout(h, float(cfg.hidden_dropout_prob), training=dropout)   # reference vanilla_bert.py:74
     logits = torch.nn.functional.linear(h, named["classifier.weight"], named["classifier.bias"])
     return torch.softmax(logits, dim=-1)
 
@@ -425,7 +511,8 @@ def surrogate_forward_train(model, xs: Tensor, words: Tensor) -> Tensor:
 # backbone runs on the inference engine (no tape); each rung keeps the backbone activation it tapped (for the map's
 # weight gradient), its pre-GELU map output and the tape of its narrow block.  No gradient flows into the backbone.
 # ------------------------------------------------------------------------------------------------
-def _ltt_side_forward(tp: _Tape, sd, cfg, pol, xs: Tensor, masks: Tensor, freeze_layer) -> Tuple[Tensor, Optional[Tensor], Tensor]:
+def _ltt_side_forward(tp: _Tape, sd, cfg, pol, xs: Tensor, masks: Tensor, freeze_layer, drop=None
+                      ) -> Tuple[Tensor, Optional[Tensor], Tensor]:
     """-> (side state (B*T, Hs) fp32, its activation copy (BERT) | None, backbone class probabilities (B, C))"""
     bw = engine.BackboneWeights(sd, cfg, pol)
     br = engine.SideBranch(sd, cfg, pol, bw.vit, 0)
@@ -448,10 +535,10 @@ def _ltt_side_forward(tp: _Tape, sd, cfg, pol, xs: Tensor, masks: Tensor, freeze
         if state["s"] is not None:
             s_in.add_(state["s"])
         if bw.vit:
-            s_out, t = vit_layer_fwd(pol, br.layers[i], s_in, masks, T, heads, eps)
+            s_out, t = vit_layer_fwd(pol, br.layers[i], s_in, masks, T, heads, eps, drop)
             sa = None
         else:
-            s_out, sa, t = bert_layer_fwd(pol, br.layers[i], s_in, pol.act(s_in), masks, T, heads, eps)
+            s_out, sa, t = bert_layer_fwd(pol, br.layers[i], s_in, pol.act(s_in), masks, T, heads, eps, drop)
         tp.rungs.append((i, x_act, z, br.layers[i], t))
         state["s"], state["sa"] = s_out, sa
 
@@ -480,14 +567,17 @@ def _ltt_rungs_backward(tp: _Tape, dx: Tensor, grads: Grads) -> None:
         dx = ds_in                                   # s_in = s_prev + GELU(map): the residual passes straight through
 
 
-def ltt_forward_train(sd, cfg, precision: str, xs: Tensor, masks: Tensor, grand, null, kind: str, freeze_layer):
+def ltt_forward_train(sd, cfg, precision: str, xs: Tensor, masks: Tensor, grand, null, kind: str, freeze_layer,
+                      dropout: bool = False):
     """kind "explainer": -> (phi (B, C, n), backbone probabilities, tape);
        kind "surrogate": -> (CLS rows of the side state (B, Hs) [ViT: before vit.s_attn_layernorm.0], backbone
                              probabilities, tape) — the tiny side head stays in torch autograd."""
     pol = _Policy(precision)
     tp = _Tape()
     tp.pol, tp.cfg, tp.masks, tp.xs, tp.kind = pol, cfg, masks, xs, kind
-    s, sa, cls = _ltt_side_forward(tp, sd, cfg, pol, xs, masks, freeze_layer)
+    drop = _Drop(cfg, True) if dropout else None      # the side ladder's dropout sites; the frozen backbone has none here
+    tp.drop, tp.head_tag = drop, 0
+    s, sa, cls = _ltt_side_forward(tp, sd, cfg, pol, xs, masks, freeze_layer, drop)
     vit = tp.bw.vit
     T, B = tp.T, tp.B
     heads, eps = cfg.num_attention_heads, cfg.layer_norm_eps
@@ -504,9 +594,9 @@ def ltt_forward_train(sd, cfg, precision: str, xs: Tensor, masks: Tensor, grand,
         prefix = f"{attn}.{i}"
         lw = LayerWeights(sd, prefix, pol, vit)
         if vit:
-            s, t = vit_layer_fwd(pol, lw, s, masks, T, heads, eps)
+            s, t = vit_layer_fwd(pol, lw, s, masks, T, heads, eps, drop)
         else:
-            s, sa, t = bert_layer_fwd(pol, lw, s, sa, masks, T, heads, eps)
+            s, sa, t = bert_layer_fwd(pol, lw, s, sa, masks, T, heads, eps, drop)
         tp.layers.append((prefix, lw, t))
     if vit:
         tp.mlp_ln_name = mlp + ".0"
@@ -516,7 +606,11 @@ def ltt_forward_train(sd, cfg, precision: str, xs: Tensor, masks: Tensor, grand,
         h0 = pol.ln(s, tp.mlp_ln[0], tp.mlp_ln[1], 1e-5)[0]
     else:
         tp.names = (mlp + ".0", mlp + ".2", mlp + ".4")
-        h0 = sa
+        if drop is not None and drop.h:      # s_attn_exp_dropout (reference models/ltt_bert.py:203)
+            tp.head_tag = drop.tag()
+            h0 = ops.dropout(s, drop.h, drop.seed, tp.head_tag, out_dtype=pol.act_dtype)
+        else:
+            h0 = sa
     na, nb, nc = tp.names
     tp.w_a, tp.w_b = pol.weight(sd[na + ".weight"]), pol.weight(sd[nb + ".weight"])
     tp.w_c, b_c = _f32(sd[nc + ".weight"]), _f32(sd[nc + ".bias"])
@@ -553,6 +647,8 @@ def ltt_backward_train(tp: _Tape, dout: Tensor) -> Grads:
     dx = _dgrad(pol, dza, tp.w_a, out_f32=True)
     if vit:
         dx = _ln_bwd(grads, tp.mlp_ln_name, tp.x_last, dx, tp.mlp_ln[0], 1e-5, None)
+    elif tp.head_tag:
+        dx = ops.dropout(dx, tp.drop.h, tp.drop.seed, tp.head_tag)
     for prefix, lw, t in reversed(tp.layers):
         if vit:
             dx = vit_layer_bwd(pol, lw, prefix, t, dx, tp.masks, T, heads, eps, grads)
@@ -566,10 +662,10 @@ def ltt_backward_train(tp: _Tape, dout: Tensor) -> Grads:
 
 class _LttTrainFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, xs, masks, grand, null, cfg, precision, kind, freeze_layer, names, *params):
+    def forward(ctx, xs, masks, grand, null, cfg, precision, kind, freeze_layer, dropout, names, *params):
         sd = {n: p.detach() for n, p in zip(names, params)}
         with torch.no_grad():
-            out, cls, tape = ltt_forward_train(sd, cfg, precision, xs, masks, grand, null, kind, freeze_layer)
+            out, cls, tape = ltt_forward_train(sd, cfg, precision, xs, masks, grand, null, kind, freeze_layer, dropout)
         ctx.tape, ctx.names = tape, names
         ctx.shapes = [p.shape for p in params]
         ctx.mark_non_differentiable(cls)
@@ -582,9 +678,9 @@ class _LttTrainFn(torch.autograd.Function):
         ctx.tape = None
         out = []
         for i, (n, shp) in enumerate(zip(ctx.names, ctx.shapes)):
-            g = grads.get(n) if ctx.needs_input_grad[9 + i] else None
+            g = grads.get(n) if ctx.needs_input_grad[10 + i] else None
             out.append(g.reshape(shp) if g is not None else None)
-        return (None,) * 9 + tuple(out)
+        return (None,) * 10 + tuple(out)
 
 
 def _ltt_apply(model, xs, words, grand, null, kind):
@@ -595,7 +691,7 @@ def _ltt_apply(model, xs, words, grand, null, kind):
     g = grand.detach() if grand is not None else None
     nl = null.detach() if null is not None else None
     return _LttTrainFn.apply(xs, words, g, nl, model.config, model.agb_precision, kind,
-                             getattr(model, "_ltt_freeze_layer", None), names, *[p for _, p in named])
+                             getattr(model, "_ltt_freeze_layer", None), _wants_dropout(model), names, *[p for _, p in named])
 
 
 def ltt_explainer_forward_train(model, xs: Tensor, words: Tensor, grand: Optional[Tensor], null: Optional[Tensor]
@@ -619,5 +715,6 @@ def ltt_surrogate_forward_train(model, xs: Tensor, words: Tensor) -> Tuple[Tenso
     else:
         h = torch.tanh(torch.nn.functional.linear(s_cls, named["bert_s_attn_pooler.dense.weight"],
                                                   named["bert_s_attn_pooler.dense.bias"]))
+        h = torch.nn.functional.dropout(h, float(cfg.hidden_dropout_prob), training=_wants_dropout(model))  # ltt_bert.py:115
     logits = torch.nn.functional.linear(h, named["s_attn_classifier.weight"], named["s_attn_classifier.bias"])
     return torch.softmax(logits, dim=-1), cls

@@ -353,7 +353,8 @@ def run_ours(args):
         train = {"metric": "explainer_train_samples_per_sec", "value": sps, "unit": "samples/s", "ms_per_step": ms_t / t_steps,
                  "steps": t_steps, "images_per_gpu_per_step": Bt, "coalitions_per_image": S, "flops_per_sample": fl_sample,
                  "tflops_per_gpu": sps / world * fl_sample * 1e-12, "gpu_launches": launches_t,
-                 "dropout": "p=0 (identity); the reference trains with p=0.1", "optimizer": "torch.optim.AdamW(fused=True), fp32 master weights",
+                 "dropout": "p=0.1 on embeddings / attention probabilities / attention-output / MLP-output (train() mode of the reference's "
+                            "config; masks from a counter hash, regenerated in the adjoint)", "optimizer": "torch.optim.AdamW(fused=True), fp32 master weights",
                  "grad_allreduce": f"NCCL, 64 MB flat buckets, world={world}"}
         peaks_t = load_peaks()
         train["frac_of_sustained_peak"] = train["tflops_per_gpu"] / peaks_t["bf16_tflops_sustained"]
@@ -417,7 +418,8 @@ def run_ours(args):
                "masked_evals_per_sec": world * rows * l_steps / (ms_le * 1e-3), "eval_ms_per_step": ms_le / l_steps,
                "train_samples_per_sec": world * Bl * l_steps / (ms_lt * 1e-3), "train_ms_per_step": ms_lt / l_steps,
                "trainable_params": int(sum(p.numel() for p in side_params)), "images_per_gpu_per_step": Bl,
-               "coalitions_per_image": S, "gpu_launches": launches_le + launches_lt, "dropout": "p=0 (identity)",
+               "coalitions_per_image": S, "gpu_launches": launches_le + launches_lt,
+               "dropout": "p=0.1 in the side ladder (train() mode); the frozen backbone runs deterministically on the inference engine",
                "grad_allreduce": f"NCCL, side parameters only, world={world}"}
 
     value = world * rows * args.steps / (ms * 1e-3)

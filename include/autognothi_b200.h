@@ -228,6 +228,23 @@ int agb_layernorm_bwd(const void* x, int x_is_bf16, const void* dy, int dy_is_bf
  * ladders of reference models/ltt_vit.py:386-396, ltt_bert.py:437-451) run a CUDA-core kernel with fp32-staged operands. */
 int agb_masked_attention_bwd(const void* qkv, const void* dctx, int io_is_bf16, const uint32_t* mask, int words,
                              int rows, int T, int H, int heads, int mode, void* dqkv, void* stream);
+/* nn.Dropout in training mode (reference models/vanilla_vit.py:253,501-503,512-516; models/vanilla_bert.py:325,559,603):
+ * out[e] = residual[e] + keep_e * y[e] / (1 - p), n elements, y fp32|bf16, residual fp32 (nullable), out fp32|bf16.
+ * keep_e comes from a counter hash of (seed, tag, e) compared with thr16 = round(p * 65536): the adjoint is the same
+ * call on the incoming gradient with the same (seed, tag), so no mask is stored. */
+int agb_dropout(const void* y, int y_is_bf16, const float* residual, void* out, int out_is_bf16, long long n,
+                int thr16, uint64_t seed, int tag, void* stream);
+/* Key-masked attention with dropout on the probabilities (training mode of reference models/vanilla_vit.py:454-459,
+ * models/vanilla_bert.py:527-532): ctx = (softmax(scores) o M / (1 - p)) V, M from the same counter hash keyed by
+ * (seed, row * heads + head, query, key).  bf16; head dim 64 with T <= 256 (tcgen05 kernels) or head dims 8/16/32.
+ * _bwd is its adjoint (regenerates M).  agb_attention_dropout_mask writes M as (rows, heads, T, T) bytes (tests). */
+int agb_masked_attention_dropout_fwd(const void* qkv, const uint32_t* mask, int words, int rows, int T, int H, int heads,
+                                     int mode, void* ctx, int thr16, uint64_t seed, void* stream);
+int agb_masked_attention_dropout_bwd(const void* qkv, const void* dctx, const uint32_t* mask, int words, int rows, int T,
+                                     int H, int heads, int mode, void* dqkv, int thr16, uint64_t seed,
+                                     void* stream);
+int agb_attention_dropout_mask(void* keep, int rows, int heads, int T, int thr16, uint64_t seed,
+                               void* stream);
 /* ViT embedding adjoint (reference models/vanilla_vit.py:242-253): dpos/dcls ACCUMULATED, dpatch (B*(T-1),H) */
 int agb_vit_embed_bwd(const float* dx, int B, int T, int H, float* dpos, float* dcls, void* dpatch,
                       int dpatch_is_bf16, void* stream);

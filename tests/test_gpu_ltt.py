@@ -136,6 +136,7 @@ def test_ltt_explainer_training_gradients(agb, golden_dir, name, precision):
     B, S, n = (int(v) for v in g["meta"])
     rec, cfgd, cfg, (srg, exp, fin) = _models(name, precision)
     exp.train()
+    exp.agb_dropout = False      # goldens: reference in eval() mode
     xs = torch.from_numpy(synth.inputs(cfgd, B, seed=0)).to(DEV)
     masks = torch.from_numpy(g["masks"].astype(np.int64)).to(DEV).reshape(B, S, n)
     v_side, grand, null = (torch.from_numpy(g[k]).to(DEV) for k in ("v_side", "grand", "null"))
@@ -177,6 +178,7 @@ def test_ltt_surrogate_training_gradients(agb, golden_dir, name):
     B, S, n = (int(v) for v in g["meta"])
     rec, cfgd, cfg, (srg, exp, fin) = _models(name, "fp32")
     srg.train()
+    srg.agb_dropout = False      # goldens: reference in eval() mode
     xs = torch.from_numpy(synth.inputs(cfgd, B, seed=0)).to(DEV)
     m1 = torch.from_numpy(g["masks"].astype(np.int64)).to(DEV).reshape(B, S, n)[:, 1, :].contiguous()
     side, main = rec.fw_surrogate(srg, xs, m1)

@@ -564,7 +564,8 @@ def _train_step_grads(golden_dir, name, precision):
     g = _load(golden_dir, f"model_{name}.npz")
     B, S, n = (int(v) for v in g["meta"])
     rec, cfgd, srg, exp = _build(name, precision)
-    exp.train()   # dropout is not applied on this path (p = 0); the golden ran the reference in eval()
+    exp.train()
+    exp.agb_dropout = False   # the golden ran the reference in eval() mode: dropout is the identity there
     xs = torch.from_numpy(synth.inputs(cfgd, B, seed=0)).to(DEV)
     masks = torch.from_numpy(g["masks"].astype(np.int64)).to(DEV).reshape(B, S, n)
     v_s, grand, null = (torch.from_numpy(g[k]).to(DEV) for k in ("v_s", "grand", "null"))
@@ -624,7 +625,7 @@ def test_training_loop_reduces_loss(agb, golden_dir):
     g = _load(golden_dir, f"model_{name}.npz")
     B, S, n = (int(v) for v in g["meta"])
     rec, cfgd, srg, exp = _build(name, "bf16")
-    exp.train()
+    exp.train()          # train() mode: hidden / attention dropout at the config's p = 0.1, as in the reference's loop
     opt = torch.optim.AdamW(exp.parameters(), lr=1e-4)
     xs = torch.from_numpy(synth.inputs(cfgd, B, seed=0)).to(DEV)
     masks = torch.from_numpy(g["masks"].astype(np.int64)).to(DEV).reshape(B, S, n)
@@ -800,7 +801,8 @@ def _surrogate_train_step(golden_dir, name, precision):
     cls.load_state_dict({k: torch.from_numpy(v) for k, v in synth.surrogate_state(cfgd, seed=5).items()}, strict=True)
     cls = cls.to(DEV).eval()
     cls.agb_precision = precision
-    srg.train()          # dropout is not applied on this path (p = 0); the golden ran the reference in eval()
+    srg.train()
+    srg.agb_dropout = False   # the golden ran the reference in eval() mode: dropout is the identity there
     B, n = t["masks"].shape
     xs = torch.from_numpy(synth.inputs(cfgd, B, seed=0)).to(DEV)
     masks = torch.from_numpy(t["masks"].astype(np.int64)).to(DEV)
@@ -864,7 +866,7 @@ def test_surrogate_training_loop_reduces_kl(agb):
     cls = rec.t_classifier(cfg)
     cls.load_state_dict({k: torch.from_numpy(v) for k, v in synth.surrogate_state(cfgd, seed=5).items()}, strict=True)
     cls = cls.to(DEV).eval()
-    srg.train()
+    srg.train()          # with dropout, as the reference's surrogate training loop
     opt = torch.optim.AdamW(srg.parameters(), lr=2e-3)
     xs = torch.from_numpy(synth.inputs(cfgd, 8, seed=1)).to(DEV)
     ones = torch.ones((8, n), dtype=torch.int64, device=DEV)
