@@ -238,6 +238,11 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank)
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
+__device__ __forceinline__ float ld_shared_cluster_f32(uint32_t cluster_addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }

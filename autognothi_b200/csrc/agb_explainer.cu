@@ -83,6 +83,131 @@ explainer_head_fwd_kernel(const TH* __restrict__ h, int T, int E, int C, const f
     for (int i = threadIdx.x; i < T * C; i += blockDim.x) pred_out[(long long)b * T * C + i] = pred[i];
 }
 
+// ------------------------------------------------------------------------------------------------
+// forward, clustered: one thread-block CLUSTER per input, CTA `rank` owns TPW * 8 consecutive tokens.  The head weights
+// (C x E fp32) sit in shared memory; each warp keeps TPW tokens x CMAX classes of accumulators in registers, so one
+// shared-memory read of W feeds TPW FMAs and h is streamed from HBM exactly once (8 B per lane, coalesced).  The token
+// sum of the efficiency normalisation crosses the CTAs of an input through distributed shared memory
+// (barrier.cluster + ld.shared::cluster): no second kernel, no atomics, deterministic.
+// (The one-CTA-per-input kernel above re-read W from L2 for every token and ran on B SMs only: 680 us at the bench
+// shape against 6 us of HBM time; profiles/r01_small_kernels_ncu.txt.)
+// ------------------------------------------------------------------------------------------------
+template <typename TH, int CMAX, int TPW>
+__global__ void __launch_bounds__(256)
+explainer_head_fwd_cluster_kernel(const TH* __restrict__ h, int T, int E, int C, const float* __restrict__ W,
+                                  const float* __restrict__ bias, const float* __restrict__ grand,
+                                  const float* __restrict__ null_v, int normalize, float* __restrict__ phi,
+                                  float* __restrict__ pred_out) {
+  constexpr int TOK = 8 * TPW;                 // tokens per CTA
+  extern __shared__ __align__(16) float sm[];
+  float* part = sm;                            // [MAXC] this CTA's token sums (same offset in every CTA of the cluster)
+  float* diff = sm + MAXC;                     // [MAXC]
+  float* pred = sm + 2 * MAXC;                 // [TOK][C]
+  float* sW = pred + TOK * MAXC;               // [C][E]
+  const int b = blockIdx.y;
+  const uint32_t rank = cluster_ctarank(), csize = gridDim.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x * 4; i < C * E; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(sW + i) = __ldg(reinterpret_cast<const float4*>(W + i));
+  __syncthreads();
+  const int t0 = (int)rank * TOK + warp * TPW;
+  float acc[TPW][CMAX];
+#pragma unroll
+  for (int k = 0; k < TPW; ++k)
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) acc[k][c] = 0.f;
+  const TH* hb = h + (long long)b * T * E;
+  for (int e = lane * 4; e < E; e += 128) {
+    float4 w[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      w[c] = (c < C) ? *reinterpret_cast<const float4*>(sW + (long long)c * E + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // all TPW rows are requested before the first FMA (tokens past the end re-read the last row; their results are
+    // dropped below), so the HBM latency is paid once per step instead of once per token
+    float4 x[TPW];
+#pragma unroll
+    for (int k = 0; k < TPW; ++k) x[k] = ld4<TH>(hb + (long long)min(t0 + k, T - 1) * E + e);
+#pragma unroll
+    for (int k = 0; k < TPW; ++k) {
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        acc[k][c] = fmaf(x[k].x, w[c].x, acc[k][c]);
+        acc[k][c] = fmaf(x[k].y, w[c].y, acc[k][c]);
+        acc[k][c] = fmaf(x[k].z, w[c].z, acc[k][c]);
+        acc[k][c] = fmaf(x[k].w, w[c].w, acc[k][c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < TPW; ++k)
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      const float v = warp_sum(acc[k][c]);
+      if (lane == 0 && c < C) pred[(warp * TPW + k) * C + c] = (t0 + k < T) ? v + bias[c] : 0.f;
+    }
+  __syncthreads();
+  for (int c = warp; c < C; c += 8) {          // this CTA's token sums: one warp per class
+    float s = 0.f;
+    for (int tt = lane; tt < TOK; tt += 32) s += pred[tt * C + c];
+    s = warp_sum(s);
+    if (lane == 0) part[c] = s;
+  }
+  cluster_sync_all();                          // every CTA's `part` is written and visible
+  if (threadIdx.x < C) {
+    const int c = threadIdx.x;
+    float tot = 0.f;
+    for (uint32_t r = 0; r < csize; ++r) tot += ld_shared_cluster_f32(mapa_rank(smem_u32(part + c), r));
+    diff[c] = normalize ? ((grand[(long long)b * C + c] - null_v[c]) - tot) / (float)T : 0.f;
+  }
+  cluster_sync_all();                          // nobody leaves (or reuses smem) while a peer may still read `part`
+  const int n = T - 1;
+  const int tb = (int)rank * TOK;
+  for (int i = threadIdx.x; i < TOK * C; i += blockDim.x) {
+    const int c = i / TOK, tt = i % TOK;       // consecutive threads = consecutive tokens: coalesced phi rows
+    const int t = tb + tt;
+    if (t >= 1 && t < T) phi[((long long)b * C + c) * n + (t - 1)] = pred[tt * C + c] + diff[c];
+  }
+  if (pred_out != nullptr)
+    for (int i = threadIdx.x; i < TOK * C; i += blockDim.x)
+      if (tb + i / C < T) pred_out[((long long)b * T + tb) * C + i] = pred[i];
+}
+
+template <typename TH, int CMAX, int TPW>
+static int launch_head_fwd_cluster(const void* h, int B, int T, int E, int C, const float* W, const float* bias,
+                                   const float* grand, const float* null_v, int normalize, float* phi, float* pred_out,
+                                   cudaStream_t st) {
+  constexpr int TOK = 8 * TPW;
+  const int csize = (T + TOK - 1) / TOK;
+  const size_t smem = ((size_t)2 * MAXC + (size_t)TOK * MAXC + (size_t)C * E) * sizeof(float);
+  if (csize > 8 || smem > 227 * 1024 || B > 65535) return AGB_ERR_UNSUPPORTED;
+  auto kern = explainer_head_fwd_cluster_kernel<TH, CMAX, TPW>;
+  AGB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(csize, B, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  AGB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, static_cast<const TH*>(h), T, E, C, W, bias, grand, null_v, normalize, phi,
+                                    pred_out));
+  return AGB_OK;
+}
+
+template <typename TH>
+static int head_fwd_cluster(const void* h, int B, int T, int E, int C, const float* W, const float* bias, const float* grand,
+                            const float* null_v, int normalize, float* phi, float* pred_out, cudaStream_t st) {
+  if ((reinterpret_cast<uintptr_t>(W) & 15) || (reinterpret_cast<uintptr_t>(h) & 15)) return AGB_ERR_UNSUPPORTED;
+#define HF(CM, TP) launch_head_fwd_cluster<TH, CM, TP>(h, B, T, E, C, W, bias, grand, null_v, normalize, phi, pred_out, st)
+  if (C <= 2) return HF(2, 8);
+  if (C <= 4) return HF(4, 8);
+  if (C <= 10) return HF(10, 8);
+  return HF(16, 4);
+#undef HF
+}
+
 int explainer_head_fwd(const void* h, int h_bf16, int B, int T, int E, int C, const float* W,
                        const float* bias, const float* grand, const float* null_v, int normalize,
                        float* phi, float* pred_out, cudaStream_t st) {
@@ -90,6 +215,11 @@ int explainer_head_fwd(const void* h, int h_bf16, int B, int T, int E, int C, co
   if (B == 0) return AGB_OK;
   AGB_REQUIRE(h && W && bias && phi, "null pointer");
   AGB_REQUIRE(!normalize || (grand && null_v), "normalisation needs grand and null");
+  {
+    const int rc = h_bf16 ? head_fwd_cluster<bf16>(h, B, T, E, C, W, bias, grand, null_v, normalize, phi, pred_out, st)
+                          : head_fwd_cluster<float>(h, B, T, E, C, W, bias, grand, null_v, normalize, phi, pred_out, st);
+    if (rc != AGB_ERR_UNSUPPORTED) return rc;
+  }
   const size_t smem = ((size_t)T * C + C) * sizeof(float);
   AGB_REQUIRE(smem <= 200 * 1024, "T*C too large");
   if (h_bf16) {
@@ -122,6 +252,10 @@ explainer_head_bwd_kernel(const float* __restrict__ dphi, const TH* __restrict__
   float* mean = sm + T * C;     // C
   const int b = blockIdx.x;
   const int n = T - 1;
+  // gridDim.y token chunks per input (more CTAs than inputs: the training batch is 32 inputs on 148 SMs); every chunk
+  // rebuilds the input's small dpred slab, handles its own tokens and adds its dW / db share with atomics
+  const int chunk = (T + gridDim.y - 1) / gridDim.y;
+  const int tc0 = blockIdx.y * chunk, tc1 = min(T, tc0 + chunk);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int c = warp; c < C; c += nw) {
     float s = 0.f;
@@ -140,7 +274,7 @@ explainer_head_bwd_kernel(const float* __restrict__ dphi, const TH* __restrict__
   if (db != nullptr) {
     for (int c = warp; c < C; c += nw) {
       float s = 0.f;
-      for (int t = lane; t < T; t += 32) s += dpred[t * C + c];
+      for (int t = tc0 + lane; t < tc1; t += 32) s += dpred[t * C + c];
       s = warp_sum(s);
       if (lane == 0) atomicAdd(db + c, s);
     }
@@ -155,28 +289,37 @@ explainer_head_bwd_kernel(const float* __restrict__ dphi, const TH* __restrict__
       wreg[c] = (c < C) ? __ldg(reinterpret_cast<const float4*>(W + (long long)c * E + e)) : make_float4(0, 0, 0, 0);
       dwacc[c] = make_float4(0, 0, 0, 0);
     }
-    for (int t = 0; t < T; ++t) {
-      const float4 x = ld4<TH>(hb + (long long)t * E + e);
-      float4 o = make_float4(0, 0, 0, 0);
+    for (int tg = tc0; tg < tc1; tg += 4) {
+      // four rows requested before the first FMA: the HBM latency is paid once per group, not once per token
+      float4 xs[4];
 #pragma unroll
-      for (int c = 0; c < MAXC; ++c) {
-        if (c < C) {
-          const float g = dpred[t * C + c];
-          o.x = fmaf(g, wreg[c].x, o.x); o.y = fmaf(g, wreg[c].y, o.y);
-          o.z = fmaf(g, wreg[c].z, o.z); o.w = fmaf(g, wreg[c].w, o.w);
-          dwacc[c].x = fmaf(g, x.x, dwacc[c].x); dwacc[c].y = fmaf(g, x.y, dwacc[c].y);
-          dwacc[c].z = fmaf(g, x.z, dwacc[c].z); dwacc[c].w = fmaf(g, x.w, dwacc[c].w);
+      for (int k = 0; k < 4; ++k) xs[k] = ld4<TH>(hb + (long long)min(tg + k, tc1 - 1) * E + e);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int t = tg + k;
+        if (t >= tc1) break;
+        const float4 x = xs[k];
+        float4 o = make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+          if (c < C) {
+            const float g = dpred[t * C + c];
+            o.x = fmaf(g, wreg[c].x, o.x); o.y = fmaf(g, wreg[c].y, o.y);
+            o.z = fmaf(g, wreg[c].z, o.z); o.w = fmaf(g, wreg[c].w, o.w);
+            dwacc[c].x = fmaf(g, x.x, dwacc[c].x); dwacc[c].y = fmaf(g, x.y, dwacc[c].y);
+            dwacc[c].z = fmaf(g, x.z, dwacc[c].z); dwacc[c].w = fmaf(g, x.w, dwacc[c].w);
+          }
         }
-      }
-      if (dh != nullptr) {
-        TH* dst = dh + ((long long)b * T + t) * E + e;
-        if (sizeof(TH) == 4) {
-          *reinterpret_cast<float4*>(dst) = o;
-        } else {
-          uint2 pk;
-          pk.x = pack_bf16x2(o.x, o.y);
-          pk.y = pack_bf16x2(o.z, o.w);
-          *reinterpret_cast<uint2*>(dst) = pk;
+        if (dh != nullptr) {
+          TH* dst = dh + ((long long)b * T + t) * E + e;
+          if (sizeof(TH) == 4) {
+            *reinterpret_cast<float4*>(dst) = o;
+          } else {
+            uint2 pk;
+            pk.x = pack_bf16x2(o.x, o.y);
+            pk.y = pack_bf16x2(o.z, o.w);
+            *reinterpret_cast<uint2*>(dst) = pk;
+          }
         }
       }
     }
@@ -200,16 +343,21 @@ int explainer_head_bwd(const float* dphi, const void* h, int h_bf16, int B, int 
   AGB_REQUIRE(dphi && h && W, "null pointer");
   const size_t smem = ((size_t)T * C + C) * sizeof(float);
   AGB_REQUIRE(smem <= 200 * 1024, "T*C too large");
+  AGB_REQUIRE(B <= 65535, "batch too large (chunk it)");
+  // token chunks so that about two waves of CTAs cover the SMs even for a small batch (at least ~16 tokens per chunk)
+  int chunks = (2 * sm_count() + B - 1) / B;
+  chunks = max(1, min(chunks, (T + 15) / 16));
+  const dim3 grid(B, chunks);
   if (h_bf16) {
     if (smem > 48 * 1024)
       AGB_CHECK_CUDA(cudaFuncSetAttribute(explainer_head_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    explainer_head_bwd_kernel<bf16><<<B, 256, smem, st>>>(dphi, static_cast<const bf16*>(h), T, E, C, W, normalize,
-                                                          static_cast<bf16*>(dh), dW, db);
+    explainer_head_bwd_kernel<bf16><<<grid, 256, smem, st>>>(dphi, static_cast<const bf16*>(h), T, E, C, W, normalize,
+                                                             static_cast<bf16*>(dh), dW, db);
   } else {
     if (smem > 48 * 1024)
       AGB_CHECK_CUDA(cudaFuncSetAttribute(explainer_head_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    explainer_head_bwd_kernel<float><<<B, 256, smem, st>>>(dphi, static_cast<const float*>(h), T, E, C, W, normalize,
-                                                           static_cast<float*>(dh), dW, db);
+    explainer_head_bwd_kernel<float><<<grid, 256, smem, st>>>(dphi, static_cast<const float*>(h), T, E, C, W, normalize,
+                                                              static_cast<float*>(dh), dW, db);
   }
   AGB_CHECK_CUDA(cudaGetLastError());
   return AGB_OK;
