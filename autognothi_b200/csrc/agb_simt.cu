@@ -332,16 +332,25 @@ template <int D>
 __global__ void __launch_bounds__(128)
 attention_narrow_kernel(const bf16* __restrict__ qkv, const uint32_t* __restrict__ mask, int words, int T, int H, int heads,
                         int mode, float scale_log2, bf16* __restrict__ ctx, unsigned drop_thr, unsigned long long drop_seed,
-                        float drop_scale) {
+                        float drop_scale, const int* __restrict__ cu) {
+  // cu != nullptr: packed variable-length rows (masked-token dropping): row r owns the tokens [cu[r], cu[r+1]) of
+  // qkv (total, 3H) / ctx (total, H), every packed token is a live key; T is then the capacity (max row length)
   extern __shared__ __align__(16) float sm_n[];
-  float* sK = sm_n;            // T x D
-  float* sV = sK + T * D;      // T x D
-  float* sVm = sV + T * D;     // D: sum of the V rows of the ViT-masked keys
-  int* sIdx = reinterpret_cast<int*>(sVm + D);   // T: indices of the kept keys
-  int* sCnt = sIdx + T;
+  const int Tcap = T;
+  int tok0 = 0;
+  if (cu != nullptr) {
+    tok0 = __ldg(cu + blockIdx.x / heads);
+    T = __ldg(cu + blockIdx.x / heads + 1) - tok0;
+  }
+  float* sK = sm_n;            // Tcap x D
+  float* sV = sK + Tcap * D;   // Tcap x D
+  float* sVm = sV + Tcap * D;  // D: sum of the V rows of the ViT-masked keys
+  int* sIdx = reinterpret_cast<int*>(sVm + D);   // Tcap: indices of the kept keys
+  int* sCnt = sIdx + Tcap;
   uint32_t* sM = reinterpret_cast<uint32_t*>(sCnt + 1);
   const int row = blockIdx.x / heads, head = blockIdx.x % heads;
-  const bf16* base = qkv + (long long)row * T * 3 * H + head * D;
+  const long long first = cu != nullptr ? (long long)tok0 : (long long)row * T;      // first token of this row
+  const bf16* base = qkv + first * 3 * H + head * D;
   constexpr int V8 = D / 8;
   for (int e = threadIdx.x; e < T * V8; e += blockDim.x) {
     const int t = e / V8, v = e % V8;
@@ -356,7 +365,7 @@ attention_narrow_kernel(const bf16* __restrict__ qkv, const uint32_t* __restrict
       sV[t * D + v * 8 + 2 * u + 1] = __uint_as_float(vw[u] & 0xFFFF0000u);
     }
   }
-  for (int e = threadIdx.x; e < words; e += blockDim.x) sM[e] = mask[(long long)row * words + e];
+  for (int e = threadIdx.x; e < words; e += blockDim.x) sM[e] = cu != nullptr ? 0xFFFFFFFFu : mask[(long long)row * words + e];
   for (int e = threadIdx.x; e < D; e += blockDim.x) sVm[e] = 0.f;
   __syncthreads();
   // kept keys compacted (one warp, ballot prefix); ViT-masked keys all carry the logit 0, so their V rows are summed
@@ -477,8 +486,8 @@ attention_narrow_kernel(const bf16* __restrict__ qkv, const uint32_t* __restrict
       }
     }
     const float r0 = l0 > 0.f ? drop_scale / l0 : 0.f, r1 = l1 > 0.f ? drop_scale / l1 : 0.f;
-    bf16* c0 = ctx + ((long long)row * T + i0) * H + head * D;
-    bf16* c1 = ctx + ((long long)row * T + i1) * H + head * D;
+    bf16* c0 = ctx + (first + i0) * H + head * D;
+    bf16* c1 = ctx + (first + i1) * H + head * D;
 #pragma unroll
     for (int v = 0; v < V8; ++v) {
       uint32_t w0[4], w1[4];
@@ -497,16 +506,31 @@ attention_narrow_kernel(const bf16* __restrict__ qkv, const uint32_t* __restrict
 
 template <int D>
 static int launch_attention_narrow(const bf16* qkv, const uint32_t* mask, int words, int rows, int T, int H, int heads,
-                                   int mode, bf16* ctx, cudaStream_t st, unsigned drop_thr, unsigned long long drop_seed) {
+                                   int mode, bf16* ctx, cudaStream_t st, unsigned drop_thr, unsigned long long drop_seed,
+                                   const int* cu = nullptr) {
+  if (cu != nullptr) words = (T + 31) / 32;     // all-ones key bits, built in shared memory
   const size_t smem = ((size_t)2 * T * D + D + T + 1) * sizeof(float) + (size_t)words * sizeof(uint32_t);
   if (smem > 227 * 1024) return AGB_ERR_UNSUPPORTED;
   AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_narrow_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int threads = min(128, (((T + 1) / 2 + 31) / 32) * 32);
   attention_narrow_kernel<D><<<rows * heads, threads, smem, st>>>(qkv, mask, words, T, H, heads, mode,
                                                                    rsqrtf((float)D) * 1.4426950408889634f, ctx, drop_thr,
-                                                                   drop_seed, 65536.0f / (65536.0f - (float)drop_thr));
+                                                                   drop_seed, 65536.0f / (65536.0f - (float)drop_thr), cu);
   AGB_CHECK_CUDA(cudaGetLastError());
   return AGB_OK;
+}
+
+// packed variable-length rows with narrow heads (the LTT ladder after masked-token dropping)
+int attention_narrow_varlen(const bf16* qkv, const int* cu, int rows, int max_len, int H, int heads, bf16* ctx, cudaStream_t st) {
+  const int d = H / heads;
+  AGB_REQUIRE(rows >= 0 && max_len > 0 && heads > 0 && H == heads * d && (d == 8 || d == 16 || d == 32) && (H % 8) == 0,
+              "narrow varlen attention shape (head dim 8 / 16 / 32)");
+  if (rows == 0) return AGB_OK;
+  AGB_REQUIRE(qkv && cu && ctx, "null pointer");
+  AGB_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(ctx) & 15) == 0, "alignment");
+  return d == 8 ? launch_attention_narrow<8>(qkv, nullptr, 0, rows, max_len, H, heads, AGB_MASK_NEGINF, ctx, st, 0, 0, cu)
+       : d == 16 ? launch_attention_narrow<16>(qkv, nullptr, 0, rows, max_len, H, heads, AGB_MASK_NEGINF, ctx, st, 0, 0, cu)
+                 : launch_attention_narrow<32>(qkv, nullptr, 0, rows, max_len, H, heads, AGB_MASK_NEGINF, ctx, st, 0, 0, cu);
 }
 
 int attention_simt(const void* qkv, int io_bf16, const uint32_t* mask, int words, int rows, int T, int H,

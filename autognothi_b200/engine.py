@@ -498,6 +498,34 @@ class SideBranch:
         self.final_ln = (_f32(sd[f"vit.s_attn_layernorm.{b}.weight"]), _f32(sd[f"vit.s_attn_layernorm.{b}.bias"])) if vit else None
 
 
+def run_ltt_bert_packed(bw: BackboneWeights, branches: List[SideBranch], cfg, pol: _Policy, xs: Tensor, masks: Tensor, S: int,
+                        stop: int):
+    """LTT surrogate evaluation for additive (-inf) masks on the kept tokens only (SURVEY.md 8f-3 applied to the ladder): a
+    masked token is never attended to in the backbone NOR in the ladder (both use the same key mask) and both heads read
+    token 0, so neither output can depend on it.  Backbone and ladder run on the packed rows with variable-length
+    attention.  -> (backbone CLS rows (rows, H) fp32, [ladder CLS rows (rows, Hs) fp32 per branch])"""
+    T = n_players_of(cfg) + 1
+    H, heads, eps = cfg.hidden_size, cfg.num_attention_heads, cfg.layer_norm_eps
+    cu, src, total = ops.pack_kept_tokens(masks, T, S)
+    x = embed(bw, cfg, pol, xs, 1).reshape(-1, H).index_select(0, src)       # (total, H) packed residual stream
+    xa = pol.act(x)
+    side: List[Optional[Tensor]] = [None] * len(branches)
+    for i, lw in enumerate(bw.layers):
+        ctx = ops.attention_varlen(pol.linear(xa, lw.wqkv, lw.bqkv), cu, T, heads)
+        x, xa = bert_layer(pol, lw, x, xa, masks, T, heads, eps, ctx=ctx)
+        if i >= stop:
+            continue
+        for k, br in enumerate(branches):
+            w, b = br.maps[i]
+            slw = br.layers[i]
+            s = pol.linear(xa, w, b, act=ops.ACT_GELU, residual=side[k], out_f32=True)
+            sa = pol.act(s)
+            sctx = ops.attention_varlen(pol.linear(sa, slw.wqkv, slw.bqkv), cu, T, heads)
+            side[k], _ = bert_layer(pol, slw, s, sa, masks, T, heads, eps, ctx=sctx)
+    first = cu[:-1].long()                                                   # packed index of every row's CLS token
+    return x.index_select(0, first), [s.index_select(0, first) for s in side]
+
+
 def run_ltt(bw: BackboneWeights, branches: List[SideBranch], cfg, pol: _Policy, xs: Tensor, masks: Tensor, S: int,
             freeze_layer: Optional[int] = None):
     """-> (x, xa of the backbone as run_backbone, [(side state (rows*T, Hs) fp32, activation copy | None) per branch])
@@ -603,9 +631,20 @@ class LttEngine:
             return e, e.clone()
         per = max(1, max_rows // S)
         srg, cls = [], []
+        cfg = self.cfg
+        L = len(self.bw.layers)
+        stop = L if self.freeze_layer is None else max(1, min(L, int(self.freeze_layer)))
+        hs = cfg.s_attn_hidden_size // cfg.num_attention_heads
+        packed = (not self.bw.vit and DROP_MASKED_TOKENS and self.pol.bf16 and n_players_of(cfg) + 1 <= 512
+                  and cfg.hidden_size == cfg.num_attention_heads * 64 and hs in (8, 16, 32) and cfg.s_attn_hidden_size % 8 == 0)
         for b0 in range(0, B, per):
             b1 = min(B, b0 + per)
             rows = (b1 - b0) * S
+            if packed:
+                x, sides_cls = run_ltt_bert_packed(self.bw, self.branches[:1], cfg, self.pol, xs[b0:b1], masks[b0 * S:b1 * S], S, stop)
+                cls.append(self._main_probs(x, rows))
+                srg.append(self._side_probs(sides_cls[0], rows))
+                continue
             x, _, sides = run_ltt(self.bw, self.branches[:1], self.cfg, self.pol, xs[b0:b1], masks[b0 * S:b1 * S], S, self.freeze_layer)
             cls.append(self._main_probs(x, rows))
             srg.append(self._side_probs(sides[0][0], rows))

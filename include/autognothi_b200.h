@@ -118,7 +118,8 @@ int agb_mask_counts(const uint32_t* packed, int rows, int words, int T, int* cou
 int agb_packed_token_index(const uint32_t* packed, int rows, int words, int T, int S, const int* cu, int64_t* src,
                            void* stream);
 /* Attention over packed variable-length rows: qkv (total_tokens, 3H) bf16, row r = tokens [cu[r], cu[r+1]) (every packed
- * token is a live key), max_len >= every row length (<= 512); ctx (total_tokens, H).  tcgen05 kernel, head dim 64. */
+ * token is a live key), max_len >= every row length (<= 512); ctx (total_tokens, H).  tcgen05 kernel for head dim 64;
+ * head dims 8 / 16 / 32 (the LTT side ladder, reference models/ltt_bert.py:437-451) run the narrow-head kernel. */
 int agb_attention_bf16_varlen(const void* qkv, const int* cu, int rows, int max_len, int total_tokens, int H, int heads,
                               void* ctx, void* stream);
 

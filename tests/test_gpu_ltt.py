@@ -212,3 +212,30 @@ def test_narrow_head_attention_matches_the_fp32_kernel(agb, T, heads, d, mode):
     got = agb.masked_attention(qkv16, masks, T, heads, mode)
     assert got.dtype == torch.bfloat16
     np.testing.assert_allclose(_np(got), _np(ref), rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("name", ["ltt_bert_mini", "ltt_bert_base_128"])
+def test_ltt_bert_masked_token_dropping_is_exact(agb, golden_dir, name):
+    """Additive masks: a masked token is attended to neither in the backbone nor in the ladder and both heads read token
+    0, so carrying only the kept tokens (packed rows, variable-length attention incl. the narrow-head kernel) gives the
+    same probabilities as the full-length path."""
+    from autognothi_b200 import engine
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    B, S, n = (int(v) for v in g["meta"])
+    rec, cfgd, cfg, (srg, exp, fin) = _models(name, "bf16")
+    xs = torch.from_numpy(synth.inputs(cfgd, B, seed=0)).to(DEV)
+    masks = torch.from_numpy(g["masks"].astype(np.int64)).to(DEV).reshape(B, S, n)
+    edge = masks.clone()
+    edge[0, 0, :] = 0            # only CLS kept
+    edge[0, 1, :] = 1            # everything kept
+    try:
+        with torch.no_grad():
+            engine.DROP_MASKED_TOKENS = True
+            a_side, a_main = rec.fw_surrogate(srg, xs, edge)
+            engine.DROP_MASKED_TOKENS = False
+            b_side, b_main = rec.fw_surrogate(srg, xs, edge)
+    finally:
+        engine.DROP_MASKED_TOKENS = True
+    np.testing.assert_allclose(_np(a_side), _np(b_side), atol=3e-3)
+    np.testing.assert_allclose(_np(a_main), _np(b_main), atol=3e-3)
+    np.testing.assert_allclose(_np(a_side).sum(1), 1.0, atol=1e-5)
