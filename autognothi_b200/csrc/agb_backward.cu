@@ -970,17 +970,9 @@ int attention_bwd(const void* qkv, const void* dctx, int io_bf16, const uint32_t
   if (T > 256) {
     // two-kernel form (operands staged in bf16, fp32 math): fp32 I/O is accepted but is not the exact mode here
     AGB_REQUIRE(rows * heads <= 65535, "grid limits (chunk the rows)");
-    static float* stat = nullptr;           // grow-only scratch for the row statistics (single-stream use)
-    static size_t stat_elems = 0;
-    const size_t need = (size_t)rows * heads * 2 * T;
-    if (need > stat_elems) {
-      if (stat != nullptr) {
-        AGB_CHECK_CUDA(cudaStreamSynchronize(st));
-        AGB_CHECK_CUDA(cudaFree(stat));
-      }
-      AGB_CHECK_CUDA(cudaMalloc(&stat, need * sizeof(float)));
-      stat_elems = need;
-    }
+    // row statistics (L, D) between the two kernels: stream-ordered scratch, released after the second kernel
+    float* stat = nullptr;
+    AGB_CHECK_CUDA(cudaMallocAsync(&stat, (size_t)rows * heads * 2 * T * sizeof(float), st));
     const int nwl = 8;
     const size_t smem_l = (size_t)2 * T * AB_LD * 2 + (size_t)2 * ABL_BLK * AB_LD * 2 + (size_t)2 * T * 4 +
                           (size_t)nwl * 2 * T * 4;
@@ -997,7 +989,9 @@ int attention_bwd(const void* qkv, const void* dctx, int io_bf16, const uint32_t
     if (io_bf16) ABL_LAUNCH(bf16);
     else ABL_LAUNCH(float);
 #undef ABL_LAUNCH
-    AGB_CHECK_CUDA(cudaGetLastError());
+    const cudaError_t launch_err = cudaGetLastError();
+    AGB_CHECK_CUDA(cudaFreeAsync(stat, st));
+    AGB_CHECK_CUDA(launch_err);
     return AGB_OK;
   }
   const int nw = 8;

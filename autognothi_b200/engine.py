@@ -442,6 +442,31 @@ class ExplainerEngine:
         return ops.explainer_head_fwd(h, B, T, self.w_c, self.b_c, grand, null, bool(cfg.explainer_normalize), want_pred)
 
 
+class DuoExplainerEngine(ExplainerEngine):
+    """Duo explainer (reference models/duo_vanilla_vit.py:62-123, duo_vanilla_bert.py:72-148): the explainer's own backbone
+    also feeds a classification head.  -> (phi, class output): ViT softmax probabilities, BERT raw logits."""
+
+    def __init__(self, sd: State, cfg, precision: str):
+        super().__init__(sd, cfg, precision)
+        self.w_cls, self.b_cls = _f32(sd["classifier.weight"]), _f32(sd["classifier.bias"])
+        if not self.bw.vit:
+            self.pool = (_f32(sd["bert_pooler.dense.weight"]), _f32(sd["bert_pooler.dense.bias"]))
+
+    @torch.no_grad()
+    def duo(self, xs: Tensor, masks: Tensor, grand: Optional[Tensor], null: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+        cfg = self.cfg
+        B = xs.shape[0]
+        if B == 0:
+            return _empty_outputs(cfg, xs.device)[::-1]
+        x, xa = run_backbone(self.bw, cfg, self.pol, xs, masks, 1)
+        x3 = x.reshape(B, -1, cfg.hidden_size)
+        if self.bw.vit:
+            cls = ops.cls_head(x3, 0, self.w_cls, self.b_cls, ln=(self.bw.final_ln[0], self.bw.final_ln[1], cfg.layer_norm_eps))
+        else:
+            cls = ops.cls_head(x3, 1, self.w_cls, self.b_cls, pool=self.pool, want_logits=True)[1]
+        return self.tail(x, xa, masks, B, grand, null), cls
+
+
 class FroyoFinalEngine(ExplainerEngine):
     """Froyo bundle (reference models/froyo_vit.py:100-171, models/froyo_bert.py:103-204): ONE frozen backbone pass feeds
     the classifier head, the surrogate head (srg_*) and the explainer tail."""

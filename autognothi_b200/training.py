@@ -296,6 +296,9 @@ def forward_train(sd: Dict[str, Tensor], cfg, precision: str, xs: Tensor, masks:
     if vit:
         tp.x_pre_final = x if train_backbone else None
         _, x = ops.layernorm(x, bw.final_ln[0], bw.final_ln[1], eps, want_bf16=False, want_f32=True)
+    # CLS row of the backbone output (ViT: after vit.layernorm; BERT: last block's output): the Duo variants hang a
+    # classification head on it (reference models/duo_vanilla_vit.py:104-109, duo_vanilla_bert.py:120-125)
+    tp.x_cls = x.reshape(B, T, H)[:, 0, :].clone()
     for i in range(cfg.explainer_attn_num_layers):
         prefix = f"explainer_attn.{i}"
         lw = LayerWeights(sd, prefix, pol, vit)
@@ -328,7 +331,8 @@ def forward_train(sd: Dict[str, Tensor], cfg, precision: str, xs: Tensor, masks:
     return phi, tp
 
 
-def backward_train(tp: _Tape, dphi: Tensor) -> Grads:
+def backward_train(tp: _Tape, dphi: Tensor, dx_cls: Optional[Tensor] = None) -> Grads:
+    """dx_cls (B, H): gradient w.r.t. tape.x_cls coming from a head outside this node (Duo variants), or None."""
     pol, cfg, bw = tp.pol, tp.cfg, tp.bw
     vit = bw.vit
     T, B = tp.T, tp.B
@@ -351,6 +355,9 @@ def backward_train(tp: _Tape, dphi: Tensor) -> Grads:
     n_backbone = len(bw.layers) if tp.train_backbone else 0
     for idx in range(len(tp.layers) - 1, -1, -1):
         prefix, lw, t = tp.layers[idx]
+        if tp.train_backbone and idx == n_backbone - 1 and dx_cls is not None:
+            dx = dx.clone()
+            dx.view(B, T, H)[:, 0, :] += dx_cls          # the classification head's share, at the CLS rows
         if vit and tp.train_backbone and idx == n_backbone - 1:
             # crossing from explainer_attn back into the backbone: adjoint of vit.layernorm
             dx = _ln_bwd(grads, "vit.layernorm", tp.x_pre_final, dx, bw.final_ln[0], eps, None)
@@ -373,12 +380,17 @@ class _ExplainerTrainFn(torch.autograd.Function):
             phi, tape = forward_train(sd, cfg, precision, xs, masks, grand, null, train_backbone, dropout)
         ctx.tape, ctx.names = tape, names
         ctx.shapes = [p.shape for p in params]
-        return phi
+        ctx.set_materialize_grads(False)
+        return phi, tape.x_cls
 
     @staticmethod
-    def backward(ctx, dphi):
+    def backward(ctx, dphi, dx_cls):
         with torch.no_grad():
-            grads = backward_train(ctx.tape, dphi.contiguous().float())
+            if dphi is None:      # only the class output was used downstream
+                dphi = torch.zeros((ctx.tape.B, ctx.tape.cfg.num_labels, ctx.tape.T - 1), dtype=torch.float32,
+                                   device=ctx.tape.hb.device)
+            grads = backward_train(ctx.tape, dphi.contiguous().float(),
+                                   dx_cls.contiguous().float() if dx_cls is not None else None)
         ctx.tape = None
         out = []
         for n, shp in zip(ctx.names, ctx.shapes):
@@ -404,7 +416,35 @@ def explainer_forward_train(model, xs: Tensor, words: Tensor, grand: Optional[Te
         raise RuntimeError("autognothi_b200 models run on CUDA only (no CPU fallback)")
     g = grand.detach() if grand is not None else None
     nl = null.detach() if null is not None else None
-    return _ExplainerTrainFn.apply(xs, words, g, nl, model.config, model.agb_precision, _wants_dropout(model), names, *params)
+    phi, _x_cls = _ExplainerTrainFn.apply(xs, words, g, nl, model.config, model.agb_precision, _wants_dropout(model), names,
+                                          *params)
+    return phi
+
+
+def duo_explainer_forward_train(model, xs: Tensor, words: Tensor, grand: Optional[Tensor], null: Optional[Tensor]
+                                ) -> Tuple[Tensor, Tensor]:
+    """Differentiable forward of the Duo explainers (reference models/duo_vanilla_vit.py:96-123, duo_vanilla_bert.py:110-148;
+    trained with cross_entropy(class output) + Shapley loss, scripts/train_duo_explainer.py:180-196).
+    -> (phi, class output): ViT softmax probabilities, BERT raw logits — as the reference returns them.  The backbone +
+    explainer tail is one autograd node with two outputs (phi and the CLS row of the backbone output); the small
+    classification head stays in torch autograd and its gradient re-enters the node at the CLS rows."""
+    named_all = dict(model.named_parameters())
+    head = ("classifier.", "bert_pooler.")
+    named = [(n, p) for n, p in named_all.items() if not n.startswith(head)]
+    names = [n for n, _ in named]
+    if named[0][1].device.type != "cuda":
+        raise RuntimeError("autognothi_b200 models run on CUDA only (no CPU fallback)")
+    cfg = model.config
+    g = grand.detach() if grand is not None else None
+    nl = null.detach() if null is not None else None
+    dropout = _wants_dropout(model)
+    phi, x_cls = _ExplainerTrainFn.apply(xs, words, g, nl, cfg, model.agb_precision, dropout, names, *[p for _, p in named])
+    if hasattr(cfg, "img_px_size"):
+        logits = torch.nn.functional.linear(x_cls, named_all["classifier.weight"], named_all["classifier.bias"])
+        return phi, torch.softmax(logits, dim=-1)
+    h = torch.tanh(torch.nn.functional.linear(x_cls, named_all["bert_pooler.dense.weight"], named_all["bert_pooler.dense.bias"]))
+    h = torch.nn.functional.dropout(h, float(cfg.hidden_dropout_prob), training=dropout)
+    return phi, torch.nn.functional.linear(h, named_all["classifier.weight"], named_all["classifier.bias"])
 
 
 # ------------------------------------------------------------------------------------------------

@@ -380,7 +380,68 @@ def gen_ltt():
         json.dump(keys, f, indent=0, sort_keys=True)
 
 
+def gen_duo():
+    """Duo variants (reference models/duo_vanilla_{vit,bert}.py): explainer outputs (attributions + class output), the bundle,
+    and the dual-objective training step of scripts/train_duo_explainer.py:180-196 (cross_entropy(class output, labels) +
+    Shapley loss; eval() mode: dropout = identity) with gradients from the reference's autograd."""
+    ref_dvit = __import__(f"{REF_NAME}.models.duo_vanilla_vit", fromlist=["x"])
+    ref_dbert = __import__(f"{REF_NAME}.models.duo_vanilla_bert", fromlist=["x"])
+    keys = {}
+    for name, B, S in [("vit_mini", 2, 4), ("bert_mini", 3, 4)]:
+        cfg = ocfg.get_config(name)
+        vit = ocfg.is_vit(cfg)
+        n = ocfg.n_players(cfg)
+        mod = ref_dvit if vit else ref_dbert
+        pre = "DuoVanillaViT" if vit else "DuoVanillaBert"
+        dcfg = getattr(mod, pre + "Config")(**cfg)
+        exp, fin = getattr(mod, pre + "Explainer")(dcfg), getattr(mod, pre + "Final")(dcfg)
+        keys[name] = {"explainer": {k: list(v.shape) for k, v in exp.state_dict().items()},
+                      "final": {k: list(v.shape) for k, v in fin.state_dict().items()}}
+        for i, m in enumerate((exp, fin)):
+            m.load_state_dict(to_torch_state(synth.state_like({k: v.shape for k, v in m.state_dict().items()}, seed=50 + i)), strict=True)
+            m.eval()
+        g = np.load(os.path.join(HERE, f"model_{name}.npz"))
+        masks = torch.from_numpy(g["masks"].astype(np.int64))
+        v_s, grand, null = (torch.from_numpy(g[k]) for k in ("v_s", "grand", "null"))
+        xs = torch.from_numpy(synth.inputs(cfg, B, seed=0))
+        cls_col = lambda m: torch.cat([torch.ones((m.shape[0], 1), dtype=torch.long), m], dim=1)   # noqa: E731
+        ones = torch.ones((B, n), dtype=torch.long)
+        tt = (lambda x: ()) if vit else (lambda x: (torch.zeros_like(x),))
+        labels = torch.from_numpy(synth.randint("duo.labels", (B,), 0, cfg["num_labels"], 3))
+
+        def run(m_):
+            o = exp(xs, cls_col(m_), *tt(xs), grand, null)
+            return (o[0], o[1]) if vit else (o[1], o[0])          # -> (phi, class output)
+
+        phi, cls = run(ones)
+        phi_m, cls_m = run(masks.reshape(B, S, n)[:, 0, :])
+        f_cls, f_phi = fin(xs, cls_col(ones), *tt(xs))
+        with torch.enable_grad():
+            for p_ in exp.parameters():
+                p_.requires_grad_(True)
+            phi_g, cls_g = run(ones)
+            loss_cls = torch.nn.functional.cross_entropy(cls_g, labels)
+            loss_shap = ref_shapley.loss_shapley_new(B, S, n, masks.reshape(B, S, n), null, v_s, grand, phi_g)
+            (loss_cls + loss_shap).backward()
+        out = dict(phi=phi.numpy(), cls=cls.numpy(), phi_masked=phi_m.numpy(), cls_masked=cls_m.numpy(), f_cls=f_cls.numpy(),
+                   f_phi=f_phi.numpy(), labels=labels.numpy(), loss_cls=loss_cls.detach().numpy(),
+                   loss_shap=loss_shap.detach().numpy(), meta=np.array([B, S, n], dtype=np.int64))
+        names, vals = [], []
+        for k, p_ in exp.named_parameters():
+            names.append(k); vals.append(float(p_.grad.norm()) if p_.grad is not None else 0.0)
+            if p_.grad is not None and (p_.grad.numel() <= 1024 or k.startswith("classifier.") or "layers.0.attention.self.query.weight" in k):
+                out["grad::" + k] = p_.grad.numpy()
+        out["norm_names"], out["norm_values"] = np.array(names), np.array(vals, dtype=np.float64)
+        np.savez_compressed(os.path.join(HERE, f"duo_{name}.npz"), **out)
+        print(f"duo_{name}.npz phi{tuple(phi.shape)} cls{tuple(cls.shape)} loss_cls={float(loss_cls):.5f} loss_shap={float(loss_shap):.5f}")
+    with open(os.path.join(HERE, "duo_keys.json"), "w") as f:
+        json.dump(keys, f, indent=0, sort_keys=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "duo":
+        gen_duo()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ltt":
         gen_ltt()
         sys.exit(0)
@@ -403,3 +464,4 @@ if __name__ == "__main__":
     gen_surrogate_train_grads()
     gen_froyo()
     gen_ltt()
+    gen_duo()
