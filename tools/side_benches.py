@@ -129,13 +129,14 @@ def ltt():
     from autognothi_b200.recipes.ltt_vit import ltt_vit_recipe
     dev = torch.device("cuda:0")
     vit_cfg = {k: v for k, v in bench.VIT_BASE.items() if k not in ("explainer_attn_num_layers", "explainer_head_hidden_size")}
-    vit_cfg.update(explainer_s_attn_num_layers=1, explainer_s_head_hidden_size=3072, s_attn_hidden_size=192, s_attn_intermediate_size=768)
+    # ladder ratios of the reference's only LTT configuration (hidden / 8, MLP 4 x): the same as bench.py's `ltt` leg
+    vit_cfg.update(explainer_s_attn_num_layers=1, explainer_s_head_hidden_size=3072, s_attn_hidden_size=96, s_attn_intermediate_size=384)
     # reference experiments/bert_base_tayp_ltt/.hparams.json:14-32 with max_position_embeddings = 128
     bert_cfg = dict(attention_probs_dropout_prob=0.1, explainer_s_attn_num_layers=1, explainer_s_head_hidden_size=3072,
                     explainer_normalize=True, hidden_dropout_prob=0.1, hidden_size=768, intermediate_size=3072, layer_norm_eps=1e-12,
                     max_position_embeddings=128, num_attention_heads=12, num_hidden_layers=12, num_labels=2, pad_token_id=0,
                     s_attn_hidden_size=96, s_attn_intermediate_size=384, type_vocab_size=2, vocab_size=30522)
-    for tag, rec, cfgd in (("ViT-B/16 + ladder 192", ltt_vit_recipe(), vit_cfg), ("BERT-base T=128 + ladder 96", ltt_bert_recipe(), bert_cfg)):
+    for tag, rec, cfgd in (("ViT-B/16 + ladder 96", ltt_vit_recipe(), vit_cfg), ("BERT-base T=128 + ladder 96", ltt_bert_recipe(), bert_cfg)):
         cfg = rec.t_config(**cfgd)
         n = rec.n_players(cfg)
         torch.manual_seed(3407)
