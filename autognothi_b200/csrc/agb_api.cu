@@ -231,17 +231,18 @@ int agb_attention_dropout_mask(void* keep, int rows, int heads, int T, int thr16
                                void* stream) {
   return agb::attention_dropout_mask(static_cast<unsigned char*>(keep), rows, heads, T, (unsigned)thr16, seed, ST(stream));
 }
-int agb_masked_attention_dropout_fwd(const void* qkv, const uint32_t* mask, int words, int rows, int T, int H, int heads,
-                                     int mode, void* ctx, int thr16, uint64_t seed, void* stream) {
-  if (H == heads * 64)
+int agb_masked_attention_dropout_fwd(const void* qkv, int io_is_bf16, const uint32_t* mask, int words, int rows, int T, int H,
+                                     int heads, int mode, void* ctx, int thr16, uint64_t seed, void* stream) {
+  if (io_is_bf16 && H == heads * 64)
     return agb::attention_pipe_dropout(static_cast<const bf16*>(qkv), mask, words, rows, T, H, heads, mode,
                                        static_cast<bf16*>(ctx), (unsigned)thr16, seed, ST(stream));
-  return agb::attention_simt(qkv, 1, mask, words, rows, T, H, heads, mode, ctx, ST(stream), (unsigned)thr16, seed);
+  return agb::attention_simt(qkv, io_is_bf16, mask, words, rows, T, H, heads, mode, ctx, ST(stream), (unsigned)thr16, seed);
 }
-int agb_masked_attention_dropout_bwd(const void* qkv, const void* dctx, const uint32_t* mask, int words, int rows, int T,
-                                     int H, int heads, int mode, void* dqkv, int thr16, uint64_t seed,
+int agb_masked_attention_dropout_bwd(const void* qkv, const void* dctx, int io_is_bf16, const uint32_t* mask, int words,
+                                     int rows, int T, int H, int heads, int mode, void* dqkv, int thr16, uint64_t seed,
                                      void* stream) {
-  return agb::attention_bwd(qkv, dctx, 1, mask, words, rows, T, H, heads, mode, dqkv, ST(stream), (unsigned)thr16, seed);
+  return agb::attention_bwd(qkv, dctx, io_is_bf16, mask, words, rows, T, H, heads, mode, dqkv, ST(stream), (unsigned)thr16,
+                            seed);
 }
 int agb_vit_embed_bwd(const float* dx, int B, int T, int H, float* dpos, float* dcls, void* dpatch,
                       int dpatch_is_bf16, void* stream) {

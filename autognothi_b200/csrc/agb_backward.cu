@@ -624,7 +624,8 @@ attention_bwd_long_b_kernel(const TIO* __restrict__ qkv, const TIO* __restrict__
 __global__ void __launch_bounds__(256)
 attention_bwd_f32_kernel(const float* __restrict__ qkv, const float* __restrict__ dctx,
                          const uint32_t* __restrict__ mask, int words, int T, int H, int heads, int mode,
-                         float* __restrict__ dqkv) {
+                         float* __restrict__ dqkv,
+                         unsigned drop_thr, unsigned long long drop_seed, float drop_scale) {
   extern __shared__ uint8_t smraw[];
   constexpr int LD = AB_D + 1;
   float* sQ = reinterpret_cast<float*>(smraw);
@@ -662,6 +663,7 @@ attention_bwd_f32_kernel(const float* __restrict__ qkv, const float* __restrict_
       const uint32_t keep = (mrow[j >> 5] >> (j & 31)) & 1u;
       float x = a * scale;
       if (!keep) x = (mode == AGB_MASK_MUL0) ? 0.f : -INFINITY;
+      if (drop_thr) b = agb_attn_keep(drop_seed, blockIdx.x, i, j, drop_thr) ? b * drop_scale : 0.f;   // dP o M'
       s0[j] = x; s1[j] = b;
       mx = fmaxf(mx, x);
     }
@@ -707,8 +709,10 @@ attention_bwd_f32_kernel(const float* __restrict__ qkv, const float* __restrict_
       float x = a * scale;
       if (!keep) x = (mode == AGB_MASK_MUL0) ? 0.f : -INFINITY;
       const float pij = expf(x - lse[i]);
-      s0[i] = pij;
-      s1[i] = keep ? pij * (b - Dv[i]) * scale : 0.f;
+      float mk = 1.f;
+      if (drop_thr) mk = agb_attn_keep(drop_seed, blockIdx.x, i, j, drop_thr) ? drop_scale : 0.f;
+      s0[i] = pij * mk;
+      s1[i] = keep ? pij * (b * mk - Dv[i]) * scale : 0.f;
     }
     __syncwarp();
     float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
@@ -963,8 +967,9 @@ int attention_bwd(const void* qkv, const void* dctx, int io_bf16, const uint32_t
                                      heads, mode, static_cast<bf16*>(dqkv), st, drop_thr, drop_seed);
     if (rc2 != AGB_ERR_UNSUPPORTED) return rc2;
   }
-  if (drop_thr > 0) {
-    set_last_error("attention dropout adjoint: bf16 with head dim 64 and T <= 256, or head dims 8/16/32 (T = %d)", T);
+  if (drop_thr > 0 && (io_bf16 || T > 256)) {
+    set_last_error("attention dropout adjoint: T <= 256 (tcgen05 kernel in bf16, CUDA-core kernel in fp32 up to T = 200), "
+                   "or head dims 8/16/32 (T = %d)", T);
     return AGB_ERR_UNSUPPORTED;
   }
   if (T > 256) {
@@ -1005,7 +1010,8 @@ int attention_bwd(const void* qkv, const void* dctx, int io_bf16, const uint32_t
     AGB_REQUIRE(smem <= 227 * 1024, "T too large for the fp32 attention backward (<= 200)");
     AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attention_bwd_f32_kernel<<<rows * heads, nw * 32, smem, st>>>(static_cast<const float*>(qkv), static_cast<const float*>(dctx),
-                                                                  mask, words, T, H, heads, mode, static_cast<float*>(dqkv));
+                                                                  mask, words, T, H, heads, mode, static_cast<float*>(dqkv),
+                                                                  drop_thr, drop_seed, 65536.0f / (65536.0f - (float)drop_thr));
   }
   AGB_CHECK_CUDA(cudaGetLastError());
   return AGB_OK;

@@ -99,7 +99,8 @@ __device__ __forceinline__ void stf<bf16>(bf16* p, float v) { *p = __float2bfloa
 
 template <typename TIO, int MAXD32>
 __global__ void attention_simt_kernel(const TIO* __restrict__ qkv, const uint32_t* __restrict__ mask,
-                                      int words, int T, int H, int heads, int mode, TIO* __restrict__ ctx) {
+                                      int words, int T, int H, int heads, int mode, TIO* __restrict__ ctx,
+                                      unsigned drop_thr, unsigned long long drop_seed, float drop_scale) {
   extern __shared__ float sc_all[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int d = H / heads;
@@ -143,7 +144,9 @@ __global__ void attention_simt_kernel(const TIO* __restrict__ qkv, const uint32_
 #pragma unroll
   for (int i = 0; i < MAXD32; ++i) o[i] = 0.f;
   for (int j = 0; j < T; ++j) {
-    const float pj = sc[j] / z;
+    float pj = sc[j] / z;
+    if (drop_thr)      // training mode: dropout on the probabilities (the row sum above keeps all of them)
+      pj = agb_attn_keep(drop_seed, (uint32_t)(row * heads + head), (uint32_t)qi, (uint32_t)j, drop_thr) ? pj * drop_scale : 0.f;
     const TIO* vp = qkv + base + (long long)j * 3 * H + 2 * H + head * d;
 #pragma unroll
     for (int i = 0; i < MAXD32; ++i)
@@ -551,20 +554,18 @@ int attention_simt(const void* qkv, int io_bf16, const uint32_t* mask, int words
                            : launch_attention_narrow<32>(q16, mask, words, rows, T, H, heads, mode, c16, st, drop_thr, drop_seed);
     if (rc != AGB_ERR_UNSUPPORTED) return rc;
   }
-  if (drop_thr > 0) {
-    set_last_error("attention dropout: bf16 with head dim 64 (T <= 256) or head dims 8/16/32 only");
-    return AGB_ERR_UNSUPPORTED;
-  }
   AGB_REQUIRE(rows <= 65535 && heads <= 65535, "grid limits (chunk the rows)");
   const int nw = 4;
   dim3 grid((T + nw - 1) / nw, heads, rows);
   const size_t smem = (size_t)nw * T * sizeof(float);
   if (io_bf16)
     attention_simt_kernel<bf16, 4><<<grid, nw * 32, smem, st>>>(static_cast<const bf16*>(qkv), mask, words, T, H,
-                                                                heads, mode, static_cast<bf16*>(ctx));
+                                                                heads, mode, static_cast<bf16*>(ctx), drop_thr, drop_seed,
+                                                                65536.0f / (65536.0f - (float)drop_thr));
   else
     attention_simt_kernel<float, 4><<<grid, nw * 32, smem, st>>>(static_cast<const float*>(qkv), mask, words, T, H,
-                                                                 heads, mode, static_cast<float*>(ctx));
+                                                                 heads, mode, static_cast<float*>(ctx), drop_thr, drop_seed,
+                                                                 65536.0f / (65536.0f - (float)drop_thr));
   AGB_CHECK_CUDA(cudaGetLastError());
   return AGB_OK;
 }

@@ -489,26 +489,26 @@ def dropout(y: Tensor, thr16: int, seed: int, tag: int, *, residual: Optional[Te
 
 
 def masked_attention_dropout(qkv: Tensor, packed_mask: Tensor, T: int, heads: int, mode: int, thr16: int, seed: int) -> Tensor:
-    """masked_attention with dropout on the probabilities (bf16; head dim 64 with T <= 256, or head dims 8/16/32)."""
-    assert qkv.dtype == torch.bfloat16, "attention dropout runs in bf16 mode only (set module.agb_dropout = False for fp32)"
+    """masked_attention with dropout on the probabilities (bf16: head dim 64 with T <= 256 on the tcgen05 kernels, or head
+    dims 8/16/32; fp32: CUDA-core kernels)."""
     qkv = _c(qkv)
     rows = packed_mask.shape[0]
     H = qkv.shape[1] // 3
-    ctx = torch.empty((rows * T, H), dtype=torch.bfloat16, device=qkv.device)
-    nat.call("agb_masked_attention_dropout_fwd", nat.ptr(qkv), nat.ptr(packed_mask), packed_mask.shape[1], rows, T, H, heads,
-             mode, nat.ptr(ctx), thr16, seed & 0xFFFFFFFFFFFFFFFF, nat.stream())
+    ctx = torch.empty((rows * T, H), dtype=qkv.dtype, device=qkv.device)
+    nat.call("agb_masked_attention_dropout_fwd", nat.ptr(qkv), _is_bf16(qkv), nat.ptr(packed_mask), packed_mask.shape[1], rows,
+             T, H, heads, mode, nat.ptr(ctx), thr16, seed & 0xFFFFFFFFFFFFFFFF, nat.stream())
     return ctx
 
 
 def masked_attention_dropout_bwd(qkv: Tensor, dctx: Tensor, packed_mask: Tensor, T: int, heads: int, mode: int, thr16: int,
                                  seed: int) -> Tensor:
     qkv, dctx = _c(qkv), _c(dctx)
-    assert qkv.dtype == torch.bfloat16 and dctx.dtype == torch.bfloat16
+    assert qkv.dtype == dctx.dtype
     rows = qkv.shape[0] // T
     H = qkv.shape[1] // 3
     dqkv = torch.empty_like(qkv)
-    nat.call("agb_masked_attention_dropout_bwd", nat.ptr(qkv), nat.ptr(dctx), nat.ptr(packed_mask), packed_mask.shape[1], rows,
-             T, H, heads, mode, nat.ptr(dqkv), thr16, seed & 0xFFFFFFFFFFFFFFFF, nat.stream())
+    nat.call("agb_masked_attention_dropout_bwd", nat.ptr(qkv), nat.ptr(dctx), _is_bf16(qkv), nat.ptr(packed_mask),
+             packed_mask.shape[1], rows, T, H, heads, mode, nat.ptr(dqkv), thr16, seed & 0xFFFFFFFFFFFFFFFF, nat.stream())
     return dqkv
 
 

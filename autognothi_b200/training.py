@@ -9,7 +9,7 @@ reference's loop (`phi = fw_explainer(...); loss = loss_shapley_new(...); loss.b
 optimizer.step()`) runs unchanged.
 
 Dropout: the reference keeps hidden / attention-probability dropout (p = 0.1 in the checked-in configs) active while
-training.  In train() mode this path applies both (bf16 mode; `_Drop`): elementwise sites through `agb_dropout`, the
+training.  In train() mode this path applies both (`_Drop`; bf16 on the tcgen05 kernels, fp32 on the CUDA-core ones): elementwise sites through `agb_dropout`, the
 attention probabilities inside the tcgen05 attention forward and adjoint, masks regenerated from a counter hash in the
 backward pass.  `module.agb_dropout = False` gives the deterministic p = 0 path that the parity tests compare with the
 reference run in eval() mode (where its dropout is the identity); the random streams differ from torch's, so dropout

@@ -237,12 +237,13 @@ int agb_dropout(const void* y, int y_is_bf16, const float* residual, void* out, 
                 int thr16, uint64_t seed, int tag, void* stream);
 /* Key-masked attention with dropout on the probabilities (training mode of reference models/vanilla_vit.py:454-459,
  * models/vanilla_bert.py:527-532): ctx = (softmax(scores) o M / (1 - p)) V, M from the same counter hash keyed by
- * (seed, row * heads + head, query, key).  bf16; head dim 64 with T <= 256 (tcgen05 kernels) or head dims 8/16/32.
+ * (seed, row * heads + head, query, key).  bf16: head dim 64 with T <= 256 (tcgen05 kernels) or head dims 8/16/32;
+ * fp32 (the exact mode): CUDA-core kernels, adjoint up to T = 200 at head dim 64.
  * _bwd is its adjoint (regenerates M).  agb_attention_dropout_mask writes M as (rows, heads, T, T) bytes (tests). */
-int agb_masked_attention_dropout_fwd(const void* qkv, const uint32_t* mask, int words, int rows, int T, int H, int heads,
-                                     int mode, void* ctx, int thr16, uint64_t seed, void* stream);
-int agb_masked_attention_dropout_bwd(const void* qkv, const void* dctx, const uint32_t* mask, int words, int rows, int T,
-                                     int H, int heads, int mode, void* dqkv, int thr16, uint64_t seed,
+int agb_masked_attention_dropout_fwd(const void* qkv, int io_is_bf16, const uint32_t* mask, int words, int rows, int T, int H,
+                                     int heads, int mode, void* ctx, int thr16, uint64_t seed, void* stream);
+int agb_masked_attention_dropout_bwd(const void* qkv, const void* dctx, int io_is_bf16, const uint32_t* mask, int words,
+                                     int rows, int T, int H, int heads, int mode, void* dqkv, int thr16, uint64_t seed,
                                      void* stream);
 int agb_attention_dropout_mask(void* keep, int rows, int heads, int T, int thr16, uint64_t seed,
                                void* stream);

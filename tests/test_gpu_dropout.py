@@ -92,6 +92,28 @@ def test_attention_dropout_forward_and_adjoint_vs_torch(agb, T, heads, d, mode):
     assert float((plain.float() - got.float()).abs().max()) > 0.05 * scale
 
 
+@pytest.mark.parametrize("T,heads,d,mode", [(197, 2, 64, 0), (64, 2, 64, 1), (33, 2, 16, 1)])
+def test_attention_dropout_fp32_mode_vs_torch(agb, T, heads, d, mode):
+    """The exact (fp32, CUDA-core) mode applies the same counter-hash mask: forward and adjoint against torch autograd."""
+    torch.manual_seed(T + d)
+    rows, H, p = 2, heads * d, 0.1
+    thr = agb.dropout_thr(p)
+    seed = 0xABCDEF + T
+    qkv = torch.randn(rows * T, 3 * H, device=DEV) * 1.2
+    dctx = torch.randn(rows * T, H, device=DEV)
+    dense = (torch.rand(rows, T - 1, device=DEV) > 0.35).to(torch.int64)
+    masks = agb.pack_masks(dense, prepend_cls=True)
+    tok = torch.cat([torch.ones((rows, 1), dtype=torch.int64, device=DEV), dense], 1)
+    keep = agb.attention_dropout_mask(rows, heads, T, thr, seed, DEV)
+    q32 = qkv.clone().requires_grad_(True)
+    ref = _torch_attention(q32, tok, keep, T, heads, mode, 65536.0 / (65536.0 - thr))
+    ref.backward(dctx)
+    got = agb.masked_attention_dropout(qkv, masks, T, heads, mode, thr, seed)
+    np.testing.assert_allclose(_np(got), _np(ref), rtol=1e-4, atol=1e-5)
+    dq = agb.masked_attention_dropout_bwd(qkv, dctx, masks, T, heads, mode, thr, seed)
+    np.testing.assert_allclose(_np(dq), _np(q32.grad), rtol=2e-3, atol=2e-4 * float(q32.grad.abs().max()))
+
+
 @pytest.mark.parametrize("name", ["vit_mini", "bert_mini"])
 def test_explainer_training_with_dropout_is_seeded_and_learns(agb, golden_dir, name):
     """train() mode on the drop-in explainer: dropout active (gradients differ from the p = 0 path), reproducible under
