@@ -358,6 +358,44 @@ def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tens
     return x, xa
 
 
+# Small calls are launch-bound: the reference's scripts evaluate 2-8 inputs x 4-32 coalitions at a time, where the ~65 kernel
+# launches of a ViT-Base evaluation cost more host time (~1.8 ms through Python + ctypes) than the GPU needs.  Calls of at most
+# GRAPH_MAX_ROWS (input, coalition) rows are therefore captured once per shape into a CUDA graph and replayed (fixed-layout
+# paths only: the packed BERT path sizes its buffers from a device-side count).  0 = off.
+GRAPH_MAX_ROWS = 128
+GRAPH_CACHE_ENTRIES = 4
+
+
+class _GraphCache:
+    """shape-keyed CUDA graphs of a pure function of device tensors (static inputs copied in, static output cloned out)"""
+
+    def __init__(self):
+        self.entries: Dict[Any, Any] = {}
+
+    def run(self, key, fn, inputs: Tuple[Tensor, ...]) -> Tensor:
+        entry = self.entries.get(key)
+        if entry is None:
+            static_in = [t.clone() for t in inputs]
+            side = torch.cuda.Stream(device=inputs[0].device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):            # warm-up off the capture: lazy allocations, function attributes
+                for _ in range(2):
+                    fn(*static_in)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = fn(*static_in)
+            if len(self.entries) >= GRAPH_CACHE_ENTRIES:
+                self.entries.pop(next(iter(self.entries)))
+            entry = (graph, static_in, static_out)
+            self.entries[key] = entry
+        graph, static_in, static_out = entry
+        for dst, src in zip(static_in, inputs):
+            dst.copy_(src)
+        graph.replay()
+        return static_out.clone()
+
+
 class SurrogateEngine:
     """Masked value function v(S): class probabilities for (input, coalition) rows.
     reference models/vanilla_vit.py:51-56, models/vanilla_bert.py:61-77"""
@@ -369,6 +407,12 @@ class SurrogateEngine:
         self.w_cls, self.b_cls = _f32(sd["classifier.weight"]), _f32(sd["classifier.bias"])
         if not self.bw.vit:
             self.w_pool, self.b_pool = _f32(sd["bert_pooler.dense.weight"]), _f32(sd["bert_pooler.dense.bias"])
+        self.graphs = _GraphCache()
+
+    def _packed_path(self) -> bool:
+        cfg = self.cfg
+        return (not self.bw.vit and DROP_MASKED_TOKENS and self.pol.bf16 and CLS_ONLY_LAST_BLOCK
+                and cfg.hidden_size == cfg.num_attention_heads * 64)
 
     @torch.no_grad()
     def probs(self, xs: Tensor, masks: Tensor, S: int, max_rows: int = 1024) -> Tensor:
@@ -378,6 +422,16 @@ class SurrogateEngine:
         assert masks.shape[0] == B * S
         if B * S == 0:
             return torch.empty((0, cfg.num_labels), dtype=torch.float32, device=xs.device)
+        from . import _native as nat
+        if (0 < B * S <= GRAPH_MAX_ROWS and B * S <= max_rows and self.pol.bf16 and not self._packed_path()
+                and nat.PROFILE is None and not torch.cuda.is_current_stream_capturing()):
+            key = (tuple(xs.shape), xs.dtype, tuple(masks.shape), S, FUSE_LAYERNORM, CLS_ONLY_LAST_BLOCK, SHARE_FIRST_BLOCK)
+            return self.graphs.run(key, lambda x_, m_: self._probs_eager(x_, m_, S, max_rows), (xs.contiguous(), masks))
+        return self._probs_eager(xs, masks, S, max_rows)
+
+    def _probs_eager(self, xs: Tensor, masks: Tensor, S: int, max_rows: int) -> Tensor:
+        cfg, T = self.cfg, n_players_of(self.cfg) + 1
+        B = xs.shape[0]
         per = max(1, max_rows // S)
         outs: List[Tensor] = []
         for b0 in range(0, B, per):
@@ -418,6 +472,20 @@ class ExplainerEngine:
             n, C = n_players_of(self.cfg), self.cfg.num_labels
             phi = torch.empty((0, C, n), dtype=torch.float32, device=xs.device)
             return (phi, torch.empty((0, n + 1, C), dtype=torch.float32, device=xs.device)) if want_pred else phi
+        from . import _native as nat
+        B = xs.shape[0]
+        if (B <= GRAPH_MAX_ROWS and self.pol.bf16 and not want_pred and grand is not None and null is not None
+                and nat.PROFILE is None and not torch.cuda.is_current_stream_capturing()):
+            # small explainer calls are launch-bound as well: one CUDA graph per shape (see GRAPH_MAX_ROWS)
+            if not hasattr(self, "graphs"):
+                self.graphs = _GraphCache()
+            key = (tuple(xs.shape), xs.dtype, tuple(masks.shape), tuple(grand.shape), tuple(null.shape), FUSE_LAYERNORM)
+
+            def fn(x_, m_, g_, n_):
+                h, ha = run_backbone(self.bw, self.cfg, self.pol, x_, m_, 1)
+                return self.tail(h, ha, m_, B, g_, n_, False)
+
+            return self.graphs.run(key, fn, (xs.contiguous(), masks, grand.float().contiguous(), null.float().contiguous()))
         x, xa = run_backbone(self.bw, self.cfg, self.pol, xs, masks, 1)
         return self.tail(x, xa, masks, xs.shape[0], grand, null, want_pred)
 

@@ -90,3 +90,54 @@ def test_row_chunking_is_invisible(agb, name):
         rest, _ = rec.fw_surrogate(srg, xs[64:], ash.PackedMasks(pm.words[64 * S:].contiguous(), n))
     assert full.shape == (B * S, cfgd["num_labels"])
     assert torch.equal(full, torch.cat([first, rest], 0))
+
+
+@pytest.mark.parametrize("name", ["vit_mini", "vit_tiny", "bert_mini"])
+def test_cuda_graph_replay_of_small_calls_is_invisible(agb, name):
+    """Calls of <= GRAPH_MAX_ROWS rows are captured once per shape and replayed: bit-identical to the eager launches, for
+    fresh inputs on every replay, across alternating shapes, and after the weights change (the engine is rebuilt)."""
+    from autognothi_b200 import engine
+    rec, cfgd, cfg, srg, exp = _build(name, "bf16")
+    n = rec.n_players(cfg)
+    old_rows, old_drop = engine.GRAPH_MAX_ROWS, engine.DROP_MASKED_TOKENS
+    engine.DROP_MASKED_TOKENS = False           # the packed BERT path is never captured (data-dependent buffer sizes)
+    try:
+        for it in range(6):
+            B, S = ((2, 4), (1, 8), (3, 2))[it % 3]
+            xs = torch.from_numpy(synth.inputs(cfgd, B, seed=10 + it)).to(DEV)
+            g = torch.Generator(device="cpu").manual_seed(100 + it)
+            masks = (torch.rand((B, S, n), generator=g) > 0.5).to(torch.int64).to(DEV)
+            with torch.no_grad():
+                engine.GRAPH_MAX_ROWS = 128
+                a, _ = rec.fw_surrogate(srg, xs, masks)
+                engine.GRAPH_MAX_ROWS = 0
+                b, _ = rec.fw_surrogate(srg, xs, masks)
+            assert torch.equal(a, b), (it, float((a - b).abs().max()))
+            if it == 3:
+                with torch.no_grad():
+                    srg.classifier.weight.mul_(1.5)        # bumps the parameter version -> packed weights and graphs rebuilt
+    finally:
+        engine.GRAPH_MAX_ROWS, engine.DROP_MASKED_TOKENS = old_rows, old_drop
+
+
+@pytest.mark.parametrize("name", ["vit_mini", "bert_mini"])
+def test_cuda_graph_replay_of_small_explainer_calls_is_invisible(agb, name):
+    from autognothi_b200 import engine
+    rec, cfgd, cfg, srg, exp = _build(name, "bf16")
+    n, C = rec.n_players(cfg), cfgd["num_labels"]
+    old_rows = engine.GRAPH_MAX_ROWS
+    try:
+        for it in range(4):
+            B = (2, 3)[it % 2]
+            xs = torch.from_numpy(synth.inputs(cfgd, B, seed=20 + it)).to(DEV)
+            g = torch.Generator(device="cpu").manual_seed(200 + it)
+            masks = (torch.rand((B, n), generator=g) > 0.3).to(torch.int64).to(DEV)
+            grand, null = torch.rand((B, C), generator=g).to(DEV), torch.rand((1, C), generator=g).to(DEV)
+            with torch.no_grad():
+                engine.GRAPH_MAX_ROWS = 128
+                a, _ = rec.fw_explainer(exp, xs, masks, grand, null)
+                engine.GRAPH_MAX_ROWS = 0
+                b, _ = rec.fw_explainer(exp, xs, masks, grand, null)
+            assert torch.equal(a, b), (it, float((a - b).abs().max()))
+    finally:
+        engine.GRAPH_MAX_ROWS = old_rows
