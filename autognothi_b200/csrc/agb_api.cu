@@ -18,6 +18,7 @@ int cls_attention(const void* q, long long ldq, const void* kv, long long ldkv, 
 int mask_counts(const uint32_t* packed, int rows, int words, int T, int* counts, cudaStream_t st);
 int packed_token_index(const uint32_t* packed, int rows, int words, int T, int S, const int* cu, long long* src,
                        cudaStream_t st);
+int attention_pipe_prefix(const bf16* qkv, const int* nkeep, int rows, int T, int H, int heads, bf16* ctx, cudaStream_t stream);
 int attention_narrow_varlen(const bf16* qkv, const int* cu, int rows, int max_len, int H, int heads, bf16* ctx, cudaStream_t st);
 int attention_varlen(const bf16* qkv, const int* cu, int rows, int max_len, int total_tokens, int H, int heads, bf16* ctx,
                      cudaStream_t stream);
@@ -147,6 +148,9 @@ int agb_attention_bf16_varlen(const void* qkv, const int* cu, int rows, int max_
                                         ST(stream));
   return agb::attention_varlen(static_cast<const bf16*>(qkv), cu, rows, max_len, total_tokens, H, heads,
                                static_cast<bf16*>(ctx), ST(stream));
+}
+int agb_attention_bf16_prefix(const void* qkv, const int* nkeep, int rows, int T, int H, int heads, void* ctx, void* stream) {
+  return agb::attention_pipe_prefix(static_cast<const bf16*>(qkv), nkeep, rows, T, H, heads, static_cast<bf16*>(ctx), ST(stream));
 }
 int agb_cls_attention_varlen(const void* q, long long ldq, const void* kv, long long ldkv, int k_off, int v_off,
                              int io_is_bf16, const int* cu, int rows, int max_len, int H, int heads, void* ctx,

@@ -27,6 +27,11 @@ constexpr int AP_O_COL = 128;      // O accumulator at columns [128, 192) of the
 constexpr int AP_KV_RING = 3;
 constexpr int AP_PREP_THREADS = 32;
 constexpr int AP_MODE_VARLEN = 2;   // internal third mode: packed variable-length rows, every packed token is a live key
+// internal fourth mode (ViT "logit := 0" masks with the tokens of every row permuted so that the kept ones come first):
+// keys [0, nkeep[row]) are kept; the masked keys [nkeep, T) all carry the logit 0, so they are folded into ONE virtual
+// key at column nkeep whose logit is log(n_masked) / scale and whose V row is the mean of the masked V rows — the same
+// softmax, with about half the columns to exponentiate at the sampler's average coalition size
+constexpr int AP_MODE_PREFIX = 3;
 
 struct AttPipeParams {
   const uint32_t* mask;
@@ -40,6 +45,7 @@ struct AttPipeParams {
   int ring;          // K/V ring depth (units), limited by shared memory
   int kvb;           // bytes reserved per K (or V) tile: NK * 128, or 2 x 256-row TMA boxes when NK > 256
   const int* cu;     // AP_MODE_VARLEN: row r owns the packed tokens [cu[r], cu[r+1]) of qkv (total_tokens, 3H)
+  const int* nkeep;  // AP_MODE_PREFIX: kept tokens of row r (CLS included) = its first nkeep[r] tokens
   bf16* ctx;
   long long* trace;  // optional [items][8] clock64 timestamps of CTA 0 (diagnostics), or nullptr
   // attention-probability dropout (training forward only; DROP instantiations): P kept iff 16 hash bits >= drop_thr
@@ -65,23 +71,25 @@ __device__ __forceinline__ void ap_load(uint32_t addr, uint32_t (&s)[W]) {
   tmem_wait_ld();
 }
 
-template <int W, bool MASKED>
-__device__ __forceinline__ float ap_max_chunk(uint32_t addr, float m, uint32_t live_lo, uint32_t live_hi) {
+template <int W, bool MASKED, bool VIRT = false>
+__device__ __forceinline__ float ap_max_chunk(uint32_t addr, float m, uint32_t live_lo, uint32_t live_hi, int vj = -1,
+                                              float vval = 0.f) {
   uint32_t s[W];
   ap_load<W>(addr, s);
 #pragma unroll
   for (int j = 0; j < W; ++j) {
     float v = __uint_as_float(s[j]);
+    if (VIRT && j == vj) v = vval;          // the virtual key that stands for all masked keys
     if (MASKED && !(((j < 32 ? live_lo : live_hi) >> (j & 31)) & 1u)) v = -INFINITY;
     m = fmaxf(m, v);
   }
   return m;
 }
 
-template <int W, bool MASKED, bool DROP = false>
+template <int W, bool MASKED, bool DROP = false, bool VIRT = false>
 __device__ __forceinline__ float ap_exp_chunk(uint32_t s_addr, uint32_t p_addr, float scale_log2, float m_scaled,
                                               uint32_t live_lo, uint32_t live_hi, uint32_t dkey = 0u, uint32_t pair0 = 0u,
-                                              uint32_t dthr = 0u) {
+                                              uint32_t dthr = 0u, int vj = -1, float vval = 0.f) {
   uint32_t s[W];
   ap_load<W>(s_addr, s);
   uint32_t pk[W / 2];
@@ -89,6 +97,10 @@ __device__ __forceinline__ float ap_exp_chunk(uint32_t s_addr, uint32_t p_addr, 
 #pragma unroll
   for (int j = 0; j < W / 2; ++j) {
     float a = __uint_as_float(s[2 * j]), b = __uint_as_float(s[2 * j + 1]);
+    if (VIRT) {
+      if (2 * j == vj) a = vval;
+      if (2 * j + 1 == vj) b = vval;
+    }
     if (MASKED) {
       const int j0 = 2 * j, j1 = 2 * j + 1;
       if (!(((j0 < 32 ? live_lo : live_hi) >> (j0 & 31)) & 1u)) a = -INFINITY;
@@ -271,7 +283,12 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const uint32_t av = skv0 + b * 2 * kvb16 + kvb16;
       const uint32_t d_o = tmem_base + g * rstride + o_col, a_p = tmem_base + g * rstride;
       const uint64_t dv = dv0 + av;
-      const int nks = NK / 16;
+      int nks = NK / 16;
+      if (MODE == AP_MODE_PREFIX) {           // only the kept keys + the virtual key carry probability mass
+        const int u = blockIdx.x + ui * grid;
+        const int nk = __ldg(p.nkeep + u / p.heads);
+        nks = (nk + (nk < T ? 1 : 0) + 15) / 16;     // P beyond these columns is zero or never written: not needed
+      }
 #pragma unroll 4
       for (int ks = 0; ks < nks; ++ks)
         umma_ts_e(e, d_o, a_p + ks * 8, dv + ks * (2048 >> 4), idesc_o, ks != 0 ? 1u : 0u);
@@ -285,6 +302,41 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     for (int ui = 0; ui < nu; ++ui) {
       const int b = ui % R, n = ui / R;
       mbar_wait(smem_u32(&kv_full[b]), n & 1);
+      if (MODE == AP_MODE_PREFIX) {
+        // V row of the virtual key = mean of the masked V rows [nk, T).  Lane = (16-byte chunk of the row, row group): four
+        // row groups stride the masked rows, each lane sums its 8 dims, the groups are folded with shuffles.
+        const int u = blockIdx.x + ui * grid;
+        const int nk = __ldg(p.nkeep + u / p.heads);
+        if (nk < T) {
+          const uint8_t* sV = sKV + b * 2 * kvb + kvb;
+          const uint32_t chunk = (uint32_t)tid & 7u;
+          float acc[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+          for (int j = nk + (tid >> 3); j < T; j += 4) {
+            const uint4 w = *reinterpret_cast<const uint4*>(sV + j * 128 + ((chunk ^ ((uint32_t)j & 7u)) << 4));
+            acc[0] += bf16_lo(w.x); acc[1] += bf16_hi(w.x);
+            acc[2] += bf16_lo(w.y); acc[3] += bf16_hi(w.y);
+            acc[4] += bf16_lo(w.z); acc[5] += bf16_hi(w.z);
+            acc[6] += bf16_lo(w.w); acc[7] += bf16_hi(w.w);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+            acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+          }
+          const float invn = 1.0f / (float)(T - nk);
+          __syncwarp();              // every masked row (incl. row nk) has been read before row nk is overwritten
+          if (tid < 8) {
+            uint4 o;
+            o.x = pack_bf16x2(acc[0] * invn, acc[1] * invn);
+            o.y = pack_bf16x2(acc[2] * invn, acc[3] * invn);
+            o.z = pack_bf16x2(acc[4] * invn, acc[5] * invn);
+            o.w = pack_bf16x2(acc[6] * invn, acc[7] * invn);
+            *reinterpret_cast<uint4*>(sKV + b * 2 * kvb + kvb + nk * 128 + ((chunk ^ ((uint32_t)nk & 7u)) << 4)) = o;
+          }
+        }
+      }
       if (MODE == AGB_MASK_MUL0) {
         const int u = blockIdx.x + ui * grid;
         const int row = u / p.heads;
@@ -320,6 +372,18 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         Tr = __ldg(p.cu + row + 1) - tok0;
       }
       const bool warp_live = (m * 128 + qd * 32) < Tr;    // warp-uniform: any real query row in this warp?
+      // key columns the softmax has to visit: all of them, or (AP_MODE_PREFIX) the kept keys + one virtual key
+      int Tk = Tr, NKu = NK, vcol = -1;
+      float vval = 0.f;
+      if (MODE == AP_MODE_PREFIX) {
+        const int nk = __ldg(p.nkeep + row);
+        if (nk < T) {
+          vcol = nk;
+          vval = __log2f((float)(T - nk)) / scale_log2;   // exp2(vval * scale_log2 - m) = n_masked * exp2(0 - m)
+        }
+        Tk = nk + (nk < T ? 1 : 0);
+        NKu = (Tk + 15) / 16 * 16;
+      }
       mbar_wait(smem_u32(&s_full[g]), n & 1);
       if (qd == 0) AP_TRACE(k, 4);
       tc_fence_after();
@@ -327,20 +391,22 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       if (warp_live) {
         // ViT: keys [0, n_fast) are all live (masked keys keep their exact-0 logit) -> no per-element selects;
         // the chunk holding the T boundary (and every BERT chunk) takes the masked variant.
-        const int n_fast = (MODE != AGB_MASK_NEGINF) ? (Tr / 64) * 64 : 0;
+        constexpr bool VIRT = (MODE == AP_MODE_PREFIX);
+        // (AP_MODE_PREFIX: the chunk that holds the virtual column always takes the masked variant)
+        const int n_fast = (MODE == AP_MODE_PREFIX) ? ((Tk - 1) / 64) * 64 : (MODE != AGB_MASK_NEGINF) ? (Tr / 64) * 64 : 0;
         // pass 1: row maximum
         float mx = -INFINITY;
         int c0 = 0;
         for (; c0 < n_fast; c0 += 64) mx = ap_max_chunk<64, false>(lane_addr + c0, mx, 0u, 0u);
-        for (; c0 + 64 <= NK; c0 += 64) {
+        for (; c0 + 64 <= NKu; c0 += 64) {
           uint32_t lo, hi;
-          ap_live_bits(mrow, p.words, MODE, Tr, c0, 64, lo, hi);
-          mx = ap_max_chunk<64, true>(lane_addr + c0, mx, lo, hi);
+          ap_live_bits(mrow, p.words, MODE, Tk, c0, 64, lo, hi);
+          mx = ap_max_chunk<64, true, VIRT>(lane_addr + c0, mx, lo, hi, vcol - c0, vval);
         }
-        for (; c0 < NK; c0 += 16) {
+        for (; c0 < NKu; c0 += 16) {
           uint32_t lo, hi;
-          ap_live_bits(mrow, p.words, MODE, Tr, c0, 16, lo, hi);
-          mx = ap_max_chunk<16, true>(lane_addr + c0, mx, lo, hi);
+          ap_live_bits(mrow, p.words, MODE, Tk, c0, 16, lo, hi);
+          mx = ap_max_chunk<16, true, VIRT>(lane_addr + c0, mx, lo, hi, vcol - c0, vval);
         }
         const float m_scaled = mx * scale_log2;
         // pass 2: P = exp2(s*scale - max*scale) -> bf16 pairs -> TMEM (overlaying consumed S columns)
@@ -350,17 +416,17 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         for (; c0 < n_fast; c0 += 64)
           sum += ap_exp_chunk<64, false, DROP>(lane_addr + c0, lane_addr + (c0 >> 1), scale_log2, m_scaled, 0u, 0u, dkey,
                                                c0 >> 1, p.drop_thr);
-        for (; c0 + 64 <= NK; c0 += 64) {
+        for (; c0 + 64 <= NKu; c0 += 64) {
           uint32_t lo, hi;
-          ap_live_bits(mrow, p.words, MODE, Tr, c0, 64, lo, hi);
-          sum += ap_exp_chunk<64, true, DROP>(lane_addr + c0, lane_addr + (c0 >> 1), scale_log2, m_scaled, lo, hi, dkey,
-                                              c0 >> 1, p.drop_thr);
+          ap_live_bits(mrow, p.words, MODE, Tk, c0, 64, lo, hi);
+          sum += ap_exp_chunk<64, true, DROP, VIRT>(lane_addr + c0, lane_addr + (c0 >> 1), scale_log2, m_scaled, lo, hi, dkey,
+                                                    c0 >> 1, p.drop_thr, vcol - c0, vval);
         }
-        for (; c0 < NK; c0 += 16) {
+        for (; c0 < NKu; c0 += 16) {
           uint32_t lo, hi;
-          ap_live_bits(mrow, p.words, MODE, Tr, c0, 16, lo, hi);
-          sum += ap_exp_chunk<16, true, DROP>(lane_addr + c0, lane_addr + (c0 >> 1), scale_log2, m_scaled, lo, hi, dkey,
-                                              c0 >> 1, p.drop_thr);
+          ap_live_bits(mrow, p.words, MODE, Tk, c0, 16, lo, hi);
+          sum += ap_exp_chunk<16, true, DROP, VIRT>(lane_addr + c0, lane_addr + (c0 >> 1), scale_log2, m_scaled, lo, hi, dkey,
+                                                    c0 >> 1, p.drop_thr, vcol - c0, vval);
         }
         tmem_wait_st();
         inv = (DROP ? p.drop_scale : 1.0f) / sum;
@@ -412,8 +478,9 @@ int get_attention_variant() { return g_attention_variant; }
 // T = sequence length (fixed layout) or an upper bound of the row lengths (packed layout, cu != nullptr)
 static int attention_pipe_launch(const bf16* qkv, const uint32_t* mask, int words, int rows, int share, int T, int H,
                                  int heads, int mode, bf16* ctx, const int* cu, int total_tokens, cudaStream_t stream,
-                                 unsigned drop_thr = 0, unsigned long long drop_seed = 0) {
+                                 unsigned drop_thr = 0, unsigned long long drop_seed = 0, const int* nkeep = nullptr) {
   AttPipeParams p;
+  p.nkeep = nkeep;
   p.drop_thr = drop_thr;
   p.drop_seed = drop_seed;
   p.drop_scale = 65536.0f / (65536.0f - (float)drop_thr);
@@ -454,11 +521,22 @@ static int attention_pipe_launch(const bf16* qkv, const uint32_t* mask, int word
 #undef AP_SET
     AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<AGB_MASK_MUL0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<AGB_MASK_NEGINF, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AGB_CHECK_CUDA(cudaFuncSetAttribute(attention_pipe_kernel<AP_MODE_PREFIX, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured_smem = smem;
   }
   const int grid = p.units < sm_count() ? p.units : sm_count();
 #define AP_GO(M_, G_) attention_pipe_kernel<M_, G_><<<grid, AP_THREADS, smem, stream>>>(tmQ, tmKV, p)
   const int kmode = cu ? AP_MODE_VARLEN : mode;
+  if (nkeep != nullptr) {
+    // kept-first token order (ViT masks): keys [0, nkeep[row]) + one virtual key for the masked rest
+    if (cu != nullptr || share != 1 || p.groups != 2 || mode != AGB_MASK_MUL0 || drop_thr > 0) {
+      set_last_error("prefix-mask attention: ViT mask semantics, fixed layout, T <= 256 (T = %d)", T);
+      return AGB_ERR_UNSUPPORTED;
+    }
+    attention_pipe_kernel<AP_MODE_PREFIX, 2><<<grid, AP_THREADS, smem, stream>>>(tmQ, tmKV, p);
+    AGB_CHECK_CUDA(cudaGetLastError());
+    return AGB_OK;
+  }
   if (drop_thr > 0) {
     // training forward with attention-probability dropout: fixed layout, T <= 256 (the adjoint's range)
     if (cu != nullptr || share != 1 || p.groups != 2) {
@@ -488,6 +566,16 @@ int attention_pipe(const bf16* qkv, const uint32_t* mask, int words, int rows, i
                    int mode, bf16* ctx, cudaStream_t stream) {
   if (g_attention_variant == 1) return AGB_ERR_UNSUPPORTED;
   return attention_pipe_launch(qkv, mask, words, rows, share, T, H, heads, mode, ctx, nullptr, 0, stream);
+}
+
+// ViT-masked attention on rows whose tokens were permuted so that the kept ones come first (nkeep[row] of them, CLS
+// included): the masked keys are folded into one virtual key (see AP_MODE_PREFIX).
+int attention_pipe_prefix(const bf16* qkv, const int* nkeep, int rows, int T, int H, int heads, bf16* ctx, cudaStream_t stream) {
+  AGB_REQUIRE(rows >= 0 && T > 0 && heads > 0 && H == heads * AP_D, "prefix attention shape (head dim 64)");
+  if (rows == 0) return AGB_OK;
+  AGB_REQUIRE(qkv && nkeep && ctx, "null pointer");
+  AGB_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(ctx) & 15) == 0, "alignment");
+  return attention_pipe_launch(qkv, nullptr, 0, rows, 1, T, H, heads, AGB_MASK_MUL0, ctx, nullptr, 0, stream, 0, 0, nkeep);
 }
 
 int attention_pipe_dropout(const bf16* qkv, const uint32_t* mask, int words, int rows, int T, int H, int heads, int mode,

@@ -163,7 +163,7 @@ def vit_layer(pol: _Policy, lw: LayerWeights, x: Tensor, masks: Tensor, T: int, 
 
 
 def vit_layer_fused(lw: LayerWeights, x: Tensor, x16: Optional[Tensor], stats: Optional[Tensor], masks: Tensor, T: int,
-                    heads: int, eps: float, last: bool, ctx: Optional[Tensor] = None
+                    heads: int, eps: float, last: bool, ctx: Optional[Tensor] = None, nkeep: Optional[Tensor] = None
                     ) -> Tuple[Tensor, Optional[Tensor], Optional[Tensor]]:
     """Same block as vit_layer (bf16 mode) without LayerNorm kernels: x16 / stats are the bf16 copy and per-row
     (sum, sum of squares) partials of the fp32 residual stream x, produced by the previous residual GEMM's epilogue
@@ -171,7 +171,8 @@ def vit_layer_fused(lw: LayerWeights, x: Tensor, x16: Optional[Tensor], stats: O
     f = lw.fold()
     if ctx is None:
         qkv, _, _ = ops.gemm_bf16_fused(x16, f["wqkv"], f["bqkv"], ln=(stats, f["cqkv"], eps))
-        ctx = ops.masked_attention(qkv, masks, T, heads, ops.MASK_MUL0)
+        # nkeep: the rows are in kept-first token order -> the masked keys fold into one virtual key
+        ctx = ops.attention_prefix(qkv, nkeep, T, heads) if nkeep is not None else ops.masked_attention(qkv, masks, T, heads, ops.MASK_MUL0)
     _, y16, ystats = ops.gemm_bf16_fused(ctx, lw.wo, lw.bo, residual=x, out=x, emit_copy_stats=True)
     h = ops.gemm_bf16_fused(y16, f["w1"], f["b1"], act=ops.ACT_GELU, ln=(ystats, f["c1"], eps))[0]
     if last:
@@ -210,6 +211,15 @@ SHARE_FIRST_BLOCK = True
 # attended to and the head reads only token 0, so only the kept tokens of every row are carried through the encoder
 # (packed back to back; variable-length attention).  SURVEY.md 8f-3.
 DROP_MASKED_TOKENS = True
+# ViT surrogate / classifier evaluation (multiplicative "logit := 0" masks, bf16, head reads token 0): the tokens of every
+# (input, coalition) row are permuted so that the kept ones come first.  Everything between the attentions is token-wise
+# and attention is permutation-equivariant, so the CLS output is unchanged; the attention kernel then sees the masked keys
+# as one contiguous tail, all with the logit 0, and folds them into ONE virtual key (agb_attention_bf16_prefix).
+# Exact (tests/test_gpu_edges.py) but OFF by default: the attention kernel gets 14 % faster (390 -> 336 us per layer at the
+# bench shape, its share of the step 17.0 % -> 14.8 %), which the sort + two gathers of the switch give back — an A/B on
+# one box measured 28.0 k vs 28.2 k evals/s (tools/ab_kept_first.py).  Pays off once the softmax stage is no longer
+# bound by TMEM round trips per chunk.
+KEPT_FIRST_ORDER = False
 
 
 def last_block_cls_only(pol: _Policy, lw: LayerWeights, vit: bool, x: Tensor, xa: Optional[Tensor], x16: Optional[Tensor],
@@ -301,6 +311,7 @@ def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tens
     # so that block's LayerNorm + QKV projection runs once per input and the attention kernel reads the shared rows.
     share = (SHARE_FIRST_BLOCK and S > 1 and pol.bf16 and len(full) > 0 and T <= 512 and H == heads * 64)
     ctx0 = None
+    nkeep = None             # set when the rows are switched to kept-first token order (KEPT_FIRST_ORDER)
     if share:
         x_img = embed(bw, cfg, pol, xs, 1)                                   # (B, T, H) fp32, one row block per input
         assert x_img.shape[1] == T, f"sequence length {x_img.shape[1]} != n_players + 1 = {T}"
@@ -316,7 +327,21 @@ def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tens
         else:
             qkv0 = pol.linear(pol.act(xi), lw0.wqkv, lw0.bqkv)
         ctx0 = ops.masked_attention(qkv0, masks, T, heads, ops.MASK_MUL0 if bw.vit else ops.MASK_NEGINF, share=S)
-        x3 = x_img.repeat_interleave(S, dim=0)                               # the residual stream of every coalition
+        if (KEPT_FIRST_ORDER and cls_only and fused and layer_hook is None and T <= 256 and len(full) > 1):
+            # kept-first token order per row (stable: CLS stays first): gather the residual stream and the first block's
+            # attention output into that order; from here on the masks are prefixes of length nkeep
+            rows_ = masks.shape[0]
+            dense = ops.unpack_masks(masks, T - 1)                                        # (rows, n) {0,1} players
+            keep = torch.cat([torch.ones((rows_, 1), dtype=dense.dtype, device=dense.device), dense], 1)
+            order = torch.sort(1 - keep, dim=1, stable=True).indices                      # (rows, T)
+            nkeep = keep.sum(1).to(torch.int32).contiguous()
+            r = torch.arange(rows_, device=order.device)
+            x3 = x_img.reshape(-1, H).index_select(0, (order + (r // S)[:, None] * T).reshape(-1)).reshape(rows_, T, H)
+            ctx0 = ctx0.index_select(0, (order + r[:, None] * T).reshape(-1))
+            masks = ops.pack_masks((torch.arange(T - 1, device=order.device)[None, :] < (nkeep[:, None] - 1)).to(torch.int64),
+                                   prepend_cls=True)
+        else:
+            x3 = x_img.repeat_interleave(S, dim=0)                           # the residual stream of every coalition
     else:
         x3 = embed(bw, cfg, pol, xs, S)
     assert x3.shape[1] == T, f"sequence length {x3.shape[1]} != n_players + 1 = {T}"
@@ -331,7 +356,7 @@ def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tens
             for i, lw in enumerate(full):
                 x, x16, stats = vit_layer_fused(lw, x, x16, stats, masks, T, heads, eps,
                                                 last=(not cls_only and i == len(full) - 1 and layer_hook is None),
-                                                ctx=ctx0 if i == 0 else None)
+                                                ctx=ctx0 if i == 0 else None, nkeep=nkeep)
                 if layer_hook is not None:
                     layer_hook(i, x, x16)
             if cls_only:

@@ -345,6 +345,19 @@ def attention_varlen(qkv: Tensor, cu: Tensor, max_len: int, heads: int) -> Tenso
     return ctx
 
 
+def attention_prefix(qkv: Tensor, nkeep: Tensor, T: int, heads: int) -> Tensor:
+    """ViT-masked attention for kept-first token order: qkv (rows*T, 3H) bf16, nkeep (rows,) int32 kept tokens per row (CLS
+    included) -> ctx (rows*T, H).  The masked keys are folded into one virtual key (agb_attention_bf16_prefix)."""
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and nkeep.dtype == torch.int32 and nkeep.is_contiguous()
+    rows = nkeep.shape[0]
+    H = qkv.shape[1] // 3
+    assert qkv.shape[0] == rows * T
+    ctx = torch.empty((rows * T, H), dtype=torch.bfloat16, device=qkv.device)
+    nat.NEXT_META = None
+    nat.call("agb_attention_bf16_prefix", nat.ptr(qkv), nat.ptr(nkeep), rows, T, H, heads, nat.ptr(ctx), nat.stream())
+    return ctx
+
+
 def cls_attention_varlen(q: Tensor, kv: Tensor, k_off: int, v_off: int, cu: Tensor, max_len: int, heads: int) -> Tensor:
     """CLS-query attention over packed rows: q (rows, H), kv (total_tokens, ld) -> ctx (rows, H) bf16."""
     assert q.dtype == torch.bfloat16 and kv.dtype == torch.bfloat16 and q.stride(1) == 1 and kv.stride(1) == 1

@@ -122,6 +122,11 @@ int agb_packed_token_index(const uint32_t* packed, int rows, int words, int T, i
  * head dims 8 / 16 / 32 (the LTT side ladder, reference models/ltt_bert.py:437-451) run the narrow-head kernel. */
 int agb_attention_bf16_varlen(const void* qkv, const int* cu, int rows, int max_len, int total_tokens, int H, int heads,
                               void* ctx, void* stream);
+/* ViT-masked attention (reference models/vanilla_vit.py:444-459: masked logit := 0) on rows whose tokens were permuted so
+ * that the kept ones come first: keys [0, nkeep[row]) keep their logits, the masked keys [nkeep[row], T) all have the
+ * logit 0 and are folded into ONE virtual key of weight (T - nkeep) whose value row is the mean of theirs — the same
+ * softmax, with fewer columns to exponentiate.  qkv (rows, T, 3H) bf16 -> ctx (rows, T, H); head dim 64, T <= 256. */
+int agb_attention_bf16_prefix(const void* qkv, const int* nkeep, int rows, int T, int H, int heads, void* ctx, void* stream);
 
 /* ---- row kernels ---------------------------------------------------------------------------- */
 /* nn.LayerNorm over the last dim (reference models/vanilla_vit.py:94,213,369,373; vanilla_bert.py:

@@ -141,3 +141,35 @@ def test_cuda_graph_replay_of_small_explainer_calls_is_invisible(agb, name):
             assert torch.equal(a, b), (it, float((a - b).abs().max()))
     finally:
         engine.GRAPH_MAX_ROWS = old_rows
+
+
+@pytest.mark.parametrize("name", ["vit_mini", "vit_tiny", "vit_base"])
+def test_kept_first_token_order_is_exact_work_skipping(agb, golden_dir, name):
+    """ViT surrogate: permuting every row's tokens so that the kept ones come first and folding the masked keys (all with
+    the logit 0) into one virtual key changes nothing but rounding — incl. the empty and the full coalition."""
+    import os
+    from autognothi_b200 import engine
+    g = np.load(os.path.join(golden_dir, f"model_{name}.npz"))
+    B, S, n = (int(v) for v in g["meta"])
+    rec, cfgd, cfg, srg, exp = _build(name, "bf16")
+    xs = torch.from_numpy(synth.inputs(cfgd, B, seed=0)).to(DEV)
+    masks = torch.from_numpy(g["masks"].astype(np.int64)).to(DEV).reshape(B, S, n)
+    edge = masks.clone()
+    edge[0, 0, :] = 0
+    edge[0, 1, :] = 1
+    edge[0, 1, 5] = 0
+    old = engine.KEPT_FIRST_ORDER
+    try:
+        with torch.no_grad():
+            engine.KEPT_FIRST_ORDER = True
+            a, _ = rec.fw_surrogate(srg, xs, masks)
+            ae, _ = rec.fw_surrogate(srg, xs, edge)
+            engine.KEPT_FIRST_ORDER = False
+            b, _ = rec.fw_surrogate(srg, xs, masks)
+            be, _ = rec.fw_surrogate(srg, xs, edge)
+    finally:
+        engine.KEPT_FIRST_ORDER = old
+    np.testing.assert_allclose(_np(a), _np(b), atol=3e-3)
+    np.testing.assert_allclose(_np(ae), _np(be), atol=3e-3)
+    np.testing.assert_allclose(_np(a), g["v_s"], atol=2e-2)
+    np.testing.assert_allclose(_np(a).sum(1), 1.0, atol=1e-5)
