@@ -110,6 +110,57 @@ layernorm_reg_kernel(const TIn* __restrict__ x, long long in_stride, int rows, i
   }
 }
 
+// Narrow rows (H = 32 * NV4 <= 128: the LTT side ladders, hidden/8 = 96 for ViT-Base and BERT-base): 8 lanes per row, 4 rows
+// per warp, the row held in registers (NV4 independent 16-byte loads per lane), 3-step shuffles inside the 8-lane group.
+template <typename TIn, int NV4>
+__global__ void __launch_bounds__(256)
+layernorm_narrow_kernel(const TIn* __restrict__ x, long long in_stride, int rows, int H,
+                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                        bf16* __restrict__ out_bf16, float* __restrict__ out_f32, long long out_stride) {
+  const int lane = threadIdx.x & 31, sub = lane & 7;
+  const int row_raw = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4 + (lane >> 3);
+  const bool live = row_raw < rows;
+  const int row = live ? row_raw : rows - 1;         // dead groups redo the last row (shuffles stay full-warp), no store
+  const TIn* xr = x + (long long)row * in_stride;
+  float4 v[NV4];
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) v[i] = load4<TIn>(xr + (i * 8 + sub) * 4);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+  for (int sh = 4; sh >= 1; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
+  const float mean = s / (float)H;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    ss += (a * a + b * b) + (c * c + d * d);
+  }
+#pragma unroll
+  for (int sh = 4; sh >= 1; sh >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, sh);
+  const float rstd = rsqrtf(ss / (float)H + eps);
+  if (!live) return;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const int col = (i * 8 + sub) * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + col));
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * g.x + b.x;
+    o.y = (v[i].y - mean) * rstd * g.y + b.y;
+    o.z = (v[i].z - mean) * rstd * g.z + b.z;
+    o.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + (long long)row * out_stride + col) = o;
+    if (out_bf16) {
+      uint2 pk;
+      pk.x = pack_bf16x2(o.x, o.y);
+      pk.y = pack_bf16x2(o.z, o.w);
+      *reinterpret_cast<uint2*>(out_bf16 + (long long)row * out_stride + col) = pk;
+    }
+  }
+}
+
 template <typename TIn>
 static void launch_layernorm(const TIn* x, long long in_stride, int rows, int H, const float* gamma, const float* beta,
                              float eps, bf16* out_bf16, float* out_f32, long long out_stride, cudaStream_t st) {
@@ -118,6 +169,17 @@ static void launch_layernorm(const TIn* x, long long in_stride, int rows, int H,
 #define AGB_LN(NV4)                                                                                                  \
   layernorm_reg_kernel<TIn, NV4><<<blocks, warps * 32, 0, st>>>(x, in_stride, rows, H, gamma, beta, eps, out_bf16, \
                                                                 out_f32, out_stride)
+  if (H % 32 == 0 && H < 128) {
+    const int nblocks = (rows + warps * 4 - 1) / (warps * 4);
+#define AGB_LNN(NV4)                                                                                                     \
+  layernorm_narrow_kernel<TIn, NV4><<<nblocks, warps * 32, 0, st>>>(x, in_stride, rows, H, gamma, beta, eps, out_bf16, \
+                                                                    out_f32, out_stride)
+    if (H == 32) AGB_LNN(1);
+    else if (H == 64) AGB_LNN(2);
+    else AGB_LNN(3);
+#undef AGB_LNN
+    return;
+  }
   switch ((H % 128 == 0 && H <= 1024) ? H / 128 : 0) {
     case 1: AGB_LN(1); break;
     case 2: AGB_LN(2); break;

@@ -507,10 +507,27 @@ attention_narrow_kernel(const bf16* __restrict__ qkv, const uint32_t* __restrict
   }
 }
 
+int attention_narrow_mma(const bf16* qkv, const uint32_t* mask, int words, int rows, int T, int H, int heads, int mode, bf16* ctx,
+                         cudaStream_t st, const int* cu);
+
+static bool narrow_simt_forced() {
+  static const bool forced = [] {
+    const char* e = getenv("AGB_NARROW_SIMT");
+    return e != nullptr && e[0] != '\0' && e[0] != '0';
+  }();
+  return forced;
+}
+
 template <int D>
 static int launch_attention_narrow(const bf16* qkv, const uint32_t* mask, int words, int rows, int T, int H, int heads,
                                    int mode, bf16* ctx, cudaStream_t st, unsigned drop_thr, unsigned long long drop_seed,
                                    const int* cu = nullptr) {
+  // no dropout (every inference call): the warp-level tensor-core kernel (agb_attention_narrow.cu);
+  // AGB_NARROW_SIMT=1 keeps the CUDA-core kernel for A/B runs
+  if (drop_thr == 0 && !narrow_simt_forced()) {
+    const int rc = attention_narrow_mma(qkv, mask, words, rows, T, H, heads, mode, ctx, st, cu);
+    if (rc != AGB_ERR_UNSUPPORTED) return rc;
+  }
   if (cu != nullptr) words = (T + 31) / 32;     // all-ones key bits, built in shared memory
   const size_t smem = ((size_t)2 * T * D + D + T + 1) * sizeof(float) + (size_t)words * sizeof(uint32_t);
   if (smem > 227 * 1024) return AGB_ERR_UNSUPPORTED;

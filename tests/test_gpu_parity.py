@@ -258,7 +258,7 @@ def test_gemm_f32_exact_mode(agb):
     torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("H", [128, 192, 768, 1024])
+@pytest.mark.parametrize("H", [32, 64, 96, 128, 192, 768, 1024])      # 32 / 64 / 96: the 8-lanes-per-row ladder kernel
 def test_layernorm(agb, H):
     torch.manual_seed(3)
     x = torch.randn(333, H, device=DEV) * 3 + 1
