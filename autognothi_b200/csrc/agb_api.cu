@@ -73,6 +73,7 @@ int layernorm(const void* x, int in_bf16, long long in_stride, int rows, int H, 
               cudaStream_t st);
 int cast_f32_to_bf16(const float* in, bf16* out, long long n, cudaStream_t st);
 int vit_im2col(const float* img, int B, int C, int px, int P, void* out, int out_bf16, cudaStream_t st);
+int repeat_rows(const void* src, int B, long long row_bytes, int S, void* dst, cudaStream_t st);
 int vit_assemble(const float* patch_emb, const float* cls, const float* pos, int B, int S, int T, int H,
                  float* x, cudaStream_t st);
 int bert_embed(const int64_t* ids, const float* word, const float* pos, const float* type0,
@@ -296,6 +297,9 @@ int agb_vit_im2col(const float* images, int B, int C, int px, int P, void* out, 
 int agb_vit_assemble(const float* patch_emb, const float* cls_token, const float* pos_emb, int B,
                      int S, int T, int H, float* x, void* stream) {
   return agb::vit_assemble(patch_emb, cls_token, pos_emb, B, S, T, H, x, ST(stream));
+}
+int agb_repeat_rows(const void* src, int B, long long row_bytes, int S, void* dst, void* stream) {
+  return agb::repeat_rows(src, B, row_bytes, S, dst, ST(stream));
 }
 int agb_bert_embed(const int64_t* ids, const float* word, const float* pos, const float* type0,
                    const float* gamma, const float* beta, float eps, int B, int S, int T, int H,

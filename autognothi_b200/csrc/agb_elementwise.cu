@@ -351,6 +351,34 @@ int vit_assemble(const float* patch_emb, const float* cls, const float* pos, int
 }
 
 // ------------------------------------------------------------------------------------------------
+// Row fan-out: S consecutive copies of every source row (16-byte vectors; one load, S coalesced stores per thread).
+// The first-block sharing path embeds every input once and fans its residual stream out to the S coalition rows here.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+repeat_rows_kernel(const uint4* __restrict__ src, long long total16, long long row16, int S, uint4* __restrict__ dst) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total16) return;
+  const long long b = gid / row16, c = gid - b * row16;
+  const uint4 v = src[gid];
+  uint4* d = dst + b * S * row16 + c;
+#pragma unroll 4
+  for (int s = 0; s < S; ++s) d[(long long)s * row16] = v;
+}
+
+int repeat_rows(const void* src, int B, long long row_bytes, int S, void* dst, cudaStream_t st) {
+  AGB_REQUIRE(B >= 0 && S > 0 && row_bytes > 0 && (row_bytes % 16) == 0, "rows of whole 16-byte vectors");
+  if (B == 0) return AGB_OK;
+  AGB_REQUIRE(src && dst, "null pointer");
+  AGB_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0, "alignment");
+  const long long row16 = row_bytes / 16, total16 = row16 * B;
+  AGB_REQUIRE((total16 + 255) / 256 <= 0x7fffffffLL, "grid limits");
+  repeat_rows_kernel<<<(unsigned)((total16 + 255) / 256), 256, 0, st>>>(static_cast<const uint4*>(src), total16, row16, S,
+                                                                       static_cast<uint4*>(dst));
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // BERT embeddings (reference models/vanilla_bert.py:307-325): LN(word[id] + type[tt] + pos[t]),
 // token_type_ids are all zero on this path (reference recipes/vanilla_bert.py:289).  One warp per
 // token; the normalised row is broadcast to the S coalition rows of its input.

@@ -341,7 +341,7 @@ def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tens
             masks = ops.pack_masks((torch.arange(T - 1, device=order.device)[None, :] < (nkeep[:, None] - 1)).to(torch.int64),
                                    prepend_cls=True)
         else:
-            x3 = x_img.repeat_interleave(S, dim=0)                           # the residual stream of every coalition
+            x3 = ops.repeat_rows(x_img, S)                                   # the residual stream of every coalition
     else:
         x3 = embed(bw, cfg, pol, xs, S)
     assert x3.shape[1] == T, f"sequence length {x3.shape[1]} != n_players + 1 = {T}"

@@ -242,6 +242,21 @@ def vit_assemble(patch_emb: Tensor, cls_token: Tensor, pos_emb: Tensor, B: int, 
     return x
 
 
+def repeat_rows(x: Tensor, S: int) -> Tensor:
+    """(B, ...) -> (B*S, ...): S consecutive copies of every leading-dim slice (torch.repeat_interleave(x, S, 0) as one
+    vectorised kernel: agb_repeat_rows)."""
+    x = _c(x)
+    B = x.shape[0]
+    row_bytes = (x.numel() // B) * x.element_size() if B else 16
+    if S == 1:
+        return x.clone()
+    if row_bytes % 16 != 0 or x.data_ptr() % 16 != 0:
+        return x.repeat_interleave(S, dim=0)
+    out = torch.empty((B * S,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    nat.call("agb_repeat_rows", nat.ptr(x), B, row_bytes, S, nat.ptr(out), nat.stream())
+    return out
+
+
 def bert_embed(ids: Tensor, word: Tensor, pos: Tensor, type_emb: Tensor, gamma: Tensor, beta: Tensor, eps: float,
                S: int) -> Tensor:
     ids = _c(ids)

@@ -143,6 +143,10 @@ int agb_vit_im2col(const float* images, int B, int C, int px, int P, void* out, 
  * models/vanilla_vit.py:242-253; replaces Xs_EXT of scripts/train_explainer.py:159-163). */
 int agb_vit_assemble(const float* patch_emb, const float* cls_token, const float* pos_emb, int B,
                      int S, int T, int H, float* x, void* stream);
+/* S consecutive copies of every source row: dst[(b*S + s)] = src[b], rows of row_bytes (multiple of 16) bytes.
+ * The embedded input of the first-block sharing path fanned out to its S coalition rows on the device (replaces the
+ * Xs_EXT replication loop of reference scripts/train_explainer.py:159-163 at the residual-stream level). */
+int agb_repeat_rows(const void* src, int B, long long row_bytes, int S, void* dst, void* stream);
 /* word + token_type(0) + position embeddings -> LayerNorm, broadcast to S rows per input
  * (reference models/vanilla_bert.py:307-325). ids (B,T) int64. */
 int agb_bert_embed(const int64_t* ids, const float* word, const float* pos, const float* type0,

@@ -173,3 +173,17 @@ def test_kept_first_token_order_is_exact_work_skipping(agb, golden_dir, name):
     np.testing.assert_allclose(_np(ae), _np(be), atol=3e-3)
     np.testing.assert_allclose(_np(a), g["v_s"], atol=2e-2)
     np.testing.assert_allclose(_np(a).sum(1), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("shape,S,dtype", [((3, 197, 768), 32, torch.float32), ((5, 17, 24), 7, torch.bfloat16),
+                                           ((1, 128, 768), 2, torch.float32), ((4, 3, 5), 3, torch.float32),
+                                           ((0, 8, 16), 4, torch.float32)])
+def test_repeat_rows_equals_repeat_interleave(agb, shape, S, dtype):
+    """agb_repeat_rows (the residual stream of an input fanned out to its S coalition rows) is bit-identical to
+    torch.repeat_interleave; rows that are not whole 16-byte vectors take the torch path."""
+    torch.manual_seed(1)
+    x = torch.randn(shape, device=DEV).to(dtype)
+    got = agb.repeat_rows(x, S)
+    assert got.shape == (shape[0] * S,) + shape[1:] and got.dtype == dtype
+    assert torch.equal(got, x.repeat_interleave(S, dim=0))
+    assert got.data_ptr() != x.data_ptr() or x.numel() == 0
