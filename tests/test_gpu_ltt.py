@@ -202,11 +202,16 @@ def test_narrow_head_attention_matches_the_fp32_kernel(agb, T, heads, d, mode):
     """bf16 narrow-head kernel (two queries per thread, online softmax) vs the exact fp32 CUDA-core kernel on the same
     bf16-rounded inputs; mode 0 = ViT (masked logit := 0), 1 = BERT (masked key absent)."""
     torch.manual_seed(T * 7 + d)
-    rows, H = 3, heads * d
+    rows, H = 6, heads * d
     qkv16 = (torch.randn(rows * T, 3 * H, device=DEV) * 1.5).to(torch.bfloat16)
     dense = (torch.rand(rows, T - 1, device=DEV) > 0.4).to(torch.int64)
     dense[0] = 1
     dense[1, : (T - 1) // 2] = 0
+    dense[2] = 0                        # only CLS kept: ViT -> the virtual masked key carries the row, BERT -> ctx = V[CLS]
+    dense[3] = 0
+    dense[3, -min(15, T - 1):] = 1      # CLS + 15 players: exactly one full 16-key block (when T > 16)
+    dense[4] = 0
+    dense[4, : min(16, T - 1)] = 1      # 17 kept keys: a second block with 15 pad keys
     masks = agb.pack_masks(dense, prepend_cls=True)
     ref = agb.masked_attention(qkv16.float().contiguous(), masks, T, heads, mode)
     got = agb.masked_attention(qkv16, masks, T, heads, mode)
