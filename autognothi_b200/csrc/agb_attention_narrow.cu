@@ -38,7 +38,8 @@ template <int D> struct NarrowLayout {
   __host__ __device__ static int tp(int T) { return (T + 15) & ~15; }      // key capacity, whole 16-key blocks
   __host__ __device__ static int vs(int T) { return tp(T) / 2 + 4; }       // V^T row (one head dim): == 4 (mod 8) words
   __host__ __device__ static size_t bytes(int T, int words) {
-    return ((size_t)tp(T) * KS + (size_t)D * vs(T) + D + words) * 4;
+    // the key-bit words are padded to whole 16-byte vectors: the compiler reads them with LDS.128 (sM is 16-byte aligned)
+    return ((size_t)tp(T) * KS + (size_t)D * vs(T) + D + ((words + 3) & ~3)) * 4;
   }
 };
 
@@ -63,13 +64,13 @@ attention_narrow_mma_kernel(const bf16* __restrict__ qkv, const uint32_t* __rest
   uint32_t* sK = sm_nm;                                   // Tp x KS : kept keys, compacted, bf16 pairs
   uint32_t* sVt = sK + Tp * KS;                           // D x VS  : their V rows transposed (word i = keys 2i, 2i+1)
   float* sVm = reinterpret_cast<float*>(sVt + D * VS);    // D       : fp32 sum of the V rows of the ViT-masked keys
-  uint32_t* sM = reinterpret_cast<uint32_t*>(sVm + D);    // words   : key bits of this row (bits >= T cleared)
+  uint32_t* sM = reinterpret_cast<uint32_t*>(sVm + D);    // words (padded to a multiple of 4): key bits of this row, bits >= T cleared
   const long long first = cu != nullptr ? (long long)tok0 : (long long)row * T;
   const bf16* base = qkv + first * 3 * H + head * D;
   const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31;
 
-  for (int e = tid; e < words; e += nthr) {
-    uint32_t w = cu != nullptr ? 0xFFFFFFFFu : mask[(long long)row * words + e];
+  for (int e = tid; e < ((words + 3) & ~3); e += nthr) {  // pad words (whole 16-byte vectors) are zero
+    uint32_t w = e >= words ? 0u : (cu != nullptr ? 0xFFFFFFFFu : mask[(long long)row * words + e]);
     const int live = T - 32 * e;                          // bits of this word that are tokens
     if (live < 32) w = live <= 0 ? 0u : (w & ((1u << live) - 1u));
     sM[e] = w;
