@@ -187,3 +187,21 @@ def test_repeat_rows_equals_repeat_interleave(agb, shape, S, dtype):
     assert got.shape == (shape[0] * S,) + shape[1:] and got.dtype == dtype
     assert torch.equal(got, x.repeat_interleave(S, dim=0))
     assert got.data_ptr() != x.data_ptr() or x.numel() == 0
+
+
+@pytest.mark.parametrize("rows,T,H,C", [(1003, 2, 768, 2), (520, 1, 256, 10)])
+def test_bert_head_rows_per_cta_kernel_is_bit_identical(agb, rows, T, H, C):
+    """>= 512 rows take cls_head_pool_rows_kernel (8 rows per CTA, pooler weight streamed once per 8 rows); the same rows in
+    chunks of < 512 take the one-row kernel.  Same summation order per dot product -> identical bits; also checked
+    against torch (reference models/vanilla_bert.py:73-77, 615-619)."""
+    torch.manual_seed(5)
+    x = torch.randn(rows, T, H, device=DEV)
+    wp, bp = torch.randn(H, H, device=DEV) / H ** 0.5, torch.randn(H, device=DEV) * 0.1
+    wc, bc = torch.randn(C, H, device=DEV) / H ** 0.5, torch.randn(C, device=DEV) * 0.1
+    probs, logits = agb.cls_head(x, 1, wc, bc, pool=(wp, bp), want_logits=True)
+    parts = [agb.cls_head(x[r0:r0 + 500].contiguous(), 1, wc, bc, pool=(wp, bp), want_logits=True) for r0 in range(0, rows, 500)]
+    assert torch.equal(probs, torch.cat([p for p, _ in parts], 0))
+    assert torch.equal(logits, torch.cat([l for _, l in parts], 0))
+    ref = torch.tanh(x[:, 0].double() @ wp.double().t() + bp.double()) @ wc.double().t() + bc.double()
+    torch.testing.assert_close(logits.double(), ref, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(probs.double(), torch.softmax(ref, -1), rtol=1e-4, atol=1e-6)
