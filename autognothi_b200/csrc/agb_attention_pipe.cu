@@ -16,6 +16,8 @@
 // the consumed S columns and used as the A operand FROM TENSOR MEMORY of the second MMA; the row sum is
 // accumulated in fp32 registers (key padding and, for BERT, masked keys are forced to P = 0 = "finfo.min
 // additive mask", so neither numerator nor denominator sees them).
+#include <stdlib.h>
+
 #include "agb_common.cuh"
 
 namespace agb {
@@ -52,6 +54,7 @@ struct AttPipeParams {
   unsigned drop_thr;
   unsigned long long drop_seed;
   float drop_scale;  // 1 / (1 - p)
+  int softmax_pipe;  // 1: software-pipelined TMEM loads over the unmasked key region (AGB_ATTN_SOFTMAX_PIPE, A/B switch)
 };
 
 #define AP_TRACE(k, slot)                                                             \
@@ -118,6 +121,68 @@ __device__ __forceinline__ float ap_exp_chunk(uint32_t s_addr, uint32_t p_addr, 
   if (W == 64) tmem_st32(p_addr, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
   else         tmem_st8(p_addr, *reinterpret_cast<uint32_t(*)[8]>(&pk[0]));
   return (sum0 + sum1) + (sum2 + sum3);
+}
+
+// ---- software-pipelined unmasked region [0, n_fast) (n_fast % 64 == 0): 32-column halves in two register buffers, the
+// tcgen05.ld of the next half in flight while the current one is reduced / exponentiated (the serial ld -> wait -> use of
+// the 64-column chunks left the softmax warps in long_scoreboard: profiles/r01_layer_ncu_full_end.txt) --------------
+__device__ __forceinline__ float ap_max32(const uint32_t (&s)[32], float m) {
+  float m0 = m, m1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    m0 = fmaxf(m0, __uint_as_float(s[j]));
+    m1 = fmaxf(m1, __uint_as_float(s[j + 1]));
+  }
+  return fmaxf(m0, m1);
+}
+
+__device__ __forceinline__ float ap_max_fast(uint32_t addr, int n_fast, float m) {
+  uint32_t a[32], b[32];
+  tmem_ld32(addr, a);
+  tmem_wait_ld_dep32(a);
+  for (int c = 0; c < n_fast; c += 64) {
+    tmem_ld32(addr + c + 32, b);
+    m = ap_max32(a, m);
+    tmem_wait_ld_dep32(b);
+    tmem_ld32(addr + min(c + 64, n_fast - 32), a);      // branch-free: the last iteration re-reads the final half
+    m = ap_max32(b, m);
+    tmem_wait_ld_dep32(a);
+  }
+  return m;
+}
+
+__device__ __forceinline__ void ap_exp32(const uint32_t (&s)[32], uint32_t (&pk)[16], float scale_log2, float m_scaled,
+                                         float (&sum)[4]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float e0 = ex2_approx(fmaf(__uint_as_float(s[2 * j]), scale_log2, -m_scaled));
+    const float e1 = ex2_approx(fmaf(__uint_as_float(s[2 * j + 1]), scale_log2, -m_scaled));
+    sum[(j & 1) * 2] += e0;
+    sum[(j & 1) * 2 + 1] += e1;
+    pk[j] = pack_bf16x2(e0, e1);
+  }
+}
+
+// P (bf16 pairs) overlays S columns that are already in registers: the pairs of columns [c, c + 32) go to [c / 2, c / 2 + 16),
+// always below the half whose load is in flight
+__device__ __forceinline__ float ap_exp_fast(uint32_t s_addr, uint32_t p_addr, int n_fast, float scale_log2, float m_scaled) {
+  uint32_t a[32], b[32], pk[16];
+  float sum[4] = {0.f, 0.f, 0.f, 0.f};
+  tmem_ld32(s_addr, a);
+  tmem_wait_ld_dep32(a);
+  for (int c = 0; c < n_fast; c += 64) {
+    tmem_ld32(s_addr + c + 32, b);
+    ap_exp32(a, pk, scale_log2, m_scaled, sum);
+    tmem_st16(p_addr + (c >> 1), pk);
+    tmem_wait_ld_dep32(b);
+    // branch-free prefetch; in the last iteration there is nothing left to fetch: read the (unused) columns of this
+    // chunk's second half again — NOT columns P has already overwritten
+    tmem_ld32(s_addr + min(c + 64, n_fast - 32), a);
+    ap_exp32(b, pk, scale_log2, m_scaled, sum);
+    tmem_wait_ld_dep32(a);
+    tmem_st16(p_addr + (c >> 1) + 16, pk);
+  }
+  return (sum[0] + sum[1]) + (sum[2] + sum[3]);
 }
 
 // live-column bits of the W-wide chunk starting at key c0: key < T, and (BERT) coalition bit set
@@ -397,6 +462,10 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         // pass 1: row maximum
         float mx = -INFINITY;
         int c0 = 0;
+        if (p.softmax_pipe && n_fast > 0) {
+          mx = ap_max_fast(lane_addr, n_fast, mx);
+          c0 = n_fast;
+        }
         for (; c0 < n_fast; c0 += 64) mx = ap_max_chunk<64, false>(lane_addr + c0, mx, 0u, 0u);
         for (; c0 + 64 <= NKu; c0 += 64) {
           uint32_t lo, hi;
@@ -413,6 +482,10 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         float sum = 0.f;
         c0 = 0;
         const uint32_t dkey = DROP ? agb_drop_key(p.drop_seed, (uint32_t)u, (uint32_t)(m * 128 + r)) : 0u;
+        if (!DROP && p.softmax_pipe && n_fast > 0) {
+          sum += ap_exp_fast(lane_addr, lane_addr, n_fast, scale_log2, m_scaled);
+          c0 = n_fast;
+        }
         for (; c0 < n_fast; c0 += 64)
           sum += ap_exp_chunk<64, false, DROP>(lane_addr + c0, lane_addr + (c0 >> 1), scale_log2, m_scaled, 0u, 0u, dkey,
                                                c0 >> 1, p.drop_thr);
@@ -484,6 +557,11 @@ static int attention_pipe_launch(const bf16* qkv, const uint32_t* mask, int word
   p.drop_thr = drop_thr;
   p.drop_seed = drop_seed;
   p.drop_scale = 65536.0f / (65536.0f - (float)drop_thr);
+  static const int softmax_pipe = [] {
+    const char* e = getenv("AGB_ATTN_SOFTMAX_PIPE");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  p.softmax_pipe = softmax_pipe;
   p.mask = mask; p.words = words; p.rows = rows; p.T = T; p.H = H; p.heads = heads; p.mode = mode;
   p.NK = (T + 15) / 16 * 16;
   p.units = rows * heads;
