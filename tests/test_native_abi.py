@@ -52,6 +52,14 @@ def test_invalid_arguments_are_rejected_without_a_gpu(built):
     assert rc == 1
     rc = lib.agb_masked_attention_bf16(None, None, 19, 1, 600, 768, 12, 0, None, None)
     assert rc == 3  # AGB_ERR_UNSUPPORTED: T > 256 belongs to the CUDA-core kernel
+    # row fan-out: rows must be whole 16-byte vectors, S positive, pointers non-null; an empty batch is a no-op
+    lib.agb_repeat_rows.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    assert lib.agb_repeat_rows(None, 2, 24, 4, None, None) == 1 and b"16-byte" in lib.agb_last_error()
+    assert lib.agb_repeat_rows(None, 2, 32, 0, None, None) == 1
+    assert lib.agb_repeat_rows(None, 2, 32, 4, None, None) == 1 and b"null" in lib.agb_last_error()
+    assert lib.agb_repeat_rows(None, 0, 32, 4, None, None) == 0
+    # narrow-head attention (side ladders) validates its shape before touching the device
+    assert lib.agb_masked_attention_simt(None, 1, None, 1, 2, 40, 96, 12, 0, None, None) == 1    # 1 mask word < 40 tokens
 
 
 def test_product_never_imports_the_oracle():
