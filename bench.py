@@ -122,11 +122,96 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle port of the reference's CPU path
+# reference arm / cpu_baseline: the UNMODIFIED reference (oracle/_ref, placed by oracle/make_ref.py) on the host cores;
+# the numpy port under oracle/ only when the reference files are not there
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step(sd, cfgd, xs_np, S, rng):
-    """What reference scripts/train_explainer.py:153-171 does per batch on CPU: sample the coalitions, replicate
-    each input S times (Xs_EXT), evaluate the masked surrogate."""
+def _force_host_threads():
+    """All host cores for torch's CPU kernels, also under torchrun (which exports OMP_NUM_THREADS=1)."""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    return cores
+
+
+class ReferenceCPU:
+    """The reference's own CPU path for one model config: random-init reference modules (seed 3407, the checked-in seed),
+    and the loop bodies of reference scripts/train_explainer.py:148-171 (masked surrogate evaluation) and
+    scripts/measure_train_resources.py:208-258 (`_explainer_batch_train`, called unmodified) + optimizer.step()."""
+
+    def __init__(self, cfgd):
+        import torch
+        from oracle.make_ref import import_reference
+        got = import_reference()
+        if got is None:
+            raise FileNotFoundError("oracle/_ref/reference missing (python oracle/make_ref.py) and no /root/reference")
+        self.pkg, mod, self.where = got
+        self.torch = torch
+        self.cores = _force_host_threads()
+        self.shapley = mod("models.shapley")
+        mvit = mod("models.vanilla_vit")
+        self.rec = mod("recipes.vanilla_vit").vanilla_vit_recipe()
+        self.mod = mod
+        torch.manual_seed(3407)
+        self.cfg = mvit.VanillaViTConfig(**cfgd)
+        self.surrogate = mvit.VanillaViTSurrogate(self.cfg).eval()
+        self.n = self.rec.n_players(self.cfg)
+        self.dev = torch.device("cpu")
+        self._train = None
+
+    def eval_step(self, xs, S):
+        """reference scripts/train_explainer.py:148-171, verbatim order: CPU mask sampling, Xs_EXT, fw_surrogate under no_grad"""
+        torch = self.torch
+        batch_size = xs.shape[0]
+        masks = self.shapley.mask_shapley_new(batch_size * S, self.n).to(self.dev)
+        xs_ext = []
+        for b in range(batch_size):
+            for _ in range(S):
+                xs_ext.append(xs[b])
+        xs_ext = torch.stack(xs_ext, dim=0)
+        self.surrogate.eval()
+        with torch.no_grad():
+            values, _ = self.rec.fw_surrogate(self.surrogate, xs_ext, masks)
+        return values
+
+    def time_eval(self, images, S, steps, warmup):
+        torch = self.torch
+        xs = torch.randn((images, 3, 224, 224), generator=torch.Generator().manual_seed(1234))
+        for _ in range(warmup):
+            self.eval_step(xs, S)
+        times = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            self.eval_step(xs, S)
+            times.append(time.perf_counter() - t0)
+        return images * S * len(times) / sum(times), sum(times) / len(times)
+
+    def time_train(self, images, S, steps, warmup):
+        """One explainer training step per `step`: the reference's `_explainer_batch_train` (mask sampling, S + 1 surrogate
+        evaluations per image, explainer fwd/bwd in train() mode = dropout p = 0.1 as configured) + AdamW step."""
+        torch = self.torch
+        mtr = self.mod("scripts.measure_train_resources")
+        if self._train is None:
+            explainer = self.rec.conv_surrogate_explainer(self.cfg, None, self.surrogate)
+            opt = torch.optim.AdamW(explainer.parameters(), lr=5e-5)
+            with torch.no_grad():
+                null, _ = self.rec.fw_surrogate(self.surrogate, self.rec.gen_null(self.cfg, None, self.dev),
+                                                torch.ones((1, self.n), dtype=torch.long))
+            self._train = (explainer, opt, null)
+        explainer, opt, null = self._train
+        xs = torch.randn((images, 3, 224, 224), generator=torch.Generator().manual_seed(4321))
+        times = []
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            loss = mtr._explainer_batch_train(self.dev, S, self.n, null, self.rec, self.surrogate, explainer, opt, xs)
+            opt.step()
+            float(loss)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+        return images * len(times) / sum(times), sum(times) / len(times)
+
+
+def cpu_port_step(sd, cfgd, xs_np, S, rng):
+    """Fallback when the reference files are absent: the numpy port (oracle/) of reference scripts/train_explainer.py:153-171."""
     import numpy as np
     from oracle import configs as ocfg
     from oracle import shapley as osh
@@ -140,7 +225,7 @@ def cpu_reference_step(sd, cfgd, xs_np, S, rng):
     return otr.fw_surrogate(sd, cfgd, xs_ext, masks)
 
 
-def time_cpu_reference(images: int, S: int, steps: int, warmup: int):
+def time_cpu_port(images: int, S: int, steps: int, warmup: int):
     import numpy as np
     from oracle import configs as ocfg
     from oracle import synth
@@ -149,32 +234,69 @@ def time_cpu_reference(images: int, S: int, steps: int, warmup: int):
     xs = synth.inputs(cfgd, images, seed=0)
     rng = np.random.default_rng(3407)
     for _ in range(warmup):
-        cpu_reference_step(sd, cfgd, xs, S, rng)
+        cpu_port_step(sd, cfgd, xs, S, rng)
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        cpu_reference_step(sd, cfgd, xs, S, rng)
+        cpu_port_step(sd, cfgd, xs, S, rng)
         times.append(time.perf_counter() - t0)
     return images * S * len(times) / sum(times), sum(times) / len(times)
+
+
+def cpu_baseline(cfgd, steps, warmup, with_train=True):
+    """-> cpu_baseline object (+ train leg) for the ViT config `cfgd`: reference when importable, else the port."""
+    images, S = 1, S_COALITIONS
+    cores = os.cpu_count() or 1
+    try:
+        ref = ReferenceCPU(cfgd)
+    except Exception as exc:          # reference files not shipped: numpy port, and say so
+        v, sec = time_cpu_port(images, 16, max(1, min(steps, 3)), 1)
+        return {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": sec * 1e3,
+                "sample": f"1 image x 16 coalitions per step, numpy/OpenBLAS fp32 port (oracle/): reference unavailable ({exc})"}, None
+    v, sec = ref.time_eval(images, S, steps, warmup)
+    out = {"value": v, "unit": UNIT, "cores": ref.cores, "kind": "reference", "ms_per_step": sec * 1e3,
+           "sample": f"{images} image x {S} coalitions = {images * S} masked evals per step ({steps} timed steps after {warmup} warm-up), "
+                     f"the unmodified reference on torch CPU fp32 ({ref.cores} threads): models/shapley.py::mask_shapley_new + Xs_EXT "
+                     "+ recipes/vanilla_vit.py::fw_surrogate exactly as scripts/train_explainer.py:148-171"}
+    train = None
+    if with_train:
+        tv, tsec = ref.time_train(1, S, max(1, min(steps, 2)), 1)
+        train = {"value": tv, "unit": "samples/s", "cores": ref.cores, "kind": "reference", "ms_per_step": tsec * 1e3,
+                 "sample": f"1 image x {S} coalitions per step: reference scripts/measure_train_resources.py::_explainer_batch_train "
+                           "(unmodified; train() mode, dropout p=0.1) + AdamW step, torch CPU fp32"}
+    return out, train
+
+
+def our_config(workload, model_name, B, S, world):
+    return {"workload": workload, "surrogate": f"{model_name} (random init, seed 3407)",
+            "images_per_gpu_per_step": B, "coalitions_per_image": S, "evals_per_gpu_per_step": B * S,
+            "parallelism": f"dp{world} (images sharded, final all_gather of probabilities)",
+            "l2": "activations per step (>3 GB) exceed L2 (126 MB); no explicit flush"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    images, S = 1, 16   # bounded sample of the workload: 16 masked ViT-B evals (~0.56 TFLOP) per step
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
-    value, sec = time_cpu_reference(images, S, steps, warmup)
-    sample = f"{images} image x {S} coalitions per step, fp32 numpy/OpenBLAS port of the reference CPU path (oracle/), {steps} steps"
+    if args.workload != "vit":
+        return run_reference_side(args)
+    workload, model_name, model_cfg = MODELS[args.model]
+    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 2))
+    if args.model != "vit_base":
+        steps = min(steps, 4)
+    base, train = cpu_baseline(dict(model_cfg), steps, warmup, with_train=not args.no_train)
+    value, sec = base["value"], base["ms_per_step"] * 1e-3
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "gpu_launches": 0,
-        "config": {"workload": WORKLOAD, "images_per_step": images, "coalitions_per_image": S},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        # the same workload as our arm; each reference step is a bounded sample of it (cpu_baseline.sample)
+        "config": our_config(workload, model_name, args.images, S_COALITIONS, max(1, args.gpus)),
+        "cpu_baseline": base,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if train is not None:
+        line["train"] = dict(train, metric="explainer_train_samples_per_sec")
     print(json.dumps(line), flush=True)
 
 
@@ -217,13 +339,28 @@ def run_ours(args):
     images_dev = torch.randn((B, 3, 224, 224), device=dev, generator=g)
     images_host = torch.randn((B, 3, 224, 224)).pin_memory()
     C = cfg.num_labels
-    gathered = [torch.empty((rows, C), device=dev) for _ in range(world)] if world > 1 else None
+    # "only a final gather" (SURVEY.md §8e): every step's probabilities are gathered to all ranks, but ASYNCHRONOUSLY — the
+    # NCCL all-gather of step i runs on NCCL's own stream while the kernels of steps i+1, i+2 run, so no rank's compute
+    # waits for a slower (power-capped) neighbour inside the loop; the timed region ends only after every gather has landed
+    GATHER_DEPTH = 2
+    gathered = [torch.empty((world * rows, C), device=dev) for _ in range(GATHER_DEPTH + 1)] if world > 1 else None
+    pending = []
+
+    def gather_async(i, probs):
+        if world == 1:
+            return
+        while len(pending) >= GATHER_DEPTH:
+            pending.pop(0).wait()
+        pending.append(dist.all_gather_into_tensor(gathered[i % (GATHER_DEPTH + 1)], probs.contiguous(), async_op=True))
+
+    def drain():
+        while pending:
+            pending.pop(0).wait()
 
     def step_resident(i):
         pm = ash.mask_shapley_new(rows, n, device=dev, rng="philox", seed=3407 + rank, offset=i * rows, packed=True)
         probs, _ = rec.fw_surrogate(surrogate, images_dev, pm)
-        if world > 1:
-            dist.all_gather(gathered, probs)      # "only a final gather" 
+        gather_async(i, probs)
         return probs
 
     # End-to-end leg: every step copies ITS OWN input batch host->device from pinned memory and reads ITS OWN
@@ -291,6 +428,7 @@ def run_ours(args):
     def timed(fn, steps, warmup, profile=False):
         for i in range(warmup):
             fn(i)
+        drain()
         barrier()
         l0 = nat.LAUNCHES
         nat.PROFILE = [] if profile else None
@@ -298,6 +436,7 @@ def run_ours(args):
         e0.record()
         for i in range(steps):
             fn(warmup + i)
+        drain()
         e1.record()
         barrier()
         prof, nat.PROFILE = nat.PROFILE, None
@@ -392,8 +531,7 @@ def run_ours(args):
             pm = ash.mask_shapley_new(rows, n, device=dev, rng="philox", seed=777 + rank, offset=i * rows, packed=True)
             with torch.no_grad():
                 side, _ = lrec.fw_surrogate(lsrg, images_dev, pm)
-            if world > 1:
-                dist.all_gather(gathered, side)
+            gather_async(i, side)
             return side
 
         def step_ltt_train(i):
@@ -481,21 +619,15 @@ def run_ours(args):
                               "computed once per image instead of once per coalition"}
 
     if rank == 0:
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline and args.model == "vit_base":
-            cores = os.cpu_count() or 1
-            v, _ = time_cpu_reference(1, 16, 2, 1)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "1 image x 16 coalitions per step (16 masked ViT-B/16 evals), numpy/OpenBLAS fp32 port of the "
-                             "reference CPU path incl. CPU mask sampling and Xs_EXT replication, 2 timed steps after 1 warm-up"}
+        cpu = cpu_train = None
+        if world == 1 and not args.no_cpu_baseline:
+            # bounded sample on the host cores AFTER the GPU legs (nothing of it is inside a timed GPU region)
+            cpu, cpu_train = cpu_baseline(cfgd, 3 if args.model == "vit_base" else 1, 1, with_train=(train is not None))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload, "surrogate": f"{model_name} (random init, seed 3407)",
-                       "images_per_gpu_per_step": B, "coalitions_per_image": S, "evals_per_gpu_per_step": rows,
-                       "parallelism": f"dp{world} (images sharded, final all_gather of probabilities)",
-                       "l2": "activations per step (>3 GB) exceed L2 (126 MB); no explicit flush"},
+            "config": our_config(workload, model_name, B, S, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": images_host.numel() * 4,
                     "d2h_bytes_per_step": rows * C * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "whole_path": whole,
@@ -506,6 +638,8 @@ def run_ours(args):
             line["ltt"] = ltt
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if cpu_train is not None and train is not None:
+            train["cpu_baseline"] = cpu_train
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -519,6 +653,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--images", type=int, default=32, help="images per GPU per step (x32 coalitions each)")
     ap.add_argument("--model", default="vit_base", choices=sorted(MODELS), help="vit_base = the metric's config (default)")
+    ap.add_argument("--workload", default="vit", choices=["vit", "bert_base_tayp_vanilla", "bert_base_tayp_kernel_shap"],
+                    help="vit = the metric's own configuration (default, BASELINE.json configs[1] / configs[4] with --model "
+                         "vit_large); the other two are BASELINE.json configs[2] and configs[3] as side workloads")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the explainer-training leg")
     ap.add_argument("--no-ltt", action="store_true", help="skip the ladder-side-tuning leg")
@@ -529,6 +666,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "vit":
+        run_ours_side(args)
     else:
         run_ours(args)
 

@@ -76,6 +76,10 @@ CONFIGS: Dict[str, Dict[str, Any]] = {
     "bert_base_128": _bert(768, 12, 12, 3072, 3072, max_pos=128),
     "bert_base_512": _bert(768, 12, 12, 3072, 3072, max_pos=512),
 }
+# the same ViT-Base/16 configuration under a second fixture name: 4 inputs x 32 coalitions = 128 rows (M = 25 216 token rows),
+# the smallest shape at which the bench's own kernel variants engage (CTA-pair GEMMs, LayerNorm-folded chain, first-block
+# sharing, CLS-only last block) — tests/golden/model_vit_base_b4s32.npz, train_vit_base_b4s32.npz
+CONFIGS["vit_base_b4s32"] = CONFIGS["vit_base"]
 # LTT (ladder side tuning) variants; side head dim = s_attn_hidden_size / num_attention_heads
 CONFIGS.update({
     "ltt_vit_mini": _ltt(CONFIGS["vit_mini"], 32, 64, 48),                 # side head dim 16

@@ -111,6 +111,7 @@ MODEL_CASES = [
     ("vit_mini_px64", 3, 4),
     ("vit_tiny", 2, 4),
     ("vit_base", 1, 2),
+    ("vit_base_b4s32", 4, 32),     # the bench's kernel variants (>= 128 rows): see oracle/configs.py
     ("vit_large", 1, 2),
     ("bert_mini", 3, 4),
     ("bert_base_128", 1, 2),
@@ -172,9 +173,12 @@ def gen_models(only=None):
 def gen_train_grads(only=None):
     """One explainer training step's loss and parameter gradients from the reference's autograd
     (scripts/train_explainer.py:182-197 semantics), in eval() mode so that dropout is the identity."""
-    for name, B, S in [("vit_mini", 2, 4), ("vit_mini_px64", 3, 4), ("bert_mini", 3, 4), ("bert_mini_512", 2, 2)]:
+    for name, B, S in [("vit_mini", 2, 4), ("vit_mini_px64", 3, 4), ("bert_mini", 3, 4), ("bert_mini_512", 2, 2),
+                       ("vit_base_b4s32", 4, 32)]:
         if only and name not in only:
             continue
+        if not only and name == "vit_base_b4s32":
+            continue        # minutes of CPU time: generated on request (`make_golden.py train vit_base_b4s32`)
         cfg = ocfg.get_config(name)
         vit = ocfg.is_vit(cfg)
         n = ocfg.n_players(cfg)
@@ -203,9 +207,15 @@ def gen_train_grads(only=None):
         for k, p_ in exp.named_parameters():
             gr = p_.grad
             norms[k] = float(gr.norm()) if gr is not None else 0.0
-            if gr is not None and (gr.numel() <= 1024 or "layers.0.attention.self.query.weight" in k
-                                   or "explainer_attn.0.output.dense.weight" in k):
+            if gr is not None and (gr.numel() <= 1024 or ((("layers.0.attention.self.query.weight" in k
+                                   or "explainer_attn.0.output.dense.weight" in k)) and gr.numel() <= 65536)):
                 out["grad::" + k] = gr.numpy()
+            elif gr is not None and name == "vit_base_b4s32":
+                # full-size model: every large tensor is pinned by a strided sample of <= 2048 elements (relative L2 on the
+                # sample estimates the tensor's), so that the fixture stays small
+                flat = gr.reshape(-1)
+                step = max(1, flat.numel() // 2048)
+                out["sample::" + k] = flat[::step][:2048].numpy().copy()
         out["norm_names"] = np.array(list(norms.keys()))
         out["norm_values"] = np.array(list(norms.values()), dtype=np.float64)
         np.savez_compressed(os.path.join(HERE, f"train_{name}.npz"), **out)
