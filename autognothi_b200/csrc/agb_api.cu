@@ -74,6 +74,12 @@ int layernorm(const void* x, int in_bf16, long long in_stride, int rows, int H, 
 int cast_f32_to_bf16(const float* in, bf16* out, long long n, cudaStream_t st);
 int vit_im2col(const float* img, int B, int C, int px, int P, void* out, int out_bf16, cudaStream_t st);
 int repeat_rows(const void* src, int B, long long row_bytes, int S, void* dst, cudaStream_t st);
+int kept_first_order(const uint32_t* packed, int rows, int words, int T, uint8_t* order, uint8_t* pos, int* nkeep,
+                     uint32_t* prefix, cudaStream_t st);
+int gather_token_rows(const void* src, const uint8_t* order, int rows, int T, int S, long long row_bytes, void* dst,
+                      cudaStream_t st);
+int attention_scatter(const bf16* qkv, const uint32_t* mask, int words, int rows, int share, int T, int H, int heads,
+                      const uint8_t* dst_pos, bf16* ctx, cudaStream_t stream);
 int vit_assemble(const float* patch_emb, const float* cls, const float* pos, int B, int S, int T, int H,
                  float* x, cudaStream_t st);
 int bert_embed(const int64_t* ids, const float* word, const float* pos, const float* type0,
@@ -300,6 +306,19 @@ int agb_vit_assemble(const float* patch_emb, const float* cls_token, const float
 }
 int agb_repeat_rows(const void* src, int B, long long row_bytes, int S, void* dst, void* stream) {
   return agb::repeat_rows(src, B, row_bytes, S, dst, ST(stream));
+}
+int agb_kept_first_order(const uint32_t* packed, int rows, int words, int T, uint8_t* order, uint8_t* pos, int* nkeep,
+                         uint32_t* prefix, void* stream) {
+  return agb::kept_first_order(packed, rows, words, T, order, pos, nkeep, prefix, ST(stream));
+}
+int agb_gather_token_rows(const void* src, const uint8_t* order, int rows, int T, int S, long long row_bytes, void* dst,
+                          void* stream) {
+  return agb::gather_token_rows(src, order, rows, T, S, row_bytes, dst, ST(stream));
+}
+int agb_masked_attention_bf16_scatter(const void* qkv, const uint32_t* mask, int words, int rows, int share, int T, int H,
+                                      int heads, const uint8_t* dst_pos, void* ctx, void* stream) {
+  return agb::attention_scatter(static_cast<const bf16*>(qkv), mask, words, rows, share, T, H, heads, dst_pos,
+                                static_cast<bf16*>(ctx), ST(stream));
 }
 int agb_bert_embed(const int64_t* ids, const float* word, const float* pos, const float* type0,
                    const float* gamma, const float* beta, float eps, int B, int S, int T, int H,

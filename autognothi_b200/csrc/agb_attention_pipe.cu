@@ -544,7 +544,11 @@ attention_pipe_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
 static long long* g_attention_trace = nullptr;
 void set_attention_trace(long long* t) { g_attention_trace = t; }
-static int g_attention_variant = 0;   // 0 auto (pipelined), 1 first-generation kernel
+long long* get_attention_trace() { return g_attention_trace; }
+// 0 auto (split-softmax kernel where it applies, else the pipelined one), 1 first-generation kernel, 2 pipelined kernel
+static int g_attention_variant = 0;
+int attention_split(const bf16* qkv, const uint32_t* mask, int words, int rows, int share, int T, int H, int heads,
+                    const int* nkeep, const uint8_t* dst_pos, bf16* ctx, cudaStream_t stream);
 void set_attention_variant(int v) { g_attention_variant = v; }
 int get_attention_variant() { return g_attention_variant; }
 
@@ -643,7 +647,26 @@ static int attention_pipe_launch(const bf16* qkv, const uint32_t* mask, int word
 int attention_pipe(const bf16* qkv, const uint32_t* mask, int words, int rows, int share, int T, int H, int heads,
                    int mode, bf16* ctx, cudaStream_t stream) {
   if (g_attention_variant == 1) return AGB_ERR_UNSUPPORTED;
+  if ((g_attention_variant == 0 || g_attention_variant == 3) && mode == AGB_MASK_MUL0) {     // third generation (agb_attention_split.cu): T <= 208
+    const int rc = attention_split(qkv, mask, words, rows, share, T, H, heads, nullptr, nullptr, ctx, stream);
+    if (rc != AGB_ERR_UNSUPPORTED) return rc;
+  }
   return attention_pipe_launch(qkv, mask, words, rows, share, T, H, heads, mode, ctx, nullptr, 0, stream);
+}
+
+// ViT-masked attention whose output rows are written in another token order: query token t of row r goes to position
+// dst_pos[r, t] (the first block of the kept-first evaluation order: projections shared per input, output per coalition)
+int attention_scatter(const bf16* qkv, const uint32_t* mask, int words, int rows, int share, int T, int H, int heads,
+                      const uint8_t* dst_pos, bf16* ctx, cudaStream_t stream) {
+  AGB_REQUIRE(share >= 1 && rows % share == 0, "share must divide the number of mask rows");
+  AGB_REQUIRE(rows >= 0 && T > 0 && T <= 256 && heads > 0 && H == heads * AP_D, "scatter attention shape (head dim 64, T <= 256)");
+  AGB_REQUIRE(words * 32 >= T, "mask words");
+  if (rows == 0) return AGB_OK;
+  AGB_REQUIRE(qkv && mask && ctx && dst_pos, "null pointer");
+  AGB_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(ctx) & 15) == 0, "alignment");
+  const int rc = attention_split(qkv, mask, words, rows, share, T, H, heads, nullptr, dst_pos, ctx, stream);
+  if (rc == AGB_ERR_UNSUPPORTED) set_last_error("scatter attention: T <= 208 (T = %d)", T);
+  return rc;
 }
 
 // ViT-masked attention on rows whose tokens were permuted so that the kept ones come first (nkeep[row] of them, CLS
@@ -653,6 +676,13 @@ int attention_pipe_prefix(const bf16* qkv, const int* nkeep, int rows, int T, in
   if (rows == 0) return AGB_OK;
   AGB_REQUIRE(qkv && nkeep && ctx, "null pointer");
   AGB_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(ctx) & 15) == 0, "alignment");
+  // kept-first order: the second-generation kernel stays the default (396 vs 418 us at the bench shape: with few live keys
+  // an item is bound by its fixed hand-off latencies, which the 16-warp split kernel has more of —
+  // profiles/r02_attention_split_notes.txt); variant 3 selects the split kernel for A/B runs
+  if (g_attention_variant == 3) {
+    const int rc = attention_split(qkv, nullptr, 0, rows, 1, T, H, heads, nkeep, nullptr, ctx, stream);
+    if (rc != AGB_ERR_UNSUPPORTED) return rc;
+  }
   return attention_pipe_launch(qkv, nullptr, 0, rows, 1, T, H, heads, AGB_MASK_MUL0, ctx, nullptr, 0, stream, 0, 0, nkeep);
 }
 

@@ -379,6 +379,89 @@ int repeat_rows(const void* src, int B, long long row_bytes, int S, void* dst, c
 }
 
 // ------------------------------------------------------------------------------------------------
+// Kept-first token order of every (input, coalition) row (ViT "logit := 0" masks, surrogate evaluation): a stable
+// partition of the tokens into kept (bit set; CLS = bit 0 always is) and masked ones.  One warp per row:
+//   order[r, q]  = token at position q          pos[r, t] = position of token t          nkeep[r] = kept tokens
+//   prefix[r, :] = packed mask of the permuted row (bits [0, nkeep) set)
+// Everything between the attentions is token-wise and attention is permutation-equivariant, so evaluating the permuted
+// rows leaves the CLS output unchanged; the attention kernels then see the masked keys as one contiguous tail.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+kept_first_order_kernel(const uint32_t* __restrict__ packed, int rows, int words, int T, uint8_t* __restrict__ order,
+                        uint8_t* __restrict__ pos, int* __restrict__ nkeep, uint32_t* __restrict__ prefix) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t* m = packed + (long long)r * words;
+  const int nw = (T + 31) >> 5;
+  int total = 0;
+  for (int w = 0; w < nw; ++w) {
+    uint32_t bits = __ldg(m + w);
+    if (w == 0) bits |= 1u;                                   // CLS is always kept
+    if ((w + 1) * 32 > T) bits &= (T & 31) ? ((1u << (T & 31)) - 1u) : 0xFFFFFFFFu;
+    total += __popc(bits);
+  }
+  int kept_before = 0;
+  for (int w = 0; w < nw; ++w) {
+    uint32_t bits = __ldg(m + w);
+    if (w == 0) bits |= 1u;
+    if ((w + 1) * 32 > T) bits &= (T & 31) ? ((1u << (T & 31)) - 1u) : 0xFFFFFFFFu;
+    const int t = w * 32 + lane;
+    if (t < T) {
+      const int kb = kept_before + __popc(bits & ((1u << lane) - 1u));
+      const bool kept = (bits >> lane) & 1u;
+      const int q = kept ? kb : total + (t - kb);             // masked tokens follow the kept ones, in token order
+      order[(long long)r * T + q] = (uint8_t)t;
+      pos[(long long)r * T + t] = (uint8_t)q;
+    }
+    kept_before += __popc(bits);
+  }
+  if (lane == 0) nkeep[r] = total;
+  for (int w = lane; w < words; w += 32) {
+    const int lo = w * 32;
+    prefix[(long long)r * words + w] = total >= lo + 32 ? 0xFFFFFFFFu : (total > lo ? ((1u << (total - lo)) - 1u) : 0u);
+  }
+}
+
+int kept_first_order(const uint32_t* packed, int rows, int words, int T, uint8_t* order, uint8_t* pos, int* nkeep,
+                     uint32_t* prefix, cudaStream_t st) {
+  AGB_REQUIRE(rows >= 0 && T > 0 && T <= 256 && words * 32 >= T, "kept-first order: T <= 256 tokens");
+  if (rows == 0) return AGB_OK;
+  AGB_REQUIRE(packed && order && pos && nkeep && prefix, "null pointer");
+  kept_first_order_kernel<<<(rows + 7) / 8, 256, 0, st>>>(packed, rows, words, T, order, pos, nkeep, prefix);
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+// dst[(r, q), :] = src[(r / S, order[r, q]), :]: the residual stream of every coalition row in kept-first token order,
+// gathered from the per-input embeddings (replaces repeat_rows on that path)
+__global__ void __launch_bounds__(256)
+gather_token_rows_kernel(const uint4* __restrict__ src, const uint8_t* __restrict__ order, long long total16, int row16, int T,
+                         int S, uint4* __restrict__ dst) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= total16) return;
+  const long long tok = gid / row16;                           // destination token row = r * T + q
+  const int c = (int)(gid - tok * row16);
+  const long long r = tok / T;
+  const int t = order[tok];
+  dst[gid] = __ldg(src + ((r / S) * T + t) * row16 + c);
+}
+
+int gather_token_rows(const void* src, const uint8_t* order, int rows, int T, int S, long long row_bytes, void* dst,
+                      cudaStream_t st) {
+  AGB_REQUIRE(rows >= 0 && T > 0 && S > 0 && rows % S == 0 && row_bytes > 0 && (row_bytes % 16) == 0, "gather_token_rows shape");
+  if (rows == 0) return AGB_OK;
+  AGB_REQUIRE(src && order && dst, "null pointer");
+  AGB_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0, "alignment");
+  const long long row16 = row_bytes / 16, total16 = row16 * rows * T;
+  AGB_REQUIRE((total16 + 255) / 256 <= 0x7fffffffLL && row16 <= 0x7fffffffLL, "grid limits");
+  gather_token_rows_kernel<<<(unsigned)((total16 + 255) / 256), 256, 0, st>>>(static_cast<const uint4*>(src), order, total16,
+                                                                             (int)row16, T, S, static_cast<uint4*>(dst));
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // BERT embeddings (reference models/vanilla_bert.py:307-325): LN(word[id] + type[tt] + pos[t]),
 // token_type_ids are all zero on this path (reference recipes/vanilla_bert.py:289).  One warp per
 // token; the normalised row is broadcast to the S coalition rows of its input.

@@ -215,11 +215,11 @@ DROP_MASKED_TOKENS = True
 # (input, coalition) row are permuted so that the kept ones come first.  Everything between the attentions is token-wise
 # and attention is permutation-equivariant, so the CLS output is unchanged; the attention kernel then sees the masked keys
 # as one contiguous tail, all with the logit 0, and folds them into ONE virtual key (agb_attention_bf16_prefix).
-# Exact (tests/test_gpu_edges.py) but OFF by default: the attention kernel gets 14 % faster (390 -> 336 us per layer at the
-# bench shape, its share of the step 17.0 % -> 14.8 %), which the sort + two gathers of the switch give back — an A/B on
-# one box measured 28.0 k vs 28.2 k evals/s (tools/ab_kept_first.py).  Pays off once the softmax stage is no longer
-# bound by TMEM round trips per chunk.
-KEPT_FIRST_ORDER = False
+# Exact (tests/test_gpu_edges.py).  Round 1 built the order with torch.sort + two index_select gathers, which gave back what
+# the attention kernel gained; now the order comes from one small kernel (agb_kept_first_order), the residual stream is
+# gathered in that order instead of being replicated (agb_gather_token_rows) and the first block's attention scatters its
+# output rows (agb_masked_attention_bf16_scatter), so the switch costs nothing extra per step.
+KEPT_FIRST_ORDER = True
 
 
 def last_block_cls_only(pol: _Policy, lw: LayerWeights, vit: bool, x: Tensor, xa: Optional[Tensor], x16: Optional[Tensor],
@@ -326,21 +326,17 @@ def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tens
             qkv0 = pol.linear(h0, lw0.wqkv, lw0.bqkv)
         else:
             qkv0 = pol.linear(pol.act(xi), lw0.wqkv, lw0.bqkv)
-        ctx0 = ops.masked_attention(qkv0, masks, T, heads, ops.MASK_MUL0 if bw.vit else ops.MASK_NEGINF, share=S)
-        if (KEPT_FIRST_ORDER and cls_only and fused and layer_hook is None and T <= 256 and len(full) > 1):
-            # kept-first token order per row (stable: CLS stays first): gather the residual stream and the first block's
-            # attention output into that order; from here on the masks are prefixes of length nkeep
-            rows_ = masks.shape[0]
-            dense = ops.unpack_masks(masks, T - 1)                                        # (rows, n) {0,1} players
-            keep = torch.cat([torch.ones((rows_, 1), dtype=dense.dtype, device=dense.device), dense], 1)
-            order = torch.sort(1 - keep, dim=1, stable=True).indices                      # (rows, T)
-            nkeep = keep.sum(1).to(torch.int32).contiguous()
-            r = torch.arange(rows_, device=order.device)
-            x3 = x_img.reshape(-1, H).index_select(0, (order + (r // S)[:, None] * T).reshape(-1)).reshape(rows_, T, H)
-            ctx0 = ctx0.index_select(0, (order + r[:, None] * T).reshape(-1))
-            masks = ops.pack_masks((torch.arange(T - 1, device=order.device)[None, :] < (nkeep[:, None] - 1)).to(torch.int64),
-                                   prepend_cls=True)
+        if (KEPT_FIRST_ORDER and cls_only and fused and layer_hook is None and T <= 208 and len(full) > 1):
+            # kept-first token order per row (stable: CLS stays first).  The first block's attention (projections shared per
+            # input, masks in the original token order) scatters its output rows into that order, the residual stream of
+            # every coalition is gathered from the per-input embeddings in that order, and from here on the masks are
+            # prefixes of length nkeep: the attention kernels fold the masked tail into one virtual key.
+            order, pos, nkeep, masks_p = ops.kept_first_order(masks, T)
+            ctx0 = ops.masked_attention_scatter(qkv0, masks, T, heads, S, pos)
+            x3 = ops.gather_token_rows(x_img, order, S)
+            masks = masks_p
         else:
+            ctx0 = ops.masked_attention(qkv0, masks, T, heads, ops.MASK_MUL0 if bw.vit else ops.MASK_NEGINF, share=S)
             x3 = ops.repeat_rows(x_img, S)                                   # the residual stream of every coalition
     else:
         x3 = embed(bw, cfg, pol, xs, S)
@@ -450,7 +446,8 @@ class SurrogateEngine:
         from . import _native as nat
         if (0 < B * S <= GRAPH_MAX_ROWS and B * S <= max_rows and self.pol.bf16 and not self._packed_path()
                 and nat.PROFILE is None and not torch.cuda.is_current_stream_capturing()):
-            key = (tuple(xs.shape), xs.dtype, tuple(masks.shape), S, FUSE_LAYERNORM, CLS_ONLY_LAST_BLOCK, SHARE_FIRST_BLOCK)
+            key = (tuple(xs.shape), xs.dtype, tuple(masks.shape), S, FUSE_LAYERNORM, CLS_ONLY_LAST_BLOCK, SHARE_FIRST_BLOCK,
+                   KEPT_FIRST_ORDER)
             return self.graphs.run(key, lambda x_, m_: self._probs_eager(x_, m_, S, max_rows), (xs.contiguous(), masks))
         return self._probs_eager(xs, masks, S, max_rows)
 

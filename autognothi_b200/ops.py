@@ -368,8 +368,49 @@ def attention_prefix(qkv: Tensor, nkeep: Tensor, T: int, heads: int) -> Tensor:
     H = qkv.shape[1] // 3
     assert qkv.shape[0] == rows * T
     ctx = torch.empty((rows * T, H), dtype=torch.bfloat16, device=qkv.device)
-    nat.NEXT_META = None
+    nat.NEXT_META = 4.0 * rows * T * T * H       # dense-equivalent FLOPs (the kernel executes fewer: trimmed key range)
     nat.call("agb_attention_bf16_prefix", nat.ptr(qkv), nat.ptr(nkeep), rows, T, H, heads, nat.ptr(ctx), nat.stream())
+    return ctx
+
+
+def kept_first_order(packed_mask: Tensor, T: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """Stable kept-first partition of every row's tokens (agb_kept_first_order): packed (rows, words) int32 ->
+    (order (rows, T) uint8 [position -> token], pos (rows, T) uint8 [token -> position], nkeep (rows,) int32,
+    prefix masks (rows, words) int32 of the permuted rows)."""
+    assert packed_mask.dtype == torch.int32 and packed_mask.is_contiguous() and T <= 256
+    rows, words = packed_mask.shape
+    dev = packed_mask.device
+    order = torch.empty((rows, T), dtype=torch.uint8, device=dev)
+    pos = torch.empty((rows, T), dtype=torch.uint8, device=dev)
+    nkeep = torch.empty((rows,), dtype=torch.int32, device=dev)
+    prefix = torch.empty((rows, words), dtype=torch.int32, device=dev)
+    nat.call("agb_kept_first_order", nat.ptr(packed_mask), rows, words, T, nat.ptr(order), nat.ptr(pos), nat.ptr(nkeep),
+             nat.ptr(prefix), nat.stream())
+    return order, pos, nkeep, prefix
+
+
+def gather_token_rows(x: Tensor, order: Tensor, S: int) -> Tensor:
+    """x (B, T, H) -> (B*S, T, H) with out[r, q] = x[r // S, order[r, q]] (agb_gather_token_rows)."""
+    x = _c(x)
+    B, T, H = x.shape
+    rows = order.shape[0]
+    assert rows == B * S and order.shape[1] == T and order.dtype == torch.uint8 and order.is_contiguous()
+    out = torch.empty((rows, T, H), dtype=x.dtype, device=x.device)
+    nat.call("agb_gather_token_rows", nat.ptr(x), nat.ptr(order), rows, T, S, H * x.element_size(), nat.ptr(out), nat.stream())
+    return out
+
+
+def masked_attention_scatter(qkv: Tensor, packed_mask: Tensor, T: int, heads: int, share: int, pos: Tensor) -> Tensor:
+    """masked_attention (ViT masks, bf16 tcgen05 kernel, `share` mask rows per qkv row block) whose query token t of row r
+    lands at token position pos[r, t] of ctx (rows*T, H)."""
+    assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and packed_mask.dtype == torch.int32 and packed_mask.is_contiguous()
+    rows = packed_mask.shape[0]
+    H = qkv.shape[1] // 3
+    assert rows % share == 0 and qkv.shape[0] == (rows // share) * T and pos.shape == (rows, T) and pos.dtype == torch.uint8
+    ctx = torch.empty((rows * T, H), dtype=torch.bfloat16, device=qkv.device)
+    nat.NEXT_META = 4.0 * rows * T * T * H
+    nat.call("agb_masked_attention_bf16_scatter", nat.ptr(qkv), nat.ptr(packed_mask), packed_mask.shape[1], rows, share, T, H,
+             heads, nat.ptr(pos), nat.ptr(ctx), nat.stream())
     return ctx
 
 

@@ -36,8 +36,11 @@ class _Drop:
     def __init__(self, cfg, enabled: bool):
         self.h = ops.dropout_thr(float(cfg.hidden_dropout_prob)) if enabled else 0
         self.a = ops.dropout_thr(float(cfg.attention_probs_dropout_prob)) if enabled else 0
-        # CPU generator: follows torch.manual_seed and costs no device synchronisation
+        # CPU generator: follows torch.manual_seed and costs no device synchronisation; the data-parallel rank is mixed in
+        # so that identically seeded replicas still draw different dropout masks
         self.seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (self.h or self.a) else 0
+        if self.seed and torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.seed = (self.seed ^ (0x51ED270B7F4A7C15 * (torch.distributed.get_rank() + 1))) & (2 ** 62 - 1)
         self.n = 0
 
     def tag(self) -> int:
@@ -331,8 +334,10 @@ def forward_train(sd: Dict[str, Tensor], cfg, precision: str, xs: Tensor, masks:
     return phi, tp
 
 
-def backward_train(tp: _Tape, dphi: Tensor, dx_cls: Optional[Tensor] = None) -> Grads:
-    """dx_cls (B, H): gradient w.r.t. tape.x_cls coming from a head outside this node (Duo variants), or None."""
+def backward_train(tp: _Tape, dphi: Tensor, dx_cls: Optional[Tensor] = None, sink=None) -> Grads:
+    """dx_cls (B, H): gradient w.r.t. tape.x_cls coming from a head outside this node (Duo variants), or None.
+    sink (dist.OverlappedGradReducer | None): gets the gradients of every stage as soon as they exist (head first, then the
+    blocks from the last to the first), so that their all-reduce overlaps the adjoint of the remaining blocks."""
     pol, cfg, bw = tp.pol, tp.cfg, tp.bw
     vit = bw.vit
     T, B = tp.T, tp.B
@@ -352,6 +357,16 @@ def backward_train(tp: _Tape, dphi: Tensor, dx_cls: Optional[Tensor] = None) -> 
         dx = _ln_bwd(grads, "explainer_mlp.0", tp.x_last, dx, tp.mlp_ln[0], 1e-5, None)
     elif tp.head_tag:
         dx = ops.dropout(dx, tp.drop.h, tp.drop.seed, tp.head_tag)
+    handed = 0
+
+    def hand_over():
+        nonlocal handed
+        if sink is not None and len(grads) > handed:
+            names = list(grads.keys())[handed:]
+            handed = len(grads)
+            sink.push(grads, names)
+
+    hand_over()
     n_backbone = len(bw.layers) if tp.train_backbone else 0
     for idx in range(len(tp.layers) - 1, -1, -1):
         prefix, lw, t = tp.layers[idx]
@@ -366,19 +381,21 @@ def backward_train(tp: _Tape, dphi: Tensor, dx_cls: Optional[Tensor] = None) -> 
             dx = vit_layer_bwd(pol, lw, prefix, t, dx, tp.masks, T, heads, eps, grads, need_dx)
         else:
             dx = bert_layer_bwd(pol, lw, prefix, t, dx, tp.masks, T, heads, eps, grads, need_dx)
+        hand_over()
     if tp.train_backbone:
         _embed_bwd(tp, dx, grads)
+    hand_over()
     return grads
 
 
 class _ExplainerTrainFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, xs, masks, grand, null, cfg, precision, dropout, names, *params):
+    def forward(ctx, xs, masks, grand, null, cfg, precision, dropout, names, sink, *params):
         sd = {n: p.detach() for n, p in zip(names, params)}
-        train_backbone = any(ctx.needs_input_grad[8 + i] for i, n in enumerate(names) if n.startswith(("vit.", "bert.")))
+        train_backbone = any(ctx.needs_input_grad[9 + i] for i, n in enumerate(names) if n.startswith(("vit.", "bert.")))
         with torch.no_grad():
             phi, tape = forward_train(sd, cfg, precision, xs, masks, grand, null, train_backbone, dropout)
-        ctx.tape, ctx.names = tape, names
+        ctx.tape, ctx.names, ctx.sink = tape, names, sink
         ctx.shapes = [p.shape for p in params]
         ctx.set_materialize_grads(False)
         return phi, tape.x_cls
@@ -390,13 +407,15 @@ class _ExplainerTrainFn(torch.autograd.Function):
                 dphi = torch.zeros((ctx.tape.B, ctx.tape.cfg.num_labels, ctx.tape.T - 1), dtype=torch.float32,
                                    device=ctx.tape.hb.device)
             grads = backward_train(ctx.tape, dphi.contiguous().float(),
-                                   dx_cls.contiguous().float() if dx_cls is not None else None)
+                                   dx_cls.contiguous().float() if dx_cls is not None else None, sink=ctx.sink)
+            if ctx.sink is not None:
+                grads = ctx.sink.finish(grads)          # averaged over the data-parallel ranks, views of the flat buckets
         ctx.tape = None
         out = []
         for n, shp in zip(ctx.names, ctx.shapes):
             g = grads.get(n)
             out.append(g.reshape(shp) if g is not None else None)
-        return (None, None, None, None, None, None, None, None, *out)
+        return (None, None, None, None, None, None, None, None, None, *out)
 
 
 def _wants_dropout(model) -> bool:
@@ -417,7 +436,7 @@ def explainer_forward_train(model, xs: Tensor, words: Tensor, grand: Optional[Te
     g = grand.detach() if grand is not None else None
     nl = null.detach() if null is not None else None
     phi, _x_cls = _ExplainerTrainFn.apply(xs, words, g, nl, model.config, model.agb_precision, _wants_dropout(model), names,
-                                          *params)
+                                          getattr(model, "agb_grad_reducer", None), *params)
     return phi
 
 
@@ -438,7 +457,7 @@ def duo_explainer_forward_train(model, xs: Tensor, words: Tensor, grand: Optiona
     g = grand.detach() if grand is not None else None
     nl = null.detach() if null is not None else None
     dropout = _wants_dropout(model)
-    phi, x_cls = _ExplainerTrainFn.apply(xs, words, g, nl, cfg, model.agb_precision, dropout, names, *[p for _, p in named])
+    phi, x_cls = _ExplainerTrainFn.apply(xs, words, g, nl, cfg, model.agb_precision, dropout, names, None, *[p for _, p in named])
     if hasattr(cfg, "img_px_size"):
         logits = torch.nn.functional.linear(x_cls, named_all["classifier.weight"], named_all["classifier.bias"])
         return phi, torch.softmax(logits, dim=-1)

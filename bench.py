@@ -462,7 +462,11 @@ def run_ours(args):
         explainer = rec.conv_surrogate_explainer(cfg, None, surrogate).train()
         explainer.agb_precision = "bf16"
         opt = torch.optim.AdamW(explainer.parameters(), lr=5e-5, fused=True)   # lr: .hparams.json train_explainer.lr
-        reducer = GradAllReducer(explainer.parameters(), bucket_mb=64.0)
+        reducer = GradAllReducer(explainer.parameters(), bucket_mb=64.0)     # broadcasts rank 0's parameters first
+        # gradients are averaged DURING the backward pass: the hand-written adjoint hands every block's gradients to
+        # 32 MB flat buckets as they are produced and each full bucket goes out as one async NCCL all-reduce
+        overlapped = reducer.attach(explainer, bucket_mb=32.0,
+                                    wire_dtype=torch.bfloat16 if args.grad_wire == "bf16" else torch.float32)
         ones = ash.PackedMasks.ones(Bt, n, dev)
         with torch.no_grad():
             null, _ = rec.fw_surrogate(surrogate, rec.gen_null(cfg, None, dev), ash.PackedMasks.ones(1, n, dev))
@@ -494,7 +498,9 @@ def run_ours(args):
                  "tflops_per_gpu": sps / world * fl_sample * 1e-12, "gpu_launches": launches_t,
                  "dropout": "p=0.1 on embeddings / attention probabilities / attention-output / MLP-output (train() mode of the reference's "
                             "config; masks from a counter hash, regenerated in the adjoint)", "optimizer": "torch.optim.AdamW(fused=True), fp32 master weights",
-                 "grad_allreduce": f"NCCL, 64 MB flat buckets, world={world}"}
+                 "grad_allreduce": f"NCCL AVG, 32 MB flat buckets filled and sent during the backward pass (last block first), "
+                                   f"wire dtype {args.grad_wire}, world={world}; {overlapped.stats['buckets'] // max(1, t_steps + 2)} "
+                                   f"all-reduces / step"}
         peaks_t = load_peaks()
         train["frac_of_sustained_peak"] = train["tflops_per_gpu"] / peaks_t["bf16_tflops_sustained"]
 
@@ -656,6 +662,8 @@ def main():
     ap.add_argument("--workload", default="vit", choices=["vit", "bert_base_tayp_vanilla", "bert_base_tayp_kernel_shap"],
                     help="vit = the metric's own configuration (default, BASELINE.json configs[1] / configs[4] with --model "
                          "vit_large); the other two are BASELINE.json configs[2] and configs[3] as side workloads")
+    ap.add_argument("--grad-wire", default="fp32", choices=["fp32", "bf16"],
+                    help="wire format of the gradient all-reduce of the training leg (fp32 = exact averaging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the explainer-training leg")
     ap.add_argument("--no-ltt", action="store_true", help="skip the ladder-side-tuning leg")

@@ -147,6 +147,22 @@ int agb_vit_assemble(const float* patch_emb, const float* cls_token, const float
  * The embedded input of the first-block sharing path fanned out to its S coalition rows on the device (replaces the
  * Xs_EXT replication loop of reference scripts/train_explainer.py:159-163 at the residual-stream level). */
 int agb_repeat_rows(const void* src, int B, long long row_bytes, int S, void* dst, void* stream);
+/* Kept-first token order of ViT coalition rows (surrogate evaluation; the mask semantics of reference
+ * models/vanilla_vit.py:449-450 make every masked key's logit 0, so the masked keys of a row are interchangeable): a stable
+ * partition of each row's tokens into kept (CLS = bit 0 always) and masked.  packed (rows, words) -> order (rows, T) uint8
+ * [position -> token], pos (rows, T) uint8 [token -> position], nkeep (rows), prefix (rows, words) packed mask of the
+ * permuted row (bits [0, nkeep) set).  T <= 256. */
+int agb_kept_first_order(const uint32_t* packed, int rows, int words, int T, uint8_t* order, uint8_t* pos, int* nkeep,
+                         uint32_t* prefix, void* stream);
+/* dst[(r, q), :] = src[(r / S, order[r, q]), :] for rows of row_bytes bytes (multiple of 16): per-coalition residual stream
+ * in kept-first order from the per-input embeddings (replaces the reference's Xs_EXT replication,
+ * scripts/train_explainer.py:159-163, on that path). */
+int agb_gather_token_rows(const void* src, const uint8_t* order, int rows, int T, int S, long long row_bytes, void* dst,
+                          void* stream);
+/* agb_masked_attention_bf16_shared whose query token t of row r is written to token position dst_pos[r, t] of ctx
+ * (rows, T, H): the first block of the kept-first evaluation order.  T <= 208, head dim 64, ViT mask semantics. */
+int agb_masked_attention_bf16_scatter(const void* qkv, const uint32_t* mask, int words, int rows, int share, int T, int H,
+                                      int heads, const uint8_t* dst_pos, void* ctx, void* stream);
 /* word + token_type(0) + position embeddings -> LayerNorm, broadcast to S rows per input
  * (reference models/vanilla_bert.py:307-325). ids (B,T) int64. */
 int agb_bert_embed(const int64_t* ids, const float* word, const float* pos, const float* type0,
@@ -187,8 +203,9 @@ int agb_cls_attention_varlen(const void* q, long long ldq, const void* kv, long 
                              int io_is_bf16, const int* cu, int rows, int max_len, int H, int heads, void* ctx,
                              long long ldc, void* stream);
 
-/* Kernel selection for agb_masked_attention_bf16 (diagnostics): 0 = automatic (pipelined, one CTA per SM),
- * 1 = first-generation kernel.  Returns the previous setting. */
+/* Kernel selection for agb_masked_attention_bf16 (diagnostics): 0 = automatic (split-softmax kernel for ViT masks at
+ * T <= 208 in token order, else the pipelined one), 1 = first-generation kernel, 2 = pipelined kernel, 3 = split-softmax
+ * kernel for the kept-first order too.  Returns the previous setting. */
 int agb_attention_set_variant(int variant);
 /* Same for agb_masked_attention_bwd: 0 = automatic (tcgen05 kernel for bf16), 1 = CUDA-core kernel. */
 int agb_attention_bwd_set_variant(int variant);

@@ -56,6 +56,34 @@ def _worker(rank, world, port, q):
                 if i == 3:
                     want = (i + 1) * sum(r + 1 for r in range(1, world)) / world
                 assert torch.allclose(p.grad, torch.full(p.shape, want)), (bucket_mb, i, p.grad.flatten()[:3], want)
+        # 4. overlapped reducer: gradients pushed stage by stage (as the hand-written adjoint does), several bucket sizes,
+        #    both wire formats; step 1 records the layout, steps 2-3 reuse it and launch buckets as they fill
+        names = [f"p{i}" for i in range(len(shapes))]
+        for bucket_mb, wire in ((1e-5, torch.float32), (2e-4, torch.float32), (32.0, torch.float32), (2e-4, torch.bfloat16)):
+            red = agd.OverlappedGradReducer(bucket_mb=bucket_mb, wire_dtype=wire)
+            for step in range(3):
+                grads = {}
+                for stage in ((0, 1), (2,), (3, 4)):
+                    for i in stage:
+                        grads[names[i]] = torch.full(shapes[i], float(rank + 1) * (i + 1) + step)
+                    red.push(grads, [names[i] for i in stage])
+                out = red.finish(grads)
+                for i, nme in enumerate(names):
+                    want = (i + 1) * sum(r + 1 for r in range(world)) / world + step
+                    assert out[nme].shape == torch.Size(shapes[i]) and out[nme].dtype == torch.float32
+                    assert torch.allclose(out[nme], torch.full(shapes[i], want), rtol=1e-2 if wire == torch.bfloat16 else 1e-6), \
+                        (bucket_mb, wire, step, nme, out[nme].flatten()[:3], want)
+            assert len(red.flat) >= (3 if bucket_mb < 1e-4 else 1)
+        # 5. parameter broadcast + replica check
+        torch.manual_seed(100 + rank)
+        ps = [torch.nn.Parameter(torch.randn(s)) for s in shapes]
+        try:
+            agd.assert_replicas_identical(ps)
+            raise AssertionError("diverged replicas not detected")
+        except RuntimeError:
+            pass
+        agd.broadcast_parameters(ps, src=0)
+        agd.assert_replicas_identical(ps)
         q.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         q.put((rank, f"FAIL {type(e).__name__}: {e}"))

@@ -175,6 +175,124 @@ def test_kept_first_token_order_is_exact_work_skipping(agb, golden_dir, name):
     np.testing.assert_allclose(_np(a).sum(1), 1.0, atol=1e-5)
 
 
+@pytest.mark.parametrize("T,rows", [(197, 33), (17, 9), (128, 4), (208, 3), (33, 70), (2, 3), (256, 2)])
+def test_kept_first_order_kernel_vs_numpy(agb, T, rows):
+    """agb_kept_first_order: stable kept/masked partition (bit-exact index work), incl. empty and full coalitions."""
+    rng = np.random.default_rng(T * 31 + rows)
+    dense = (rng.random((rows, max(T - 1, 0))) > rng.random((rows, 1))).astype(np.int64)
+    if T > 1:
+        dense[0, :] = 0
+        dense[1, :] = 1
+    packed = agb.pack_masks(torch.from_numpy(dense).to(DEV), prepend_cls=True)
+    order, pos, nkeep, prefix = agb.kept_first_order(packed, T)
+    keep = np.concatenate([np.ones((rows, 1), np.int64), dense], 1)
+    ref_order = np.argsort(1 - keep, axis=1, kind="stable")
+    assert np.array_equal(order.cpu().numpy().astype(np.int64), ref_order)
+    ref_pos = np.empty_like(ref_order)
+    np.put_along_axis(ref_pos, ref_order, np.arange(T)[None, :].repeat(rows, 0), axis=1)
+    assert np.array_equal(pos.cpu().numpy().astype(np.int64), ref_pos)
+    assert np.array_equal(nkeep.cpu().numpy(), keep.sum(1).astype(np.int32))
+    ref_prefix = agb.pack_masks(torch.from_numpy((np.arange(T - 1)[None, :] < (keep.sum(1)[:, None] - 1)).astype(np.int64)).to(DEV),
+                                prepend_cls=True)
+    assert torch.equal(prefix, ref_prefix)
+
+
+@pytest.mark.parametrize("B,S,T,H,dtype", [(3, 4, 197, 768, torch.float32), (2, 5, 17, 24, torch.bfloat16), (1, 1, 33, 8, torch.float32)])
+def test_gather_token_rows_equals_index_select(agb, B, S, T, H, dtype):
+    torch.manual_seed(B * 7 + T)
+    x = torch.randn((B, T, H), device=DEV).to(dtype)
+    order = torch.stack([torch.randperm(T, device=DEV) for _ in range(B * S)]).to(torch.uint8)
+    got = agb.gather_token_rows(x, order, S)
+    r = torch.arange(B * S, device=DEV)
+    ref = x[(r // S)[:, None], order.long()]
+    assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("T,heads,rows,share", [(197, 12, 8, 4), (197, 3, 3, 1), (128, 2, 6, 3), (17, 1, 4, 2), (208, 2, 2, 1), (65, 1, 5, 5)])
+def test_split_softmax_attention_kernels(agb, T, heads, rows, share):
+    """Third-generation attention kernel (agb_attention_split.cu), all three entry points against the fp32 CUDA-core kernel:
+    ViT masks in token order, the same with scattered output rows, and kept-first order with the virtual key."""
+    torch.manual_seed(T + heads + rows)
+    H = heads * 64
+    B = rows // share
+    qkv_b = torch.randn(B * T, 3 * H, device=DEV).to(torch.bfloat16)
+    qkv = qkv_b.reshape(B, 1, T, 3 * H).expand(B, share, T, 3 * H).reshape(rows * T, 3 * H).contiguous()
+    g = torch.Generator(device="cpu").manual_seed(rows)
+    dense = (torch.rand((rows, T - 1), generator=g) > torch.rand((rows, 1), generator=g)).to(torch.int64).to(DEV)
+    dense[0, :] = 0
+    if rows > 1:
+        dense[1, :] = 1
+    packed = agb.pack_masks(dense, prepend_cls=True)
+    ref = agb.masked_attention(qkv.float(), packed, T, heads, agb.MASK_MUL0).float()           # fp32 exact kernel
+    scale = float(ref.abs().max())
+    # (1) token order, shared projections
+    got = agb.masked_attention(qkv_b, packed, T, heads, agb.MASK_MUL0, share=share).float()
+    assert torch.isfinite(got).all()
+    assert float((got - ref).abs().max()) <= 3e-2 * scale and float((got - ref).norm() / ref.norm()) < 1e-2
+    # (2) the same, output rows scattered into kept-first order
+    order, pos, nkeep, prefix = agb.kept_first_order(packed, T)
+    sc = agb.masked_attention_scatter(qkv_b, packed, T, heads, share, pos).float().reshape(rows, T, H)
+    r = torch.arange(rows, device=DEV)
+    assert torch.equal(sc[r[:, None], pos.long()], got.reshape(rows, T, H))
+    # (3) kept-first order (split kernel = variant 3): permuted projections + nkeep -> the permuted rows of the reference
+    from autognothi_b200 import _native as nat
+    qkv_p = qkv.reshape(rows, T, 3 * H)[r[:, None], order.long()].reshape(rows * T, 3 * H).contiguous()
+    prev = nat.lib.agb_attention_set_variant(3)
+    try:
+        pf = agb.attention_prefix(qkv_p, nkeep, T, heads).float().reshape(rows, T, H)
+    finally:
+        nat.lib.agb_attention_set_variant(prev)
+    ref_p = ref.reshape(rows, T, H)[r[:, None], order.long()]
+    assert torch.isfinite(pf).all()
+    assert float((pf - ref_p).abs().max()) <= 3e-2 * scale and float((pf - ref_p).norm() / ref_p.norm()) < 1e-2
+    # and the pipelined second-generation kernel (variant 2) agrees on (1) and (3)
+    prev = nat.lib.agb_attention_set_variant(2)
+    try:
+        got2 = agb.masked_attention(qkv_b, packed, T, heads, agb.MASK_MUL0, share=share).float()
+        pf2 = agb.attention_prefix(qkv_p, nkeep, T, heads).float().reshape(rows, T, H)
+    finally:
+        nat.lib.agb_attention_set_variant(prev)
+    assert float((got2 - got).abs().max()) <= 2e-2 * scale
+    assert float((pf2 - pf).abs().max()) <= 2e-2 * scale
+
+
+@pytest.mark.parametrize("hot_keys", [(40,), (150,), (40, 150), (100, 196), (33, 70, 120, 190)])
+def test_split_softmax_lazy_maximum_rescale(agb, hot_keys):
+    """The split-softmax kernel reads S from TMEM once: the row's reference maximum comes from the first chunk of each key
+    half and is raised later only when a chunk exceeds it by 2^24, rescaling the P columns already written.  Keys with
+    huge logits late in the row force that path (and the reconciliation between the two halves); result vs the fp32 kernel."""
+    torch.manual_seed(sum(hot_keys))
+    T, heads, rows = 197, 2, 6
+    H = heads * 64
+    qkv = torch.randn(rows, T, 3 * H, device=DEV)
+    for i, kx in enumerate(hot_keys):
+        qkv[:, kx, H:2 * H] *= 60.0 * (i + 1)          # logits of this key: std ~ 140 * (i + 1), far above the first chunk's
+    qkv_b = qkv.reshape(rows * T, 3 * H).to(torch.bfloat16).contiguous()
+    g = torch.Generator(device="cpu").manual_seed(3)
+    dense = (torch.rand((rows, T - 1), generator=g) > 0.3).to(torch.int64).to(DEV)
+    dense[1, :] = 1
+    for kx in hot_keys:
+        dense[:, kx - 1] = 1                           # the hot keys stay live (a masked key's logit is 0)
+    packed = agb.pack_masks(dense, prepend_cls=True)
+    ref = agb.masked_attention(qkv_b.float(), packed, T, heads, agb.MASK_MUL0).float()
+    got = agb.masked_attention(qkv_b, packed, T, heads, agb.MASK_MUL0).float()
+    assert torch.isfinite(got).all()
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) <= 3e-2 * scale and float((got - ref).norm() / ref.norm()) < 1e-2
+    order, pos, nkeep, prefix = agb.kept_first_order(packed, T)
+    r = torch.arange(rows, device=DEV)
+    qkv_p = qkv_b.reshape(rows, T, 3 * H)[r[:, None], order.long()].reshape(rows * T, 3 * H).contiguous()
+    from autognothi_b200 import _native as nat
+    prev = nat.lib.agb_attention_set_variant(3)
+    try:
+        pf = agb.attention_prefix(qkv_p, nkeep, T, heads).float().reshape(rows, T, H)
+    finally:
+        nat.lib.agb_attention_set_variant(prev)
+    ref_p = ref.reshape(rows, T, H)[r[:, None], order.long()]
+    assert torch.isfinite(pf).all()
+    assert float((pf - ref_p).abs().max()) <= 3e-2 * scale and float((pf - ref_p).norm() / ref_p.norm()) < 1e-2
+
+
 @pytest.mark.parametrize("shape,S,dtype", [((3, 197, 768), 32, torch.float32), ((5, 17, 24), 7, torch.bfloat16),
                                            ((1, 128, 768), 2, torch.float32), ((4, 3, 5), 3, torch.float32),
                                            ((0, 8, 16), 4, torch.float32)])

@@ -436,8 +436,8 @@ def test_full_path_bf16_tensor_cores_vs_reference_golden(agb, golden_dir, name):
 
 def test_bench_shape_engages_the_bench_kernels(agb, golden_dir):
     """model_vit_base_b4s32 (4 inputs x 32 coalitions = 128 rows, M = 25 216) is the smallest reference-pinned case that runs
-    the kernel variants of the benchmark: CTA-pair tcgen05 GEMMs, the LayerNorm-folded chain, repeat_rows, first-block
-    sharing, the pipelined attention kernel and the CLS-only last block.  Checked on the launch log of the eager path."""
+    the kernel variants of the benchmark: CTA-pair tcgen05 GEMMs, the LayerNorm-folded chain, first-block sharing, the
+    kept-first token order with the split-softmax attention kernel and the CLS-only last block.  Checked on the launch log of the eager path."""
     from autognothi_b200 import _native as nat
     from autognothi_b200 import engine
     g = _load(golden_dir, "model_vit_base_b4s32.npz")
@@ -455,8 +455,8 @@ def test_bench_shape_engages_the_bench_kernels(agb, golden_dir):
     finally:
         nat.PROFILE = None
         engine.GRAPH_MAX_ROWS = old
-    for must in ("agb_gemm_bf16_fused", "agb_masked_attention_bf16_shared", "agb_masked_attention_bf16", "agb_repeat_rows",
-                 "agb_cls_attention"):
+    for must in ("agb_gemm_bf16_fused", "agb_kept_first_order", "agb_masked_attention_bf16_scatter", "agb_gather_token_rows",
+                 "agb_attention_bf16_prefix", "agb_cls_attention"):
         assert must in names, f"{must} did not run: {sorted(set(names))}"
     np.testing.assert_allclose(_np(v_s), g["v_s"], atol=2e-2)
     # graph replay (the default for <= 128 rows) gives the same numbers as the eager launches
@@ -502,14 +502,17 @@ def test_first_block_projection_sharing_is_exact(agb, golden_dir, name):
     rec, cfgd, srg, exp = _build(name, "bf16")
     xs = torch.from_numpy(synth.inputs(cfgd, B, seed=0)).to(DEV)
     masks = torch.from_numpy(g["masks"].astype(np.int64)).to(DEV).reshape(B, S, n)
+    keep_first = engine.KEPT_FIRST_ORDER
     try:
         with torch.no_grad():
+            engine.KEPT_FIRST_ORDER = False       # compare like with like: the kept-first order has its own test
             engine.SHARE_FIRST_BLOCK = True
             p_share, _ = rec.fw_surrogate(srg, xs, masks)
             engine.SHARE_FIRST_BLOCK = False
             p_plain, _ = rec.fw_surrogate(srg, xs, masks)
     finally:
         engine.SHARE_FIRST_BLOCK = True
+        engine.KEPT_FIRST_ORDER = keep_first
     np.testing.assert_allclose(_np(p_share), _np(p_plain), rtol=0, atol=1e-6)
     np.testing.assert_allclose(_np(p_share), g["v_s"], atol=2e-2)
 
@@ -687,6 +690,46 @@ def test_training_gradients_vit_base_vs_reference_autograd(agb, golden_dir, prec
         assert err <= tol + floor / (np.linalg.norm(ref) + 1e-30), f"{k}: relative L2 {err}"
     worst.sort(reverse=True)
     print(f"[{precision}] worst relative L2 per tensor:", [(round(e, 5), k) for e, k in worst[:5]])
+
+
+@pytest.mark.parametrize("wire", ["fp32", "bf16"])
+def test_overlapped_grad_reducer_is_transparent_on_one_rank(agb, golden_dir, wire):
+    """With a dist.OverlappedGradReducer attached, the adjoint hands its gradients over block by block and autograd receives
+    views of the flat buckets; on one rank the parameter gradients must be the plain ones (bf16 wire: rounded to bf16),
+    over repeated steps (the bucket layout is recorded in the first and reused afterwards)."""
+    from autognothi_b200.dist import OverlappedGradReducer
+    from autognothi_b200.models import shapley as ash
+    name = "vit_mini"
+    g = _load(golden_dir, f"model_{name}.npz")
+    B, S, n = (int(v) for v in g["meta"])
+    rec, cfgd, srg, exp = _build(name, "bf16")
+    exp.train()
+    exp.agb_dropout = False
+    xs = torch.from_numpy(synth.inputs(cfgd, B, seed=0)).to(DEV)
+    masks = torch.from_numpy(g["masks"].astype(np.int64)).to(DEV).reshape(B, S, n)
+    v_s, grand, null = (torch.from_numpy(g[k]).to(DEV) for k in ("v_s", "grand", "null"))
+    ones = torch.ones((B, n), dtype=torch.int64, device=DEV)
+
+    def grads():
+        exp.zero_grad(set_to_none=True)
+        phi, _ = rec.fw_explainer(exp, xs, ones, grand, null)
+        ash.loss_shapley_new(B, S, n, masks, null, v_s, grand, phi).backward()
+        return {k: p.grad.clone() for k, p in exp.named_parameters()}
+
+    plain = grads()
+    red = OverlappedGradReducer(bucket_mb=0.05, wire_dtype=torch.bfloat16 if wire == "bf16" else torch.float32)
+    exp.agb_grad_reducer = red
+    try:
+        for step in range(3):
+            got = grads()
+            assert len(red.flat) > 3
+            for k, ref in plain.items():
+                if wire == "fp32":
+                    assert torch.equal(got[k], ref), (step, k)
+                else:
+                    assert torch.equal(got[k], ref.to(torch.bfloat16).float()), (step, k)
+    finally:
+        del exp.agb_grad_reducer
 
 
 def test_training_loop_reduces_loss(agb, golden_dir):
