@@ -7,9 +7,23 @@ CSRC      := autognothi_b200/csrc
 SRCS      := $(wildcard $(CSRC)/*.cu)
 OBJS      := $(patsubst $(CSRC)/%.cu,build/%.o,$(SRCS))
 LIB       := autognothi_b200/lib/libautognothi_b200.so
+TLIB      := autognothi_b200/lib/libagb_torch.so
 NATIVE    := build/gemm_check
+PYTHON    ?= python
+TORCH_DIR := $(shell $(PYTHON) -c "import torch,os;print(os.path.dirname(torch.__file__))")
+TORCH_ABI := $(shell $(PYTHON) -c "import torch;print(int(torch._C._GLIBCXX_USE_CXX11_ABI))")
 
-all: $(LIB) $(NATIVE) oracle
+all: $(LIB) $(TLIB) $(NATIVE) oracle
+
+# thin torch C++ extension over the C-ABI: one TORCH_LIBRARY op per entry point, generated from the header
+build/agb_torch_binding.cpp: include/autognothi_b200.h tools/gen_torch_binding.py
+	@mkdir -p build
+	$(PYTHON) tools/gen_torch_binding.py include/autognothi_b200.h > $@
+
+$(TLIB): build/agb_torch_binding.cpp $(LIB)
+	g++ -O2 -std=c++17 -fPIC -shared -D_GLIBCXX_USE_CXX11_ABI=$(TORCH_ABI) -Iinclude -I$(TORCH_DIR)/include \
+	    -I$(TORCH_DIR)/include/torch/csrc/api/include -I/usr/local/cuda/include $< -o $@ \
+	    -L$(TORCH_DIR)/lib -ltorch -ltorch_cpu -lc10 -lc10_cuda -Lautognothi_b200/lib -lautognothi_b200 -Wl,-rpath,'$$ORIGIN'
 
 build/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/autognothi_b200.h
 	@mkdir -p build
@@ -26,6 +40,6 @@ oracle:
 	@if [ -f oracle/Makefile ]; then $(MAKE) -C oracle; fi
 
 clean:
-	rm -rf build $(LIB)
+	rm -rf build $(LIB) $(TLIB)
 
 .PHONY: all clean oracle

@@ -1,8 +1,12 @@
-"""ctypes binding of libautognothi_b200.so (the C-ABI declared in include/autognothi_b200.h).
+"""Binding of libautognothi_b200.so (the C-ABI declared in include/autognothi_b200.h).
 
-The prototypes are parsed from the header itself, so Python can never drift from the C declarations.
-There is NO fallback: if the shared library is missing or a symbol is absent, importing this module
-raises — the product path must fail loudly without its CUDA extension.
+Kernel launches go through a thin torch C++ extension, lib/libagb_torch.so: one TORCH_LIBRARY op per C-ABI entry point
+(generated from the header by tools/gen_torch_binding.py) that takes `Tensor?` arguments, checks that they live on the
+current CUDA device, launches on at::cuda's current stream and forwards to the `extern "C"` function of the same name.
+Configuration / diagnostics entry points (no stream argument) and `AGB_BINDING=ctypes` use ctypes on the same library;
+its prototypes are parsed from the header itself, so Python can never drift from the C declarations.
+There is NO fallback: if a shared library is missing or a symbol is absent, importing this module raises — the
+product path must fail loudly without its CUDA extension.
 """
 from __future__ import annotations
 
@@ -69,6 +73,20 @@ for _name, (_ret, _args) in PROTOTYPES.items():
     _fn.argtypes = [_to_ctype(t) for t, _ in _args]
 
 
+TORCH_LIB_PATH = os.path.join(_HERE, "lib", "libagb_torch.so")
+BINDING = os.environ.get("AGB_BINDING", "torch")          # "torch" (default) | "ctypes"
+assert BINDING in ("torch", "ctypes"), "AGB_BINDING must be 'torch' or 'ctypes'"
+TORCH_OPS = None
+if BINDING == "torch":
+    if not os.path.exists(TORCH_LIB_PATH):
+        raise RuntimeError(
+            f"autognothi_b200: torch extension not found at {TORCH_LIB_PATH}. Build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (or `make`). There is no CPU fallback.")
+    torch.ops.load_library(TORCH_LIB_PATH)
+    TORCH_OPS = {n: getattr(torch.ops.agb, n) for n, (_r, a) in PROTOTYPES.items()
+                 if _r == "int" and any(pn == "stream" and "*" in pt for pt, pn in a)}
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -79,16 +97,52 @@ def check(rc: int, what: str) -> None:
         raise NativeError(f"{what} failed (status {rc}): {msg.decode() if msg else '?'}")
 
 
+class _Stream:
+    """placeholder for the C-ABI's stream argument: the torch extension supplies at::cuda's current stream itself"""
+
+
+_STREAM = _Stream()
+
+
 def ptr(t):
-    """device pointer of a tensor (None -> NULL)."""
+    """device-pointer argument of a C-ABI call (None -> NULL): the tensor itself for the torch extension (which checks the
+    device and takes data_ptr() in C++), a ctypes pointer for the ctypes binding."""
     if t is None:
         return None
     assert t.is_cuda, "autognothi_b200 kernels take CUDA tensors only"
+    if TORCH_OPS is not None:
+        return t
+    assert t.device.index == torch.cuda.current_device(), \
+        f"tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}"
     return ctypes.c_void_p(t.data_ptr())
 
 
 def stream():
+    if TORCH_OPS is not None:
+        return _STREAM
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _invoke(name: str, args) -> int:
+    op = TORCH_OPS.get(name) if TORCH_OPS is not None else None
+    if op is not None:
+        conv = []
+        for a in args:
+            if a is _STREAM:
+                continue
+            if isinstance(a, int) and a >= (1 << 63):
+                a -= 1 << 64                      # uint64_t arguments (hash seeds) travel as two's-complement int64
+            conv.append(a)
+        return op(*conv)
+    # ctypes path: configuration entry points, or AGB_BINDING=ctypes
+    conv = []
+    for a in args:
+        if a is _STREAM:
+            a = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        elif isinstance(a, torch.Tensor):
+            a = ctypes.c_void_p(a.data_ptr())
+        conv.append(a)
+    return getattr(lib, name)(*conv)
 
 
 LAUNCHES = 0       # number of kernel-launching C-ABI calls made through `call` (bench.py's gpu_launches)
@@ -101,12 +155,12 @@ def call(name: str, *args) -> None:
     global LAUNCHES, NEXT_META, NEXT_INFO
     LAUNCHES += 1
     if PROFILE is None:
-        check(getattr(lib, name)(*args), name)
+        check(_invoke(name, args), name)
         return
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
-    check(getattr(lib, name)(*args), name)
+    check(_invoke(name, args), name)
     e1.record()
     PROFILE.append((name, NEXT_META, e0, e1, NEXT_INFO))
     NEXT_META = None

@@ -3,8 +3,13 @@
 The reference delegates coalition sampling, the synthetic-data build and the weighted least squares to the
 third-party `shap.KernelExplainer(link="logit")` on the CPU (models/kernel_shap_bert.py:170-185).  Here the
 classifier forwards run on the sm_100a kernels and the solve is `agb_kernelshap_solve` (batched Gram +
-Cholesky in float64 on the device).  Not reproduced: shap's own RNG stream and its optional l1_reg feature
-pre-selection — see oracle/kernelshap.py ("parity unpinned").
+Cholesky in float64 on the device).  As shap does, the regression only covers the features that VARY between
+the explained row and the background (the others get attribution 0), and an under-determined system (fewer
+distinct coalitions than varying features) gets the minimum-norm least-squares solution.
+NOT reproduced — stated loudly: shap's own RNG stream, and its default l1_reg="auto", which pre-selects features
+with LassoLarsIC("aic") whenever the sampled coalitions cover < 20 % of the 2^M space (i.e. always for M >= 14):
+this path solves the UN-regularised constrained weighted least squares on all varying features.  Parity with
+shap is therefore unpinned (shap is absent from the image; oracle/kernelshap.py).
 """
 from __future__ import annotations
 
@@ -114,6 +119,9 @@ def sample_coalitions(d: int, n_samples: int, device, seed: int = 0) -> Tuple[Te
     rows, weights = [], []
     mass = 0.0
     lo, hi = 1, d - 1
+    if d == 2:        # the only proper subsets: {0} and {1}
+        z = torch.eye(2, dtype=torch.int64, device=device).repeat((n_samples + 1) // 2, 1)[:max(n_samples, 2)]
+        return z, torch.full((z.shape[0],), 1.0 / z.shape[0], dtype=torch.float64, device=device)
     if n_samples >= 2 * d + 2 and d > 3:
         eye = torch.eye(d, dtype=torch.int64, device=device)
         rows += [eye, 1 - eye]
@@ -134,6 +142,21 @@ def sample_coalitions(d: int, n_samples: int, device, seed: int = 0) -> Tuple[Te
     return torch.cat(rows, 0), torch.cat(weights, 0)
 
 
+def _min_norm_wls(Z: Tensor, w: Tensor, probs: Tensor, f_x: Tensor, f_null: Tensor) -> Tensor:
+    """Under-determined constrained WLS (rank(E) < M - 1): minimum-norm solution of the sqrt-weighted system, what
+    numpy.linalg.lstsq gives shap in that regime.  Z (S, M) {0,1}, w (S,), probs (S, C), f_x (C,), f_null (C,) -> (C, M) fp64.
+    Rare fallback on the device (torch.linalg.pinv, fp64)."""
+    link = lambda q: torch.log(q / (1.0 - q))   # noqa: E731
+    Zd = Z.double()
+    y = link(probs.double()) - link(f_null.double())[None, :]
+    delta = link(f_x.double()) - link(f_null.double())
+    E = Zd[:, :-1] - Zd[:, -1:]
+    yt = y - Zd[:, -1:] * delta[None, :]
+    sw = w.double().sqrt()[:, None]
+    sol = torch.linalg.pinv(sw * E) @ (sw * yt)                     # (M-1, C)
+    return torch.cat([sol, (delta - sol.sum(0))[None, :]], 0).t().contiguous()
+
+
 @torch.no_grad()
 def kernel_shap_torch(fw_classifier: Callable[[Tensor], Tensor], Xs_train: Tensor, Xs_explain: Tensor, n_samples: int,
                       batch_size: int, silent: bool = True, seed: int = 0) -> Tensor:
@@ -141,7 +164,9 @@ def kernel_shap_torch(fw_classifier: Callable[[Tensor], Tensor], Xs_train: Tenso
     fw_classifier: (ids (bs, T) int64) -> probabilities (bs, C) without attention masking;
     Xs_train (data_size, T) background token ids; Xs_explain (bs, T).
     Returns (bs, C, T-1) attributions with the CLS feature dropped, following the ModelRecipe contract
-    (recipes/types.py:144-148; the reference's own slicing at l.183-185 depends on the shap version)."""
+    (recipes/types.py:144-148; the reference's own slicing at l.183-185 depends on the shap version).
+    Per explained row, as shap.KernelExplainer does: only the M features whose value differs from at least one background
+    row take part (the rest get 0), M = 0 -> all zeros, M = 1 -> that feature gets link(f(x)) - link(E f)."""
     _ = silent
     dev = Xs_explain.device
     assert dev.type == "cuda", "KernelSHAP runs on CUDA only (no CPU path)"
@@ -153,20 +178,30 @@ def kernel_shap_torch(fw_classifier: Callable[[Tensor], Tensor], Xs_train: Tenso
         outs = [fw_classifier(ids[i:i + batch_size]) for i in range(0, ids.shape[0], batch_size)]
         return torch.cat(outs, 0).double()
 
+    link = lambda q: torch.log(q / (1.0 - q))   # noqa: E731
     f_null = run(Xs_train).mean(dim=0)                          # E_bg f
     f_x = run(Xs_explain)                                        # (bs, C)
     C = f_x.shape[1]
-    Zs, Ws, Ps = [], [], []
+    out = torch.zeros((bs, C, T), dtype=torch.float64, device=dev)
     for i in range(bs):
-        Z, w = sample_coalitions(T, n_samples, dev, seed=seed + i)
-        S = Z.shape[0]
         x = Xs_explain[i]
+        idx = (Xs_train != x[None, :]).any(dim=0).nonzero().reshape(-1)      # varying features
+        M = int(idx.numel())
+        if M == 0:
+            continue
+        if M == 1:
+            out[i, :, idx[0]] = link(f_x[i]) - link(f_null)
+            continue
+        Zm, w = sample_coalitions(M, n_samples, dev, seed=seed + i)         # (S, M) over the varying features only
+        S = Zm.shape[0]
+        Z = torch.zeros((S, T), dtype=torch.int64, device=dev)
+        Z[:, idx] = Zm
         # h_x(z): present features from x, absent ones from each background row -> (S*K, T) synthetic ids
         synth = torch.where(Z[:, None, :].bool(), x[None, None, :], Xs_train[None, :, :]).reshape(S * K, T)
-        Ps.append(run(synth).reshape(S, K, C).mean(dim=1))
-        Zs.append(ops.pack_feature_masks(Z))
-        Ws.append(w)
-    phi, info = ops.kernelshap_solve(torch.stack(Zs), torch.stack(Ws), torch.stack(Ps), f_x, f_null, T, link_logit=True)
-    if int(info.abs().max()) != 0:
-        raise RuntimeError("KernelSHAP Gram matrix is not positive definite: increase n_samples")
-    return phi[:, :, 1:].float()
+        probs = run(synth).reshape(S, K, C).mean(dim=1)
+        phi, info = ops.kernelshap_solve(ops.pack_feature_masks(Zm)[None], w[None], probs[None], f_x[i:i + 1], f_null, M,
+                                         link_logit=True)
+        if int(info.abs().max()) != 0:      # fewer independent coalitions than unknowns: minimum-norm solution
+            phi = _min_norm_wls(Zm, w, probs, f_x[i], f_null)[None]
+        out[i][:, idx] = phi[0]
+    return out[:, :, 1:].float()

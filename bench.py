@@ -274,6 +274,261 @@ def our_config(workload, model_name, B, S, world):
             "l2": "activations per step (>3 GB) exceed L2 (126 MB); no explicit flush"}
 
 
+# ------------------------------------------------------------------------------------------------
+# side workloads (BASELINE.json configs[2] and configs[3]): `--workload bert_base_tayp_vanilla | bert_base_tayp_kernel_shap`
+# ------------------------------------------------------------------------------------------------
+# reference experiments/bert_base_tayp_vanilla/.hparams.json:14-30 with max_position_embeddings = 128 (BASELINE "128-token")
+BERT_BASE_128 = dict(attention_probs_dropout_prob=0.1, explainer_attn_num_layers=1, explainer_head_hidden_size=3072,
+                     explainer_normalize=True, hidden_dropout_prob=0.1, hidden_size=768, intermediate_size=3072, layer_norm_eps=1e-12,
+                     max_position_embeddings=128, num_attention_heads=12, num_hidden_layers=12, num_labels=2, pad_token_id=0,
+                     type_vocab_size=2, vocab_size=30522)
+KS_D, KS_S, KS_C = 128, 2048, 2        # configs[3]: 2048 coalitions / sample, d = 128 token positions, 2 classes
+
+
+def bert_flops_per_eval(c):
+    T, H, I, L = c["max_position_embeddings"], c["hidden_size"], c["intermediate_size"], c["num_hidden_layers"]
+    return float(L * (2 * T * H * 3 * H + 2 * T * H * H + 4 * T * H * I + 4 * T * T * H) + 2 * H * H + 2 * H * c["num_labels"])
+
+
+def cpu_baseline_bert(steps, warmup):
+    """The unmodified reference's BERT path on the host cores: models/shapley.py::mask_shapley_new + Xs_EXT +
+    recipes/vanilla_bert.py::fw_surrogate (scripts/train_explainer.py:148-171), 1 sequence x 32 coalitions per step."""
+    import torch
+    from oracle.make_ref import import_reference
+    got = import_reference()
+    cores = os.cpu_count() or 1
+    if got is None:
+        return {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": "reference files not shipped (python oracle/make_ref.py)"}
+    _pkg, mod, _where = got
+    cores = _force_host_threads()
+    shp, mb = mod("models.shapley"), mod("models.vanilla_bert")
+    rec = mod("recipes.vanilla_bert").vanilla_bert_recipe()
+    torch.manual_seed(3407)
+    cfg = mb.VanillaBertConfig(**BERT_BASE_128)
+    srg = mb.VanillaBertSurrogate(cfg).eval()
+    n, S = rec.n_players(cfg), S_COALITIONS
+    ids = torch.randint(1000, 30000, (1, n + 1), generator=torch.Generator().manual_seed(1))
+    ids[:, 0] = 101
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        masks = shp.mask_shapley_new(S, n)
+        xs_ext = torch.stack([ids[0] for _ in range(S)], dim=0)
+        with torch.no_grad():
+            rec.fw_surrogate(srg, xs_ext, masks)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return {"value": S / sec, "unit": UNIT, "cores": cores, "kind": "reference", "ms_per_step": sec * 1e3,
+            "sample": f"1 sequence x {S} coalitions per step ({steps} timed steps after {warmup} warm-up), unmodified reference BERT-base "
+                      f"T=128 surrogate on torch CPU fp32 ({cores} threads), loop body of scripts/train_explainer.py:148-171"}
+
+
+def cpu_baseline_kernelshap(steps, warmup, per_step=64):
+    """float64 numpy restatement of shap.KernelExplainer's constrained WLS (oracle/kernelshap.py; shap itself is absent from the
+    image and from /root/reference): Gram + Cholesky per explained sample on the host BLAS threads."""
+    import numpy as np
+    from oracle import kernelshap as oks
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(0)
+    Z, w = oks.sample_coalitions(KS_D, KS_S, seed=0)
+    times = []
+    for i in range(warmup + steps):
+        probs = rng.random((per_step, KS_S, KS_C)) * 0.9 + 0.05
+        fx, f0 = rng.random((per_step, KS_C)) * 0.9 + 0.05, rng.random(KS_C) * 0.9 + 0.05
+        t0 = time.perf_counter()
+        for j in range(per_step):
+            oks.explain(probs[j], fx[j], f0, Z, w)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return {"value": per_step / sec, "unit": "solves/s", "cores": cores, "kind": "port", "ms_per_step": sec * 1e3,
+            "sample": f"{per_step} solves per step ({steps} timed steps after {warmup} warm-up): d = {KS_D}, S = {KS_S}, C = {KS_C}; float64 numpy "
+                      "restatement of shap.KernelExplainer's constrained WLS (oracle/kernelshap.py) — `shap` is a third-party "
+                      "dependency absent from the image, so kind = port"}
+
+
+def run_reference_side(args):
+    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
+    if args.workload == "bert_base_tayp_vanilla":
+        base = cpu_baseline_bert(steps, warmup)
+        metric, unit, cfg = METRIC, UNIT, side_config("bert_base_tayp_vanilla", max(1, args.gpus), args)
+    else:
+        base = cpu_baseline_kernelshap(steps, warmup)
+        metric, unit, cfg = "kernelshap_solves_per_sec", "solves/s", side_config("bert_base_tayp_kernel_shap", max(1, args.gpus), args)
+    line = {"impl": "reference", "metric": metric, "value": base["value"], "unit": unit, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": base.get("ms_per_step"), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if unit == UNIT else "f64",
+            "data": "synthetic", "gpu_launches": 0, "config": cfg, "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def side_config(workload, world, args):
+    if workload == "bert_base_tayp_vanilla":
+        return {"workload": workload, "surrogate": "BERT-base, 128 positions (random init, seed 3407)", "sequences_per_gpu_per_step": args.images,
+                "coalitions_per_sequence": S_COALITIONS, "evals_per_gpu_per_step": args.images * S_COALITIONS,
+                "parallelism": f"dp{world} (sequences sharded, final all_gather of probabilities)",
+                "l2": "activations per step (> 1 GB) exceed L2 (126 MB); no explicit flush"}
+    return {"workload": workload, "solves_per_gpu_per_step": args.ks_batch, "coalitions_per_sample": KS_S, "features": KS_D, "classes": KS_C,
+            "parallelism": f"replicas x{world} (independent explained samples, no collective)",
+            "l2": "inputs per step (84 MB) + Gram workspace (127 MB) exceed L2 (126 MB); no explicit flush"}
+
+
+def run_ours_side(args):
+    """BASELINE.json configs[2] (BERT-base 128-token masked surrogate evaluation) and configs[3] (KernelSHAP batched Gram +
+    Cholesky) under the same timing contract as the headline workload."""
+    import torch
+    import torch.distributed as dist
+
+    import autognothi_b200  # noqa: F401
+    from autognothi_b200 import _native as nat
+    from autognothi_b200 import ops
+    from autognothi_b200.models import shapley as ash
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peaks = load_peaks()
+    kshap = args.workload == "bert_base_tayp_kernel_shap"
+    copy_stream = torch.cuda.Stream(device=dev)
+    if not kshap:
+        from autognothi_b200.recipes.vanilla_bert import vanilla_bert_recipe
+        rec = vanilla_bert_recipe()
+        cfg = rec.t_config(**BERT_BASE_128)
+        n = rec.n_players(cfg)
+        torch.manual_seed(3407)
+        srg = rec.t_surrogate(cfg).to(dev).eval()
+        srg.agb_precision = "bf16"
+        B, S = args.images, S_COALITIONS
+        units = B * S
+        g = torch.Generator().manual_seed(1234 + rank)
+        ids_host = torch.randint(1000, 30000, (B, n + 1), generator=g)
+        ids_host[:, 0] = 101
+        ids_host = ids_host.pin_memory()
+        ids_dev = ids_host.to(dev)
+        C = cfg.num_labels
+        out_host = torch.empty((units, C), dtype=torch.float32).pin_memory()
+        h2d, d2h = ids_host.numel() * 8, units * C * 4
+
+        def step(i, xs):
+            pm = ash.mask_shapley_new(units, n, device=dev, rng="philox", seed=3407 + rank, offset=i * units, packed=True)
+            with torch.no_grad():
+                return rec.fw_surrogate(srg, xs, pm)[0]
+
+        def step_resident(i):
+            return step(i, ids_dev)
+
+        def step_e2e(i):
+            xs = ids_host.to(dev, non_blocking=True)
+            out_host.copy_(step(i, xs), non_blocking=True)
+    else:
+        B = units = args.ks_batch
+        words = (KS_D + 31) // 32
+        gen = torch.Generator(device=dev).manual_seed(99 + rank)
+        dense = (torch.rand((B * KS_S, KS_D), device=dev, generator=gen) > torch.rand((B * KS_S, 1), device=dev, generator=gen)).to(torch.int64)
+        Zp = ops.pack_feature_masks(dense).reshape(B, KS_S, words)
+        w = torch.rand((B, KS_S), device=dev, generator=gen, dtype=torch.float64) + 0.1
+        probs = torch.rand((B, KS_S, KS_C), device=dev, generator=gen, dtype=torch.float64) * 0.9 + 0.05
+        fx = torch.rand((B, KS_C), device=dev, generator=gen, dtype=torch.float64) * 0.9 + 0.05
+        f0 = torch.rand((KS_C,), device=dev, generator=gen, dtype=torch.float64) * 0.9 + 0.05
+        host = [t.cpu().pin_memory() for t in (Zp, w, probs, fx)]
+        out_host = torch.empty((B, KS_C, KS_D), dtype=torch.float64).pin_memory()
+        h2d, d2h = sum(t.numel() * t.element_size() for t in host), out_host.numel() * 8
+
+        def step_resident(i):
+            return ops.kernelshap_solve(Zp, w, probs, fx, f0, KS_D)[0]
+
+        def step_e2e(i):
+            z_, w_, p_, fx_ = (t.to(dev, non_blocking=True) for t in host)
+            out_host.copy_(ops.kernelshap_solve(z_, w_, p_, fx_, f0, KS_D)[0], non_blocking=True)
+
+    def timed(fn, steps, warmup, profile=False):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        l0 = nat.LAUNCHES
+        nat.PROFILE = [] if profile else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        prof, nat.PROFILE = nat.PROFILE, None
+        ms = torch.tensor([e0.elapsed_time(e1), wall], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0]), float(ms[1]), nat.LAUNCHES - l0, prof
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, _, launches, prof = timed(step_resident, args.steps, args.warmup, profile=True)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e, wall_e, _, _ = timed(step_e2e, args.steps, max(2, args.warmup // 2))
+    ms_e = max(ms_e, wall_e)                     # results are on the host: the host clock bounds the same region
+    value = world * units * args.steps / (ms * 1e-3)
+    e2e_value = world * units * args.steps / (ms_e * 1e-3)
+    by_kernel = {}
+    for name, meta, a, b, *_ in prof:
+        acc = by_kernel.setdefault(name, [0.0, 0.0, 0])
+        acc[0] += a.elapsed_time(b); acc[1] += (meta or 0.0); acc[2] += 1
+    total_t = sum(v[0] for v in by_kernel.values()) or 1e-9
+    shares = {k: round(v[0] / total_t, 4) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1][0])}
+    if not kshap:
+        gemm = [sum(by_kernel.get(k, [0, 0, 0])[i] for k in ("agb_gemm_bf16", "agb_gemm_bf16_fused")) for i in range(3)]
+        achieved = gemm[1] / max(gemm[0], 1e-9) * 1e-9
+        roofline = {"bound": "tensor", "kernel": "gemm_pair_kernel / gemm_tc_kernel (agb_gemm_bf16)", "achieved": achieved,
+                    "peak": peaks["bf16_tflops_sustained"], "peak_kind": f"bf16_tflops_sustained, {peaks['source']}", "unit": "TFLOP/s",
+                    "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None, "avg_launch_us": gemm[0] / max(gemm[2], 1) * 1e3,
+                    "launches": gemm[2], "share_of_step": gemm[0] / total_t, "step_shares": shares,
+                    "note": "masked tokens are dropped before the encoder (exact for additive masks), so the GEMMs run on ~half of "
+                            "the dense token rows; achieved counts the FLOPs of the rows actually multiplied"}
+        metric, unit, dtype = METRIC, UNIT, "bf16"
+        extra = {"dense_equivalent_tflops_per_gpu": value / world * bert_flops_per_eval(BERT_BASE_128) * 1e-12,
+                 "flops_per_eval_dense": bert_flops_per_eval(BERT_BASE_128)}
+    else:
+        # SURVEY.md 8d: 112 KB algorithmic per solve (packed Z 32 KB + y 16 KB + Gram 64 KB as fp32) -> HBM bound as north_star
+        # assigns it; this implementation works in float64 (weights 16 KB, probabilities 32 KB, Gram 127 KB written + read)
+        alg_bytes = KS_S * ((KS_D + 31) // 32) * 4 + KS_S * KS_C * 4 + (KS_D - 1) ** 2 * 4
+        k = by_kernel.get("agb_kernelshap_solve", [ms, 0.0, args.steps])
+        achieved = alg_bytes * units / (k[0] / max(k[2], 1) * 1e-3) * 1e-9
+        gram_flops = 2.0 * KS_S * (KS_D - 1) ** 2 + (KS_D - 1) ** 3 / 3.0
+        roofline = {"bound": "hbm", "kernel": "kernelshap_gram_kernel + kernelshap_solve_kernel (agb_kernelshap_solve)", "achieved": achieved,
+                    "peak": peaks["hbm_gbs"], "peak_kind": f"hbm_gbs, {peaks['source']}", "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                    "traffic": None, "avg_launch_us": k[0] / max(k[2], 1) * 1e3, "launches": k[2], "share_of_step": k[0] / total_t,
+                    "algorithmic_bytes_per_solve": alg_bytes, "step_shares": shares,
+                    "fp64_tflops": value / world * gram_flops * 1e-12,
+                    "note": "the Gram accumulation is a float64 contraction (2 S d^2 = 66 MFLOP per solve) on the fp64 FMA pipe; against "
+                            "the HBM roofline north_star assigns the solve it is compute-bound by two orders of magnitude"}
+        metric, unit, dtype = "kernelshap_solves_per_sec", "solves/s", "f64"
+        extra = {}
+    if rank == 0:
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
+                "data": "synthetic", "config": side_config(args.workload, world, args),
+                "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / args.steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
+        line.update(extra)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_kernelshap(2, 1) if kshap else cpu_baseline_bert(2, 1)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -664,6 +919,7 @@ def main():
                          "vit_large); the other two are BASELINE.json configs[2] and configs[3] as side workloads")
     ap.add_argument("--grad-wire", default="fp32", choices=["fp32", "bf16"],
                     help="wire format of the gradient all-reduce of the training leg (fp32 = exact averaging)")
+    ap.add_argument("--ks-batch", type=int, default=1024, help="explained samples per GPU per step of the KernelSHAP workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the explainer-training leg")
     ap.add_argument("--no-ltt", action="store_true", help="skip the ladder-side-tuning leg")

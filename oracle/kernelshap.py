@@ -7,6 +7,14 @@ here, and no reference test pins a value at that boundary.  What follows restate
 estimator (Lundberg & Lee 2017) the way `shap.KernelExplainer.solve` implements it — eliminate one feature
 with the efficiency constraint, solve the remaining weighted least squares — WITHOUT shap's optional
 `l1_reg="auto"` LassoLarsIC feature pre-selection; coalitions and kernel weights are inputs.
+
+OMITTED ON PURPOSE, stated loudly: shap's default l1_reg="auto" runs LassoLarsIC(criterion="aic") on the
+sqrt-weighted, constraint-eliminated design whenever the sampled coalitions cover less than 20 % of the 2^M subset
+space (always for M >= 14 at the reference's n_samples = 512) and keeps only the features with a non-zero Lasso
+coefficient before the final least squares.  Neither this restatement nor the CUDA path applies that pre-selection:
+both solve the un-regularised weighted least squares over all varying features (`explain_varying` below restates
+shap's restriction to the features that differ between the explained row and the background, and the minimum-norm
+solution numpy.linalg.lstsq returns when the system is under-determined).
 """
 from __future__ import annotations
 
@@ -115,3 +123,43 @@ def explain(probs_coalitions: np.ndarray, prob_full: np.ndarray, prob_null: np.n
     y = logit(probs_coalitions) - logit(prob_null)[None, :]
     delta = logit(prob_full) - logit(prob_null)
     return wls_solve(Z, w, y, delta)
+
+
+def varying_features(x: np.ndarray, background: np.ndarray) -> np.ndarray:
+    """Indices of the features of x that differ from at least one background row (shap.KernelExplainer.varying_groups)."""
+    return np.nonzero((np.asarray(background) != np.asarray(x)[None, :]).any(axis=0))[0]
+
+
+def explain_varying(model, x: np.ndarray, background: np.ndarray, Zm: np.ndarray, w: np.ndarray) -> np.ndarray:
+    """KernelSHAP for one row the way shap.KernelExplainer.explain organises it (logit link): regression over the M
+    varying features only, the rest get 0; M = 0 -> zeros, M = 1 -> that feature gets link(f(x)) - link(E f).
+    model: (n, T) int64 ids -> (n, C) probabilities; Zm (S, M) coalitions over the varying features, w (S,) weights.
+    Under-determined systems take the minimum-norm least-squares solution (numpy lstsq).  -> phi (C, T)"""
+    x = np.asarray(x)
+    background = np.asarray(background)
+    K, T = background.shape
+    f_null = model(background).astype(np.float64).mean(axis=0)
+    f_x = model(x[None, :]).astype(np.float64)[0]
+    C = f_x.shape[0]
+    idx = varying_features(x, background)
+    M = idx.size
+    phi = np.zeros((C, T), dtype=np.float64)
+    if M == 0:
+        return phi
+    if M == 1:
+        phi[:, idx[0]] = logit(f_x) - logit(f_null)
+        return phi
+    S = Zm.shape[0]
+    assert Zm.shape[1] == M
+    Z = np.zeros((S, T), dtype=bool)
+    Z[:, idx] = Zm != 0
+    synth = np.where(Z[:, None, :], x[None, None, :], background[None, :, :]).reshape(S * K, T)
+    probs = model(synth).astype(np.float64).reshape(S, K, C).mean(axis=1)
+    y = logit(probs) - logit(f_null)[None, :]
+    delta = logit(f_x) - logit(f_null)
+    E = Zm[:, :-1].astype(np.float64) - Zm[:, -1:].astype(np.float64)
+    if np.linalg.matrix_rank(E) < M - 1:
+        phi[:, idx] = wls_solve_lstsq(Zm, w, y, delta)
+    else:
+        phi[:, idx] = wls_solve(Zm, w, y, delta)
+    return phi

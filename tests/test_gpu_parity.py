@@ -724,10 +724,11 @@ def test_overlapped_grad_reducer_is_transparent_on_one_rank(agb, golden_dir, wir
             got = grads()
             assert len(red.flat) > 3
             for k, ref in plain.items():
-                if wire == "fp32":
-                    assert torch.equal(got[k], ref), (step, k)
-                else:
-                    assert torch.equal(got[k], ref.to(torch.bfloat16).float()), (step, k)
+                # (a few gradients — bias column sums, split-K weight gradients — are accumulated with atomics and differ in the
+                # last bits from run to run, so "identical" is up to that noise)
+                scale = float(ref.abs().max()) + 1e-30
+                tol = 1e-5 if wire == "fp32" else 1e-2
+                assert float((got[k] - ref).abs().max()) <= tol * scale, (step, k, float((got[k] - ref).abs().max()), scale)
     finally:
         del exp.agb_grad_reducer
 
@@ -813,6 +814,78 @@ def test_kernel_shap_recipe_end_to_end(agb):
     assert logits.shape == (2, 2) and attr.shape == (2, 2, n) and torch.isfinite(attr).all()
     with pytest.raises(NotImplementedError):
         rec.fw_explainer(exp, xs, None, None, None)
+
+
+def _toy_ids_model(beta, bias=-0.3):
+    def np_model(ids):
+        logit1 = bias + (np.sin(np.asarray(ids) * 0.37) * beta[None, :]).sum(axis=1)
+        p1 = 1.0 / (1.0 + np.exp(-logit1))
+        return np.stack([1.0 - p1, p1], axis=1)
+
+    tb = torch.from_numpy(beta).to(DEV)
+
+    def torch_model(ids):
+        logit1 = bias + (torch.sin(ids.double() * 0.37) * tb[None, :]).sum(dim=1)
+        p1 = torch.sigmoid(logit1)
+        return torch.stack([1.0 - p1, p1], dim=1)
+    return np_model, torch_model
+
+
+@pytest.mark.parametrize("T,K,S,n_vary", [(24, 3, 400, 6), (40, 2, 300, 40), (64, 2, 40, 64), (16, 2, 64, 1), (16, 2, 64, 2)])
+def test_kernel_shap_torch_vs_oracle_varying_features(agb, T, K, S, n_vary):
+    """kernel_shap_torch against oracle.kernelshap.explain_varying on the SAME coalitions: only varying features take part,
+    M = 1 / M = 2 edge cases, and the under-determined case (S = 40 paired coalitions for 63 unknowns) takes the
+    minimum-norm solution instead of raising."""
+    from autognothi_b200.models import kernel_shap_bert as ksb
+    from oracle import kernelshap as oks
+    rng = np.random.default_rng(T + S)
+    background = rng.integers(5, 50, size=(K, T))
+    x = background[0].copy()
+    vary = np.sort(rng.choice(np.arange(1, T), size=min(n_vary, T - 1), replace=False)) if n_vary < T else np.arange(T)
+    x[vary] += 100
+    if n_vary < T:
+        background[:, :] = background[0][None, :]      # every other column identical to x
+    beta = rng.standard_normal(T) * 0.3
+    np_model, torch_model = _toy_ids_model(beta)
+    got = ksb.kernel_shap_torch(torch_model, torch.from_numpy(background).to(DEV), torch.from_numpy(x[None]).to(DEV), S, 4096, seed=3)
+    idx = oks.varying_features(x, background)
+    M = idx.size
+    if M >= 2:
+        Zm, w = ksb.sample_coalitions(M, S, torch.device(DEV), seed=3)
+        Zm, w = Zm.cpu().numpy(), w.cpu().numpy()
+    else:
+        Zm, w = np.zeros((0, M)), np.zeros(0)
+    ref = oks.explain_varying(np_model, x, background, Zm, w)
+    assert got.shape == (1, 2, T - 1)
+    np.testing.assert_allclose(got[0].cpu().numpy(), ref[:, 1:], rtol=2e-4, atol=2e-5)
+
+
+def test_kernel_shap_reference_hparams_shape_runs(agb):
+    """The reference's own KernelSHAP hparams (experiments/bert_base_tayp_kernel_shap/.hparams.json:30-31: 512 positions,
+    kernel_shap_n_samples = 512, data_size = 8) are under-determined for rows with many varying tokens; fw_final must
+    still produce finite attributions that satisfy efficiency (sum = link f(x) - link E f)."""
+    from autognothi_b200.recipes.kernel_shap_bert import kernel_shap_bert_recipe
+    rec = kernel_shap_bert_recipe()
+    base = ocfg.get_config("bert_mini_512")
+    cfgd = dict(base, kernel_shap_n_samples=512, kernel_shap_data_size=8)
+    cfg = rec.t_config(**cfgd)
+    cls = rec.t_classifier(cfg)
+    cls.load_state_dict({k: torch.from_numpy(v) for k, v in synth.surrogate_state(base, 0).items()})
+    cls = cls.to(DEV).eval()
+    exp = rec.t_explainer(cfg).to(DEV)
+    with torch.no_grad():
+        exp.Xs_train.copy_(torch.from_numpy(synth.inputs(base, 8, seed=9)).to(DEV))
+    final = rec.conv_explainer_final(cfg, None, cls, None, exp).eval()
+    final.classifier.agb_precision = "fp32"
+    xs = torch.from_numpy(synth.inputs(base, 1, seed=0)).to(DEV)
+    probs, attr = rec.fw_final(final, xs)
+    n = rec.n_players(cfg)
+    assert attr.shape == (1, 2, n) and torch.isfinite(attr).all()
+    from autognothi_b200.models.shapley import PackedMasks
+    f_null = final.classifier(exp.Xs_train, PackedMasks.ones(8, n, DEV), None).double().mean(0)
+    link = lambda q: torch.log(q / (1 - q))   # noqa: E731
+    delta = link(probs[0].double()) - link(f_null)
+    torch.testing.assert_close(attr[0].double().sum(-1), delta, rtol=1e-3, atol=1e-4)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -35,6 +35,23 @@ def test_library_exports_every_declared_symbol(built):
     assert lib.agb_version() >= 100
 
 
+def test_torch_extension_has_one_op_per_launching_entry_point():
+    """lib/libagb_torch.so (TORCH_LIBRARY "agb", generated from the header): every C-ABI function that takes a stream is
+    callable as torch.ops.agb.<name>; the remaining (configuration / diagnostics) entry points stay on ctypes.  Loads and
+    resolves without a GPU."""
+    import torch
+    from autognothi_b200 import _native
+    assert _native.BINDING == "torch" and _native.TORCH_OPS
+    launching = {n for n, (r, a) in _native.PROTOTYPES.items() if r == "int" and any(pn == "stream" and "*" in pt for pt, pn in a)}
+    assert set(_native.TORCH_OPS) == launching and len(launching) >= 40
+    for name in launching:
+        assert hasattr(torch.ops.agb, name), name
+    # CPU tensors are refused by the op itself (no CPU fallback); no launch is attempted here: the ops ask at::cuda for the
+    # current stream, which needs a device
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        torch.ops.agb.agb_pack_masks_i64(torch.zeros(4, 196, dtype=torch.int64), 4, 196, 1, None, 7)
+
+
 def test_every_prototype_cites_the_reference():
     """each entry point's comment names the reference file:line it replaces (drop-in boundary rule)"""
     src = open(HEADER).read()
