@@ -676,10 +676,8 @@ int attention_pipe_prefix(const bf16* qkv, const int* nkeep, int rows, int T, in
   if (rows == 0) return AGB_OK;
   AGB_REQUIRE(qkv && nkeep && ctx, "null pointer");
   AGB_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(ctx) & 15) == 0, "alignment");
-  // kept-first order: the second-generation kernel stays the default (396 vs 418 us at the bench shape: with few live keys
-  // an item is bound by its fixed hand-off latencies, which the 16-warp split kernel has more of —
-  // profiles/r02_attention_split_notes.txt); variant 3 selects the split kernel for A/B runs
-  if (g_attention_variant == 3) {
+  // third generation (agb_attention_split.cu) for T <= 208: 338 vs 395 us at the bench shape (profiles/r02_attention_split_notes.txt)
+  if (g_attention_variant == 0 || g_attention_variant == 3) {
     const int rc = attention_split(qkv, nullptr, 0, rows, 1, T, H, heads, nkeep, nullptr, ctx, stream);
     if (rc != AGB_ERR_UNSUPPORTED) return rc;
   }

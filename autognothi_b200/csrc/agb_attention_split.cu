@@ -9,20 +9,22 @@
 // epilogue AND the next S MMA into the same region had finished (~40 % of its time), it read S from TMEM twice (row max,
 // then exp), and one thread walked all 208 key columns of a row.  XU (MUFU) pipe 31 % busy, tensor pipe 17 %.
 //
-// Per SM, one persistent CTA of 16 warps over "items" (unit = (row, head), m-tile); item k lives in TMEM region k & 1:
+// Per SM, one persistent CTA of 24 warps over "items" (unit = (row, head), m-tile); item k lives in TMEM region k & 1:
+//   (24 warps)
 //   warp 0       TMA producer: K/V of a unit into a 3-deep ring, Q tiles into a 2-deep ring
 //   warp 1       tcgen05 issuer  S_k = Q_k K^T  (N trimmed to the live keys), as soon as region k & 1 is drained
 //   warp 2       tcgen05 issuer  O_k = P_k V    the moment P_k is complete
 //   warp 3       key prep: zero the K rows of masked keys (logit exactly 0) or, in kept-first order, build the V row of
 //                the virtual key that stands for all masked keys
 //   warps 4-7    epilogue: O_k / rowsum -> bf16 ctx (thread = query row), then release the region for S_{k+2}
-//   warps 8-15   softmax, item after item: while they work on item k in one region, the other region runs
-//                P V (k-1) -> epilogue (k-1) -> S (k+1), so S_{k+1} is waiting for them when they finish.  Two warps per
-//                TMEM lane quarter split the key columns (half 0 overlays its P on the S columns it has consumed, half 1
-//                writes its P into the region's spare columns [208, 256)).  S is read ONCE: the row's reference maximum
-//                is the maximum over the first chunk of both halves and is raised later only if a chunk exceeds it by
-//                2^24 (softmax is shift-invariant; the P already written is then rescaled in place by an exact power of
-//                two).  The tcgen05.ld of the next chunk is in flight while the current one is exponentiated.
+//   warps 8-23   softmax: two groups of 8 warps, group g serves the items of parity g (its own TMEM region), so that one
+//                group exponentiates while the other waits for  P V (k) -> epilogue (k) -> S (k+2)  on its region: the
+//                XU (MUFU) pipe, 16 exp2 / clk / SM and the floor of this kernel, always has a group feeding it.  Inside a
+//                group two warps per TMEM lane quarter split the key columns (half 0 overlays its P on the S columns it
+//                has consumed, half 1 writes its P into the region's spare columns [208, 256)).  S is read ONCE: the
+//                row's reference maximum is the maximum over the first chunk of both halves and is raised later only if a
+//                chunk exceeds it by 2^24 (softmax is shift-invariant; the P already written is then rescaled in place by
+//                an exact power of two).
 // Kept-first order (AP "prefix" mode, see agb_attention_pipe.cu): keys [0, nkeep) are live, the masked rest is ONE virtual
 // key at column nkeep (logit log(n_masked) / scale, V row = mean of the masked V rows); S, the softmax and P V then only
 // span round16(nkeep + 1) key columns.
@@ -53,7 +55,8 @@ struct Att3Params {
   const uint8_t* dst_pos; // optional (rows, T): query token t of row r is written to token position dst_pos[r, t]
   bf16* ctx;
   long long* trace;
-  int debug;              // diagnostics (AGB_ATTN_DEBUG): 1 = softmax touches only its first chunk, 2 = no MMAs are issued
+  int debug;              // diagnostics (AGB_ATTN_DEBUG): 1 = softmax touches only its first chunk, 2 = no MMAs are issued,
+                          // 4 = exact two-pass row maximum instead of the lazily raised reference maximum, 8 = spin-wait hand-offs
 };
 
 #define A3_TRACE(k, slot)                                                                                         \
@@ -112,8 +115,8 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint64_t* o_full = bars + 17;                 // [2]
   uint64_t* o_free = bars + 19;                 // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
-  float* xch = reinterpret_cast<float*>(bars + 24);   // [2 kinds][4 quarters][4 splits][32 lanes] exchange between the column splits
-  float* rowsum = xch + 2 * 512;                       // [2 regions][4 splits][128 rows]
+  float* xch = reinterpret_cast<float*>(bars + 24);   // [2 kinds][2 groups][4 quarters][2 halves][32 lanes] exchange between the halves
+  float* rowsum = xch + 2 * 512;                       // [2 regions][2 halves][128 rows]
 
   const int warp = warp_idx_uniform();
   const int lane = threadIdx.x & 31;
@@ -125,7 +128,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       mbar_init(smem_u32(&q_full[i]), 1);
       mbar_init(smem_u32(&q_empty[i]), 1);
       mbar_init(smem_u32(&s_full[i]), 1);
-      mbar_init(smem_u32(&p_full[i]), 16);
+      mbar_init(smem_u32(&p_full[i]), 8);
       mbar_init(smem_u32(&o_full[i]), 1);
       mbar_init(smem_u32(&o_free[i]), 4);
     }
@@ -198,7 +201,10 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         mbar_wait(smem_u32(&kv_prep[b]), (ui / R) & 1);
       }
       mbar_wait(smem_u32(&q_full[qb]), nq & 1);
-      if (n > 0) mbar_wait(smem_u32(&o_free[g]), (n - 1) & 1);
+      if (n > 0) {
+        if (p.debug & 8) mbar_wait_spin(smem_u32(&o_free[g]), (n - 1) & 1);
+        else mbar_wait(smem_u32(&o_free[g]), (n - 1) & 1);
+      }
       tc_fence_after();
       const uint32_t aq = sq0 + qb * (16384 >> 4);
       const uint32_t ak = skv0 + b * 2 * kvb16;
@@ -223,22 +229,20 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const int ui = k / mt, m = k - ui * mt;
       const int b = ui % R, g = k & 1, n = k >> 1;
       if (PREFIX && m == 0) n16 = unit_keys(ui) >> 4;
-      mbar_wait(smem_u32(&p_full[g]), n & 1);
+      if (p.debug & 8) mbar_wait_spin(smem_u32(&p_full[g]), n & 1);
+      else mbar_wait(smem_u32(&p_full[g]), n & 1);
       A3_TRACE(k, 2);
       tc_fence_after();
       const uint32_t d_o = tmem_base + g * A3_REGION + A3_O_COL;
       uint64_t dv = dv0 + (skv0 + b * 2 * kvb16 + kvb16);
       if (!(p.debug & 2)) {
-        // P of column split i (u_i 16-key steps starting at key column b_i): splits 0, 1 overlay the start of their own S
-        // columns, splits 2, 3 live in the spare columns (see the softmax warps)
-        int ks = 0, b_i = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int u_i = (n16 >> 2) + (i < (n16 & 3) ? 1 : 0);
-          uint32_t a_p = tmem_base + g * A3_REGION + (i < 2 ? b_i : A3_SPARE + (i - 2) * 24);
-          for (int j = 0; j < u_i; ++j, ++ks, a_p += 8, dv += (2048 >> 4)) umma_ts_e(e, d_o, a_p, dv, idesc_o, ks != 0 ? 1u : 0u);
-          b_i += u_i * 16;
-        }
+        // P of the lower key half overlays the start of the region, the upper half lives in the spare columns
+        const int ca = (n16 + 1) >> 1;
+        uint32_t a_p = tmem_base + g * A3_REGION;
+        int ks = 0;
+        for (; ks < ca; ++ks, a_p += 8, dv += (2048 >> 4)) umma_ts_e(e, d_o, a_p, dv, idesc_o, ks != 0 ? 1u : 0u);
+        a_p = tmem_base + g * A3_REGION + A3_SPARE;
+        for (; ks < n16; ++ks, a_p += 8, dv += (2048 >> 4)) umma_ts_e(e, d_o, a_p, dv, idesc_o, 1u);
       }
       umma_commit_e<1>(e, smem_u32(&o_full[g]));
       if (m == mt - 1) umma_commit_e<1>(e, smem_u32(&kv_empty[b]));
@@ -309,7 +313,8 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const int row = u / p.heads, head = u - row * p.heads;
       const bool warp_live = (m * 128 + qd * 32) < T;
       const uint32_t o_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + g * A3_REGION + A3_O_COL;
-      mbar_wait(smem_u32(&o_full[g]), n & 1);
+      if (p.debug & 8) mbar_wait_spin(smem_u32(&o_full[g]), n & 1);
+      else mbar_wait(smem_u32(&o_full[g]), n & 1);
       if (qd == 0) A3_TRACE(k, 6);
       tc_fence_after();
       // first 32 output dims -> packed bf16, then the other 32 (keeps the live registers under the 80 of this launch)
@@ -317,8 +322,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       float inv = 0.f;
       if (warp_live) {
         tmem_ld32(o_addr, o);
-        inv = 1.0f / ((rowsum[(g * 4 + 0) * 128 + r] + rowsum[(g * 4 + 1) * 128 + r]) +
-                      (rowsum[(g * 4 + 2) * 128 + r] + rowsum[(g * 4 + 3) * 128 + r]));
+        inv = 1.0f / (rowsum[(g * 2 + 0) * 128 + r] + rowsum[(g * 2 + 1) * 128 + r]);
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 16; ++j) w0[j] = pack_bf16x2(__uint_as_float(o[2 * j]) * inv, __uint_as_float(o[2 * j + 1]) * inv);
@@ -353,19 +357,20 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   } else {
     // ------------------------------ softmax ------------------------------
     const int qd = warp & 3;                        // TMEM lane quarter this warp may touch
-    const int split = (warp - 8) >> 2;              // which quarter of the key columns
+    const int g = ((warp - 8) >> 2) & 1;            // item parity (= TMEM region) this warp serves
+    const int split = (warp - 8) >> 3;              // lower / upper half of the key columns
     const int r = qd * 32 + lane;
     const float scale_log2 = 0.125f * 1.4426950408889634f;
-    float* xmax = xch + (qd * 4) * 32;              // [4 splits][32 lanes]
+    float* xmax = xch + ((g * 4 + qd) * 2) * 32;    // [2 halves][32 lanes]
     float* xfin = xmax + 512;
-    const int bar_id = 1 + qd;
-    for (int k = 0; k < n_items; ++k) {
-      const int g = k & 1, n = k >> 1;
+    const int bar_id = 1 + g * 4 + qd;
+    for (int k = g; k < n_items; k += 2) {
+      const int n = k >> 1;
       const int ui = k / mt, m = k - ui * mt;
       const int u = blockIdx.x + ui * grid;
       const int row = u / p.heads;
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + g * A3_REGION;
-      const bool warp_live = (m * 128 + qd * 32) < T;     // warp-uniform, identical for the four splits
+      const bool warp_live = (m * 128 + qd * 32) < T;     // warp-uniform, identical for both halves
       int Tk = T, vj = -1;
       float vval = 0.f;
       if (PREFIX) {
@@ -378,20 +383,20 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
       const int NKu = (Tk + 15) & ~15;
       const int n16 = NKu >> 4;
-      // my key columns [c_beg, c_end): the 16-column steps are dealt out 4-ways, the first (n16 & 3) splits get one more
-      const int ub = n16 >> 2, ux = n16 & 3;
-      const int c_beg = (split * ub + (split < ux ? split : ux)) * 16;
-      const int c_end = c_beg + (ub + (split < ux ? 1 : 0)) * 16;
+      // my key columns [c_beg, c_end): the lower half gets ceil(n16 / 2) of the 16-column steps
+      const int ca = (n16 + 1) >> 1;
+      const int c_beg = split ? ca * 16 : 0, c_end = split ? NKu : ca * 16;
       const int tail = NKu - 16;                           // the only chunk with dead columns / the virtual key
       const int fast_end = c_end < tail ? c_end : tail;
       const uint32_t tail_live = (Tk - tail) >= 16 ? 0xFFFFu : ((1u << (Tk - tail)) - 1u);
-      // P (bf16 pairs): splits 0, 1 overlay the start of their OWN S columns (writes trail reads), splits 2, 3 use the spare
-      // columns [208, 256) because the O accumulator will overwrite [128, 192)
-      const uint32_t p_start = lane_addr + (split < 2 ? (uint32_t)c_beg : (uint32_t)(A3_SPARE + (split - 2) * 24));
+      // P (bf16 pairs): the lower half overlays the S columns it has consumed (writes trail reads), the upper half uses the
+      // spare columns [208, 256): the O accumulator will overwrite [128, 192), and S columns the lower half still has to read
+      // must not be touched
+      const uint32_t p_start = lane_addr + (split ? (uint32_t)A3_SPARE : 0u);
 
       mbar_wait(smem_u32(&s_full[g]), n & 1);
       if (qd == 0 && split == 0) A3_TRACE(k, 4);
-      if (qd == 0 && split == 3) A3_TRACE(k, 13);
+      if (qd == 0 && split == 1) A3_TRACE(k, 13);
       tc_fence_after();
       if (warp_live) {
         uint32_t s[32];
@@ -438,13 +443,48 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           for (int j = 0; j < 4; ++j) sum[j] *= f;
         };
         int c = c_beg;
+        float mysum;
+        if (p.debug & 4) {
+          // ---- A/B variant: exact row maximum first, one exchange between the halves, then the exponentials.  An unloaded
+          // tcgen05.ld costs ~35 cycles per 32 columns (profiles/r02_xu_tmem_microbench.txt), but here it queues behind the
+          // other group's MUFU stream in the MIO pipe and the extra pass costs ~2000 cycles per item: not the default ----
+          float mx = -INFINITY;
+          for (int cc = c_beg; cc < c_end;) {
+            const int ww = load_chunk(cc);
+            mx = a3_max<32>(s, mx);
+            cc += ww;
+          }
+          if (qd == 0 && split == 0) A3_TRACE(k, 8);
+          xmax[split * 32 + lane] = mx;
+          a3_bar_sync(bar_id, 64);
+          if (qd == 0 && split == 0) A3_TRACE(k, 9);
+          const float m_s = fmaxf(xmax[lane], xmax[32 + lane]) * scale_log2;
+          while (c < c_end) {
+            const int w = load_chunk(c);
+            if (w == 32) {
+              uint32_t pk[16];
+              a3_exp<32>(s, pk, scale_log2, m_s, sum);
+              tmem_st16(p_cur, pk);
+              p_cur += 16;
+            } else {
+              uint32_t pk[8];
+              a3_exp<16>(*reinterpret_cast<uint32_t(*)[16]>(&s[0]), pk, scale_log2, m_s, sum);
+              tmem_st8(p_cur, pk);
+              p_cur += 8;
+            }
+            c += w;
+            if (p.debug & 1) break;
+          }
+          if (qd == 0 && split == 0) A3_TRACE(k, 10);
+          mysum = (sum[0] + sum[1]) + (sum[2] + sum[3]);
+        } else {
         int w = load_chunk(c);
         if (qd == 0 && split == 0) A3_TRACE(k, 8);
         float lm = a3_max<32>(s, -INFINITY) * scale_log2;
         xmax[split * 32 + lane] = lm;
-        a3_bar_sync(bar_id, 128);
+        a3_bar_sync(bar_id, 64);
         if (qd == 0 && split == 0) A3_TRACE(k, 9);
-        float m_s = fmaxf(fmaxf(xmax[lane], xmax[32 + lane]), fmaxf(xmax[64 + lane], xmax[96 + lane]));   // scaled reference maximum
+        float m_s = fmaxf(xmax[lane], xmax[32 + lane]);   // scaled reference maximum of the row
         while (w > 0) {
           if (w == 32) {
             uint32_t pk[16];
@@ -468,19 +508,20 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             m_s = m_new;
           }
         }
-        // ---- reconcile the four splits: common reference maximum, row sum ----
+        // ---- reconcile the two halves: common reference maximum, row sum ----
         if (qd == 0 && split == 0) A3_TRACE(k, 10);
-        float mysum = (sum[0] + sum[1]) + (sum[2] + sum[3]);
+        mysum = (sum[0] + sum[1]) + (sum[2] + sum[3]);
         xfin[split * 32 + lane] = m_s;
-        a3_bar_sync(bar_id, 128);
+        a3_bar_sync(bar_id, 64);
         if (qd == 0 && split == 0) A3_TRACE(k, 11);
-        const float m_fin = fmaxf(fmaxf(xfin[lane], xfin[32 + lane]), fmaxf(xfin[64 + lane], xfin[96 + lane]));
+        const float m_fin = fmaxf(xfin[lane], xfin[32 + lane]);
         if (__any_sync(0xffffffffu, m_fin > m_s)) {                          // rare: another split raised its maximum
           const float f = ex2_approx(m_s - m_fin);
           rescale(f);
           mysum *= f;
         }
-        rowsum[(g * 4 + split) * 128 + r] = mysum;
+        }
+        rowsum[(g * 2 + split) * 128 + r] = mysum;
         tmem_wait_st();
         if (qd == 0 && split == 0) A3_TRACE(k, 12);
       }
@@ -488,7 +529,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&p_full[g]));
       if (qd == 0 && split == 0) A3_TRACE(k, 5);
-      if (qd == 0 && split == 3) A3_TRACE(k, 15);
+      if (qd == 0 && split == 1) A3_TRACE(k, 15);
     }
   }
 

@@ -98,6 +98,30 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Busy-polling variant (mbarrier.test_wait never suspends the thread): for the few latency-critical single hand-offs of a
+// pipeline (a tcgen05 issuer waiting for its operand), where the wake-up latency of try_wait's suspension is on the
+// critical path.  Same bounded wait.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((++spins & 0xfffu) == 0 && (clock64() - t0) > 4000000000LL) {
+      printf("agb: mbarrier spin-wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x, (int)threadIdx.x,
+             bar, parity);
+      __trap();
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) — 2D / 3D tiled loads completing on an mbarrier
 // ---------------------------------------------------------------------------------------------

@@ -717,6 +717,7 @@ def test_overlapped_grad_reducer_is_transparent_on_one_rank(agb, golden_dir, wir
         return {k: p.grad.clone() for k, p in exp.named_parameters()}
 
     plain = grads()
+    gmax = max(float(v.abs().max()) for v in plain.values())
     red = OverlappedGradReducer(bucket_mb=0.05, wire_dtype=torch.bfloat16 if wire == "bf16" else torch.float32)
     exp.agb_grad_reducer = red
     try:
@@ -728,7 +729,9 @@ def test_overlapped_grad_reducer_is_transparent_on_one_rank(agb, golden_dir, wir
                 # last bits from run to run, so "identical" is up to that noise)
                 scale = float(ref.abs().max()) + 1e-30
                 tol = 1e-5 if wire == "fp32" else 1e-2
-                assert float((got[k] - ref).abs().max()) <= tol * scale, (step, k, float((got[k] - ref).abs().max()), scale)
+                err = float((got[k] - ref).abs().max())
+                # (key biases have an identically-zero gradient: both sides hold rounding noise of the overall scale)
+                assert err <= tol * scale + 1e-6 * gmax, (step, k, err, scale)
     finally:
         del exp.agb_grad_reducer
 

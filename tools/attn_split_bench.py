@@ -80,7 +80,7 @@ def trace(prefix, rows=1024):
     for k in range(40):
         row = [int(v) - t0 if int(v) > 0 else -1 for v in t[k]]
         print(f"{k:4d} {row[0]:8d} {row[1]:9d} {row[2]:7d} {row[3]:10d} | {row[4]:11d} {row[5]:9d} {row[6]:12d} {row[7]:7d} | "
-              f"{row[8]:8d} {row[9]:8d} {row[10]:8d} {row[11]:8d} {row[12]:8d} | split3: s_full_seen {row[13]:8d} arrive {row[15]:8d}")
+              f"{row[8]:8d} {row[9]:8d} {row[10]:8d} {row[11]:8d} {row[12]:8d} | upper half: s_full_seen {row[13]:8d} arrive {row[15]:8d}")
 
 
 if __name__ == "__main__":

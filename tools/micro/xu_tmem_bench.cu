@@ -45,6 +45,64 @@ __global__ void xu_kernel(float* out, long long* cyc, int iters) {
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+// (2b) the softmax chunk as the attention kernel runs it: tcgen05.ld 32 columns -> wait -> row max (FMNMX3) -> vote -> 32 x
+//      (FFMA, MUFU.EX2, FADD), 16 x F2FP -> tcgen05.st 16 columns, with 1 / 2 / 4 warps per sub-partition
+__global__ void chunk_kernel(float* out, long long* cyc, int iters) {
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    tmem_alloc(smem_u32(&slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t base = slot + (static_cast<uint32_t>((warp & 3) * 32) << 16) + ((warp >> 2) & 3) * 128;
+  // fill my 128 columns with small numbers so that exp2 stays in range
+  {
+    uint32_t z[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) z[j] = __float_as_uint(-0.01f * (float)(j + (threadIdx.x & 31)));
+    for (int c = 0; c < 128; c += 32) tmem_st32(base + c, z);
+    tmem_wait_st();
+  }
+  float sum[4] = {0.f, 0.f, 0.f, 0.f};
+  float m_s = 0.f;
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    uint32_t s[32], pk[16];
+    const uint32_t a = base + ((it & 1) ? 64 : 32);
+    tmem_ld32(a, s);
+    tmem_wait_ld();
+    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      m0 = fmaxf(m0, __uint_as_float(s[j]));
+      m1 = fmaxf(m1, __uint_as_float(s[j + 1]));
+      m2 = fmaxf(m2, __uint_as_float(s[j + 2]));
+      m3 = fmaxf(m3, __uint_as_float(s[j + 3]));
+    }
+    const float lm = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * 0.18f;
+    if (__any_sync(0xffffffffu, lm > m_s + 24.f)) m_s = lm;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float e0 = ex2_approx(fmaf(__uint_as_float(s[2 * j]), 0.18f, -m_s));
+      const float e1 = ex2_approx(fmaf(__uint_as_float(s[2 * j + 1]), 0.18f, -m_s));
+      sum[(j & 1) * 2] += e0;
+      sum[(j & 1) * 2 + 1] += e1;
+      pk[j] = pack_bf16x2(e0, e1);
+    }
+    tmem_st16(base, pk);
+  }
+  tmem_wait_st();
+  const long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (sum[0] + sum[1]) + (sum[2] + sum[3]);
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+  if (warp == 0) tmem_dealloc(slot, 512);
+}
+
 // (3) the same MUFU loop in warps 8-15 (2 per sub-partition) while warps 0-7 spin on an mbarrier, as the service / epilogue
 //     warps of the attention kernel do.  SPIN 0: no spinners (they exit), 1: try_wait loop, 2: try_wait with a suspend-time hint,
 //     3: try_wait loop with __nanosleep(64) between polls
@@ -170,6 +228,15 @@ int main() {
       printf("xu mode %d (%s): %2d warps/CTA (%d per sub-partition): %8lld cycles, %.2f cycles per MUFU.EX2 warp-instruction per sub-partition "
              "=> %.1f exp2 / clk / SM\n", mode, mode == 0 ? "FFMA+MUFU+FADD+F2FP" : "MUFU only", warps, warps / 4, h[0], per, 32.0 / per * 4);
     }
+  }
+  for (int warps : {4, 8, 16}) {
+    for (int rep = 0; rep < 2; ++rep) {
+      chunk_kernel<<<148, warps * 32>>>(out, cyc, iters);
+      cudaDeviceSynchronize();
+    }
+    cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    printf("softmax chunk (tcgen05.ld x32, max, vote, 32 exp2, tcgen05.st x16): %2d warps/CTA (%d per sub-partition): %.1f cycles per chunk per warp, "
+           "%.2f cycles per MUFU.EX2 per sub-partition\n", warps, warps / 4, (double)h[0] / iters, (double)h[0] / ((double)iters * 32 * (warps / 4)));
   }
   for (int spin = 0; spin < 4; ++spin) {
     for (int rep = 0; rep < 2; ++rep) {
