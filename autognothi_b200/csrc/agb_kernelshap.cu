@@ -11,6 +11,8 @@
 //     A = L L^T (Cholesky), phi[:-1] = A^-1 R, phi[-1] = delta - sum  (kernel 2: blocked, one CTA per sample)
 // shap's optional l1_reg feature pre-selection is NOT part of this path (documented in oracle/kernelshap.py).
 // Bytes per sample (S=2048, d=127, C=2): packed Z 32 KB + p 16 KB in, A 127 KB out/in, phi 2 KB out.
+#include <stdlib.h>
+
 #include "agb_common.cuh"
 
 namespace agb {
@@ -59,12 +61,12 @@ __global__ void __launch_bounds__(KG_THREADS, 6)
 kernelshap_gram_kernel(const uint32_t* __restrict__ Z, int words, const double* __restrict__ w,
                        const double* __restrict__ probs, const double* __restrict__ fx,
                        const double* __restrict__ f0, int S, int d, int C, int link, double* __restrict__ A,
-                       double* __restrict__ R) {
+                       double* __restrict__ R, int rhs_only) {
   const int n = d - 1;
   const int tiles = (n + KG_T - 1) / KG_T;
   const int n_lower = tiles * (tiles + 1) / 2;
   const int b = blockIdx.y;
-  const int tile = blockIdx.x;
+  const int tile = blockIdx.x + (rhs_only ? n_lower : 0);     // rhs_only: the Gram tiles come from the tensor-core kernel
   const bool is_rhs = tile >= n_lower;
   int tj = 0, tk = 0;                      // tile row, tile column (tk <= tj: lower triangle, symmetric matrix)
   if (is_rhs) {
@@ -195,6 +197,324 @@ kernelshap_gram_kernel(const uint32_t* __restrict__ Z, int words, const double* 
 #pragma unroll
       for (int c = 0; c < CMAX; ++c)
         if (c < C) R[((long long)b * n + j) * C + c] = acc[c >> 3][c & 7];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Gram matrix on the tensor cores, exactly (round 2).  A[j,k] = sum_s w_s z'[s,j] z'[s,k] with z' in {0,1}: the only
+// non-integer factor is the weight.  Per sample the weights are put on a common fixed-point grid, q_s = round(|w_s| *
+// 2^(55 - e_max)) < 2^56, and cut into seven 8-bit limbs; then
+//     A = 2^(e_max - 55) * sum_l 2^(8 l) * ( (Z' o limb_l)^T Z' )
+// and every bracket is a product of small INTEGERS: limb values 0..255 and bits 0/1 are exact in bf16, their products are
+// exact, and a sum of S <= 65536 of them stays below 2^24, so tcgen05.mma kind::f16 with its fp32 accumulator computes
+// each bracket without any rounding.  The seven brackets are recombined in float64 (one rounding per addition, fixed
+// order: bit-reproducible; the result is the correctly scaled sum of the 56-bit fixed-point weights, i.e. at least as
+// accurate as the float64 FMA chain it replaces, whose own rounding error is S * 2^-53).
+// One CTA = one 128 (j) x 64 (k) tile of one sample's lower triangle; operands are GENERATED in shared memory, MN-major
+// SWIZZLE_128B tiles of 32 coalitions: for a coalition row s and 8 consecutive features the 8 mask bits index a 256-entry
+// table of 16-byte lane masks, which is ANDed with the broadcast value — 3 instructions per 8 operand elements.
+// The j side carries the plain bits (one A tile, shared by all limbs), the k side the bits times the limb value: the seven
+// limb tiles sit back to back in shared memory, so they are ONE B operand with N = 7 x 64 = 448 accumulator columns
+// (issued as N = 256 + N = 192): four tcgen05.mma per stage instead of fourteen, and A is read twice instead of 7 times.
+//   warp 0        tcgen05 issuer: per stage 2 K-steps x (N = 256, N = 192), D_l = TMEM columns [64 l, 64 l + 64)
+//   warps 1-8     operand generators (3-stage ring), then the epilogue: fp32 integers -> float64 recombination -> A
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int KT_BM = 128, KT_BN = 64, KT_BK = 32, KT_LIMBS = 7, KT_STAGES = 4;
+constexpr int KT_A_BYTES = KT_BK * KT_BM * 2;                 // A tile = the j-features' bits as bf16 0 / 1: 32 rows x 256 B (two mn atoms)
+constexpr int KT_B_BYTES = KT_BK * KT_BN * 2;                 // one limb's B tile: the k-features' bits x limb value, 32 rows x 128 B
+constexpr int KT_STAGE_BYTES = KT_A_BYTES + KT_LIMBS * KT_B_BYTES;     // 36 864
+constexpr int KT_THREADS = 288;                               // warp 0 issuer + 8 generator warps
+constexpr int KT_SMEM = 1024 + KT_STAGES * KT_STAGE_BYTES + 4096 /*lut*/ + KT_BK * KT_STAGES * 8 * 4 /*limbs*/ + 512;
+
+__global__ void __launch_bounds__(KT_THREADS, 1)
+kernelshap_gram_tc_kernel(const uint32_t* __restrict__ Z, int words, const double* __restrict__ w, int S, int d,
+                          double* __restrict__ A) {
+  extern __shared__ uint8_t kt_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(kt_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* stages = smem;
+  uint4* lut = reinterpret_cast<uint4*>(smem + KT_STAGES * KT_STAGE_BYTES);           // [256] 8 x u16 lane masks
+  uint32_t* limbs = reinterpret_cast<uint32_t*>(lut + 256);                            // [stage][32 coalitions][8] bf16 pairs
+  uint64_t* bars = reinterpret_cast<uint64_t*>(limbs + KT_STAGES * KT_BK * 8);
+  uint64_t* full = bars;              // [4]
+  uint64_t* empty = bars + 4;         // [4]
+  uint64_t* done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  double* red = reinterpret_cast<double*>(bars + 10);                                  // [9] per-warp maxima
+
+  const int n = d - 1;
+  const int b = blockIdx.y;
+  // tile index -> (tj, tk): j-tile tj owns the k-tiles 0 .. 2 tj + 1 (lower triangle incl. the diagonal block)
+  int tj = 0, rest = blockIdx.x;
+  while (rest >= 2 * tj + 2) { rest -= 2 * tj + 2; ++tj; }
+  const int tk = rest;
+  const int j0 = tj * KT_BM, k0 = tk * KT_BN;
+  const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
+  const uint32_t* Zb = Z + (long long)b * S * words;
+  const double* wb = w + (long long)b * S;
+  const int last = d - 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < KT_STAGES; ++i) {
+      mbar_init(smem_u32(&full[i]), 8);
+      mbar_init(smem_u32(&empty[i]), 1);
+    }
+    mbar_init(smem_u32(done), 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  // lane-mask table and the sample's largest |weight| (common fixed-point exponent)
+  for (int e = threadIdx.x; e < 256; e += KT_THREADS) {
+    uint4 m;
+    m.x = ((e & 1) ? 0x0000FFFFu : 0u) | ((e & 2) ? 0xFFFF0000u : 0u);
+    m.y = ((e & 4) ? 0x0000FFFFu : 0u) | ((e & 8) ? 0xFFFF0000u : 0u);
+    m.z = ((e & 16) ? 0x0000FFFFu : 0u) | ((e & 32) ? 0xFFFF0000u : 0u);
+    m.w = ((e & 64) ? 0x0000FFFFu : 0u) | ((e & 128) ? 0xFFFF0000u : 0u);
+    lut[e] = m;
+  }
+  double wmax = 0.0;
+  for (int s = threadIdx.x; s < S; s += KT_THREADS) wmax = fmax(wmax, fabs(wb[s]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wmax = fmax(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+  if (lane == 0) red[warp] = wmax;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  wmax = 0.0;
+#pragma unroll
+  for (int i = 0; i < KT_THREADS / 32; ++i) wmax = fmax(wmax, red[i]);
+  int e_max = 0;
+  if (wmax > 0.0) frexp(wmax, &e_max);               // wmax = m * 2^e_max, m in [0.5, 1)
+  const double to_fixed = ldexp(1.0, 56 - e_max);    // |w| * to_fixed < 2^56
+  const int n_stages = (S + KT_BK - 1) / KT_BK;
+
+  if (warp == 0) {
+    // ------------------------------ tcgen05 issuer ------------------------------
+    const uint32_t idesc_lo = make_idesc_bf16(KT_BM, 4 * KT_BN, 1, 1);     // limbs 0-3: N = 256
+    const uint32_t idesc_hi = make_idesc_bf16(KT_BM, 3 * KT_BN, 1, 1);     // limbs 4-6: N = 192
+    for (int st = 0; st < n_stages; ++st) {
+      const int sl = st % KT_STAGES;
+      mbar_wait(smem_u32(&full[sl]), (st / KT_STAGES) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(stages + sl * KT_STAGE_BYTES);
+        const uint32_t sb = sa + KT_A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < KT_BK / 16; ++kk) {
+          const uint64_t da = make_smem_desc_sw128(sa + kk * 2048, KT_BK * 128, 1024);
+          const uint64_t db0 = make_smem_desc_sw128(sb + kk * 2048, KT_BK * 128, 1024);
+          const uint64_t db1 = make_smem_desc_sw128(sb + 4 * KT_B_BYTES + kk * 2048, KT_BK * 128, 1024);
+          umma_ss(tmem_base, da, db0, idesc_lo, (st | kk) != 0 ? 1u : 0u);
+          umma_ss(tmem_base + 4 * KT_BN, da, db1, idesc_hi, (st | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&empty[sl]));
+        if (st == n_stages - 1) umma_commit(smem_u32(done));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------ operand generators ------------------------------
+    const int gt = threadIdx.x - 32;                   // 0 .. 255
+    // my tasks of a stage: two A tasks (coalition row r, 16-byte chunk c of the 128 j-features) and one B task
+    const int ra0 = gt >> 4, ca0 = gt & 15;            // task gt
+    const int ra1 = (gt + 256) >> 4;                   // task gt + 256 (same chunk column, row + 16)
+    const int rb = gt >> 3, cb = gt & 7;
+    const int ja = j0 + ca0 * 8, kf = k0 + cb * 8;
+    const uint32_t va = ja < n ? ks_valid_bits(ja & ~31, n) : 0u, vb = kf < n ? ks_valid_bits(kf & ~31, n) : 0u;
+    // the mask bytes (and, for the first 32 threads, the weight) of the NEXT stage are fetched while the current one is
+    // generated: the two dependent-free global loads per task are the long-latency part of a stage
+    // RAW words are kept in registers and only turned into bytes one iteration later, so the loads stay in flight
+    uint32_t nf_a0 = 0, nd_a0 = 0, nf_a1 = 0, nd_a1 = 0, nf_b = 0, nd_b = 0;
+    double nx_w = 0.0;
+    const int wl = last >> 5, wa_ = ja >> 5, wb_ = kf >> 5;
+    auto fetch = [&](int st) {
+      const int s0 = st * KT_BK;
+      const int sa0 = s0 + ra0, sa1 = s0 + ra1, sbr = s0 + rb;
+      nf_a0 = nd_a0 = nf_a1 = nd_a1 = nf_b = nd_b = 0u;
+      if (sa0 < S && va) { nf_a0 = __ldg(Zb + (long long)sa0 * words + wl); nd_a0 = __ldg(Zb + (long long)sa0 * words + wa_); }
+      if (sa1 < S && va) { nf_a1 = __ldg(Zb + (long long)sa1 * words + wl); nd_a1 = __ldg(Zb + (long long)sa1 * words + wa_); }
+      if (sbr < S && vb) { nf_b = __ldg(Zb + (long long)sbr * words + wl); nd_b = __ldg(Zb + (long long)sbr * words + wb_); }
+      nx_w = (sbr < S) ? wb[sbr] : 0.0;                   // weight of my B task's coalition
+    };
+    auto to_byte = [&](uint32_t fw, uint32_t dw, uint32_t valid, int f) -> uint32_t {
+      const uint32_t flip = ((fw >> (last & 31)) & 1u) ? 0xFFFFFFFFu : 0u;
+      return (((dw ^ flip) & valid) >> (f & 31)) & 0xFFu;
+    };
+    fetch(0);
+    for (int st = 0; st < n_stages; ++st) {
+      const int sl = st % KT_STAGES;
+      // (rows past S were fetched as zero words with a zero flip word: byte 0)
+      const uint32_t b_a0 = to_byte(nf_a0, nd_a0, va, ja), b_a1 = to_byte(nf_a1, nd_a1, va, ja), b_b = to_byte(nf_b, nd_b, vb, kf);
+      const double wv = nx_w;
+      if (st + 1 < n_stages) fetch(st + 1);
+      if (st >= KT_STAGES) mbar_wait(smem_u32(&empty[sl]), ((st / KT_STAGES) - 1) & 1);
+      // (1) limb values of my B task's coalition: bf16 pair (v, v) of sign * ((q >> 8 l) & 255).  Every thread converts its
+      // own weight (8 threads share a coalition: redundant, but no exchange and no barrier between the generator warps,
+      // so their per-stage latency chains overlap instead of adding up)
+      uint32_t lv[KT_LIMBS];
+      {
+        unsigned long long q = (unsigned long long)__double2ull_rn(fabs(wv) * to_fixed);
+        if (q >> 56) q = (1ull << 56) - 1;
+        const bool neg = wv < 0.0;
+#pragma unroll
+        for (int l = 0; l < KT_LIMBS; ++l) {
+          const float v = (float)(uint32_t)((q >> (8 * l)) & 255ull);
+          const uint32_t h = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(neg ? -v : v));
+          lv[l] = h | (h << 16);
+        }
+      }
+      uint8_t* sa = stages + sl * KT_STAGE_BYTES;
+      uint8_t* sb = sa + KT_A_BYTES;
+      // (2) A tile (j side): bf16 1.0 where the bit is set
+#pragma unroll
+      for (int rep = 0; rep < 2; ++rep) {
+        const int r = rep ? ra1 : ra0;
+        const uint4 m = lut[rep ? b_a1 : b_a0];
+        const uint32_t one = 0x3F803F80u;
+        const uint32_t off = (uint32_t)(ca0 >> 3) * (KT_BK * 128) + (uint32_t)r * 128 + ((((uint32_t)ca0 & 7u) ^ ((uint32_t)r & 7u)) << 4);
+        *reinterpret_cast<uint4*>(sa + off) = make_uint4(m.x & one, m.y & one, m.z & one, m.w & one);
+      }
+      // (3) B tiles (k side), one per limb, back to back: bit x limb value
+      {
+        const uint4 m = lut[b_b];
+        const uint32_t off = (uint32_t)rb * 128 + ((((uint32_t)cb) ^ ((uint32_t)rb & 7u)) << 4);
+#pragma unroll
+        for (int l = 0; l < KT_LIMBS; ++l)
+          *reinterpret_cast<uint4*>(sb + l * KT_B_BYTES + off) = make_uint4(m.x & lv[l], m.y & lv[l], m.z & lv[l], m.w & lv[l]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&full[sl]));
+    }
+    // ------------------------------ epilogue: recombine the limbs in float64 ------------------------------
+    mbar_wait(smem_u32(done), 0);
+    tc_fence_after();
+    const int gw = warp - 1;                     // 0 .. 7
+    const int qd = warp & 3;                     // TMEM lane quarter this warp may touch
+    const int chalf = (gw >> 2) & 1;             // which 32 of the 64 k-columns (two warps share a lane quarter)
+    // warps 1..8: (warp & 3) = 1,2,3,0,1,2,3,0 -> every quarter is covered twice, once per column half
+    const int j = j0 + qd * 32 + lane;
+    double res[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) res[i] = 0.0;
+    const double inv_fixed = ldexp(1.0, e_max - 56);
+#pragma unroll
+    for (int l = KT_LIMBS - 1; l >= 0; --l) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + l * KT_BN + chalf * 32, v);
+      tmem_wait_ld();
+      const double sc = (double)(1ull << (8 * l));
+#pragma unroll
+      for (int i = 0; i < 32; ++i) res[i] = fma((double)__uint_as_float(v[i]), sc, res[i]);
+    }
+    if (j < n) {
+      double* arow = A + ((long long)b * n + j) * n;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int k = k0 + chalf * 32 + i;
+        if (k < n) arow[k] = res[i] * inv_fixed;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// Right-hand sides R[j,c] = sum_s z'[s,j] * (w_s sigma_s y~[s,c]) when the Gram matrix comes from the tensor-core kernel:
+// one CTA per sample, thread = feature j.  Per chunk of 128 coalitions the per-coalition values v[s][c] = w_s sigma_s y~[s,c]
+// and the flipped mask words are staged once; every thread then walks the chunk, testing its own bit (the word is a warp
+// broadcast) and adding v — a masked float64 sum, 2 S C additions per feature.
+constexpr int KR_CH = 128;
+// grid (B, G): slice g of G handles the coalitions [g * S / G, (g + 1) * S / G) and adds into R (zeroed by the caller when
+// G > 1); inside the CTA, `parts` threads share a feature (interleaved coalitions, combined through shared memory)
+template <int CMAX>
+__global__ void __launch_bounds__(256)
+kernelshap_rhs_kernel(const uint32_t* __restrict__ Z, int words, const double* __restrict__ w, const double* __restrict__ probs,
+                      const double* __restrict__ fx, const double* __restrict__ f0, int S, int d, int C, int link,
+                      double* __restrict__ R) {
+  __shared__ double v[KR_CH][CMAX];
+  __shared__ uint32_t zs[KR_CH][33];          // up to 32 mask words per coalition (d <= 1024), padded against bank conflicts
+  __shared__ double l0s[CMAX], dls[CMAX];
+  __shared__ double comb[256][CMAX > 4 ? 1 : CMAX];      // partial sums of the parts (only used when parts > 1, C <= 4)
+  const int n = d - 1, b = blockIdx.x, t = threadIdx.x, last = d - 1;
+  const int G = gridDim.y, g = blockIdx.y;
+  const int s_lo = (int)((long long)S * g / G), s_hi = (int)((long long)S * (g + 1) / G);
+  const uint32_t* Zb = Z + (long long)b * S * words;
+  if (t < C) {
+    l0s[t] = ks_link(f0[t], link);
+    dls[t] = ks_link(fx[(long long)b * C + t], link) - l0s[t];
+  }
+  __syncthreads();
+  const int npad = (n + 31) & ~31;
+  const int parts = (CMAX <= 4 && npad <= 128) ? 256 / npad : 1;      // threads per feature
+  const int span = parts > 1 ? npad : 256;
+  for (int jb = 0; jb < n; jb += span) {
+    const int j = jb + (parts > 1 ? t % npad : t);
+    const int part = parts > 1 ? t / npad : 0;
+    double acc[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) acc[c] = 0.0;
+    for (int s0 = s_lo; s0 < s_hi; s0 += KR_CH) {
+      __syncthreads();
+      for (int e = t; e < KR_CH * words; e += 256) {
+        const int ss = e / words, wi = e - ss * words;
+        uint32_t val = 0;
+        if (s0 + ss < s_hi) {
+          const uint32_t* zr = Zb + (long long)(s0 + ss) * words;
+          const uint32_t flip = ((__ldg(zr + (last >> 5)) >> (last & 31)) & 1u) ? 0xFFFFFFFFu : 0u;
+          val = __ldg(zr + wi) ^ flip;
+        }
+        zs[ss][wi] = val;
+      }
+      for (int e = t; e < KR_CH * C; e += 256) {
+        const int ss = e / C, c = e - ss * C;
+        double val = 0.0;
+        if (s0 + ss < s_hi) {
+          const uint32_t* zr = Zb + (long long)(s0 + ss) * words;
+          const double zl = (double)((__ldg(zr + (last >> 5)) >> (last & 31)) & 1u);
+          const double yv = ks_link(probs[((long long)b * S + s0 + ss) * C + c], link) - l0s[c];
+          val = w[(long long)b * S + s0 + ss] * (1.0 - 2.0 * zl) * (yv - zl * dls[c]);
+        }
+        v[ss][c] = val;
+      }
+      __syncthreads();
+      if (j < n && part < parts) {
+        const int wi = j >> 5, sh = j & 31;
+#pragma unroll 4
+        for (int ss = part; ss < KR_CH; ss += parts) {
+          const bool on = (zs[ss][wi] >> sh) & 1u;
+#pragma unroll
+          for (int c = 0; c < CMAX; ++c)
+            if (c < C) acc[c] += on ? v[ss][c] : 0.0;
+        }
+      }
+    }
+    if (parts > 1) {
+      __syncthreads();
+      if (CMAX <= 4) {
+#pragma unroll
+        for (int c = 0; c < (CMAX > 4 ? 1 : CMAX); ++c) comb[t][c] = acc[c];
+      }
+      __syncthreads();
+      if (part == 0 && CMAX <= 4) {
+        for (int q = 1; q < parts; ++q)
+#pragma unroll
+          for (int c = 0; c < (CMAX > 4 ? 1 : CMAX); ++c) acc[c] += comb[q * npad + (t % npad)][c];
+      }
+    }
+    if (j < n && part == 0) {
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) {
+          double* dst = R + ((long long)b * n + j) * C + c;
+          if (G > 1) atomicAdd(dst, acc[c]);
+          else *dst = acc[c];
+        }
     }
   }
 }
@@ -412,9 +732,33 @@ int kernelshap_solve(const uint32_t* Z, int words, const double* w, const double
   const size_t smem = kc_smem_doubles(n, C) * sizeof(double);
   AGB_REQUIRE(smem <= 227 * 1024, "KernelSHAP: d too large for the shared-memory panel (d <= 1024)");
   const int tiles = (n + KG_T - 1) / KG_T;
-  dim3 grid(tiles * (tiles + 1) / 2 + tiles, B);
-  if (C <= 4) kernelshap_gram_kernel<4><<<grid, KG_THREADS, 0, st>>>(Z, words, w, probs, fx, f0, S, d, C, link, A, R);
-  else        kernelshap_gram_kernel<16><<<grid, KG_THREADS, 0, st>>>(Z, words, w, probs, fx, f0, S, d, C, link, A, R);
+  // Gram matrix: tensor cores (exact integer limbs, see kernelshap_gram_tc_kernel) unless AGB_KS_GRAM=fp64 asks for the
+  // float64 FMA kernel; the right-hand sides E^T W y~ (real-valued y) always take the float64 kernel's rhs tiles
+  static const bool use_tc = [] { const char* e = getenv("AGB_KS_GRAM"); return !(e != nullptr && e[0] == 'f'); }();
+  const bool tc = use_tc && S <= 65536;
+  if (tc) {
+    static bool configured = false;
+    if (!configured) {
+      AGB_CHECK_CUDA(cudaFuncSetAttribute(kernelshap_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KT_SMEM));
+      configured = true;
+    }
+    const int tjn = (n + KT_BM - 1) / KT_BM;
+    dim3 gtc(tjn * (tjn + 1), B);                 // sum over tj of (2 tj + 2) k-tiles
+    kernelshap_gram_tc_kernel<<<gtc, KT_THREADS, KT_SMEM, st>>>(Z, words, w, S, d, A);
+    AGB_CHECK_CUDA(cudaGetLastError());
+  }
+  if (tc && words <= 32) {
+    int G = (4 * sm_count()) / B;                 // few samples: slice the coalitions over several CTAs per sample
+    G = G < 1 ? 1 : (G > 8 ? 8 : G);
+    if (G > 1) AGB_CHECK_CUDA(cudaMemsetAsync(R, 0, sizeof(double) * (size_t)B * n * C, st));
+    dim3 gr(B, G);
+    if (C <= 4) kernelshap_rhs_kernel<4><<<gr, 256, 0, st>>>(Z, words, w, probs, fx, f0, S, d, C, link, R);
+    else        kernelshap_rhs_kernel<16><<<gr, 256, 0, st>>>(Z, words, w, probs, fx, f0, S, d, C, link, R);
+  } else {
+    dim3 grid(tc ? tiles : tiles * (tiles + 1) / 2 + tiles, B);
+    if (C <= 4) kernelshap_gram_kernel<4><<<grid, KG_THREADS, 0, st>>>(Z, words, w, probs, fx, f0, S, d, C, link, A, R, tc ? 1 : 0);
+    else        kernelshap_gram_kernel<16><<<grid, KG_THREADS, 0, st>>>(Z, words, w, probs, fx, f0, S, d, C, link, A, R, tc ? 1 : 0);
+  }
   AGB_CHECK_CUDA(cudaGetLastError());
   AGB_CHECK_CUDA(cudaFuncSetAttribute(kernelshap_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kernelshap_solve_kernel<<<B, KC_THREADS, smem, st>>>(A, R, fx, f0, d, C, link, phi, info);

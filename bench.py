@@ -680,6 +680,8 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    by_rank = []          # per timed leg: ms per step of every rank (multi-GPU runs)
+
     def timed(fn, steps, warmup, profile=False):
         for i in range(warmup):
             fn(i)
@@ -697,6 +699,11 @@ def run_ours(args):
         prof, nat.PROFILE = nat.PROFILE, None
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
+            # every rank's own device time (the spread between the fastest and the slowest GPU of the box is what weak
+            # scaling loses here: the path has no per-step data exchange), then the max over ranks = the reported time
+            per_rank = [torch.empty_like(ms) for _ in range(world)]
+            dist.all_gather(per_rank, ms)
+            by_rank.append([round(float(t) / steps, 3) for t in per_rank])
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), nat.LAUNCHES - l0, prof
 
@@ -742,6 +749,7 @@ def run_ours(args):
 
         t_steps = max(2, min(args.steps, 5))
         ms_t, launches_t, _ = timed(step_train, t_steps, 2)
+        train_by_rank = by_rank[-1] if by_rank else None
         sps = world * Bt * t_steps / (ms_t * 1e-3)
         fl_eval = flops_per_eval(cfgd)
         H, I, E, T = cfg.hidden_size, cfg.intermediate_size, cfg.explainer_head_hidden_size, n + 1
@@ -758,6 +766,8 @@ def run_ours(args):
                                    f"all-reduces / step"}
         peaks_t = load_peaks()
         train["frac_of_sustained_peak"] = train["tflops_per_gpu"] / peaks_t["bf16_tflops_sustained"]
+        if train_by_rank is not None:
+            train["ms_per_step_by_rank"] = train_by_rank
 
     # ---- LTT leg (BASELINE.json north_star: "frozen backbone plus side network", "explainer side-network training uses an
     # NCCL gradient allreduce"; reference models/ltt_vit.py, recipes/ltt_vit.py): the same ViT backbone frozen, a narrow
@@ -893,6 +903,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": rows * C * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "whole_path": whole,
         }
+        if by_rank:
+            line["ms_per_step_by_rank"] = by_rank[0]
         if train is not None:
             line["train"] = train
         if ltt is not None:
