@@ -446,8 +446,8 @@ class SurrogateEngine:
         from . import _native as nat
         if (0 < B * S <= GRAPH_MAX_ROWS and B * S <= max_rows and self.pol.bf16 and not self._packed_path()
                 and nat.PROFILE is None and not torch.cuda.is_current_stream_capturing()):
-            key = (tuple(xs.shape), xs.dtype, tuple(masks.shape), S, FUSE_LAYERNORM, CLS_ONLY_LAST_BLOCK, SHARE_FIRST_BLOCK,
-                   KEPT_FIRST_ORDER)
+            key = (xs.device, tuple(xs.shape), xs.dtype, tuple(masks.shape), S, FUSE_LAYERNORM, CLS_ONLY_LAST_BLOCK,
+                   SHARE_FIRST_BLOCK, KEPT_FIRST_ORDER)
             return self.graphs.run(key, lambda x_, m_: self._probs_eager(x_, m_, S, max_rows), (xs.contiguous(), masks))
         return self._probs_eager(xs, masks, S, max_rows)
 
@@ -501,7 +501,7 @@ class ExplainerEngine:
             # small explainer calls are launch-bound as well: one CUDA graph per shape (see GRAPH_MAX_ROWS)
             if not hasattr(self, "graphs"):
                 self.graphs = _GraphCache()
-            key = (tuple(xs.shape), xs.dtype, tuple(masks.shape), tuple(grand.shape), tuple(null.shape), FUSE_LAYERNORM)
+            key = (xs.device, tuple(xs.shape), xs.dtype, tuple(masks.shape), tuple(grand.shape), tuple(null.shape), FUSE_LAYERNORM)
 
             def fn(x_, m_, g_, n_):
                 h, ha = run_backbone(self.bw, self.cfg, self.pol, x_, m_, 1)

@@ -71,7 +71,7 @@ class _LttModule(_EngineModule):
 
     def _ltt(self) -> engine.LttEngine:
         kind = self._kind
-        eng = self._engine(lambda sd, cfg, prec: engine.LttEngine(sd, cfg, prec, kind))
+        eng = self._engine(lambda sd, cfg, prec: engine.LttEngine(sd, cfg, prec, kind), kind_key=f"ltt:{kind}")
         eng.freeze_layer = getattr(self, "_ltt_freeze_layer", None)
         return eng
 

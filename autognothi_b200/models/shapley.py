@@ -162,20 +162,22 @@ class _NormalizeFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pred, grand, null):
         ctx.T = pred.shape[1]
+        ctx.null_shape = null.shape
         return ops.normalize_shapley(pred, grand, null)
 
     @staticmethod
     def backward(ctx, g):
         # out = pred + ((grand - null) - sum_t pred)/T  ->  dpred = g - mean_t(g); dgrand = mean-sum; dnull = -that
         gs = g.sum(dim=1)
-        return g - gs.unsqueeze(1) / ctx.T, gs / ctx.T, -(gs.sum(dim=0, keepdim=True)) / ctx.T
+        dnull = (-(gs.sum(dim=0, keepdim=True)) / ctx.T).reshape(ctx.null_shape)     # null may be (1, C) or (C,)
+        return g - gs.unsqueeze(1) / ctx.T, gs / ctx.T, dnull
 
 
 def normalize_shapley_explanation(pred: Tensor, grand: Tensor, null: Tensor) -> Tensor:
     """Additive efficiency normalisation (reference models/shapley.py:82-93): the divisor is
     pred.shape[1] — callers pass the un-sliced (B, T, C) tensor, CLS included."""
     assert pred.is_cuda and pred.dim() == 3
-    if torch.is_grad_enabled() and (pred.requires_grad or grand.requires_grad):
+    if torch.is_grad_enabled() and (pred.requires_grad or grand.requires_grad or null.requires_grad):
         return _NormalizeFn.apply(pred, grand, null)
     return ops.normalize_shapley(pred, grand, null)
 
@@ -204,5 +206,5 @@ def loss_shapley_new(batch_size: int, n_mask_samples: int, n_players: int, mask:
     pm = as_packed(mask, batch_size * n_mask_samples)
     assert pm.n_players == n_players and phi.shape == (batch_size, phi.shape[1], n_players)
     if phi.dtype != torch.float32:
-        raise TypeError("phi must be float32 (the reference's `mask.float() @ phi` raises for other dtypes)")
+        phi = phi.float()          # the loss is computed in fp32 (the reference's `mask.float() @ phi` needs matching dtypes)
     return _ShapleyLossFn.apply(phi, pm.words, v_0, v_s, batch_size, n_mask_samples, n_players)

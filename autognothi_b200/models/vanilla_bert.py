@@ -5,6 +5,8 @@ which the attention kernel implements by zeroing the masked K/V rows (AGB_MASK_N
 `token_type_ids` must be all zeros on this path (reference recipes/vanilla_bert.py:289)."""
 from __future__ import annotations
 
+import os
+
 from typing import Optional, Tuple
 
 import pydantic
@@ -42,9 +44,12 @@ class VanillaBertConfig(pydantic.BaseModel):
 
 
 def _check_token_types(token_type_ids: Optional[Tensor]) -> None:
-    # a device-side all-zero check would force a sync on the hot path; shape/dtype only
+    # a device-side all-zero check would force a sync on the hot path: shape/dtype only, unless AGB_DEBUG_CHECKS=1
     if token_type_ids is not None:
         assert token_type_ids.dtype in (torch.int64, torch.int32), "token_type_ids must be an integer tensor"
+        if os.environ.get("AGB_DEBUG_CHECKS") == "1" and bool((token_type_ids != 0).any()):
+            raise ValueError("token_type_ids must be all zero on this path (reference recipes/vanilla_bert.py:289 always "
+                             "passes zeros; only token type 0 is embedded)")
 
 
 class VanillaBertClassifier(_EngineModule):

@@ -53,17 +53,22 @@ class _EngineModule(nn.Module):
 
     agb_precision: str = "bf16"
 
-    def _engine(self, kind):
+    def _engine(self, kind, kind_key=None):
+        """kind: engine class or factory (sd, config, precision) -> engine; kind_key names it in the cache when `kind` is a
+        fresh closure (the LTT modules), so that a module asking for two kinds never gets the wrong one back."""
         sig = (self.agb_precision, _tree.state_signature(self))
         cache = self.__dict__.setdefault("_agb_cache", {})
         if cache.get("sig") != sig:
+            cache.clear()
+            cache["sig"] = sig
+        key = ("eng", kind_key if kind_key is not None else getattr(kind, "__qualname__", repr(kind)))
+        if key not in cache:
             sd = {k: v for k, v in self.state_dict().items()}
             dev = next(self.parameters()).device
             if dev.type != "cuda":
                 raise RuntimeError("autognothi_b200 models run on CUDA only: call .to('cuda') first (no CPU fallback)")
-            cache["sig"] = sig
-            cache["eng"] = kind(sd, self.config, self.agb_precision)
-        return cache["eng"]
+            cache[key] = kind(sd, self.config, self.agb_precision)
+        return cache[key]
 
 
 class VanillaViTClassifier(_EngineModule):

@@ -323,3 +323,33 @@ def test_bert_head_rows_per_cta_kernel_is_bit_identical(agb, rows, T, H, C):
     ref = torch.tanh(x[:, 0].double() @ wp.double().t() + bp.double()) @ wc.double().t() + bc.double()
     torch.testing.assert_close(logits.double(), ref, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(probs.double(), torch.softmax(ref, -1), rtol=1e-4, atol=1e-6)
+
+
+def test_normalize_and_loss_follow_the_reference_on_gradient_and_dtype_edges(agb):
+    """a `null` that alone requires grad gets its gradient, in the shape it was passed ((1, C) or (C,)), and
+    loss_shapley_new accepts a non-fp32 phi (computed in fp32) — compared with the formulas of reference
+    models/shapley.py:82-93 and 40-50 evaluated by torch autograd."""
+    from autognothi_b200.models import shapley as ash
+    torch.manual_seed(4)
+    B, T, C, S = 3, 9, 4, 6
+    n = T - 1
+    pred = torch.randn(B, T, C, device=DEV)
+    grand = torch.rand(B, C, device=DEV)
+    for shape in ((1, C), (C,)):
+        null = torch.rand(shape, device=DEV, requires_grad=True)
+        out = ash.normalize_shapley_explanation(pred, grand, null)
+        out.square().sum().backward()
+        null2 = null.detach().clone().requires_grad_(True)
+        ref = pred + ((grand - null2.reshape(1, C)) - pred.sum(dim=1)).unsqueeze(1) / T
+        ref.square().sum().backward()
+        assert null.grad is not None and null.grad.shape == null.shape
+        torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(null.grad, null2.grad, rtol=1e-4, atol=1e-5)
+    masks = (torch.rand(B, S, n, device=DEV) > 0.5).to(torch.int64)
+    phi = torch.randn(B, C, n, device=DEV)
+    v0, vs = torch.rand(1, C, device=DEV), torch.rand(B * S, C, device=DEV)
+    l32 = ash.loss_shapley_new(B, S, n, masks, v0, vs, None, phi)
+    l16 = ash.loss_shapley_new(B, S, n, masks, v0, vs, None, phi.to(torch.bfloat16))
+    ref = n * ((v0 + torch.bmm(masks.float(), phi.permute(0, 2, 1)).reshape(B * S, C) - vs) ** 2).mean()
+    torch.testing.assert_close(l32, ref, rtol=1e-5, atol=1e-6)
+    assert abs(float(l16) - float(ref)) <= 3e-2 * abs(float(ref))
