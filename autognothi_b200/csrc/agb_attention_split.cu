@@ -25,6 +25,10 @@
 //                row's reference maximum is the maximum over the first chunk of both halves and is raised later only if a
 //                chunk exceeds it by 2^24 (softmax is shift-invariant; the P already written is then rescaled in place by
 //                an exact power of two).
+// High-O layout (AGB_ATTN_DEBUG=16, OFF by default — measured 5 % slower): an item whose key columns fit in 192 TMEM columns (kept-first order, >= 16 masked keys: ~80 % of the rows)
+// keeps its O accumulator at [192, 256) and the upper half's P on that half's own consumed S columns, so nothing of the
+// item lives in [0, 192) once P V has completed: S of item k + 2 — if it also fits in 192 columns — is issued as soon as
+// P V (k) is done and overlaps the epilogue of item k instead of waiting for it.
 // Kept-first order (AP "prefix" mode, see agb_attention_pipe.cu): keys [0, nkeep) are live, the masked rest is ONE virtual
 // key at column nkeep (logit log(n_masked) / scale, V row = mean of the masked V rows); S, the softmax and P V then only
 // span round16(nkeep + 1) key columns.
@@ -40,6 +44,7 @@ constexpr int A3_TMEM_COLS = 512;
 constexpr int A3_REGION = 256;     // TMEM columns per region (item parity)
 constexpr int A3_O_COL = 128;      // O accumulator at [128, 192) of the region (S columns consumed by then)
 constexpr int A3_SPARE = 208;      // P of the upper key half at [208, 256)
+constexpr int A3_O_HI = 192;       // "high-O" layout (kept-first items with <= 192 key columns): O at [192, 256), see below
 constexpr int A3_KV_RING = 3;
 constexpr int A3_MAX_NK = 208;
 constexpr float A3_LAZY = 24.f;    // log2 units a chunk may exceed the row's reference maximum before it is raised
@@ -56,7 +61,8 @@ struct Att3Params {
   bf16* ctx;
   long long* trace;
   int debug;              // diagnostics (AGB_ATTN_DEBUG): 1 = softmax touches only its first chunk, 2 = no MMAs are issued,
-                          // 4 = exact two-pass row maximum instead of the lazily raised reference maximum, 8 = spin-wait hand-offs
+                          // 4 = exact two-pass row maximum instead of the lazily raised reference maximum, 8 = spin-wait hand-offs,
+                          // 16 = high-O layout (A/B: measured SLOWER, 403 vs 382 us kept-first on one box — off by default)
 };
 
 #define A3_TRACE(k, slot)                                                                                         \
@@ -202,7 +208,11 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
       mbar_wait(smem_u32(&q_full[qb]), nq & 1);
       if (n > 0) {
-        if (p.debug & 8) mbar_wait_spin(smem_u32(&o_free[g]), (n - 1) & 1);
+        // region g still holds item k - 2.  If both that item and this one use the high-O layout, [0, 192) is free the
+        // moment P V (k - 2) has completed (o_full); otherwise wait until its epilogue has drained O (o_free).
+        const bool early = PREFIX && (p.debug & 16) && unit_keys(ui) <= A3_O_HI && unit_keys((k - 2) / mt) <= A3_O_HI;
+        if (early) mbar_wait(smem_u32(&o_full[g]), (n - 1) & 1);
+        else if (p.debug & 8) mbar_wait_spin(smem_u32(&o_free[g]), (n - 1) & 1);
         else mbar_wait(smem_u32(&o_free[g]), (n - 1) & 1);
       }
       tc_fence_after();
@@ -233,15 +243,19 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       else mbar_wait(smem_u32(&p_full[g]), n & 1);
       A3_TRACE(k, 2);
       tc_fence_after();
-      const uint32_t d_o = tmem_base + g * A3_REGION + A3_O_COL;
+      const bool hi_o = PREFIX && (p.debug & 16) && n16 * 16 <= A3_O_HI;
+      const uint32_t d_o = tmem_base + g * A3_REGION + (hi_o ? A3_O_HI : A3_O_COL);
       uint64_t dv = dv0 + (skv0 + b * 2 * kvb16 + kvb16);
+      // the O columns of this item were last read by the epilogue of item k - 2 (the S issuer may not have waited for it)
+      if (n > 0) mbar_wait(smem_u32(&o_free[g]), (n - 1) & 1);
       if (!(p.debug & 2)) {
-        // P of the lower key half overlays the start of the region, the upper half lives in the spare columns
+        // P of the lower key half overlays the start of the region; the upper half's P lives in the spare columns, or
+        // (high-O layout) on that half's own consumed S columns
         const int ca = (n16 + 1) >> 1;
         uint32_t a_p = tmem_base + g * A3_REGION;
         int ks = 0;
         for (; ks < ca; ++ks, a_p += 8, dv += (2048 >> 4)) umma_ts_e(e, d_o, a_p, dv, idesc_o, ks != 0 ? 1u : 0u);
-        a_p = tmem_base + g * A3_REGION + A3_SPARE;
+        a_p = tmem_base + g * A3_REGION + (hi_o ? ca * 16 : A3_SPARE);
         for (; ks < n16; ++ks, a_p += 8, dv += (2048 >> 4)) umma_ts_e(e, d_o, a_p, dv, idesc_o, 1u);
       }
       umma_commit_e<1>(e, smem_u32(&o_full[g]));
@@ -312,7 +326,8 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const int u = blockIdx.x + ui * grid;
       const int row = u / p.heads, head = u - row * p.heads;
       const bool warp_live = (m * 128 + qd * 32) < T;
-      const uint32_t o_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + g * A3_REGION + A3_O_COL;
+      const bool hi_o = PREFIX && (p.debug & 16) && unit_keys(ui) <= A3_O_HI;
+      const uint32_t o_addr = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + g * A3_REGION + (hi_o ? A3_O_HI : A3_O_COL);
       if (p.debug & 8) mbar_wait_spin(smem_u32(&o_full[g]), n & 1);
       else mbar_wait(smem_u32(&o_full[g]), n & 1);
       if (qd == 0) A3_TRACE(k, 6);
@@ -392,7 +407,8 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       // P (bf16 pairs): the lower half overlays the S columns it has consumed (writes trail reads), the upper half uses the
       // spare columns [208, 256): the O accumulator will overwrite [128, 192), and S columns the lower half still has to read
       // must not be touched
-      const uint32_t p_start = lane_addr + (split ? (uint32_t)A3_SPARE : 0u);
+      const bool hi_o = PREFIX && (p.debug & 16) && NKu <= A3_O_HI;        // (high-O layout: see the file header)
+      const uint32_t p_start = lane_addr + (split ? (uint32_t)(hi_o ? ca * 16 : A3_SPARE) : 0u);
 
       mbar_wait(smem_u32(&s_full[g]), n & 1);
       if (qd == 0 && split == 0) A3_TRACE(k, 4);
