@@ -755,17 +755,21 @@ def run_ours(args):
         H, I, E, T = cfg.hidden_size, cfg.intermediate_size, cfg.explainer_head_hidden_size, n + 1
         layer = 2 * T * H * 3 * H + 2 * T * H * H + 4 * T * H * I + 4 * T * T * H
         fl_exp = fl_eval + layer + 2 * T * H * E + 2 * T * E * E + 2 * T * E * cfg.num_labels
-        fl_sample = (S + 1) * fl_eval + 3 * fl_exp
+        fl_sample = (S + 1) * fl_eval + 3 * fl_exp             # dense: what the reference computes per training sample
+        # executed: the S masked evaluations skip work exactly (CLS-only last block, shared first-block projections); the
+        # grand evaluation (S = 1) only skips the last block's non-CLS rows; the explainer's own fwd + bwd is dense
+        fl_sample_exec = S * flops_per_eval_executed(cfgd, S) + flops_per_eval_executed(cfgd, 1) + 3 * fl_exp
         train = {"metric": "explainer_train_samples_per_sec", "value": sps, "unit": "samples/s", "ms_per_step": ms_t / t_steps,
-                 "steps": t_steps, "images_per_gpu_per_step": Bt, "coalitions_per_image": S, "flops_per_sample": fl_sample,
-                 "tflops_per_gpu": sps / world * fl_sample * 1e-12, "gpu_launches": launches_t,
+                 "steps": t_steps, "images_per_gpu_per_step": Bt, "coalitions_per_image": S, "flops_per_sample": fl_sample_exec,
+                 "flops_per_sample_dense": fl_sample, "tflops_per_gpu": sps / world * fl_sample_exec * 1e-12,
+                 "dense_equivalent_tflops_per_gpu": sps / world * fl_sample * 1e-12, "gpu_launches": launches_t,
                  "dropout": "p=0.1 on embeddings / attention probabilities / attention-output / MLP-output (train() mode of the reference's "
                             "config; masks from a counter hash, regenerated in the adjoint)", "optimizer": "torch.optim.AdamW(fused=True), fp32 master weights",
                  "grad_allreduce": f"NCCL AVG, 32 MB flat buckets filled and sent during the backward pass (last block first), "
                                    f"wire dtype {args.grad_wire}, world={world}; {overlapped.stats['buckets'] // max(1, t_steps + 2)} "
                                    f"all-reduces / step"}
         peaks_t = load_peaks()
-        train["frac_of_sustained_peak"] = train["tflops_per_gpu"] / peaks_t["bf16_tflops_sustained"]
+        train["frac_of_sustained_peak"] = train["tflops_per_gpu"] / peaks_t["bf16_tflops_sustained"]     # on EXECUTED FLOPs
         if train_by_rank is not None:
             train["ms_per_step_by_rank"] = train_by_rank
 
