@@ -536,7 +536,7 @@ __host__ __device__ inline size_t kc_smem_doubles(int n, int C) {
   return (size_t)KC_NB * KC_LD + KC_NB + (panel > back ? panel : back);
 }
 
-__global__ void __launch_bounds__(KC_THREADS)
+__global__ void __launch_bounds__(KC_THREADS, 2)
 kernelshap_solve_kernel(double* __restrict__ A, double* __restrict__ R, const double* __restrict__ fx,
                         const double* __restrict__ f0, int d, int C, int link, double* __restrict__ phi,
                         int* __restrict__ info) {
