@@ -220,6 +220,31 @@ kernelshap_gram_kernel(const uint32_t* __restrict__ Z, int words, const double* 
 //   warp 0        tcgen05 issuer: per stage 2 K-steps x (N = 256, N = 192), D_l = TMEM columns [64 l, 64 l + 64)
 //   warps 1-8     operand generators (3-stage ring), then the epilogue: fp32 integers -> float64 recombination -> A
 // ------------------------------------------------------------------------------------------------------------------
+// explicit shared-space accesses (generic ld / st on a shared pointer go through the slower generic path of the LSU:
+// 11 % of the kernel's stall samples were `stall_lg` / MIO on ST.E.128 / LD.E.128, profiles/r02_kernelshap_gram_ncu.txt)
+__device__ __forceinline__ void kt_sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 kt_lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+// |w| * 2^(56 - e_max) rounded to nearest, as a 56-bit integer, with INTEGER instructions only (the float64 pipe is slow:
+// the DMUL + F2I pair was 10 % of the stall samples).  w = mant * 2^(exp - 1075) with the implicit bit set.
+__device__ __forceinline__ unsigned long long kt_to_fixed(double w, int e_max) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(w) & 0x7FFFFFFFFFFFFFFFull;
+  const int ex = (int)(bits >> 52);
+  if (ex == 0) return 0ull;                                  // zero / subnormal: below the grid
+  const unsigned long long mant = (bits & 0x000FFFFFFFFFFFFFull) | 0x0010000000000000ull;
+  const int sh = ex - 1075 + 56 - e_max;                     // q = mant * 2^sh; sh <= 3 because |w| < 2^e_max
+  unsigned long long q;
+  if (sh >= 0) q = mant << sh;
+  else if (sh < -54) q = 0ull;
+  else q = (mant + (1ull << (-sh - 1))) >> (-sh);
+  return q >> 56 ? (1ull << 56) - 1 : q;
+}
+
 constexpr int KT_BM = 128, KT_BN = 64, KT_BK = 32, KT_LIMBS = 7, KT_STAGES = 4;
 constexpr int KT_A_BYTES = KT_BK * KT_BM * 2;                 // A tile = the j-features' bits as bf16 0 / 1: 32 rows x 256 B (two mn atoms)
 constexpr int KT_B_BYTES = KT_BK * KT_BN * 2;                 // one limb's B tile: the k-features' bits x limb value, 32 rows x 128 B
@@ -289,7 +314,6 @@ kernelshap_gram_tc_kernel(const uint32_t* __restrict__ Z, int words, const doubl
   for (int i = 0; i < KT_THREADS / 32; ++i) wmax = fmax(wmax, red[i]);
   int e_max = 0;
   if (wmax > 0.0) frexp(wmax, &e_max);               // wmax = m * 2^e_max, m in [0.5, 1)
-  const double to_fixed = ldexp(1.0, 56 - e_max);    // |w| * to_fixed < 2^56
   const int n_stages = (S + KT_BK - 1) / KT_BK;
 
   if (warp == 0) {
@@ -319,6 +343,7 @@ kernelshap_gram_tc_kernel(const uint32_t* __restrict__ Z, int words, const doubl
   } else {
     // ------------------------------ operand generators ------------------------------
     const int gt = threadIdx.x - 32;                   // 0 .. 255
+    const uint32_t stages_s = smem_u32(stages), lut_s = smem_u32(lut);
     // my tasks of a stage: two A tasks (coalition row r, 16-byte chunk c of the 128 j-features) and one B task
     const int ra0 = gt >> 4, ca0 = gt & 15;            // task gt
     const int ra1 = (gt + 256) >> 4;                   // task gt + 256 (same chunk column, row + 16)
@@ -357,9 +382,8 @@ kernelshap_gram_tc_kernel(const uint32_t* __restrict__ Z, int words, const doubl
       // so their per-stage latency chains overlap instead of adding up)
       uint32_t lv[KT_LIMBS];
       {
-        unsigned long long q = (unsigned long long)__double2ull_rn(fabs(wv) * to_fixed);
-        if (q >> 56) q = (1ull << 56) - 1;
-        const bool neg = wv < 0.0;
+        const unsigned long long q = kt_to_fixed(wv, e_max);
+        const bool neg = __double2hiint(wv) < 0;
 #pragma unroll
         for (int l = 0; l < KT_LIMBS; ++l) {
           const float v = (float)(uint32_t)((q >> (8 * l)) & 255ull);
@@ -367,24 +391,24 @@ kernelshap_gram_tc_kernel(const uint32_t* __restrict__ Z, int words, const doubl
           lv[l] = h | (h << 16);
         }
       }
-      uint8_t* sa = stages + sl * KT_STAGE_BYTES;
-      uint8_t* sb = sa + KT_A_BYTES;
+      const uint32_t sa = stages_s + sl * KT_STAGE_BYTES;
+      const uint32_t sb = sa + KT_A_BYTES;
       // (2) A tile (j side): bf16 1.0 where the bit is set
 #pragma unroll
       for (int rep = 0; rep < 2; ++rep) {
         const int r = rep ? ra1 : ra0;
-        const uint4 m = lut[rep ? b_a1 : b_a0];
+        const uint4 m = kt_lds128(lut_s + (rep ? b_a1 : b_a0) * 16);
         const uint32_t one = 0x3F803F80u;
         const uint32_t off = (uint32_t)(ca0 >> 3) * (KT_BK * 128) + (uint32_t)r * 128 + ((((uint32_t)ca0 & 7u) ^ ((uint32_t)r & 7u)) << 4);
-        *reinterpret_cast<uint4*>(sa + off) = make_uint4(m.x & one, m.y & one, m.z & one, m.w & one);
+        kt_sts128(sa + off, m.x & one, m.y & one, m.z & one, m.w & one);
       }
       // (3) B tiles (k side), one per limb, back to back: bit x limb value
       {
-        const uint4 m = lut[b_b];
+        const uint4 m = kt_lds128(lut_s + b_b * 16);
         const uint32_t off = (uint32_t)rb * 128 + ((((uint32_t)cb) ^ ((uint32_t)rb & 7u)) << 4);
 #pragma unroll
         for (int l = 0; l < KT_LIMBS; ++l)
-          *reinterpret_cast<uint4*>(sb + l * KT_B_BYTES + off) = make_uint4(m.x & lv[l], m.y & lv[l], m.z & lv[l], m.w & lv[l]);
+          kt_sts128(sb + l * KT_B_BYTES + off, m.x & lv[l], m.y & lv[l], m.z & lv[l], m.w & lv[l]);
       }
       fence_proxy_async_smem();
       __syncwarp();
