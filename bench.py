@@ -40,7 +40,11 @@ VIT_BASE = dict(attention_probs_dropout_prob=0.1, explainer_attn_num_layers=1, e
 # runs the same legs on it (a side configuration: the default line stays ViT-Base/16, the metric's own config)
 VIT_LARGE = dict(VIT_BASE, explainer_head_hidden_size=4096, hidden_size=1024, intermediate_size=4096,
                  num_attention_heads=16, num_hidden_layers=24)
-MODELS = {"vit_base": ("vit_base_imagenette_vanilla", "ViT-Base/16", VIT_BASE),
+# reference experiments/vit_tiny_imagenette_vanilla/.hparams.json:20-35 — BASELINE.json configs[0] (the reference's own CPU-runnable
+# case); `--model vit_tiny` runs the same legs on it
+VIT_TINY = dict(VIT_BASE, explainer_head_hidden_size=768, hidden_size=192, intermediate_size=768, num_attention_heads=3)
+MODELS = {"vit_tiny": ("vit_tiny_imagenette_vanilla", "ViT-Tiny/16", VIT_TINY),
+          "vit_base": ("vit_base_imagenette_vanilla", "ViT-Base/16", VIT_BASE),
           "vit_large": ("vit_large_imagenette_vanilla", "ViT-Large/16", VIT_LARGE)}
 
 
@@ -860,9 +864,9 @@ def run_ours(args):
         "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
         "frac_of_burst_peak": achieved / peaks["bf16_tflops"],
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture of a whole layer at
-        # this exact shape (profiles/r01_layer_ncu_full.txt: QKV 1.197, out-proj 1.814, FC1 1.509, FC2 2.887 GB; mean);
+        # this exact shape (profiles/r02_layer_ncu_full_end.txt: QKV 1.197, out-proj 1.817, FC1 1.507, FC2 2.862 GB; mean);
         # algorithmic bytes per launch of the same four GEMMs (operands + residual + outputs once): 1.24/1.87/1.55/2.80 GB
-        "traffic": 1.852e9 if (B * S * (n + 1) == 201728 and args.model == "vit_base") else None, "traffic_unit": "bytes per launch (ncu, mean of the 4 layer GEMMs)",
+        "traffic": 1.846e9 if (B * S * (n + 1) == 201728 and args.model == "vit_base") else None, "traffic_unit": "bytes per launch (ncu, mean of the 4 layer GEMMs)",
         "avg_launch_us": gemm[0] / gemm[2] * 1e3, "launches": gemm[2], "share_of_step": gemm[0] / total_t,
         "step_shares": {k: round(v[0] / total_t, 4) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1][0])},
     }
