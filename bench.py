@@ -754,6 +754,13 @@ def run_ours(args):
         t_steps = max(2, min(args.steps, 5))
         ms_t, launches_t, _ = timed(step_train, t_steps, 2)
         train_by_rank = by_rank[-1] if by_rank else None
+        # attribution run (multi-GPU only, outside the reported number): the same step with the gradient exchange switched
+        # off — the difference is what the all-reduce still costs after overlapping it with the backward pass
+        ms_t_nosync = None
+        if world > 1 and args.attribute_comm:
+            explainer.agb_grad_reducer = None
+            ms_t_nosync, _, _ = timed(step_train, t_steps, 1)
+            explainer.agb_grad_reducer = overlapped
         sps = world * Bt * t_steps / (ms_t * 1e-3)
         fl_eval = flops_per_eval(cfgd)
         H, I, E, T = cfg.hidden_size, cfg.intermediate_size, cfg.explainer_head_hidden_size, n + 1
@@ -776,6 +783,9 @@ def run_ours(args):
         train["frac_of_sustained_peak"] = train["tflops_per_gpu"] / peaks_t["bf16_tflops_sustained"]     # on EXECUTED FLOPs
         if train_by_rank is not None:
             train["ms_per_step_by_rank"] = train_by_rank
+        if ms_t_nosync is not None:
+            train["ms_per_step_without_grad_exchange"] = ms_t_nosync / t_steps
+            train["exposed_grad_exchange_ms_per_step"] = (ms_t - ms_t_nosync) / t_steps
 
     # ---- LTT leg (BASELINE.json north_star: "frozen backbone plus side network", "explainer side-network training uses an
     # NCCL gradient allreduce"; reference models/ltt_vit.py, recipes/ltt_vit.py): the same ViT backbone frozen, a narrow
@@ -937,6 +947,8 @@ def main():
     ap.add_argument("--workload", default="vit", choices=["vit", "bert_base_tayp_vanilla", "bert_base_tayp_kernel_shap"],
                     help="vit = the metric's own configuration (default, BASELINE.json configs[1] / configs[4] with --model "
                          "vit_large); the other two are BASELINE.json configs[2] and configs[3] as side workloads")
+    ap.add_argument("--attribute-comm", action="store_true",
+                    help="multi-GPU: also time the training step with the gradient exchange off (attribution only)")
     ap.add_argument("--grad-wire", default="fp32", choices=["fp32", "bf16"],
                     help="wire format of the gradient all-reduce of the training leg (fp32 = exact averaging)")
     ap.add_argument("--ks-batch", type=int, default=1024, help="explained samples per GPU per step of the KernelSHAP workload")
