@@ -435,16 +435,19 @@ int kept_first_order(const uint32_t* packed, int rows, int words, int T, uint8_t
 
 // dst[(r, q), :] = src[(r / S, order[r, q]), :]: the residual stream of every coalition row in kept-first token order,
 // gathered from the per-input embeddings (replaces repeat_rows on that path)
+// one warp per destination token row (no integer divisions per element; 8 rows per CTA)
 __global__ void __launch_bounds__(256)
-gather_token_rows_kernel(const uint4* __restrict__ src, const uint8_t* __restrict__ order, long long total16, int row16, int T,
+gather_token_rows_kernel(const uint4* __restrict__ src, const uint8_t* __restrict__ order, long long n_tok, int row16, int T,
                          int S, uint4* __restrict__ dst) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= total16) return;
-  const long long tok = gid / row16;                           // destination token row = r * T + q
-  const int c = (int)(gid - tok * row16);
+  const long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);           // destination token row = r * T + q
+  if (tok >= n_tok) return;
+  const int lane = threadIdx.x & 31;
   const long long r = tok / T;
   const int t = order[tok];
-  dst[gid] = __ldg(src + ((r / S) * T + t) * row16 + c);
+  const uint4* s = src + ((r / S) * T + t) * row16;
+  uint4* d = dst + tok * row16;
+#pragma unroll 2
+  for (int c = lane; c < row16; c += 32) d[c] = __ldg(s + c);
 }
 
 int gather_token_rows(const void* src, const uint8_t* order, int rows, int T, int S, long long row_bytes, void* dst,
@@ -453,10 +456,10 @@ int gather_token_rows(const void* src, const uint8_t* order, int rows, int T, in
   if (rows == 0) return AGB_OK;
   AGB_REQUIRE(src && order && dst, "null pointer");
   AGB_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0, "alignment");
-  const long long row16 = row_bytes / 16, total16 = row16 * rows * T;
-  AGB_REQUIRE((total16 + 255) / 256 <= 0x7fffffffLL && row16 <= 0x7fffffffLL, "grid limits");
-  gather_token_rows_kernel<<<(unsigned)((total16 + 255) / 256), 256, 0, st>>>(static_cast<const uint4*>(src), order, total16,
-                                                                             (int)row16, T, S, static_cast<uint4*>(dst));
+  const long long row16 = row_bytes / 16, n_tok = (long long)rows * T;
+  AGB_REQUIRE((n_tok + 7) / 8 <= 0x7fffffffLL && row16 <= 0x7fffffffLL, "grid limits");
+  gather_token_rows_kernel<<<(unsigned)((n_tok + 7) / 8), 256, 0, st>>>(static_cast<const uint4*>(src), order, n_tok, (int)row16, T, S,
+                                                                       static_cast<uint4*>(dst));
   AGB_CHECK_CUDA(cudaGetLastError());
   return AGB_OK;
 }
