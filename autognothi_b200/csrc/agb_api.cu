@@ -32,7 +32,11 @@ int get_attention_variant();
 int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, int M, int N, int K,
                       float alpha, const float* bias, int act, const bf16* res_bf16, const float* res_f32, int ldr,
                       void* out, int ldo, int out_f32, const float* ln_stats, int ln_parts, const float* ln_colsum,
-                      float ln_eps, bf16* out16, int ldo16, float* stats_out, cudaStream_t stream);
+                      float ln_eps, bf16* out16, int ldo16, float* stats_out, cudaStream_t stream, bf16* hl_hi = nullptr,
+                      bf16* hl_lo = nullptr, int ld_hl = 0);
+int gather_token_rows_hilo(const float* src, const uint8_t* order, int rows, int T, int S, int H, bf16* hi, bf16* lo,
+                           cudaStream_t st);
+int split_hilo(const float* x, long long n, bf16* hi, bf16* lo, cudaStream_t st);
 int rowstats_cast(const float* x, long long ldx, int rows, int H, bf16* out, long long ldo, float* stats,
                   cudaStream_t st);
 void set_gemm_variant(int v);
@@ -198,6 +202,21 @@ int agb_gemm_bf16_fused(const void* A, int lda, const void* B, int ldb, int M, i
     agb::set_last_error("agb_gemm_bf16_fused: shape / epilogue combination not covered (M=%d N=%d K=%d act=%d)", M, N, K, act);
   return rc;
 }
+int agb_gemm_bf16_hilo(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias, void* x_hi,
+                       void* x_lo, int ldx, float* stats_out, void* stream) {
+  AGB_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && x_hi && x_lo && stats_out, "operands");
+  AGB_REQUIRE((N % 256) == 0 && (lda % 8) == 0 && (ldb % 8) == 0 && (ldx % 8) == 0, "alignment");
+  AGB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0, "alignment");
+  const int rc = agb::gemm_bf16_pair_ex(static_cast<const bf16*>(A), lda, 0, static_cast<const bf16*>(B), ldb, 0, M, N, K,
+                                        1.0f, bias, 0, nullptr, nullptr, 0, nullptr, 0, 0, nullptr, 0, nullptr, 0.f, nullptr, 0,
+                                        stats_out, ST(stream), static_cast<bf16*>(x_hi), static_cast<bf16*>(x_lo), ldx);
+  if (rc == AGB_ERR_UNSUPPORTED)
+    agb::set_last_error("agb_gemm_bf16_hilo: shape not covered (M=%d N=%d K=%d)", M, N, K);
+  return rc;
+}
+int agb_split_hilo(const float* x, long long n, void* hi, void* lo, void* stream) {
+  return agb::split_hilo(x, n, static_cast<bf16*>(hi), static_cast<bf16*>(lo), ST(stream));
+}
 int agb_gemm_stats_parts(int N) { return 2 * ((N + 255) / 256); }
 int agb_rowstats_cast(const float* x, long long ldx, int rows, int H, void* out_bf16, long long ldo, float* stats,
                       void* stream) {
@@ -314,6 +333,10 @@ int agb_kept_first_order(const uint32_t* packed, int rows, int words, int T, uin
 int agb_gather_token_rows(const void* src, const uint8_t* order, int rows, int T, int S, long long row_bytes, void* dst,
                           void* stream) {
   return agb::gather_token_rows(src, order, rows, T, S, row_bytes, dst, ST(stream));
+}
+int agb_gather_token_rows_hilo(const float* src, const uint8_t* order, int rows, int T, int S, int H, void* hi, void* lo,
+                               void* stream) {
+  return agb::gather_token_rows_hilo(src, order, rows, T, S, H, static_cast<bf16*>(hi), static_cast<bf16*>(lo), ST(stream));
 }
 int agb_masked_attention_bf16_scatter(const void* qkv, const uint32_t* mask, int words, int rows, int share, int T, int H,
                                       int heads, const uint8_t* dst_pos, void* ctx, void* stream) {

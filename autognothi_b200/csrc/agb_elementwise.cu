@@ -450,6 +450,76 @@ gather_token_rows_kernel(const uint4* __restrict__ src, const uint8_t* __restric
   for (int c = lane; c < row16; c += 32) d[c] = __ldg(s + c);
 }
 
+// hi/lo planes of an fp32 value: hi = bf16(x), lo = bf16(x - hi); hi + lo carries 16 significant bits of x
+__device__ __forceinline__ void split_hilo8(const float4 a, const float4 b, uint4& hi, uint4& lo) {
+  hi.x = pack_bf16x2(a.x, a.y); hi.y = pack_bf16x2(a.z, a.w); hi.z = pack_bf16x2(b.x, b.y); hi.w = pack_bf16x2(b.z, b.w);
+  lo.x = pack_bf16x2(a.x - bf16_lo(hi.x), a.y - bf16_hi(hi.x));
+  lo.y = pack_bf16x2(a.z - bf16_lo(hi.y), a.w - bf16_hi(hi.y));
+  lo.z = pack_bf16x2(b.x - bf16_lo(hi.z), b.y - bf16_hi(hi.z));
+  lo.w = pack_bf16x2(b.z - bf16_lo(hi.w), b.w - bf16_hi(hi.w));
+}
+
+// gather_token_rows with the destination written as hi/lo planes (the residual stream of agb_gemm_bf16_hilo):
+// one warp per destination token row, 8 fp32 values -> 16 B of each plane per lane and step
+__global__ void __launch_bounds__(256)
+gather_token_rows_hilo_kernel(const float4* __restrict__ src, const uint8_t* __restrict__ order, long long n_tok, int row8, int T,
+                              int S, uint4* __restrict__ hi, uint4* __restrict__ lo) {
+  const long long tok = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (tok >= n_tok) return;
+  const int lane = threadIdx.x & 31;
+  const long long r = tok / T;
+  const int t = order[tok];
+  const float4* s = src + ((r / S) * T + t) * (2LL * row8);
+  uint4* dh = hi + tok * row8;
+  uint4* dl = lo + tok * row8;
+  for (int c = lane; c < row8; c += 32) {
+    uint4 h, l;
+    split_hilo8(__ldg(s + 2 * c), __ldg(s + 2 * c + 1), h, l);
+    dh[c] = h;
+    dl[c] = l;
+  }
+}
+
+int gather_token_rows_hilo(const float* src, const uint8_t* order, int rows, int T, int S, int H, bf16* hi, bf16* lo,
+                           cudaStream_t st) {
+  AGB_REQUIRE(rows >= 0 && T > 0 && S > 0 && H > 0 && H % 8 == 0 && rows % S == 0, "shape");
+  if (rows == 0) return AGB_OK;
+  AGB_REQUIRE(src && order && hi && lo, "null pointer");
+  AGB_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(hi) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(lo) & 15) == 0, "alignment");
+  const long long n_tok = (long long)rows * T;
+  AGB_REQUIRE((n_tok + 7) / 8 <= 0x7fffffffLL, "grid limits");
+  gather_token_rows_hilo_kernel<<<(unsigned)((n_tok + 7) / 8), 256, 0, st>>>(reinterpret_cast<const float4*>(src), order, n_tok,
+                                                                            H / 8, T, S, reinterpret_cast<uint4*>(hi),
+                                                                            reinterpret_cast<uint4*>(lo));
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
+__global__ void __launch_bounds__(256)
+split_hilo_kernel(const float4* __restrict__ x, long long n8, uint4* __restrict__ hi, uint4* __restrict__ lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  uint4 h, l;
+  split_hilo8(__ldg(x + 2 * i), __ldg(x + 2 * i + 1), h, l);
+  hi[i] = h;
+  lo[i] = l;
+}
+
+int split_hilo(const float* x, long long n, bf16* hi, bf16* lo, cudaStream_t st) {
+  AGB_REQUIRE(n >= 0 && n % 8 == 0, "element count must be a multiple of 8");
+  if (n == 0) return AGB_OK;
+  AGB_REQUIRE(x && hi && lo, "null pointer");
+  AGB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(hi) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(lo) & 15) == 0, "alignment");
+  const long long n8 = n / 8;
+  AGB_REQUIRE((n8 + 255) / 256 <= 0x7fffffffLL, "grid limits");
+  split_hilo_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(x), n8,
+                                                                 reinterpret_cast<uint4*>(hi), reinterpret_cast<uint4*>(lo));
+  AGB_CHECK_CUDA(cudaGetLastError());
+  return AGB_OK;
+}
+
 int gather_token_rows(const void* src, const uint8_t* order, int rows, int T, int S, long long row_bytes, void* dst,
                       cudaStream_t st) {
   AGB_REQUIRE(rows >= 0 && T > 0 && S > 0 && rows % S == 0 && row_bytes > 0 && (row_bytes % 16) == 0, "gather_token_rows shape");

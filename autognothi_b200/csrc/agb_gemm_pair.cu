@@ -17,6 +17,7 @@
 //   * GELU costs one MUFU and 8 issue slots (gelu_erf_tanhform) instead of two MUFU and ~16.
 //   * producer and MMA warps run convergently with elected-lane predication (uniform-register operands).
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (leader CTA only) + TMEM owner, 2..9 = epilogue.
+#include <cstdlib>
 #include <type_traits>
 
 #include "agb_common.cuh"
@@ -54,10 +55,17 @@ __global__ void __launch_bounds__(PG_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                  const __grid_constant__ CUtensorMap tmOut2, const PairGemmParams p) {
-  static_assert(RES == 0 || OUT_F32 == 1, "fp32 residual pairs with fp32 output");
-  static_assert(!STATS || (RES == 2 && OUT_F32 == 1), "statistics ride the fp32 residual epilogue");
+  // RES == 3 ("hi/lo"): the residual stream lives in HBM as two bf16 planes, x = hi + lo (hi = bf16(x), lo = bf16(x - hi):
+  // 16 significant bits).  The epilogue TMA-loads both planes of a 32 x 64 chunk, adds the accumulator, re-splits and
+  // stores both planes IN PLACE: the hi plane is at the same time the bf16 copy the next (LayerNorm-folded) GEMM reads as
+  // its A operand, so the separate copy of the fp32 variant (2 of its 12 bytes per element) is never written.
+  constexpr bool HL = RES == 3;
+  static_assert(RES == 0 || HL || OUT_F32 == 1, "fp32 residual pairs with fp32 output");
+  static_assert(!HL || (OUT_F32 == 0 && STATS == 1 && ACT == 0 && LNIN == 0), "hi/lo residual: bf16 planes + statistics");
+  static_assert(!STATS || (RES == 2 && OUT_F32 == 1) || HL, "statistics ride the residual epilogues");
   static_assert(!LNIN || (RES == 0 && OUT_F32 == 0), "folded LayerNorm feeds the bf16-output epilogues");
-  constexpr int NBOX = NBUF + (STATS ? 1 : 0);        // staging boxes per epilogue warp
+  constexpr int SLOT_BYTES = HL ? 2 * PG_BOX_BYTES : PG_BOX_BYTES;     // one ring slot (hi/lo: the two planes back to back)
+  constexpr int NBOX = HL ? 2 * NBUF : NBUF + (STATS ? 1 : 0);         // staging boxes per epilogue warp
   constexpr int B_ROWS = PG_BN / CG;                 // B rows staged by this CTA
   constexpr int A_BYTES = PG_BM * PG_BK * 2;
   constexpr int B_BYTES = B_ROWS * PG_BK * 2;
@@ -231,8 +239,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (!chunk_coords(g, row0, col0)) return;
       const int b = g % NBUF;
       const uint32_t bar = smem_u32(&my_res[b]);
-      mbar_arrive_expect_tx(bar, PG_BOX_BYTES);
-      tma_load_2d(stg_u32 + b * PG_BOX_BYTES, &tmRes, bar, col0, row0);
+      mbar_arrive_expect_tx(bar, SLOT_BYTES);
+      tma_load_2d(stg_u32 + b * SLOT_BYTES, &tmRes, bar, col0, row0);
+      if (HL) tma_load_2d(stg_u32 + b * SLOT_BYTES + PG_BOX_BYTES, &tmOut2, bar, col0, row0);   // lo plane
     };
 
     if (RES && lane == 0) {
@@ -276,7 +285,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int col0 = tcol0 + c * CHUNK_COLS;
         const bool active = row_ok && col0 < p.N;
         const int b = g % NBUF;
-        const uint32_t buf = stg_u32 + b * PG_BOX_BYTES;
+        const uint32_t buf = stg_u32 + b * SLOT_BYTES;
         uint32_t r[CHUNK_COLS];
         if (active) {
           tmem_ld32(tm_addr + c * CHUNK_COLS, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
@@ -310,7 +319,32 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint32_t addr = buf + row_off + ((static_cast<uint32_t>(j) ^ sw) << 4);
-            if (OUT_F32) {
+            if constexpr (HL) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias_c + (FULL ? 8 * j : min(8 * j, n_last))));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias_c + (FULL ? 8 * j + 4 : min(8 * j + 4, n_last))));
+              uint32_t hw[4], lw[4];
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(hw[0]), "=r"(hw[1]), "=r"(hw[2]), "=r"(hw[3]) : "r"(addr) : "memory");
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(lw[0]), "=r"(lw[1]), "=r"(lw[2]), "=r"(lw[3]) : "r"(addr + PG_BOX_BYTES) : "memory");
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              uint32_t nh[4], nl[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                // hi + lo is exact in fp32 (16 significant bits); one rounding for the sum with the accumulator
+                const float v0 = fmaf(__uint_as_float(r[8 * j + 2 * i + 0]), p.alpha, bb[2 * i + 0]) + (bf16_lo(hw[i]) + bf16_lo(lw[i]));
+                const float v1 = fmaf(__uint_as_float(r[8 * j + 2 * i + 1]), p.alpha, bb[2 * i + 1]) + (bf16_hi(hw[i]) + bf16_hi(lw[i]));
+                st_sum += v0 + v1;
+                st_sq = fmaf(v0, v0, fmaf(v1, v1, st_sq));
+                nh[i] = pack_bf16x2(v0, v1);
+                nl[i] = pack_bf16x2(v0 - bf16_lo(nh[i]), v1 - bf16_hi(nh[i]));
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(nh[0]), "r"(nh[1]), "r"(nh[2]), "r"(nh[3])
+                           : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + PG_BOX_BYTES), "r"(nl[0]), "r"(nl[1]), "r"(nl[2]),
+                           "r"(nl[3])
+                           : "memory");
+            } else if (OUT_F32) {
               const float4 bias4 = __ldg(reinterpret_cast<const float4*>(bias_c + (FULL ? 4 * j : min(4 * j, n_last))));
               float4 v;
               v.x = fmaf(__uint_as_float(r[4 * j + 0]), p.alpha, bias4.x);
@@ -384,7 +418,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&tmOut, buf, col0, out_row0);
-            if (STATS && (c & 1)) tma_store_2d(&tmOut2, buf16, col0 - CHUNK_COLS, row0);   // 64 bf16 columns
+            if (HL) tma_store_2d(&tmOut2, buf + PG_BOX_BYTES, col0, row0);                 // lo plane
+            else if (STATS && (c & 1)) tma_store_2d(&tmOut2, buf16, col0 - CHUNK_COLS, row0);   // 64 bf16 columns
             bulk_commit();
             if (RES) bulk_wait_read<0>();   // boxes handed to the store engine: free for the next residual / copy
           }
@@ -413,9 +448,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int CG, int STAGES, int NBUF, int STATS>
+template <int CG, int STAGES, int NBUF, int STATS, int HL = 0>
 constexpr int pair_smem_bytes() {
-  return STAGES * (PG_BM * PG_BK * 2 + (PG_BN / CG) * PG_BK * 2) + PG_EPI_WARPS * (NBUF + STATS) * PG_BOX_BYTES +
+  return STAGES * (PG_BM * PG_BK * 2 + (PG_BN / CG) * PG_BK * 2) + PG_EPI_WARPS * (HL ? 2 * NBUF : NBUF + STATS) * PG_BOX_BYTES +
          (2 * STAGES + 4 + PG_EPI_WARPS * NBUF) * 8 + 16 + 1024;
 }
 
@@ -423,7 +458,7 @@ template <int CG, int STAGES, int NBUF, int ACT, int RES, int OUT_F32, int LNIN,
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                        const CUtensorMap& tmRes, const CUtensorMap& tmOut2, const PairGemmParams& p,
                        cudaStream_t stream) {
-  constexpr int SMEM = pair_smem_bytes<CG, STAGES, NBUF, STATS>();
+  constexpr int SMEM = pair_smem_bytes<CG, STAGES, NBUF, STATS, RES == 3>();
   static_assert(SMEM <= 232448, "shared memory budget");
   auto kern = gemm_pair_kernel<CG, STAGES, NBUF, ACT, RES, OUT_F32, LNIN, STATS>;
   static int max_pairs = 0;   // co-resident CTAs (CG = 1) or clusters (CG = 2)
@@ -478,11 +513,14 @@ static float* g_splitk_ws = nullptr;      // grow-only workspace (single-stream 
 static size_t g_splitk_ws_bytes = 0;
 
 static int g_gemm_variant = 0;  // 0 auto, 1 legacy kernel only, 2 force CG=1, 3 force CG=2
+static int g_hl_cfg = [] { const char* e = getenv("AGB_GEMM_HILO_CFG"); return e ? atoi(e) : 0; }();   // A/B switch, see below
 void set_gemm_variant(int v) { g_gemm_variant = v; }
 int get_gemm_variant() { return g_gemm_variant; }
 
 // Returns AGB_ERR_UNSUPPORTED when this kernel does not cover the request (the caller then uses the
 // first-generation kernel): narrow N, bf16 residual, fp32 residual with bf16 output, GELU + residual.
+// hl_hi / hl_lo (round 2): the residual stream as two bf16 planes updated in place (kernel comment at RES == 3); `out`,
+// `res_f32` and `out16` are unused then and stats_out is mandatory.
 // Optional fusions (nullptr = off):
 //   ln_stats / ln_colsum : LayerNorm of the A rows folded into the epilogue (bf16 output only, no residual)
 //   out16 / stats_out    : with an fp32 residual epilogue, also emit a bf16 copy of the output and its per-row
@@ -490,10 +528,18 @@ int get_gemm_variant() { return g_gemm_variant; }
 int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, int M, int N, int K,
                       float alpha, const float* bias, int act, const bf16* res_bf16, const float* res_f32, int ldr,
                       void* out, int ldo, int out_f32, const float* ln_stats, int ln_parts, const float* ln_colsum,
-                      float ln_eps, bf16* out16, int ldo16, float* stats_out, cudaStream_t stream) {
+                      float ln_eps, bf16* out16, int ldo16, float* stats_out, cudaStream_t stream, bf16* hl_hi, bf16* hl_lo,
+                      int ld_hl) {
   const bool lnin = ln_stats != nullptr, stats = stats_out != nullptr;
+  const bool hl = hl_hi != nullptr;
   if (g_gemm_variant == 1) return AGB_ERR_UNSUPPORTED;
   if (N < 192 || res_bf16 != nullptr) return AGB_ERR_UNSUPPORTED;
+  if (hl) {   // hi/lo residual planes, updated in place: x = hi + lo  <-  x + alpha A B^T + bias
+    if (hl_lo == nullptr || res_f32 != nullptr || act != 0 || lnin || !stats || (N % PG_BN) != 0 || (ld_hl % 8) != 0 ||
+        (reinterpret_cast<uintptr_t>(hl_hi) & 15) != 0 || (reinterpret_cast<uintptr_t>(hl_lo) & 15) != 0)
+      return AGB_ERR_UNSUPPORTED;
+    out = hl_hi; ldo = ld_hl; out_f32 = 0;
+  }
   if (res_f32 != nullptr && (!out_f32 || act != 0)) return AGB_ERR_UNSUPPORTED;
   const int oes = out_f32 ? 4 : 2;
   if (((long long)ldo * oes) % 16 != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0) return AGB_ERR_UNSUPPORTED;
@@ -502,8 +548,8 @@ int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, 
   if (lnin && (out_f32 || res_f32 || a_mn || ln_colsum == nullptr || ln_parts <= 0 || ln_parts > 8 || alpha != 1.0f ||
                (reinterpret_cast<uintptr_t>(ln_colsum) & 15) != 0))
     return AGB_ERR_UNSUPPORTED;
-  if (stats && (!res_f32 || out16 == nullptr || (N % PG_BN) != 0 || (ldo16 % 8) != 0 ||
-                (reinterpret_cast<uintptr_t>(out16) & 15) != 0))
+  if (stats && !hl && (!res_f32 || out16 == nullptr || (N % PG_BN) != 0 || (ldo16 % 8) != 0 ||
+                       (reinterpret_cast<uintptr_t>(out16) & 15) != 0))
     return AGB_ERR_UNSUPPORTED;
 
   // CTA pairs pay off once there is at least ~one full wave of 256-row tiles; small problems keep CG = 1
@@ -517,7 +563,7 @@ int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, 
   const int num_kb = (K + PG_BK - 1) / PG_BK;
   void* final_out = out;
   const int final_ldo = ldo;
-  if (cg == 1 && out_f32 && !res_f32 && !lnin && !stats && act == 0 && bias == nullptr && alpha == 1.0f &&
+  if (cg == 1 && out_f32 && !res_f32 && !hl && !lnin && !stats && act == 0 && bias == nullptr && alpha == 1.0f &&
       (M % PG_BM) == 0 && (N % 4) == 0 && (ldo % 4) == 0 && num_kb >= 32 && g_gemm_variant == 0) {
     const long long tiles1 = (long long)(M / PG_BM) * ((N + PG_BN - 1) / PG_BN);
     int want = (int)(sm_count() / tiles1);
@@ -554,10 +600,11 @@ int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, 
   rc = encode_tmap_2d(&tmOut, out, oes, N, (uint64_t)M * splits, (uint64_t)ldo * oes, out_f32 ? 32 : 64, 32);
   if (rc != AGB_OK) return rc;
   if (res_f32) rc = encode_tmap_2d(&tmRes, res_f32, 4, N, M, (uint64_t)ldr * 4, 32, 32);
-  else         tmRes = tmOut;
+  else         tmRes = tmOut;                 // hi/lo: the hi plane is residual and output
   if (rc != AGB_OK) return rc;
-  if (stats) rc = encode_tmap_2d(&tmOut2, out16, 2, N, M, (uint64_t)ldo16 * 2, 64, 32);
-  else       tmOut2 = tmOut;
+  if (hl)         rc = encode_tmap_2d(&tmOut2, hl_lo, 2, N, M, (uint64_t)ld_hl * 2, 64, 32);
+  else if (stats) rc = encode_tmap_2d(&tmOut2, out16, 2, N, M, (uint64_t)ldo16 * 2, 64, 32);
+  else            tmOut2 = tmOut;
   if (rc != AGB_OK) return rc;
 
   if (bias == nullptr) {   // the epilogue reads bias unconditionally: substitute zeros
@@ -574,7 +621,21 @@ int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, 
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.alpha = alpha; p.a_mn = a_mn; p.b_mn = b_mn;
   p.splits = splits; p.kb_per_split = kb_per_split;
   p.ln_stats = ln_stats; p.ln_parts = ln_parts; p.ln_colsum = ln_colsum; p.ln_eps = ln_eps; p.stats_out = stats_out;
-  const int res = res_f32 ? 2 : 0;
+  const int res = hl ? 3 : (res_f32 ? 2 : 0);
+  if (hl) {
+    // ring slots are 8 KB here (both planes of a 32 x 64 chunk).  Short K (the HBM-bound out-projection): 3 stages + two
+    // slots per warp (342-345 us in-step at the bench shape), or (AGB_GEMM_HILO_CFG=1) 4 stages + one slot (350-368 us);
+    // long K (FC2): 5 stages + one slot.  An L2 prefetch of the residual chunks (cp.async.bulk.prefetch.tensor) 2-16 chunks
+    // ahead of their TMA load was measured and made every residual GEMM SLOWER (profiles/r02_hilo_residual_ab.txt).
+    if (cg == 2) {
+      if (K < 2048) {
+        if (g_hl_cfg == 1) return launch_pair<2, 4, 1, 0, 3, 0, 0, 1>(tmA, tmB, tmOut, tmRes, tmOut2, p, stream);
+        return launch_pair<2, 3, 2, 0, 3, 0, 0, 1>(tmA, tmB, tmOut, tmRes, tmOut2, p, stream);
+      }
+      return launch_pair<2, 5, 1, 0, 3, 0, 0, 1>(tmA, tmB, tmOut, tmRes, tmOut2, p, stream);
+    }
+    return launch_pair<1, 3, 1, 0, 3, 0, 0, 1>(tmA, tmB, tmOut, tmRes, tmOut2, p, stream);
+  }
   // (stages, residual ring) per configuration: CTA pairs stage 32 KB per k-block (5 stages: the K = 3072 GEMM was
   // latency-starved with 4), single CTAs 48 KB (3 stages); the statistics variant trades one ring slot for the copy box
   auto finish = [&](int lrc) -> int {
@@ -614,7 +675,7 @@ int gemm_bf16_pair(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int
                    float alpha, const float* bias, int act, const bf16* res_bf16, const float* res_f32, int ldr,
                    void* out, int ldo, int out_f32, cudaStream_t stream) {
   return gemm_bf16_pair_ex(A, lda, a_mn, B, ldb, b_mn, M, N, K, alpha, bias, act, res_bf16, res_f32, ldr, out, ldo,
-                           out_f32, nullptr, 0, nullptr, 0.f, nullptr, 0, nullptr, stream);
+                           out_f32, nullptr, 0, nullptr, 0.f, nullptr, 0, nullptr, stream, nullptr, nullptr, 0);
 }
 
 }  // namespace agb

@@ -11,6 +11,7 @@ replication (scripts/train_explainer.py:159-163) never exists.  S = 1 gives the 
 """
 from __future__ import annotations
 
+import os
 from typing import Any, Dict, List, Optional, Tuple
 
 import torch
@@ -182,6 +183,27 @@ def vit_layer_fused(lw: LayerWeights, x: Tensor, x16: Optional[Tensor], stats: O
     return x, x16n, statsn
 
 
+# Surrogate / classifier evaluation of the bf16 ViT backbone (fused chain, CLS-only last block): the residual stream lives in
+# HBM as two bf16 planes, x = hi + lo (16 significant bits; hi = bf16(x)), updated in place by the residual GEMMs
+# (agb_gemm_bf16_hilo).  The hi plane IS the bf16 copy the LayerNorm-folded QKV / FC1 GEMMs read, so the separate copy of the
+# fp32-stream variant is never written: 10 instead of 12 bytes per element for the HBM-bound output projection.  A plain bf16
+# stream (8 bits) pushes the attributions past the 1e-2 tolerance; 16 bits does not move them.
+HILO_RESIDUAL = os.environ.get("AGB_HILO_RESIDUAL", "1") != "0"      # the environment switch is for A/B runs of bench.py
+
+
+def vit_layer_hilo(lw: LayerWeights, xh: Tensor, xl: Tensor, stats: Optional[Tensor], T: int, heads: int, eps: float,
+                   masks: Tensor, ctx: Optional[Tensor] = None, nkeep: Optional[Tensor] = None) -> Tensor:
+    """vit_layer_fused on the hi/lo residual stream (xh, xl) (rows*T, H) bf16, updated in place; stats: row statistics of
+    the incoming stream (unused when the caller supplies the first block's ctx).  -> statistics of the outgoing stream."""
+    f = lw.fold()
+    if ctx is None:
+        qkv, _, _ = ops.gemm_bf16_fused(xh, f["wqkv"], f["bqkv"], ln=(stats, f["cqkv"], eps))
+        ctx = ops.attention_prefix(qkv, nkeep, T, heads) if nkeep is not None else ops.masked_attention(qkv, masks, T, heads, ops.MASK_MUL0)
+    ystats = ops.gemm_bf16_hilo(ctx, lw.wo, lw.bo, xh, xl)
+    h = ops.gemm_bf16_fused(xh, f["w1"], f["b1"], act=ops.ACT_GELU, ln=(ystats, f["c1"], eps))[0]
+    return ops.gemm_bf16_hilo(h, lw.w2, lw.b2, xh, xl)
+
+
 def bert_layer(pol: _Policy, lw: LayerWeights, x: Tensor, xa: Optional[Tensor], masks: Tensor, T: int, heads: int, eps: float,
                ctx: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     """post-LN block; x fp32 residual stream, xa its activation-dtype copy.
@@ -222,13 +244,20 @@ DROP_MASKED_TOKENS = True
 KEPT_FIRST_ORDER = True
 
 
-def last_block_cls_only(pol: _Policy, lw: LayerWeights, vit: bool, x: Tensor, xa: Optional[Tensor], x16: Optional[Tensor],
-                        stats: Optional[Tensor], masks: Tensor, T: int, heads: int, eps: float) -> Tuple[Tensor, Optional[Tensor]]:
+def last_block_cls_only(pol: _Policy, lw: LayerWeights, vit: bool, x: Optional[Tensor], xa: Optional[Tensor], x16: Optional[Tensor],
+                        stats: Optional[Tensor], masks: Tensor, T: int, heads: int, eps: float,
+                        x_lo: Optional[Tensor] = None) -> Tuple[Tensor, Optional[Tensor]]:
     """Last encoder block restricted to the CLS query.  x (rows*T, H) fp32 residual stream; ViT fused path passes
     (x16, stats) for the folded LayerNorm, otherwise they are None; BERT passes xa (activation-dtype copy of x).
+    hi/lo residual stream: x is None, x16 is the hi plane and x_lo the lo plane.
     -> (x_cls (rows, H) fp32 after the block, activation copy | None)"""
-    rows, H = masks.shape[0], x.shape[1]
-    x_cls = x.view(rows, T, H)[:, 0, :].contiguous()
+    rows = masks.shape[0]
+    if x is None:
+        H = x16.shape[1]
+        x_cls = x16.view(rows, T, H)[:, 0, :].float() + x_lo.view(rows, T, H)[:, 0, :].float()
+    else:
+        H = x.shape[1]
+        x_cls = x.view(rows, T, H)[:, 0, :].contiguous()
     wq, wkv, bq, bkv = lw.wqkv[:H], lw.wqkv[H:], lw.bqkv[:H], lw.bqkv[H:]
     if vit:
         if x16 is not None:
@@ -312,6 +341,8 @@ def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tens
     share = (SHARE_FIRST_BLOCK and S > 1 and pol.bf16 and len(full) > 0 and T <= 512 and H == heads * 64)
     ctx0 = None
     nkeep = None             # set when the rows are switched to kept-first token order (KEPT_FIRST_ORDER)
+    hilo = HILO_RESIDUAL and fused and cls_only and layer_hook is None and len(full) > 0
+    xh = xl = None           # hi/lo residual stream (see HILO_RESIDUAL)
     if share:
         x_img = embed(bw, cfg, pol, xs, 1)                                   # (B, T, H) fp32, one row block per input
         assert x_img.shape[1] == T, f"sequence length {x_img.shape[1]} != n_players + 1 = {T}"
@@ -333,7 +364,11 @@ def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tens
             # prefixes of length nkeep: the attention kernels fold the masked tail into one virtual key.
             order, pos, nkeep, masks_p = ops.kept_first_order(masks, T)
             ctx0 = ops.masked_attention_scatter(qkv0, masks, T, heads, S, pos)
-            x3 = ops.gather_token_rows(x_img, order, S)
+            if hilo:
+                xh, xl = ops.gather_token_rows_hilo(x_img, order, S)
+                x3 = xh
+            else:
+                x3 = ops.gather_token_rows(x_img, order, S)
             masks = masks_p
         else:
             ctx0 = ops.masked_attention(qkv0, masks, T, heads, ops.MASK_MUL0 if bw.vit else ops.MASK_NEGINF, share=S)
@@ -344,6 +379,16 @@ def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tens
     rows = x3.shape[0]
     assert masks.shape[0] == rows, f"need one packed mask row per (input, coalition): {masks.shape[0]} vs {rows}"
     x = x3.reshape(rows * T, H)
+    if hilo:
+        stats = None
+        if xh is None:
+            if ctx0 is None:
+                _, stats = ops.rowstats_cast(x)
+            xh, xl = ops.split_hilo(x)
+        xh, xl = xh.reshape(rows * T, H), xl.reshape(rows * T, H)
+        for i, lw in enumerate(full):
+            stats = vit_layer_hilo(lw, xh, xl, stats, T, heads, eps, masks, ctx=ctx0 if i == 0 else None, nkeep=nkeep)
+        return last_block_cls_only(pol, bw.layers[-1], True, None, None, xh, stats, masks, T, heads, eps, x_lo=xl)
     if bw.vit:
         if fused:
             x16 = stats = None
@@ -447,7 +492,7 @@ class SurrogateEngine:
         if (0 < B * S <= GRAPH_MAX_ROWS and B * S <= max_rows and self.pol.bf16 and not self._packed_path()
                 and nat.PROFILE is None and not torch.cuda.is_current_stream_capturing()):
             key = (xs.device, tuple(xs.shape), xs.dtype, tuple(masks.shape), S, FUSE_LAYERNORM, CLS_ONLY_LAST_BLOCK,
-                   SHARE_FIRST_BLOCK, KEPT_FIRST_ORDER)
+                   SHARE_FIRST_BLOCK, KEPT_FIRST_ORDER, HILO_RESIDUAL)
             return self.graphs.run(key, lambda x_, m_: self._probs_eager(x_, m_, S, max_rows), (xs.contiguous(), masks))
         return self._probs_eager(xs, masks, S, max_rows)
 

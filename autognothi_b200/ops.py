@@ -173,6 +173,33 @@ def gemm_bf16_fused(a: Tensor, w: Tensor, bias: Optional[Tensor], *, act: int = 
     return out, copy16, stats
 
 
+def gemm_bf16_hilo(a: Tensor, w: Tensor, bias: Optional[Tensor], x_hi: Tensor, x_lo: Tensor) -> Tensor:
+    """Residual GEMM on a hi/lo residual stream (agb_gemm_bf16_hilo): (x_hi + x_lo) += a @ w.T + bias, both bf16 planes
+    updated in place; -> per-row partial statistics [M, parts, 2] of the new stream for the LayerNorm-folded consumer."""
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and x_hi.shape == (M, N) and x_lo.shape == (M, N)
+    assert x_hi.dtype == torch.bfloat16 and x_lo.dtype == torch.bfloat16 and x_hi.is_contiguous() and x_lo.is_contiguous()
+    stats = torch.empty((M, gemm_stats_parts(N), 2), dtype=torch.float32, device=a.device)
+    nat.NEXT_META = 2.0 * M * N * K
+    nat.NEXT_INFO = (f"M{M} N{N} K{K} +res hi/lo +stats",
+                     2.0 * M * K + 2.0 * N * K + 8.0 * M * N + 8.0 * M * gemm_stats_parts(N))
+    nat.call("agb_gemm_bf16_hilo", nat.ptr(a), a.stride(0), nat.ptr(w), w.stride(0), M, N, K, nat.ptr(bias), nat.ptr(x_hi),
+             nat.ptr(x_lo), N, nat.ptr(stats), nat.stream())
+    return stats
+
+
+def split_hilo(x: Tensor) -> Tuple[Tensor, Tensor]:
+    """fp32 -> (hi, lo) bf16 planes with hi + lo == x to 16 significant bits (agb_split_hilo)."""
+    x = _c(x)
+    assert x.dtype == torch.float32 and x.numel() % 8 == 0
+    hi = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    nat.call("agb_split_hilo", nat.ptr(x), x.numel(), nat.ptr(hi), nat.ptr(lo), nat.stream())
+    return hi, lo
+
+
 def rowstats_cast(x: Tensor) -> Tuple[Tensor, Tensor]:
     """fp32 (rows, H) -> (bf16 copy, stats (rows, 1, 2) = per-row (sum, sum of squares))."""
     assert x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1
@@ -398,6 +425,19 @@ def gather_token_rows(x: Tensor, order: Tensor, S: int) -> Tensor:
     out = torch.empty((rows, T, H), dtype=x.dtype, device=x.device)
     nat.call("agb_gather_token_rows", nat.ptr(x), nat.ptr(order), rows, T, S, H * x.element_size(), nat.ptr(out), nat.stream())
     return out
+
+
+def gather_token_rows_hilo(x: Tensor, order: Tensor, S: int) -> Tuple[Tensor, Tensor]:
+    """gather_token_rows of fp32 rows, written as the (hi, lo) bf16 planes of the hi/lo residual stream."""
+    x = _c(x)
+    B, T, H = x.shape
+    rows = order.shape[0]
+    assert x.dtype == torch.float32 and H % 8 == 0
+    assert rows == B * S and order.shape[1] == T and order.dtype == torch.uint8 and order.is_contiguous()
+    hi = torch.empty((rows, T, H), dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty((rows, T, H), dtype=torch.bfloat16, device=x.device)
+    nat.call("agb_gather_token_rows_hilo", nat.ptr(x), nat.ptr(order), rows, T, S, H, nat.ptr(hi), nat.ptr(lo), nat.stream())
+    return hi, lo
 
 
 def masked_attention_scatter(qkv: Tensor, packed_mask: Tensor, T: int, heads: int, share: int, pos: Tensor) -> Tensor:

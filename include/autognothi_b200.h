@@ -62,6 +62,16 @@ int agb_gemm_bf16_fused(const void* A, int lda, const void* B, int ldb, int M, i
                         const float* ln_stats, int ln_parts, const float* ln_colsum, float ln_eps,
                         void* out_bf16_copy, int ldo_copy, float* stats_out, void* stream);
 int agb_gemm_stats_parts(int N);
+/* Residual GEMM of the same chain on a hi/lo residual stream (round 2; the two residual adds of reference
+ * models/vanilla_vit.py:369-376).  The stream x is kept as two bf16 planes with x = hi + lo (hi = bf16(x), lo = bf16(x - hi):
+ * 16 significant bits); the call updates both planes IN PLACE,  x <- x + A B^T + bias,  and writes the per-row partial
+ * statistics of the new x exactly as agb_gemm_bf16_fused does.  The hi plane doubles as the bf16 copy the consuming
+ * LayerNorm-folded GEMM takes as A, so no separate copy is written: 10 instead of 12 bytes of HBM traffic per element for
+ * the HBM-bound attention output projection.  N % 256 == 0, ldx % 8 == 0; AGB_ERR_UNSUPPORTED otherwise. */
+int agb_gemm_bf16_hilo(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias, void* x_hi,
+                       void* x_lo, int ldx, float* stats_out, void* stream);
+/* fp32 -> hi/lo planes (n % 8 == 0). */
+int agb_split_hilo(const float* x, long long n, void* hi, void* lo, void* stream);
 /* bf16 copy + one (sum, sum of squares) pair per row of an fp32 matrix: the entry of the chain above. */
 int agb_rowstats_cast(const float* x, long long ldx, int rows, int H, void* out_bf16, long long ldo, float* stats,
                       void* stream);
@@ -159,6 +169,9 @@ int agb_kept_first_order(const uint32_t* packed, int rows, int words, int T, uin
  * scripts/train_explainer.py:159-163, on that path). */
 int agb_gather_token_rows(const void* src, const uint8_t* order, int rows, int T, int S, long long row_bytes, void* dst,
                           void* stream);
+/* agb_gather_token_rows from fp32 rows of H values into hi/lo planes (the residual stream of agb_gemm_bf16_hilo). */
+int agb_gather_token_rows_hilo(const float* src, const uint8_t* order, int rows, int T, int S, int H, void* hi, void* lo,
+                               void* stream);
 /* agb_masked_attention_bf16_shared whose query token t of row r is written to token position dst_pos[r, t] of ctx
  * (rows, T, H): the first block of the kept-first evaluation order.  T <= 208, head dim 64, ViT mask semantics. */
 int agb_masked_attention_bf16_scatter(const void* qkv, const uint32_t* mask, int words, int rows, int share, int T, int H,

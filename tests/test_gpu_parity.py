@@ -171,6 +171,85 @@ def test_gemm_bf16_layernorm_folded_chain(agb, M, act):
     torch.testing.assert_close(out.float(), ref, rtol=3e-2, atol=3e-2)
 
 
+def _hilo_ref(x):
+    hi = x.bfloat16()
+    return hi, (x - hi.float()).bfloat16()
+
+
+def test_split_hilo_bit_exact(agb):
+    """hi = bf16(x), lo = bf16(x - hi): bit-exact against the torch formula; hi + lo carries 16 significant bits."""
+    torch.manual_seed(2)
+    x = torch.randn(1000, 768, device=DEV) * torch.logspace(-3, 3, 1000, device=DEV)[:, None]
+    hi, lo = agb.split_hilo(x)
+    rh, rl = _hilo_ref(x)
+    assert torch.equal(hi, rh) and torch.equal(lo, rl)
+    rel = ((hi.float() + lo.float()) - x).abs() / x.abs().clamp_min(1e-30)
+    assert float(rel.max()) <= 2.0 ** -16
+
+
+@pytest.mark.parametrize("M,K", [(300, 768), (6304, 3072), (25216 + 17, 768), (40000, 3072)])
+def test_gemm_bf16_hilo_residual(agb, M, K):
+    """agb_gemm_bf16_hilo: (hi + lo) += A W^T + b in place; the new hi plane is bf16 of the new stream (what the consuming
+    LayerNorm-folded GEMM reads), hi + lo reproduces it to 16 bits, statistics as the fp32-stream variant emits them."""
+    torch.manual_seed(4)
+    H = 768
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    w = (torch.randn(H, K, device=DEV) / K ** 0.5).bfloat16()
+    b = torch.randn(H, device=DEV) * 0.1
+    x = torch.randn(M, H, device=DEV) * 2.0 + 0.3
+    hi, lo = agb.split_hilo(x)
+    x0 = hi.float() + lo.float()
+    # the fp32-stream kernel on the same inputs is the like-for-like reference (same MMA order); torch fp32 the loose one
+    y_f32, y16, st_f32 = agb.gemm_bf16_fused(a, w, b, residual=x0.clone(), emit_copy_stats=True, out_dtype=torch.float32)
+    stats = agb.gemm_bf16_hilo(a, w, b, hi, lo)
+    y = hi.float() + lo.float()
+    torch.testing.assert_close(y, x0 + a.float() @ w.float().t() + b, rtol=2e-3, atol=2e-3)
+    # |hi + lo - v| <= 2^-17 |v| of the re-split (plus one fp32 rounding of the sum)
+    assert float(((y - y_f32).abs() / y_f32.abs().clamp_min(1e-3)).max()) <= 2.0 ** -15
+    assert float((hi != y16).float().mean()) <= 1e-3          # same rounding except where fp32 ties differ by the add order
+    assert torch.equal(lo, (y - hi.float()).bfloat16())       # lo is itself a bf16 number: the split is idempotent
+    assert stats.shape == st_f32.shape
+    torch.testing.assert_close(stats, st_f32, rtol=1e-4, atol=1e-2)
+    # second application keeps accumulating in place
+    agb.gemm_bf16_hilo(a, w, b, hi, lo)
+    torch.testing.assert_close(hi.float() + lo.float(), y_f32 + a.float() @ w.float().t() + b, rtol=3e-3, atol=3e-3)
+
+
+def test_gather_token_rows_hilo(agb):
+    torch.manual_seed(6)
+    B, S, T, H = 3, 5, 197, 768
+    x = torch.randn(B, T, H, device=DEV) * 3
+    order = torch.stack([torch.randperm(T, device=DEV) for _ in range(B * S)]).to(torch.uint8)
+    ref = agb.gather_token_rows(x, order, S)
+    hi, lo = agb.gather_token_rows_hilo(x, order, S)
+    rh, rl = _hilo_ref(ref)
+    assert torch.equal(hi, rh) and torch.equal(lo, rl)
+
+
+def test_vit_base_hilo_residual_stream_matches_fp32_stream(agb):
+    """bf16 ViT-B surrogate evaluation with the residual stream as hi/lo bf16 planes vs the fp32 stream (both kept-first and
+    token order): the 16-bit stream does not move the probabilities (a plain bf16 stream does)."""
+    from autognothi_b200 import engine
+    rec, cfgd, srg, exp = _build("vit_base", "bf16")
+    B, S = 4, 32
+    n = rec.n_players(rec.t_config(**cfgd))
+    xs = torch.from_numpy(synth.inputs(cfgd, B, seed=3)).to(DEV)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    masks = (torch.rand((B, S, n), generator=g) > 0.5).to(torch.int64).to(DEV)
+    old = engine.HILO_RESIDUAL, engine.KEPT_FIRST_ORDER, engine.SHARE_FIRST_BLOCK
+    out = {}
+    try:
+        with torch.no_grad():
+            for hl in (True, False):
+                for kf, share in ((True, True), (False, True), (False, False)):
+                    engine.HILO_RESIDUAL, engine.KEPT_FIRST_ORDER, engine.SHARE_FIRST_BLOCK = hl, kf, share
+                    out[(hl, kf, share)] = rec.fw_surrogate(srg, xs, masks)[0].float()
+    finally:
+        engine.HILO_RESIDUAL, engine.KEPT_FIRST_ORDER, engine.SHARE_FIRST_BLOCK = old
+    for key in ((True, True), (False, True), (False, False)):
+        torch.testing.assert_close(out[(True,) + key], out[(False,) + key], rtol=0, atol=1e-3)
+
+
 def test_vit_base_layernorm_folding_matches_layernorm_kernels(agb):
     """bf16 ViT-B backbone with every LayerNorm folded into the GEMMs vs the LayerNorm-kernel path."""
     from autognothi_b200 import engine
