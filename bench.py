@@ -71,6 +71,11 @@ def flops_per_eval_executed(c, S=S_COALITIONS):
     return flops_per_eval(c) - float(layer - last) - float(shared)
 
 
+def _hilo_on() -> bool:
+    from autognothi_b200 import engine
+    return bool(engine.HILO_RESIDUAL and engine.FUSE_LAYERNORM and engine.CLS_ONLY_LAST_BLOCK)
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -874,9 +879,11 @@ def run_ours(args):
         "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
         "frac_of_burst_peak": achieved / peaks["bf16_tflops"],
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture of a whole layer at
-        # this exact shape (profiles/r02_layer_ncu_full_end.txt: QKV 1.197, out-proj 1.817, FC1 1.507, FC2 2.862 GB; mean);
-        # algorithmic bytes per launch of the same four GEMMs (operands + residual + outputs once): 1.24/1.87/1.55/2.80 GB
-        "traffic": 1.846e9 if (B * S * (n + 1) == 201728 and args.model == "vit_base") else None, "traffic_unit": "bytes per launch (ncu, mean of the 4 layer GEMMs)",
+        # this exact shape: hi/lo residual stream (profiles/r02_layer_ncu_full_hilo.txt) QKV 1.198, out-proj 1.508, FC1 1.509,
+        # FC2 2.606 GB, mean 1.705; fp32 residual stream (r02_layer_ncu_full_end.txt) 1.197 / 1.817 / 1.507 / 2.862, mean 1.846;
+        # algorithmic bytes per launch of the same four GEMMs (operands + residual + outputs once): 1.24/1.55/1.55/2.49 GB (hi/lo)
+        "traffic": (1.705e9 if _hilo_on() else 1.846e9) if (B * S * (n + 1) == 201728 and args.model == "vit_base") else None,
+        "traffic_unit": "bytes per launch (ncu, mean of the 4 layer GEMMs)",
         "avg_launch_us": gemm[0] / gemm[2] * 1e3, "launches": gemm[2], "share_of_step": gemm[0] / total_t,
         "step_shares": {k: round(v[0] / total_t, 4) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1][0])},
     }

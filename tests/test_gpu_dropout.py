@@ -40,7 +40,8 @@ def test_elementwise_dropout_statistics_residual_and_adjoint(agb, p):
     yy = torch.randn(n, device=DEV)
     lhs = float((agb.dropout(yy, thr, 99, 3) * g).double().sum())
     rhs = float((yy * agb.dropout(g, thr, 99, 3)).double().sum())
-    assert abs(lhs - rhs) <= 1e-6 * max(1.0, abs(lhs))
+    # the two sides round y * scale resp. g * scale in fp32: ~6e-8 relative per term, a random walk over n = 2^20 terms
+    assert abs(lhs - rhs) <= 1e-3
     # no visible structure: neighbouring elements are uncorrelated
     k = kept.float() - (1 - p)
     assert abs(float((k[:-1] * k[1:]).mean())) < 5e-3
