@@ -515,8 +515,8 @@ def test_full_path_bf16_tensor_cores_vs_reference_golden(agb, golden_dir, name):
 
 def test_bench_shape_engages_the_bench_kernels(agb, golden_dir):
     """model_vit_base_b4s32 (4 inputs x 32 coalitions = 128 rows, M = 25 216) is the smallest reference-pinned case that runs
-    the kernel variants of the benchmark: CTA-pair tcgen05 GEMMs, the LayerNorm-folded chain, first-block sharing, the
-    kept-first token order with the split-softmax attention kernel and the CLS-only last block.  Checked on the launch log of the eager path."""
+    the kernel variants of the benchmark: CTA-pair tcgen05 GEMMs, the LayerNorm-folded chain on the hi/lo residual stream,
+    first-block sharing, the kept-first token order with the split-softmax attention kernel and the CLS-only last block.  Checked on the launch log of the eager path."""
     from autognothi_b200 import _native as nat
     from autognothi_b200 import engine
     g = _load(golden_dir, "model_vit_base_b4s32.npz")
@@ -534,8 +534,8 @@ def test_bench_shape_engages_the_bench_kernels(agb, golden_dir):
     finally:
         nat.PROFILE = None
         engine.GRAPH_MAX_ROWS = old
-    for must in ("agb_gemm_bf16_fused", "agb_kept_first_order", "agb_masked_attention_bf16_scatter", "agb_gather_token_rows",
-                 "agb_attention_bf16_prefix", "agb_cls_attention"):
+    for must in ("agb_gemm_bf16_fused", "agb_gemm_bf16_hilo", "agb_kept_first_order", "agb_masked_attention_bf16_scatter",
+                 "agb_gather_token_rows_hilo", "agb_attention_bf16_prefix", "agb_cls_attention"):
         assert must in names, f"{must} did not run: {sorted(set(names))}"
     np.testing.assert_allclose(_np(v_s), g["v_s"], atol=2e-2)
     # graph replay (the default for <= 128 rows) gives the same numbers as the eager launches
