@@ -33,7 +33,7 @@ int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, 
                       float alpha, const float* bias, int act, const bf16* res_bf16, const float* res_f32, int ldr,
                       void* out, int ldo, int out_f32, const float* ln_stats, int ln_parts, const float* ln_colsum,
                       float ln_eps, bf16* out16, int ldo16, float* stats_out, cudaStream_t stream, bf16* hl_hi = nullptr,
-                      bf16* hl_lo = nullptr, int ld_hl = 0);
+                      bf16* hl_lo = nullptr, int ld_hl = 0, unsigned drop_thr = 0, unsigned drop_key = 0);
 int gather_token_rows_hilo(const float* src, const uint8_t* order, int rows, int T, int S, int H, bf16* hi, bf16* lo,
                            cudaStream_t st);
 int split_hilo(const float* x, long long n, bf16* hi, bf16* lo, cudaStream_t st);
@@ -212,6 +212,20 @@ int agb_gemm_bf16_hilo(const void* A, int lda, const void* B, int ldb, int M, in
                                         stats_out, ST(stream), static_cast<bf16*>(x_hi), static_cast<bf16*>(x_lo), ldx);
   if (rc == AGB_ERR_UNSUPPORTED)
     agb::set_last_error("agb_gemm_bf16_hilo: shape not covered (M=%d N=%d K=%d)", M, N, K);
+  return rc;
+}
+int agb_gemm_bf16_dropout_residual(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias,
+                                   const float* residual_f32, int ldr, float* out, int thr16, uint64_t seed, int tag, void* stream) {
+  AGB_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && out && residual_f32, "operands");
+  AGB_REQUIRE(thr16 > 0 && thr16 < 65536, "dropout threshold");
+  AGB_REQUIRE((N % 4) == 0 && (lda % 8) == 0 && (ldb % 8) == 0 && (ldr % 4) == 0, "alignment");
+  AGB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0, "alignment");
+  const unsigned key = agb::agb_drop_key(seed, (uint32_t)tag, 0x5bd1e995u);     // the stream of agb_dropout(seed, tag)
+  const int rc = agb::gemm_bf16_pair_ex(static_cast<const bf16*>(A), lda, 0, static_cast<const bf16*>(B), ldb, 0, M, N, K,
+                                        1.0f, bias, 0, nullptr, residual_f32, ldr, out, N, 1, nullptr, 0, nullptr, 0.f, nullptr,
+                                        0, nullptr, ST(stream), nullptr, nullptr, 0, (unsigned)thr16, key);
+  if (rc == AGB_ERR_UNSUPPORTED)
+    agb::set_last_error("agb_gemm_bf16_dropout_residual: shape not covered (M=%d N=%d K=%d)", M, N, K);
   return rc;
 }
 int agb_split_hilo(const float* x, long long n, void* hi, void* lo, void* stream) {

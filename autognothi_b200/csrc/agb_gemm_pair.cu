@@ -48,6 +48,10 @@ struct PairGemmParams {
   // split-K (wgrad: few output tiles, very long K): tile t = (split, m, n); split sp covers k-blocks
   // [sp * kb_per_split, ...) and stores its fp32 partial at output rows sp * M + m (reduced by splitk_reduce_kernel)
   int splits, kb_per_split;
+  // fp32 residual epilogue with nn.Dropout on the GEMM output (training): out = residual + keep * (alpha acc + bias) / (1 - p),
+  // keep regenerated from the counter hash of agb_dropout (same key, element index = row * N + col; contiguous output)
+  unsigned drop_thr, drop_key;
+  float drop_scale;
 };
 
 template <int CG, int STAGES, int NBUF, int ACT, int RES, int OUT_F32, int LNIN, int STATS>
@@ -355,6 +359,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 v.x = gelu_erf_tanhform(v.x); v.y = gelu_erf_tanhform(v.y);
                 v.z = gelu_erf_tanhform(v.z); v.w = gelu_erf_tanhform(v.w);
               }
+              if (RES == 2 && !STATS && p.drop_thr != 0u) {
+                const uint32_t pair0 = (static_cast<uint32_t>(row0 + lane) * static_cast<uint32_t>(p.N) +
+                                        static_cast<uint32_t>(col0 + 4 * j)) >> 1;
+                const uint32_t x0 = agb_drop_bits(p.drop_key, pair0), x1 = agb_drop_bits(p.drop_key, pair0 + 1u);
+                v.x = (x0 & 0xFFFFu) >= p.drop_thr ? v.x * p.drop_scale : 0.f;
+                v.y = (x0 >> 16) >= p.drop_thr ? v.y * p.drop_scale : 0.f;
+                v.z = (x1 & 0xFFFFu) >= p.drop_thr ? v.z * p.drop_scale : 0.f;
+                v.w = (x1 >> 16) >= p.drop_thr ? v.w * p.drop_scale : 0.f;
+              }
               if (RES) {
                 float4 rr;
                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -529,7 +542,7 @@ int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, 
                       float alpha, const float* bias, int act, const bf16* res_bf16, const float* res_f32, int ldr,
                       void* out, int ldo, int out_f32, const float* ln_stats, int ln_parts, const float* ln_colsum,
                       float ln_eps, bf16* out16, int ldo16, float* stats_out, cudaStream_t stream, bf16* hl_hi, bf16* hl_lo,
-                      int ld_hl) {
+                      int ld_hl, unsigned drop_thr, unsigned drop_key) {
   const bool lnin = ln_stats != nullptr, stats = stats_out != nullptr;
   const bool hl = hl_hi != nullptr;
   if (g_gemm_variant == 1) return AGB_ERR_UNSUPPORTED;
@@ -547,6 +560,9 @@ int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, 
     return AGB_ERR_UNSUPPORTED;
   if (lnin && (out_f32 || res_f32 || a_mn || ln_colsum == nullptr || ln_parts <= 0 || ln_parts > 8 || alpha != 1.0f ||
                (reinterpret_cast<uintptr_t>(ln_colsum) & 15) != 0))
+    return AGB_ERR_UNSUPPORTED;
+  if (drop_thr != 0u && (!res_f32 || !out_f32 || stats || lnin || hl || ldo != N || (N % 4) != 0 ||
+                         (long long)M * N >= (1ll << 32)))
     return AGB_ERR_UNSUPPORTED;
   if (stats && !hl && (!res_f32 || out16 == nullptr || (N % PG_BN) != 0 || (ldo16 % 8) != 0 ||
                        (reinterpret_cast<uintptr_t>(out16) & 15) != 0))
@@ -621,6 +637,7 @@ int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, 
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.alpha = alpha; p.a_mn = a_mn; p.b_mn = b_mn;
   p.splits = splits; p.kb_per_split = kb_per_split;
   p.ln_stats = ln_stats; p.ln_parts = ln_parts; p.ln_colsum = ln_colsum; p.ln_eps = ln_eps; p.stats_out = stats_out;
+  p.drop_thr = drop_thr; p.drop_key = drop_key; p.drop_scale = 65536.0f / (65536.0f - (float)drop_thr);
   const int res = hl ? 3 : (res_f32 ? 2 : 0);
   if (hl) {
     // ring slots are 8 KB here (both planes of a 32 x 64 chunk).  Short K (the HBM-bound out-projection): 3 stages + two
@@ -675,7 +692,7 @@ int gemm_bf16_pair(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int
                    float alpha, const float* bias, int act, const bf16* res_bf16, const float* res_f32, int ldr,
                    void* out, int ldo, int out_f32, cudaStream_t stream) {
   return gemm_bf16_pair_ex(A, lda, a_mn, B, ldb, b_mn, M, N, K, alpha, bias, act, res_bf16, res_f32, ldr, out, ldo,
-                           out_f32, nullptr, 0, nullptr, 0.f, nullptr, 0, nullptr, stream, nullptr, nullptr, 0);
+                           out_f32, nullptr, 0, nullptr, 0.f, nullptr, 0, nullptr, stream, nullptr, nullptr, 0, 0u, 0u);
 }
 
 }  // namespace agb

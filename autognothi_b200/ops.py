@@ -597,6 +597,25 @@ def dropout(y: Tensor, thr16: int, seed: int, tag: int, *, residual: Optional[Te
     return out
 
 
+def gemm_dropout_residual_supported(M: int, N: int) -> bool:
+    return N >= 192 and N % 4 == 0 and M * N < (1 << 32)
+
+
+def gemm_bf16_dropout_residual(a: Tensor, w: Tensor, bias: Optional[Tensor], residual: Tensor, thr16: int, seed: int, tag: int) -> Tensor:
+    """residual + dropout(a @ w.T + bias) in one tcgen05 GEMM (agb_gemm_bf16_dropout_residual); the keep mask is the stream of
+    dropout(seed, tag) over the (M, N) output, so `dropout` on the gradient is its adjoint."""
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and residual.shape == (M, N) and residual.dtype == torch.float32 and residual.stride(1) == 1
+    assert gemm_dropout_residual_supported(M, N) and 0 < thr16 < 65536
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    nat.NEXT_META = 2.0 * M * N * K
+    nat.call("agb_gemm_bf16_dropout_residual", nat.ptr(a), a.stride(0), nat.ptr(w), w.stride(0), M, N, K, nat.ptr(bias),
+             nat.ptr(residual), residual.stride(0), nat.ptr(out), thr16, seed & 0xFFFFFFFFFFFFFFFF, tag, nat.stream())
+    return out
+
+
 def masked_attention_dropout(qkv: Tensor, packed_mask: Tensor, T: int, heads: int, mode: int, thr16: int, seed: int) -> Tensor:
     """masked_attention with dropout on the probabilities (bf16: head dim 64 with T <= 256 on the tcgen05 kernels, or head
     dims 8/16/32; fp32: CUDA-core kernels)."""

@@ -28,6 +28,50 @@ from .engine import LayerWeights, _Policy, _f32, n_players_of
 Grads = Dict[str, Tensor]
 
 
+class _ZeroArena:
+    """fp32 zeros for the small accumulate-into gradients of one backward pass (bias column sums, LayerNorm gamma / beta): slices
+    of one zero-filled chunk, i.e. one memset instead of ~110 fill launches per ViT-Base step.  The slices are handed to autograd
+    as they are (contiguous views; the chunk lives as long as any of them)."""
+    CHUNK = 1 << 18
+
+    def __init__(self):
+        self.buf: Optional[Tensor] = None
+        self.off = 0
+
+    def take(self, shape, device) -> Tensor:
+        n = 1
+        for d in shape:
+            n *= int(d)
+        step = (n + 63) // 64 * 64          # 256-byte aligned slices
+        if step > self.CHUNK:
+            return torch.zeros(tuple(shape), dtype=torch.float32, device=device)
+        if self.buf is None or self.buf.device != device or self.off + step > self.buf.numel():
+            self.buf = torch.zeros((self.CHUNK,), dtype=torch.float32, device=device)
+            self.off = 0
+        out = self.buf[self.off:self.off + n].view(tuple(shape))
+        self.off += step
+        return out
+
+
+_ARENA: Optional[_ZeroArena] = None     # set for the duration of a backward pass (autograd Function.backward below)
+
+
+def _zeros(shape, device) -> Tensor:
+    if _ARENA is not None:
+        return _ARENA.take(shape, device)
+    return torch.zeros(tuple(shape), dtype=torch.float32, device=device)
+
+
+class _arena_scope:
+    def __enter__(self):
+        global _ARENA
+        self.prev, _ARENA = _ARENA, _ZeroArena()
+
+    def __exit__(self, *exc):
+        global _ARENA
+        _ARENA = self.prev
+
+
 class _Drop:
     """Dropout state of one training forward (reference: nn.Dropout modules active in train() mode, hidden_dropout_prob on
     embeddings / attention-output / MLP-output, attention_probs_dropout_prob on the attention probabilities).  Masks come
@@ -54,11 +98,18 @@ class _Drop:
 _NO_DROP = None
 
 
+# bf16 training: residual + dropout(dense) inside the GEMM's epilogue (agb_gemm_bf16_dropout_residual) instead of a bf16
+# GEMM output followed by agb_dropout; same mask stream, the dense output is no longer rounded to bf16 in between.
+FUSE_DROPOUT = True
+
+
 def _linear_drop(pol: _Policy, drop, a: Tensor, w: Tensor, b: Tensor, residual: Tensor) -> Tuple[Tensor, int]:
     """residual + dropout(a @ w^T + b) -> (fp32, site tag | 0): with p = 0 the residual rides in the GEMM epilogue."""
     if drop is None or not drop.h:
         return pol.linear(a, w, b, residual=residual, out_f32=True), 0
     tag = drop.tag()
+    if pol.bf16 and FUSE_DROPOUT and ops.gemm_dropout_residual_supported(a.shape[0], w.shape[0]):
+        return ops.gemm_bf16_dropout_residual(a, w, b, residual, drop.h, drop.seed, tag), tag
     return ops.dropout(pol.linear(a, w, b), drop.h, drop.seed, tag, residual=residual, out_dtype=torch.float32), tag
 
 
@@ -97,7 +148,7 @@ def _dgrad(pol: _Policy, dy: Tensor, w: Tensor, *, out_f32: bool, residual: Opti
 
 
 def _bias_grad(dy: Tensor) -> Tensor:
-    g = torch.zeros((dy.shape[1],), dtype=torch.float32, device=dy.device)
+    g = _zeros((dy.shape[1],), dy.device)
     ops.colsum_into(dy, g)
     return g
 
@@ -116,8 +167,9 @@ def _qkv_bwd(pol: _Policy, grads: Grads, prefix: str, dqkv: Tensor, x: Tensor, H
 
 
 def _ln_bwd(grads: Grads, name: str, x: Tensor, dy: Tensor, gamma: Tensor, eps: float, dres: Optional[Tensor]) -> Tensor:
-    dg = torch.zeros_like(gamma)
-    db = torch.zeros_like(gamma)
+    assert gamma.dtype == torch.float32
+    dg = _zeros(gamma.shape, gamma.device)
+    db = _zeros(gamma.shape, gamma.device)
     dx = ops.layernorm_bwd(x, dy, gamma, eps, dres, dg, db)
     grads[name + ".weight"], grads[name + ".bias"] = dg, db
     return dx
@@ -402,7 +454,7 @@ class _ExplainerTrainFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dphi, dx_cls):
-        with torch.no_grad():
+        with torch.no_grad(), _arena_scope():
             if dphi is None:      # only the class output was used downstream
                 dphi = torch.zeros((ctx.tape.B, ctx.tape.cfg.num_labels, ctx.tape.T - 1), dtype=torch.float32,
                                    device=ctx.tape.hb.device)
@@ -524,7 +576,7 @@ class _BackboneTrainFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dx_cls):
-        with torch.no_grad():
+        with torch.no_grad(), _arena_scope():
             grads = backbone_backward_train(ctx.tape, dx_cls.contiguous().float())
         ctx.tape = None
         out = []
@@ -732,7 +784,7 @@ class _LttTrainFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, _dcls):
-        with torch.no_grad():
+        with torch.no_grad(), _arena_scope():
             grads = ltt_backward_train(ctx.tape, dout.contiguous().float())
         ctx.tape = None
         out = []

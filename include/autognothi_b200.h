@@ -70,6 +70,13 @@ int agb_gemm_stats_parts(int N);
  * the HBM-bound attention output projection.  N % 256 == 0, ldx % 8 == 0; AGB_ERR_UNSUPPORTED otherwise. */
 int agb_gemm_bf16_hilo(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias, void* x_hi,
                        void* x_lo, int ldx, float* stats_out, void* stream);
+/* Training: out = residual + Dropout(A B^T + bias) in ONE kernel (reference models/vanilla_vit.py:501-503, 512-516: dense ->
+ * nn.Dropout -> residual add).  The keep mask is the counter-hash stream of agb_dropout(seed, tag) over the element index of the
+ * contiguous (M, N) output, so the adjoint (agb_dropout on the gradient) regenerates it.  0 < thr16 < 65536; M * N < 2^32;
+ * AGB_ERR_UNSUPPORTED when the tcgen05 pair kernel does not cover the shape (callers then run agb_gemm_bf16 + agb_dropout). */
+int agb_gemm_bf16_dropout_residual(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias,
+                                   const float* residual_f32, int ldr, float* out, int thr16, uint64_t seed, int tag,
+                                   void* stream);
 /* fp32 -> hi/lo planes (n % 8 == 0). */
 int agb_split_hilo(const float* x, long long n, void* hi, void* lo, void* stream);
 /* bf16 copy + one (sum, sum of squares) pair per row of an fp32 matrix: the entry of the chain above. */

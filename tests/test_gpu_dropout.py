@@ -61,6 +61,54 @@ def _torch_attention(qkv, dense_tok, keep, T, heads, mode, scale_keep):
     return (pr @ v).permute(0, 2, 1, 3).reshape(rows * T, H)
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 768, 768), (12608, 768, 3072), (25216 + 40, 768, 768)])
+def test_gemm_with_fused_dropout_residual(agb, M, N, K):
+    """agb_gemm_bf16_dropout_residual == agb_gemm_bf16 followed by agb_dropout with the same (seed, tag): identical keep mask
+    (the adjoint regenerates it through agb_dropout), values equal up to the bf16 rounding the unfused path applies to the
+    dense output in between."""
+    torch.manual_seed(11)
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    w = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
+    b = torch.randn(N, device=DEV) * 0.1
+    res = torch.randn(M, N, device=DEV)
+    thr, seed, tag = agb.dropout_thr(0.1), 0x1234567890ABCDEF, 5
+    fused = agb.gemm_bf16_dropout_residual(a, w, b, res, thr, seed, tag)
+    y = agb.gemm_bf16(a, w, b)
+    unfused = agb.dropout(y, thr, seed, tag, residual=res, out_dtype=torch.float32)
+    keep = agb.dropout(torch.ones(M, N, device=DEV), thr, seed, tag) != 0
+    assert abs(float(keep.float().mean()) - 0.9) < 5e-3
+    assert torch.equal(fused[~keep], res[~keep])                       # dropped elements: the residual passes through untouched
+    scale = 65536.0 / (65536.0 - thr)
+    ref = res + keep * (a.float() @ w.float().t() + b) * scale
+    torch.testing.assert_close(fused, ref, rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(fused, unfused, rtol=1e-2, atol=1e-2)   # y rounded to bf16 on the unfused side
+
+
+def test_gelu_bf16_fast_forms_vs_torch(agb):
+    """bf16 GELU forward / adjoint kernels (one MUFU each: the tanh-form refit of erf-GELU and ITS derivative) against torch's
+    exact erf GELU and autograd; fp32 I/O keeps the exact erf / exp forms."""
+    torch.manual_seed(12)
+    z = (torch.randn(4096, 768, device=DEV) * 2.5)
+    dy = torch.randn(4096, 768, device=DEV)
+    zr = z.clone().requires_grad_(True)
+    f_ref = torch.nn.functional.gelu(zr)
+    f_ref.backward(dy)
+    f32 = agb.gelu_fwd(z)
+    d32 = agb.gelu_bwd(dy, z)
+    torch.testing.assert_close(f32, f_ref.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(d32, zr.grad, rtol=1e-4, atol=1e-5)
+    z16, dy16 = z.bfloat16(), dy.bfloat16()
+    z16r = z16.float().requires_grad_(True)
+    f16_ref = torch.nn.functional.gelu(z16r)
+    f16_ref.backward(dy16.float())
+    f16 = agb.gelu_fwd(z16)
+    d16 = agb.gelu_bwd(dy16, z16)
+    assert f16.dtype == torch.bfloat16 and d16.dtype == torch.bfloat16
+    # approximant within 3e-4 (forward) / 9e-4 (derivative) of the exact forms, then one bf16 rounding
+    torch.testing.assert_close(f16.float(), f16_ref.detach(), rtol=8e-3, atol=1e-3)
+    torch.testing.assert_close(d16.float(), z16r.grad, rtol=8e-3, atol=4e-3)
+
+
 @pytest.mark.parametrize("T,heads,d,mode", [(197, 2, 64, 0), (128, 2, 64, 1), (33, 1, 64, 1), (256, 1, 64, 0), (197, 3, 16, 0),
                                             (128, 4, 8, 1), (40, 2, 32, 0)])
 def test_attention_dropout_forward_and_adjoint_vs_torch(agb, T, heads, d, mode):
