@@ -33,7 +33,8 @@ int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, 
                       float alpha, const float* bias, int act, const bf16* res_bf16, const float* res_f32, int ldr,
                       void* out, int ldo, int out_f32, const float* ln_stats, int ln_parts, const float* ln_colsum,
                       float ln_eps, bf16* out16, int ldo16, float* stats_out, cudaStream_t stream, bf16* hl_hi = nullptr,
-                      bf16* hl_lo = nullptr, int ld_hl = 0, unsigned drop_thr = 0, unsigned drop_key = 0);
+                      bf16* hl_lo = nullptr, int ld_hl = 0, unsigned drop_thr = 0, unsigned drop_key = 0, bf16* z_out = nullptr,
+                      int ldz_out = 0, const bf16* z_in = nullptr, int ldz_in = 0);
 int gather_token_rows_hilo(const float* src, const uint8_t* order, int rows, int T, int S, int H, bf16* hi, bf16* lo,
                            cudaStream_t st);
 int split_hilo(const float* x, long long n, bf16* hi, bf16* lo, cudaStream_t st);
@@ -226,6 +227,31 @@ int agb_gemm_bf16_dropout_residual(const void* A, int lda, const void* B, int ld
                                         0, nullptr, ST(stream), nullptr, nullptr, 0, (unsigned)thr16, key);
   if (rc == AGB_ERR_UNSUPPORTED)
     agb::set_last_error("agb_gemm_bf16_dropout_residual: shape not covered (M=%d N=%d K=%d)", M, N, K);
+  return rc;
+}
+int agb_gemm_bf16_gelu_dual(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias, void* z_out,
+                            void* gelu_out, int ldo, void* stream) {
+  AGB_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && z_out && gelu_out, "operands");
+  AGB_REQUIRE((N % 4) == 0 && (lda % 8) == 0 && (ldb % 8) == 0 && (ldo % 8) == 0, "alignment");
+  AGB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0, "alignment");
+  const int rc = agb::gemm_bf16_pair_ex(static_cast<const bf16*>(A), lda, 0, static_cast<const bf16*>(B), ldb, 0, M, N, K,
+                                        1.0f, bias, 2, nullptr, nullptr, 0, gelu_out, ldo, 0, nullptr, 0, nullptr, 0.f, nullptr, 0,
+                                        nullptr, ST(stream), nullptr, nullptr, 0, 0u, 0u, static_cast<bf16*>(z_out), ldo);
+  if (rc == AGB_ERR_UNSUPPORTED)
+    agb::set_last_error("agb_gemm_bf16_gelu_dual: shape not covered (M=%d N=%d K=%d)", M, N, K);
+  return rc;
+}
+int agb_gemm_bf16_gelu_bwd(const void* dY, int ldy, const void* W, int ldw, int M, int N, int K, const void* z, int ldz,
+                           void* dz, int ldo, void* stream) {
+  AGB_REQUIRE(M > 0 && N > 0 && K > 0 && dY && W && z && dz, "operands");
+  AGB_REQUIRE((N % 4) == 0 && (ldy % 8) == 0 && (ldw % 8) == 0 && (ldo % 8) == 0 && (ldz % 8) == 0, "alignment");
+  AGB_REQUIRE((reinterpret_cast<uintptr_t>(dY) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, "alignment");
+  // W is the forward weight [K, N] (out_features K x in_features N): the MN-major B operand of dY W
+  const int rc = agb::gemm_bf16_pair_ex(static_cast<const bf16*>(dY), ldy, 0, static_cast<const bf16*>(W), ldw, 1, M, N, K,
+                                        1.0f, nullptr, 0, nullptr, nullptr, 0, dz, ldo, 0, nullptr, 0, nullptr, 0.f, nullptr, 0,
+                                        nullptr, ST(stream), nullptr, nullptr, 0, 0u, 0u, nullptr, 0, static_cast<const bf16*>(z), ldz);
+  if (rc == AGB_ERR_UNSUPPORTED)
+    agb::set_last_error("agb_gemm_bf16_gelu_bwd: shape not covered (M=%d N=%d K=%d)", M, N, K);
   return rc;
 }
 int agb_split_hilo(const float* x, long long n, void* hi, void* lo, void* stream) {

@@ -43,17 +43,6 @@ __device__ __forceinline__ float gelu_grad(float x) {
   const float pdf = 0.3989422804014327f * expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
-// bf16 activations: derivative of the SAME approximant the tcgen05 epilogues and gelu_fwd use for bf16 data
-// (gelu_erf_tanhform: 0.5 x (1 + tanh(x (c0 + c1 x^2))), one MUFU), so forward and adjoint stay consistent:
-//   g'(x) = 0.5 (1 + t) + 0.5 x (1 - t^2) (c0 + 3 c1 x^2);  |g' - exact| <= 9e-4 (bf16 resolves 4e-3 near 1).
-// The erf / exp forms above made both kernels compute-bound (85 / 105 us per 12608 x 3072 launch against 26 / 39 us of HBM time).
-__device__ __forceinline__ float gelu_grad_tanhform(float x) {
-  const float x2 = x * x;
-  const float t = tanh_approx(x * fmaf(0.03470090309328562f, x2, 0.8001570568972525f));
-  const float hx = 0.5f * x;
-  const float du = fmaf(3.0f * 0.03470090309328562f, x2, 0.8001570568972525f);
-  return fmaf(hx * fmaf(-t, t, 1.0f), du, fmaf(0.5f, t, 0.5f));
-}
 template <typename T> __device__ __forceinline__ float gelu_fwd_of(float x) { return gelu_erf_exact(x); }
 template <> __device__ __forceinline__ float gelu_fwd_of<bf16>(float x) { return gelu_erf_tanhform(x); }
 template <typename T> __device__ __forceinline__ float gelu_grad_of(float x) { return gelu_grad(x); }

@@ -64,12 +64,19 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // stores both planes IN PLACE: the hi plane is at the same time the bf16 copy the next (LayerNorm-folded) GEMM reads as
   // its A operand, so the separate copy of the fp32 variant (2 of its 12 bytes per element) is never written.
   constexpr bool HL = RES == 3;
-  static_assert(RES == 0 || HL || OUT_F32 == 1, "fp32 residual pairs with fp32 output");
+  // Training epilogues (bf16 output).  ACT == 2: GELU with the pre-activation as a second output (tmOut2): z for the adjoint,
+  // GELU(z) for the next GEMM, from one pass over the accumulator.  RES == 4: the dgrad GEMM feeding a GELU adjoint,
+  // out = acc * gelu'(z) with the z tile TMA-loaded like a residual (tmRes) and overwritten in place in its staging box.
+  constexpr bool DUAL = ACT == 2;
+  constexpr bool GBWD = RES == 4;
+  static_assert(!DUAL || (OUT_F32 == 0 && RES == 0 && STATS == 0), "GELU + pre-activation: bf16 outputs, no residual");
+  static_assert(!GBWD || (OUT_F32 == 0 && ACT == 0 && LNIN == 0 && STATS == 0), "GELU adjoint epilogue: bf16 output");
+  static_assert(RES == 0 || HL || GBWD || OUT_F32 == 1, "fp32 residual pairs with fp32 output");
   static_assert(!HL || (OUT_F32 == 0 && STATS == 1 && ACT == 0 && LNIN == 0), "hi/lo residual: bf16 planes + statistics");
   static_assert(!STATS || (RES == 2 && OUT_F32 == 1) || HL, "statistics ride the residual epilogues");
   static_assert(!LNIN || (RES == 0 && OUT_F32 == 0), "folded LayerNorm feeds the bf16-output epilogues");
-  constexpr int SLOT_BYTES = HL ? 2 * PG_BOX_BYTES : PG_BOX_BYTES;     // one ring slot (hi/lo: the two planes back to back)
-  constexpr int NBOX = HL ? 2 * NBUF : NBUF + (STATS ? 1 : 0);         // staging boxes per epilogue warp
+  constexpr int SLOT_BYTES = (HL || DUAL) ? 2 * PG_BOX_BYTES : PG_BOX_BYTES;   // one ring slot (two boxes back to back: hi / lo planes, GELU(z) / z)
+  constexpr int NBOX = (HL || DUAL) ? 2 * NBUF : NBUF + (STATS ? 1 : 0);       // staging boxes per epilogue warp
   constexpr int B_ROWS = PG_BN / CG;                 // B rows staged by this CTA
   constexpr int A_BYTES = PG_BM * PG_BK * 2;
   constexpr int B_BYTES = B_ROWS * PG_BK * 2;
@@ -109,7 +116,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut);
     if (RES) tma_prefetch_desc(&tmRes);
-    if (STATS) tma_prefetch_desc(&tmOut2);
+    if (STATS || DUAL) tma_prefetch_desc(&tmOut2);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
@@ -243,7 +250,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (!chunk_coords(g, row0, col0)) return;
       const int b = g % NBUF;
       const uint32_t bar = smem_u32(&my_res[b]);
-      mbar_arrive_expect_tx(bar, SLOT_BYTES);
+      mbar_arrive_expect_tx(bar, HL ? 2 * PG_BOX_BYTES : PG_BOX_BYTES);
       tma_load_2d(stg_u32 + b * SLOT_BYTES, &tmRes, bar, col0, row0);
       if (HL) tma_load_2d(stg_u32 + b * SLOT_BYTES + PG_BOX_BYTES, &tmOut2, bar, col0, row0);   // lo plane
     };
@@ -415,7 +422,26 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               v[6] = fmaf(__uint_as_float(r[8 * j + 6]), p.alpha, b1.z);
               v[7] = fmaf(__uint_as_float(r[8 * j + 7]), p.alpha, b1.w);
               }
-              if (ACT == 1) {
+              if constexpr (GBWD) {
+                uint32_t zw[4];
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(zw[0]), "=r"(zw[1]), "=r"(zw[2]), "=r"(zw[3]) : "r"(addr) : "memory");
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  v[2 * i + 0] *= gelu_grad_tanhform(bf16_lo(zw[i]));
+                  v[2 * i + 1] *= gelu_grad_tanhform(bf16_hi(zw[i]));
+                }
+              }
+              if constexpr (DUAL) {
+                // the adjoint differentiates at the ROUNDED pre-activation, as the unfused path (bf16 z -> gelu kernel) does
+                const uint32_t z0 = pack_bf16x2(v[0], v[1]), z1 = pack_bf16x2(v[2], v[3]), z2 = pack_bf16x2(v[4], v[5]),
+                               z3 = pack_bf16x2(v[6], v[7]);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + PG_BOX_BYTES), "r"(z0), "r"(z1), "r"(z2), "r"(z3)
+                             : "memory");
+                v[0] = bf16_lo(z0); v[1] = bf16_hi(z0); v[2] = bf16_lo(z1); v[3] = bf16_hi(z1);
+                v[4] = bf16_lo(z2); v[5] = bf16_hi(z2); v[6] = bf16_lo(z3); v[7] = bf16_hi(z3);
+              }
+              if (ACT != 0) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = gelu_erf_tanhform(v[i]);
               }
@@ -431,7 +457,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&tmOut, buf, col0, out_row0);
-            if (HL) tma_store_2d(&tmOut2, buf + PG_BOX_BYTES, col0, row0);                 // lo plane
+            if (HL || DUAL) tma_store_2d(&tmOut2, buf + PG_BOX_BYTES, col0, row0);         // lo plane / pre-activation
             else if (STATS && (c & 1)) tma_store_2d(&tmOut2, buf16, col0 - CHUNK_COLS, row0);   // 64 bf16 columns
             bulk_commit();
             if (RES) bulk_wait_read<0>();   // boxes handed to the store engine: free for the next residual / copy
@@ -463,7 +489,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <int CG, int STAGES, int NBUF, int STATS, int HL = 0>
 constexpr int pair_smem_bytes() {
-  return STAGES * (PG_BM * PG_BK * 2 + (PG_BN / CG) * PG_BK * 2) + PG_EPI_WARPS * (HL ? 2 * NBUF : NBUF + STATS) * PG_BOX_BYTES +
+  return STAGES * (PG_BM * PG_BK * 2 + (PG_BN / CG) * PG_BK * 2) + PG_EPI_WARPS * (HL ? 2 * NBUF : NBUF + STATS) * PG_BOX_BYTES +   // HL: any two-box slot
          (2 * STAGES + 4 + PG_EPI_WARPS * NBUF) * 8 + 16 + 1024;
 }
 
@@ -471,7 +497,7 @@ template <int CG, int STAGES, int NBUF, int ACT, int RES, int OUT_F32, int LNIN,
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                        const CUtensorMap& tmRes, const CUtensorMap& tmOut2, const PairGemmParams& p,
                        cudaStream_t stream) {
-  constexpr int SMEM = pair_smem_bytes<CG, STAGES, NBUF, STATS, RES == 3>();
+  constexpr int SMEM = pair_smem_bytes<CG, STAGES, NBUF, STATS, (RES == 3 || ACT == 2)>();
   static_assert(SMEM <= 232448, "shared memory budget");
   auto kern = gemm_pair_kernel<CG, STAGES, NBUF, ACT, RES, OUT_F32, LNIN, STATS>;
   static int max_pairs = 0;   // co-resident CTAs (CG = 1) or clusters (CG = 2)
@@ -542,7 +568,7 @@ int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, 
                       float alpha, const float* bias, int act, const bf16* res_bf16, const float* res_f32, int ldr,
                       void* out, int ldo, int out_f32, const float* ln_stats, int ln_parts, const float* ln_colsum,
                       float ln_eps, bf16* out16, int ldo16, float* stats_out, cudaStream_t stream, bf16* hl_hi, bf16* hl_lo,
-                      int ld_hl, unsigned drop_thr, unsigned drop_key) {
+                      int ld_hl, unsigned drop_thr, unsigned drop_key, bf16* z_out, int ldz_out, const bf16* z_in, int ldz_in) {
   const bool lnin = ln_stats != nullptr, stats = stats_out != nullptr;
   const bool hl = hl_hi != nullptr;
   if (g_gemm_variant == 1) return AGB_ERR_UNSUPPORTED;
@@ -561,6 +587,15 @@ int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, 
   if (lnin && (out_f32 || res_f32 || a_mn || ln_colsum == nullptr || ln_parts <= 0 || ln_parts > 8 || alpha != 1.0f ||
                (reinterpret_cast<uintptr_t>(ln_colsum) & 15) != 0))
     return AGB_ERR_UNSUPPORTED;
+  // training epilogues: act == 2 (GELU + pre-activation z_out), z_in (out = acc * gelu'(z_in)); bf16 outputs, nothing else fused
+  const bool dual = act == 2, gbwd = z_in != nullptr;
+  if (dual && (z_out == nullptr || out_f32 || res_f32 || lnin || stats || hl || (ldz_out % 8) != 0 ||
+               (reinterpret_cast<uintptr_t>(z_out) & 15) != 0))
+    return AGB_ERR_UNSUPPORTED;
+  if (gbwd && (act != 0 || out_f32 || res_f32 || lnin || stats || hl || bias != nullptr || (ldz_in % 8) != 0 ||
+               (reinterpret_cast<uintptr_t>(z_in) & 15) != 0))
+    return AGB_ERR_UNSUPPORTED;
+  if (act != 0 && act != 1 && !dual) return AGB_ERR_UNSUPPORTED;
   if (drop_thr != 0u && (!res_f32 || !out_f32 || stats || lnin || hl || ldo != N || (N % 4) != 0 ||
                          (long long)M * N >= (1ll << 32)))
     return AGB_ERR_UNSUPPORTED;
@@ -615,10 +650,12 @@ int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, 
   if (rc != AGB_OK) return rc;
   rc = encode_tmap_2d(&tmOut, out, oes, N, (uint64_t)M * splits, (uint64_t)ldo * oes, out_f32 ? 32 : 64, 32);
   if (rc != AGB_OK) return rc;
-  if (res_f32) rc = encode_tmap_2d(&tmRes, res_f32, 4, N, M, (uint64_t)ldr * 4, 32, 32);
-  else         tmRes = tmOut;                 // hi/lo: the hi plane is residual and output
+  if (res_f32)   rc = encode_tmap_2d(&tmRes, res_f32, 4, N, M, (uint64_t)ldr * 4, 32, 32);
+  else if (gbwd) rc = encode_tmap_2d(&tmRes, z_in, 2, N, M, (uint64_t)ldz_in * 2, 64, 32);
+  else           tmRes = tmOut;               // hi/lo: the hi plane is residual and output
   if (rc != AGB_OK) return rc;
   if (hl)         rc = encode_tmap_2d(&tmOut2, hl_lo, 2, N, M, (uint64_t)ld_hl * 2, 64, 32);
+  else if (dual)  rc = encode_tmap_2d(&tmOut2, z_out, 2, N, M, (uint64_t)ldz_out * 2, 64, 32);
   else if (stats) rc = encode_tmap_2d(&tmOut2, out16, 2, N, M, (uint64_t)ldo16 * 2, 64, 32);
   else            tmOut2 = tmOut;
   if (rc != AGB_OK) return rc;
@@ -639,6 +676,17 @@ int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, 
   p.ln_stats = ln_stats; p.ln_parts = ln_parts; p.ln_colsum = ln_colsum; p.ln_eps = ln_eps; p.stats_out = stats_out;
   p.drop_thr = drop_thr; p.drop_key = drop_key; p.drop_scale = 65536.0f / (65536.0f - (float)drop_thr);
   const int res = hl ? 3 : (res_f32 ? 2 : 0);
+  if (dual) {   // two-box slots: 5 stages (160 KB) + one slot per warp (64 KB)
+    if (cg == 2) return launch_pair<2, 5, 1, 2, 0, 0, 0, 0>(tmA, tmB, tmOut, tmRes, tmOut2, p, stream);
+    return launch_pair<1, 3, 1, 2, 0, 0, 0, 0>(tmA, tmB, tmOut, tmRes, tmOut2, p, stream);
+  }
+  if (gbwd) {
+    if (cg == 2) {
+      if (K < 2048) return launch_pair<2, 4, 2, 0, 4, 0, 0, 0>(tmA, tmB, tmOut, tmRes, tmOut2, p, stream);
+      return launch_pair<2, 5, 2, 0, 4, 0, 0, 0>(tmA, tmB, tmOut, tmRes, tmOut2, p, stream);
+    }
+    return launch_pair<1, 3, 2, 0, 4, 0, 0, 0>(tmA, tmB, tmOut, tmRes, tmOut2, p, stream);
+  }
   if (hl) {
     // ring slots are 8 KB here (both planes of a 32 x 64 chunk).  Short K (the HBM-bound out-projection): 3 stages + two
     // slots per warp (342-345 us in-step at the bench shape), or (AGB_GEMM_HILO_CFG=1) 4 stages + one slot (350-368 us);
@@ -692,7 +740,8 @@ int gemm_bf16_pair(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int
                    float alpha, const float* bias, int act, const bf16* res_bf16, const float* res_f32, int ldr,
                    void* out, int ldo, int out_f32, cudaStream_t stream) {
   return gemm_bf16_pair_ex(A, lda, a_mn, B, ldb, b_mn, M, N, K, alpha, bias, act, res_bf16, res_f32, ldr, out, ldo,
-                           out_f32, nullptr, 0, nullptr, 0.f, nullptr, 0, nullptr, stream, nullptr, nullptr, 0, 0u, 0u);
+                           out_f32, nullptr, 0, nullptr, 0.f, nullptr, 0, nullptr, stream, nullptr, nullptr, 0, 0u, 0u, nullptr, 0,
+                           nullptr, 0);
 }
 
 }  // namespace agb

@@ -597,6 +597,35 @@ def dropout(y: Tensor, thr16: int, seed: int, tag: int, *, residual: Optional[Te
     return out
 
 
+def gemm_bf16_gelu_dual(a: Tensor, w: Tensor, bias: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    """-> (z = a @ w.T + bias, GELU(z)), both bf16, from one GEMM (agb_gemm_bf16_gelu_dual; N >= 192)."""
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and N >= 192 and N % 8 == 0
+    z = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    f = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    nat.NEXT_META = 2.0 * M * N * K
+    nat.call("agb_gemm_bf16_gelu_dual", nat.ptr(a), a.stride(0), nat.ptr(w), w.stride(0), M, N, K, nat.ptr(bias), nat.ptr(z),
+             nat.ptr(f), N, nat.stream())
+    return z, f
+
+
+def gemm_bf16_gelu_bwd(dy: Tensor, w: Tensor, z: Tensor) -> Tensor:
+    """dz = (dy @ w) * GELU'(z): dy (M, K), w (K, N) the forward weight of the layer AFTER the GELU, z (M, N) the stored
+    pre-activation (agb_gemm_bf16_gelu_bwd; N >= 192)."""
+    assert dy.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and z.dtype == torch.bfloat16
+    assert dy.stride(1) == 1 and w.stride(1) == 1 and z.stride(1) == 1
+    M, K = dy.shape
+    N = w.shape[1]
+    assert w.shape[0] == K and z.shape == (M, N) and N >= 192 and N % 8 == 0
+    dz = torch.empty((M, N), dtype=torch.bfloat16, device=dy.device)
+    nat.NEXT_META = 2.0 * M * N * K
+    nat.call("agb_gemm_bf16_gelu_bwd", nat.ptr(dy), dy.stride(0), nat.ptr(w), w.stride(0), M, N, K, nat.ptr(z), z.stride(0),
+             nat.ptr(dz), N, nat.stream())
+    return dz
+
+
 def gemm_dropout_residual_supported(M: int, N: int) -> bool:
     return N >= 192 and N % 4 == 0 and M * N < (1 << 32)
 

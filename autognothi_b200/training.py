@@ -17,6 +17,7 @@ itself is checked against a torch re-statement that uses the exported masks (tes
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -100,7 +101,7 @@ _NO_DROP = None
 
 # bf16 training: residual + dropout(dense) inside the GEMM's epilogue (agb_gemm_bf16_dropout_residual) instead of a bf16
 # GEMM output followed by agb_dropout; same mask stream, the dense output is no longer rounded to bf16 in between.
-FUSE_DROPOUT = True
+FUSE_DROPOUT = os.environ.get("AGB_FUSE_DROPOUT", "1") != "0"
 
 
 def _linear_drop(pol: _Policy, drop, a: Tensor, w: Tensor, b: Tensor, residual: Tensor) -> Tuple[Tensor, int]:
@@ -147,6 +148,27 @@ def _dgrad(pol: _Policy, dy: Tensor, w: Tensor, *, out_f32: bool, residual: Opti
     return ops.gemm_f32(dy, w, w_mn=True, residual=residual)
 
 
+# bf16 training: the GELU forward rides in the epilogue of the GEMM in front of it (two outputs: pre-activation for the adjoint,
+# activation for the next GEMM) and the GELU adjoint in the epilogue of the dgrad GEMM behind it, instead of separate
+# elementwise kernels (agb_gemm_bf16_gelu_dual / agb_gemm_bf16_gelu_bwd).  Wide layers only (N >= 192: the tcgen05 pair kernel).
+FUSE_GELU = os.environ.get("AGB_FUSE_GELU", "1") != "0"            # environment switches: A/B runs of bench.py
+
+
+def _linear_gelu(pol: _Policy, a: Tensor, w: Tensor, b: Tensor) -> Tuple[Tensor, Tensor]:
+    """-> (z = a @ w^T + b, GELU(z))"""
+    if pol.bf16 and FUSE_GELU and w.shape[0] >= 192 and w.shape[0] % 8 == 0:
+        return ops.gemm_bf16_gelu_dual(a, w, b)
+    z = pol.linear(a, w, b)
+    return z, ops.gelu_fwd(z)
+
+
+def _dgrad_gelu(pol: _Policy, dy: Tensor, w: Tensor, z: Tensor) -> Tensor:
+    """dz = (dy @ W) * GELU'(z)   (W [N_out, K_in]: the layer behind the GELU; z its input's pre-activation)"""
+    if pol.bf16 and FUSE_GELU and w.shape[1] >= 192 and w.shape[1] % 8 == 0:
+        return ops.gemm_bf16_gelu_bwd(dy, w, z)
+    return ops.gelu_bwd(_dgrad(pol, dy, w, out_f32=False), z)
+
+
 def _bias_grad(dy: Tensor) -> Tensor:
     g = _zeros((dy.shape[1],), dy.device)
     ops.colsum_into(dy, g)
@@ -184,8 +206,7 @@ def vit_layer_fwd(pol, lw: LayerWeights, x: Tensor, masks: Tensor, T: int, heads
     ctx, ta = _attention_fwd(drop, qkv, masks, T, heads, ops.MASK_MUL0)
     x_mid, t1 = _linear_drop(pol, drop, ctx, lw.wo, lw.bo, x)
     h2 = pol.ln(x_mid, lw.ln2[0], lw.ln2[1], eps)[0]
-    z = pol.linear(h2, lw.w1, lw.b1)
-    f = ops.gelu_fwd(z)
+    z, f = _linear_gelu(pol, h2, lw.w1, lw.b1)
     x_out, t2 = _linear_drop(pol, drop, f, lw.w2, lw.b2, x_mid)
     return x_out, dict(x_in=x, h1=h1, qkv=qkv, ctx=ctx, x_mid=x_mid, h2=h2, z=z, f=f, drop=drop, tags=(ta, t1, t2))
 
@@ -196,8 +217,7 @@ def vit_layer_bwd(pol, lw: LayerWeights, prefix: str, t: dict, dx_out: Tensor, m
     drop, (ta, t1, t2) = t["drop"], t["tags"]
     g = _act_drop(pol, drop, dx_out, t2)
     _linear_bwd(pol, grads, prefix + ".output.dense", g, t["f"])
-    df = _dgrad(pol, g, lw.w2, out_f32=False)
-    dz = ops.gelu_bwd(df, t["z"])
+    dz = _dgrad_gelu(pol, g, lw.w2, t["z"])
     _linear_bwd(pol, grads, prefix + ".intermediate.dense", dz, t["h2"])
     dh2 = _dgrad(pol, dz, lw.w1, out_f32=True)
     dx_mid = _ln_bwd(grads, prefix + ".layernorm_after", t["x_mid"], dh2, lw.ln2[0], eps, dx_out)
@@ -225,8 +245,7 @@ def bert_layer_fwd(pol, lw: LayerWeights, x: Tensor, xa: Tensor, masks: Tensor, 
         aa, a = pol.ln(a_pre, lw.ln1[0], lw.ln1[1], eps, want_f32=True)
     else:
         a, aa = a_pre, pol.act(a_pre)
-    z = pol.linear(aa, lw.w1, lw.b1)
-    f = ops.gelu_fwd(z)
+    z, f = _linear_gelu(pol, aa, lw.w1, lw.b1)
     y_pre, t2 = _linear_drop(pol, drop, f, lw.w2, lw.b2, a)
     ya, y = pol.ln(y_pre, lw.ln2[0], lw.ln2[1], eps, want_f32=True)
     return y, ya, dict(xa=xa, qkv=qkv, ctx=ctx, a_pre=a_pre, aa=aa, z=z, f=f, y_pre=y_pre, drop=drop, tags=(ta, t1, t2))
@@ -239,8 +258,7 @@ def bert_layer_bwd(pol, lw: LayerWeights, prefix: str, t: dict, dy: Tensor, mask
     d_ypre = _ln_bwd(grads, prefix + ".output.LayerNorm", t["y_pre"], dy, lw.ln2[0], eps, None)
     g = _act_drop(pol, drop, d_ypre, t2)
     _linear_bwd(pol, grads, prefix + ".output.dense", g, t["f"])
-    df = _dgrad(pol, g, lw.w2, out_f32=False)
-    dz = ops.gelu_bwd(df, t["z"])
+    dz = _dgrad_gelu(pol, g, lw.w2, t["z"])
     _linear_bwd(pol, grads, prefix + ".intermediate.dense", dz, t["aa"])
     da = _dgrad(pol, dz, lw.w1, out_f32=True, residual=d_ypre)
     d_apre = _ln_bwd(grads, prefix + ".attention.output.LayerNorm", t["a_pre"], da, lw.ln1[0], eps, None) \
@@ -378,10 +396,8 @@ def forward_train(sd: Dict[str, Tensor], cfg, precision: str, xs: Tensor, masks:
     tp.w_a, tp.w_b = pol.weight(sd[na + ".weight"]), pol.weight(sd[nb + ".weight"])
     tp.w_c, b_c = _f32(sd[nc + ".weight"]), _f32(sd[nc + ".bias"])
     tp.h0 = h0
-    tp.za = pol.linear(h0, tp.w_a, _f32(sd[na + ".bias"]))
-    tp.ha = ops.gelu_fwd(tp.za)
-    tp.zb = pol.linear(tp.ha, tp.w_b, _f32(sd[nb + ".bias"]))
-    tp.hb = ops.gelu_fwd(tp.zb)
+    tp.za, tp.ha = _linear_gelu(pol, h0, tp.w_a, _f32(sd[na + ".bias"]))
+    tp.zb, tp.hb = _linear_gelu(pol, tp.ha, tp.w_b, _f32(sd[nb + ".bias"]))
     phi = ops.explainer_head_fwd(tp.hb, B, T, tp.w_c, b_c, grand, null, bool(cfg.explainer_normalize))
     return phi, tp
 
@@ -401,8 +417,7 @@ def backward_train(tp: _Tape, dphi: Tensor, dx_cls: Optional[Tensor] = None, sin
     grads[nc + ".weight"], grads[nc + ".bias"] = dWc, dbc
     dzb = ops.gelu_bwd(dhb, tp.zb)
     _linear_bwd(pol, grads, nb, dzb, tp.ha)
-    dha = _dgrad(pol, dzb, tp.w_b, out_f32=False)
-    dza = ops.gelu_bwd(dha, tp.za)
+    dza = _dgrad_gelu(pol, dzb, tp.w_b, tp.za)
     _linear_bwd(pol, grads, na, dza, tp.h0)
     dx = _dgrad(pol, dza, tp.w_a, out_f32=True)
     if vit:
@@ -726,10 +741,8 @@ def ltt_forward_train(sd, cfg, precision: str, xs: Tensor, masks: Tensor, grand,
     tp.w_a, tp.w_b = pol.weight(sd[na + ".weight"]), pol.weight(sd[nb + ".weight"])
     tp.w_c, b_c = _f32(sd[nc + ".weight"]), _f32(sd[nc + ".bias"])
     tp.h0 = h0
-    tp.za = pol.linear(h0, tp.w_a, _f32(sd[na + ".bias"]))
-    tp.ha = ops.gelu_fwd(tp.za)
-    tp.zb = pol.linear(tp.ha, tp.w_b, _f32(sd[nb + ".bias"]))
-    tp.hb = ops.gelu_fwd(tp.zb)
+    tp.za, tp.ha = _linear_gelu(pol, h0, tp.w_a, _f32(sd[na + ".bias"]))
+    tp.zb, tp.hb = _linear_gelu(pol, tp.ha, tp.w_b, _f32(sd[nb + ".bias"]))
     phi = ops.explainer_head_fwd(tp.hb, B, T, tp.w_c, b_c, grand, null, bool(cfg.explainer_normalize))
     return phi, cls, tp
 
@@ -752,8 +765,7 @@ def ltt_backward_train(tp: _Tape, dout: Tensor) -> Grads:
     grads[nc + ".weight"], grads[nc + ".bias"] = dWc, dbc
     dzb = ops.gelu_bwd(dhb, tp.zb)
     _linear_bwd(pol, grads, nb, dzb, tp.ha)
-    dha = _dgrad(pol, dzb, tp.w_b, out_f32=False)
-    dza = ops.gelu_bwd(dha, tp.za)
+    dza = _dgrad_gelu(pol, dzb, tp.w_b, tp.za)
     _linear_bwd(pol, grads, na, dza, tp.h0)
     dx = _dgrad(pol, dza, tp.w_a, out_f32=True)
     if vit:

@@ -77,6 +77,16 @@ int agb_gemm_bf16_hilo(const void* A, int lda, const void* B, int ldb, int M, in
 int agb_gemm_bf16_dropout_residual(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias,
                                    const float* residual_f32, int ldr, float* out, int thr16, uint64_t seed, int tag,
                                    void* stream);
+/* Training, MLP of a block (reference models/vanilla_vit.py:487-493: dense -> nn.GELU): z = A B^T + bias (bf16, kept for the
+ * adjoint) and gelu_out = GELU(z) (bf16, the next GEMM's operand) from ONE pass over the accumulator; both (M, N) with pitch ldo.
+ * GELU is evaluated at the rounded z, as a separate agb_gelu_fwd on the stored z would. */
+int agb_gemm_bf16_gelu_dual(const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias, void* z_out,
+                            void* gelu_out, int ldo, void* stream);
+/* Its adjoint in the dgrad GEMM's epilogue: dz = (dY W) * GELU'(z), dY (M, K) bf16, W the forward weight stored [K, N]
+ * (out_features x in_features), z / dz (M, N) bf16.  Replaces agb_gemm_bf16 + agb_gelu_bwd (the derivative is that of the
+ * tanh-form approximant the bf16 kernels use, |error| <= 9e-4). */
+int agb_gemm_bf16_gelu_bwd(const void* dY, int ldy, const void* W, int ldw, int M, int N, int K, const void* z, int ldz,
+                           void* dz, int ldo, void* stream);
 /* fp32 -> hi/lo planes (n % 8 == 0). */
 int agb_split_hilo(const float* x, long long n, void* hi, void* lo, void* stream);
 /* bf16 copy + one (sum, sum of squares) pair per row of an fp32 matrix: the entry of the chain above. */

@@ -84,6 +84,33 @@ def test_gemm_with_fused_dropout_residual(agb, M, N, K):
     torch.testing.assert_close(fused, unfused, rtol=1e-2, atol=1e-2)   # y rounded to bf16 on the unfused side
 
 
+@pytest.mark.parametrize("M", [300, 12608, 25216 + 8])
+def test_gemm_with_fused_gelu_forward_and_adjoint(agb, M):
+    """agb_gemm_bf16_gelu_dual == GEMM then GELU kernel (bit-identical z; GELU evaluated at the rounded z on both sides), and
+    agb_gemm_bf16_gelu_bwd == dgrad GEMM then GELU-adjoint kernel up to the bf16 rounding of the intermediate gradient; both
+    against torch fp32."""
+    torch.manual_seed(13)
+    K, N = 768, 3072
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    w1 = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
+    b1 = torch.randn(N, device=DEV) * 0.1
+    z, f = agb.gemm_bf16_gelu_dual(a, w1, b1)
+    z_ref = agb.gemm_bf16(a, w1, b1)
+    assert torch.equal(z, z_ref)
+    assert torch.equal(f, agb.gelu_fwd(z_ref))
+    torch.testing.assert_close(f.float(), torch.nn.functional.gelu(a.float() @ w1.float().t() + b1), rtol=2e-2, atol=2e-2)
+    # adjoint: dz = (dy W2) * GELU'(z), W2 (K, N) = forward weight of the layer behind the GELU
+    dy = torch.randn(M, K, device=DEV).bfloat16()
+    w2 = (torch.randn(K, N, device=DEV) / N ** 0.5).bfloat16()
+    dz = agb.gemm_bf16_gelu_bwd(dy, w2, z)
+    dz_unfused = agb.gelu_bwd(agb.gemm_bf16(dy, w2, w_mn=True), z)
+    zr = z.float().requires_grad_(True)
+    torch.nn.functional.gelu(zr).backward(dy.float() @ w2.float())
+    torch.testing.assert_close(dz.float(), zr.grad, rtol=2e-2, atol=5e-3)
+    assert float((dz.float() - zr.grad).norm() / zr.grad.norm()) < 5e-3
+    assert float((dz.float() - dz_unfused.float()).norm() / dz_unfused.float().norm()) < 5e-3
+
+
 def test_gelu_bf16_fast_forms_vs_torch(agb):
     """bf16 GELU forward / adjoint kernels (one MUFU each: the tanh-form refit of erf-GELU and ITS derivative) against torch's
     exact erf GELU and autograd; fp32 I/O keeps the exact erf / exp forms."""
