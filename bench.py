@@ -485,7 +485,22 @@ def run_ours_side(args):
     if rank == 0:
         sampler.start()
     ms, _, launches, prof = timed(step_resident, args.steps, args.warmup, profile=True)
+    continued = False
+    if rank == 0 and len(sampler.lines) < 3:
+        # timed region shorter than the sampler's 100 ms period (KernelSHAP: ~35 ms): keep running the SAME step, untimed,
+        # until a few samples exist, so that the line still carries clocks / throttle reasons under this load
+        continued = True
+        t_end = time.perf_counter() + 2.0
+        i = 0
+        while len(sampler.lines) < 5 and time.perf_counter() < t_end:
+            step_resident(args.warmup + args.steps + i)
+            i += 1
+            if i % 8 == 0:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
+    if continued and clocks is not None:
+        clocks["sampled"] = "during an untimed continuation of the same step (timed region < 100 ms sampling period)"
     ms_e, wall_e, _, _ = timed(step_e2e, args.steps, max(2, args.warmup // 2))
     ms_e = max(ms_e, wall_e)                     # results are on the host: the host clock bounds the same region
     value = world * units * args.steps / (ms * 1e-3)
@@ -515,13 +530,15 @@ def run_ours_side(args):
         k = by_kernel.get("agb_kernelshap_solve", [ms, 0.0, args.steps])
         achieved = alg_bytes * units / (k[0] / max(k[2], 1) * 1e-3) * 1e-9
         gram_flops = 2.0 * KS_S * (KS_D - 1) ** 2 + (KS_D - 1) ** 3 / 3.0
-        roofline = {"bound": "hbm", "kernel": "kernelshap_gram_kernel + kernelshap_solve_kernel (agb_kernelshap_solve)", "achieved": achieved,
+        roofline = {"bound": "hbm", "kernel": "kernelshap_gram_tc_kernel + kernelshap_rhs_kernel + kernelshap_solve_kernel (agb_kernelshap_solve)", "achieved": achieved,
                     "peak": peaks["hbm_gbs"], "peak_kind": f"hbm_gbs, {peaks['source']}", "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                     "traffic": None, "avg_launch_us": k[0] / max(k[2], 1) * 1e3, "launches": k[2], "share_of_step": k[0] / total_t,
                     "algorithmic_bytes_per_solve": alg_bytes, "step_shares": shares,
-                    "fp64_tflops": value / world * gram_flops * 1e-12,
-                    "note": "the Gram accumulation is a float64 contraction (2 S d^2 = 66 MFLOP per solve) on the fp64 FMA pipe; against "
-                            "the HBM roofline north_star assigns the solve it is compute-bound by two orders of magnitude"}
+                    "fp64_equivalent_tflops": value / world * gram_flops * 1e-12,
+                    "note": "the Gram accumulation is a contraction (2 S d^2 = 66 MFLOP per solve, float64-exact): since round 2 it runs on the "
+                            "tensor cores as seven exact 8-bit fixed-point limbs of the weights (tcgen05, bit-reproducible float64 "
+                            "recombination), followed by a float64 Cholesky per sample; against the HBM roofline north_star assigns the "
+                            "solve it is compute-bound by two orders of magnitude, so frac is small by construction"}
         metric, unit, dtype = "kernelshap_solves_per_sec", "solves/s", "f64"
         extra = {}
     if rank == 0:
