@@ -16,6 +16,8 @@
 //     instructions per output element instead of ~14 and touches global memory only through TMA.
 //   * GELU costs one MUFU and 8 issue slots (gelu_erf_tanhform) instead of two MUFU and ~16.
 //   * producer and MMA warps run convergently with elected-lane predication (uniform-register operands).
+//   * round 2: further epilogue modes on the same skeleton — hi/lo residual planes updated in place (RES = 3), GELU with the
+//     pre-activation as a second output (ACT = 2), GELU adjoint with a TMA-loaded z tile (RES = 4), dropout + fp32 residual.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (leader CTA only) + TMEM owner, 2..9 = epilogue.
 #include <cstdlib>
 #include <type_traits>

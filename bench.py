@@ -929,7 +929,8 @@ def run_ours(args):
         "step_shares": {k: round(v[0] / total_t, 4) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1][0])},
     }
     # per-shape view of the same launches: tensor-bound shapes against the bf16 peak, the residual GEMM with K = H
-    # (out-proj, 9.3 KB/row of fp32 residual in/out + bf16 copy) against the measured HBM bandwidth
+    # (out-proj: 7.7 KB/row with the hi/lo residual planes in/out, 9.3 KB/row with the fp32 stream + bf16 copy) against the
+    # measured HBM bandwidth
     shapes = {}
     for name, meta, a, b, *rest in prof:
         info = rest[0] if rest else None
