@@ -29,12 +29,6 @@ void set_attention_bwd_variant(int v);
 int get_attention_bwd_variant();
 void set_attention_trace(long long* t);
 int get_attention_variant();
-int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, int M, int N, int K,
-                      float alpha, const float* bias, int act, const bf16* res_bf16, const float* res_f32, int ldr,
-                      void* out, int ldo, int out_f32, const float* ln_stats, int ln_parts, const float* ln_colsum,
-                      float ln_eps, bf16* out16, int ldo16, float* stats_out, cudaStream_t stream, bf16* hl_hi = nullptr,
-                      bf16* hl_lo = nullptr, int ld_hl = 0, unsigned drop_thr = 0, unsigned drop_key = 0, bf16* z_out = nullptr,
-                      int ldz_out = 0, const bf16* z_in = nullptr, int ldz_in = 0);
 int gather_token_rows_hilo(const float* src, const uint8_t* order, int rows, int T, int S, int H, bf16* hi, bf16* lo,
                            cudaStream_t st);
 int split_hilo(const float* x, long long n, bf16* hi, bf16* lo, cudaStream_t st);
@@ -195,10 +189,12 @@ int agb_gemm_bf16_fused(const void* A, int lda, const void* B, int ldb, int M, i
   AGB_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && out, "operands");
   AGB_REQUIRE((N % 4) == 0 && (lda % 8) == 0 && (ldb % 8) == 0, "alignment");
   AGB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0, "alignment");
-  const int rc = agb::gemm_bf16_pair_ex(static_cast<const bf16*>(A), lda, 0, static_cast<const bf16*>(B), ldb, 0, M, N, K,
-                                        1.0f, bias, act, nullptr, residual_f32, ldr, out, ldo, out_is_f32, ln_stats,
-                                        ln_parts, ln_colsum, ln_eps, static_cast<bf16*>(out_bf16_copy), ldo_copy,
-                                        stats_out, ST(stream));
+  agb::PairGemmCall c;
+  c.A = static_cast<const bf16*>(A); c.lda = lda; c.B = static_cast<const bf16*>(B); c.ldb = ldb; c.M = M; c.N = N; c.K = K;
+  c.bias = bias; c.act = act; c.res_f32 = residual_f32; c.ldr = ldr; c.out = out; c.ldo = ldo; c.out_f32 = out_is_f32;
+  c.ln_stats = ln_stats; c.ln_parts = ln_parts; c.ln_colsum = ln_colsum; c.ln_eps = ln_eps;
+  c.out16 = static_cast<bf16*>(out_bf16_copy); c.ldo16 = ldo_copy; c.stats_out = stats_out;
+  const int rc = agb::gemm_bf16_pair_call(c, ST(stream));
   if (rc == AGB_ERR_UNSUPPORTED)
     agb::set_last_error("agb_gemm_bf16_fused: shape / epilogue combination not covered (M=%d N=%d K=%d act=%d)", M, N, K, act);
   return rc;
@@ -208,9 +204,11 @@ int agb_gemm_bf16_hilo(const void* A, int lda, const void* B, int ldb, int M, in
   AGB_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && x_hi && x_lo && stats_out, "operands");
   AGB_REQUIRE((N % 256) == 0 && (lda % 8) == 0 && (ldb % 8) == 0 && (ldx % 8) == 0, "alignment");
   AGB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0, "alignment");
-  const int rc = agb::gemm_bf16_pair_ex(static_cast<const bf16*>(A), lda, 0, static_cast<const bf16*>(B), ldb, 0, M, N, K,
-                                        1.0f, bias, 0, nullptr, nullptr, 0, nullptr, 0, 0, nullptr, 0, nullptr, 0.f, nullptr, 0,
-                                        stats_out, ST(stream), static_cast<bf16*>(x_hi), static_cast<bf16*>(x_lo), ldx);
+  agb::PairGemmCall c;
+  c.A = static_cast<const bf16*>(A); c.lda = lda; c.B = static_cast<const bf16*>(B); c.ldb = ldb; c.M = M; c.N = N; c.K = K;
+  c.bias = bias; c.stats_out = stats_out;
+  c.hl_hi = static_cast<bf16*>(x_hi); c.hl_lo = static_cast<bf16*>(x_lo); c.ld_hl = ldx;
+  const int rc = agb::gemm_bf16_pair_call(c, ST(stream));
   if (rc == AGB_ERR_UNSUPPORTED)
     agb::set_last_error("agb_gemm_bf16_hilo: shape not covered (M=%d N=%d K=%d)", M, N, K);
   return rc;
@@ -222,9 +220,11 @@ int agb_gemm_bf16_dropout_residual(const void* A, int lda, const void* B, int ld
   AGB_REQUIRE((N % 4) == 0 && (lda % 8) == 0 && (ldb % 8) == 0 && (ldr % 4) == 0, "alignment");
   AGB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0, "alignment");
   const unsigned key = agb::agb_drop_key(seed, (uint32_t)tag, 0x5bd1e995u);     // the stream of agb_dropout(seed, tag)
-  const int rc = agb::gemm_bf16_pair_ex(static_cast<const bf16*>(A), lda, 0, static_cast<const bf16*>(B), ldb, 0, M, N, K,
-                                        1.0f, bias, 0, nullptr, residual_f32, ldr, out, N, 1, nullptr, 0, nullptr, 0.f, nullptr,
-                                        0, nullptr, ST(stream), nullptr, nullptr, 0, (unsigned)thr16, key);
+  agb::PairGemmCall c;
+  c.A = static_cast<const bf16*>(A); c.lda = lda; c.B = static_cast<const bf16*>(B); c.ldb = ldb; c.M = M; c.N = N; c.K = K;
+  c.bias = bias; c.res_f32 = residual_f32; c.ldr = ldr; c.out = out; c.ldo = N; c.out_f32 = 1;
+  c.drop_thr = (unsigned)thr16; c.drop_key = key;
+  const int rc = agb::gemm_bf16_pair_call(c, ST(stream));
   if (rc == AGB_ERR_UNSUPPORTED)
     agb::set_last_error("agb_gemm_bf16_dropout_residual: shape not covered (M=%d N=%d K=%d)", M, N, K);
   return rc;
@@ -234,9 +234,10 @@ int agb_gemm_bf16_gelu_dual(const void* A, int lda, const void* B, int ldb, int 
   AGB_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && z_out && gelu_out, "operands");
   AGB_REQUIRE((N % 4) == 0 && (lda % 8) == 0 && (ldb % 8) == 0 && (ldo % 8) == 0, "alignment");
   AGB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0, "alignment");
-  const int rc = agb::gemm_bf16_pair_ex(static_cast<const bf16*>(A), lda, 0, static_cast<const bf16*>(B), ldb, 0, M, N, K,
-                                        1.0f, bias, 2, nullptr, nullptr, 0, gelu_out, ldo, 0, nullptr, 0, nullptr, 0.f, nullptr, 0,
-                                        nullptr, ST(stream), nullptr, nullptr, 0, 0u, 0u, static_cast<bf16*>(z_out), ldo);
+  agb::PairGemmCall c;
+  c.A = static_cast<const bf16*>(A); c.lda = lda; c.B = static_cast<const bf16*>(B); c.ldb = ldb; c.M = M; c.N = N; c.K = K;
+  c.bias = bias; c.act = 2; c.out = gelu_out; c.ldo = ldo; c.z_out = static_cast<bf16*>(z_out); c.ldz_out = ldo;
+  const int rc = agb::gemm_bf16_pair_call(c, ST(stream));
   if (rc == AGB_ERR_UNSUPPORTED)
     agb::set_last_error("agb_gemm_bf16_gelu_dual: shape not covered (M=%d N=%d K=%d)", M, N, K);
   return rc;
@@ -247,9 +248,10 @@ int agb_gemm_bf16_gelu_bwd(const void* dY, int ldy, const void* W, int ldw, int 
   AGB_REQUIRE((N % 4) == 0 && (ldy % 8) == 0 && (ldw % 8) == 0 && (ldo % 8) == 0 && (ldz % 8) == 0, "alignment");
   AGB_REQUIRE((reinterpret_cast<uintptr_t>(dY) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, "alignment");
   // W is the forward weight [K, N] (out_features K x in_features N): the MN-major B operand of dY W
-  const int rc = agb::gemm_bf16_pair_ex(static_cast<const bf16*>(dY), ldy, 0, static_cast<const bf16*>(W), ldw, 1, M, N, K,
-                                        1.0f, nullptr, 0, nullptr, nullptr, 0, dz, ldo, 0, nullptr, 0, nullptr, 0.f, nullptr, 0,
-                                        nullptr, ST(stream), nullptr, nullptr, 0, 0u, 0u, nullptr, 0, static_cast<const bf16*>(z), ldz);
+  agb::PairGemmCall c;
+  c.A = static_cast<const bf16*>(dY); c.lda = ldy; c.B = static_cast<const bf16*>(W); c.ldb = ldw; c.b_mn = 1;
+  c.M = M; c.N = N; c.K = K; c.out = dz; c.ldo = ldo; c.z_in = static_cast<const bf16*>(z); c.ldz_in = ldz;
+  const int rc = agb::gemm_bf16_pair_call(c, ST(stream));
   if (rc == AGB_ERR_UNSUPPORTED)
     agb::set_last_error("agb_gemm_bf16_gelu_bwd: shape not covered (M=%d N=%d K=%d)", M, N, K);
   return rc;

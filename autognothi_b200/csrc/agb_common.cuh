@@ -554,4 +554,33 @@ int encode_tmap_3d_bf16(CUtensorMap* out, const void* gptr, uint64_t d0, uint64_
                         uint32_t box1, uint32_t box2);
 int sm_count();
 
+// ---------------------------------------------------------------------------------------------
+// One request to the CTA-pair tcgen05 GEMM (agb_gemm_pair.cu):  C = epilogue(alpha * A * B^T + bias).
+// Fields left at their defaults are off.  gemm_bf16_pair_call returns AGB_ERR_UNSUPPORTED for combinations / shapes the
+// kernel does not cover (narrow N, bf16 residual, ...): the generic entry point then runs the first-generation kernel.
+// ---------------------------------------------------------------------------------------------
+struct PairGemmCall {
+  const bf16* A = nullptr;  int lda = 0, a_mn = 0;       // operand majorness: 0 = K-major [rows, K], 1 = MN-major [K, rows]
+  const bf16* B = nullptr;  int ldb = 0, b_mn = 0;
+  int M = 0, N = 0, K = 0;
+  float alpha = 1.0f;
+  const float* bias = nullptr;
+  int act = 0;                                           // 0 none, 1 GELU, 2 GELU + pre-activation to z_out (training)
+  const bf16* res_bf16 = nullptr;                        // (not covered by this kernel)
+  const float* res_f32 = nullptr;  int ldr = 0;          // fp32 residual (fp32 output)
+  void* out = nullptr;  int ldo = 0, out_f32 = 0;
+  // LayerNorm of the A rows folded into the epilogue (bf16 output, no residual): row statistics + column sums of B
+  const float* ln_stats = nullptr;  int ln_parts = 0;  const float* ln_colsum = nullptr;  float ln_eps = 0.f;
+  // fp32 residual epilogue: also emit a bf16 copy of the output and per-row partial (sum, sum of squares) per 128-column slab
+  bf16* out16 = nullptr;  int ldo16 = 0;
+  float* stats_out = nullptr;                            // [M][2 * ceil(N / 256)][2]; mandatory with hl_hi
+  // residual stream as two bf16 planes updated in place (x = hi + lo); `out`, `res_f32`, `out16` unused
+  bf16* hl_hi = nullptr;  bf16* hl_lo = nullptr;  int ld_hl = 0;
+  // nn.Dropout on the GEMM output ahead of the fp32 residual add (threshold 0 = off; key of agb_dropout's stream)
+  unsigned drop_thr = 0, drop_key = 0;
+  bf16* z_out = nullptr;  int ldz_out = 0;               // act == 2: pre-activation
+  const bf16* z_in = nullptr;  int ldz_in = 0;           // out = acc * GELU'(z_in)  (bf16 output, no bias)
+};
+int gemm_bf16_pair_call(const PairGemmCall& call, cudaStream_t stream);
+
 }  // namespace agb

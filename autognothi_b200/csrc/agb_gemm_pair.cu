@@ -560,17 +560,29 @@ int get_gemm_variant() { return g_gemm_variant; }
 
 // Returns AGB_ERR_UNSUPPORTED when this kernel does not cover the request (the caller then uses the
 // first-generation kernel): narrow N, bf16 residual, fp32 residual with bf16 output, GELU + residual.
-// hl_hi / hl_lo (round 2): the residual stream as two bf16 planes updated in place (kernel comment at RES == 3); `out`,
-// `res_f32` and `out16` are unused then and stats_out is mandatory.
+// Field meanings: PairGemmCall in agb_common.cuh.
 // Optional fusions (nullptr = off):
 //   ln_stats / ln_colsum : LayerNorm of the A rows folded into the epilogue (bf16 output only, no residual)
 //   out16 / stats_out    : with an fp32 residual epilogue, also emit a bf16 copy of the output and its per-row
 //                          partial (sum, sum of squares) over each 128-column slab: stats_out [M][2*ceil(N/256)][2]
-int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, int M, int N, int K,
-                      float alpha, const float* bias, int act, const bf16* res_bf16, const float* res_f32, int ldr,
-                      void* out, int ldo, int out_f32, const float* ln_stats, int ln_parts, const float* ln_colsum,
-                      float ln_eps, bf16* out16, int ldo16, float* stats_out, cudaStream_t stream, bf16* hl_hi, bf16* hl_lo,
-                      int ld_hl, unsigned drop_thr, unsigned drop_key, bf16* z_out, int ldz_out, const bf16* z_in, int ldz_in) {
+int gemm_bf16_pair_call(const PairGemmCall& call, cudaStream_t stream) {
+  const bf16* A = call.A; const int lda = call.lda, a_mn = call.a_mn;
+  const bf16* B = call.B; const int ldb = call.ldb, b_mn = call.b_mn;
+  const int M = call.M, N = call.N, K = call.K;
+  const float alpha = call.alpha;
+  const float* bias = call.bias;
+  const int act = call.act;
+  const bf16* res_bf16 = call.res_bf16;
+  const float* res_f32 = call.res_f32; const int ldr = call.ldr;
+  void* out = call.out; int ldo = call.ldo, out_f32 = call.out_f32;
+  const float* ln_stats = call.ln_stats; const int ln_parts = call.ln_parts;
+  const float* ln_colsum = call.ln_colsum; const float ln_eps = call.ln_eps;
+  bf16* out16 = call.out16; const int ldo16 = call.ldo16;
+  float* stats_out = call.stats_out;
+  bf16* hl_hi = call.hl_hi; bf16* hl_lo = call.hl_lo; const int ld_hl = call.ld_hl;
+  const unsigned drop_thr = call.drop_thr, drop_key = call.drop_key;
+  bf16* z_out = call.z_out; const int ldz_out = call.ldz_out;
+  const bf16* z_in = call.z_in; const int ldz_in = call.ldz_in;
   const bool lnin = ln_stats != nullptr, stats = stats_out != nullptr;
   const bool hl = hl_hi != nullptr;
   if (g_gemm_variant == 1) return AGB_ERR_UNSUPPORTED;
@@ -741,9 +753,11 @@ int gemm_bf16_pair_ex(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, 
 int gemm_bf16_pair(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, int M, int N, int K,
                    float alpha, const float* bias, int act, const bf16* res_bf16, const float* res_f32, int ldr,
                    void* out, int ldo, int out_f32, cudaStream_t stream) {
-  return gemm_bf16_pair_ex(A, lda, a_mn, B, ldb, b_mn, M, N, K, alpha, bias, act, res_bf16, res_f32, ldr, out, ldo,
-                           out_f32, nullptr, 0, nullptr, 0.f, nullptr, 0, nullptr, stream, nullptr, nullptr, 0, 0u, 0u, nullptr, 0,
-                           nullptr, 0);
+  PairGemmCall c;
+  c.A = A; c.lda = lda; c.a_mn = a_mn; c.B = B; c.ldb = ldb; c.b_mn = b_mn; c.M = M; c.N = N; c.K = K;
+  c.alpha = alpha; c.bias = bias; c.act = act; c.res_bf16 = res_bf16; c.res_f32 = res_f32; c.ldr = ldr;
+  c.out = out; c.ldo = ldo; c.out_f32 = out_f32;
+  return gemm_bf16_pair_call(c, stream);
 }
 
 }  // namespace agb
