@@ -79,6 +79,58 @@ def test_invalid_arguments_are_rejected_without_a_gpu(built):
     assert lib.agb_masked_attention_simt(None, 1, None, 1, 2, 40, 96, 12, 0, None, None) == 1    # 1 mask word < 40 tokens
 
 
+def test_round2_entry_points_validate_before_touching_the_device(built):
+    """hi/lo residual GEMM, fused training epilogues, hi/lo gather / split: shapes and pointers are checked first"""
+    lib = ctypes.CDLL(built)
+    lib.agb_last_error.restype = ctypes.c_char_p
+    vp, ci, cl = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong
+    lib.agb_gemm_bf16_hilo.argtypes = [vp, ci, vp, ci, ci, ci, ci, vp, vp, vp, ci, vp, vp]
+    assert lib.agb_gemm_bf16_hilo(None, 768, None, 768, 256, 768, 768, None, None, None, 768, None, None) == 1
+    assert b"operands" in lib.agb_last_error()
+    one = ctypes.c_void_p(16)          # any non-null 16-byte-aligned value: the call must fail on the shape, before any use
+    assert lib.agb_gemm_bf16_hilo(one, 768, one, 768, 256, 700, 768, None, one, one, 768, one, None) == 1      # N % 256
+    assert b"alignment" in lib.agb_last_error()
+    lib.agb_gemm_bf16_dropout_residual.argtypes = [vp, ci, vp, ci, ci, ci, ci, vp, vp, ci, vp, ci, ctypes.c_uint64, ci, vp]
+    assert lib.agb_gemm_bf16_dropout_residual(one, 768, one, 768, 256, 768, 768, None, one, 768, one, 0, 1, 1, None) == 1
+    assert b"threshold" in lib.agb_last_error()
+    assert lib.agb_gemm_bf16_dropout_residual(one, 768, one, 768, 256, 768, 768, None, None, 768, one, 6554, 1, 1, None) == 1
+    lib.agb_gemm_bf16_gelu_dual.argtypes = [vp, ci, vp, ci, ci, ci, ci, vp, vp, vp, ci, vp]
+    assert lib.agb_gemm_bf16_gelu_dual(one, 768, one, 768, 256, 3072, 768, None, None, one, 3072, None) == 1
+    lib.agb_gemm_bf16_gelu_bwd.argtypes = [vp, ci, vp, ci, ci, ci, ci, vp, ci, vp, ci, vp]
+    assert lib.agb_gemm_bf16_gelu_bwd(one, 768, one, 3072, 256, 3072, 768, None, 3072, one, 3072, None) == 1
+    lib.agb_split_hilo.argtypes = [vp, cl, vp, vp, vp]
+    assert lib.agb_split_hilo(None, 12, None, None, None) == 1 and b"multiple of 8" in lib.agb_last_error()
+    assert lib.agb_split_hilo(None, 0, None, None, None) == 0
+    lib.agb_gather_token_rows_hilo.argtypes = [vp, vp, ci, ci, ci, ci, vp, vp, vp]
+    assert lib.agb_gather_token_rows_hilo(None, None, 6, 197, 4, 768, None, None, None) == 1      # rows % S
+    assert lib.agb_gather_token_rows_hilo(None, None, 0, 197, 4, 768, None, None, None) == 0
+
+
+def test_zero_arena_hands_out_disjoint_zero_slices():
+    """training._ZeroArena: the small accumulate-into gradients of one backward pass are slices of one zero chunk"""
+    import torch
+
+    from autognothi_b200 import training
+    arena = training._ZeroArena()
+    cpu = torch.device("cpu")
+    a = arena.take((768,), cpu)
+    b = arena.take((3, 5), cpu)
+    c = arena.take((training._ZeroArena.CHUNK + 1,), cpu)          # larger than a chunk: its own allocation
+    assert a.shape == (768,) and b.shape == (3, 5) and c.numel() == training._ZeroArena.CHUNK + 1
+    assert a.is_contiguous() and b.is_contiguous() and float(a.abs().sum() + b.abs().sum() + c.abs().sum()) == 0.0
+    a += 1.0
+    assert float(b.abs().sum()) == 0.0                             # disjoint
+    assert a.data_ptr() % 256 == b.data_ptr() % 256                # 256-byte steps between slices
+    first = arena.buf
+    for _ in range(training._ZeroArena.CHUNK // 1024 + 2):         # exhausting the chunk opens a fresh one, zero again
+        x = arena.take((1024,), cpu)
+    assert arena.buf is not first and float(x.abs().sum()) == 0.0
+    with training._arena_scope():
+        assert training._ARENA is not None
+        z = training._zeros((4,), cpu)
+    assert training._ARENA is None and z.shape == (4,)
+
+
 def test_product_never_imports_the_oracle():
     """oracle/ is test infrastructure: nothing under autognothi_b200/ may import it."""
     pkg = os.path.join(ROOT, "autognothi_b200")
