@@ -322,12 +322,15 @@ def run_bert_packed(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: T
 
 
 def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tensor, S: int, cls_only: bool = False,
-                 layer_hook=None) -> Tuple[Tensor, Optional[Tensor]]:
+                 layer_hook=None, token0_only: bool = False) -> Tuple[Tensor, Optional[Tensor]]:
     """-> (x (rows*T, H) fp32 after the encoder stack [ViT: BEFORE the final LayerNorm], activation copy | None).
     cls_only (surrogate / classifier heads): the last block runs for the CLS query only and x is (rows, H).
-    layer_hook(i, x, x_act): called after every block with its output (fp32 residual stream, activation-dtype copy or
-    None) — the side ladders of the LTT variants tap the frozen backbone here; x is updated in place by the next block,
-    so the hook must consume it on the same stream."""
+    layer_hook(i, x, x_act, masks): called after every block with its output (fp32 residual stream | None, activation-dtype
+    copy | None, the packed masks that go with the rows' token order) — the side ladders of the LTT variants tap the frozen
+    backbone here; x is updated in place by the next block, so the hook must consume it on the same stream.
+    token0_only (with a hook; the LTT surrogate ladders): everything downstream — the hook and the caller's heads — reads
+    token 0 only and is equivariant to a per-row permutation of the tokens given the permuted masks, so the stack may run in
+    kept-first order on the hi/lo residual stream; x is then the CLS rows (rows, H) and the hook gets x = None."""
     T = n_players_of(cfg) + 1
     H, heads, eps = cfg.hidden_size, cfg.num_attention_heads, cfg.layer_norm_eps
     cls_only = cls_only and CLS_ONLY_LAST_BLOCK and len(bw.layers) > 0 and layer_hook is None
@@ -341,7 +344,8 @@ def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tens
     share = (SHARE_FIRST_BLOCK and S > 1 and pol.bf16 and len(full) > 0 and T <= 512 and H == heads * 64)
     ctx0 = None
     nkeep = None             # set when the rows are switched to kept-first token order (KEPT_FIRST_ORDER)
-    hilo = HILO_RESIDUAL and fused and cls_only and layer_hook is None and len(full) > 0
+    free_order = cls_only or (token0_only and layer_hook is not None)      # nobody downstream depends on the token order
+    hilo = HILO_RESIDUAL and fused and free_order and len(full) > 0
     xh = xl = None           # hi/lo residual stream (see HILO_RESIDUAL)
     if share:
         x_img = embed(bw, cfg, pol, xs, 1)                                   # (B, T, H) fp32, one row block per input
@@ -357,7 +361,7 @@ def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tens
             qkv0 = pol.linear(h0, lw0.wqkv, lw0.bqkv)
         else:
             qkv0 = pol.linear(pol.act(xi), lw0.wqkv, lw0.bqkv)
-        if (KEPT_FIRST_ORDER and cls_only and fused and layer_hook is None and T <= 208 and len(full) > 1):
+        if (KEPT_FIRST_ORDER and free_order and fused and T <= 208 and len(full) > 1):
             # kept-first token order per row (stable: CLS stays first).  The first block's attention (projections shared per
             # input, masks in the original token order) scatters its output rows into that order, the residual stream of
             # every coalition is gathered from the per-input embeddings in that order, and from here on the masks are
@@ -388,6 +392,10 @@ def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tens
         xh, xl = xh.reshape(rows * T, H), xl.reshape(rows * T, H)
         for i, lw in enumerate(full):
             stats = vit_layer_hilo(lw, xh, xl, stats, T, heads, eps, masks, ctx=ctx0 if i == 0 else None, nkeep=nkeep)
+            if layer_hook is not None:
+                layer_hook(i, None, xh, masks)
+        if not cls_only:         # token0_only: the caller's heads read the CLS rows
+            return xh.view(rows, T, H)[:, 0, :].float() + xl.view(rows, T, H)[:, 0, :].float(), None
         return last_block_cls_only(pol, bw.layers[-1], True, None, None, xh, stats, masks, T, heads, eps, x_lo=xl)
     if bw.vit:
         if fused:
@@ -399,7 +407,7 @@ def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tens
                                                 last=(not cls_only and i == len(full) - 1 and layer_hook is None),
                                                 ctx=ctx0 if i == 0 else None, nkeep=nkeep)
                 if layer_hook is not None:
-                    layer_hook(i, x, x16)
+                    layer_hook(i, x, x16, masks)
             if cls_only:
                 if x16 is None:      # single-block model: the CLS-only block is also the first one
                     x16, stats = ops.rowstats_cast(x)
@@ -408,7 +416,7 @@ def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tens
         for i, lw in enumerate(full):
             x = vit_layer(pol, lw, x, masks, T, heads, eps, ctx=ctx0 if i == 0 else None)
             if layer_hook is not None:
-                layer_hook(i, x, None)
+                layer_hook(i, x, None, masks)
         if cls_only:
             return last_block_cls_only(pol, bw.layers[-1], True, x, None, None, None, masks, T, heads, eps)
         return x, None
@@ -416,7 +424,7 @@ def run_backbone(bw: BackboneWeights, cfg, pol: _Policy, xs: Tensor, masks: Tens
     for i, lw in enumerate(full):
         x, xa = bert_layer(pol, lw, x, xa, masks, T, heads, eps, ctx=ctx0 if i == 0 else None)
         if layer_hook is not None:
-            layer_hook(i, x, xa)
+            layer_hook(i, x, xa, masks)
     if cls_only:
         if xa is None:
             xa = pol.act(x)
@@ -690,7 +698,7 @@ def run_ltt_bert_packed(bw: BackboneWeights, branches: List[SideBranch], cfg, po
 
 
 def run_ltt(bw: BackboneWeights, branches: List[SideBranch], cfg, pol: _Policy, xs: Tensor, masks: Tensor, S: int,
-            freeze_layer: Optional[int] = None):
+            freeze_layer: Optional[int] = None, token0_only: bool = False):
     """-> (x, xa of the backbone as run_backbone, [(side state (rows*T, Hs) fp32, activation copy | None) per branch])
     freeze_layer: reference `_ltt_freeze_layer` — blocks >= it do not feed the ladders."""
     T = n_players_of(cfg) + 1
@@ -700,7 +708,8 @@ def run_ltt(bw: BackboneWeights, branches: List[SideBranch], cfg, pol: _Policy, 
     side: List[Optional[Tensor]] = [None] * len(branches)
     side_a: List[Optional[Tensor]] = [None] * len(branches)
 
-    def hook(i: int, x: Tensor, x_act: Optional[Tensor]) -> None:
+    def hook(i: int, x: Optional[Tensor], x_act: Optional[Tensor], m: Tensor) -> None:
+        # m: the masks in the token order the backbone runs in (kept-first order permutes the tokens of every row)
         if i >= stop:
             return
         if x_act is None:
@@ -709,11 +718,11 @@ def run_ltt(bw: BackboneWeights, branches: List[SideBranch], cfg, pol: _Policy, 
             w, b = br.maps[i]
             s = pol.linear(x_act, w, b, act=ops.ACT_GELU, residual=side[k], out_f32=True)
             if bw.vit:
-                side[k] = vit_layer(pol, br.layers[i], s, masks, T, heads, eps)
+                side[k] = vit_layer(pol, br.layers[i], s, m, T, heads, eps)
             else:
-                side[k], side_a[k] = bert_layer(pol, br.layers[i], s, pol.act(s), masks, T, heads, eps)
+                side[k], side_a[k] = bert_layer(pol, br.layers[i], s, pol.act(s), m, T, heads, eps)
 
-    x, xa = run_backbone(bw, cfg, pol, xs, masks, S, layer_hook=hook)
+    x, xa = run_backbone(bw, cfg, pol, xs, masks, S, layer_hook=hook, token0_only=token0_only)
     return x, xa, list(zip(side, side_a))
 
 
@@ -808,7 +817,9 @@ class LttEngine:
                 cls.append(self._main_probs(x, rows))
                 srg.append(self._side_probs(sides_cls[0], rows))
                 continue
-            x, _, sides = run_ltt(self.bw, self.branches[:1], self.cfg, self.pol, xs[b0:b1], masks[b0 * S:b1 * S], S, self.freeze_layer)
+            # both heads read token 0 and the ladder is token-wise + attention: free to run in kept-first order (hi/lo stream)
+            x, _, sides = run_ltt(self.bw, self.branches[:1], self.cfg, self.pol, xs[b0:b1], masks[b0 * S:b1 * S], S, self.freeze_layer,
+                                  token0_only=True)
             cls.append(self._main_probs(x, rows))
             srg.append(self._side_probs(sides[0][0], rows))
         return (srg[0], cls[0]) if len(srg) == 1 else (torch.cat(srg, 0), torch.cat(cls, 0))

@@ -650,7 +650,7 @@ def _ltt_side_forward(tp: _Tape, sd, cfg, pol, xs: Tensor, masks: Tensor, freeze
     tp.bw, tp.br, tp.T, tp.B, tp.rungs = bw, br, T, B, []
     state: Dict[str, Optional[Tensor]] = {"s": None, "sa": None}
 
-    def hook(i: int, x: Tensor, x_act: Optional[Tensor]) -> None:
+    def hook(i: int, x: Tensor, x_act: Optional[Tensor], _masks=None) -> None:
         if i >= stop:
             return
         if x_act is None:

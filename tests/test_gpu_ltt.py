@@ -196,6 +196,43 @@ def test_ltt_surrogate_training_gradients(agb, golden_dir, name):
         assert abs(got - ref_norms[k]) <= 2e-3 * ref_norms[k] + floor, f"{k}: |grad| {got} vs {ref_norms[k]}"
 
 
+def test_ltt_vit_base_surrogate_kept_first_order_is_exact(agb):
+    """LTT surrogate evaluation at ViT-Base size (ladder width 96, head dim 8): both heads read token 0 and the ladder is
+    token-wise + attention, so backbone AND ladder may run in kept-first token order on the hi/lo residual stream
+    (engine.run_backbone(token0_only=True)); same probabilities as the token-order / fp32-stream path."""
+    from autognothi_b200 import engine
+    from autognothi_b200.recipes.ltt_vit import ltt_vit_recipe
+    rec = ltt_vit_recipe()
+    cfgd = dict(ocfg.get_config("vit_base"))
+    for k in ("explainer_attn_num_layers", "explainer_head_hidden_size"):
+        cfgd.pop(k, None)
+    cfgd.update(explainer_s_attn_num_layers=1, explainer_s_head_hidden_size=cfgd["intermediate_size"],
+                s_attn_hidden_size=cfgd["hidden_size"] // 8, s_attn_intermediate_size=cfgd["hidden_size"] // 2)
+    cfg = rec.t_config(**cfgd)
+    torch.manual_seed(21)
+    srg = rec.t_surrogate(cfg).to(DEV).eval()
+    srg.agb_precision = "bf16"
+    B, S = 3, 16
+    n = rec.n_players(cfg)
+    xs = torch.randn(B, 3, 224, 224, device=DEV)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    masks = (torch.rand((B, S, n), generator=g) > torch.rand((B, S, 1), generator=g)).to(torch.int64).to(DEV)
+    masks[0, 0, :] = 0
+    masks[0, 1, :] = 1
+    old = engine.KEPT_FIRST_ORDER, engine.HILO_RESIDUAL
+    try:
+        with torch.no_grad():
+            engine.KEPT_FIRST_ORDER, engine.HILO_RESIDUAL = True, True
+            side_a, cls_a = rec.fw_surrogate(srg, xs, masks)
+            engine.KEPT_FIRST_ORDER, engine.HILO_RESIDUAL = False, False
+            side_b, cls_b = rec.fw_surrogate(srg, xs, masks)
+    finally:
+        engine.KEPT_FIRST_ORDER, engine.HILO_RESIDUAL = old
+    np.testing.assert_allclose(_np(side_a), _np(side_b), atol=3e-3)
+    np.testing.assert_allclose(_np(cls_a), _np(cls_b), atol=3e-3)
+    np.testing.assert_allclose(_np(side_a).sum(1), 1.0, atol=1e-5)
+
+
 @pytest.mark.parametrize("T,heads,d,mode", [(197, 12, 16, 0), (128, 12, 8, 1), (17, 2, 32, 0), (512, 3, 8, 1), (33, 2, 16, 1),
                                             (197, 3, 32, 0)])
 def test_narrow_head_attention_matches_the_fp32_kernel(agb, T, heads, d, mode):
